@@ -1,0 +1,23 @@
+"""Import alias: ``import b200face`` -> the package that lives in
+``facerecognition-multiarchitecture-pipeline_b200/`` (a directory name Python cannot import
+directly because of the hyphens).  This file only redirects ``__path__``."""
+import os as _os
+
+_PKG_DIR = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))),
+                         "facerecognition-multiarchitecture-pipeline_b200")
+__path__.append(_PKG_DIR)
+
+from ._lib import lib_path, load_library, LibraryMissingError  # noqa: E402,F401
+from .head import (  # noqa: E402,F401
+    ArcMarginProduct, ArcFaceNet, arcface_loss, head_schedule, HeadStats,
+)
+from .gallery import (  # noqa: E402,F401
+    compare_faces, gallery_topk, cosine_class_match, GalleryIndex,
+)
+from . import parallel  # noqa: E402,F401
+
+__all__ = [
+    "ArcMarginProduct", "ArcFaceNet", "arcface_loss", "head_schedule", "HeadStats",
+    "compare_faces", "gallery_topk", "cosine_class_match", "GalleryIndex",
+    "parallel", "lib_path", "load_library", "LibraryMissingError",
+]

@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path of BASELINE.json on B200: fused ArcFace head (fwd+bwd) samples/s, with
+the gallery-match queries/s beside it.  Prints ONE JSON line (rank 0).
+
+    python bench.py --gpus 1 --steps K --warmup W                 # cfg3: 512-d x 100k classes, batch 512, bf16
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+                                                                  # cfg4: 1M classes class-sharded, batch 4096
+    python bench.py --impl reference ...                          # CPU arm: the reference algorithm (torch port)
+
+A "step" = one fused head forward+backward (K1 x2, K2, loss, hook scalar, K3, normalise-backward) on one
+synthetic batch.  `value` times the steps with x / labels already in HBM; `e2e` times the same step
+through the public API (ArcMarginProduct.forward_loss + backward) with x and labels coming from pinned
+host memory every step and the loss read back every step.  Inputs (W bf16 102 MB + dW fp32 205 MB) exceed
+the 126 MB L2, so no explicit flush is needed between iterations (config.l2 = "inputs_exceed_l2").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CFG3 = dict(B=512, C=100_000, D=512)
+CFG4 = dict(B=4096, C=1_000_000, D=512)
+CFG2 = dict(Q=1000, N=10_000, D=512, k=1)
+STREAM = dict(Q=128, N=1_000_000, D=512, k=5)
+EPOCH = 10            # post-warm-up schedule state: m_eff = 0.45, s_eff = 6.72
+LS = 0.05
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gallery", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.lines, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.time(), ln.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [ln.split(",") for ts, ln in self.lines if t0 - 0.05 <= ts <= t1 + 0.15] or \
+               [ln.split(",") for _, ln in self.lines[-3:]]
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0])); smax.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if "Active" in v and "Not" not in v:
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def synth_head(B, C_local, D, rank_seed, dev, c_lo, C_total):
+    """SURVEY 8d recipe: x ~ N(0,1) -> bf16, W xavier_normal(gain sqrt2) -> bf16 compute copy,
+    y ~ U{0..C-1}; 12.5 % of the rows planted near their class centre so the margin is exercised."""
+    g = torch.Generator(device=dev).manual_seed(1234)
+    std = (2.0 ** 0.5) * (2.0 / (C_total + D)) ** 0.5
+    gw = torch.Generator(device=dev).manual_seed(4321 + rank_seed)
+    w = (torch.randn(C_local, D, generator=gw, device=dev) * std).to(torch.bfloat16)
+    x = torch.randn(B, D, generator=g, device=dev)
+    y = torch.randint(0, C_total, (B,), generator=g, device=dev)
+    if C_local == C_total:                        # single shard: plant rows near their own class centre
+        n = B // 8
+        x[:n] = 3.0 * w[y[:n]].float() + 0.3 * std * torch.randn(n, D, generator=g, device=dev)
+    return x.to(torch.bfloat16), w, y
+
+
+def engine_code(name):
+    from b200face import _lib
+    return {"auto": _lib.ENGINE_AUTO, "simt": _lib.ENGINE_SIMT, "tcgen05": _lib.ENGINE_TCGEN05}[name]
+
+
+def run_b200(args):
+    import b200face
+    from b200face import _lib, parallel
+    from b200face.head import HeadStats, arcface_loss, effective_margin_scale, head_schedule
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    group = None
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+        group = torch.distributed.group.WORLD
+    lib = b200face.load_library()
+    cfgw = CFG3 if world == 1 else CFG4
+    B, C_total, D = cfgw["B"], cfgw["C"], cfgw["D"]
+    c_lo, c_hi = parallel.shard_bounds(C_total, world, rank)
+    C_local = c_hi - c_lo
+    x, w, y = synth_head(B, C_local, D, rank, dev, c_lo, C_total)
+    w.requires_grad_(True)
+    mf, sf = head_schedule(EPOCH, 10, True, True, 0.0, 0.3)
+    m_eff, s_eff = effective_margin_scale(32.0, 0.5, mf, sf, True)
+    eng = engine_code(args.engine)
+
+    def step(xin, stats=None):
+        xin = xin.detach().requires_grad_(True)
+        w.grad = None
+        loss = arcface_loss(xin, w, y, m_eff=m_eff, s_eff=s_eff, label_smoothing=LS, class_offset=c_lo,
+                            num_classes_total=C_total, group=group, stats=stats, engine=eng)
+        loss.backward()
+        return loss
+
+    def sync_all():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(x)
+    # ---- timed region 1: inputs resident in HBM ------------------------------------------------
+    _lib.TIMERS.clear(); _lib.PROFILE = True
+    sync_all()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = lib.b200f_launch_count()
+    t_wall0 = time.time()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step(x)
+    e1.record()
+    sync_all()
+    t_wall1 = time.time()
+    launches = lib.b200f_launch_count() - l0
+    _lib.PROFILE = False
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+    ms_total = float(ms)
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    kern = {k: statistics.mean(a.elapsed_time(b) for a, b in v) for k, v in _lib.TIMERS.items() if v}
+    # ---- timed region 2: end to end through the public API, host buffers ------------------------
+    xh = x.cpu().pin_memory(); yh = y.cpu().pin_memory()
+    head = b200face.ArcMarginProduct(D, C_local) if world == 1 else None
+    if head is not None:
+        head = head.to(dev); head.update_epoch(EPOCH); head.train(); head.engine = eng
+        head.compute_dtype = torch.bfloat16
+        head.weight = torch.nn.Parameter(w.detach().clone())          # bf16 parameter: no per-step cast
+    def e2e_step():
+        xd = xh.to(dev, non_blocking=True); yd = yh.to(dev, non_blocking=True)
+        if head is not None:
+            head.zero_grad(set_to_none=True)
+            l = head.forward_loss(xd.requires_grad_(True), yd, LS)
+        else:
+            w.grad = None
+            l = arcface_loss(xd.requires_grad_(True), w, yd, m_eff=m_eff, s_eff=s_eff, label_smoothing=LS,
+                             class_offset=c_lo, num_classes_total=C_total, group=group, engine=eng)
+        l.backward()
+        return float(l.item())                                        # D2H read of the step's result
+    for _ in range(3):
+        e2e_step()
+    sync_all()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    sync_all()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(ms2, op=torch.distributed.ReduceOp.MAX)
+    e2e_val = B * args.steps / (float(ms2) * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+    pk = peaks()
+    value = B * args.steps / (ms_total * 1e-3)
+    flops_step = 6.0 * B * C_total * D
+    # dominant kernel = the fused forward GEMM+epilogue (K2): 2*B*C_local*D algorithmic FLOP per launch
+    k2_ms = kern.get("arcface_fwd")
+    roof = None
+    if k2_ms:
+        ach = 2.0 * B * C_local * D / (k2_ms * 1e-3) / 1e12
+        roof = {"kernel": "K2 arcface_fwd (cosine GEMM + margin + softmax-CE statistics)", "bound": "tensor",
+                "achieved": round(ach, 2), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                "frac": round(ach / pk["tf_sustained"], 4), "traffic": load_traffic("arcface_fwd"),
+                "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
+                "algorithmic_flop_per_launch": 2.0 * B * C_local * D, "avg_launch_ms": round(k2_ms, 4)}
+    out = {
+        "metric": "arcface_head_samples_per_sec", "value": round(value, 1), "unit": "samples/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True,
+        "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": ("cfg3: ArcFace head 512-d, 100k classes, batch 512 bf16 fwd+bwd, 1 B200" if world == 1 else
+                                f"cfg4: ArcFace partial-FC 512-d, 1M classes class-sharded over {world} B200 "
+                                f"({C_local} per rank), batch 4096, one all-reduce each way"),
+                   "B": B, "C_total": C_total, "C_per_rank": C_local, "D": D, "label_smoothing": LS,
+                   "m_eff": round(m_eff, 4), "s_eff": round(s_eff, 4), "engine": args.engine,
+                   "grads": "dx fp32, dW fp32", "l2": "inputs_exceed_l2 (W bf16 + dW fp32 = 3 x C x D x 2 B per rank)",
+                   "parallelism": "single GPU" if world == 1 else f"class-parallel x{world} (NCCL all-reduce [B,4] fwd, [B,D] bwd)"},
+        "algorithmic_tflops": round(flops_step * args.steps / (ms_total * 1e-3) / 1e12, 2),
+        "frac_of_bf16_peak": round(flops_step * args.steps / (ms_total * 1e-3) / 1e12 / (pk["tf_sustained"] * world), 4),
+        "e2e": {"value": round(e2e_val, 1), "unit": "samples/s", "h2d_bytes_per_step": int(xh.numel() * 2 + yh.numel() * 8),
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roof,
+        "kernel_ms": {k: round(v, 4) for k, v in kern.items()},
+        "loss": round(float(loss), 5),
+    }
+    if world == 1 and not args.no_gallery:
+        out["gallery"] = bench_gallery(dev, pk, eng)
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_head_baseline(CFG3)
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def load_traffic(kernel):
+    """dram bytes per launch of the named kernel from the committed ncu capture (profiles/), else null."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(kernel)
+    return None
+
+
+def bench_gallery(dev, pk, eng):
+    """Gallery match beside the head: cfg2 (1k x 10k, top-1 + threshold; latency-bound, 22 MB fits L2)
+    and the streaming regime (Q=128 vs 1M x 512 fp32: 2.05 GB per pass, HBM-bound)."""
+    import b200face
+    g = torch.Generator(device=dev).manual_seed(1234)
+    res = {}
+    for name, c in (("cfg2", CFG2), ("stream_q128_n1m", STREAM)):
+        G = torch.nn.functional.normalize(torch.randn(c["N"], c["D"], generator=g, device=dev), dim=1)
+        Q = torch.nn.functional.normalize(torch.randn(c["Q"], c["D"], generator=g, device=dev), dim=1)
+        h = c["Q"] // 2
+        src = torch.randint(0, c["N"], (h,), generator=g, device=dev)
+        tau = 0.5 + 2.0 * torch.rand(h, 1, generator=g, device=dev)
+        Q[:h] = torch.nn.functional.normalize(G[src] + tau / c["D"] ** 0.5 * torch.randn(h, c["D"], generator=g, device=dev), dim=1)
+        for _ in range(3):
+            b200face.gallery_topk(Q, G, c["k"], 1.0, "l2eps", engine=eng)
+        torch.cuda.synchronize()
+        reps = 10 if name == "cfg2" else 5
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            idx, score, acc = b200face.gallery_topk(Q, G, c["k"], 1.0, "l2eps", engine=eng)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        byt = c["N"] * c["D"] * 4 + c["Q"] * c["D"] * 4 + c["Q"] * c["k"] * 12
+        Qh = Q.cpu().pin_memory()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            i2, s2, a2 = b200face.gallery_topk(Qh.to(dev, non_blocking=True), G, c["k"], 1.0, "l2eps", engine=eng)
+            host = (i2.cpu(), s2.cpu(), a2.cpu())
+        e1.record(); torch.cuda.synchronize()
+        ms_e2e = e0.elapsed_time(e1) / reps
+        res[name] = {"queries_per_sec": round(c["Q"] / (ms * 1e-3), 1), "ms": round(ms, 4),
+                     "e2e_queries_per_sec": round(c["Q"] / (ms_e2e * 1e-3), 1),
+                     "accepted_frac": round(float(acc.float().mean()), 3),
+                     "algorithmic_GBps": round(byt / (ms * 1e-3) / 1e9, 1),
+                     "frac_of_hbm_peak": round(byt / (ms * 1e-3) / 1e9 / pk["hbm"], 4),
+                     "algorithmic_tflops": round(2.0 * c["Q"] * c["N"] * c["D"] / (ms * 1e-3) / 1e12, 2)}
+        del G, Q
+    return res
+
+
+def cpu_head_baseline(c, budget_s=20.0):
+    """The reference algorithm on this box's host cores (oracle/torch_port.py, kind 'port': the
+    reference is pure Python and is not on the GPU box).  Bounded: full cfg3 steps until ~budget_s."""
+    from oracle import torch_port
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(1234)
+    head = torch_port.HeadPort(c["D"], c["C"])
+    head.current_epoch = EPOCH
+    head.train()
+    x = torch.randn(c["B"], c["D"], generator=g)
+    y = torch.randint(0, c["C"], (c["B"],), generator=g)
+    torch_port.head_step(head, x, y, LS)                     # warm-up
+    t0 = time.time(); n = 0
+    while True:
+        torch_port.head_step(head, x, y, LS); n += 1
+        if time.time() - t0 > budget_s or n >= 10:
+            break
+    dt = (time.time() - t0) / n
+    return {"value": round(c["B"] / dt, 1), "unit": "samples/s", "cores": threads, "kind": "port",
+            "sample": f"{n} full cfg3 head steps (B={c['B']}, C={c['C']}, fp32 torch CPU, fwd+bwd), {dt:.2f} s each"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (torch port of
+    src/face_models.py:334-429 + CrossEntropyLoss + autograd), all host threads, cfg3."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import torch_port
+    c = CFG3
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(1234)
+    head = torch_port.HeadPort(c["D"], c["C"])
+    head.current_epoch = EPOCH
+    head.train()
+    x = torch.randn(c["B"], c["D"], generator=g)
+    y = torch.randint(0, c["C"], (c["B"],), generator=g)
+    # bounded: the whole run must end within a few minutes whatever K is asked
+    t0 = time.time(); torch_port.head_step(head, x, y, LS); probe = time.time() - t0
+    steps = max(1, min(args.steps, int(150.0 / max(probe, 1e-3))))
+    warm = max(0, min(args.warmup, int(30.0 / max(probe, 1e-3)) ))
+    for _ in range(warm):
+        torch_port.head_step(head, x, y, LS)
+    t0 = time.time()
+    for _ in range(steps):
+        loss, _, _ = torch_port.head_step(head, x, y, LS)
+    dt = time.time() - t0
+    val = c["B"] * steps / dt
+    sample = f"{steps} full cfg3 head steps (B={c['B']}, C={c['C']}, fp32, fwd+bwd) of the reference algorithm on CPU"
+    print(json.dumps({
+        "impl": "reference", "metric": "arcface_head_samples_per_sec", "value": round(val, 1), "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm + 1, "ms_per_step": round(dt / steps * 1e3, 2),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg3: ArcFace head 512-d, 100k classes, batch 512 fwd+bwd (reference CPU path)",
+                   "B": c["B"], "C_total": c["C"], "D": c["D"], "label_smoothing": LS},
+        "cpu_baseline": {"value": round(val, 1), "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": round(val, 1), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "loss": round(float(loss), 5)}), flush=True)
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -1,0 +1,212 @@
+// C ABI, part 2: the ArcFace head (K2 forward statistics, K3 backward): argument checking, workspace
+// carving and engine dispatch.  No allocation, no synchronisation.  Declared in include/b200face.h.
+#include "common.cuh"
+#include "head_simt.cuh"
+#include "umma_api.cuh"
+
+namespace b200f {
+
+static inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
+static inline bool dtype_ok(int dt) { return dt == B200F_F32 || dt == B200F_BF16; }
+static inline size_t elem_size(int dt) { return dt == B200F_F32 ? 4 : 2; }
+
+// ---- head workspace plan (shared by the size query and the calls) -------------------------
+struct HeadPlan {
+  // forward
+  int n_chunks, tiles_per_chunk, m_tiles;
+  size_t off_part, off_cos;
+  // backward
+  int64_t Cc, ldg;
+  int n_splits; int64_t k_per_split;
+  size_t off_G, off_r, off_dxpart;
+  size_t total;
+};
+
+static HeadPlan plan_head(int64_t B, int64_t C, int D) {
+  HeadPlan pl{};
+  const int sms = num_sms();
+  pl.m_tiles = (int)ceil_div(B, simt::BM);
+  const int64_t n_tiles = ceil_div(C, simt::BN);
+  int64_t want_chunks = ceil_div((int64_t)4 * sms, pl.m_tiles);
+  if (want_chunks > n_tiles) want_chunks = n_tiles;
+  if (want_chunks < 1) want_chunks = 1;
+  pl.tiles_per_chunk = (int)ceil_div(n_tiles, want_chunks);
+  pl.n_chunks = (int)ceil_div(n_tiles, pl.tiles_per_chunk);
+  size_t off = 0;
+  pl.off_part = off; off += align_up(sizeof(float) * pl.n_chunks * B * head_simt::PART_COLS, 256);
+  pl.off_cos = off;  off += align_up(sizeof(float) * 2 * (size_t)pl.n_chunks * pl.m_tiles, 256);
+  const size_t fwd_total = off;
+  // backward: G chunk of at most 64 MB fp32
+  const int64_t c_round = ceil_div(C, simt::BN) * simt::BN;
+  int64_t cc = ((int64_t)(64u << 20) / 4 / B) / simt::BN * simt::BN;
+  if (cc < simt::BN) cc = simt::BN;
+  if (cc > c_round) cc = c_round;
+  pl.Cc = cc; pl.ldg = cc;
+  const int64_t d_tiles = ceil_div(D, simt::BN);
+  int64_t splits = ceil_div((int64_t)2 * sms, pl.m_tiles * d_tiles);
+  const int64_t max_splits = cc / simt::BN;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  pl.k_per_split = ceil_div(cc / simt::BN, splits) * simt::BN;
+  pl.n_splits = (int)ceil_div(cc, pl.k_per_split);
+  off = 0;
+  pl.off_G = off;      off += align_up(sizeof(float) * (size_t)B * pl.ldg, 256);
+  pl.off_r = off;      off += align_up(sizeof(float) * (size_t)cc, 256);
+  pl.off_dxpart = off; off += align_up(sizeof(float) * (size_t)pl.n_splits * B * D, 256);
+  pl.total = off > fwd_total ? off : fwd_total;
+  return pl;
+}
+
+template <typename T>
+static int head_fwd_simt(const void* x, const void* w, const float* inv_nx, const float* inv_nw,
+                         const int64_t* label, int64_t B, int64_t C, int64_t class_offset, int D,
+                         const b200f_head_cfg* cfg, float* row_stats, float* row_best,
+                         int64_t* row_argmax, float* cos_minmax, int32_t* nan_flag, float* logits,
+                         int64_t ld_logits, char* ws, const HeadPlan& pl, cudaStream_t st) {
+  head_simt::FwdParams p{};
+  p.x = x; p.w = w; p.inv_nx = inv_nx; p.inv_nw = inv_nw; p.label = label;
+  p.B = B; p.C = C; p.class_offset = class_offset; p.D = D;
+  p.hm = HeadMath{cfg->m_eff, cfg->s_eff, cfg->easy_margin};
+  p.n_chunks = pl.n_chunks; p.tiles_per_chunk = pl.tiles_per_chunk;
+  p.part = reinterpret_cast<float*>(ws + pl.off_part);
+  p.cos_part = reinterpret_cast<float*>(ws + pl.off_cos);
+  p.nan_flag = nan_flag; p.logits = logits; p.ld_logits = ld_logits;
+  p.vec_x = simt::vec_friendly<T>(x, D); p.vec_w = simt::vec_friendly<T>(w, D);
+  dim3 grid(pl.n_chunks, pl.m_tiles);
+  head_simt::fwd_kernel<T><<<grid, simt::THREADS, 0, st>>>(p);
+  B200F_LAUNCH_OK("head_simt::fwd_kernel");
+  head_simt::reduce_partials_kernel<<<(unsigned)ceil_div(B, 256), 256, 0, st>>>(
+      p.part, pl.n_chunks, B, p.cos_part, pl.n_chunks * pl.m_tiles, row_stats, row_best, row_argmax,
+      cos_minmax);
+  B200F_LAUNCH_OK("head_simt::reduce_partials_kernel");
+  return B200F_OK;
+}
+
+template <typename T>
+static int head_bwd_simt(const void* x, const void* w, const float* inv_nx, const float* inv_nw,
+                         const int64_t* label, const float* lse, const float* grad_scale,
+                         const float* dlogits, int64_t ld_dlogits, int64_t B,
+                         int64_t C, int64_t class_offset, int D, const b200f_head_cfg* cfg,
+                         float* dxhat, float* dw, char* ws, const HeadPlan& pl, cudaStream_t st) {
+  float* G = reinterpret_cast<float*>(ws + pl.off_G);
+  float* r = reinterpret_cast<float*>(ws + pl.off_r);
+  float* dxpart = reinterpret_cast<float*>(ws + pl.off_dxpart);
+  const bool vx = simt::vec_friendly<T>(x, D), vw = simt::vec_friendly<T>(w, D);
+  const int64_t d_tiles = ceil_div(D, simt::BN);
+  int chunk_no = 0;
+  for (int64_t c0 = 0; c0 < C; c0 += pl.Cc, ++chunk_no) {
+    const int64_t c_cnt = (C - c0 < pl.Cc) ? (C - c0) : pl.Cc;
+    head_simt::BwdGParams g{};
+    g.x = x; g.w = w; g.inv_nx = inv_nx; g.inv_nw = inv_nw; g.label = label; g.lse = lse;
+    g.grad_scale = grad_scale; g.B = B; g.C = C; g.class_offset = class_offset; g.c0 = c0; g.Cc = pl.Cc;
+    g.D = D; g.hm = HeadMath{cfg->m_eff, cfg->s_eff, cfg->easy_margin};
+    g.ls_eps = cfg->label_smoothing; g.inv_Ctot = 1.0f / (float)cfg->num_classes_total;
+    g.G = G; g.ldg = pl.ldg; g.r = r; g.vec_x = vx; g.vec_w = vw;
+    g.dlogits = dlogits; g.ld_dlogits = ld_dlogits;
+    head_simt::bwd_g_kernel<T><<<(unsigned)ceil_div(c_cnt, simt::BN), simt::THREADS, 0, st>>>(g);
+    B200F_LAUNCH_OK("head_simt::bwd_g_kernel");
+
+    head_simt::BwdDwParams dwp{};
+    dwp.x = x; dwp.w = w; dwp.inv_nx = inv_nx; dwp.inv_nw = inv_nw; dwp.G = G; dwp.ldg = pl.ldg; dwp.r = r;
+    dwp.B = B; dwp.C = C; dwp.c0 = c0; dwp.Cc = pl.Cc; dwp.D = D; dwp.dw = dw; dwp.vec_x = vx;
+    dim3 gdw((unsigned)ceil_div(c_cnt, simt::BM), (unsigned)d_tiles);
+    head_simt::bwd_dw_kernel<T><<<gdw, simt::THREADS, 0, st>>>(dwp);
+    B200F_LAUNCH_OK("head_simt::bwd_dw_kernel");
+
+    head_simt::BwdDxParams dxp{};
+    dxp.w = w; dxp.inv_nw = inv_nw; dxp.G = G; dxp.ldg = pl.ldg; dxp.B = B; dxp.C = C; dxp.c0 = c0;
+    dxp.Cc = pl.Cc; dxp.D = D; dxp.k_per_split = pl.k_per_split; dxp.part = dxpart; dxp.vec_w = vw;
+    const int splits = (int)ceil_div(c_cnt, pl.k_per_split);
+    dim3 gdx(pl.m_tiles, (unsigned)d_tiles, splits);
+    head_simt::bwd_dx_kernel<T><<<gdx, simt::THREADS, 0, st>>>(dxp);
+    B200F_LAUNCH_OK("head_simt::bwd_dx_kernel");
+    const int64_t n = B * D;
+    head_simt::reduce_splits_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(dxpart, splits, n, dxhat,
+                                                                               chunk_no > 0);
+    B200F_LAUNCH_OK("head_simt::reduce_splits_kernel");
+  }
+  return B200F_OK;
+}
+
+}  // namespace b200f
+
+using namespace b200f;
+
+extern "C" {
+
+size_t b200f_head_workspace_bytes(int64_t B, int64_t C_local, int D, int dtype, int engine) {
+  if (B <= 0 || C_local <= 0 || D <= 0) return 0;
+  size_t simt_bytes = plan_head(B, C_local, D).total;
+  size_t umma_bytes = umma::head_workspace_bytes(B, C_local, D, dtype, engine);
+  return simt_bytes > umma_bytes ? simt_bytes : umma_bytes;
+}
+
+static int check_head_args(const char* who, const void* x, const void* w, int dtype, const float* inv_nx,
+                           const float* inv_nw, const int64_t* label, int64_t B, int64_t C, int D,
+                           const b200f_head_cfg* cfg) {
+  if (!dtype_ok(dtype)) return fail(B200F_ERR_ARG, "%s: bad dtype %d", who, dtype);
+  if (B <= 0 || C <= 0 || D <= 0) return fail(B200F_ERR_ARG, "%s: bad shape B=%lld C=%lld D=%d", who, (long long)B, (long long)C, D);
+  if (!x || !w || !inv_nx || !inv_nw || !label || !cfg) return fail(B200F_ERR_ARG, "%s: null pointer", who);
+  if (cfg->num_classes_total < C) return fail(B200F_ERR_ARG, "%s: num_classes_total < C_local", who);
+  if (cfg->num_classes_total >= (int64_t)1 << 31) return fail(B200F_ERR_ARG, "%s: more than 2^31 classes", who);
+  return B200F_OK;
+}
+
+int b200f_arcface_fwd(const void* x, const void* w, int dtype, const float* inv_nx, const float* inv_nw,
+                      const int64_t* label, int64_t B, int64_t C_local, int64_t class_offset, int D,
+                      const b200f_head_cfg* cfg, float* row_stats, float* row_best, int64_t* row_argmax,
+                      float* cos_minmax, int32_t* nan_flag, float* logits_or_null, int64_t ld_logits,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_head_args("arcface_fwd", x, w, dtype, inv_nx, inv_nw, label, B, C_local, D, cfg);
+  if (rc) return rc;
+  if (!row_stats || !nan_flag) return fail(B200F_ERR_ARG, "arcface_fwd: null output");
+  if (logits_or_null && ld_logits < C_local) return fail(B200F_ERR_ARG, "arcface_fwd: ld_logits < C_local");
+  const size_t need = b200f_head_workspace_bytes(B, C_local, D, dtype, cfg->engine);
+  if (!workspace || workspace_bytes < need)
+    return fail(B200F_ERR_WORKSPACE, "arcface_fwd: workspace %zu < %zu", workspace_bytes, need);
+  cudaStream_t st = as_stream(stream);
+  if (umma::head_engine_selected(B, C_local, D, dtype, cfg->engine, logits_or_null != nullptr)) {
+    return umma::head_fwd(x, w, inv_nx, inv_nw, label, B, C_local, class_offset, D, cfg, row_stats, row_best,
+                          row_argmax, cos_minmax, nan_flag, static_cast<char*>(workspace), workspace_bytes, st);
+  }
+  if (cfg->engine == B200F_ENGINE_TCGEN05)
+    return fail(B200F_ERR_UNSUPPORTED, "arcface_fwd: tcgen05 engine does not take this call (dtype/shape/logits)");
+  const HeadPlan pl = plan_head(B, C_local, D);
+  if (dtype == B200F_F32)
+    return head_fwd_simt<float>(x, w, inv_nx, inv_nw, label, B, C_local, class_offset, D, cfg, row_stats, row_best,
+                                row_argmax, cos_minmax, nan_flag, logits_or_null, ld_logits,
+                                static_cast<char*>(workspace), pl, st);
+  return head_fwd_simt<__nv_bfloat16>(x, w, inv_nx, inv_nw, label, B, C_local, class_offset, D, cfg, row_stats,
+                                      row_best, row_argmax, cos_minmax, nan_flag, logits_or_null, ld_logits,
+                                      static_cast<char*>(workspace), pl, st);
+}
+
+int b200f_arcface_bwd(const void* x, const void* w, int dtype, const float* inv_nx, const float* inv_nw,
+                      const int64_t* label, const float* lse, const float* grad_scale,
+                      const float* dlogits_or_null, int64_t ld_dlogits, int64_t B,
+                      int64_t C_local, int64_t class_offset, int D, const b200f_head_cfg* cfg, float* dxhat,
+                      float* dw, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_head_args("arcface_bwd", x, w, dtype, inv_nx, inv_nw, label, B, C_local, D, cfg);
+  if (rc) return rc;
+  if (!lse || !grad_scale || !dxhat || !dw) return fail(B200F_ERR_ARG, "arcface_bwd: null pointer");
+  const size_t need = b200f_head_workspace_bytes(B, C_local, D, dtype, cfg->engine);
+  if (!workspace || workspace_bytes < need)
+    return fail(B200F_ERR_WORKSPACE, "arcface_bwd: workspace %zu < %zu", workspace_bytes, need);
+  cudaStream_t st = as_stream(stream);
+  if (dlogits_or_null && ld_dlogits < C_local) return fail(B200F_ERR_ARG, "arcface_bwd: ld_dlogits < C_local");
+  if (umma::head_engine_selected(B, C_local, D, dtype, cfg->engine, dlogits_or_null != nullptr)) {
+    return umma::head_bwd(x, w, inv_nx, inv_nw, label, lse, grad_scale, B, C_local, class_offset, D, cfg, dxhat,
+                          dw, static_cast<char*>(workspace), workspace_bytes, st);
+  }
+  if (cfg->engine == B200F_ENGINE_TCGEN05)
+    return fail(B200F_ERR_UNSUPPORTED, "arcface_bwd: tcgen05 engine does not take this call (dtype/shape)");
+  const HeadPlan pl = plan_head(B, C_local, D);
+  if (dtype == B200F_F32)
+    return head_bwd_simt<float>(x, w, inv_nx, inv_nw, label, lse, grad_scale, dlogits_or_null, ld_dlogits, B,
+                                C_local, class_offset, D, cfg, dxhat, dw, static_cast<char*>(workspace), pl, st);
+  return head_bwd_simt<__nv_bfloat16>(x, w, inv_nx, inv_nw, label, lse, grad_scale, dlogits_or_null, ld_dlogits,
+                                      B, C_local, class_offset, D, cfg, dxhat, dw,
+                                      static_cast<char*>(workspace), pl, st);
+}
+
+}  // extern "C"

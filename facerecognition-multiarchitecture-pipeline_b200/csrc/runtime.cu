@@ -1,0 +1,132 @@
+// C ABI, part 1: runtime (errors, version) and the HBM-bound row kernels (K1, normalise-backward,
+// loss finalize, hook scalar).  Declared in include/b200face.h.
+#include <stdarg.h>
+#include <atomic>
+
+#include "common.cuh"
+#include "rowops.cuh"
+
+namespace b200f {
+
+std::string& last_error_ref() {
+  static thread_local std::string err;
+  return err;
+}
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  last_error_ref() = buf;
+  return code;
+}
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+unsigned long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+int num_sms() {
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != cached_dev) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 148;
+    cached = prop.multiProcessorCount;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+static inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
+static inline bool dtype_ok(int dt) { return dt == B200F_F32 || dt == B200F_BF16; }
+static inline size_t elem_size(int dt) { return dt == B200F_F32 ? 4 : 2; }
+
+}  // namespace b200f
+
+using namespace b200f;
+
+extern "C" {
+
+int b200f_version(void) { return 100; }
+
+unsigned long long b200f_launch_count(void) { return launch_count(); }
+
+const char* b200f_last_error(void) { return last_error_ref().c_str(); }
+
+int b200f_has_tcgen05(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 0;
+  return (prop.major == 10) ? 1 : 0;
+}
+
+int b200f_l2norm_rows(const void* in, int in_dtype, int64_t rows, int dim, float eps, float* inv_norm,
+                      void* out_or_null, int out_dtype, void* stream) {
+  if (!dtype_ok(in_dtype) || (out_or_null && !dtype_ok(out_dtype)))
+    return fail(B200F_ERR_ARG, "l2norm_rows: bad dtype");
+  if (rows < 0 || dim <= 0) return fail(B200F_ERR_ARG, "l2norm_rows: bad shape rows=%lld dim=%d", (long long)rows, dim);
+  if (rows == 0) return B200F_OK;
+  if (!in || (!inv_norm && !out_or_null)) return fail(B200F_ERR_ARG, "l2norm_rows: null pointer");
+  const unsigned grid = (unsigned)ceil_div(rows, rowops::ROWS_PER_BLOCK);
+  const int threads = rowops::ROWS_PER_BLOCK * 32;
+  cudaStream_t st = as_stream(stream);
+  const int per_in = 16 / (int)elem_size(in_dtype);
+  bool vec = (dim % per_in == 0) && (reinterpret_cast<uintptr_t>(in) % 16 == 0);
+  if (out_or_null) vec = vec && (reinterpret_cast<uintptr_t>(out_or_null) % 16 == 0);
+#define L2N_LAUNCH(TI, TO, V)                                                                      \
+  rowops::l2norm_rows_kernel<TI, TO, V><<<grid, threads, 0, st>>>(                                  \
+      static_cast<const TI*>(in), rows, dim, eps, inv_norm, static_cast<TO*>(out_or_null))
+#define L2N_DISPATCH(TI, TO) do { if (vec) L2N_LAUNCH(TI, TO, true); else L2N_LAUNCH(TI, TO, false); } while (0)
+  const int od = out_or_null ? out_dtype : B200F_F32;
+  if (in_dtype == B200F_F32 && od == B200F_F32) L2N_DISPATCH(float, float);
+  else if (in_dtype == B200F_F32) L2N_DISPATCH(float, __nv_bfloat16);
+  else if (od == B200F_F32) L2N_DISPATCH(__nv_bfloat16, float);
+  else L2N_DISPATCH(__nv_bfloat16, __nv_bfloat16);
+#undef L2N_DISPATCH
+#undef L2N_LAUNCH
+  B200F_LAUNCH_OK("l2norm_rows_kernel");
+  return B200F_OK;
+}
+
+int b200f_l2norm_bwd(const void* v, int dtype, const float* inv_norm, const float* dvhat, int64_t rows,
+                     int dim, float* dv, void* stream) {
+  if (!dtype_ok(dtype)) return fail(B200F_ERR_ARG, "l2norm_bwd: bad dtype");
+  if (rows < 0 || dim <= 0) return fail(B200F_ERR_ARG, "l2norm_bwd: bad shape");
+  if (rows == 0) return B200F_OK;
+  if (!v || !inv_norm || !dvhat || !dv) return fail(B200F_ERR_ARG, "l2norm_bwd: null pointer");
+  const unsigned grid = (unsigned)ceil_div(rows, rowops::ROWS_PER_BLOCK);
+  const int threads = rowops::ROWS_PER_BLOCK * 32;
+  if (dtype == B200F_F32)
+    rowops::l2norm_bwd_kernel<float><<<grid, threads, 0, as_stream(stream)>>>(
+        static_cast<const float*>(v), inv_norm, dvhat, rows, dim, dv);
+  else
+    rowops::l2norm_bwd_kernel<__nv_bfloat16><<<grid, threads, 0, as_stream(stream)>>>(
+        static_cast<const __nv_bfloat16*>(v), inv_norm, dvhat, rows, dim, dv);
+  B200F_LAUNCH_OK("l2norm_bwd_kernel");
+  return B200F_OK;
+}
+
+int b200f_arcface_loss(const float* row_stats, int64_t B, const b200f_head_cfg* cfg, float* lse, float* loss,
+                       float* pq_norm2, void* stream) {
+  if (!row_stats || !cfg || B <= 0) return fail(B200F_ERR_ARG, "arcface_loss: bad argument");
+  rowops::loss_kernel<<<1, 1024, 0, as_stream(stream)>>>(row_stats, B, cfg->s_eff, cfg->label_smoothing,
+                                                         (double)cfg->num_classes_total, lse, loss, pq_norm2);
+  B200F_LAUNCH_OK("loss_kernel");
+  return B200F_OK;
+}
+
+int b200f_arcface_hook_scale(const float* pq_norm2, const float* upstream, int64_t B, float s_eff,
+                             int hook_enabled, float max_grad_norm, int phase, int epoch, float* out3,
+                             void* stream) {
+  if (!pq_norm2 || !out3 || B <= 0) return fail(B200F_ERR_ARG, "arcface_hook_scale: bad argument");
+  rowops::hook_scale_kernel<<<1, 1, 0, as_stream(stream)>>>(pq_norm2, upstream, (double)B, s_eff, hook_enabled,
+                                                            max_grad_norm, phase, epoch, out3);
+  B200F_LAUNCH_OK("hook_scale_kernel");
+  return B200F_OK;
+}
+
+}  // extern "C"

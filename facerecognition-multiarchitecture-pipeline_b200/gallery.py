@@ -1,0 +1,184 @@
+"""Host side of the gallery match over libb200face.so (kernel K4).
+
+Reference surface mirrored here:
+  compare_faces(emb, refs, thresh) -> (name, dist, idx)      /root/reference/src/app.py:50-64
+  cosine class-centre match (normalize @ normalize.T * s, max(1))
+      /root/reference/src/hyperparameter_tuning.py:1039-1046,1076 ; src/face_models.py:891-893
+Batched entry: gallery_topk(Q, G, k, thresh, metric).  GalleryIndex keeps the gallery resident on the
+GPU so the Streamlit loop (src/app.py:631-639) does not re-upload it every frame.
+
+No CPU path: the kernels run on CUDA or the call raises."""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import check, dtype_code, ptr, require_cuda, stream_ptr
+
+_METRICS = {"l2eps": _lib.METRIC_L2EPS, "cos": _lib.METRIC_COS}
+MAX_K = 16
+
+
+def _default_device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("b200face gallery match needs a CUDA device (no CPU fallback)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _inv_norm(t: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load_library()
+    inv = torch.empty(t.shape[0], dtype=torch.float32, device=t.device)
+    if t.shape[0]:
+        check(lib.b200f_l2norm_rows(ptr(t), dtype_code(t), t.shape[0], t.shape[1], 1e-12, ptr(inv), None, 0,
+                                    stream_ptr(t.device)), "b200f_l2norm_rows")
+    return inv
+
+
+def gallery_topk(q: torch.Tensor, g: torch.Tensor, k: int = 1, thresh: float = 1.0, metric: str = "l2eps",
+                 *, index_offset: int = 0, g_inv: Optional[torch.Tensor] = None,
+                 engine: int = _lib.ENGINE_AUTO) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Per query the k best gallery rows.  q [Q,D], g [N,D] CUDA, same dtype (fp32 / bf16).
+    metric 'l2eps': score = ||q - g + 1e-6||_2 ascending, accept = best <= thresh  (app.py:59-64)
+    metric 'cos'  : score = cosine of the row-normalised vectors, descending, accept = best >= thresh
+    Returns (idx [Q,k] int64 global row ids, -1 = no such neighbour; score [Q,k] fp32; accept [Q] bool).
+    Ties go to the lowest index (strict '<', app.py:60)."""
+    if metric not in _METRICS:
+        raise ValueError(f"metric must be one of {list(_METRICS)}")
+    if not 1 <= k <= MAX_K:
+        raise ValueError(f"k must be in [1, {MAX_K}]")
+    require_cuda(q, g)
+    if q.dtype != g.dtype:
+        raise TypeError("queries and gallery must share a dtype")
+    q = q.contiguous()
+    g = g.contiguous()
+    Q, D = q.shape
+    N = g.shape[0]
+    if N and g.shape[1] != D:
+        raise ValueError("dimension mismatch between queries and gallery")
+    lib = _lib.load_library()
+    dev = q.device
+    idx = torch.empty(Q, k, dtype=torch.int64, device=dev)
+    score = torch.empty(Q, k, dtype=torch.float32, device=dev)
+    accept = torch.empty(Q, dtype=torch.uint8, device=dev)
+    q_inv = gi = None
+    if metric == "cos":
+        q_inv = _inv_norm(q)
+        gi = g_inv if g_inv is not None else _inv_norm(g)
+    nbytes = lib.b200f_gallery_workspace_bytes(Q, N, D, k, dtype_code(q), engine)
+    ws = _lib.workspace(nbytes, dev, "gallery")
+    check(lib.b200f_gallery_topk(ptr(q), ptr(g), dtype_code(q), ptr(q_inv), ptr(gi), Q, N, int(index_offset), D,
+                                 k, _METRICS[metric], float(thresh), engine, ptr(idx), ptr(score), ptr(accept),
+                                 ptr(ws), ws.numel(), stream_ptr(dev)), "b200f_gallery_topk")
+    return idx, score, accept.bool()
+
+
+def merge_topk(idx_all: torch.Tensor, score_all: torch.Tensor, thresh: float, metric: str):
+    """Merge P per-shard lists [P,Q,k] (global ids) into the global top-k (lowest id wins ties)."""
+    require_cuda(idx_all, score_all)
+    lib = _lib.load_library()
+    P, Q, k = idx_all.shape
+    dev = idx_all.device
+    idx = torch.empty(Q, k, dtype=torch.int64, device=dev)
+    score = torch.empty(Q, k, dtype=torch.float32, device=dev)
+    accept = torch.empty(Q, dtype=torch.uint8, device=dev)
+    check(lib.b200f_gallery_merge(ptr(idx_all.contiguous()), ptr(score_all.contiguous()), P, Q, k,
+                                  _METRICS[metric], float(thresh), ptr(idx), ptr(score), ptr(accept),
+                                  stream_ptr(dev)), "b200f_gallery_merge")
+    return idx, score, accept.bool()
+
+
+def compare_faces(emb, refs, thresh):
+    """Drop-in for src/app.py:50-64.  emb: Tensor [1,D] (any device) or None; refs: list of dicts with
+    'name' and 'embedding' (Tensor [1,D]); returns (name, min_dist, index) or ("Unknown", d, None)."""
+    if emb is None or not refs:
+        return "Unknown", float('inf'), None
+    dev = emb.device if emb.is_cuda else _default_device()
+    q = emb.reshape(1, -1).to(device=dev, dtype=torch.float32)
+    g = torch.cat([r['embedding'].reshape(1, -1) for r in refs], dim=0).to(device=dev, dtype=torch.float32)
+    idx, score, accept = gallery_topk(q, g, 1, thresh, "l2eps")
+    i, d, ok = int(idx[0, 0].item()), float(score[0, 0].item()), bool(accept[0].item())
+    if i < 0:
+        return "Unknown", float('inf'), None
+    return (refs[i]['name'], d, i) if ok else ("Unknown", d, None)
+
+
+def cosine_class_match(emb: torch.Tensor, weight: torch.Tensor, s: float = 1.0):
+    """pred = (normalize(emb) @ normalize(weight).T * s).max(1)   (hyperparameter_tuning.py:1039-1046,1076)
+    without the [B,C] matrix: K4 with k=1, metric=cos, gallery = class centres.
+    Returns (pred [B] int64, best_logit [B] fp32)."""
+    idx, score, _ = gallery_topk(emb.to(weight.dtype) if emb.dtype != weight.dtype else emb, weight, 1,
+                                 -2.0, "cos")
+    return idx[:, 0], score[:, 0] * s
+
+
+class GalleryIndex:
+    """Device-resident reference store for the recognition loop (src/app.py: refs list,
+    add/rename/delete at :428-433,477-513; pickle format of save_refs/load_refs :67-123)."""
+
+    def __init__(self, dim: int = 512, device=None, dtype=torch.float32, capacity: int = 1024):
+        self.device = torch.device(device) if device is not None else _default_device()
+        self.dim, self.dtype = dim, dtype
+        self.names: List[str] = []
+        self._buf = torch.empty(capacity, dim, dtype=dtype, device=self.device)
+
+    def __len__(self):
+        return len(self.names)
+
+    @property
+    def embeddings(self) -> torch.Tensor:
+        return self._buf[:len(self.names)]
+
+    def add(self, name: str, embedding: torch.Tensor) -> int:
+        n = len(self.names)
+        if n == self._buf.shape[0]:
+            grown = torch.empty(2 * n, self.dim, dtype=self.dtype, device=self.device)
+            grown[:n] = self._buf
+            self._buf = grown
+        self._buf[n] = embedding.reshape(-1).to(device=self.device, dtype=self.dtype)
+        self.names.append(name)
+        return n
+
+    def rename(self, index: int, name: str):
+        self.names[index] = name
+
+    def delete(self, index: int):
+        n = len(self.names)
+        if index < n - 1:
+            self._buf[index:n - 1] = self._buf[index + 1:n].clone()
+        del self.names[index]
+
+    @classmethod
+    def from_refs(cls, refs: Sequence[dict], device=None, dtype=torch.float32):
+        dim = refs[0]['embedding'].numel() if refs else 512
+        gi = cls(dim, device, dtype, capacity=max(16, len(refs)))
+        for r in refs:
+            gi.add(r['name'], r['embedding'])
+        return gi
+
+    @classmethod
+    def from_saved(cls, saved: Sequence[dict], device=None, dtype=torch.float32):
+        """From the unpickled list save_refs writes ({'name','embedding_numpy','image_path'}, app.py:82-86)."""
+        refs = [{'name': r['name'], 'embedding': torch.as_tensor(r['embedding_numpy'])} for r in saved]
+        return cls.from_refs(refs, device, dtype)
+
+    def to_saved(self, image_paths: Optional[Sequence[str]] = None) -> List[dict]:
+        emb = self.embeddings.float().cpu().numpy()
+        return [{'name': n, 'embedding_numpy': emb[i:i + 1].copy(),
+                 'image_path': image_paths[i] if image_paths else None} for i, n in enumerate(self.names)]
+
+    def match(self, emb: torch.Tensor, thresh: float = 1.0, k: int = 1, metric: str = "l2eps"):
+        """Batched compare_faces: emb [Q,D].  Returns (idx, score, accept) device tensors."""
+        q = emb.reshape(-1, self.dim).to(device=self.device, dtype=self.dtype)
+        return gallery_topk(q, self.embeddings, k, thresh, metric)
+
+    def compare_faces(self, emb: Optional[torch.Tensor], thresh: float):
+        """compare_faces(emb, refs, thresh) against the resident gallery."""
+        if emb is None or not self.names:
+            return "Unknown", float('inf'), None
+        idx, score, accept = self.match(emb, thresh, 1)
+        i, d, ok = int(idx[0, 0].item()), float(score[0, 0].item()), bool(accept[0].item())
+        if i < 0:
+            return "Unknown", float('inf'), None
+        return (self.names[i], d, i) if ok else ("Unknown", d, None)

@@ -1,0 +1,477 @@
+"""Host side of the ArcFace head: drop-in mirrors of the reference modules over libb200face.so.
+
+Reference surface mirrored here (same names, arguments, attributes, state_dict keys, errors):
+  ArcMarginProduct  /root/reference/src/face_models.py:297-445
+  ArcFaceNet        /root/reference/src/face_models.py:447-613   (trunk = torchvision, unchanged)
+  criterion         nn.CrossEntropyLoss(label_smoothing=eps)     src/training.py:341,515
+
+New, fused entry: ``ArcMarginProduct.forward_loss(input, label, label_smoothing)`` /
+``ArcFaceNet.forward_loss(x, labels, label_smoothing)`` -- loss directly, the B x C logits are never
+written (kernels K1-K3, include/b200face.h).  ``forward(input, label) -> logits`` is kept for
+callers that need the logits (small C); it runs the same kernels with the logits store enabled.
+
+No CPU path: every call needs CUDA tensors and the built library, otherwise it raises.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+from ._lib import HeadCfg, check, dtype_code, ptr, require_cuda, stream_ptr
+
+MAX_SCALE = 24.0        # face_models.py:403
+NORM_EPS = 1e-12        # face_models.py:351
+
+
+def head_schedule(current_epoch, warm_up_epochs, use_warm_up, training, margin_factor, scale_factor):
+    """Warm-up schedule, face_models.py:336-348.  Returns the (margin_factor, scale_factor) the
+    module stores after the call."""
+    if training and use_warm_up:
+        if current_epoch < warm_up_epochs:
+            progress = current_epoch / warm_up_epochs
+            margin_factor = min(0.9, progress * progress)
+            scale_factor = min(0.8, 0.3 + 0.5 * progress)
+        else:
+            margin_factor = 0.9
+            scale_factor = 0.8
+    return margin_factor, scale_factor
+
+
+def effective_margin_scale(s, m, margin_factor, scale_factor, training):
+    """(m_eff, s_eff) exactly as forward applies them, face_models.py:369,401-409."""
+    m_eff = m * margin_factor if training else m
+    effective_s = min(s, MAX_SCALE)
+    s_eff = effective_s * min(0.8, scale_factor) if training else effective_s
+    if m > 0.4 and training:
+        s_eff = s_eff * (0.8 - 0.5 * margin_factor)
+    return m_eff, s_eff
+
+
+@dataclass
+class HeadStats:
+    """Device-resident side outputs of one fused forward (read them lazily: .item() syncs)."""
+    row_best: Optional[torch.Tensor] = None      # [B] max logit per row (this shard)
+    row_argmax: Optional[torch.Tensor] = None    # [B] its global class index
+    cos_minmax: Optional[torch.Tensor] = None    # [2] {min, max} raw cosine (face_models.py:358-360)
+    nan_flag: Optional[torch.Tensor] = None      # [1] int32, 1 if a logit was scrubbed (:423-427)
+    hook_out: Optional[torch.Tensor] = None      # [3] grad_scale, ||dL/dt||_F, kappa (after backward)
+    lse: Optional[torch.Tensor] = None           # [B]
+    dx_f32: Optional[torch.Tensor] = None        # [B,D] fp32 dL/dx before the cast to x.dtype (after backward)
+
+
+@dataclass
+class _Hook:
+    enabled: bool = False
+    max_grad_norm: float = 1.0
+    phase: int = 1
+    epoch: int = 0
+
+
+def _head_cfg(m_eff, s_eff, label_smoothing, easy, c_total, engine) -> HeadCfg:
+    return HeadCfg(float(m_eff), float(s_eff), float(label_smoothing), int(bool(easy)), int(c_total),
+                   int(engine), 0)
+
+
+def _row_inv_norm(t: torch.Tensor) -> torch.Tensor:
+    """K1: 1 / max(||row||, 1e-12) per row."""
+    lib = _lib.load_library()
+    inv = torch.empty(t.shape[0], dtype=torch.float32, device=t.device)
+    check(lib.b200f_l2norm_rows(ptr(t), dtype_code(t), t.shape[0], t.shape[1], NORM_EPS, ptr(inv), None, 0,
+                                stream_ptr(t.device)), "b200f_l2norm_rows")
+    return inv
+
+
+def l2_normalize(t: torch.Tensor, out_dtype: Optional[torch.dtype] = None):
+    """K1 with the normalised rows materialised: returns (t_hat, inv_norm)."""
+    require_cuda(t)
+    t = t.contiguous()
+    lib = _lib.load_library()
+    out = torch.empty(t.shape, dtype=out_dtype or t.dtype, device=t.device)
+    inv = torch.empty(t.shape[0], dtype=torch.float32, device=t.device)
+    check(lib.b200f_l2norm_rows(ptr(t), dtype_code(t), t.shape[0], t.shape[1], NORM_EPS, ptr(inv), ptr(out),
+                                dtype_code(out), stream_ptr(t.device)), "b200f_l2norm_rows")
+    return out, inv
+
+
+def _fwd_kernels(x, w, label, cfg: HeadCfg, class_offset, want_logits):
+    lib = _lib.load_library()
+    B, D = x.shape
+    C = w.shape[0]
+    dev = x.device
+    inv_nx = _row_inv_norm(x)
+    with _lib.timed("l2norm_rows_w", dev):
+        inv_nw = _row_inv_norm(w)
+    row_stats = torch.empty(B, _lib.STAT_COLS, dtype=torch.float32, device=dev)
+    row_best = torch.empty(B, dtype=torch.float32, device=dev)
+    row_argmax = torch.empty(B, dtype=torch.int64, device=dev)
+    cos_minmax = torch.empty(2, dtype=torch.float32, device=dev)
+    nan_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    logits = torch.empty(B, C, dtype=torch.float32, device=dev) if want_logits else None
+    nbytes = lib.b200f_head_workspace_bytes(B, C, D, dtype_code(x), cfg.engine)
+    ws = _lib.workspace(nbytes, dev, "head")
+    with _lib.timed("arcface_fwd", dev):
+        check(lib.b200f_arcface_fwd(ptr(x), ptr(w), dtype_code(x), ptr(inv_nx), ptr(inv_nw), ptr(label), B, C,
+                                    int(class_offset), D, cfg, ptr(row_stats), ptr(row_best), ptr(row_argmax),
+                                    ptr(cos_minmax), ptr(nan_flag), ptr(logits), C, ptr(ws), ws.numel(),
+                                    stream_ptr(dev)), "b200f_arcface_fwd")
+    return inv_nx, inv_nw, row_stats, row_best, row_argmax, cos_minmax, nan_flag, logits
+
+
+def _bwd_kernels(x, w, label, inv_nx, inv_nw, lse, grad_scale, cfg: HeadCfg, class_offset,
+                 dlogits=None):
+    lib = _lib.load_library()
+    B, D = x.shape
+    C = w.shape[0]
+    dev = x.device
+    dxhat = torch.empty(B, D, dtype=torch.float32, device=dev)
+    dw = torch.empty(C, D, dtype=torch.float32, device=dev)
+    nbytes = lib.b200f_head_workspace_bytes(B, C, D, dtype_code(x), cfg.engine)
+    ws = _lib.workspace(nbytes, dev, "head")
+    with _lib.timed("arcface_bwd", dev):
+        check(lib.b200f_arcface_bwd(ptr(x), ptr(w), dtype_code(x), ptr(inv_nx), ptr(inv_nw), ptr(label), ptr(lse),
+                                    ptr(grad_scale), ptr(dlogits), (dlogits.shape[1] if dlogits is not None else 0),
+                                    B, C, int(class_offset), D, cfg, ptr(dxhat), ptr(dw), ptr(ws), ws.numel(),
+                                    stream_ptr(dev)), "b200f_arcface_bwd")
+    return dxhat, dw
+
+
+def _normalize_bwd(x, inv_nx, dxhat):
+    lib = _lib.load_library()
+    dx = torch.empty_like(dxhat)
+    check(lib.b200f_l2norm_bwd(ptr(x), dtype_code(x), ptr(inv_nx), ptr(dxhat), x.shape[0], x.shape[1], ptr(dx),
+                               stream_ptr(x.device)), "b200f_l2norm_bwd")
+    return dx
+
+
+class _ArcFaceLossFn(torch.autograd.Function):
+    """loss = CE_labelsmooth(ArcMargin(x, w, y), y) fused: K1 + K2 (+ all-reduce) + K2b forward,
+    hook scalar + K3 (+ all-reduce) + normalise-backward in backward."""
+
+    @staticmethod
+    def forward(ctx, x, w, label, cfg: HeadCfg, class_offset, group, hook: _Hook, stats: HeadStats):
+        inv_nx, inv_nw, row_stats, row_best, row_argmax, cos_minmax, nan_flag, _ = _fwd_kernels(
+            x, w, label, cfg, class_offset, False)
+        if group is not None:
+            from . import parallel
+            parallel.reduce_row_stats(row_stats, group)          # one SUM all-reduce of [B,4]
+        lib = _lib.load_library()
+        B = x.shape[0]
+        lse = torch.empty(B, dtype=torch.float32, device=x.device)
+        out2 = torch.empty(2, dtype=torch.float32, device=x.device)   # loss, pq_norm2
+        check(lib.b200f_arcface_loss(ptr(row_stats), B, cfg, ptr(lse), ptr(out2), ptr(out2[1:]),
+                                     stream_ptr(x.device)), "b200f_arcface_loss")
+        stats.row_best, stats.row_argmax = row_best, row_argmax
+        stats.cos_minmax, stats.nan_flag, stats.lse = cos_minmax, nan_flag, lse
+        ctx.save_for_backward(x, w, label, inv_nx, inv_nw, lse, out2)
+        ctx.cfg, ctx.class_offset, ctx.group, ctx.hook, ctx.stats = cfg, class_offset, group, hook, stats
+        return out2[0].clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, w, label, inv_nx, inv_nw, lse, out2 = ctx.saved_tensors
+        cfg, hook = ctx.cfg, ctx.hook
+        lib = _lib.load_library()
+        up = grad_out.to(torch.float32).contiguous()
+        out3 = torch.empty(3, dtype=torch.float32, device=x.device)
+        check(lib.b200f_arcface_hook_scale(ptr(out2[1:]), ptr(up), x.shape[0], cfg.s_eff, int(hook.enabled),
+                                           float(hook.max_grad_norm), int(hook.phase), int(hook.epoch),
+                                           ptr(out3), stream_ptr(x.device)), "b200f_arcface_hook_scale")
+        ctx.stats.hook_out = out3
+        dxhat, dw = _bwd_kernels(x, w, label, inv_nx, inv_nw, lse, out3, cfg, ctx.class_offset)
+        if ctx.group is not None:
+            from . import parallel
+            parallel.reduce_dxhat(dxhat, ctx.group)              # one SUM all-reduce of [B,D]
+        dx = _normalize_bwd(x, inv_nx, dxhat)
+        ctx.stats.dx_f32 = dx
+        return dx.to(x.dtype), dw.to(w.dtype), None, None, None, None, None, None
+
+
+class _ArcLogitsFn(torch.autograd.Function):
+    """Compatibility path: the scaled logits themselves (ArcMarginProduct.forward).  Backward takes the
+    upstream dL/dlogits and runs the same K3 kernels with G = dlogits * s_eff * dphi * clamp-mask."""
+
+    @staticmethod
+    def forward(ctx, x, w, label, cfg: HeadCfg, hook: _Hook, stats: HeadStats):
+        inv_nx, inv_nw, _rs, row_best, row_argmax, cos_minmax, nan_flag, logits = _fwd_kernels(
+            x, w, label, cfg, 0, True)
+        stats.row_best, stats.row_argmax = row_best, row_argmax
+        stats.cos_minmax, stats.nan_flag = cos_minmax, nan_flag
+        ctx.save_for_backward(x, w, label, inv_nx, inv_nw)
+        ctx.cfg, ctx.hook, ctx.stats = cfg, hook, stats
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        x, w, label, inv_nx, inv_nw = ctx.saved_tensors
+        cfg, hook = ctx.cfg, ctx.hook
+        dlogits = dlogits.to(torch.float32).contiguous()
+        # the legacy hook sees grad_input = dL/d(pre-scale output) = dlogits * s_eff (face_models.py:541)
+        n = torch.linalg.vector_norm(dlogits) * cfg.s_eff
+        kappa = torch.ones((), dtype=torch.float32, device=x.device)
+        if hook.enabled:
+            thr = hook.max_grad_norm
+            if hook.phase == 1:
+                thr = min(0.5, hook.max_grad_norm)
+            if hook.epoch < 10:
+                thr = min(thr, 0.5 + 0.05 * hook.epoch)
+            thr_t = torch.where(n > 3.0, torch.clamp(torch.full_like(n, thr), max=0.5), torch.full_like(n, thr))
+            kappa = torch.where(n > thr_t, thr_t / (n + 1e-8), torch.ones_like(n))
+        out3 = torch.stack([kappa * cfg.s_eff, n, kappa]).to(torch.float32)
+        ctx.stats.hook_out = out3
+        lse_dummy = torch.zeros(1, dtype=torch.float32, device=x.device)
+        dxhat, dw = _bwd_kernels(x, w, label, inv_nx, inv_nw, lse_dummy, out3, cfg, 0, dlogits=dlogits)
+        dx = _normalize_bwd(x, inv_nx, dxhat)
+        return dx.to(x.dtype), dw.to(w.dtype), None, None, None, None
+
+
+def arcface_loss(x, weight, label, *, m_eff, s_eff, label_smoothing=0.05, easy_margin=False,
+                 class_offset=0, num_classes_total=None, group=None, hook: Optional[_Hook] = None,
+                 stats: Optional[HeadStats] = None, engine=_lib.ENGINE_AUTO):
+    """Functional fused head: mean label-smoothed CE of the ArcFace logits of (x, weight).
+    x [B,D], weight [C_local,D] (same dtype: fp32 or bf16, CUDA), label [B] int64 global ids."""
+    require_cuda(x, weight, label)
+    if x.dtype != weight.dtype:
+        raise TypeError(f"x ({x.dtype}) and weight ({weight.dtype}) must share a dtype")
+    cfg = _head_cfg(m_eff, s_eff, label_smoothing, easy_margin,
+                    num_classes_total if num_classes_total is not None else weight.shape[0], engine)
+    return _ArcFaceLossFn.apply(x.contiguous(), weight.contiguous(), label.contiguous().to(torch.int64), cfg,
+                                class_offset, group, hook or _Hook(), stats if stats is not None else HeadStats())
+
+
+class ArcMarginProduct(nn.Module):
+    """Drop-in for the reference ArcMarginProduct (face_models.py:297-445): same constructor, the
+    same externally mutated attributes (s, m, easy_margin, use_warm_up, warm_up_epochs, margin_factor,
+    scale_factor, current_epoch -- hyperparameter_tuning.py:829-840 pokes them), same state_dict
+    (``weight`` [C,D] fp32, buffer ``u`` [1])."""
+
+    def __init__(self, in_feats, out_feats, s=32.0, m=0.5, use_warm_up=True, easy_margin=False):
+        super().__init__()
+        self.in_feats = in_feats
+        self.out_feats = out_feats
+        self.s = s
+        self.m = m
+        self.easy_margin = easy_margin
+        self.use_warm_up = use_warm_up
+        self.warm_up_epochs = 10
+        self.margin_factor = 0.0
+        self.scale_factor = 0.3
+        self.current_epoch = 0
+        self.weight = nn.Parameter(torch.empty(out_feats, in_feats, dtype=torch.float32))
+        nn.init.xavier_normal_(self.weight, gain=math.sqrt(2))
+        self.register_buffer('u', torch.zeros(1))
+        self.easy_margin_used = False
+        self.engine = _lib.ENGINE_AUTO
+        self.compute_dtype: Optional[torch.dtype] = None   # None: follow the input's dtype
+        self.last_stats = HeadStats()
+        self._hook = _Hook()
+        self._w_shadow = None
+
+    # -- schedule + effective parameters (host logic, stateful exactly like the reference) --------
+    def _step_schedule(self):
+        self.margin_factor, self.scale_factor = head_schedule(
+            self.current_epoch, self.warm_up_epochs, self.use_warm_up, self.training,
+            self.margin_factor, self.scale_factor)
+        m_eff, s_eff = effective_margin_scale(self.s, self.m, self.margin_factor, self.scale_factor,
+                                              self.training)
+        # face_models.py:415-420: the warning branches draw from the CPU generator only when the
+        # first two conditions hold; the "rescale" multiplies by 20/20 (a no-op) -- both kept.
+        if s_eff > 20.0 and self.training and torch.rand(1).item() < 0.05:
+            print(f"Warning: Scale value too high ({s_eff:.1f}) - reducing to prevent instability")
+        elif s_eff < 3.0 and self.training and torch.rand(1).item() < 0.05:
+            print(f"Warning: Scale value too low ({s_eff:.1f}) - might train slowly")
+        if self.easy_margin:
+            self.easy_margin_used = True
+        return m_eff, s_eff
+
+    def _operands(self, input):
+        require_cuda(input, self.weight)
+        dt = self.compute_dtype or (input.dtype if input.dtype in (torch.float32, torch.bfloat16)
+                                    else torch.float32)
+        x = input.to(dt).contiguous()
+        if self.weight.dtype == dt:
+            w = self.weight
+        else:
+            w = _CastWeight.apply(self.weight, dt)       # autograd-visible cast, grad returns in fp32
+        return x, w
+
+    def forward(self, input, label):
+        """Scaled logits [B,C] fp32 (compatibility path; stores the logits)."""
+        m_eff, s_eff = self._step_schedule()
+        x, w = self._operands(input)
+        cfg = _head_cfg(m_eff, s_eff, 0.0, self.easy_margin, self.out_feats, self.engine)
+        self.last_stats = HeadStats()
+        return _ArcLogitsFn.apply(x, w.contiguous(), label.contiguous().to(torch.int64), cfg, self._hook,
+                                  self.last_stats)
+
+    def forward_loss(self, input, label, label_smoothing=0.05, return_pred=False):
+        """Fused criterion(forward(input,label), label) with nn.CrossEntropyLoss(label_smoothing):
+        the logits never reach HBM.  return_pred: also return outputs.max(1) indices
+        (hyperparameter_tuning.py:1001)."""
+        m_eff, s_eff = self._step_schedule()
+        x, w = self._operands(input)
+        self.last_stats = HeadStats()
+        loss = arcface_loss(x, w, label, m_eff=m_eff, s_eff=s_eff, label_smoothing=label_smoothing,
+                            easy_margin=self.easy_margin, hook=self._hook, stats=self.last_stats,
+                            engine=self.engine)
+        if return_pred:
+            return loss, self.last_stats.row_argmax
+        return loss
+
+    def update_epoch(self, epoch):
+        self.current_epoch = epoch
+
+    # reference attributes that used to be filled with .item() syncs on every forward (:358-360):
+    # now read lazily from the device
+    @property
+    def max_cos_theta(self):
+        t = self.last_stats.cos_minmax
+        return float(t[1].item()) if t is not None else 0.0
+
+    @property
+    def min_cos_theta(self):
+        t = self.last_stats.cos_minmax
+        return float(t[0].item()) if t is not None else 0.0
+
+    @property
+    def nan_seen(self):
+        t = self.last_stats.nan_flag
+        seen = bool(t.item()) if t is not None else False
+        if seen:
+            print("Uh oh! NaN or Inf in ArcFace output!")      # face_models.py:427
+        return seen
+
+    def get_margin_stats(self):
+        return {
+            'margin_factor': self.margin_factor,
+            'scale_factor': self.scale_factor,
+            'effective_margin': self.m * self.margin_factor,
+            'effective_scale': self.s * self.scale_factor,
+            'max_cos_theta': self.max_cos_theta,
+            'min_cos_theta': self.min_cos_theta,
+            'easy_margin_used': self.easy_margin_used if self.easy_margin else False,
+        }
+
+
+class _CastWeight(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, w, dtype):
+        ctx.src_dtype = w.dtype
+        return w.to(dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(ctx.src_dtype), None
+
+
+class ArcFaceNet(nn.Module):
+    """Drop-in for the reference ArcFaceNet (face_models.py:447-613).  The ResNet18 trunk is
+    torchvision's (out of scope); the head tail -- embedding, bn, dropout, normalise, ArcFace, and
+    the backward-hook gradient renormalisation (:538-570) -- is mirrored over the fused kernels.
+    state_dict keys match the reference so its checkpoints load strictly."""
+
+    def __init__(self, num_classes=18, dropout_rate=0.2, s=32.0, m=0.5, easy_margin=False,
+                 backbone: Optional[nn.Module] = None, pretrained: bool = False):
+        super().__init__()
+        if backbone is None:
+            import torchvision.models as models
+            weights = models.ResNet18_Weights.IMAGENET1K_V1 if pretrained else None
+            backbone = models.resnet18(weights=weights)
+        self.backbone = backbone
+        self.features = nn.Sequential(*list(self.backbone.children())[:-1])
+        self.embedding = nn.Linear(512, 512, bias=False)
+        self.bn = nn.BatchNorm1d(512, eps=1e-5)
+        self.dropout = nn.Dropout(p=dropout_rate)
+        self.arcface = ArcMarginProduct(512, num_classes, s=s, m=m, use_warm_up=True, easy_margin=easy_margin)
+        self.max_grad_norm = 1.0
+        self.current_epoch = 0
+        self.phase = 1
+        self.backbone_frozen = False
+        self.val_classifier = nn.Linear(512, num_classes)
+        nn.init.xavier_normal_(self.val_classifier.weight, gain=math.sqrt(2))
+        self._hook_armed = False          # the reference registers its hook after the 1st forward
+
+    def freeze_backbone(self):
+        self.backbone_frozen = True
+        self.phase = 1
+        for param_name, param in self.named_parameters():
+            if 'backbone' in param_name or 'features' in param_name:
+                param.requires_grad = False
+
+    def unfreeze_backbone(self):
+        self.backbone_frozen = False
+        self.phase = 2
+        for param in self.parameters():
+            param.requires_grad = True
+
+    def set_max_grad_norm(self, max_norm):
+        self.max_grad_norm = max_norm
+
+    def _tail(self, x, training):
+        x = self.features(x)
+        x = x.view(x.size(0), -1)
+        x = self.embedding(x)
+        x = self.bn(x)
+        if training:
+            x = self.dropout(x)
+        return F.normalize(x, p=2, dim=1, eps=1e-12)
+
+    def _arm_hook(self):
+        # hook state as the reference's closure would read it at backward time (:544-556)
+        self.arcface._hook = _Hook(enabled=self._hook_armed, max_grad_norm=self.max_grad_norm,
+                                   phase=self.phase, epoch=self.current_epoch)
+        self._hook_armed = True
+
+    def forward(self, x, labels=None):
+        emb = self._tail(x, self.training)
+        if self.training:
+            if labels is None:
+                raise ValueError("Labels must be provided during training")
+            self.arcface.update_epoch(self.current_epoch)
+            self._arm_hook()
+            return self.arcface(emb, labels)
+        self.val_classifier.weight.data = F.normalize(self.val_classifier.weight.data, p=2, dim=1, eps=1e-12)
+        if labels is not None:
+            return self.val_classifier(emb)
+        return emb
+
+    def forward_loss(self, x, labels, label_smoothing=0.05, return_pred=False):
+        """Fused training step head: == criterion(self(x, labels), labels) incl. the hook."""
+        if labels is None:
+            raise ValueError("Labels must be provided during training")
+        emb = self._tail(x, self.training)
+        self.arcface.update_epoch(self.current_epoch)
+        self._arm_hook()
+        return self.arcface.forward_loss(emb, labels, label_smoothing, return_pred)
+
+    def get_embedding(self, x):
+        x = self.features(x)
+        x = x.view(x.size(0), -1)
+        x = self.embedding(x)
+        x = self.bn(x)
+        return F.normalize(x, p=2, dim=1, eps=1e-12)
+
+    def update_epoch(self, epoch):
+        self.current_epoch = epoch
+        self.arcface.update_epoch(epoch)
+
+    @property
+    def last_grad_norm(self):
+        t = self.arcface.last_stats.hook_out
+        return float(t[1].item()) if (t is not None and self.arcface._hook.enabled) else 0.0
+
+    def get_arcface_stats(self):
+        stats = self.arcface.get_margin_stats()
+        stats['grad_norm'] = self.last_grad_norm
+        stats['max_grad_norm'] = self.max_grad_norm
+        stats['phase'] = self.phase
+        stats['backbone_frozen'] = self.backbone_frozen
+        return stats
+
+    def get_training_phase(self):
+        return {'phase': self.phase, 'backbone_frozen': self.backbone_frozen, 'epoch': self.current_epoch}

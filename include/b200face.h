@@ -1,0 +1,166 @@
+/* b200face.h -- C ABI of libb200face.so (B200 / sm_100a).
+ *
+ * The reference (henryhcooperr/FaceRecognition-MultiArchitecture-Pipeline) is pure Python and
+ * exposes no FFI; the drop-in boundary is the Python surface
+ *     ArcMarginProduct.forward / update_epoch / get_margin_stats   src/face_models.py:297-445
+ *     criterion = nn.CrossEntropyLoss(label_smoothing=eps)          src/training.py:341,515
+ *     loss.backward() + ArcFaceNet backward hook                    src/face_models.py:538-570
+ *     compare_faces(emb, refs, thresh)                              src/app.py:50-64
+ *     cosine class-centre match                                     src/hyperparameter_tuning.py:1039-1046,1076
+ * and this header is what a ctypes binding of that surface calls (INTEGRATION.md shows the
+ * binding).  Conventions for every entry point:
+ *   - all data pointers are DEVICE pointers, row-major, borrowed for the call; the caller
+ *     (PyTorch) owns every buffer including the workspace;
+ *   - the last argument is the cudaStream_t to launch on (void* so no CUDA header is needed);
+ *   - no allocation, no implicit synchronisation, no global mutable state;
+ *   - return 0 on success, <0 on error; b200f_last_error() gives the thread-local message.
+ * Element types: B200F_F32 / B200F_BF16.  All arithmetic accumulates in fp32.
+ */
+#ifndef B200FACE_H_
+#define B200FACE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200F_F32   0
+#define B200F_BF16  1
+
+#define B200F_METRIC_L2EPS 0   /* || q - g + 1e-6 ||_2, ascending   (src/app.py:59)            */
+#define B200F_METRIC_COS   1   /* <q,g> * inv|q| * inv|g|, descending (hyperparameter_tuning.py:1046) */
+
+#define B200F_OK            0
+#define B200F_ERR_ARG      -1
+#define B200F_ERR_CUDA     -2
+#define B200F_ERR_WORKSPACE -3
+#define B200F_ERR_UNSUPPORTED -4
+
+/* Engines for the GEMM-shaped stages. AUTO picks the tcgen05/TMEM/TMA path for bf16 inputs
+ * whose shapes it supports and the fp32 CUDA-core path otherwise (fp32 inputs: the 1e-5 bar
+ * needs fp32 products). */
+#define B200F_ENGINE_AUTO    0
+#define B200F_ENGINE_SIMT    1
+#define B200F_ENGINE_TCGEN05 2
+
+/* Effective head parameters for ONE forward/backward call.  The epoch-driven schedule
+ * (src/face_models.py:336-348), the 24.0 scale cap and the m>0.4 damping (:401-409) are host
+ * logic; the kernels see only their result. */
+typedef struct b200f_head_cfg {
+  float   m_eff;             /* m * margin_factor (training) or m (eval)      :369        */
+  float   s_eff;             /* effective scale applied to the logits        :401-412    */
+  float   label_smoothing;   /* eps of nn.CrossEntropyLoss                   training.py:341 */
+  int32_t easy_margin;       /* 0: cos(min(pi-1e-4, theta+m)), 1: easy branch :372-397   */
+  int64_t num_classes_total; /* C over all shards (label smoothing uses eps/C)            */
+  int32_t engine;            /* B200F_ENGINE_*                                             */
+  int32_t reserved;
+} b200f_head_cfg;
+
+/* Per-row forward statistics, [B, B200F_STAT_COLS] fp32, additive over class shards
+ * (the softmax shift is the constant s_eff: |logit| <= s_eff):               */
+#define B200F_STAT_SUMEXP   0   /* sum_j exp(z_ij - s_eff)                                 */
+#define B200F_STAT_SUMEXP2  1   /* sum_j exp(2 (z_ij - s_eff))  -> ||p-q||_F for the hook  */
+#define B200F_STAT_ZTARGET  2   /* z_{i,y_i} (0 on shards that do not own y_i)             */
+#define B200F_STAT_SUMZ     3   /* sum_j z_ij                  (label smoothing)           */
+#define B200F_STAT_COLS     4
+
+int         b200f_version(void);
+const char* b200f_last_error(void);
+/* number of kernels this library has launched in the process so far (diagnostic; bench.py's
+ * gpu_launches is a difference of two reads) */
+unsigned long long b200f_launch_count(void);
+/* 1 when the library was built with the tcgen05 kernels and the current device is sm_100 */
+int         b200f_has_tcgen05(void);
+
+/* K1 -- fused row L2-normalise: inv_norm[r] = 1 / max(||in[r,:]||_2, eps)  (F.normalize,
+ * src/face_models.py:351-352,525).  out (optional) = in * inv_norm in out_dtype. */
+int b200f_l2norm_rows(const void* in, int in_dtype, int64_t rows, int dim, float eps,
+                      float* inv_norm, void* out_or_null, int out_dtype, void* stream);
+
+/* Bytes of workspace the head calls need for (B, C_local, D). */
+size_t b200f_head_workspace_bytes(int64_t B, int64_t C_local, int D, int dtype, int engine);
+
+/* K2 -- cosine logits x_hat . w_hat^T for this shard's classes [class_offset, class_offset+C_local),
+ * clamp, angular margin on the target column, scale, NaN/Inf scrub, and the per-row softmax /
+ * cross-entropy statistics, without writing the B x C logits (src/face_models.py:351-427 +
+ * training.py:515).  Outputs:
+ *   row_stats  [B,4] fp32 (see B200F_STAT_*), row_best [B] fp32 + row_argmax [B] int64
+ *   (max logit and its GLOBAL class index, first index on ties), cos_minmax [2] fp32
+ *   ({min,max} raw cosine over the shard, :358-360), nan_flag [1] int32 (set to 1 when a
+ *   non-finite logit was scrubbed to 0, :423-427).
+ *   logits_or_null: when non-NULL the scaled logits are ALSO stored ([B, ld_logits] fp32) --
+ *   the compatibility path of ArcMarginProduct.forward at small C. */
+int b200f_arcface_fwd(const void* x, const void* w, int dtype,
+                      const float* inv_nx, const float* inv_nw, const int64_t* label,
+                      int64_t B, int64_t C_local, int64_t class_offset, int D,
+                      const b200f_head_cfg* cfg,
+                      float* row_stats, float* row_best, int64_t* row_argmax,
+                      float* cos_minmax, int32_t* nan_flag,
+                      float* logits_or_null, int64_t ld_logits,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* K2b -- after the (optional) cross-shard SUM of row_stats: lse[i] = s_eff + log(sumexp_i),
+ * loss = mean_i[ lse_i - (1-eps) z_target_i - (eps/C) sum_z_i ]  (CrossEntropyLoss with
+ * label smoothing, mean reduction), pq_norm2 = sum_ij (p_ij - q_ij)^2  (the Frobenius norm the
+ * ArcFaceNet hook clips on, src/face_models.py:541). */
+int b200f_arcface_loss(const float* row_stats, int64_t B, const b200f_head_cfg* cfg,
+                       float* lse, float* loss, float* pq_norm2, void* stream);
+
+/* Hook scalar (src/face_models.py:538-567), on the device, no host sync:
+ *   n = |upstream| * s_eff / B * sqrt(pq_norm2);  kappa = thr/(n+1e-8) if n > thr else 1
+ *   with thr from (max_grad_norm, phase, epoch) and the n > 3 rule.
+ * out[0] = grad_scale = upstream * kappa * s_eff / B   (what K3 multiplies (p-q) by)
+ * out[1] = n (last_grad_norm), out[2] = kappa.   hook_enabled = 0 -> kappa = 1. */
+int b200f_arcface_hook_scale(const float* pq_norm2, const float* upstream, int64_t B,
+                             float s_eff, int hook_enabled, float max_grad_norm, int phase,
+                             int epoch, float* out3, void* stream);
+
+/* K3 -- backward for this shard: recompute the logits tile by tile, form
+ *   G_ij = grad_scale * (p_ij - q_ij) * dphi/dc * 1[lo <= cos <= hi]
+ * and produce
+ *   dxhat [B,D] fp32   = G . w_hat            (this shard's partial; SUM over shards)
+ *   dw    [C_local,D] fp32 = normalise-backward of (G^T . x_hat) w.r.t. the raw weight rows
+ * lse from K2b (global), grad_scale = out3[0] of b200f_arcface_hook_scale (device scalar).
+ * dlogits_or_null: compatibility path of ArcMarginProduct.forward -> logits: when non-NULL
+ * ([B, ld_dlogits] fp32, upstream dL/dlogits of this shard) G_ij = grad_scale * dlogits_ij * dphi/dc *
+ * clamp-mask instead, and lse is ignored. */
+int b200f_arcface_bwd(const void* x, const void* w, int dtype,
+                      const float* inv_nx, const float* inv_nw, const int64_t* label,
+                      const float* lse, const float* grad_scale,
+                      const float* dlogits_or_null, int64_t ld_dlogits,
+                      int64_t B, int64_t C_local, int64_t class_offset, int D,
+                      const b200f_head_cfg* cfg,
+                      float* dxhat, float* dw,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* Normalise-backward for rows: dv = inv_n * (dvhat - vhat * <vhat, dvhat>), vhat = v * inv_n
+ * (autograd of F.normalize, src/face_models.py:351,525).  dv fp32 [rows, dim]. */
+int b200f_l2norm_bwd(const void* v, int dtype, const float* inv_norm, const float* dvhat,
+                     int64_t rows, int dim, float* dv, void* stream);
+
+/* K4 -- gallery match: for each query the k best rows of this gallery shard.
+ *   metric L2EPS: score = || q - g + 1e-6 ||_2 ascending, accept = best <= thresh (src/app.py:50-64)
+ *   metric COS  : score = <q,g> * q_inv[i] * g_inv[j] descending, accept = best >= thresh
+ *                 (q_inv / g_inv from b200f_l2norm_rows; NULL = 1)
+ * idx [Q,k] int64 holds GLOBAL indices (index_offset + local row), -1 for missing slots;
+ * ties go to the lowest index (strict '<' at src/app.py:60). k <= 16. */
+size_t b200f_gallery_workspace_bytes(int64_t Q, int64_t N_local, int D, int k, int dtype, int engine);
+int b200f_gallery_topk(const void* q, const void* g, int dtype,
+                       const float* q_inv, const float* g_inv,
+                       int64_t Q, int64_t N_local, int64_t index_offset, int D,
+                       int k, int metric, float thresh, int engine,
+                       int64_t* idx, float* score, uint8_t* accept,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* Merge P per-shard top-k lists (after an all-gather): idx_all/score_all [P,Q,k] ->
+ * idx/score [Q,k], accept [Q]; lowest global index wins ties. */
+int b200f_gallery_merge(const int64_t* idx_all, const float* score_all, int P, int64_t Q, int k,
+                        int metric, float thresh,
+                        int64_t* idx, float* score, uint8_t* accept, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200FACE_H_ */

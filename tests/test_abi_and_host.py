@@ -1,0 +1,144 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/b200face.h declares
+(no compute calls without a GPU), the host logic mirrors the reference's module surface, and the
+product refuses to run without CUDA (no fallback)."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, golden
+import oracle
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as ge
+    if not os.path.exists(ge.LIB):
+        ge.build_library()
+    import b200face
+    return b200face.load_library()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    hdr = open(os.path.join(ROOT, "include", "b200face.h")).read()
+    declared = set(re.findall(r"\b(b200f_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 12
+    from b200face import _lib
+    assert declared == set(_lib.PROTOTYPES), "ctypes prototypes and header disagree"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} missing from libb200face.so"
+    assert lib.b200f_version() >= 100
+
+
+def test_head_cfg_struct_layout():
+    import ctypes
+    from b200face._lib import HeadCfg
+    assert ctypes.sizeof(HeadCfg) == 32          # 3 floats + int32 + int64 + 2 int32, as in the header
+    assert HeadCfg.num_classes_total.offset == 16
+
+
+def test_no_cpu_fallback():
+    import b200face
+    head = b200face.ArcMarginProduct(16, 4)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        head.forward_loss(torch.randn(2, 16), torch.tensor([0, 1]))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        head(torch.randn(2, 16), torch.tensor([0, 1]))
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="CUDA"):
+            b200face.compare_faces(torch.zeros(1, 8), [{"name": "a", "embedding": torch.zeros(1, 8)}], 1.0)
+
+
+def test_compare_faces_degenerate_inputs_match_reference():
+    """src/app.py:51: None query or empty refs -> ("Unknown", inf, None) without touching the GPU."""
+    import b200face
+    assert b200face.compare_faces(None, [{"name": "a", "embedding": torch.zeros(1, 8)}], 1.0) == ("Unknown", float("inf"), None)
+    assert b200face.compare_faces(torch.zeros(1, 8), [], 1.0) == ("Unknown", float("inf"), None)
+
+
+@pytest.mark.parametrize("warm", [5, 10, 20])
+@pytest.mark.parametrize("training", [True, False])
+def test_schedule_matches_oracle(warm, training):
+    import b200face
+    from b200face.head import effective_margin_scale
+    for epoch in range(0, 30):
+        for (s, m) in ((32.0, 0.5), (16.0, 0.3), (64.0, 0.45), (10.0, 0.5)):
+            cfg = oracle.HeadConfig(s=s, m=m, warm_up_epochs=warm, current_epoch=epoch, training=training,
+                                    margin_factor=0.1, scale_factor=0.2)
+            mf, sf = b200face.head_schedule(epoch, warm, True, training, 0.1, 0.2)
+            assert (mf, sf) == oracle.warmup_schedule(cfg)
+            assert effective_margin_scale(s, m, mf, sf, training) == oracle.effective_margin_scale(cfg)
+
+
+def test_schedule_defaults_are_the_reference_numbers():
+    """epoch-0 s_eff = 24*0.3*0.8 = 5.76; post-warm-up 24*0.8*0.35 = 6.72, m_eff = 0.45."""
+    from b200face.head import effective_margin_scale, head_schedule
+    mf, sf = head_schedule(0, 10, True, True, 0.0, 0.3)
+    assert effective_margin_scale(32.0, 0.5, mf, sf, True) == pytest.approx((0.0, 5.76))
+    mf, sf = head_schedule(10, 10, True, True, 0.0, 0.3)
+    assert effective_margin_scale(32.0, 0.5, mf, sf, True) == pytest.approx((0.45, 6.72))
+    assert effective_margin_scale(32.0, 0.5, mf, sf, False) == pytest.approx((0.5, 24.0))
+
+
+def test_arc_margin_product_surface():
+    """Same ctor / attributes / state_dict as face_models.py:307-332 so reference checkpoints load."""
+    import b200face
+    head = b200face.ArcMarginProduct(512, 36, s=30.0, m=0.4, use_warm_up=False, easy_margin=True)
+    sd = head.state_dict()
+    assert set(sd) == {"weight", "u"}
+    assert sd["weight"].shape == (36, 512) and sd["weight"].dtype == torch.float32 and sd["u"].shape == (1,)
+    for attr, val in dict(s=30.0, m=0.4, easy_margin=True, use_warm_up=False, warm_up_epochs=10,
+                          margin_factor=0.0, scale_factor=0.3, current_epoch=0, in_feats=512, out_feats=36).items():
+        assert getattr(head, attr) == val
+    head.update_epoch(7)
+    assert head.current_epoch == 7
+    stats = head.get_margin_stats()
+    assert set(stats) == {"margin_factor", "scale_factor", "effective_margin", "effective_scale",
+                          "max_cos_theta", "min_cos_theta", "easy_margin_used"}
+    assert stats["effective_scale"] == 30.0 * 0.3          # reports s*scale_factor, not the applied scale
+    # xavier_normal_(gain=sqrt(2)): std = sqrt(2) * sqrt(2/(fan_in+fan_out))
+    big = b200face.ArcMarginProduct(512, 2000)
+    assert float(big.weight.std()) == pytest.approx((2.0 ** 0.5) * (2.0 / 2512) ** 0.5, rel=0.03)
+    d = golden("head_epoch0.npz")
+    ref_sd = {"weight": torch.tensor(d["w"]), "u": torch.zeros(1)}
+    b200face.ArcMarginProduct(512, 36).load_state_dict(ref_sd, strict=True)
+
+
+def test_arcfacenet_surface_and_errors():
+    import b200face
+    net = b200face.ArcFaceNet(num_classes=5)
+    keys = set(net.state_dict())
+    for k in ("arcface.weight", "arcface.u", "embedding.weight", "bn.weight", "bn.running_mean",
+              "val_classifier.weight", "val_classifier.bias", "backbone.conv1.weight", "features.0.weight"):
+        assert k in keys
+    net.train()
+    with pytest.raises(ValueError, match="Labels must be provided during training"):
+        net(torch.randn(2, 3, 32, 32))
+    net.eval()
+    with torch.no_grad():
+        emb = net(torch.randn(2, 3, 32, 32))
+        assert emb.shape == (2, 512)
+        assert torch.allclose(emb.norm(dim=1), torch.ones(2), atol=1e-5)
+        assert net(torch.randn(2, 3, 32, 32), torch.tensor([0, 1])).shape == (2, 5)
+    net.update_epoch(3)
+    assert net.arcface.current_epoch == 3 and net.current_epoch == 3
+    net.freeze_backbone()
+    assert net.phase == 1 and not net.backbone.conv1.weight.requires_grad and net.arcface.weight.requires_grad
+    net.unfreeze_backbone()
+    assert net.phase == 2 and net.backbone.conv1.weight.requires_grad
+    st = net.get_arcface_stats()
+    assert st["grad_norm"] == 0.0 and st["max_grad_norm"] == 1.0 and st["phase"] == 2
+
+
+def test_shard_bounds_cover_everything():
+    from b200face.parallel import shard_bounds
+    for total in (1, 7, 36, 100000, 1000000):
+        for world in (1, 2, 3, 8):
+            prev = 0
+            for r in range(world):
+                lo, hi = shard_bounds(total, world, r)
+                assert lo == prev and hi >= lo
+                prev = hi
+            assert prev == total

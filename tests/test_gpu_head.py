@@ -1,0 +1,319 @@
+"""GPU parity of the ArcFace head (kernels K1-K3 through the C ABI) against the reference-pinned
+oracle and the committed golden vectors.  Tolerances are the north star's: norm-wise relative error
+<= 1e-5 for fp32 inputs, <= 1e-3 for bf16 inputs (oracle = the reference arithmetic in fp64 on the
+bf16-rounded inputs)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import cfg_from_golden, golden, head_golden_names, rel_err
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+TOL_F32 = 1e-5
+TOL_BF16 = 1e-3
+
+
+def _head_from_cfg(cfg, C, D, dev, w):
+    import b200face
+    head = b200face.ArcMarginProduct(D, C, s=cfg.s, m=cfg.m, use_warm_up=cfg.use_warm_up,
+                                     easy_margin=cfg.easy_margin).to(dev)
+    head.warm_up_epochs = cfg.warm_up_epochs
+    head.margin_factor, head.scale_factor = cfg.margin_factor, cfg.scale_factor
+    head.update_epoch(cfg.current_epoch)
+    head.train(cfg.training)
+    with torch.no_grad():
+        head.weight.copy_(torch.as_tensor(w))
+    return head
+
+
+# ------------------------------------------------------------------ K1
+@pytest.mark.parametrize("rows,dim", [(1, 512), (37, 512), (1000, 512), (129, 100), (64, 33), (5, 4096), (3, 7)])
+@pytest.mark.parametrize("in_dt,out_dt", [(torch.float32, torch.float32), (torch.float32, torch.bfloat16),
+                                          (torch.bfloat16, torch.float32), (torch.bfloat16, torch.bfloat16)])
+def test_l2norm_rows(cuda_device, rows, dim, in_dt, out_dt):
+    from b200face.head import l2_normalize
+    g = torch.Generator().manual_seed(rows * 1000 + dim)
+    x = (torch.randn(rows, dim, generator=g) * 3).to(in_dt)
+    x[0] = 0                                                   # eps path: 0 / max(0, 1e-12) = 0
+    out, inv = l2_normalize(x.to(cuda_device), out_dtype=out_dt)
+    xf = x.float().double()
+    ref_inv = 1.0 / xf.norm(dim=1).clamp_min(1e-12)
+    ref = xf * ref_inv[:, None]
+    np.testing.assert_allclose(inv.cpu().double().numpy()[1:], ref_inv.numpy()[1:], rtol=3e-7)
+    assert float(inv[0]) == pytest.approx(1e12, rel=1e-6)
+    tol = 3e-7 if out_dt == torch.float32 else 2 ** -8
+    np.testing.assert_allclose(out.float().cpu().double().numpy(), ref.numpy(), rtol=tol, atol=1e-30)
+    assert torch.all(out[0] == 0)
+
+
+# ------------------------------------------------------------------ golden vectors (reference outputs)
+@pytest.mark.parametrize("name", head_golden_names())
+def test_golden_logits_compat_path(cuda_device, name):
+    d = golden(f"head_{name}.npz")
+    cfg = cfg_from_golden(d)
+    head = _head_from_cfg(cfg, d["w"].shape[0], d["w"].shape[1], cuda_device, d["w"])
+    x = torch.tensor(d["x"], device=cuda_device, requires_grad=True)
+    y = torch.tensor(d["y"], device=cuda_device)
+    out = head(x, y)
+    tol = 2e-4 if name.startswith("extreme") else TOL_F32
+    assert rel_err(out.detach().cpu().numpy(), d["logits"]) < tol
+    assert head.max_cos_theta == pytest.approx(float(d["cos_max"]), abs=2e-6)
+    assert head.min_cos_theta == pytest.approx(float(d["cos_min"]), abs=2e-6)
+    assert head.margin_factor == float(d["cfg"][7]) or not cfg.training
+    # caller's criterion + backward, exactly as src/training.py:515-521
+    loss = torch.nn.CrossEntropyLoss(label_smoothing=cfg.label_smoothing)(out, y)
+    loss.backward()
+    gt = 5e-3 if name.startswith("extreme") else 2e-5
+    assert float(loss) == pytest.approx(float(d["loss"]), rel=1e-5)
+    assert rel_err(x.grad.cpu().numpy(), d["dx"]) < gt
+    assert rel_err(head.weight.grad.cpu().numpy(), d["dw"]) < gt
+
+
+@pytest.mark.parametrize("name", head_golden_names())
+def test_golden_fused_loss_and_grads(cuda_device, name):
+    d = golden(f"head_{name}.npz")
+    cfg = cfg_from_golden(d)
+    head = _head_from_cfg(cfg, d["w"].shape[0], d["w"].shape[1], cuda_device, d["w"])
+    x = torch.tensor(d["x"], device=cuda_device, requires_grad=True)
+    y = torch.tensor(d["y"], device=cuda_device)
+    loss, pred = head.forward_loss(x, y, label_smoothing=cfg.label_smoothing, return_pred=True)
+    loss.backward()
+    assert float(loss) == pytest.approx(float(d["loss"]), rel=1e-5)
+    gt = 5e-3 if name.startswith("extreme") else 2e-5
+    assert rel_err(x.grad.cpu().numpy(), d["dx"]) < gt
+    assert rel_err(head.weight.grad.cpu().numpy(), d["dw"]) < gt
+    if not name.startswith("extreme"):
+        assert np.array_equal(pred.cpu().numpy(), d["logits"].argmax(1))
+    assert not head.nan_seen
+
+
+def test_golden_hook_arcfacenet(cuda_device):
+    """The ArcFaceNet backward hook (face_models.py:538-570) on the reference's own recorded step 2."""
+    import b200face
+    from b200face.head import _Hook
+    d = golden("hook_arcfacenet.npz")
+    max_gn, phase, epoch = [float(v) for v in d["meta"]]
+    for step, enabled in ((0, False), (1, True)):
+        head = b200face.ArcMarginProduct(512, 36).to(cuda_device)
+        head.update_epoch(int(epoch)); head.train()
+        with torch.no_grad():
+            head.weight.copy_(torch.tensor(d["w"]))
+        head._hook = _Hook(enabled=enabled, max_grad_norm=max_gn, phase=int(phase), epoch=int(epoch))
+        x = torch.tensor(d[f"emb{step}"], device=cuda_device, requires_grad=True)
+        y = torch.tensor(d[f"y{step}"], device=cuda_device)
+        loss = head.forward_loss(x, y, 0.05)
+        loss.backward()
+        assert float(loss) == pytest.approx(float(d[f"loss{step}"]), rel=1e-5)
+        assert rel_err(x.grad.cpu().numpy(), d[f"demb{step}"]) < 2e-5
+        assert rel_err(head.weight.grad.cpu().numpy(), d[f"dw{step}"]) < 2e-5
+        if enabled:
+            out3 = head.last_stats.hook_out.cpu().numpy()
+            assert out3[1] == pytest.approx(float(d["last_grad_norm1"]), rel=1e-5)
+            assert out3[2] < 1.0
+        # same through the logits path + external criterion
+        head.zero_grad(); x.grad = None
+        out = head(x, y)
+        torch.nn.CrossEntropyLoss(label_smoothing=0.05)(out, y).backward()
+        assert rel_err(x.grad.cpu().numpy(), d[f"demb{step}"]) < 2e-5
+        assert rel_err(head.weight.grad.cpu().numpy(), d[f"dw{step}"]) < 2e-5
+
+
+def test_arcfacenet_hook_arms_after_first_forward(cuda_device):
+    import b200face
+    torch.manual_seed(0)
+    net = b200face.ArcFaceNet(num_classes=12).to(cuda_device).train()
+    img = torch.randn(4, 3, 64, 64, device=cuda_device)
+    y = torch.tensor([0, 3, 5, 11], device=cuda_device)
+    net.forward_loss(img, y).backward()
+    assert net.last_grad_norm == 0.0                       # hook not registered during step 1
+    net.zero_grad()
+    net.forward_loss(img, y).backward()
+    assert net.last_grad_norm > 0.5                        # ~1.9 at init: clip active
+    assert float(net.arcface.last_stats.hook_out[2]) < 1.0
+    with pytest.raises(ValueError, match="Labels must be provided during training"):
+        net(img)
+
+
+# ------------------------------------------------------------------ oracle on seeded inputs
+def _random_case(B, C, D, seed, planted=0.125):
+    g = torch.Generator().manual_seed(seed)
+    w = torch.randn(C, D, generator=g) * (2.0 / (C + D)) ** 0.5 * 2 ** 0.5
+    x = torch.randn(B, D, generator=g)
+    y = torch.randint(0, C, (B,), generator=g)
+    n = int(B * planted)
+    x[:n] = 3.0 * w[y[:n]] + 0.3 * torch.randn(n, D, generator=g) * w.std()
+    return x, w, y
+
+
+@pytest.mark.parametrize("B,C,D", [(200, 3000, 512), (130, 1001, 96), (7, 5, 40), (256, 4096, 512)])
+@pytest.mark.parametrize("epoch,easy", [(0, False), (12, False), (12, True)])
+def test_fp32_vs_oracle(cuda_device, B, C, D, epoch, easy):
+    import b200face
+    x, w, y = _random_case(B, C, D, B + C + D + epoch)
+    cfg = oracle.HeadConfig(current_epoch=epoch, easy_margin=easy, training=True, label_smoothing=0.1)
+    head = _head_from_cfg(cfg, C, D, cuda_device, w)
+    xg = x.to(cuda_device).requires_grad_(True)
+    loss, pred = head.forward_loss(xg, y.to(cuda_device), 0.1, return_pred=True)
+    loss.backward()
+    ref = oracle.head_forward_backward(x.numpy(), w.numpy(), y.numpy(), cfg)
+    assert float(loss) == pytest.approx(float(ref["loss"]), rel=TOL_F32)
+    assert rel_err(xg.grad.cpu().numpy(), ref["dx"]) < TOL_F32
+    assert rel_err(head.weight.grad.cpu().numpy(), ref["dw"]) < TOL_F32
+    assert (pred.cpu().numpy() == ref["argmax"]).mean() > 0.995     # fp32 ties at 1 ulp may flip
+    assert head.max_cos_theta == pytest.approx(ref["cos_max"], abs=2e-6)
+    assert head.min_cos_theta == pytest.approx(ref["cos_min"], abs=2e-6)
+
+
+@pytest.mark.parametrize("engine", ["auto", "simt"])
+@pytest.mark.parametrize("B,C,D", [(256, 4096, 512), (200, 3000, 512), (512, 10240, 512), (100, 700, 64)])
+def test_bf16_vs_oracle(cuda_device, B, C, D, engine):
+    import b200face
+    from b200face import _lib
+    x, w, y = _random_case(B, C, D, 17 * B + C)
+    xb, wb = x.bfloat16(), w.bfloat16()
+    cfg = oracle.HeadConfig(current_epoch=12, training=True, label_smoothing=0.05)
+    head = _head_from_cfg(cfg, C, D, cuda_device, wb.float())
+    head.engine = _lib.ENGINE_AUTO if engine == "auto" else _lib.ENGINE_SIMT
+    xg = xb.to(cuda_device).requires_grad_(True)
+    loss = head.forward_loss(xg, y.to(cuda_device), 0.05)
+    loss.backward()
+    ref = oracle.head_forward_backward(xb.float().numpy(), wb.float().numpy(), y.numpy(), cfg)
+    assert float(loss) == pytest.approx(float(ref["loss"]), rel=TOL_BF16)
+    # x.grad comes back in bf16 (autograd forces the input's dtype); the kernels' fp32 dx is kept in
+    # last_stats.dx_f32 and that is what is held to the bar
+    assert rel_err(head.weight.grad.cpu().numpy(), ref["dw"]) < TOL_BF16
+    assert rel_err(head.last_stats.dx_f32.cpu().numpy(), ref["dx"]) < TOL_BF16
+    assert rel_err(xg.grad.float().cpu().numpy(), ref["dx"]) < TOL_BF16 + 2 ** -8
+
+
+def test_nan_inf_scrub(cuda_device):
+    """face_models.py:423-427: non-finite logits become 0 (and their gradient is cut)."""
+    import b200face
+    x, w, y = _random_case(16, 50, 64, 5, planted=0)
+    x[3, 7] = float("inf")
+    cfg = oracle.HeadConfig(current_epoch=12, training=True, label_smoothing=0.05)
+    head = _head_from_cfg(cfg, 50, 64, cuda_device, w)
+    loss = head.forward_loss(x.to(cuda_device), y.to(cuda_device), 0.05)
+    assert head.nan_seen
+    z, _, _, nan_seen = oracle.arc_logits(x.numpy(), w.numpy(), y.numpy(), cfg)
+    assert nan_seen
+    ref_loss, _ = oracle.smoothed_cross_entropy(z, y.numpy(), 0.05)
+    assert float(loss) == pytest.approx(float(ref_loss), rel=1e-5)
+
+
+def test_upstream_gradient_and_linearity(cuda_device):
+    import b200face
+    x, w, y = _random_case(64, 500, 128, 3)
+    cfg = oracle.HeadConfig(current_epoch=12, training=True, label_smoothing=0.05)
+    grads = []
+    for scale in (1.0, 2.0, -0.5):
+        head = _head_from_cfg(cfg, 500, 128, cuda_device, w)
+        xg = x.to(cuda_device).requires_grad_(True)
+        (head.forward_loss(xg, y.to(cuda_device), 0.05) * scale).backward()
+        grads.append((xg.grad.clone(), head.weight.grad.clone()))
+    for (gx, gw), scale in zip(grads[1:], (2.0, -0.5)):
+        torch.testing.assert_close(gx, grads[0][0] * scale, rtol=1e-6, atol=1e-12)
+        torch.testing.assert_close(gw, grads[0][1] * scale, rtol=1e-6, atol=1e-12)
+
+
+# ------------------------------------------------------------------ class shards on one GPU (partial-FC algebra through the real kernels)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("n_shards", [2, 3, 8])
+def test_class_shards_serial(cuda_device, dtype, n_shards):
+    from b200face import _lib
+    from b200face import head as H
+    from b200face.parallel import shard_bounds
+    B, C, D = 96, 2000, 512
+    x, w, y = _random_case(B, C, D, 11)
+    x, w = x.to(dtype).to(cuda_device), w.to(dtype).to(cuda_device)
+    yd = y.to(cuda_device)
+    cfg_o = oracle.HeadConfig(current_epoch=12, training=True, label_smoothing=0.05)
+    m_eff, s_eff = oracle.effective_margin_scale(cfg_o)
+    lib = _lib.load_library()
+
+    def run(bounds):
+        cfg = H._head_cfg(m_eff, s_eff, 0.05, False, C, _lib.ENGINE_AUTO)
+        stats = torch.zeros(B, 4, device=cuda_device)
+        saved = []
+        for lo, hi in bounds:
+            ws = w[lo:hi].contiguous()
+            inv_nx, inv_nw, rs, *_ = H._fwd_kernels(x, ws, yd, cfg, lo, False)
+            stats += rs                                      # == the all-reduce
+            saved.append((ws, inv_nx, inv_nw, lo))
+        lse = torch.empty(B, device=cuda_device); out2 = torch.empty(2, device=cuda_device)
+        _lib.check(lib.b200f_arcface_loss(_lib.ptr(stats), B, cfg, _lib.ptr(lse), _lib.ptr(out2), _lib.ptr(out2[1:]),
+                                          _lib.stream_ptr(cuda_device)), "loss")
+        out3 = torch.empty(3, device=cuda_device)
+        _lib.check(lib.b200f_arcface_hook_scale(_lib.ptr(out2[1:]), None, B, s_eff, 0, 1.0, 1, 0, _lib.ptr(out3),
+                                                _lib.stream_ptr(cuda_device)), "hook")
+        dxhat = torch.zeros(B, D, device=cuda_device)
+        dws = []
+        for ws, inv_nx, inv_nw, lo in saved:
+            part, dw = H._bwd_kernels(x, ws, yd, inv_nx, inv_nw, lse, out3, cfg, lo)
+            dxhat += part
+            dws.append(dw)
+        dx = H._normalize_bwd(x, saved[0][1], dxhat)
+        return float(out2[0]), dx, torch.cat(dws)
+
+    loss1, dx1, dw1 = run([(0, C)])
+    lossP, dxP, dwP = run([shard_bounds(C, n_shards, r) for r in range(n_shards)])
+    assert lossP == pytest.approx(loss1, rel=2e-6)
+    assert rel_err(dxP.cpu().numpy(), dx1.cpu().numpy()) < 5e-6
+    assert rel_err(dwP.cpu().numpy(), dw1.cpu().numpy()) < 5e-6
+    ref = oracle.head_forward_backward(x.float().cpu().numpy(), w.float().cpu().numpy(), y.numpy(), cfg_o)
+    tol = TOL_F32 if dtype == torch.float32 else TOL_BF16
+    assert lossP == pytest.approx(float(ref["loss"]), rel=tol)
+    assert rel_err(dwP.cpu().numpy(), ref["dw"]) < tol
+
+
+# ------------------------------------------------------------------ BASELINE sizes: size-independent properties
+@pytest.mark.parametrize("dtype", [torch.bfloat16])
+def test_cfg3_full_size_properties(cuda_device, dtype):
+    """cfg3: 512-d, 100k classes, batch 512.  The oracle cannot finish this in seconds, so check
+    properties the math guarantees: the normalise-backward makes every gradient row orthogonal to its
+    input row, gradients are linear in the upstream scalar, the loss is invariant to row scaling of x and
+    w (cosine logits), and the class-sharded evaluation agrees with the unsharded one."""
+    import b200face
+    B, C, D = 512, 100_000, 512
+    g = torch.Generator().manual_seed(1234)
+    w = (torch.randn(C, D, generator=g) * (2.0 / (C + D)) ** 0.5 * 2 ** 0.5).to(dtype)
+    x = torch.randn(B, D, generator=g)
+    y = torch.randint(0, C, (B,), generator=g)
+    x[:64] = 3.0 * w[y[:64]].float() + 0.3 * torch.randn(64, D, generator=g) * float(w.float().std())
+    x = x.to(dtype)
+    head = b200face.ArcMarginProduct(D, C).to(cuda_device)
+    head.update_epoch(10); head.train()
+    with torch.no_grad():
+        head.weight.copy_(w.float())
+    xg = x.to(cuda_device).requires_grad_(True)
+    loss = head.forward_loss(xg, y.to(cuda_device), 0.05)
+    loss.backward()
+    lv = float(loss)
+    assert np.isfinite(lv) and 0.8 * np.log(C) < lv < 1.2 * np.log(C)
+    dw = head.weight.grad
+    wf = head.weight.detach()
+    ortho = (dw * wf).sum(1).abs() / (dw.norm(dim=1) * wf.norm(dim=1) + 1e-30)
+    assert float(ortho.max()) < 2e-3                        # dW_j orthogonal to w_j
+    # scale invariance: cosine logits ignore row norms (power-of-two scaling is exact in bf16)
+    head2 = b200face.ArcMarginProduct(D, C).to(cuda_device)
+    head2.update_epoch(10); head2.train()
+    with torch.no_grad():
+        head2.weight.copy_(w.float() * 4.0)
+    loss2 = head2.forward_loss((x.float() * 0.5).to(dtype).to(cuda_device), y.to(cuda_device), 0.05)
+    assert float(loss2) == pytest.approx(lv, rel=1e-6)
+    # a 5k-class slice against the oracle: logits statistics of those columns via the eval-free path
+    sub = slice(0, 5000)
+    ysub = torch.randint(0, 5000, (64,), generator=g)
+    head3 = b200face.ArcMarginProduct(D, 5000).to(cuda_device)
+    head3.update_epoch(10); head3.train()
+    with torch.no_grad():
+        head3.weight.copy_(w[sub].float())
+    x3 = x[:64].to(cuda_device).requires_grad_(True)
+    l3 = head3.forward_loss(x3, ysub.to(cuda_device), 0.05)
+    l3.backward()
+    cfg = oracle.HeadConfig(current_epoch=10, training=True, label_smoothing=0.05)
+    ref = oracle.head_forward_backward(x[:64].float().numpy(), w[sub].float().numpy(), ysub.numpy(), cfg)
+    assert float(l3) == pytest.approx(float(ref["loss"]), rel=TOL_BF16)
+    assert rel_err(head3.weight.grad.cpu().numpy(), ref["dw"]) < TOL_BF16
