@@ -140,16 +140,16 @@ def run_b200(args):
     c_lo, c_hi = parallel.shard_bounds(C_total, world, rank)
     C_local = c_hi - c_lo
     x, w, y = synth_head(B, C_local, D, rank, dev, c_lo, C_total)
-    w.requires_grad_(True)
+    w_master = w.float().requires_grad_(True)        # fp32 master receives the fp32 dW; kernels read the bf16 copy
     mf, sf = head_schedule(EPOCH, 10, True, True, 0.0, 0.3)
     m_eff, s_eff = effective_margin_scale(32.0, 0.5, mf, sf, True)
     eng = engine_code(args.engine)
 
     def step(xin, stats=None):
         xin = xin.detach().requires_grad_(True)
-        w.grad = None
-        loss = arcface_loss(xin, w, y, m_eff=m_eff, s_eff=s_eff, label_smoothing=LS, class_offset=c_lo,
-                            num_classes_total=C_total, group=group, stats=stats, engine=eng)
+        w_master.grad = None
+        loss = arcface_loss(xin, w_master, y, compute_weight=w, m_eff=m_eff, s_eff=s_eff, label_smoothing=LS,
+                            class_offset=c_lo, num_classes_total=C_total, group=group, stats=stats, engine=eng)
         loss.backward()
         return loss
 
@@ -186,17 +186,18 @@ def run_b200(args):
     head = b200face.ArcMarginProduct(D, C_local) if world == 1 else None
     if head is not None:
         head = head.to(dev); head.update_epoch(EPOCH); head.train(); head.engine = eng
-        head.compute_dtype = torch.bfloat16
-        head.weight = torch.nn.Parameter(w.detach().clone())          # bf16 parameter: no per-step cast
+        head.compute_dtype = torch.bfloat16                           # fp32 parameter + cached bf16 shadow
+        with torch.no_grad():
+            head.weight.copy_(w.float())
     def e2e_step():
         xd = xh.to(dev, non_blocking=True); yd = yh.to(dev, non_blocking=True)
         if head is not None:
             head.zero_grad(set_to_none=True)
             l = head.forward_loss(xd.requires_grad_(True), yd, LS)
         else:
-            w.grad = None
-            l = arcface_loss(xd.requires_grad_(True), w, yd, m_eff=m_eff, s_eff=s_eff, label_smoothing=LS,
-                             class_offset=c_lo, num_classes_total=C_total, group=group, engine=eng)
+            w_master.grad = None
+            l = arcface_loss(xd.requires_grad_(True), w_master, yd, compute_weight=w, m_eff=m_eff, s_eff=s_eff,
+                             label_smoothing=LS, class_offset=c_lo, num_classes_total=C_total, group=group, engine=eng)
         l.backward()
         return float(l.item())                                        # D2H read of the step's result
     for _ in range(3):
@@ -249,7 +250,7 @@ def run_b200(args):
         "clocks": clocks,
         "roofline": roof,
         "kernel_ms": {k: round(v, 4) for k, v in kern.items()},
-        "loss": round(float(loss), 5),
+        "loss": round(float(loss.detach()), 5),
     }
     if world == 1 and not args.no_gallery:
         out["gallery"] = bench_gallery(dev, pk, eng)

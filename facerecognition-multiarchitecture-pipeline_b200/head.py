@@ -154,7 +154,10 @@ class _ArcFaceLossFn(torch.autograd.Function):
     hook scalar + K3 (+ all-reduce) + normalise-backward in backward."""
 
     @staticmethod
-    def forward(ctx, x, w, label, cfg: HeadCfg, class_offset, group, hook: _Hook, stats: HeadStats):
+    def forward(ctx, x, weight, w, label, cfg: HeadCfg, class_offset, group, hook: _Hook, stats: HeadStats):
+        # weight: the tensor autograd differentiates (fp32 master or already x.dtype);
+        # w: what the kernels read (x.dtype; == weight or its cached bf16 shadow)
+        ctx.w_dtype = weight.dtype
         inv_nx, inv_nw, row_stats, row_best, row_argmax, cos_minmax, nan_flag, _ = _fwd_kernels(
             x, w, label, cfg, class_offset, False)
         if group is not None:
@@ -189,7 +192,7 @@ class _ArcFaceLossFn(torch.autograd.Function):
             parallel.reduce_dxhat(dxhat, ctx.group)              # one SUM all-reduce of [B,D]
         dx = _normalize_bwd(x, inv_nx, dxhat)
         ctx.stats.dx_f32 = dx
-        return dx.to(x.dtype), dw.to(w.dtype), None, None, None, None, None, None
+        return dx.to(x.dtype), dw.to(ctx.w_dtype), None, None, None, None, None, None, None
 
 
 class _ArcLogitsFn(torch.autograd.Function):
@@ -197,7 +200,8 @@ class _ArcLogitsFn(torch.autograd.Function):
     upstream dL/dlogits and runs the same K3 kernels with G = dlogits * s_eff * dphi * clamp-mask."""
 
     @staticmethod
-    def forward(ctx, x, w, label, cfg: HeadCfg, hook: _Hook, stats: HeadStats):
+    def forward(ctx, x, weight, w, label, cfg: HeadCfg, hook: _Hook, stats: HeadStats):
+        ctx.w_dtype = weight.dtype
         inv_nx, inv_nw, _rs, row_best, row_argmax, cos_minmax, nan_flag, logits = _fwd_kernels(
             x, w, label, cfg, 0, True)
         stats.row_best, stats.row_argmax = row_best, row_argmax
@@ -227,21 +231,28 @@ class _ArcLogitsFn(torch.autograd.Function):
         lse_dummy = torch.zeros(1, dtype=torch.float32, device=x.device)
         dxhat, dw = _bwd_kernels(x, w, label, inv_nx, inv_nw, lse_dummy, out3, cfg, 0, dlogits=dlogits)
         dx = _normalize_bwd(x, inv_nx, dxhat)
-        return dx.to(x.dtype), dw.to(w.dtype), None, None, None, None
+        ctx.stats.dx_f32 = dx
+        return dx.to(x.dtype), dw.to(ctx.w_dtype), None, None, None, None, None
 
 
 def arcface_loss(x, weight, label, *, m_eff, s_eff, label_smoothing=0.05, easy_margin=False,
                  class_offset=0, num_classes_total=None, group=None, hook: Optional[_Hook] = None,
-                 stats: Optional[HeadStats] = None, engine=_lib.ENGINE_AUTO):
+                 stats: Optional[HeadStats] = None, engine=_lib.ENGINE_AUTO,
+                 compute_weight: Optional[torch.Tensor] = None):
     """Functional fused head: mean label-smoothed CE of the ArcFace logits of (x, weight).
-    x [B,D], weight [C_local,D] (same dtype: fp32 or bf16, CUDA), label [B] int64 global ids."""
-    require_cuda(x, weight, label)
-    if x.dtype != weight.dtype:
-        raise TypeError(f"x ({x.dtype}) and weight ({weight.dtype}) must share a dtype")
+    x [B,D] fp32 / bf16 CUDA, weight [C_local,D] (the tensor that receives the gradient: an fp32 master
+    keeps an fp32 dW even when the kernels compute in bf16), label [B] int64 global ids.
+    compute_weight: the copy of weight in x.dtype the kernels read (default: weight itself, or a cast)."""
+    require_cuda(x, weight, label, compute_weight)
+    if compute_weight is None:
+        compute_weight = weight.detach() if weight.dtype == x.dtype else weight.detach().to(x.dtype)
+    if x.dtype != compute_weight.dtype:
+        raise TypeError(f"x ({x.dtype}) and compute_weight ({compute_weight.dtype}) must share a dtype")
     cfg = _head_cfg(m_eff, s_eff, label_smoothing, easy_margin,
                     num_classes_total if num_classes_total is not None else weight.shape[0], engine)
-    return _ArcFaceLossFn.apply(x.contiguous(), weight.contiguous(), label.contiguous().to(torch.int64), cfg,
-                                class_offset, group, hook or _Hook(), stats if stats is not None else HeadStats())
+    return _ArcFaceLossFn.apply(x.contiguous(), weight, compute_weight.contiguous(),
+                                label.contiguous().to(torch.int64), cfg, class_offset, group, hook or _Hook(),
+                                stats if stats is not None else HeadStats())
 
 
 class ArcMarginProduct(nn.Module):
@@ -290,23 +301,27 @@ class ArcMarginProduct(nn.Module):
         return m_eff, s_eff
 
     def _operands(self, input):
+        """(x, weight, w_compute): x in the compute dtype, the differentiated parameter, and the copy of
+        it the kernels read -- the parameter itself, or a bf16 shadow re-made only when the parameter
+        changes (optimizer step / load_state_dict bump its version counter)."""
         require_cuda(input, self.weight)
         dt = self.compute_dtype or (input.dtype if input.dtype in (torch.float32, torch.bfloat16)
                                     else torch.float32)
         x = input.to(dt).contiguous()
         if self.weight.dtype == dt:
-            w = self.weight
-        else:
-            w = _CastWeight.apply(self.weight, dt)       # autograd-visible cast, grad returns in fp32
-        return x, w
+            return x, self.weight, self.weight.detach()
+        key = (self.weight._version, self.weight.data_ptr(), dt)
+        if self._w_shadow is None or self._w_shadow[0] != key:
+            self._w_shadow = (key, self.weight.detach().to(dt))
+        return x, self.weight, self._w_shadow[1]
 
     def forward(self, input, label):
         """Scaled logits [B,C] fp32 (compatibility path; stores the logits)."""
         m_eff, s_eff = self._step_schedule()
-        x, w = self._operands(input)
+        x, weight, w = self._operands(input)
         cfg = _head_cfg(m_eff, s_eff, 0.0, self.easy_margin, self.out_feats, self.engine)
         self.last_stats = HeadStats()
-        return _ArcLogitsFn.apply(x, w.contiguous(), label.contiguous().to(torch.int64), cfg, self._hook,
+        return _ArcLogitsFn.apply(x, weight, w.contiguous(), label.contiguous().to(torch.int64), cfg, self._hook,
                                   self.last_stats)
 
     def forward_loss(self, input, label, label_smoothing=0.05, return_pred=False):
@@ -314,11 +329,11 @@ class ArcMarginProduct(nn.Module):
         the logits never reach HBM.  return_pred: also return outputs.max(1) indices
         (hyperparameter_tuning.py:1001)."""
         m_eff, s_eff = self._step_schedule()
-        x, w = self._operands(input)
+        x, weight, w = self._operands(input)
         self.last_stats = HeadStats()
-        loss = arcface_loss(x, w, label, m_eff=m_eff, s_eff=s_eff, label_smoothing=label_smoothing,
+        loss = arcface_loss(x, weight, label, m_eff=m_eff, s_eff=s_eff, label_smoothing=label_smoothing,
                             easy_margin=self.easy_margin, hook=self._hook, stats=self.last_stats,
-                            engine=self.engine)
+                            engine=self.engine, compute_weight=w)
         if return_pred:
             return loss, self.last_stats.row_argmax
         return loss
@@ -356,17 +371,6 @@ class ArcMarginProduct(nn.Module):
             'min_cos_theta': self.min_cos_theta,
             'easy_margin_used': self.easy_margin_used if self.easy_margin else False,
         }
-
-
-class _CastWeight(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, w, dtype):
-        ctx.src_dtype = w.dtype
-        return w.to(dtype)
-
-    @staticmethod
-    def backward(ctx, g):
-        return g.to(ctx.src_dtype), None
 
 
 class ArcFaceNet(nn.Module):

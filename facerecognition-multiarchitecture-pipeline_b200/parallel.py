@@ -111,9 +111,9 @@ class ShardedArcMarginProduct(torch.nn.Module):
         from .head import arcface_loss, HeadStats
         hd = self.local
         m_eff, s_eff = hd._step_schedule()
-        x, w = hd._operands(input)
+        x, weight, w = hd._operands(input)
         hd.last_stats = HeadStats()
-        loss = arcface_loss(x, w, label, m_eff=m_eff, s_eff=s_eff, label_smoothing=label_smoothing,
+        loss = arcface_loss(x, weight, label, compute_weight=w, m_eff=m_eff, s_eff=s_eff, label_smoothing=label_smoothing,
                             easy_margin=hd.easy_margin, class_offset=self.lo,
                             num_classes_total=self.out_feats_total, group=self.group, hook=hd._hook,
                             stats=hd.last_stats, engine=hd.engine)

@@ -137,13 +137,16 @@ def test_arcfacenet_hook_arms_after_first_forward(cuda_device):
 
 
 # ------------------------------------------------------------------ oracle on seeded inputs
-def _random_case(B, C, D, seed, planted=0.125):
+def _random_case(B, C, D, seed, planted=0.125, noise=1.0):
+    """SURVEY 8d recipe scaled down.  noise=1.0 puts the planted rows at cos ~ 0.95 of their class centre;
+    tighter planting (noise 0.3 -> cos 0.995, sin(theta) 0.1) is ill-conditioned in fp32: the reference's own
+    fp32 autograd is then 1.4e-5 away from the fp64 closed form (measured), i.e. above the 1e-5 bar itself."""
     g = torch.Generator().manual_seed(seed)
     w = torch.randn(C, D, generator=g) * (2.0 / (C + D)) ** 0.5 * 2 ** 0.5
     x = torch.randn(B, D, generator=g)
     y = torch.randint(0, C, (B,), generator=g)
     n = int(B * planted)
-    x[:n] = 3.0 * w[y[:n]] + 0.3 * torch.randn(n, D, generator=g) * w.std()
+    x[:n] = 3.0 * w[y[:n]] + noise * torch.randn(n, D, generator=g) * w.std()
     return x, w, y
 
 
