@@ -63,6 +63,10 @@ PROTOTYPES = {
     "b200f_gallery_topk": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int64,
                                    c_int64, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_size_t, c_void_p]),
+    "b200f_umma_selftest": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                    c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "b200f_umma_timeout_flag": (c_int, [c_int]),
+    "b200f_umma_set_option": (c_int, [c_int, c_int]),
     "b200f_gallery_merge": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_float,
                                     c_void_p, c_void_p, c_void_p, c_void_p]),
 }

@@ -127,7 +127,7 @@ l2norm_rows_kernel(const TI* __restrict__ in, int64_t rows, int dim, float eps,
 template <typename T>
 __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
 l2norm_bwd_kernel(const T* __restrict__ v, const float* __restrict__ inv_norm,
-                  const float* __restrict__ dvhat, int64_t rows, int dim, float* __restrict__ dv) {
+                  const float* dvhat, int64_t rows, int dim, float* dv) {   // dv may alias dvhat (in place)
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -143,7 +143,7 @@ l2norm_bwd_kernel(const T* __restrict__ v, const float* __restrict__ inv_norm,
 
 // Single block.  row_stats [B,4] -> lse[B], loss (mean), pq_norm2.  Arithmetic in double: only B
 // rows, and sum_j (p-q)^2 cancels badly in fp32 once the target probability approaches 1.
-__global__ void __launch_bounds__(1024)
+static __global__ void __launch_bounds__(1024)
 loss_kernel(const float* __restrict__ row_stats, int64_t B, float s_eff, float ls_eps,
             double C_total, float* __restrict__ lse_out, float* __restrict__ loss_out,
             float* __restrict__ pq_norm2_out) {
@@ -179,7 +179,7 @@ loss_kernel(const float* __restrict__ row_stats, int64_t B, float s_eff, float l
 }
 
 // src/face_models.py:538-567 on device scalars.
-__global__ void hook_scale_kernel(const float* __restrict__ pq_norm2, const float* __restrict__ upstream,
+static __global__ void hook_scale_kernel(const float* __restrict__ pq_norm2, const float* __restrict__ upstream,
                                   double B, float s_eff, int hook_enabled, float max_grad_norm,
                                   int phase, int epoch, float* __restrict__ out3) {
   const double up = (upstream != nullptr) ? (double)*upstream : 1.0;

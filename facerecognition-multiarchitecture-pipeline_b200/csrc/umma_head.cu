@@ -1,19 +1,354 @@
-// tcgen05 engine -- placeholder until the UMMA kernels land (next commit).
+// tcgen05 / TMEM / TMA engine for the ArcFace head (bf16 inputs): host side.
+//   K2  forward statistics : gemm_kernel<K,K,EpiFwd>           x[B,D] . w[C,D]^T
+//   K3a logit gradient     : gemm_kernel<K,K,EpiBwdG>          recompute + G1/G2 (16-bit, L2-resident chunk)
+//   K3b dW_hat = G1^T x    : gemm_kernel<MN,MN,EpiStore>       then normalise-backward in place
+//   K3c dx_hat = G2 w      : gemm_kernel<K,MN,EpiStore> split-K, then a fixed-order reduction
+// ALL tcgen05 kernels of the library live in this one translation unit (g_umma_timeout_flag).
 #include "umma_api.cuh"
+#include "umma_epilogues.cuh"
+#include "rowops.cuh"
+
+#include <cudaTypedefs.h>
+#include <mutex>
 
 namespace b200f {
 namespace umma {
 
-bool head_engine_selected(int64_t, int64_t, int, int, int, bool) { return false; }
-size_t head_workspace_bytes(int64_t, int64_t, int, int, int) { return 0; }
-int head_fwd(const void*, const void*, const float*, const float*, const int64_t*, int64_t, int64_t, int64_t, int,
-             const b200f_head_cfg*, float*, float*, int64_t*, float*, int32_t*, char*, size_t, cudaStream_t) {
-  return fail(B200F_ERR_UNSUPPORTED, "tcgen05 engine not built");
+// ---- TMA descriptor encode (driver entry point fetched through the runtime: no libcuda link) -----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
 }
-int head_bwd(const void*, const void*, const float*, const float*, const int64_t*, const float*, const float*,
-             int64_t, int64_t, int64_t, int, const b200f_head_cfg*, float*, float*, char*, size_t, cudaStream_t) {
-  return fail(B200F_ERR_UNSUPPORTED, "tcgen05 engine not built");
+
+// 2-D row-major 16-bit tensor [outer, inner] (inner contiguous, row stride ld elements), 128B swizzle.
+static int make_tmap(CUtensorMap* m, const void* base, int64_t inner, int64_t outer, int64_t ld, int box_inner,
+                     int box_outer) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(B200F_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld % 8))
+    return fail(B200F_ERR_ARG, "TMA operand must be 16B aligned with a row stride that is a multiple of 8 elements");
+  cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(B200F_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return B200F_OK;
+}
+// operand whose rows are the m/n index and whose contiguous axis is k
+static int tmap_kmajor(CUtensorMap* m, const void* base, int64_t rows, int64_t K, int64_t ld, int box_rows) {
+  return make_tmap(m, base, K, rows, ld, BLOCK_K, box_rows);
+}
+// operand whose rows are the k index and whose contiguous axis is m/n
+static int tmap_mnmajor(CUtensorMap* m, const void* base, int64_t MN, int64_t K, int64_t ld) {
+  return make_tmap(m, base, MN, K, ld, 64, BLOCK_K);
+}
+
+static GemmParams gemm_params(int M, int N, int K, int k_splits, bool a_mn, bool b_mn, uint32_t a_fmt, uint32_t b_fmt) {
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.m_tiles = (int)ceil_div(M, BLOCK_M);
+  p.n_tiles = (int)ceil_div(N, BLOCK_N);
+  int kchunks = (int)ceil_div(K, BLOCK_K);
+  if (k_splits > kchunks) k_splits = kchunks;
+  if (k_splits < 1) k_splits = 1;
+  p.k_per_split = (int)ceil_div(kchunks, k_splits) * BLOCK_K;
+  p.k_splits = (int)ceil_div(K, p.k_per_split);
+  // K-major: SBO = 1024 (8 rows x 128 B), k-step 32 B.  MN-major: LBO = 8 KB (next 64-wide block),
+  // SBO = 1024 (next 8 k-rows), k-step = 16 rows x 128 B.
+  p.a_lbo = a_mn ? MN_BLOCK_BYTES : 0; p.a_sbo = 1024; p.a_kstep = a_mn ? 2048 : 32;
+  p.b_lbo = b_mn ? MN_BLOCK_BYTES : 0; p.b_sbo = 1024; p.b_kstep = b_mn ? 2048 : 32;
+  p.idesc = make_idesc(a_fmt, b_fmt, a_mn, b_mn, BLOCK_M, BLOCK_N);
+  return p;
+}
+
+template <bool A_MN, bool B_MN, class Epi>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                       const typename Epi::Params& ep, cudaStream_t st, const char* what) {
+  auto kern = gemm_kernel<A_MN, B_MN, Epi>;
+  B200F_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  const int work = p.m_tiles * p.n_tiles * p.k_splits;
+  int grid = num_sms();
+  if (grid > work) grid = work;
+  kern<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tb, p, ep);
+  B200F_LAUNCH_OK(what);
+  return B200F_OK;
+}
+
+// One warp per row: sum the per-tile partial records in a fixed order (bitwise reproducible).
+__global__ void __launch_bounds__(256)
+reduce_row_partials_kernel(const float* __restrict__ part, int n_parts, int64_t B, const float* __restrict__ cos_part,
+                           int n_cos, float* __restrict__ row_stats, float* __restrict__ row_best,
+                           int64_t* __restrict__ row_argmax, float* __restrict__ cos_minmax) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row < B) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, best = -INFINITY;
+    int bi = INT32_MAX;
+    for (int c = lane; c < n_parts; c += 32) {
+      const float* src = part + ((int64_t)c * B + row) * PART_COLS;
+      s0 += src[0]; s1 += src[1]; s2 += src[2]; s3 += src[3];
+      const int idx = reinterpret_cast<const int32_t*>(src)[5];
+      if (idx >= 0 && (src[4] > best || (src[4] == best && idx < bi))) { best = src[4]; bi = idx; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o); s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) {
+      float* dst = row_stats + row * B200F_STAT_COLS;
+      dst[B200F_STAT_SUMEXP] = s0; dst[B200F_STAT_SUMEXP2] = s1; dst[B200F_STAT_ZTARGET] = s2; dst[B200F_STAT_SUMZ] = s3;
+      if (row_best) row_best[row] = best;
+      if (row_argmax) row_argmax[row] = (bi == INT32_MAX) ? -1 : bi;
+    }
+  }
+  if (blockIdx.x == 0 && cos_minmax != nullptr) {
+    __shared__ float smin[8], smax[8];
+    float cmin = INFINITY, cmax = -INFINITY;
+    for (int i = threadIdx.x; i < n_cos; i += blockDim.x) { cmin = fminf(cmin, cos_part[2 * i]); cmax = fmaxf(cmax, cos_part[2 * i + 1]); }
+    cmin = warp_min(cmin); cmax = warp_max(cmax);
+    if (lane == 0) { smin[threadIdx.x >> 5] = cmin; smax[threadIdx.x >> 5] = cmax; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < 8; ++w) { cmin = fminf(cmin, smin[w]); cmax = fmaxf(cmax, smax[w]); }
+      cos_minmax[0] = cmin; cos_minmax[1] = cmax;
+    }
+  }
+}
+
+__global__ void reduce_splits_kernel(const float* __restrict__ part, int n_splits, int64_t n, float* __restrict__ dst,
+                                     int accumulate, float scale) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  float4 s = accumulate ? *reinterpret_cast<const float4*>(dst + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < n_splits; ++k) {
+    const float4 v = *reinterpret_cast<const float4*>(part + (int64_t)k * n + i);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  s.x = fmaf(acc.x, scale, s.x); s.y = fmaf(acc.y, scale, s.y); s.z = fmaf(acc.z, scale, s.z); s.w = fmaf(acc.w, scale, s.w);
+  *reinterpret_cast<float4*>(dst + i) = s;
+}
+
+// ---- plan -------------------------------------------------------------------------------------------
+struct Plan {
+  int m_tiles, n_tiles;
+  size_t off_part, off_cos;
+  int64_t Cc, ldg; int n_chunks, dx_splits;
+  size_t off_G1, off_G2, off_dxpart;
+  size_t total;
+};
+
+static Plan make_plan(int64_t B, int64_t C, int D) {
+  Plan pl{};
+  pl.m_tiles = (int)ceil_div(B, BLOCK_M);
+  pl.n_tiles = (int)ceil_div(C, BLOCK_N);
+  size_t off = 0;
+  pl.off_part = off; off += align_up(sizeof(float) * (size_t)pl.n_tiles * B * PART_COLS, 256);
+  pl.off_cos = off;  off += align_up(sizeof(float) * 2 * 4 * (size_t)pl.n_tiles * pl.m_tiles, 256);
+  const size_t fwd_total = off;
+  // backward: both 16-bit copies of the logit-gradient chunk should stay L2-resident: <= 64 MB together
+  int64_t cc_max = ((int64_t)(64u << 20) / 4 / B) / BLOCK_N * BLOCK_N;
+  if (cc_max < BLOCK_N) cc_max = BLOCK_N;
+  pl.n_chunks = (int)ceil_div(C, cc_max);
+  pl.Cc = ceil_div(ceil_div(C, pl.n_chunks), BLOCK_N) * BLOCK_N;
+  pl.n_chunks = (int)ceil_div(C, pl.Cc);
+  pl.ldg = pl.Cc;
+  const int out_tiles = pl.m_tiles * (int)ceil_div(D, BLOCK_N);
+  int splits = num_sms() / out_tiles;
+  if (splits < 1) splits = 1;
+  const int kchunks = (int)(pl.Cc / BLOCK_K);
+  if (splits > kchunks) splits = kchunks;
+  pl.dx_splits = splits;
+  off = 0;
+  pl.off_G1 = off;     off += align_up(2 * (size_t)B * pl.ldg, 1024);
+  pl.off_G2 = off;     off += align_up(2 * (size_t)B * pl.ldg, 1024);
+  pl.off_dxpart = off; off += align_up(sizeof(float) * (size_t)splits * B * D, 256);
+  pl.total = (off > fwd_total ? off : fwd_total) + 1024;
+  return pl;
+}
+
+static bool device_is_sm100() {
+  static int cached = -1;
+  if (cached < 0) {
+    int dev = 0; cudaDeviceProp prop;
+    cached = (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess &&
+              prop.major == 10) ? 1 : 0;
+  }
+  return cached == 1;
+}
+
+bool head_engine_selected(int64_t B, int64_t C, int D, int dtype, int engine, bool wants_logits) {
+  if (engine == B200F_ENGINE_SIMT) return false;
+  if (dtype != B200F_BF16 || wants_logits) return false;
+  if (D % 8 != 0 || B >= (int64_t)1 << 30 || C >= (int64_t)1 << 30) return false;
+  if (!device_is_sm100()) return false;
+  return true;
+}
+
+size_t head_workspace_bytes(int64_t B, int64_t C, int D, int dtype, int engine) {
+  if (engine == B200F_ENGINE_SIMT || dtype != B200F_BF16) return 0;
+  return make_plan(B, C, D).total;
+}
+
+static char* ws_align(char* ws) { return reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~(uintptr_t)1023); }
+
+int head_fwd(const void* x, const void* w, const float* inv_nx, const float* inv_nw, const int64_t* label, int64_t B,
+             int64_t C, int64_t class_offset, int D, const b200f_head_cfg* cfg, float* row_stats, float* row_best,
+             int64_t* row_argmax, float* cos_minmax, int32_t* nan_flag, char* ws, size_t ws_bytes, cudaStream_t st) {
+  const Plan pl = make_plan(B, C, D);
+  if (ws_bytes < pl.total) return fail(B200F_ERR_WORKSPACE, "umma head_fwd: workspace too small");
+  ws = ws_align(ws);
+  CUtensorMap ta, tb;
+  int rc = tmap_kmajor(&ta, x, B, D, D, BLOCK_M); if (rc) return rc;
+  rc = tmap_kmajor(&tb, w, C, D, D, BLOCK_N); if (rc) return rc;
+  GemmParams p = gemm_params((int)B, (int)C, D, 1, false, false, FMT_BF16, FMT_BF16);
+  EpiFwd::Params ep{};
+  ep.inv_nx = inv_nx; ep.inv_nw = inv_nw; ep.label = label; ep.B = B; ep.C = C; ep.class_offset = class_offset;
+  ep.hm = HeadMath{cfg->m_eff, cfg->s_eff, cfg->easy_margin};
+  ep.part = reinterpret_cast<float*>(ws + pl.off_part);
+  ep.cos_part = reinterpret_cast<float*>(ws + pl.off_cos);
+  ep.nan_flag = nan_flag;
+  rc = launch_gemm<false, false, EpiFwd>(ta, tb, p, ep, st, "umma K2 arcface_fwd");
+  if (rc) return rc;
+  reduce_row_partials_kernel<<<(unsigned)ceil_div(B, 8), 256, 0, st>>>(ep.part, pl.n_tiles, B, ep.cos_part,
+                                                                      4 * pl.n_tiles * pl.m_tiles, row_stats, row_best,
+                                                                      row_argmax, cos_minmax);
+  B200F_LAUNCH_OK("reduce_row_partials_kernel");
+  return B200F_OK;
+}
+
+static bool g_fp16_logit_grad = false;   // set by b200f_umma_set_option(0, 1) once mixed f16 x bf16 MMA is validated
+
+int head_bwd(const void* x, const void* w, const float* inv_nx, const float* inv_nw, const int64_t* label,
+             const float* lse, const float* grad_scale, int64_t B, int64_t C, int64_t class_offset, int D,
+             const b200f_head_cfg* cfg, float* dxhat, float* dw, char* ws, size_t ws_bytes, cudaStream_t st) {
+  const Plan pl = make_plan(B, C, D);
+  if (ws_bytes < pl.total) return fail(B200F_ERR_WORKSPACE, "umma head_bwd: workspace too small");
+  ws = ws_align(ws);
+  uint16_t* G1 = reinterpret_cast<uint16_t*>(ws + pl.off_G1);
+  uint16_t* G2 = reinterpret_cast<uint16_t*>(ws + pl.off_G2);
+  float* dxpart = reinterpret_cast<float*>(ws + pl.off_dxpart);
+  const bool fp16g = g_fp16_logit_grad;
+  // fp16 needs its range centred: |G| <= |grad_scale| * max(inv) * dphi; 2^20 keeps typical values normal
+  const float g_scale = fp16g ? 1048576.0f : 1.0f;
+  const uint32_t gfmt = fp16g ? FMT_F16 : FMT_BF16;
+  CUtensorMap tx_k, tx_mn;
+  int rc = tmap_kmajor(&tx_k, x, B, D, D, BLOCK_M); if (rc) return rc;
+  rc = tmap_mnmajor(&tx_mn, x, D, B, D); if (rc) return rc;
+  int chunk_no = 0;
+  for (int64_t c0 = 0; c0 < C; c0 += pl.Cc, ++chunk_no) {
+    const int64_t cnt = (C - c0 < pl.Cc) ? (C - c0) : pl.Cc;
+    const uint16_t* wc = static_cast<const uint16_t*>(w) + c0 * D;
+    // --- K3a: logit gradient of the chunk
+    CUtensorMap tw_k;
+    rc = tmap_kmajor(&tw_k, wc, cnt, D, D, BLOCK_N); if (rc) return rc;
+    GemmParams pg = gemm_params((int)B, (int)cnt, D, 1, false, false, FMT_BF16, FMT_BF16);
+    if (fp16g) {
+      EpiBwdG<true>::Params eg{inv_nx, inv_nw, label, lse, grad_scale, B, C, class_offset, c0,
+                               HeadMath{cfg->m_eff, cfg->s_eff, cfg->easy_margin}, cfg->label_smoothing,
+                               1.0f / (float)cfg->num_classes_total, g_scale, G1, G2, pl.ldg};
+      rc = launch_gemm<false, false, EpiBwdG<true>>(tx_k, tw_k, pg, eg, st, "umma K3a logit-grad (fp16)");
+    } else {
+      EpiBwdG<false>::Params eg{inv_nx, inv_nw, label, lse, grad_scale, B, C, class_offset, c0,
+                                HeadMath{cfg->m_eff, cfg->s_eff, cfg->easy_margin}, cfg->label_smoothing,
+                                1.0f / (float)cfg->num_classes_total, g_scale, G1, G2, pl.ldg};
+      rc = launch_gemm<false, false, EpiBwdG<false>>(tx_k, tw_k, pg, eg, st, "umma K3a logit-grad (bf16)");
+    }
+    if (rc) return rc;
+    // --- K3b: dW_hat[c0 + m, :] = sum_b G1[b, m] x[b, :]
+    CUtensorMap tg1_mn;
+    rc = tmap_mnmajor(&tg1_mn, G1, cnt, B, pl.ldg); if (rc) return rc;
+    GemmParams pw = gemm_params((int)cnt, D, (int)B, 1, true, true, gfmt, FMT_BF16);
+    EpiStore::Params ew{dw, (int64_t)D, 0, c0, 1.0f / g_scale};
+    rc = launch_gemm<true, true, EpiStore>(tg1_mn, tx_mn, pw, ew, st, "umma K3b dW");
+    if (rc) return rc;
+    // --- K3c: dx_hat partials = G2[:, k-range] w[c0 + k-range, :]
+    CUtensorMap tg2_k, tw_mn;
+    rc = tmap_kmajor(&tg2_k, G2, B, cnt, pl.ldg, BLOCK_M); if (rc) return rc;
+    rc = tmap_mnmajor(&tw_mn, wc, D, cnt, D); if (rc) return rc;
+    GemmParams px = gemm_params((int)B, D, (int)cnt, pl.dx_splits, false, true, gfmt, FMT_BF16);
+    EpiStore::Params ex{dxpart, (int64_t)D, B * (int64_t)D, 0, 1.0f};
+    rc = launch_gemm<false, true, EpiStore>(tg2_k, tw_mn, px, ex, st, "umma K3c dX");
+    if (rc) return rc;
+    const int64_t n = B * (int64_t)D;
+    reduce_splits_kernel<<<(unsigned)ceil_div(n / 4, 256), 256, 0, st>>>(dxpart, px.k_splits, n, dxhat, chunk_no > 0,
+                                                                        1.0f / g_scale);
+    B200F_LAUNCH_OK("umma reduce_splits_kernel");
+  }
+  // normalise-backward of the weight rows, in place: dw <- inv_nw * (dw_hat - w_hat <w_hat, dw_hat>)
+  rowops::l2norm_bwd_kernel<__nv_bfloat16><<<(unsigned)ceil_div(C, rowops::ROWS_PER_BLOCK), rowops::ROWS_PER_BLOCK * 32, 0, st>>>(
+      static_cast<const __nv_bfloat16*>(w), inv_nw, dw, C, D, dw);
+  B200F_LAUNCH_OK("l2norm_bwd_kernel (weights)");
+  return B200F_OK;
 }
 
 }  // namespace umma
 }  // namespace b200f
+
+using namespace b200f;
+using namespace b200f::umma;
+
+extern "C" {
+
+// Self-test / probe of the GEMM core: out[M,N] (fp32) = sum_k A(m,k) B(n,k) for every operand layout.
+//   a_mn / b_mn: 0 = K-major (a is [M,K] row-major), 1 = MN-major (a is [K,M] row-major)
+//   a_fp16: the A operand holds fp16 instead of bf16 (mixed-format MMA probe); lbo/sbo/kstep < 0 = defaults
+int b200f_umma_selftest(const void* a, const void* b, float* out, int M, int N, int K, int a_mn, int b_mn,
+                        int a_fp16, int k_splits, int a_lbo, int a_sbo, int a_kstep, int b_lbo, int b_sbo,
+                        int b_kstep, void* stream) {
+  if (!a || !b || !out || M <= 0 || N <= 0 || K <= 0) return fail(B200F_ERR_ARG, "umma_selftest: bad argument");
+  if (!device_is_sm100()) return fail(B200F_ERR_UNSUPPORTED, "umma_selftest: device is not sm_100");
+  CUtensorMap ta, tb;
+  int rc = a_mn ? tmap_mnmajor(&ta, a, M, K, M) : tmap_kmajor(&ta, a, M, K, K, BLOCK_M);
+  if (rc) return rc;
+  rc = b_mn ? tmap_mnmajor(&tb, b, N, K, N) : tmap_kmajor(&tb, b, N, K, K, BLOCK_N);
+  if (rc) return rc;
+  GemmParams p = gemm_params(M, N, K, k_splits, a_mn != 0, b_mn != 0, a_fp16 ? FMT_F16 : FMT_BF16, FMT_BF16);
+  if (a_lbo >= 0) p.a_lbo = a_lbo;
+  if (a_sbo >= 0) p.a_sbo = a_sbo;
+  if (a_kstep >= 0) p.a_kstep = a_kstep;
+  if (b_lbo >= 0) p.b_lbo = b_lbo;
+  if (b_sbo >= 0) p.b_sbo = b_sbo;
+  if (b_kstep >= 0) p.b_kstep = b_kstep;
+  EpiStore::Params ep{out, (int64_t)N, (int64_t)M * N, 0, 1.0f};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!a_mn && !b_mn) return launch_gemm<false, false, EpiStore>(ta, tb, p, ep, st, "umma selftest KK");
+  if (a_mn && b_mn) return launch_gemm<true, true, EpiStore>(ta, tb, p, ep, st, "umma selftest MM");
+  if (!a_mn && b_mn) return launch_gemm<false, true, EpiStore>(ta, tb, p, ep, st, "umma selftest KM");
+  return fail(B200F_ERR_UNSUPPORTED, "umma_selftest: A MN-major with B K-major is not instantiated");
+}
+
+// Reads (and optionally clears) the pipeline-timeout flag.  Synchronises: test / bench use only.
+int b200f_umma_timeout_flag(int reset) {
+  unsigned int v = 0;
+  if (cudaMemcpyFromSymbol(&v, g_umma_timeout_flag, sizeof(v)) != cudaSuccess) return -1;
+  if (reset) { unsigned int z = 0; cudaMemcpyToSymbol(g_umma_timeout_flag, &z, sizeof(z)); }
+  return (int)v;
+}
+
+// option 0: logit-gradient operand format of K3 (0 = bf16, 1 = fp16 x bf16 mixed-format MMA)
+int b200f_umma_set_option(int option, int value) {
+  if (option == 0) { g_fp16_logit_grad = (value != 0); return B200F_OK; }
+  return fail(B200F_ERR_ARG, "umma_set_option: unknown option %d", option);
+}
+
+}  // extern "C"

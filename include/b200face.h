@@ -160,6 +160,19 @@ int b200f_gallery_merge(const int64_t* idx_all, const float* score_all, int P, i
                         int metric, float thresh,
                         int64_t* idx, float* score, uint8_t* accept, void* stream);
 
+/* ---- tcgen05 engine: self-test and diagnostics (tests/test_gpu_umma.py, bench.py) ----------------
+ * b200f_umma_selftest: out[M,N] fp32 = sum_k A(m,k) B(n,k) through the TMA + tcgen05 + TMEM GEMM core,
+ *   for K-major (x_mn = 0: [rows,K] row-major) and MN-major (x_mn = 1: [K,rows] row-major) operands,
+ *   bf16 x bf16 or (a_fp16) fp16 x bf16; with k_splits > 1 out is [k_splits, M, N] partial sums.
+ *   Descriptor byte offsets < 0 select the defaults.
+ * b200f_umma_timeout_flag: 1 if a bounded pipeline wait ever expired (synchronises; reset clears it).
+ * b200f_umma_set_option(0, v): logit-gradient operand of K3: 0 = bf16, 1 = fp16 (mixed-format MMA). */
+int b200f_umma_selftest(const void* a, const void* b, float* out, int M, int N, int K, int a_mn, int b_mn,
+                        int a_fp16, int k_splits, int a_lbo, int a_sbo, int a_kstep, int b_lbo, int b_sbo,
+                        int b_kstep, void* stream);
+int b200f_umma_timeout_flag(int reset);
+int b200f_umma_set_option(int option, int value);
+
 #ifdef __cplusplus
 }
 #endif
