@@ -186,7 +186,8 @@ def run_b200(args):
     head = b200face.ArcMarginProduct(D, C_local) if world == 1 else None
     if head is not None:
         head = head.to(dev); head.update_epoch(EPOCH); head.train(); head.engine = eng
-        head.compute_dtype = torch.bfloat16                           # fp32 parameter + cached bf16 shadow
+        head.compute_dtype = torch.bfloat16
+        head.cache_weight_prep = False                                # training changes W every step: K1(W) is timed
         with torch.no_grad():
             head.weight.copy_(w.float())
     def e2e_step():

@@ -12,7 +12,7 @@ from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int
 
 import torch
 
-F32, BF16 = 0, 1
+F32, BF16, F16N = 0, 1, 2
 METRIC_L2EPS, METRIC_COS = 0, 1
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
 STAT_SUMEXP, STAT_SUMEXP2, STAT_ZTARGET, STAT_SUMZ, STAT_COLS = 0, 1, 2, 3, 4
@@ -29,7 +29,7 @@ class HeadCfg(Structure):
     """struct b200f_head_cfg"""
     _fields_ = [("m_eff", c_float), ("s_eff", c_float), ("label_smoothing", c_float),
                 ("easy_margin", c_int32), ("num_classes_total", c_int64), ("engine", c_int32),
-                ("reserved", c_int32)]
+                ("operand_scale", c_float)]
 
 
 def lib_path() -> str:
@@ -45,7 +45,7 @@ PROTOTYPES = {
     "b200f_launch_count": (ctypes.c_ulonglong, []),
     "b200f_has_tcgen05": (c_int, []),
     "b200f_l2norm_rows": (c_int, [c_void_p, c_int, c_int64, c_int, c_float, c_void_p, c_void_p, c_int,
-                                  c_void_p]),
+                                  c_float, c_void_p]),
     "b200f_head_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int, c_int]),
     "b200f_arcface_fwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                   c_int64, c_int64, c_int64, c_int, POINTER(HeadCfg),
@@ -58,7 +58,8 @@ PROTOTYPES = {
     "b200f_arcface_bwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, POINTER(HeadCfg),
                                   c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
-    "b200f_l2norm_bwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "b200f_l2norm_bwd": (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p, c_int64, c_int, c_void_p,
+                                 c_void_p]),
     "b200f_gallery_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int, c_int, c_int]),
     "b200f_gallery_topk": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int64,
                                    c_int64, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p,
@@ -66,7 +67,6 @@ PROTOTYPES = {
     "b200f_umma_selftest": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                     c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b200f_umma_timeout_flag": (c_int, [c_int]),
-    "b200f_umma_set_option": (c_int, [c_int, c_int]),
     "b200f_gallery_merge": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_float,
                                     c_void_p, c_void_p, c_void_p, c_void_p]),
 }
@@ -103,6 +103,8 @@ def dtype_code(t: torch.Tensor) -> int:
         return F32
     if t.dtype == torch.bfloat16:
         return BF16
+    if t.dtype == torch.float16:
+        return F16N        # fp16 only ever appears as K1's normalised operand format
     raise TypeError(f"b200face kernels take float32 or bfloat16, got {t.dtype}")
 
 

@@ -135,20 +135,27 @@ using namespace b200f;
 extern "C" {
 
 size_t b200f_head_workspace_bytes(int64_t B, int64_t C_local, int D, int dtype, int engine) {
+  (void)engine;
   if (B <= 0 || C_local <= 0 || D <= 0) return 0;
-  size_t simt_bytes = plan_head(B, C_local, D).total;
-  size_t umma_bytes = umma::head_workspace_bytes(B, C_local, D, dtype, engine);
-  return simt_bytes > umma_bytes ? simt_bytes : umma_bytes;
+  if (dtype == B200F_F16N) return umma::head_workspace_bytes(B, C_local, D);
+  return plan_head(B, C_local, D).total;
 }
 
+// dtype B200F_F16N (pre-normalised fp16 operands from K1) selects the tcgen05 engine; B200F_F32 /
+// B200F_BF16 run on the fp32 CUDA-core engine.
 static int check_head_args(const char* who, const void* x, const void* w, int dtype, const float* inv_nx,
                            const float* inv_nw, const int64_t* label, int64_t B, int64_t C, int D,
                            const b200f_head_cfg* cfg) {
-  if (!dtype_ok(dtype)) return fail(B200F_ERR_ARG, "%s: bad dtype %d", who, dtype);
+  if (!dtype_ok(dtype) && dtype != B200F_F16N) return fail(B200F_ERR_ARG, "%s: bad dtype %d", who, dtype);
   if (B <= 0 || C <= 0 || D <= 0) return fail(B200F_ERR_ARG, "%s: bad shape B=%lld C=%lld D=%d", who, (long long)B, (long long)C, D);
-  if (!x || !w || !inv_nx || !inv_nw || !label || !cfg) return fail(B200F_ERR_ARG, "%s: null pointer", who);
+  if (!x || !w || !label || !cfg) return fail(B200F_ERR_ARG, "%s: null pointer", who);
+  if (dtype != B200F_F16N && (!inv_nx || !inv_nw)) return fail(B200F_ERR_ARG, "%s: inverse norms required", who);
   if (cfg->num_classes_total < C) return fail(B200F_ERR_ARG, "%s: num_classes_total < C_local", who);
   if (cfg->num_classes_total >= (int64_t)1 << 31) return fail(B200F_ERR_ARG, "%s: more than 2^31 classes", who);
+  if (dtype == B200F_F16N && cfg->engine == B200F_ENGINE_SIMT)
+    return fail(B200F_ERR_UNSUPPORTED, "%s: B200F_F16N operands belong to the tcgen05 engine", who);
+  if (dtype != B200F_F16N && cfg->engine == B200F_ENGINE_TCGEN05)
+    return fail(B200F_ERR_UNSUPPORTED, "%s: the tcgen05 engine takes B200F_F16N operands (K1 output)", who);
   return B200F_OK;
 }
 
@@ -165,12 +172,11 @@ int b200f_arcface_fwd(const void* x, const void* w, int dtype, const float* inv_
   if (!workspace || workspace_bytes < need)
     return fail(B200F_ERR_WORKSPACE, "arcface_fwd: workspace %zu < %zu", workspace_bytes, need);
   cudaStream_t st = as_stream(stream);
-  if (umma::head_engine_selected(B, C_local, D, dtype, cfg->engine, logits_or_null != nullptr)) {
-    return umma::head_fwd(x, w, inv_nx, inv_nw, label, B, C_local, class_offset, D, cfg, row_stats, row_best,
-                          row_argmax, cos_minmax, nan_flag, static_cast<char*>(workspace), workspace_bytes, st);
+  if (dtype == B200F_F16N) {
+    if (logits_or_null) return fail(B200F_ERR_UNSUPPORTED, "arcface_fwd: the tcgen05 engine never stores logits");
+    return umma::head_fwd(x, w, label, B, C_local, class_offset, D, cfg, row_stats, row_best, row_argmax, cos_minmax,
+                          nan_flag, static_cast<char*>(workspace), workspace_bytes, st);
   }
-  if (cfg->engine == B200F_ENGINE_TCGEN05)
-    return fail(B200F_ERR_UNSUPPORTED, "arcface_fwd: tcgen05 engine does not take this call (dtype/shape/logits)");
   const HeadPlan pl = plan_head(B, C_local, D);
   if (dtype == B200F_F32)
     return head_fwd_simt<float>(x, w, inv_nx, inv_nw, label, B, C_local, class_offset, D, cfg, row_stats, row_best,
@@ -194,12 +200,12 @@ int b200f_arcface_bwd(const void* x, const void* w, int dtype, const float* inv_
     return fail(B200F_ERR_WORKSPACE, "arcface_bwd: workspace %zu < %zu", workspace_bytes, need);
   cudaStream_t st = as_stream(stream);
   if (dlogits_or_null && ld_dlogits < C_local) return fail(B200F_ERR_ARG, "arcface_bwd: ld_dlogits < C_local");
-  if (umma::head_engine_selected(B, C_local, D, dtype, cfg->engine, dlogits_or_null != nullptr)) {
-    return umma::head_bwd(x, w, inv_nx, inv_nw, label, lse, grad_scale, B, C_local, class_offset, D, cfg, dxhat,
-                          dw, static_cast<char*>(workspace), workspace_bytes, st);
+  if (dtype == B200F_F16N) {
+    if (dlogits_or_null) return fail(B200F_ERR_UNSUPPORTED, "arcface_bwd: the tcgen05 engine has no dlogits path");
+    if (!inv_nw) return fail(B200F_ERR_ARG, "arcface_bwd: inv_nw required");
+    return umma::head_bwd(x, w, inv_nw, label, lse, grad_scale, B, C_local, class_offset, D, cfg, dxhat, dw,
+                          static_cast<char*>(workspace), workspace_bytes, st);
   }
-  if (cfg->engine == B200F_ENGINE_TCGEN05)
-    return fail(B200F_ERR_UNSUPPORTED, "arcface_bwd: tcgen05 engine does not take this call (dtype/shape)");
   const HeadPlan pl = plan_head(B, C_local, D);
   if (dtype == B200F_F32)
     return head_bwd_simt<float>(x, w, inv_nx, inv_nw, label, lse, grad_scale, dlogits_or_null, ld_dlogits, B,

@@ -1,13 +1,22 @@
 // HBM-bound row kernels: K1 fused L2-normalise, normalise-backward, loss finalize, hook scalar.
 // Reference: F.normalize(v, p=2, dim=1, eps=1e-12) at src/face_models.py:351-352,525 and its
 // autograd; nn.CrossEntropyLoss(label_smoothing) src/training.py:341; hook src/face_models.py:538-567.
+//
+// Layout: one warp owns ROWS_PER_WARP consecutive rows and issues ALL of their 16-byte loads before the
+// first reduction, so each SM keeps >= 64 KB in flight (HBM latency x bandwidth needs ~45 KB per SM).
 #pragma once
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace b200f {
+
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+
 namespace rowops {
 
-constexpr int ROWS_PER_BLOCK = 8;   // one warp per row
+constexpr int WARPS_PER_BLOCK = 8;
+constexpr int ROWS_PER_WARP = 4;
+constexpr int ROWS_PER_BLOCK = WARPS_PER_BLOCK * ROWS_PER_WARP;   // 32
 
 // 16-byte vector of elements -> fp32
 template <typename T> struct Vec16;
@@ -30,30 +39,42 @@ template <> struct Vec16<__nv_bfloat16> {
     }
   }
 };
+template <> struct Vec16<__half> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const __half* p, float (&v)[8]) {
+    uint4 raw = __ldg(reinterpret_cast<const uint4*>(p));
+    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(h[i]);
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  }
+};
 
 template <typename TO> __device__ __forceinline__ void store_elem(TO* p, float v);
 template <> __device__ __forceinline__ void store_elem<float>(float* p, float v) { *p = v; }
-template <> __device__ __forceinline__ void store_elem<__nv_bfloat16>(__nv_bfloat16* p, float v) {
-  *p = __float2bfloat16_rn(v);
-}
+template <> __device__ __forceinline__ void store_elem<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ void store_elem<__half>(__half* p, float v) { *p = __float2half_rn(v); }
 
-// N consecutive outputs as one vector store (N = 4 or 8; dst is N*sizeof(TO)-aligned)
-template <typename TO, int N> struct StoreN;
-template <> struct StoreN<float, 4> {
-  static __device__ __forceinline__ void put(float* d, const float (&v)[4], float s) {
-    *reinterpret_cast<float4*>(d) = make_float4(v[0] * s, v[1] * s, v[2] * s, v[3] * s);
-  }
-};
-template <> struct StoreN<float, 8> {
-  static __device__ __forceinline__ void put(float* d, const float (&v)[8], float s) {
-    reinterpret_cast<float4*>(d)[0] = make_float4(v[0] * s, v[1] * s, v[2] * s, v[3] * s);
-    reinterpret_cast<float4*>(d)[1] = make_float4(v[4] * s, v[5] * s, v[6] * s, v[7] * s);
-  }
-};
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// N consecutive outputs (times s) as vector stores; dst is N*sizeof(TO)-aligned
+template <typename TO, int N> struct StoreN;
+template <int N> struct StoreN<float, N> {
+  static __device__ __forceinline__ void put(float* d, const float (&v)[N], float s) {
+#pragma unroll
+    for (int i = 0; i < N; i += 4)
+      *reinterpret_cast<float4*>(d + i) = make_float4(v[i] * s, v[i + 1] * s, v[i + 2] * s, v[i + 3] * s);
+  }
+};
 template <> struct StoreN<__nv_bfloat16, 4> {
   static __device__ __forceinline__ void put(__nv_bfloat16* d, const float (&v)[4], float s) {
     *reinterpret_cast<uint2*>(d) = make_uint2(pack_bf16x2(v[0] * s, v[1] * s), pack_bf16x2(v[2] * s, v[3] * s));
@@ -65,80 +86,186 @@ template <> struct StoreN<__nv_bfloat16, 8> {
                                               pack_bf16x2(v[4] * s, v[5] * s), pack_bf16x2(v[6] * s, v[7] * s));
   }
 };
+template <> struct StoreN<__half, 4> {
+  static __device__ __forceinline__ void put(__half* d, const float (&v)[4], float s) {
+    *reinterpret_cast<uint2*>(d) = make_uint2(pack_f16x2(v[0] * s, v[1] * s), pack_f16x2(v[2] * s, v[3] * s));
+  }
+};
+template <> struct StoreN<__half, 8> {
+  static __device__ __forceinline__ void put(__half* d, const float (&v)[8], float s) {
+    *reinterpret_cast<uint4*>(d) = make_uint4(pack_f16x2(v[0] * s, v[1] * s), pack_f16x2(v[2] * s, v[3] * s),
+                                              pack_f16x2(v[4] * s, v[5] * s), pack_f16x2(v[6] * s, v[7] * s));
+  }
+};
 
-// One warp per row.  VEC: rows are 16B-aligned and dim is a multiple of the vector width.
-// MAXV: number of 16B vectors per lane kept in registers between the two passes (dim <= 32*N*MAXV);
-// longer rows are re-read for the optional output pass.
-template <typename TI, typename TO, bool VEC>
-__global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
-l2norm_rows_kernel(const TI* __restrict__ in, int64_t rows, int dim, float eps,
-                   float* __restrict__ inv_norm, TO* __restrict__ out) {
-  const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const TI* src = in + row * dim;
+// K1, vector path.  VPL = 16-byte vectors per lane per row (dim <= 32 * N * VPL, dim % N == 0).
+template <typename TI, typename TO, int VPL>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+l2norm_rows_vec_kernel(const TI* __restrict__ in, int64_t rows, int dim, float eps, float out_scale,
+                       float* __restrict__ inv_norm, TO* __restrict__ out) {
   constexpr int N = Vec16<TI>::N;
-  constexpr int MAXV = 4;
-  float keep[MAXV][N];
-  float ss = 0.f;
-  if (VEC) {
-    const int nvec = dim / N;
+  const int lane = threadIdx.x & 31;
+  const int64_t row0 = ((int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5)) * ROWS_PER_WARP;
+  if (row0 >= rows) return;
+  const int nvec = dim / N;
+  float val[ROWS_PER_WARP][VPL][N];
 #pragma unroll
-    for (int it = 0; it < MAXV; ++it) {
+  for (int r = 0; r < ROWS_PER_WARP; ++r) {
+    const bool rok = row0 + r < rows;
+#pragma unroll
+    for (int it = 0; it < VPL; ++it) {
       const int v = lane + it * 32;
-      if (v < nvec) {
-        Vec16<TI>::load(src + v * N, keep[it]);
+      if (rok && v < nvec) {
+        Vec16<TI>::load(in + (row0 + r) * dim + v * N, val[r][it]);
+      } else {
 #pragma unroll
-        for (int e = 0; e < N; ++e) ss = fmaf(keep[it][e], keep[it][e], ss);
+        for (int e = 0; e < N; ++e) val[r][it][e] = 0.f;
       }
     }
-    for (int v = lane + MAXV * 32; v < nvec; v += 32) {
-      float tmp[N];
-      Vec16<TI>::load(src + v * N, tmp);
-#pragma unroll
-      for (int e = 0; e < N; ++e) ss = fmaf(tmp[e], tmp[e], ss);
-    }
-  } else {
-    for (int d = lane; d < dim; d += 32) { const float x = to_f32<TI>(src[d]); ss = fmaf(x, x, ss); }
   }
+#pragma unroll
+  for (int r = 0; r < ROWS_PER_WARP; ++r) {
+    float ss = 0.f;
+#pragma unroll
+    for (int it = 0; it < VPL; ++it)
+#pragma unroll
+      for (int e = 0; e < N; ++e) ss = fmaf(val[r][it][e], val[r][it][e], ss);
+    ss = warp_sum(ss);
+    if (row0 + r >= rows) continue;
+    const float inv = 1.0f / fmaxf(sqrtf(ss), eps);
+    if (lane == 0 && inv_norm != nullptr) inv_norm[row0 + r] = inv;
+    if (out != nullptr) {
+      const float s = inv * out_scale;
+#pragma unroll
+      for (int it = 0; it < VPL; ++it) {
+        const int v = lane + it * 32;
+        if (v < nvec) StoreN<TO, N>::put(out + (row0 + r) * dim + v * N, val[r][it], s);
+      }
+    }
+  }
+}
+
+// K1, generic path (any dim / alignment): one warp per row, scalar accesses.
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+l2norm_rows_generic_kernel(const TI* __restrict__ in, int64_t rows, int dim, float eps, float out_scale,
+                           float* __restrict__ inv_norm, TO* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const TI* src = in + row * dim;
+  float ss = 0.f;
+  for (int d = lane; d < dim; d += 32) { const float x = to_f32<TI>(src[d]); ss = fmaf(x, x, ss); }
   ss = warp_sum(ss);
   const float inv = 1.0f / fmaxf(sqrtf(ss), eps);
   if (lane == 0 && inv_norm != nullptr) inv_norm[row] = inv;
   if (out == nullptr) return;
-  TO* dst = out + row * dim;
-  if (VEC) {
-    const int nvec = dim / N;
+  const float s = inv * out_scale;
+  for (int d = lane; d < dim; d += 32) store_elem<TO>(out + row * dim + d, to_f32<TI>(src[d]) * s);
+}
+
+// dv = inv * (dvhat - vhat * <vhat, dvhat>),  vhat = v * vmul  (vmul = inv_norm for raw rows, 1/v_scale for
+// pre-normalised fp16 rows).  Vector path: one warp per row, all loads issued before the reduction.
+// dv may alias dvhat (in place): every element is read and written by the same lane.
+template <typename T, bool PRENORM, int VPL>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+l2norm_bwd_vec_kernel(const T* __restrict__ v, float v_scale, const float* __restrict__ inv_norm, const float* dvhat,
+                      int64_t rows, int dim, float* dv) {
+  constexpr int N = Vec16<T>::N;                // 8 (16-bit) or 4 (fp32) elements per 16-byte vector of v
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nvec = dim / N;
+  const float inv = inv_norm[row];
+  const float vmul = PRENORM ? (1.0f / v_scale) : inv;
+  float xv[VPL][N], gv[VPL][N];
 #pragma unroll
-    for (int it = 0; it < MAXV; ++it) {
-      const int v = lane + it * 32;
-      if (v < nvec) StoreN<TO, N>::put(dst + v * N, keep[it], inv);
+  for (int it = 0; it < VPL; ++it) {
+    const int k = lane + it * 32;
+    if (k < nvec) {
+      Vec16<T>::load(v + row * dim + k * N, xv[it]);
+#pragma unroll
+      for (int e = 0; e < N; e += 4) {
+        const float4 g4 = *reinterpret_cast<const float4*>(dvhat + row * dim + k * N + e);
+        gv[it][e] = g4.x; gv[it][e + 1] = g4.y; gv[it][e + 2] = g4.z; gv[it][e + 3] = g4.w;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < N; ++e) { xv[it][e] = 0.f; gv[it][e] = 0.f; }
     }
-    for (int v = lane + MAXV * 32; v < nvec; v += 32) {
-      float tmp[N];
-      Vec16<TI>::load(src + v * N, tmp);
-      StoreN<TO, N>::put(dst + v * N, tmp, inv);
+  }
+  float dot = 0.f;
+#pragma unroll
+  for (int it = 0; it < VPL; ++it)
+#pragma unroll
+    for (int e = 0; e < N; ++e) { xv[it][e] *= vmul; dot = fmaf(xv[it][e], gv[it][e], dot); }
+  dot = warp_sum(dot);
+#pragma unroll
+  for (int it = 0; it < VPL; ++it) {
+    const int k = lane + it * 32;
+    if (k < nvec) {
+#pragma unroll
+      for (int e = 0; e < N; e += 4)
+        *reinterpret_cast<float4*>(dv + row * dim + k * N + e) =
+            make_float4(inv * (gv[it][e] - xv[it][e] * dot), inv * (gv[it][e + 1] - xv[it][e + 1] * dot),
+                        inv * (gv[it][e + 2] - xv[it][e + 2] * dot), inv * (gv[it][e + 3] - xv[it][e + 3] * dot));
     }
-  } else {
-    for (int d = lane; d < dim; d += 32) store_elem<TO>(dst + d, to_f32<TI>(src[d]) * inv);
   }
 }
 
-// dv = inv * (dvhat - vhat * <vhat, dvhat>), vhat = v * inv.   One warp per row.
-template <typename T>
-__global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
-l2norm_bwd_kernel(const T* __restrict__ v, const float* __restrict__ inv_norm,
-                  const float* dvhat, int64_t rows, int dim, float* dv) {   // dv may alias dvhat (in place)
+template <typename T, bool PRENORM>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+l2norm_bwd_generic_kernel(const T* __restrict__ v, float v_scale, const float* __restrict__ inv_norm,
+                          const float* dvhat, int64_t rows, int dim, float* dv) {
   const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
+  const int64_t row = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   if (row >= rows) return;
   const T* src = v + row * dim;
   const float* g = dvhat + row * dim;
   const float inv = inv_norm[row];
+  const float vmul = PRENORM ? (1.0f / v_scale) : inv;
   float dot = 0.f;
-  for (int d = lane; d < dim; d += 32) dot = fmaf(to_f32<T>(src[d]) * inv, g[d], dot);
+  for (int d = lane; d < dim; d += 32) dot = fmaf(to_f32<T>(src[d]) * vmul, g[d], dot);
   dot = warp_sum(dot);
   float* o = dv + row * dim;
-  for (int d = lane; d < dim; d += 32) o[d] = inv * (g[d] - to_f32<T>(src[d]) * inv * dot);
+  for (int d = lane; d < dim; d += 32) o[d] = inv * (g[d] - to_f32<T>(src[d]) * vmul * dot);
+}
+
+// Host-side dispatch helpers (used by runtime.cu and by the tcgen05 engine).
+template <typename TI, typename TO>
+static inline void launch_l2norm_rows(const TI* in, int64_t rows, int dim, float eps, float out_scale, float* inv_norm,
+                                      TO* out, cudaStream_t st) {
+  constexpr int N = Vec16<TI>::N;
+  bool vec = (dim % N == 0) && (reinterpret_cast<uintptr_t>(in) % 16 == 0) && (dim <= 32 * N * 4);
+  if (out) vec = vec && (reinterpret_cast<uintptr_t>(out) % 16 == 0);
+  if (vec) {
+    const int nvec = dim / N;
+    const unsigned grid = (unsigned)ceil_div(rows, ROWS_PER_BLOCK);
+    if (nvec <= 32) l2norm_rows_vec_kernel<TI, TO, 1><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(in, rows, dim, eps, out_scale, inv_norm, out);
+    else if (nvec <= 64) l2norm_rows_vec_kernel<TI, TO, 2><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(in, rows, dim, eps, out_scale, inv_norm, out);
+    else l2norm_rows_vec_kernel<TI, TO, 4><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(in, rows, dim, eps, out_scale, inv_norm, out);
+  } else {
+    l2norm_rows_generic_kernel<TI, TO><<<(unsigned)ceil_div(rows, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, st>>>(
+        in, rows, dim, eps, out_scale, inv_norm, out);
+  }
+}
+
+template <typename T, bool PRENORM>
+static inline void launch_l2norm_bwd(const T* v, float v_scale, const float* inv_norm, const float* dvhat, int64_t rows,
+                                     int dim, float* dv, cudaStream_t st) {
+  constexpr int N = Vec16<T>::N;
+  const bool vec = (dim % N == 0) && (dim % 4 == 0) && (reinterpret_cast<uintptr_t>(v) % 16 == 0) &&
+                   (reinterpret_cast<uintptr_t>(dvhat) % 16 == 0) && (reinterpret_cast<uintptr_t>(dv) % 16 == 0) &&
+                   (dim <= 32 * N * 4);
+  const unsigned grid = (unsigned)ceil_div(rows, WARPS_PER_BLOCK);
+  if (vec) {
+    const int nvec = dim / N;
+    if (nvec <= 32) l2norm_bwd_vec_kernel<T, PRENORM, 1><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(v, v_scale, inv_norm, dvhat, rows, dim, dv);
+    else if (nvec <= 64) l2norm_bwd_vec_kernel<T, PRENORM, 2><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(v, v_scale, inv_norm, dvhat, rows, dim, dv);
+    else l2norm_bwd_vec_kernel<T, PRENORM, 4><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(v, v_scale, inv_norm, dvhat, rows, dim, dv);
+  } else {
+    l2norm_bwd_generic_kernel<T, PRENORM><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(v, v_scale, inv_norm, dvhat, rows, dim, dv);
+  }
 }
 
 // Single block.  row_stats [B,4] -> lse[B], loss (mean), pq_norm2.  Arithmetic in double: only B
@@ -180,8 +307,8 @@ loss_kernel(const float* __restrict__ row_stats, int64_t B, float s_eff, float l
 
 // src/face_models.py:538-567 on device scalars.
 static __global__ void hook_scale_kernel(const float* __restrict__ pq_norm2, const float* __restrict__ upstream,
-                                  double B, float s_eff, int hook_enabled, float max_grad_norm,
-                                  int phase, int epoch, float* __restrict__ out3) {
+                                         double B, float s_eff, int hook_enabled, float max_grad_norm,
+                                         int phase, int epoch, float* __restrict__ out3) {
   const double up = (upstream != nullptr) ? (double)*upstream : 1.0;
   const double base = (double)s_eff / B;
   const double n = fabs(up) * base * sqrt((double)*pq_norm2);
@@ -193,9 +320,13 @@ static __global__ void hook_scale_kernel(const float* __restrict__ pq_norm2, con
     if (n > 3.0) thr = fmin(thr, 0.5);
     if (n > thr) kappa = thr / (n + 1e-8);
   }
-  out3[0] = (float)(up * kappa * base);
+  const double gs = up * kappa * base;
+  out3[0] = (float)gs;
   out3[1] = (float)n;
   out3[2] = (float)kappa;
+  // power of two that puts |grad_scale| * g_scale in (512, 1024]: the fp16 range centring of the
+  // tcgen05 engine's logit-gradient buffer (exact to undo)
+  out3[3] = (gs != 0.0 && isfinite(gs)) ? (float)exp2(10.0 - ceil(log2(fabs(gs)))) : 1.0f;
 }
 
 }  // namespace rowops

@@ -65,48 +65,43 @@ int b200f_has_tcgen05(void) {
 }
 
 int b200f_l2norm_rows(const void* in, int in_dtype, int64_t rows, int dim, float eps, float* inv_norm,
-                      void* out_or_null, int out_dtype, void* stream) {
-  if (!dtype_ok(in_dtype) || (out_or_null && !dtype_ok(out_dtype)))
-    return fail(B200F_ERR_ARG, "l2norm_rows: bad dtype");
+                      void* out_or_null, int out_dtype, float out_scale, void* stream) {
+  if (!dtype_ok(in_dtype)) return fail(B200F_ERR_ARG, "l2norm_rows: bad input dtype %d", in_dtype);
+  if (out_or_null && !(dtype_ok(out_dtype) || out_dtype == B200F_F16N))
+    return fail(B200F_ERR_ARG, "l2norm_rows: bad output dtype %d", out_dtype);
   if (rows < 0 || dim <= 0) return fail(B200F_ERR_ARG, "l2norm_rows: bad shape rows=%lld dim=%d", (long long)rows, dim);
   if (rows == 0) return B200F_OK;
   if (!in || (!inv_norm && !out_or_null)) return fail(B200F_ERR_ARG, "l2norm_rows: null pointer");
-  const unsigned grid = (unsigned)ceil_div(rows, rowops::ROWS_PER_BLOCK);
-  const int threads = rowops::ROWS_PER_BLOCK * 32;
   cudaStream_t st = as_stream(stream);
-  const int per_in = 16 / (int)elem_size(in_dtype);
-  bool vec = (dim % per_in == 0) && (reinterpret_cast<uintptr_t>(in) % 16 == 0);
-  if (out_or_null) vec = vec && (reinterpret_cast<uintptr_t>(out_or_null) % 16 == 0);
-#define L2N_LAUNCH(TI, TO, V)                                                                      \
-  rowops::l2norm_rows_kernel<TI, TO, V><<<grid, threads, 0, st>>>(                                  \
-      static_cast<const TI*>(in), rows, dim, eps, inv_norm, static_cast<TO*>(out_or_null))
-#define L2N_DISPATCH(TI, TO) do { if (vec) L2N_LAUNCH(TI, TO, true); else L2N_LAUNCH(TI, TO, false); } while (0)
   const int od = out_or_null ? out_dtype : B200F_F32;
-  if (in_dtype == B200F_F32 && od == B200F_F32) L2N_DISPATCH(float, float);
-  else if (in_dtype == B200F_F32) L2N_DISPATCH(float, __nv_bfloat16);
-  else if (od == B200F_F32) L2N_DISPATCH(__nv_bfloat16, float);
-  else L2N_DISPATCH(__nv_bfloat16, __nv_bfloat16);
-#undef L2N_DISPATCH
-#undef L2N_LAUNCH
-  B200F_LAUNCH_OK("l2norm_rows_kernel");
+#define L2N(TI, TO) rowops::launch_l2norm_rows<TI, TO>(static_cast<const TI*>(in), rows, dim, eps, out_scale, inv_norm, \
+                                                      static_cast<TO*>(out_or_null), st)
+  if (in_dtype == B200F_F32) {
+    if (od == B200F_F32) L2N(float, float); else if (od == B200F_BF16) L2N(float, __nv_bfloat16); else L2N(float, __half);
+  } else {
+    if (od == B200F_F32) L2N(__nv_bfloat16, float); else if (od == B200F_BF16) L2N(__nv_bfloat16, __nv_bfloat16);
+    else L2N(__nv_bfloat16, __half);
+  }
+#undef L2N
+  B200F_LAUNCH_OK("l2norm_rows kernel");
   return B200F_OK;
 }
 
-int b200f_l2norm_bwd(const void* v, int dtype, const float* inv_norm, const float* dvhat, int64_t rows,
+int b200f_l2norm_bwd(const void* v, int dtype, float v_scale, const float* inv_norm, const float* dvhat, int64_t rows,
                      int dim, float* dv, void* stream) {
-  if (!dtype_ok(dtype)) return fail(B200F_ERR_ARG, "l2norm_bwd: bad dtype");
+  if (!dtype_ok(dtype) && dtype != B200F_F16N) return fail(B200F_ERR_ARG, "l2norm_bwd: bad dtype");
   if (rows < 0 || dim <= 0) return fail(B200F_ERR_ARG, "l2norm_bwd: bad shape");
   if (rows == 0) return B200F_OK;
   if (!v || !inv_norm || !dvhat || !dv) return fail(B200F_ERR_ARG, "l2norm_bwd: null pointer");
-  const unsigned grid = (unsigned)ceil_div(rows, rowops::ROWS_PER_BLOCK);
-  const int threads = rowops::ROWS_PER_BLOCK * 32;
+  if (dtype == B200F_F16N && !(v_scale > 0.f)) return fail(B200F_ERR_ARG, "l2norm_bwd: v_scale must be > 0");
+  cudaStream_t st = as_stream(stream);
   if (dtype == B200F_F32)
-    rowops::l2norm_bwd_kernel<float><<<grid, threads, 0, as_stream(stream)>>>(
-        static_cast<const float*>(v), inv_norm, dvhat, rows, dim, dv);
+    rowops::launch_l2norm_bwd<float, false>(static_cast<const float*>(v), 1.f, inv_norm, dvhat, rows, dim, dv, st);
+  else if (dtype == B200F_BF16)
+    rowops::launch_l2norm_bwd<__nv_bfloat16, false>(static_cast<const __nv_bfloat16*>(v), 1.f, inv_norm, dvhat, rows, dim, dv, st);
   else
-    rowops::l2norm_bwd_kernel<__nv_bfloat16><<<grid, threads, 0, as_stream(stream)>>>(
-        static_cast<const __nv_bfloat16*>(v), inv_norm, dvhat, rows, dim, dv);
-  B200F_LAUNCH_OK("l2norm_bwd_kernel");
+    rowops::launch_l2norm_bwd<__half, true>(static_cast<const __half*>(v), v_scale, inv_norm, dvhat, rows, dim, dv, st);
+  B200F_LAUNCH_OK("l2norm_bwd kernel");
   return B200F_OK;
 }
 
@@ -120,11 +115,11 @@ int b200f_arcface_loss(const float* row_stats, int64_t B, const b200f_head_cfg* 
 }
 
 int b200f_arcface_hook_scale(const float* pq_norm2, const float* upstream, int64_t B, float s_eff,
-                             int hook_enabled, float max_grad_norm, int phase, int epoch, float* out3,
+                             int hook_enabled, float max_grad_norm, int phase, int epoch, float* out4,
                              void* stream) {
-  if (!pq_norm2 || !out3 || B <= 0) return fail(B200F_ERR_ARG, "arcface_hook_scale: bad argument");
+  if (!pq_norm2 || !out4 || B <= 0) return fail(B200F_ERR_ARG, "arcface_hook_scale: bad argument");
   rowops::hook_scale_kernel<<<1, 1, 0, as_stream(stream)>>>(pq_norm2, upstream, (double)B, s_eff, hook_enabled,
-                                                            max_grad_norm, phase, epoch, out3);
+                                                            max_grad_norm, phase, epoch, out4);
   B200F_LAUNCH_OK("hook_scale_kernel");
   return B200F_OK;
 }

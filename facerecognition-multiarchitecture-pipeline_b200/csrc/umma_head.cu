@@ -1,8 +1,9 @@
-// tcgen05 / TMEM / TMA engine for the ArcFace head (bf16 inputs): host side.
-//   K2  forward statistics : gemm_kernel<K,K,EpiFwd>           x[B,D] . w[C,D]^T
-//   K3a logit gradient     : gemm_kernel<K,K,EpiBwdG>          recompute + G1/G2 (16-bit, L2-resident chunk)
-//   K3b dW_hat = G1^T x    : gemm_kernel<MN,MN,EpiStore>       then normalise-backward in place
-//   K3c dx_hat = G2 w      : gemm_kernel<K,MN,EpiStore> split-K, then a fixed-order reduction
+// tcgen05 / TMEM / TMA engine for the ArcFace head: host side.
+// Operands are the fp16, L2-normalised, power-of-two-scaled rows K1 emits (dtype B200F_F16N).
+//   K2  forward statistics : gemm_kernel<K,K,EpiFwd>           x_hat[B,D] . w_hat[C,D]^T
+//   K3a logit gradient     : gemm_kernel<K,K,EpiBwdG>          recompute + G (fp16, L2-resident chunk)
+//   K3b dW_hat = G^T x_hat : gemm_kernel<MN,MN,EpiStore>       then normalise-backward in place
+//   K3c dx_hat = G w_hat   : gemm_kernel<K,MN,EpiStore> split-K, then a fixed-order reduction
 // ALL tcgen05 kernels of the library live in this one translation unit (g_umma_timeout_flag).
 #include "umma_api.cuh"
 #include "umma_epilogues.cuh"
@@ -69,7 +70,7 @@ static GemmParams gemm_params(int M, int N, int K, int k_splits, bool a_mn, bool
   p.k_per_split = (int)ceil_div(kchunks, k_splits) * BLOCK_K;
   p.k_splits = (int)ceil_div(K, p.k_per_split);
   // K-major: SBO = 1024 (8 rows x 128 B), k-step 32 B.  MN-major: LBO = 8 KB (next 64-wide block),
-  // SBO = 1024 (next 8 k-rows), k-step = 16 rows x 128 B.
+  // SBO = 1024 (next 8 k-rows), k-step = 16 rows x 128 B.   (validated on B200 by tools/umma_probe.py)
   p.a_lbo = a_mn ? MN_BLOCK_BYTES : 0; p.a_sbo = 1024; p.a_kstep = a_mn ? 2048 : 32;
   p.b_lbo = b_mn ? MN_BLOCK_BYTES : 0; p.b_sbo = 1024; p.b_kstep = b_mn ? 2048 : 32;
   p.idesc = make_idesc(a_fmt, b_fmt, a_mn, b_mn, BLOCK_M, BLOCK_N);
@@ -134,17 +135,19 @@ reduce_row_partials_kernel(const float* __restrict__ part, int n_parts, int64_t 
   }
 }
 
+// dst (=|+=) scale / *dev_scale * sum_s part[s], fixed order
 __global__ void reduce_splits_kernel(const float* __restrict__ part, int n_splits, int64_t n, float* __restrict__ dst,
-                                     int accumulate, float scale) {
+                                     int accumulate, float scale, const float* __restrict__ dev_scale) {
   const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
+  const float sc = (dev_scale != nullptr) ? scale / __ldg(dev_scale) : scale;
   float4 s = accumulate ? *reinterpret_cast<const float4*>(dst + i) : make_float4(0.f, 0.f, 0.f, 0.f);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int k = 0; k < n_splits; ++k) {
     const float4 v = *reinterpret_cast<const float4*>(part + (int64_t)k * n + i);
     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
   }
-  s.x = fmaf(acc.x, scale, s.x); s.y = fmaf(acc.y, scale, s.y); s.z = fmaf(acc.z, scale, s.z); s.w = fmaf(acc.w, scale, s.w);
+  s.x = fmaf(acc.x, sc, s.x); s.y = fmaf(acc.y, sc, s.y); s.z = fmaf(acc.z, sc, s.z); s.w = fmaf(acc.w, sc, s.w);
   *reinterpret_cast<float4*>(dst + i) = s;
 }
 
@@ -153,7 +156,7 @@ struct Plan {
   int m_tiles, n_tiles;
   size_t off_part, off_cos;
   int64_t Cc, ldg; int n_chunks, dx_splits;
-  size_t off_G1, off_G2, off_dxpart;
+  size_t off_G, off_dxpart;
   size_t total;
 };
 
@@ -165,8 +168,8 @@ static Plan make_plan(int64_t B, int64_t C, int D) {
   pl.off_part = off; off += align_up(sizeof(float) * (size_t)pl.n_tiles * B * PART_COLS, 256);
   pl.off_cos = off;  off += align_up(sizeof(float) * 2 * 4 * (size_t)pl.n_tiles * pl.m_tiles, 256);
   const size_t fwd_total = off;
-  // backward: both 16-bit copies of the logit-gradient chunk should stay L2-resident: <= 64 MB together
-  int64_t cc_max = ((int64_t)(64u << 20) / 4 / B) / BLOCK_N * BLOCK_N;
+  // backward: the fp16 logit-gradient chunk should stay L2-resident (126 MB L2): <= 48 MB
+  int64_t cc_max = ((int64_t)(48u << 20) / 2 / B) / BLOCK_N * BLOCK_N;
   if (cc_max < BLOCK_N) cc_max = BLOCK_N;
   pl.n_chunks = (int)ceil_div(C, cc_max);
   pl.Cc = ceil_div(ceil_div(C, pl.n_chunks), BLOCK_N) * BLOCK_N;
@@ -179,8 +182,7 @@ static Plan make_plan(int64_t B, int64_t C, int D) {
   if (splits > kchunks) splits = kchunks;
   pl.dx_splits = splits;
   off = 0;
-  pl.off_G1 = off;     off += align_up(2 * (size_t)B * pl.ldg, 1024);
-  pl.off_G2 = off;     off += align_up(2 * (size_t)B * pl.ldg, 1024);
+  pl.off_G = off;      off += align_up(2 * (size_t)B * pl.ldg, 1024);
   pl.off_dxpart = off; off += align_up(sizeof(float) * (size_t)splits * B * D, 256);
   pl.total = (off > fwd_total ? off : fwd_total) + 1024;
   return pl;
@@ -196,34 +198,35 @@ static bool device_is_sm100() {
   return cached == 1;
 }
 
-bool head_engine_selected(int64_t B, int64_t C, int D, int dtype, int engine, bool wants_logits) {
-  if (engine == B200F_ENGINE_SIMT) return false;
-  if (dtype != B200F_BF16 || wants_logits) return false;
-  if (D % 8 != 0 || B >= (int64_t)1 << 30 || C >= (int64_t)1 << 30) return false;
-  if (!device_is_sm100()) return false;
-  return true;
-}
+bool available() { return device_is_sm100(); }
 
-size_t head_workspace_bytes(int64_t B, int64_t C, int D, int dtype, int engine) {
-  if (engine == B200F_ENGINE_SIMT || dtype != B200F_BF16) return 0;
-  return make_plan(B, C, D).total;
-}
+size_t head_workspace_bytes(int64_t B, int64_t C, int D) { return make_plan(B, C, D).total; }
 
 static char* ws_align(char* ws) { return reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~(uintptr_t)1023); }
 
-int head_fwd(const void* x, const void* w, const float* inv_nx, const float* inv_nw, const int64_t* label, int64_t B,
-             int64_t C, int64_t class_offset, int D, const b200f_head_cfg* cfg, float* row_stats, float* row_best,
-             int64_t* row_argmax, float* cos_minmax, int32_t* nan_flag, char* ws, size_t ws_bytes, cudaStream_t st) {
+static int check_shape(int64_t B, int64_t C, int D, const b200f_head_cfg* cfg) {
+  if (!device_is_sm100()) return fail(B200F_ERR_UNSUPPORTED, "tcgen05 engine needs an sm_100 device");
+  if (D % 8 != 0) return fail(B200F_ERR_UNSUPPORTED, "tcgen05 engine needs D %% 8 == 0 (got %d)", D);
+  if (B >= ((int64_t)1 << 30) || C >= ((int64_t)1 << 30)) return fail(B200F_ERR_UNSUPPORTED, "tcgen05 engine: B, C < 2^30");
+  if (!(cfg->operand_scale > 0.f)) return fail(B200F_ERR_ARG, "tcgen05 engine: cfg.operand_scale must be > 0");
+  return B200F_OK;
+}
+
+int head_fwd(const void* xh, const void* wh, const int64_t* label, int64_t B, int64_t C, int64_t class_offset, int D,
+             const b200f_head_cfg* cfg, float* row_stats, float* row_best, int64_t* row_argmax, float* cos_minmax,
+             int32_t* nan_flag, char* ws, size_t ws_bytes, cudaStream_t st) {
+  int rc = check_shape(B, C, D, cfg); if (rc) return rc;
   const Plan pl = make_plan(B, C, D);
   if (ws_bytes < pl.total) return fail(B200F_ERR_WORKSPACE, "umma head_fwd: workspace too small");
   ws = ws_align(ws);
   CUtensorMap ta, tb;
-  int rc = tmap_kmajor(&ta, x, B, D, D, BLOCK_M); if (rc) return rc;
-  rc = tmap_kmajor(&tb, w, C, D, D, BLOCK_N); if (rc) return rc;
-  GemmParams p = gemm_params((int)B, (int)C, D, 1, false, false, FMT_BF16, FMT_BF16);
+  rc = tmap_kmajor(&ta, xh, B, D, D, BLOCK_M); if (rc) return rc;
+  rc = tmap_kmajor(&tb, wh, C, D, D, BLOCK_N); if (rc) return rc;
+  GemmParams p = gemm_params((int)B, (int)C, D, 1, false, false, FMT_F16, FMT_F16);
   EpiFwd::Params ep{};
-  ep.inv_nx = inv_nx; ep.inv_nw = inv_nw; ep.label = label; ep.B = B; ep.C = C; ep.class_offset = class_offset;
+  ep.label = label; ep.B = B; ep.C = C; ep.class_offset = class_offset;
   ep.hm = HeadMath{cfg->m_eff, cfg->s_eff, cfg->easy_margin};
+  ep.inv_scale = 1.0f / (cfg->operand_scale * cfg->operand_scale);
   ep.part = reinterpret_cast<float*>(ws + pl.off_part);
   ep.cos_part = reinterpret_cast<float*>(ws + pl.off_cos);
   ep.nan_flag = nan_flag;
@@ -236,68 +239,54 @@ int head_fwd(const void* x, const void* w, const float* inv_nx, const float* inv
   return B200F_OK;
 }
 
-static bool g_fp16_logit_grad = false;   // set by b200f_umma_set_option(0, 1) once mixed f16 x bf16 MMA is validated
-
-int head_bwd(const void* x, const void* w, const float* inv_nx, const float* inv_nw, const int64_t* label,
-             const float* lse, const float* grad_scale, int64_t B, int64_t C, int64_t class_offset, int D,
-             const b200f_head_cfg* cfg, float* dxhat, float* dw, char* ws, size_t ws_bytes, cudaStream_t st) {
+int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t* label, const float* lse,
+             const float* grad4, int64_t B, int64_t C, int64_t class_offset, int D, const b200f_head_cfg* cfg,
+             float* dxhat, float* dw, char* ws, size_t ws_bytes, cudaStream_t st) {
+  int rc = check_shape(B, C, D, cfg); if (rc) return rc;
   const Plan pl = make_plan(B, C, D);
   if (ws_bytes < pl.total) return fail(B200F_ERR_WORKSPACE, "umma head_bwd: workspace too small");
   ws = ws_align(ws);
-  uint16_t* G1 = reinterpret_cast<uint16_t*>(ws + pl.off_G1);
-  uint16_t* G2 = reinterpret_cast<uint16_t*>(ws + pl.off_G2);
+  uint16_t* G = reinterpret_cast<uint16_t*>(ws + pl.off_G);
   float* dxpart = reinterpret_cast<float*>(ws + pl.off_dxpart);
-  const bool fp16g = g_fp16_logit_grad;
-  // fp16 needs its range centred: |G| <= |grad_scale| * max(inv) * dphi; 2^20 keeps typical values normal
-  const float g_scale = fp16g ? 1048576.0f : 1.0f;
-  const uint32_t gfmt = fp16g ? FMT_F16 : FMT_BF16;
+  const float S = cfg->operand_scale;
   CUtensorMap tx_k, tx_mn;
-  int rc = tmap_kmajor(&tx_k, x, B, D, D, BLOCK_M); if (rc) return rc;
-  rc = tmap_mnmajor(&tx_mn, x, D, B, D); if (rc) return rc;
+  rc = tmap_kmajor(&tx_k, xh, B, D, D, BLOCK_M); if (rc) return rc;
+  rc = tmap_mnmajor(&tx_mn, xh, D, B, D); if (rc) return rc;
   int chunk_no = 0;
   for (int64_t c0 = 0; c0 < C; c0 += pl.Cc, ++chunk_no) {
     const int64_t cnt = (C - c0 < pl.Cc) ? (C - c0) : pl.Cc;
-    const uint16_t* wc = static_cast<const uint16_t*>(w) + c0 * D;
+    const uint16_t* wc = static_cast<const uint16_t*>(wh) + c0 * D;
     // --- K3a: logit gradient of the chunk
     CUtensorMap tw_k;
     rc = tmap_kmajor(&tw_k, wc, cnt, D, D, BLOCK_N); if (rc) return rc;
-    GemmParams pg = gemm_params((int)B, (int)cnt, D, 1, false, false, FMT_BF16, FMT_BF16);
-    if (fp16g) {
-      EpiBwdG<true>::Params eg{inv_nx, inv_nw, label, lse, grad_scale, B, C, class_offset, c0,
-                               HeadMath{cfg->m_eff, cfg->s_eff, cfg->easy_margin}, cfg->label_smoothing,
-                               1.0f / (float)cfg->num_classes_total, g_scale, G1, G2, pl.ldg};
-      rc = launch_gemm<false, false, EpiBwdG<true>>(tx_k, tw_k, pg, eg, st, "umma K3a logit-grad (fp16)");
-    } else {
-      EpiBwdG<false>::Params eg{inv_nx, inv_nw, label, lse, grad_scale, B, C, class_offset, c0,
-                                HeadMath{cfg->m_eff, cfg->s_eff, cfg->easy_margin}, cfg->label_smoothing,
-                                1.0f / (float)cfg->num_classes_total, g_scale, G1, G2, pl.ldg};
-      rc = launch_gemm<false, false, EpiBwdG<false>>(tx_k, tw_k, pg, eg, st, "umma K3a logit-grad (bf16)");
-    }
+    GemmParams pg = gemm_params((int)B, (int)cnt, D, 1, false, false, FMT_F16, FMT_F16);
+    EpiBwdG::Params eg{label, lse, grad4, B, C, class_offset, c0, HeadMath{cfg->m_eff, cfg->s_eff, cfg->easy_margin},
+                       cfg->label_smoothing, 1.0f / (float)cfg->num_classes_total, 1.0f / (S * S), G, pl.ldg};
+    rc = launch_gemm<false, false, EpiBwdG>(tx_k, tw_k, pg, eg, st, "umma K3a logit-grad");
     if (rc) return rc;
-    // --- K3b: dW_hat[c0 + m, :] = sum_b G1[b, m] x[b, :]
-    CUtensorMap tg1_mn;
-    rc = tmap_mnmajor(&tg1_mn, G1, cnt, B, pl.ldg); if (rc) return rc;
-    GemmParams pw = gemm_params((int)cnt, D, (int)B, 1, true, true, gfmt, FMT_BF16);
-    EpiStore::Params ew{dw, (int64_t)D, 0, c0, 1.0f / g_scale};
-    rc = launch_gemm<true, true, EpiStore>(tg1_mn, tx_mn, pw, ew, st, "umma K3b dW");
+    // --- K3b: dW_hat[c0 + m, :] = sum_b G[b, m] x_hat[b, :]
+    CUtensorMap tg_mn;
+    rc = tmap_mnmajor(&tg_mn, G, cnt, B, pl.ldg); if (rc) return rc;
+    GemmParams pw = gemm_params((int)cnt, D, (int)B, 1, true, true, FMT_F16, FMT_F16);
+    EpiStore::Params ew{dw, (int64_t)D, 0, c0, 1.0f / S, grad4 + 3};
+    rc = launch_gemm<true, true, EpiStore>(tg_mn, tx_mn, pw, ew, st, "umma K3b dW");
     if (rc) return rc;
-    // --- K3c: dx_hat partials = G2[:, k-range] w[c0 + k-range, :]
-    CUtensorMap tg2_k, tw_mn;
-    rc = tmap_kmajor(&tg2_k, G2, B, cnt, pl.ldg, BLOCK_M); if (rc) return rc;
+    // --- K3c: dx_hat partials = G[:, k-range] w_hat[c0 + k-range, :]
+    CUtensorMap tg_k, tw_mn;
+    rc = tmap_kmajor(&tg_k, G, B, cnt, pl.ldg, BLOCK_M); if (rc) return rc;
     rc = tmap_mnmajor(&tw_mn, wc, D, cnt, D); if (rc) return rc;
-    GemmParams px = gemm_params((int)B, D, (int)cnt, pl.dx_splits, false, true, gfmt, FMT_BF16);
-    EpiStore::Params ex{dxpart, (int64_t)D, B * (int64_t)D, 0, 1.0f};
-    rc = launch_gemm<false, true, EpiStore>(tg2_k, tw_mn, px, ex, st, "umma K3c dX");
+    GemmParams px = gemm_params((int)B, D, (int)cnt, pl.dx_splits, false, true, FMT_F16, FMT_F16);
+    EpiStore::Params ex{dxpart, (int64_t)D, B * (int64_t)D, 0, 1.0f, nullptr};
+    rc = launch_gemm<false, true, EpiStore>(tg_k, tw_mn, px, ex, st, "umma K3c dX");
     if (rc) return rc;
     const int64_t n = B * (int64_t)D;
     reduce_splits_kernel<<<(unsigned)ceil_div(n / 4, 256), 256, 0, st>>>(dxpart, px.k_splits, n, dxhat, chunk_no > 0,
-                                                                        1.0f / g_scale);
+                                                                        1.0f / S, grad4 + 3);
     B200F_LAUNCH_OK("umma reduce_splits_kernel");
   }
   // normalise-backward of the weight rows, in place: dw <- inv_nw * (dw_hat - w_hat <w_hat, dw_hat>)
-  rowops::l2norm_bwd_kernel<__nv_bfloat16><<<(unsigned)ceil_div(C, rowops::ROWS_PER_BLOCK), rowops::ROWS_PER_BLOCK * 32, 0, st>>>(
-      static_cast<const __nv_bfloat16*>(w), inv_nw, dw, C, D, dw);
-  B200F_LAUNCH_OK("l2norm_bwd_kernel (weights)");
+  rowops::launch_l2norm_bwd<__half, true>(static_cast<const __half*>(wh), S, inv_nw, dw, C, D, dw, st);
+  B200F_LAUNCH_OK("l2norm_bwd kernel (weights)");
   return B200F_OK;
 }
 
@@ -311,9 +300,9 @@ extern "C" {
 
 // Self-test / probe of the GEMM core: out[M,N] (fp32) = sum_k A(m,k) B(n,k) for every operand layout.
 //   a_mn / b_mn: 0 = K-major (a is [M,K] row-major), 1 = MN-major (a is [K,M] row-major)
-//   a_fp16: the A operand holds fp16 instead of bf16 (mixed-format MMA probe); lbo/sbo/kstep < 0 = defaults
+//   fmt: 0 = bf16 x bf16, 1 = fp16 (A) x bf16 (B) [unsupported by the hardware: faults], 2 = fp16 x fp16
 int b200f_umma_selftest(const void* a, const void* b, float* out, int M, int N, int K, int a_mn, int b_mn,
-                        int a_fp16, int k_splits, int a_lbo, int a_sbo, int a_kstep, int b_lbo, int b_sbo,
+                        int fmt, int k_splits, int a_lbo, int a_sbo, int a_kstep, int b_lbo, int b_sbo,
                         int b_kstep, void* stream) {
   if (!a || !b || !out || M <= 0 || N <= 0 || K <= 0) return fail(B200F_ERR_ARG, "umma_selftest: bad argument");
   if (!device_is_sm100()) return fail(B200F_ERR_UNSUPPORTED, "umma_selftest: device is not sm_100");
@@ -322,14 +311,15 @@ int b200f_umma_selftest(const void* a, const void* b, float* out, int M, int N, 
   if (rc) return rc;
   rc = b_mn ? tmap_mnmajor(&tb, b, N, K, N) : tmap_kmajor(&tb, b, N, K, K, BLOCK_N);
   if (rc) return rc;
-  GemmParams p = gemm_params(M, N, K, k_splits, a_mn != 0, b_mn != 0, a_fp16 ? FMT_F16 : FMT_BF16, FMT_BF16);
+  GemmParams p = gemm_params(M, N, K, k_splits, a_mn != 0, b_mn != 0, fmt >= 1 ? FMT_F16 : FMT_BF16,
+                             fmt == 2 ? FMT_F16 : FMT_BF16);
   if (a_lbo >= 0) p.a_lbo = a_lbo;
   if (a_sbo >= 0) p.a_sbo = a_sbo;
   if (a_kstep >= 0) p.a_kstep = a_kstep;
   if (b_lbo >= 0) p.b_lbo = b_lbo;
   if (b_sbo >= 0) p.b_sbo = b_sbo;
   if (b_kstep >= 0) p.b_kstep = b_kstep;
-  EpiStore::Params ep{out, (int64_t)N, (int64_t)M * N, 0, 1.0f};
+  EpiStore::Params ep{out, (int64_t)N, (int64_t)M * N, 0, 1.0f, nullptr};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!a_mn && !b_mn) return launch_gemm<false, false, EpiStore>(ta, tb, p, ep, st, "umma selftest KK");
   if (a_mn && b_mn) return launch_gemm<true, true, EpiStore>(ta, tb, p, ep, st, "umma selftest MM");
@@ -343,12 +333,6 @@ int b200f_umma_timeout_flag(int reset) {
   if (cudaMemcpyFromSymbol(&v, g_umma_timeout_flag, sizeof(v)) != cudaSuccess) return -1;
   if (reset) { unsigned int z = 0; cudaMemcpyToSymbol(g_umma_timeout_flag, &z, sizeof(z)); }
   return (int)v;
-}
-
-// option 0: logit-gradient operand format of K3 (0 = bf16, 1 = fp16 x bf16 mixed-format MMA)
-int b200f_umma_set_option(int option, int value) {
-  if (option == 0) { g_fp16_logit_grad = (value != 0); return B200F_OK; }
-  return fail(B200F_ERR_ARG, "umma_set_option: unknown option %d", option);
 }
 
 }  // extern "C"

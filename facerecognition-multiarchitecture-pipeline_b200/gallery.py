@@ -31,7 +31,7 @@ def _inv_norm(t: torch.Tensor) -> torch.Tensor:
     lib = _lib.load_library()
     inv = torch.empty(t.shape[0], dtype=torch.float32, device=t.device)
     if t.shape[0]:
-        check(lib.b200f_l2norm_rows(ptr(t), dtype_code(t), t.shape[0], t.shape[1], 1e-12, ptr(inv), None, 0,
+        check(lib.b200f_l2norm_rows(ptr(t), dtype_code(t), t.shape[0], t.shape[1], 1e-12, ptr(inv), None, 0, 1.0,
                                     stream_ptr(t.device)), "b200f_l2norm_rows")
     return inv
 

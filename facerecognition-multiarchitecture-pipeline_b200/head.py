@@ -75,16 +75,21 @@ class _Hook:
 
 def _head_cfg(m_eff, s_eff, label_smoothing, easy, c_total, engine) -> HeadCfg:
     return HeadCfg(float(m_eff), float(s_eff), float(label_smoothing), int(bool(easy)), int(c_total),
-                   int(engine), 0)
+                   int(engine), OPERAND_SCALE)
 
 
-def _row_inv_norm(t: torch.Tensor) -> torch.Tensor:
-    """K1: 1 / max(||row||, 1e-12) per row."""
+OPERAND_SCALE = 256.0   # K1 emits x_hat * 2^8 / w_hat * 2^8 in fp16 for the tcgen05 engine (|x_hat| <= 1)
+
+
+def _k1(t: torch.Tensor, want_f16n: bool):
+    """K1, fused row L2-normalise.  Returns (operand, inv_norm): operand is t itself (CUDA-core engine: the
+    1/||.|| factors are applied in the epilogue) or the fp16 normalised rows * OPERAND_SCALE (tcgen05 engine)."""
     lib = _lib.load_library()
     inv = torch.empty(t.shape[0], dtype=torch.float32, device=t.device)
-    check(lib.b200f_l2norm_rows(ptr(t), dtype_code(t), t.shape[0], t.shape[1], NORM_EPS, ptr(inv), None, 0,
-                                stream_ptr(t.device)), "b200f_l2norm_rows")
-    return inv
+    out = torch.empty(t.shape, dtype=torch.float16, device=t.device) if want_f16n else None
+    check(lib.b200f_l2norm_rows(ptr(t), dtype_code(t), t.shape[0], t.shape[1], NORM_EPS, ptr(inv), ptr(out),
+                                _lib.F16N, OPERAND_SCALE, stream_ptr(t.device)), "b200f_l2norm_rows")
+    return (out if want_f16n else t), inv
 
 
 def l2_normalize(t: torch.Tensor, out_dtype: Optional[torch.dtype] = None):
@@ -95,57 +100,85 @@ def l2_normalize(t: torch.Tensor, out_dtype: Optional[torch.dtype] = None):
     out = torch.empty(t.shape, dtype=out_dtype or t.dtype, device=t.device)
     inv = torch.empty(t.shape[0], dtype=torch.float32, device=t.device)
     check(lib.b200f_l2norm_rows(ptr(t), dtype_code(t), t.shape[0], t.shape[1], NORM_EPS, ptr(inv), ptr(out),
-                                dtype_code(out), stream_ptr(t.device)), "b200f_l2norm_rows")
+                                dtype_code(out), 1.0, stream_ptr(t.device)), "b200f_l2norm_rows")
     return out, inv
 
 
-def _fwd_kernels(x, w, label, cfg: HeadCfg, class_offset, want_logits):
+def use_tcgen05(x: torch.Tensor, engine: int, wants_logits: bool = False) -> bool:
+    """Engine choice (include/b200face.h): bf16 inputs go to the tcgen05/TMEM/TMA engine, fp32 inputs to the
+    fp32 CUDA-core engine (the 1e-5 bar needs fp32 products) unless the caller forces an engine."""
+    if engine == _lib.ENGINE_SIMT or wants_logits or x.shape[1] % 8 != 0:
+        if engine == _lib.ENGINE_TCGEN05:
+            raise RuntimeError("the tcgen05 engine needs D % 8 == 0 and does not store logits")
+        return False
+    if not _lib.load_library().b200f_has_tcgen05():
+        if engine == _lib.ENGINE_TCGEN05:
+            raise RuntimeError("the tcgen05 engine needs an sm_100 device")
+        return False
+    return engine == _lib.ENGINE_TCGEN05 or x.dtype == torch.bfloat16
+
+
+def _prepare_weight(w: torch.Tensor, f16n: bool, cache: Optional[dict]):
+    """K1 on the class weights; with a cache dict the result is reused until the tensor's version changes
+    (optimizer step / load_state_dict).  Training steps change it every step, so bench.py passes no cache."""
+    key = (w.data_ptr(), w._version, tuple(w.shape), w.dtype, f16n)
+    if cache is not None and cache.get("key") == key:
+        return cache["val"]
+    with _lib.timed("l2norm_rows_w", w.device):
+        val = _k1(w, f16n)
+    if cache is not None:
+        cache["key"], cache["val"] = key, val
+    return val
+
+
+def _fwd_kernels(x, w, label, cfg: HeadCfg, class_offset, want_logits, w_cache=None):
     lib = _lib.load_library()
     B, D = x.shape
     C = w.shape[0]
     dev = x.device
-    inv_nx = _row_inv_norm(x)
-    with _lib.timed("l2norm_rows_w", dev):
-        inv_nw = _row_inv_norm(w)
+    f16n = use_tcgen05(x, cfg.engine, want_logits)
+    if not f16n and x.dtype != w.dtype:
+        raise TypeError(f"CUDA-core engine: x ({x.dtype}) and weight ({w.dtype}) must share a dtype")
+    xo, inv_nx = _k1(x, f16n)
+    wo, inv_nw = _prepare_weight(w, f16n, w_cache)
     row_stats = torch.empty(B, _lib.STAT_COLS, dtype=torch.float32, device=dev)
     row_best = torch.empty(B, dtype=torch.float32, device=dev)
     row_argmax = torch.empty(B, dtype=torch.int64, device=dev)
     cos_minmax = torch.empty(2, dtype=torch.float32, device=dev)
     nan_flag = torch.zeros(1, dtype=torch.int32, device=dev)
     logits = torch.empty(B, C, dtype=torch.float32, device=dev) if want_logits else None
-    nbytes = lib.b200f_head_workspace_bytes(B, C, D, dtype_code(x), cfg.engine)
+    nbytes = lib.b200f_head_workspace_bytes(B, C, D, dtype_code(xo), cfg.engine)
     ws = _lib.workspace(nbytes, dev, "head")
     with _lib.timed("arcface_fwd", dev):
-        check(lib.b200f_arcface_fwd(ptr(x), ptr(w), dtype_code(x), ptr(inv_nx), ptr(inv_nw), ptr(label), B, C,
+        check(lib.b200f_arcface_fwd(ptr(xo), ptr(wo), dtype_code(xo), ptr(inv_nx), ptr(inv_nw), ptr(label), B, C,
                                     int(class_offset), D, cfg, ptr(row_stats), ptr(row_best), ptr(row_argmax),
                                     ptr(cos_minmax), ptr(nan_flag), ptr(logits), C, ptr(ws), ws.numel(),
                                     stream_ptr(dev)), "b200f_arcface_fwd")
-    return inv_nx, inv_nw, row_stats, row_best, row_argmax, cos_minmax, nan_flag, logits
+    return xo, wo, inv_nx, inv_nw, row_stats, row_best, row_argmax, cos_minmax, nan_flag, logits
 
 
-def _bwd_kernels(x, w, label, inv_nx, inv_nw, lse, grad_scale, cfg: HeadCfg, class_offset,
-                 dlogits=None):
+def _bwd_kernels(xo, wo, label, inv_nx, inv_nw, lse, grad4, cfg: HeadCfg, class_offset, dlogits=None):
     lib = _lib.load_library()
-    B, D = x.shape
-    C = w.shape[0]
-    dev = x.device
+    B, D = xo.shape
+    C = wo.shape[0]
+    dev = xo.device
     dxhat = torch.empty(B, D, dtype=torch.float32, device=dev)
     dw = torch.empty(C, D, dtype=torch.float32, device=dev)
-    nbytes = lib.b200f_head_workspace_bytes(B, C, D, dtype_code(x), cfg.engine)
+    nbytes = lib.b200f_head_workspace_bytes(B, C, D, dtype_code(xo), cfg.engine)
     ws = _lib.workspace(nbytes, dev, "head")
     with _lib.timed("arcface_bwd", dev):
-        check(lib.b200f_arcface_bwd(ptr(x), ptr(w), dtype_code(x), ptr(inv_nx), ptr(inv_nw), ptr(label), ptr(lse),
-                                    ptr(grad_scale), ptr(dlogits), (dlogits.shape[1] if dlogits is not None else 0),
+        check(lib.b200f_arcface_bwd(ptr(xo), ptr(wo), dtype_code(xo), ptr(inv_nx), ptr(inv_nw), ptr(label), ptr(lse),
+                                    ptr(grad4), ptr(dlogits), (dlogits.shape[1] if dlogits is not None else 0),
                                     B, C, int(class_offset), D, cfg, ptr(dxhat), ptr(dw), ptr(ws), ws.numel(),
                                     stream_ptr(dev)), "b200f_arcface_bwd")
     return dxhat, dw
 
 
-def _normalize_bwd(x, inv_nx, dxhat):
+def _normalize_bwd(xo, inv_nx, dxhat):
     lib = _lib.load_library()
     dx = torch.empty_like(dxhat)
-    check(lib.b200f_l2norm_bwd(ptr(x), dtype_code(x), ptr(inv_nx), ptr(dxhat), x.shape[0], x.shape[1], ptr(dx),
-                               stream_ptr(x.device)), "b200f_l2norm_bwd")
+    check(lib.b200f_l2norm_bwd(ptr(xo), dtype_code(xo), OPERAND_SCALE, ptr(inv_nx), ptr(dxhat), xo.shape[0],
+                               xo.shape[1], ptr(dx), stream_ptr(xo.device)), "b200f_l2norm_bwd")
     return dx
 
 
@@ -154,12 +187,13 @@ class _ArcFaceLossFn(torch.autograd.Function):
     hook scalar + K3 (+ all-reduce) + normalise-backward in backward."""
 
     @staticmethod
-    def forward(ctx, x, weight, w, label, cfg: HeadCfg, class_offset, group, hook: _Hook, stats: HeadStats):
+    def forward(ctx, x, weight, w, label, cfg: HeadCfg, class_offset, group, hook: _Hook, stats: HeadStats,
+                w_cache):
         # weight: the tensor autograd differentiates (fp32 master or already x.dtype);
-        # w: what the kernels read (x.dtype; == weight or its cached bf16 shadow)
-        ctx.w_dtype = weight.dtype
-        inv_nx, inv_nw, row_stats, row_best, row_argmax, cos_minmax, nan_flag, _ = _fwd_kernels(
-            x, w, label, cfg, class_offset, False)
+        # w: what K1 reads (== weight, or a bf16 compute copy of it)
+        ctx.w_dtype, ctx.x_dtype = weight.dtype, x.dtype
+        x, w, inv_nx, inv_nw, row_stats, row_best, row_argmax, cos_minmax, nan_flag, _ = _fwd_kernels(
+            x, w, label, cfg, class_offset, False, w_cache)
         if group is not None:
             from . import parallel
             parallel.reduce_row_stats(row_stats, group)          # one SUM all-reduce of [B,4]
@@ -181,7 +215,7 @@ class _ArcFaceLossFn(torch.autograd.Function):
         cfg, hook = ctx.cfg, ctx.hook
         lib = _lib.load_library()
         up = grad_out.to(torch.float32).contiguous()
-        out3 = torch.empty(3, dtype=torch.float32, device=x.device)
+        out3 = torch.empty(4, dtype=torch.float32, device=x.device)
         check(lib.b200f_arcface_hook_scale(ptr(out2[1:]), ptr(up), x.shape[0], cfg.s_eff, int(hook.enabled),
                                            float(hook.max_grad_norm), int(hook.phase), int(hook.epoch),
                                            ptr(out3), stream_ptr(x.device)), "b200f_arcface_hook_scale")
@@ -192,7 +226,7 @@ class _ArcFaceLossFn(torch.autograd.Function):
             parallel.reduce_dxhat(dxhat, ctx.group)              # one SUM all-reduce of [B,D]
         dx = _normalize_bwd(x, inv_nx, dxhat)
         ctx.stats.dx_f32 = dx
-        return dx.to(x.dtype), dw.to(ctx.w_dtype), None, None, None, None, None, None, None
+        return dx.to(ctx.x_dtype), dw.to(ctx.w_dtype), None, None, None, None, None, None, None, None
 
 
 class _ArcLogitsFn(torch.autograd.Function):
@@ -202,7 +236,7 @@ class _ArcLogitsFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, w, label, cfg: HeadCfg, hook: _Hook, stats: HeadStats):
         ctx.w_dtype = weight.dtype
-        inv_nx, inv_nw, _rs, row_best, row_argmax, cos_minmax, nan_flag, logits = _fwd_kernels(
+        x, w, inv_nx, inv_nw, _rs, row_best, row_argmax, cos_minmax, nan_flag, logits = _fwd_kernels(
             x, w, label, cfg, 0, True)
         stats.row_best, stats.row_argmax = row_best, row_argmax
         stats.cos_minmax, stats.nan_flag = cos_minmax, nan_flag
@@ -226,7 +260,7 @@ class _ArcLogitsFn(torch.autograd.Function):
                 thr = min(thr, 0.5 + 0.05 * hook.epoch)
             thr_t = torch.where(n > 3.0, torch.clamp(torch.full_like(n, thr), max=0.5), torch.full_like(n, thr))
             kappa = torch.where(n > thr_t, thr_t / (n + 1e-8), torch.ones_like(n))
-        out3 = torch.stack([kappa * cfg.s_eff, n, kappa]).to(torch.float32)
+        out3 = torch.stack([kappa * cfg.s_eff, n, kappa, torch.ones_like(kappa)]).to(torch.float32)
         ctx.stats.hook_out = out3
         lse_dummy = torch.zeros(1, dtype=torch.float32, device=x.device)
         dxhat, dw = _bwd_kernels(x, w, label, inv_nx, inv_nw, lse_dummy, out3, cfg, 0, dlogits=dlogits)
@@ -238,21 +272,22 @@ class _ArcLogitsFn(torch.autograd.Function):
 def arcface_loss(x, weight, label, *, m_eff, s_eff, label_smoothing=0.05, easy_margin=False,
                  class_offset=0, num_classes_total=None, group=None, hook: Optional[_Hook] = None,
                  stats: Optional[HeadStats] = None, engine=_lib.ENGINE_AUTO,
-                 compute_weight: Optional[torch.Tensor] = None):
+                 compute_weight: Optional[torch.Tensor] = None, weight_cache: Optional[dict] = None):
     """Functional fused head: mean label-smoothed CE of the ArcFace logits of (x, weight).
     x [B,D] fp32 / bf16 CUDA, weight [C_local,D] (the tensor that receives the gradient: an fp32 master
     keeps an fp32 dW even when the kernels compute in bf16), label [B] int64 global ids.
     compute_weight: the copy of weight in x.dtype the kernels read (default: weight itself, or a cast)."""
     require_cuda(x, weight, label, compute_weight)
     if compute_weight is None:
-        compute_weight = weight.detach() if weight.dtype == x.dtype else weight.detach().to(x.dtype)
-    if x.dtype != compute_weight.dtype:
-        raise TypeError(f"x ({x.dtype}) and compute_weight ({compute_weight.dtype}) must share a dtype")
+        if weight.dtype == x.dtype or use_tcgen05(x, engine):
+            compute_weight = weight.detach()          # K1 reads the master directly (fp32 or bf16)
+        else:
+            compute_weight = weight.detach().to(x.dtype)
     cfg = _head_cfg(m_eff, s_eff, label_smoothing, easy_margin,
                     num_classes_total if num_classes_total is not None else weight.shape[0], engine)
     return _ArcFaceLossFn.apply(x.contiguous(), weight, compute_weight.contiguous(),
                                 label.contiguous().to(torch.int64), cfg, class_offset, group, hook or _Hook(),
-                                stats if stats is not None else HeadStats())
+                                stats if stats is not None else HeadStats(), weight_cache)
 
 
 class ArcMarginProduct(nn.Module):
@@ -282,6 +317,8 @@ class ArcMarginProduct(nn.Module):
         self.last_stats = HeadStats()
         self._hook = _Hook()
         self._w_shadow = None
+        self._w_prep = {}                  # K1 output for the current weight version
+        self.cache_weight_prep = True      # reuse K1(weight) until the parameter changes
 
     # -- schedule + effective parameters (host logic, stateful exactly like the reference) --------
     def _step_schedule(self):
@@ -300,15 +337,15 @@ class ArcMarginProduct(nn.Module):
             self.easy_margin_used = True
         return m_eff, s_eff
 
-    def _operands(self, input):
-        """(x, weight, w_compute): x in the compute dtype, the differentiated parameter, and the copy of
-        it the kernels read -- the parameter itself, or a bf16 shadow re-made only when the parameter
-        changes (optimizer step / load_state_dict bump its version counter)."""
+    def _operands(self, input, wants_logits=False):
+        """(x, weight, w_compute): x in the compute dtype, the differentiated parameter, and the tensor K1
+        reads.  tcgen05 engine: K1 normalises the fp32 master straight into fp16 operands, no shadow copy.
+        CUDA-core engine with a bf16 x and an fp32 master: a bf16 shadow, re-made when the parameter changes."""
         require_cuda(input, self.weight)
         dt = self.compute_dtype or (input.dtype if input.dtype in (torch.float32, torch.bfloat16)
                                     else torch.float32)
         x = input.to(dt).contiguous()
-        if self.weight.dtype == dt:
+        if self.weight.dtype == dt or use_tcgen05(x, self.engine, wants_logits):
             return x, self.weight, self.weight.detach()
         key = (self.weight._version, self.weight.data_ptr(), dt)
         if self._w_shadow is None or self._w_shadow[0] != key:
@@ -318,7 +355,7 @@ class ArcMarginProduct(nn.Module):
     def forward(self, input, label):
         """Scaled logits [B,C] fp32 (compatibility path; stores the logits)."""
         m_eff, s_eff = self._step_schedule()
-        x, weight, w = self._operands(input)
+        x, weight, w = self._operands(input, wants_logits=True)
         cfg = _head_cfg(m_eff, s_eff, 0.0, self.easy_margin, self.out_feats, self.engine)
         self.last_stats = HeadStats()
         return _ArcLogitsFn.apply(x, weight, w.contiguous(), label.contiguous().to(torch.int64), cfg, self._hook,
@@ -333,7 +370,8 @@ class ArcMarginProduct(nn.Module):
         self.last_stats = HeadStats()
         loss = arcface_loss(x, weight, label, m_eff=m_eff, s_eff=s_eff, label_smoothing=label_smoothing,
                             easy_margin=self.easy_margin, hook=self._hook, stats=self.last_stats,
-                            engine=self.engine, compute_weight=w)
+                            engine=self.engine, compute_weight=w,
+                            weight_cache=self._w_prep if self.cache_weight_prep else None)
         if return_pred:
             return loss, self.last_stats.row_argmax
         return loss

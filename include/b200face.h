@@ -14,7 +14,9 @@
  *   - the last argument is the cudaStream_t to launch on (void* so no CUDA header is needed);
  *   - no allocation, no implicit synchronisation, no global mutable state;
  *   - return 0 on success, <0 on error; b200f_last_error() gives the thread-local message.
- * Element types: B200F_F32 / B200F_BF16.  All arithmetic accumulates in fp32.
+ * Element types: B200F_F32 / B200F_BF16 run the head on the fp32 CUDA-core engine (fp32 products: the
+ * 1e-5 bar); B200F_F16N (K1's normalised fp16 output, made from bf16 or fp32 inputs) runs it on the
+ * tcgen05/TMEM/TMA engine.  All arithmetic accumulates in fp32.
  */
 #ifndef B200FACE_H_
 #define B200FACE_H_
@@ -28,6 +30,11 @@ extern "C" {
 
 #define B200F_F32   0
 #define B200F_BF16  1
+/* fp16 rows that are ALREADY L2-normalised and multiplied by a power of two (operand_scale below):
+ * what K1 emits for the tcgen05 engine.  x_hat / w_hat elements are <= 1 in magnitude, so fp16's 11-bit
+ * significand is used at full precision (bf16 inputs are widened, never narrowed).  Only valid as the
+ * out_dtype of b200f_l2norm_rows and as the operand dtype of the head calls on the tcgen05 engine. */
+#define B200F_F16N  2
 
 #define B200F_METRIC_L2EPS 0   /* || q - g + 1e-6 ||_2, ascending   (src/app.py:59)            */
 #define B200F_METRIC_COS   1   /* <q,g> * inv|q| * inv|g|, descending (hyperparameter_tuning.py:1046) */
@@ -55,7 +62,7 @@ typedef struct b200f_head_cfg {
   int32_t easy_margin;       /* 0: cos(min(pi-1e-4, theta+m)), 1: easy branch :372-397   */
   int64_t num_classes_total; /* C over all shards (label smoothing uses eps/C)            */
   int32_t engine;            /* B200F_ENGINE_*                                             */
-  int32_t reserved;
+  float   operand_scale;     /* B200F_F16N operands: x = x_hat * operand_scale, w = w_hat * operand_scale */
 } b200f_head_cfg;
 
 /* Per-row forward statistics, [B, B200F_STAT_COLS] fp32, additive over class shards
@@ -75,9 +82,10 @@ unsigned long long b200f_launch_count(void);
 int         b200f_has_tcgen05(void);
 
 /* K1 -- fused row L2-normalise: inv_norm[r] = 1 / max(||in[r,:]||_2, eps)  (F.normalize,
- * src/face_models.py:351-352,525).  out (optional) = in * inv_norm in out_dtype. */
+ * src/face_models.py:351-352,525).  out (optional) = in * inv_norm * out_scale in out_dtype
+ * (B200F_F32 / B200F_BF16 / B200F_F16N). */
 int b200f_l2norm_rows(const void* in, int in_dtype, int64_t rows, int dim, float eps,
-                      float* inv_norm, void* out_or_null, int out_dtype, void* stream);
+                      float* inv_norm, void* out_or_null, int out_dtype, float out_scale, void* stream);
 
 /* Bytes of workspace the head calls need for (B, C_local, D). */
 size_t b200f_head_workspace_bytes(int64_t B, int64_t C_local, int D, int dtype, int engine);
@@ -112,10 +120,12 @@ int b200f_arcface_loss(const float* row_stats, int64_t B, const b200f_head_cfg* 
  *   n = |upstream| * s_eff / B * sqrt(pq_norm2);  kappa = thr/(n+1e-8) if n > thr else 1
  *   with thr from (max_grad_norm, phase, epoch) and the n > 3 rule.
  * out[0] = grad_scale = upstream * kappa * s_eff / B   (what K3 multiplies (p-q) by)
- * out[1] = n (last_grad_norm), out[2] = kappa.   hook_enabled = 0 -> kappa = 1. */
+ * out[1] = n (last_grad_norm), out[2] = kappa, out[3] = g_scale (power of two with |grad_scale| * g_scale in
+ * (512, 1024]: range centring of the tcgen05 engine's fp16 logit-gradient buffer).  out has FOUR floats and
+ * is what b200f_arcface_bwd takes as grad_scale.   hook_enabled = 0 -> kappa = 1. */
 int b200f_arcface_hook_scale(const float* pq_norm2, const float* upstream, int64_t B,
                              float s_eff, int hook_enabled, float max_grad_norm, int phase,
-                             int epoch, float* out3, void* stream);
+                             int epoch, float* out4, void* stream);
 
 /* K3 -- backward for this shard: recompute the logits tile by tile, form
  *   G_ij = grad_scale * (p_ij - q_ij) * dphi/dc * 1[lo <= cos <= hi]
@@ -136,8 +146,9 @@ int b200f_arcface_bwd(const void* x, const void* w, int dtype,
                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* Normalise-backward for rows: dv = inv_n * (dvhat - vhat * <vhat, dvhat>), vhat = v * inv_n
- * (autograd of F.normalize, src/face_models.py:351,525).  dv fp32 [rows, dim]. */
-int b200f_l2norm_bwd(const void* v, int dtype, const float* inv_norm, const float* dvhat,
+ * (autograd of F.normalize, src/face_models.py:351,525).  dv fp32 [rows, dim].  With dtype B200F_F16N
+ * v holds v_hat * v_scale already (v_scale ignored otherwise).  dv may alias dvhat. */
+int b200f_l2norm_bwd(const void* v, int dtype, float v_scale, const float* inv_norm, const float* dvhat,
                      int64_t rows, int dim, float* dv, void* stream);
 
 /* K4 -- gallery match: for each query the k best rows of this gallery shard.
@@ -163,15 +174,14 @@ int b200f_gallery_merge(const int64_t* idx_all, const float* score_all, int P, i
 /* ---- tcgen05 engine: self-test and diagnostics (tests/test_gpu_umma.py, bench.py) ----------------
  * b200f_umma_selftest: out[M,N] fp32 = sum_k A(m,k) B(n,k) through the TMA + tcgen05 + TMEM GEMM core,
  *   for K-major (x_mn = 0: [rows,K] row-major) and MN-major (x_mn = 1: [K,rows] row-major) operands,
- *   bf16 x bf16 or (a_fp16) fp16 x bf16; with k_splits > 1 out is [k_splits, M, N] partial sums.
+ *   fmt 0 = bf16 x bf16, 2 = fp16 x fp16 (1 = fp16 x bf16 faults: not a hardware format pair); with k_splits > 1 out is [k_splits, M, N] partial sums.
  *   Descriptor byte offsets < 0 select the defaults.
  * b200f_umma_timeout_flag: 1 if a bounded pipeline wait ever expired (synchronises; reset clears it).
- * b200f_umma_set_option(0, v): logit-gradient operand of K3: 0 = bf16, 1 = fp16 (mixed-format MMA). */
+ */
 int b200f_umma_selftest(const void* a, const void* b, float* out, int M, int N, int K, int a_mn, int b_mn,
-                        int a_fp16, int k_splits, int a_lbo, int a_sbo, int a_kstep, int b_lbo, int b_sbo,
+                        int fmt, int k_splits, int a_lbo, int a_sbo, int a_kstep, int b_lbo, int b_sbo,
                         int b_kstep, void* stream);
 int b200f_umma_timeout_flag(int reset);
-int b200f_umma_set_option(int option, int value);
 
 #ifdef __cplusplus
 }

@@ -242,22 +242,22 @@ def test_class_shards_serial(cuda_device, dtype, n_shards):
         saved = []
         for lo, hi in bounds:
             ws = w[lo:hi].contiguous()
-            inv_nx, inv_nw, rs, *_ = H._fwd_kernels(x, ws, yd, cfg, lo, False)
+            xo, wo, inv_nx, inv_nw, rs, *_ = H._fwd_kernels(x, ws, yd, cfg, lo, False)
             stats += rs                                      # == the all-reduce
-            saved.append((ws, inv_nx, inv_nw, lo))
+            saved.append((xo, wo, inv_nx, inv_nw, lo))
         lse = torch.empty(B, device=cuda_device); out2 = torch.empty(2, device=cuda_device)
         _lib.check(lib.b200f_arcface_loss(_lib.ptr(stats), B, cfg, _lib.ptr(lse), _lib.ptr(out2), _lib.ptr(out2[1:]),
                                           _lib.stream_ptr(cuda_device)), "loss")
-        out3 = torch.empty(3, device=cuda_device)
-        _lib.check(lib.b200f_arcface_hook_scale(_lib.ptr(out2[1:]), None, B, s_eff, 0, 1.0, 1, 0, _lib.ptr(out3),
+        out4 = torch.empty(4, device=cuda_device)
+        _lib.check(lib.b200f_arcface_hook_scale(_lib.ptr(out2[1:]), None, B, s_eff, 0, 1.0, 1, 0, _lib.ptr(out4),
                                                 _lib.stream_ptr(cuda_device)), "hook")
         dxhat = torch.zeros(B, D, device=cuda_device)
         dws = []
-        for ws, inv_nx, inv_nw, lo in saved:
-            part, dw = H._bwd_kernels(x, ws, yd, inv_nx, inv_nw, lse, out3, cfg, lo)
+        for xo, wo, inv_nx, inv_nw, lo in saved:
+            part, dw = H._bwd_kernels(xo, wo, yd, inv_nx, inv_nw, lse, out4, cfg, lo)
             dxhat += part
             dws.append(dw)
-        dx = H._normalize_bwd(x, saved[0][1], dxhat)
+        dx = H._normalize_bwd(saved[0][0], saved[0][2], dxhat)
         return float(out2[0]), dx, torch.cat(dws)
 
     loss1, dx1, dw1 = run([(0, C)])
