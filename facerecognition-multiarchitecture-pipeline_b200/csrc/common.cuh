@@ -112,7 +112,9 @@ struct HeadMath {
   __device__ __forceinline__ float phi(float c) const {
     float theta = acosf(c);
     if (easy) return (c > 0.0f) ? cosf(theta + m_eff) : c;
-    return cosf(fminf(B200F_PI_CLAMP, theta + m_eff));
+    const float tm = theta + m_eff;
+    // torch.minimum propagates NaN (fminf would return the clamp and hide it from the :423 scrub)
+    return cosf((tm != tm) ? tm : fminf(B200F_PI_CLAMP, tm));
   }
   // d phi / d c  (autograd of acos -> +m -> minimum -> cos)
   __device__ __forceinline__ float dphi(float c) const {

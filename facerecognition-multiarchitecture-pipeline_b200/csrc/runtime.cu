@@ -32,9 +32,9 @@ int num_sms() {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 148;
   if (dev != cached_dev) {
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 148;
-    cached = prop.multiProcessorCount;
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 148;
+    cached = n;
     cached_dev = dev;
   }
   return cached;
@@ -57,11 +57,18 @@ unsigned long long b200f_launch_count(void) { return launch_count(); }
 const char* b200f_last_error(void) { return last_error_ref().c_str(); }
 
 int b200f_has_tcgen05(void) {
+  // cudaGetDeviceProperties costs milliseconds: ask once per device (this is on the per-step host path)
+  static std::atomic<int> cache[64];            // 0 = unknown, 1 = no, 2 = yes
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-  cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 0;
-  return (prop.major == 10) ? 1 : 0;
+  if (dev >= 0 && dev < 64) {
+    const int c = cache[dev].load(std::memory_order_relaxed);
+    if (c != 0) return c == 2;
+  }
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  if (dev >= 0 && dev < 64) cache[dev].store(major == 10 ? 2 : 1, std::memory_order_relaxed);
+  return major == 10 ? 1 : 0;
 }
 
 int b200f_l2norm_rows(const void* in, int in_dtype, int64_t rows, int dim, float eps, float* inv_norm,

@@ -189,11 +189,14 @@ static Plan make_plan(int64_t B, int64_t C, int D) {
 }
 
 static bool device_is_sm100() {
-  static int cached = -1;
-  if (cached < 0) {
-    int dev = 0; cudaDeviceProp prop;
-    cached = (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess &&
-              prop.major == 10) ? 1 : 0;
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  if (dev != cached_dev) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return false;
+    cached = (major == 10) ? 1 : 0;
+    cached_dev = dev;
   }
   return cached == 1;
 }
