@@ -1,15 +1,18 @@
 // tcgen05 / TMEM / TMA engine for the ArcFace head: host side.
 // Operands are the fp16, L2-normalised, power-of-two-scaled rows K1 emits (dtype B200F_F16N).
-//   K2  forward statistics : gemm_kernel<K,K,EpiFwd>           x_hat[B,D] . w_hat[C,D]^T
-//   K3a logit gradient     : gemm_kernel<K,K,EpiBwdG>          recompute + G (fp16, L2-resident chunk)
+//   K2  forward statistics : xw_kernel<PAIR, XwFwd>            x_hat[B,D] . w_hat[C,D]^T, x_hat resident in smem
+//   K3a logit gradient     : xw_kernel<PAIR, XwBwdG>           recompute + G (fp16, L2-resident chunk)
 //   K3b dW_hat = G^T x_hat : gemm_kernel<MN,MN,EpiStore>       then normalise-backward in place
 //   K3c dx_hat = G w_hat   : gemm_kernel<K,MN,EpiStore> split-K, then a fixed-order reduction
+// PAIR = 2 runs K2 / K3a on tcgen05 cta_group::2 CTA pairs (clusters of two), PAIR = 1 on single CTAs.
 // ALL tcgen05 kernels of the library live in this one translation unit (g_umma_timeout_flag).
 #include "umma_api.cuh"
 #include "umma_epilogues.cuh"
+#include "umma_xw_epilogues.cuh"
 #include "rowops.cuh"
 
 #include <cudaTypedefs.h>
+#include <atomic>
 #include <mutex>
 
 namespace b200f {
@@ -101,7 +104,7 @@ reduce_row_partials_kernel(const float* __restrict__ part, int n_parts, int64_t 
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, best = -INFINITY;
     int bi = INT32_MAX;
     for (int c = lane; c < n_parts; c += 32) {
-      const float* src = part + ((int64_t)c * B + row) * PART_COLS;
+      const float* src = part + (row * n_parts + c) * PART_COLS;       // [B, n_parts, PART_COLS]: coalesced
       s0 += src[0]; s1 += src[1]; s2 += src[2]; s3 += src[3];
       const int idx = reinterpret_cast<const int32_t*>(src)[5];
       if (idx >= 0 && (src[4] > best || (src[4] == best && idx < bi))) { best = src[4]; bi = idx; }
@@ -151,9 +154,86 @@ __global__ void reduce_splits_kernel(const float* __restrict__ part, int n_split
   *reinterpret_cast<float4*>(dst + i) = s;
 }
 
+// ---- X-stationary kernel: launch geometry ---------------------------------------------------------
+static std::atomic<int> g_pair{2};                 // 2 = tcgen05 cta_group::2 CTA pairs, 1 = single CTAs
+
+template <int PAIR, class Epi>
+static int xw_set_smem() {
+  static thread_local int done_dev = -1;
+  int dev = 0;
+  B200F_CUDA_OK(cudaGetDevice(&dev));
+  if (done_dev != dev) {
+    B200F_CUDA_OK(cudaFuncSetAttribute(xw_kernel<PAIR, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XW_SMEM_BYTES));
+    done_dev = dev;
+  }
+  return B200F_OK;
+}
+
+// clusters of `pair` CTAs that can be co-resident (1 CTA per SM: 227 KB of shared memory each)
+static int xw_max_clusters(int pair) {
+  if (pair == 1) return num_sms();
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return num_sms() / 2;
+  if (dev != cached_dev) {
+    int n = 0;
+    if (xw_set_smem<2, XwFwd>() == B200F_OK) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)num_sms() / 2 * 2); cfg.blockDim = dim3(XW_THREADS); cfg.dynamicSmemBytes = XW_SMEM_BYTES;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      if (cudaOccupancyMaxActiveClusters(&n, xw_kernel<2, XwFwd>, &cfg) != cudaSuccess) { n = 0; (void)cudaGetLastError(); }
+    }
+    if (n <= 0 || n > num_sms() / 2) n = num_sms() / 2;
+    cached = n; cached_dev = dev;
+  }
+  return cached;
+}
+
+static int gcd_int(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
+
+struct XwPlan { int pair, m_groups, n_tiles, n_clusters, n_chunks, items, grid; };
+
+static XwPlan xw_plan(int64_t B, int64_t C, int pair) {
+  XwPlan q{};
+  q.pair = pair;
+  q.m_groups = (int)ceil_div(B, (int64_t)XW_M * pair);
+  q.n_tiles = (int)ceil_div(C, (int64_t)XW_WROWS * pair);
+  q.n_clusters = xw_max_clusters(pair);
+  // items = m_groups * n_chunks is a multiple of the cluster count whenever the class range allows it
+  int nc = q.n_clusters / gcd_int(q.n_clusters, q.m_groups);
+  if (nc > q.n_tiles) nc = q.n_tiles;
+  if (nc < 1) nc = 1;
+  q.n_chunks = nc;
+  q.items = q.m_groups * q.n_chunks;
+  q.grid = pair * (q.items < q.n_clusters ? q.items : q.n_clusters);
+  return q;
+}
+
+template <int PAIR, class Epi>
+static int launch_xw(const CUtensorMap& tx, const CUtensorMap& tw, const XwPlan& q, int64_t B, int64_t C, int D,
+                     const typename Epi::Params& ep, cudaStream_t st, const char* what) {
+  int rc = xw_set_smem<PAIR, Epi>(); if (rc) return rc;
+  XwParams p{};
+  p.B = (int)B; p.C = (int)C; p.D = D;
+  p.kb_count = (int)ceil_div(D, XW_K);
+  p.m_groups = q.m_groups; p.n_tiles = q.n_tiles; p.n_chunks = q.n_chunks;
+  p.idesc = make_idesc(FMT_F16, FMT_F16, false, false, XW_M * PAIR, XW_WROWS * PAIR);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)q.grid); cfg.blockDim = dim3(XW_THREADS); cfg.dynamicSmemBytes = XW_SMEM_BYTES; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = PAIR; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, xw_kernel<PAIR, Epi>, tx, tw, p, ep);
+  if (e != cudaSuccess) return fail(B200F_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+  B200F_LAUNCH_OK(what);
+  return B200F_OK;
+}
+
 // ---- plan -------------------------------------------------------------------------------------------
 struct Plan {
-  int m_tiles, n_tiles;
+  XwPlan fwd;
   size_t off_part, off_cos;
   int64_t Cc, ldg; int n_chunks, dx_splits;
   size_t off_G, off_dxpart;
@@ -162,11 +242,16 @@ struct Plan {
 
 static Plan make_plan(int64_t B, int64_t C, int D) {
   Plan pl{};
-  pl.m_tiles = (int)ceil_div(B, BLOCK_M);
-  pl.n_tiles = (int)ceil_div(C, BLOCK_N);
+  const int pair = g_pair.load(std::memory_order_relaxed);
+  pl.fwd = xw_plan(B, C, pair);
+  const int m_tiles = (int)ceil_div(B, BLOCK_M);
   size_t off = 0;
-  pl.off_part = off; off += align_up(sizeof(float) * (size_t)pl.n_tiles * B * PART_COLS, 256);
-  pl.off_cos = off;  off += align_up(sizeof(float) * 2 * 4 * (size_t)pl.n_tiles * pl.m_tiles, 256);
+  // sized for either pairing so that a workspace stays valid when the mode is switched
+  const XwPlan p1 = xw_plan(B, C, 1), p2 = xw_plan(B, C, 2);
+  const size_t part_max = (size_t)(p1.n_chunks > p2.n_chunks ? p1.n_chunks : p2.n_chunks);
+  const size_t cos_max = (size_t)(p1.items > 2 * p2.items ? p1.items : 2 * p2.items) * XW_EPI_WARPS;
+  pl.off_part = off; off += align_up(sizeof(float) * part_max * B * PART_COLS, 256);
+  pl.off_cos = off;  off += align_up(sizeof(float) * 2 * cos_max, 256);
   const size_t fwd_total = off;
   // backward: the fp16 logit-gradient chunk should stay L2-resident (126 MB L2): <= 48 MB
   int64_t cc_max = ((int64_t)(48u << 20) / 2 / B) / BLOCK_N * BLOCK_N;
@@ -175,7 +260,7 @@ static Plan make_plan(int64_t B, int64_t C, int D) {
   pl.Cc = ceil_div(ceil_div(C, pl.n_chunks), BLOCK_N) * BLOCK_N;
   pl.n_chunks = (int)ceil_div(C, pl.Cc);
   pl.ldg = pl.Cc;
-  const int out_tiles = pl.m_tiles * (int)ceil_div(D, BLOCK_N);
+  const int out_tiles = m_tiles * (int)ceil_div(D, BLOCK_N);
   int splits = num_sms() / out_tiles;
   if (splits < 1) splits = 1;
   const int kchunks = (int)(pl.Cc / BLOCK_K);
@@ -209,7 +294,8 @@ static char* ws_align(char* ws) { return reinterpret_cast<char*>((reinterpret_ca
 
 static int check_shape(int64_t B, int64_t C, int D, const b200f_head_cfg* cfg) {
   if (!device_is_sm100()) return fail(B200F_ERR_UNSUPPORTED, "tcgen05 engine needs an sm_100 device");
-  if (D % 8 != 0) return fail(B200F_ERR_UNSUPPORTED, "tcgen05 engine needs D %% 8 == 0 (got %d)", D);
+  if (D % 8 != 0 || D > XW_MAX_KB * XW_K)
+    return fail(B200F_ERR_UNSUPPORTED, "tcgen05 engine needs D %% 8 == 0 and D <= %d (got %d)", XW_MAX_KB * XW_K, D);
   if (B >= ((int64_t)1 << 30) || C >= ((int64_t)1 << 30)) return fail(B200F_ERR_UNSUPPORTED, "tcgen05 engine: B, C < 2^30");
   if (!(cfg->operand_scale > 0.f)) return fail(B200F_ERR_ARG, "tcgen05 engine: cfg.operand_scale must be > 0");
   return B200F_OK;
@@ -222,21 +308,22 @@ int head_fwd(const void* xh, const void* wh, const int64_t* label, int64_t B, in
   const Plan pl = make_plan(B, C, D);
   if (ws_bytes < pl.total) return fail(B200F_ERR_WORKSPACE, "umma head_fwd: workspace too small");
   ws = ws_align(ws);
-  CUtensorMap ta, tb;
-  rc = tmap_kmajor(&ta, xh, B, D, D, BLOCK_M); if (rc) return rc;
-  rc = tmap_kmajor(&tb, wh, C, D, D, BLOCK_N); if (rc) return rc;
-  GemmParams p = gemm_params((int)B, (int)C, D, 1, false, false, FMT_F16, FMT_F16);
-  EpiFwd::Params ep{};
-  ep.label = label; ep.B = B; ep.C = C; ep.class_offset = class_offset;
+  CUtensorMap tx, tw;
+  rc = tmap_kmajor(&tx, xh, B, D, D, XW_M); if (rc) return rc;
+  rc = tmap_kmajor(&tw, wh, C, D, D, XW_WROWS); if (rc) return rc;
+  const XwPlan& q = pl.fwd;
+  XwFwd::Params ep{};
+  ep.label = label; ep.class_offset = class_offset;
   ep.hm = HeadMath{cfg->m_eff, cfg->s_eff, cfg->easy_margin};
   ep.inv_scale = 1.0f / (cfg->operand_scale * cfg->operand_scale);
   ep.part = reinterpret_cast<float*>(ws + pl.off_part);
   ep.cos_part = reinterpret_cast<float*>(ws + pl.off_cos);
-  ep.nan_flag = nan_flag;
-  rc = launch_gemm<false, false, EpiFwd>(ta, tb, p, ep, st, "umma K2 arcface_fwd");
+  ep.nan_flag = nan_flag; ep.pair = q.pair;
+  rc = (q.pair == 2) ? launch_xw<2, XwFwd>(tx, tw, q, B, C, D, ep, st, "umma K2 arcface_fwd (cta pair)")
+                     : launch_xw<1, XwFwd>(tx, tw, q, B, C, D, ep, st, "umma K2 arcface_fwd");
   if (rc) return rc;
-  reduce_row_partials_kernel<<<(unsigned)ceil_div(B, 8), 256, 0, st>>>(ep.part, pl.n_tiles, B, ep.cos_part,
-                                                                      4 * pl.n_tiles * pl.m_tiles, row_stats, row_best,
+  reduce_row_partials_kernel<<<(unsigned)ceil_div(B, 8), 256, 0, st>>>(ep.part, q.n_chunks, B, ep.cos_part,
+                                                                      q.items * q.pair * XW_EPI_WARPS, row_stats, row_best,
                                                                       row_argmax, cos_minmax);
   B200F_LAUNCH_OK("reduce_row_partials_kernel");
   return B200F_OK;
@@ -253,19 +340,20 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
   float* dxpart = reinterpret_cast<float*>(ws + pl.off_dxpart);
   const float S = cfg->operand_scale;
   CUtensorMap tx_k, tx_mn;
-  rc = tmap_kmajor(&tx_k, xh, B, D, D, BLOCK_M); if (rc) return rc;
+  rc = tmap_kmajor(&tx_k, xh, B, D, D, XW_M); if (rc) return rc;
   rc = tmap_mnmajor(&tx_mn, xh, D, B, D); if (rc) return rc;
   int chunk_no = 0;
   for (int64_t c0 = 0; c0 < C; c0 += pl.Cc, ++chunk_no) {
     const int64_t cnt = (C - c0 < pl.Cc) ? (C - c0) : pl.Cc;
     const uint16_t* wc = static_cast<const uint16_t*>(wh) + c0 * D;
-    // --- K3a: logit gradient of the chunk
+    // --- K3a: logit gradient of the chunk (x_hat resident, w_hat rows [c0, c0 + cnt) streamed)
     CUtensorMap tw_k;
-    rc = tmap_kmajor(&tw_k, wc, cnt, D, D, BLOCK_N); if (rc) return rc;
-    GemmParams pg = gemm_params((int)B, (int)cnt, D, 1, false, false, FMT_F16, FMT_F16);
-    EpiBwdG::Params eg{label, lse, grad4, B, C, class_offset, c0, HeadMath{cfg->m_eff, cfg->s_eff, cfg->easy_margin},
-                       cfg->label_smoothing, 1.0f / (float)cfg->num_classes_total, 1.0f / (S * S), G, pl.ldg};
-    rc = launch_gemm<false, false, EpiBwdG>(tx_k, tw_k, pg, eg, st, "umma K3a logit-grad");
+    rc = tmap_kmajor(&tw_k, wc, cnt, D, D, XW_WROWS); if (rc) return rc;
+    const XwPlan qg = xw_plan(B, cnt, pl.fwd.pair);
+    XwBwdG::Params eg{label, lse, grad4, class_offset + c0, HeadMath{cfg->m_eff, cfg->s_eff, cfg->easy_margin},
+                      cfg->label_smoothing, 1.0f / (float)cfg->num_classes_total, 1.0f / (S * S), G, pl.ldg};
+    rc = (qg.pair == 2) ? launch_xw<2, XwBwdG>(tx_k, tw_k, qg, B, cnt, D, eg, st, "umma K3a logit-grad (cta pair)")
+                        : launch_xw<1, XwBwdG>(tx_k, tw_k, qg, B, cnt, D, eg, st, "umma K3a logit-grad");
     if (rc) return rc;
     // --- K3b: dW_hat[c0 + m, :] = sum_b G[b, m] x_hat[b, :]
     CUtensorMap tg_mn;
@@ -328,6 +416,29 @@ int b200f_umma_selftest(const void* a, const void* b, float* out, int M, int N, 
   if (a_mn && b_mn) return launch_gemm<true, true, EpiStore>(ta, tb, p, ep, st, "umma selftest MM");
   if (!a_mn && b_mn) return launch_gemm<false, true, EpiStore>(ta, tb, p, ep, st, "umma selftest KM");
   return fail(B200F_ERR_UNSUPPORTED, "umma_selftest: A MN-major with B K-major is not instantiated");
+}
+
+// Self-test of the X-stationary kernel: out[B,C] (fp32) = x[B,D] . w[C,D]^T with fp16 operands, on single CTAs
+// (pair = 1) or tcgen05 cta_group::2 CTA pairs (pair = 2).
+int b200f_umma_xw_selftest(const void* x, const void* w, float* out, int B, int C, int D, int pair, void* stream) {
+  if (!x || !w || !out || B <= 0 || C <= 0 || D <= 0 || (pair != 1 && pair != 2))
+    return fail(B200F_ERR_ARG, "umma_xw_selftest: bad argument");
+  if (!device_is_sm100()) return fail(B200F_ERR_UNSUPPORTED, "umma_xw_selftest: device is not sm_100");
+  if (D % 8 != 0 || D > XW_MAX_KB * XW_K) return fail(B200F_ERR_UNSUPPORTED, "umma_xw_selftest: D %% 8 == 0 and D <= 512");
+  CUtensorMap tx, tw;
+  int rc = tmap_kmajor(&tx, x, B, D, D, XW_M); if (rc) return rc;
+  rc = tmap_kmajor(&tw, w, C, D, D, XW_WROWS); if (rc) return rc;
+  const XwPlan q = xw_plan(B, C, pair);
+  XwStore::Params ep{out, (int64_t)C};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return (pair == 2) ? launch_xw<2, XwStore>(tx, tw, q, B, C, D, ep, st, "umma xw selftest (cta pair)")
+                     : launch_xw<1, XwStore>(tx, tw, q, B, C, D, ep, st, "umma xw selftest");
+}
+
+// Selects single-CTA (1) or CTA-pair (2, default) execution of K2 / K3a; returns the previous setting.
+int b200f_umma_set_pair(int pair) {
+  if (pair != 1 && pair != 2) return g_pair.load();
+  return g_pair.exchange(pair);
 }
 
 // Reads (and optionally clears) the pipeline-timeout flag.  Synchronises: test / bench use only.

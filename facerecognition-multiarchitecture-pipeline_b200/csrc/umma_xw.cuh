@@ -1,0 +1,330 @@
+// X-stationary tcgen05 kernel for the two cosine-logit stages of the head (K2 forward statistics, K3a logit
+// gradient):   S[b, c] = sum_k x_hat(b, k) * w_hat(c, k)      fp16 operands, fp32 accumulation in TMEM.
+//
+// Why not the generic GEMM core (umma_gemm.cuh): with 128 x 256 output tiles every k-block re-reads 48 KB of
+// operands from L2 per 512 tensor cycles -- 94 B/clk/SM against an L2 that sustains ~42 B/clk/SM chip-wide --
+// so the generic core is L2-bound at ~1/3 of the tensor peak.  Here
+//   * a CTA keeps its 128 rows of x_hat (<= 128 KB, D <= 512) resident in shared memory for a whole work
+//     item and streams only class-weight tiles through a 5-stage TMA ring, and
+//   * (PAIR = 2) two CTAs of a cluster form one tcgen05 cta_group::2 pair: one 256 x 256 x 16 MMA per k-step
+//     spans both SMs, each CTA loads only ITS 128 classes of the weight tile, so the per-SM L2 ingest drops
+//     to 16 KB per 512 tensor cycles (32 B/clk/SM) and W is read from L2 once per 256 rows of the batch.
+//
+// Roles per CTA (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA of the pair only),
+// warps 2..9 = epilogue (two warps per TMEM lane quadrant; each takes half of the tile's columns; the next
+// 32-column tcgen05.ld is in flight while the current one is processed).  Accumulators are double-buffered
+// in TMEM (2 x 256 columns).
+//
+// Work: item = (row group g of 128*PAIR rows, class chunk); a cluster walks items cluster_id, +n_clusters, ..
+// The Epilogue policy sees every 32-column slice of the accumulators plus item begin / end hooks, so per-row
+// statistics stay in registers across all class tiles of an item (one partial record per row and chunk).
+#pragma once
+#include "umma_core.cuh"
+
+namespace b200f {
+namespace umma {
+
+constexpr int XW_M = 128;                       // rows of x per CTA
+constexpr int XW_WROWS = 128;                   // class rows per CTA per stage (tile width = 128 * PAIR)
+constexpr int XW_K = 64;                        // k-block (one 128 B swizzle row of fp16)
+constexpr int XW_MAX_KB = 8;                    // D <= 512 stays resident
+constexpr int XW_STAGES = 5;
+constexpr int XW_TILE_BYTES = XW_M * XW_K * 2;  // 16 KB: one k-block of x, or one stage of w
+constexpr int XW_EPI_WARPS = 8;
+constexpr int XW_THREADS = 64 + 32 * XW_EPI_WARPS;   // 320
+constexpr int XW_SCRATCH_FLOATS = 2048;
+constexpr int XW_NUM_BARS = 2 + 2 * XW_STAGES + 4;
+constexpr size_t XW_SMEM_BYTES = 1024 + (size_t)(XW_MAX_KB + XW_STAGES) * XW_TILE_BYTES + XW_SCRATCH_FLOATS * 4 + 256;
+constexpr uint32_t XW_ACC_STRIDE = 256;         // TMEM columns between the two accumulator stages
+
+// ---- cluster / CTA-pair primitives ------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier that sits at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+// TMA load issued by either CTA of a pair; the transaction bytes land on the LEADER CTA's barrier
+// (peer bit of the shared::cluster address cleared).
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+template <int PAIR>
+__device__ __forceinline__ void xw_tma_load(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  if (PAIR == 2) tma_load_2d_pair(smem_dst, m, bar, c0, c1);
+  else tma_load_2d(smem_dst, m, bar, c0, c1);
+}
+template <int PAIR>
+__device__ __forceinline__ void xw_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  if (PAIR == 2) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    mma_f16_ss(tmem_d, da, db, idesc, accumulate);
+  }
+}
+// completion of all MMAs issued so far -> arrive on `bar` (in BOTH CTAs of a pair)
+template <int PAIR>
+__device__ __forceinline__ void xw_commit(uint64_t* bar) {
+  if (PAIR == 2) {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+  } else {
+    mma_commit(bar);
+  }
+}
+template <int PAIR>
+__device__ __forceinline__ void xw_tmem_alloc(uint32_t* slot, uint32_t ncols) {   // whole warp
+  if (PAIR == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  } else {
+    tmem_alloc(slot, ncols);
+  }
+}
+template <int PAIR>
+__device__ __forceinline__ void xw_tmem_dealloc(uint32_t taddr, uint32_t ncols) {  // whole warp
+  if (PAIR == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  else tmem_dealloc(taddr, ncols);
+}
+
+// tcgen05.ld without the wait (software pipelining), and a wait that carries the registers as operands so
+// the compiler cannot schedule their uses above it.
+__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, float (&v)[32]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait_dep(float (&v)[32]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.wait::ld.sync.aligned;"
+      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+        "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+        "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+        "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+      :
+      : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() {      // the 256 epilogue threads only
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+}
+
+struct XwParams {
+  int B, C, D;                          // rows of x, classes of this launch, feature dim
+  int kb_count;                         // ceil(D / 64) <= XW_MAX_KB
+  int m_groups, n_tiles, n_chunks;      // row groups of 128*PAIR rows, class tiles of 128*PAIR, class chunks
+  uint32_t idesc;
+};
+
+struct XwItem {                         // what an epilogue thread knows about its work item
+  int item, chunk, group;
+  int rank, ew, quad, half, lane;       // CTA rank in the pair, epilogue warp 0..7, TMEM quadrant, column half, lane
+  int64_t row;                          // global row of x owned by this thread
+};
+
+// Epilogue policy interface:
+//   struct Epi { struct Params; struct State;
+//     static __device__ void item_begin(State&, const Params&, const XwParams&, const XwItem&);
+//     static __device__ void slice(State&, const Params&, const XwParams&, const XwItem&, float (&v)[32], int cls0);
+//         v = accumulators of row it.row for classes [cls0, cls0 + 32) of this launch (warp-uniform cls0 < C)
+//     static __device__ void item_end(State&, const Params&, const XwParams&, const XwItem&, float* scratch); }
+template <int PAIR, class Epi>
+__global__ void __launch_bounds__(XW_THREADS, 1)
+xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const XwParams p,
+          const typename Epi::Params ep) {
+  constexpr int TN = XW_WROWS * PAIR;                        // class-tile width of the cluster
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* xres = smem;                                      // XW_MAX_KB x 16 KB
+  uint8_t* ring = smem + (size_t)XW_MAX_KB * XW_TILE_BYTES;  // XW_STAGES x 16 KB
+  float* scratch = reinterpret_cast<float*>(ring + (size_t)XW_STAGES * XW_TILE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + XW_SCRATCH_FLOATS);
+  uint64_t* x_full = bars;                                   // TMA -> MMA (leader)
+  uint64_t* x_empty = bars + 1;                              // MMA -> TMA (both CTAs)
+  uint64_t* full_bar = bars + 2;                             // [STAGES] TMA -> MMA (leader)
+  uint64_t* empty_bar = bars + 2 + XW_STAGES;                // [STAGES] MMA -> TMA (both CTAs)
+  uint64_t* acc_full = bars + 2 + 2 * XW_STAGES;             // [2] MMA -> epilogue (both CTAs)
+  uint64_t* acc_empty = acc_full + 2;                        // [2] epilogue (both CTAs) -> MMA (leader)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + XW_NUM_BARS);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rank = (PAIR == 2) ? (int)cluster_ctarank() : 0;
+  const int cluster_id = blockIdx.x / PAIR;
+  const int n_clusters = gridDim.x / PAIR;
+  const int items = p.m_groups * p.n_chunks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_w);
+    mbar_init(x_full, PAIR);
+    mbar_init(x_empty, 1);
+    for (int s = 0; s < XW_STAGES; ++s) { mbar_init(&full_bar[s], PAIR); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], PAIR * XW_EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == 1) xw_tmem_alloc<PAIR>(tmem_slot, 512);
+  tc_fence_before_sync();
+  __syncthreads();
+  if (PAIR == 2) cluster_sync_all();                         // the peer's barriers exist before anyone signals them
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer (one lane, both CTAs) =================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int item_no = 0;
+      bool ok = true;
+      for (int item = cluster_id; item < items && ok; item += n_clusters, ++item_no) {
+        const int g = item % p.m_groups, chunk = item / p.m_groups;
+        const int t_begin = (int)((int64_t)chunk * p.n_tiles / p.n_chunks);
+        const int t_end = (int)((int64_t)(chunk + 1) * p.n_tiles / p.n_chunks);
+        if (item_no > 0) { ok = mbar_wait(x_empty, (uint32_t)((item_no - 1) & 1)); if (!ok) break; }
+        if (rank == 0) mbar_arrive_expect_tx(x_full, (uint32_t)(PAIR * p.kb_count * XW_TILE_BYTES));
+        else mbar_arrive_cluster(x_full, 0);
+        const int row0 = (g * PAIR + rank) * XW_M;
+        for (int kb = 0; kb < p.kb_count; ++kb)
+          xw_tma_load<PAIR>(xres + (size_t)kb * XW_TILE_BYTES, &tm_x, x_full, kb * XW_K, row0);
+        for (int t = t_begin; t < t_end && ok; ++t) {
+          const int n0 = t * TN + rank * XW_WROWS;
+          for (int kb = 0; kb < p.kb_count; ++kb) {
+            ok = mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (!ok) break;
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(PAIR * XW_TILE_BYTES));
+            else mbar_arrive_cluster(&full_bar[stage], 0);
+            xw_tma_load<PAIR>(ring + (size_t)stage * XW_TILE_BYTES, &tm_w, &full_bar[stage], kb * XW_K, n0);
+            if (++stage == XW_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+      // do not leave while the leader's last commit may still signal this CTA's barriers
+      if (ok && item_no > 0) mbar_wait(x_empty, (uint32_t)((item_no - 1) & 1));
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (one lane of the leader CTA) =================
+    if (lane == 0 && rank == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      int item_no = 0;
+      bool ok = true;
+      const uint32_t xres_addr = smem_u32(xres), ring_addr = smem_u32(ring);
+      for (int item = cluster_id; item < items && ok; item += n_clusters, ++item_no) {
+        const int chunk = item / p.m_groups;
+        const int t_begin = (int)((int64_t)chunk * p.n_tiles / p.n_chunks);
+        const int t_end = (int)((int64_t)(chunk + 1) * p.n_tiles / p.n_chunks);
+        ok = mbar_wait(x_full, (uint32_t)(item_no & 1));
+        if (!ok) break;
+        tc_fence_after_sync();
+        for (int t = t_begin; t < t_end && ok; ++t) {
+          ok = mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+          if (!ok) break;
+          tc_fence_after_sync();
+          const uint32_t d_tmem = tmem_base + (uint32_t)acc * XW_ACC_STRIDE;
+          for (int kb = 0; kb < p.kb_count; ++kb) {
+            ok = mbar_wait(&full_bar[stage], phase);
+            if (!ok) break;
+            tc_fence_after_sync();
+            const uint32_t sa = xres_addr + (uint32_t)kb * XW_TILE_BYTES;
+            const uint32_t sb = ring_addr + (uint32_t)stage * XW_TILE_BYTES;
+#pragma unroll
+            for (int kk = 0; kk < XW_K / 16; ++kk) {
+              const uint64_t da = make_smem_desc(sa + kk * 32, 0, 1024);
+              const uint64_t db = make_smem_desc(sb + kk * 32, 0, 1024);
+              xw_mma<PAIR>(d_tmem, da, db, p.idesc, (uint32_t)((kb | kk) != 0));
+            }
+            xw_commit<PAIR>(&empty_bar[stage]);
+            if (++stage == XW_STAGES) { stage = 0; phase ^= 1; }
+          }
+          if (!ok) break;
+          xw_commit<PAIR>(&acc_full[acc]);
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if (ok) xw_commit<PAIR>(x_empty);
+      }
+    }
+  } else {
+    // ================= epilogue (8 warps, both CTAs) =================
+    XwItem it;
+    it.rank = rank; it.ew = warp - 2; it.quad = warp & 3; it.half = (warp - 2) >> 2; it.lane = lane;
+    int acc = 0; uint32_t acc_phase = 0;
+    bool ok = true;
+    constexpr int SLICES = TN / 64;                            // 32-column slices per warp per tile
+    for (int item = cluster_id; item < items && ok; item += n_clusters) {
+      it.item = item; it.group = item % p.m_groups; it.chunk = item / p.m_groups;
+      it.row = (int64_t)(it.group * PAIR + rank) * XW_M + it.quad * 32 + lane;
+      const int t_begin = (int)((int64_t)it.chunk * p.n_tiles / p.n_chunks);
+      const int t_end = (int)((int64_t)(it.chunk + 1) * p.n_tiles / p.n_chunks);
+      typename Epi::State stt;
+      Epi::item_begin(stt, ep, p, it);
+      for (int t = t_begin; t < t_end; ++t) {
+        ok = mbar_wait(&acc_full[acc], acc_phase);
+        ok = __all_sync(0xffffffffu, ok);
+        if (!ok) break;
+        tc_fence_after_sync();
+        const int col_base = it.half * (TN / 2);
+        const uint32_t taddr = tmem_base + (uint32_t)acc * XW_ACC_STRIDE + ((uint32_t)(it.quad * 32) << 16) + (uint32_t)col_base;
+        const int cls_base = t * TN + col_base;
+        float va[32], vb[32];
+        tmem_ld32_async(taddr, va);
+#pragma unroll
+        for (int s = 0; s < SLICES; ++s) {
+          if ((s & 1) == 0) {
+            tmem_ld_wait_dep(va);
+            if (s + 1 < SLICES) tmem_ld32_async(taddr + (uint32_t)(s + 1) * 32, vb);
+            if (cls_base + s * 32 < p.C) Epi::slice(stt, ep, p, it, va, cls_base + s * 32);
+          } else {
+            tmem_ld_wait_dep(vb);
+            if (s + 1 < SLICES) tmem_ld32_async(taddr + (uint32_t)(s + 1) * 32, va);
+            if (cls_base + s * 32 < p.C) Epi::slice(stt, ep, p, it, vb, cls_base + s * 32);
+          }
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) {
+          if (PAIR == 2) mbar_arrive_cluster(&acc_empty[acc], 0);
+          else mbar_arrive(&acc_empty[acc]);
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      if (!ok) break;
+      Epi::item_end(stt, ep, p, it, scratch);
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (PAIR == 2) cluster_sync_all();
+  if (warp == 1) { tc_fence_after_sync(); xw_tmem_dealloc<PAIR>(tmem_base, 512); }
+}
+
+}  // namespace umma
+}  // namespace b200f

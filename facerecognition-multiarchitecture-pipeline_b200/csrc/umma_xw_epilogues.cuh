@@ -1,0 +1,261 @@
+// Epilogue policies of the X-stationary kernel (umma_xw.cuh) for the ArcFace head.
+//
+// Operands are the fp16 rows K1 emits: x_hat * S and w_hat * S (already L2-normalised, S a power of two), so
+// an accumulator is  acc = S^2 * cos(theta)  and the epilogues need no per-row / per-column scale.  Every
+// policy has a fast path for whole 32-column slices (no clamp, no target column, no NaN scrub -- validated
+// after the fact from the slice's min / max / sum) and a careful path that applies the reference's
+// element-wise sequence (src/face_models.py:363-427) to the same registers.
+#pragma once
+#include <cuda_fp16.h>
+#include "common.cuh"
+#include "umma_epilogues.cuh"
+#include "umma_xw.cuh"
+
+namespace b200f {
+namespace umma {
+
+constexpr int PART_COLS = 6;   // sumexp, sumexp2, ztarget, sumz, best, bestidx (int32 bits)
+
+// -------------------------------------------------------------------------------------------------
+// Raw accumulators -> out[row, class] (self-test of the kernel itself).
+struct XwStore {
+  struct Params { float* out; int64_t ld; };
+  struct State { bool row_ok; };
+  static __device__ __forceinline__ void item_begin(State& st, const Params&, const XwParams& p, const XwItem& it) {
+    st.row_ok = it.row < p.B;
+  }
+  static __device__ __forceinline__ void slice(State& st, const Params& ep, const XwParams& p, const XwItem& it,
+                                               float (&v)[32], int cls0) {
+    if (!st.row_ok) return;
+    const int cc = min(32, p.C - cls0);
+    float* dst = ep.out + it.row * ep.ld + cls0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) if (j < cc) dst[j] = v[j];
+  }
+  static __device__ __forceinline__ void item_end(State&, const Params&, const XwParams&, const XwItem&, float*) {}
+};
+
+// -------------------------------------------------------------------------------------------------
+// K2: cosine logits -> margin -> scale -> softmax / cross-entropy statistics (src/face_models.py:355-427,
+// training.py:515).  Nothing B x C is stored: ONE partial record per (row, class chunk).
+struct XwFwd {
+  struct Params {
+    const int64_t* label;
+    int64_t class_offset;       // global id of this launch's class 0
+    HeadMath hm;
+    float inv_scale;            // 1 / S^2 : cos = acc * inv_scale
+    float* part;                // [B, n_chunks, PART_COLS]
+    float* cos_part;            // [items * PAIR * 8, 2]
+    int32_t* nan_flag;
+    int pair;
+  };
+  struct State {
+    float sumexp, sumexp2, sumz, ztgt, best, cmin, cmax;
+    int bestidx, tgt;
+    bool row_ok, saw_nan;
+  };
+
+  static __device__ __forceinline__ void item_begin(State& st, const Params& ep, const XwParams& p, const XwItem& it) {
+    st.sumexp = st.sumexp2 = st.sumz = st.ztgt = 0.f;
+    st.best = -INFINITY; st.bestidx = -1;
+    st.cmin = INFINITY; st.cmax = -INFINITY;
+    st.saw_nan = false;
+    st.row_ok = it.row < p.B;
+    st.tgt = -1;
+    if (st.row_ok) {
+      const int64_t tg = __ldg(ep.label + it.row) - ep.class_offset;
+      if (tg >= 0 && tg < p.C) st.tgt = (int)tg;
+    }
+  }
+
+  static __device__ __forceinline__ void slice(State& st, const Params& ep, const XwParams& p, const XwItem& it,
+                                               float (&v)[32], int cls0) {
+    const int cc = min(32, p.C - cls0);
+    const float s_eff = ep.hm.s_eff;
+    const float isc = ep.inv_scale;
+    const float zs = isc * s_eff;                             // z = acc * zs off the target column
+    const float a = zs * LOG2E, b = -s_eff * LOG2E;           // exp(z - s_eff) = 2^(acc*a + b)
+    const float lo = cos_lo(), hi = cos_hi();
+    // four independent accumulator lanes: the dependent chains are 8 long, not 32 (latency, not issue, bounds
+    // a lone epilogue warp); the summation order is still fixed, so results are bitwise reproducible
+    float ce4[4] = {0.f, 0.f, 0.f, 0.f}, cq4[4] = {0.f, 0.f, 0.f, 0.f}, ct4[4] = {0.f, 0.f, 0.f, 0.f};
+    float mn4[4] = {INFINITY, INFINITY, INFINITY, INFINITY}, mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float tt = v[j + u];
+        const float e = ex2_approx(fmaf(tt, a, b));
+        ce4[u] += e;
+        cq4[u] = fmaf(e, e, cq4[u]);
+        ct4[u] += tt;
+        mn4[u] = fminf(mn4[u], tt);
+        mx4[u] = fmaxf(mx4[u], tt);
+      }
+    }
+    const float ce = (ce4[0] + ce4[1]) + (ce4[2] + ce4[3]);
+    const float ce2 = (cq4[0] + cq4[1]) + (cq4[2] + cq4[3]);
+    const float ct = (ct4[0] + ct4[1]) + (ct4[2] + ct4[3]);
+    const float tmn = fminf(fminf(mn4[0], mn4[1]), fminf(mn4[2], mn4[3]));
+    const float tmx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+    const bool has_t = (st.tgt >= cls0) && (st.tgt < cls0 + 32);
+    bool careful = !(s_eff > 0.f) || has_t || (cc < 32) || !(tmx * isc <= hi) || !(tmn * isc >= lo) ||
+                   !isfinite(ct) || !isfinite(ce);
+    careful = __any_sync(0xffffffffu, careful);               // warp stays convergent for the next tcgen05.ld
+    if (!careful) {
+      st.sumexp += ce; st.sumexp2 += ce2; st.sumz = fmaf(ct, zs, st.sumz);
+      st.cmin = fminf(st.cmin, tmn * isc); st.cmax = fmaxf(st.cmax, tmx * isc);
+      const float bz = tmx * zs;
+      if (bz > st.best) {                                     // rare after the first few slices
+        st.best = bz;
+        int tix = 31;
+#pragma unroll
+        for (int j = 30; j >= 0; --j) if (v[j] == tmx) tix = j;   // first index of the maximum
+        st.bestidx = cls0 + tix;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (j < cc) {
+          const float cosv = v[j] * isc;
+          st.cmin = fminf(st.cmin, cosv); st.cmax = fmaxf(st.cmax, cosv);
+          const float c = (cosv != cosv) ? cosv : fminf(fmaxf(cosv, lo), hi);
+          const bool is_t = (cls0 + j == st.tgt);
+          const float tv = is_t ? ep.hm.phi(c) : c;
+          float z = tv * s_eff;
+          if (!isfinite(z)) { z = 0.f; st.saw_nan = true; }
+          if (is_t) st.ztgt = z;
+          const float e = exp2f((z - s_eff) * LOG2E);
+          st.sumexp += e; st.sumexp2 = fmaf(e, e, st.sumexp2); st.sumz += z;
+          if (z > st.best) { st.best = z; st.bestidx = cls0 + j; }
+        }
+      }
+    }
+    (void)it;
+  }
+
+  static __device__ __forceinline__ void item_end(State& st, const Params& ep, const XwParams& p, const XwItem& it,
+                                                  float* scratch) {
+    // the two column halves of a row live in two warps: the upper half parks its record in shared memory
+    float* slot = scratch + (it.quad * 32 + it.lane) * 8;
+    if (it.half == 1) {
+      slot[0] = st.sumexp; slot[1] = st.sumexp2; slot[2] = st.ztgt; slot[3] = st.sumz; slot[4] = st.best;
+      reinterpret_cast<int*>(slot)[5] = st.bestidx;
+    }
+    epi_bar_sync();
+    if (it.half == 0 && st.row_ok) {
+      const float ob = slot[4];
+      const int oi = reinterpret_cast<const int*>(slot)[5];
+      float best = st.best; int bi = st.bestidx;
+      if (oi >= 0 && (bi < 0 || ob > best || (ob == best && oi < bi))) { best = ob; bi = oi; }
+      float* dst = ep.part + (it.row * p.n_chunks + it.chunk) * PART_COLS;
+      dst[0] = st.sumexp + slot[0]; dst[1] = st.sumexp2 + slot[1]; dst[2] = st.ztgt + slot[2];
+      dst[3] = st.sumz + slot[3]; dst[4] = best;
+      reinterpret_cast<int32_t*>(dst)[5] = (bi < 0) ? -1 : (int32_t)(ep.class_offset + bi);
+    }
+    float cmin = st.row_ok ? st.cmin : INFINITY, cmax = st.row_ok ? st.cmax : -INFINITY;
+    cmin = warp_min(cmin); cmax = warp_max(cmax);
+    if (it.lane == 0) {
+      float* cp = ep.cos_part + 2 * (((int64_t)it.item * ep.pair + it.rank) * XW_EPI_WARPS + it.ew);
+      cp[0] = cmin; cp[1] = cmax;
+    }
+    if (__any_sync(0xffffffffu, st.saw_nan) && it.lane == 0) atomicExch(ep.nan_flag, 1);
+    epi_bar_sync();
+  }
+};
+
+// -------------------------------------------------------------------------------------------------
+// K3a: recompute the logits of a class chunk and emit the logit gradient as fp16 (one L2-resident buffer
+// that both consumer GEMMs read),
+//   G_ij = g_scale * grad_scale * (p_ij - q_ij) * dphi/dc * 1[lo <= cos <= hi]      (SURVEY 8a closed form)
+// grad4 = {grad_scale, n, kappa, g_scale} from b200f_arcface_hook_scale; g_scale is the power of two that
+// puts |grad_scale| * g_scale in (512, 1024], so a target-column entry (|p-q| <= 1, dphi <~ 30) stays below
+// fp16 max and entries down to p ~ 1e-7 stay normal; the consumers divide it out again.
+struct XwBwdG {
+  struct Params {
+    const int64_t* label; const float* lse; const float* grad4;
+    int64_t class_offset;       // global id of this launch's class 0
+    HeadMath hm;
+    float ls_eps, inv_Ctot, inv_scale;
+    uint16_t* G; int64_t ldg;   // G[row, class of this launch]
+  };
+  struct State { float lse, gs; int tgt; bool row_ok; };
+
+  static __device__ __forceinline__ void item_begin(State& st, const Params& ep, const XwParams& p, const XwItem& it) {
+    st.row_ok = it.row < p.B;
+    st.lse = st.row_ok ? __ldg(ep.lse + it.row) : 0.f;
+    st.gs = __ldg(ep.grad4) * __ldg(ep.grad4 + 3);
+    st.tgt = -1;
+    if (st.row_ok) {
+      const int64_t tg = __ldg(ep.label + it.row) - ep.class_offset;
+      if (tg >= 0 && tg < p.C) st.tgt = (int)tg;
+    }
+  }
+
+  static __device__ __forceinline__ void slice(State& st, const Params& ep, const XwParams& p, const XwItem& it,
+                                               float (&v)[32], int cls0) {
+    const int cc = min(32, p.C - cls0);
+    const float s_eff = ep.hm.s_eff;
+    const float isc = ep.inv_scale;
+    const float a = isc * s_eff * LOG2E, b = -st.lse * LOG2E; // p = 2^(acc*a + b)
+    const float lo = cos_lo(), hi = cos_hi();
+    const float gs = st.gs;
+    const float q_off = ep.ls_eps * ep.inv_Ctot;
+    const float gq = gs * q_off;
+    float g[32];
+    float mn4[4] = {INFINITY, INFINITY, INFINITY, INFINITY}, mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    float ck4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float tt = v[j + u];
+        g[j + u] = fmaf(gs, ex2_approx(fmaf(tt, a, b)), -gq);
+        mn4[u] = fminf(mn4[u], tt); mx4[u] = fmaxf(mx4[u], tt);
+        ck4[u] += tt;
+      }
+    }
+    const float tmn = fminf(fminf(mn4[0], mn4[1]), fminf(mn4[2], mn4[3]));
+    const float tmx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+    const float chk = (ck4[0] + ck4[1]) + (ck4[2] + ck4[3]);
+    const bool has_t = (st.tgt >= cls0) && (st.tgt < cls0 + 32);
+    bool careful = !(s_eff > 0.f) || has_t || !(tmx * isc <= hi) || !(tmn * isc >= lo) || !isfinite(chk);
+    careful = __any_sync(0xffffffffu, careful);
+    if (careful) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float cosv = v[j] * isc;
+        const float c = (cosv != cosv) ? cosv : fminf(fmaxf(cosv, lo), hi);
+        const bool is_t = (cls0 + j == st.tgt);
+        const float tv = is_t ? ep.hm.phi(c) : c;
+        float z = tv * s_eff;
+        float f = is_t ? ep.hm.dphi(c) : 1.0f;
+        if (!isfinite(z)) { z = 0.f; f = 0.f; }
+        if (!(cosv >= lo && cosv <= hi)) f = 0.f;
+        const float pr = exp2f((z - st.lse) * LOG2E);
+        const float q = is_t ? (1.0f - ep.ls_eps) + q_off : q_off;
+        g[j] = fminf(fmaxf(gs * (pr - q) * f, -65504.f), 65504.f);
+      }
+    }
+    if (st.row_ok) {
+      uint16_t* gdst = ep.G + it.row * ep.ldg + cls0;
+      if (cc == 32) {
+        uint32_t w1[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) w1[j] = pack_f16(g[2 * j], g[2 * j + 1]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(gdst + 8 * j) = make_uint4(w1[4 * j], w1[4 * j + 1], w1[4 * j + 2], w1[4 * j + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < cc) gdst[j] = (uint16_t)(pack_f16(g[j], 0.f) & 0xffff);
+      }
+    }
+  }
+
+  static __device__ __forceinline__ void item_end(State&, const Params&, const XwParams&, const XwItem&, float*) {}
+};
+
+}  // namespace umma
+}  // namespace b200f

@@ -78,6 +78,7 @@ def _head_cfg(m_eff, s_eff, label_smoothing, easy, c_total, engine) -> HeadCfg:
                    int(engine), OPERAND_SCALE)
 
 
+TCGEN05_MAX_D = 512     # x_hat rows stay resident in shared memory (8 k-blocks of 64): csrc/umma_xw.cuh
 OPERAND_SCALE = 256.0   # K1 emits x_hat * 2^8 / w_hat * 2^8 in fp16 for the tcgen05 engine (|x_hat| <= 1)
 
 
@@ -107,9 +108,9 @@ def l2_normalize(t: torch.Tensor, out_dtype: Optional[torch.dtype] = None):
 def use_tcgen05(x: torch.Tensor, engine: int, wants_logits: bool = False) -> bool:
     """Engine choice (include/b200face.h): bf16 inputs go to the tcgen05/TMEM/TMA engine, fp32 inputs to the
     fp32 CUDA-core engine (the 1e-5 bar needs fp32 products) unless the caller forces an engine."""
-    if engine == _lib.ENGINE_SIMT or wants_logits or x.shape[1] % 8 != 0:
+    if engine == _lib.ENGINE_SIMT or wants_logits or x.shape[1] % 8 != 0 or x.shape[1] > TCGEN05_MAX_D:
         if engine == _lib.ENGINE_TCGEN05:
-            raise RuntimeError("the tcgen05 engine needs D % 8 == 0 and does not store logits")
+            raise RuntimeError("the tcgen05 engine needs D % 8 == 0, D <= 512 and does not store logits")
         return False
     if not _lib.load_library().b200f_has_tcgen05():
         if engine == _lib.ENGINE_TCGEN05:

@@ -182,6 +182,11 @@ int b200f_umma_selftest(const void* a, const void* b, float* out, int M, int N, 
                         int fmt, int k_splits, int a_lbo, int a_sbo, int a_kstep, int b_lbo, int b_sbo,
                         int b_kstep, void* stream);
 int b200f_umma_timeout_flag(int reset);
+/* b200f_umma_xw_selftest: out[B,C] fp32 = x[B,D] . w[C,D]^T (fp16 operands, D % 8 == 0, D <= 512) through the
+ *   X-stationary kernel that carries K2 / K3a, on single CTAs (pair = 1) or cta_group::2 CTA pairs (pair = 2).
+ * b200f_umma_set_pair: process-wide choice between the two for the head calls (default 2); returns the old one. */
+int b200f_umma_xw_selftest(const void* x, const void* w, float* out, int B, int C, int D, int pair, void* stream);
+int b200f_umma_set_pair(int pair);
 
 #ifdef __cplusplus
 }

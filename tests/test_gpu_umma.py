@@ -43,6 +43,27 @@ def test_gemm_core_many_tiles_persistent(cuda_device):
     assert _run(cuda_device, 1024, 148 * 256 + 512, 256, 0, 0, 2) < 2e-6
 
 
+@pytest.mark.parametrize("pair", [1, 2])
+@pytest.mark.parametrize("B,C,D", [(128, 128, 64), (256, 256, 512), (512, 4096, 512), (300, 1000, 200), (8, 8, 8),
+                                   (1024, 148 * 300, 512), (130, 70000, 512)])
+def test_xw_kernel(cuda_device, B, C, D, pair):
+    """The X-stationary kernel that carries K2 / K3a (x_hat resident in shared memory, class tiles streamed), on
+    single CTAs and on tcgen05 cta_group::2 CTA pairs: raw accumulators against torch fp32 matmul."""
+    import b200face
+    from b200face import _lib
+    lib = b200face.load_library()
+    g = torch.Generator(device=cuda_device).manual_seed(B + C + D)
+    x = torch.randn(B, D, generator=g, device=cuda_device).half()
+    w = torch.randn(C, D, generator=g, device=cuda_device).half()
+    out = torch.full((B, C), float("nan"), device=cuda_device)
+    _lib.check(lib.b200f_umma_xw_selftest(_lib.ptr(x), _lib.ptr(w), _lib.ptr(out), B, C, D, pair,
+                                          _lib.stream_ptr(cuda_device)), "umma_xw_selftest")
+    torch.cuda.synchronize()
+    assert lib.b200f_umma_timeout_flag(1) == 0, "a bounded pipeline wait expired"
+    ref = x.float() @ w.float().t()
+    assert float((out - ref).norm() / ref.norm()) < 2e-6
+
+
 @pytest.mark.parametrize("in_dt", [torch.float32, torch.bfloat16])
 def test_k1_emits_normalised_fp16_operands(cuda_device, in_dt):
     from b200face.head import OPERAND_SCALE, _k1
