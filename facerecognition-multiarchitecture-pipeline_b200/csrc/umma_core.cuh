@@ -56,6 +56,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: returns false (and raises the global flag) instead of spinning forever.
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
+#pragma unroll 1
   for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
     if (mbar_try_wait(bar, parity)) return true;
   }

@@ -154,16 +154,27 @@ __global__ void reduce_splits_kernel(const float* __restrict__ part, int n_split
   *reinterpret_cast<float4*>(dst + i) = s;
 }
 
+// coef[c] = { inv_nw[c] / (S g_scale), sum_rb r_part[rb, c] } for the classes of one chunk (fixed order)
+__global__ void reduce_r_kernel(const float* __restrict__ r_part, int n_rb, int64_t ldr, int64_t cnt,
+                                const float* __restrict__ inv_nw, const float* __restrict__ grad4, float S,
+                                float2* __restrict__ coef) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cnt) return;
+  float s = 0.f;
+  for (int rb = 0; rb < n_rb; ++rb) s += r_part[(int64_t)rb * ldr + c];
+  coef[c] = make_float2(__ldg(inv_nw + c) / (S * __ldg(grad4 + 3)), s);
+}
+
 // ---- X-stationary kernel: launch geometry ---------------------------------------------------------
 static std::atomic<int> g_pair{2};                 // 2 = tcgen05 cta_group::2 CTA pairs, 1 = single CTAs
 
-template <int PAIR, class Epi>
+template <int PAIR, bool MN, class Epi>
 static int xw_set_smem() {
   static thread_local int done_dev = -1;
   int dev = 0;
   B200F_CUDA_OK(cudaGetDevice(&dev));
   if (done_dev != dev) {
-    B200F_CUDA_OK(cudaFuncSetAttribute(xw_kernel<PAIR, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XW_SMEM_BYTES));
+    B200F_CUDA_OK(cudaFuncSetAttribute(xw_kernel<PAIR, MN, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XW_SMEM_BYTES));
     done_dev = dev;
   }
   return B200F_OK;
@@ -177,13 +188,13 @@ static int xw_max_clusters(int pair) {
   if (cudaGetDevice(&dev) != cudaSuccess) return num_sms() / 2;
   if (dev != cached_dev) {
     int n = 0;
-    if (xw_set_smem<2, XwFwd>() == B200F_OK) {
+    if (xw_set_smem<2, false, XwFwd>() == B200F_OK) {
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3((unsigned)num_sms() / 2 * 2); cfg.blockDim = dim3(XW_THREADS); cfg.dynamicSmemBytes = XW_SMEM_BYTES;
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
-      if (cudaOccupancyMaxActiveClusters(&n, xw_kernel<2, XwFwd>, &cfg) != cudaSuccess) { n = 0; (void)cudaGetLastError(); }
+      if (cudaOccupancyMaxActiveClusters(&n, xw_kernel<2, false, XwFwd>, &cfg) != cudaSuccess) { n = 0; (void)cudaGetLastError(); }
     }
     if (n <= 0 || n > num_sms() / 2) n = num_sms() / 2;
     cached = n; cached_dev = dev;
@@ -211,21 +222,21 @@ static XwPlan xw_plan(int64_t B, int64_t C, int pair) {
   return q;
 }
 
-template <int PAIR, class Epi>
+template <int PAIR, bool MN, class Epi>
 static int launch_xw(const CUtensorMap& tx, const CUtensorMap& tw, const XwPlan& q, int64_t B, int64_t C, int D,
                      const typename Epi::Params& ep, cudaStream_t st, const char* what) {
-  int rc = xw_set_smem<PAIR, Epi>(); if (rc) return rc;
+  int rc = xw_set_smem<PAIR, MN, Epi>(); if (rc) return rc;
   XwParams p{};
   p.B = (int)B; p.C = (int)C; p.D = D;
   p.kb_count = (int)ceil_div(D, XW_K);
   p.m_groups = q.m_groups; p.n_tiles = q.n_tiles; p.n_chunks = q.n_chunks;
-  p.idesc = make_idesc(FMT_F16, FMT_F16, false, false, XW_M * PAIR, XW_WROWS * PAIR);
+  p.idesc = make_idesc(FMT_F16, FMT_F16, MN, MN, XW_M * PAIR, XW_WROWS * PAIR);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)q.grid); cfg.blockDim = dim3(XW_THREADS); cfg.dynamicSmemBytes = XW_SMEM_BYTES; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = PAIR; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, xw_kernel<PAIR, Epi>, tx, tw, p, ep);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, xw_kernel<PAIR, MN, Epi>, tx, tw, p, ep);
   if (e != cudaSuccess) return fail(B200F_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
   B200F_LAUNCH_OK(what);
   return B200F_OK;
@@ -236,7 +247,9 @@ struct Plan {
   XwPlan fwd;
   size_t off_part, off_cos;
   int64_t Cc, ldg; int n_chunks, dx_splits;
-  size_t off_G, off_dxpart;
+  size_t off_G, off_dxpart, off_rpart, off_coef;
+  int n_rb;                 // 32-row blocks of the batch that K3a emits r partials for
+  bool fused_dw;            // B <= 512: dW GEMM on the MN-major X-stationary kernel with the normalise-backward fused
   size_t total;
 };
 
@@ -269,6 +282,10 @@ static Plan make_plan(int64_t B, int64_t C, int D) {
   off = 0;
   pl.off_G = off;      off += align_up(2 * (size_t)B * pl.ldg, 1024);
   pl.off_dxpart = off; off += align_up(sizeof(float) * (size_t)splits * B * D, 256);
+  pl.fused_dw = (B <= (int64_t)XW_MAX_KB * XW_K);
+  pl.n_rb = (int)ceil_div(B, 2 * XW_M) * 2 * 4;          // covers either pairing
+  pl.off_rpart = off; off += pl.fused_dw ? align_up(sizeof(float) * (size_t)pl.n_rb * pl.Cc, 256) : 0;
+  pl.off_coef = off;  off += pl.fused_dw ? align_up(sizeof(float2) * (size_t)C, 256) : 0;
   pl.total = (off > fwd_total ? off : fwd_total) + 1024;
   return pl;
 }
@@ -319,8 +336,8 @@ int head_fwd(const void* xh, const void* wh, const int64_t* label, int64_t B, in
   ep.part = reinterpret_cast<float*>(ws + pl.off_part);
   ep.cos_part = reinterpret_cast<float*>(ws + pl.off_cos);
   ep.nan_flag = nan_flag; ep.pair = q.pair;
-  rc = (q.pair == 2) ? launch_xw<2, XwFwd>(tx, tw, q, B, C, D, ep, st, "umma K2 arcface_fwd (cta pair)")
-                     : launch_xw<1, XwFwd>(tx, tw, q, B, C, D, ep, st, "umma K2 arcface_fwd");
+  rc = (q.pair == 2) ? launch_xw<2, false, XwFwd>(tx, tw, q, B, C, D, ep, st, "umma K2 arcface_fwd (cta pair)")
+                     : launch_xw<1, false, XwFwd>(tx, tw, q, B, C, D, ep, st, "umma K2 arcface_fwd");
   if (rc) return rc;
   reduce_row_partials_kernel<<<(unsigned)ceil_div(B, 8), 256, 0, st>>>(ep.part, q.n_chunks, B, ep.cos_part,
                                                                       q.items * q.pair * XW_EPI_WARPS, row_stats, row_best,
@@ -350,18 +367,33 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
     CUtensorMap tw_k;
     rc = tmap_kmajor(&tw_k, wc, cnt, D, D, XW_WROWS); if (rc) return rc;
     const XwPlan qg = xw_plan(B, cnt, pl.fwd.pair);
+    float* r_part = pl.fused_dw ? reinterpret_cast<float*>(ws + pl.off_rpart) : nullptr;
     XwBwdG::Params eg{label, lse, grad4, class_offset + c0, HeadMath{cfg->m_eff, cfg->s_eff, cfg->easy_margin},
-                      cfg->label_smoothing, 1.0f / (float)cfg->num_classes_total, 1.0f / (S * S), G, pl.ldg};
-    rc = (qg.pair == 2) ? launch_xw<2, XwBwdG>(tx_k, tw_k, qg, B, cnt, D, eg, st, "umma K3a logit-grad (cta pair)")
-                        : launch_xw<1, XwBwdG>(tx_k, tw_k, qg, B, cnt, D, eg, st, "umma K3a logit-grad");
+                      cfg->label_smoothing, 1.0f / (float)cfg->num_classes_total, 1.0f / (S * S), G, pl.ldg,
+                      r_part, pl.Cc, qg.pair};
+    rc = (qg.pair == 2) ? launch_xw<2, false, XwBwdG>(tx_k, tw_k, qg, B, cnt, D, eg, st, "umma K3a logit-grad (cta pair)")
+                        : launch_xw<1, false, XwBwdG>(tx_k, tw_k, qg, B, cnt, D, eg, st, "umma K3a logit-grad");
     if (rc) return rc;
-    // --- K3b: dW_hat[c0 + m, :] = sum_b G[b, m] x_hat[b, :]
     CUtensorMap tg_mn;
     rc = tmap_mnmajor(&tg_mn, G, cnt, B, pl.ldg); if (rc) return rc;
-    GemmParams pw = gemm_params((int)cnt, D, (int)B, 1, true, true, FMT_F16, FMT_F16);
-    EpiStore::Params ew{dw, (int64_t)D, 0, c0, 1.0f / S, grad4 + 3};
-    rc = launch_gemm<true, true, EpiStore>(tg_mn, tx_mn, pw, ew, st, "umma K3b dW");
-    if (rc) return rc;
+    if (pl.fused_dw) {
+      // --- K3b: dW[c0 + c, d] = inv_nw_c (sum_b G[b, c] x_hat[b, d] - w_hat[c, d] r_c), x_hat^T resident, G streamed
+      float2* coef = reinterpret_cast<float2*>(ws + pl.off_coef);
+      reduce_r_kernel<<<(unsigned)ceil_div(cnt, 256), 256, 0, st>>>(r_part, qg.m_groups * qg.pair * 4, pl.Cc, cnt,
+                                                                  inv_nw + c0, grad4, S, coef + c0);
+      B200F_LAUNCH_OK("umma reduce_r_kernel");
+      const XwPlan qw = xw_plan(D, cnt, qg.pair);
+      XwDw::Params ew{coef, static_cast<const __half*>(wh), dw, c0, D};
+      rc = (qw.pair == 2) ? launch_xw<2, true, XwDw>(tx_mn, tg_mn, qw, D, cnt, (int)B, ew, st, "umma K3b dW (cta pair)")
+                          : launch_xw<1, true, XwDw>(tx_mn, tg_mn, qw, D, cnt, (int)B, ew, st, "umma K3b dW");
+      if (rc) return rc;
+    } else {
+      // --- K3b (batch > 512): dW_hat[c0 + m, :] = sum_b G[b, m] x_hat[b, :] on the generic core
+      GemmParams pw = gemm_params((int)cnt, D, (int)B, 1, true, true, FMT_F16, FMT_F16);
+      EpiStore::Params ew{dw, (int64_t)D, 0, c0, 1.0f / S, grad4 + 3};
+      rc = launch_gemm<true, true, EpiStore>(tg_mn, tx_mn, pw, ew, st, "umma K3b dW");
+      if (rc) return rc;
+    }
     // --- K3c: dx_hat partials = G[:, k-range] w_hat[c0 + k-range, :]
     CUtensorMap tg_k, tw_mn;
     rc = tmap_kmajor(&tg_k, G, B, cnt, pl.ldg, BLOCK_M); if (rc) return rc;
@@ -375,9 +407,11 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
                                                                         1.0f / S, grad4 + 3);
     B200F_LAUNCH_OK("umma reduce_splits_kernel");
   }
-  // normalise-backward of the weight rows, in place: dw <- inv_nw * (dw_hat - w_hat <w_hat, dw_hat>)
-  rowops::launch_l2norm_bwd<__half, true>(static_cast<const __half*>(wh), S, inv_nw, dw, C, D, dw, st);
-  B200F_LAUNCH_OK("l2norm_bwd kernel (weights)");
+  if (!pl.fused_dw) {
+    // normalise-backward of the weight rows, in place: dw <- inv_nw * (dw_hat - w_hat <w_hat, dw_hat>)
+    rowops::launch_l2norm_bwd<__half, true>(static_cast<const __half*>(wh), S, inv_nw, dw, C, D, dw, st);
+    B200F_LAUNCH_OK("l2norm_bwd kernel (weights)");
+  }
   return B200F_OK;
 }
 
@@ -431,8 +465,8 @@ int b200f_umma_xw_selftest(const void* x, const void* w, float* out, int B, int 
   const XwPlan q = xw_plan(B, C, pair);
   XwStore::Params ep{out, (int64_t)C};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return (pair == 2) ? launch_xw<2, XwStore>(tx, tw, q, B, C, D, ep, st, "umma xw selftest (cta pair)")
-                     : launch_xw<1, XwStore>(tx, tw, q, B, C, D, ep, st, "umma xw selftest");
+  return (pair == 2) ? launch_xw<2, false, XwStore>(tx, tw, q, B, C, D, ep, st, "umma xw selftest (cta pair)")
+                     : launch_xw<1, false, XwStore>(tx, tw, q, B, C, D, ep, st, "umma xw selftest");
 }
 
 // Selects single-CTA (1) or CTA-pair (2, default) execution of K2 / K3a; returns the previous setting.

@@ -138,8 +138,13 @@ __device__ __forceinline__ void epi_bar_sync() {      // the 256 epilogue thread
   asm volatile("bar.sync 1, 256;" ::: "memory");
 }
 
+// MN = false: both operands K-major (x[B, D], w[C, D] row-major: the cosine-logit stages).
+// MN = true : both operands MN-major, i.e. stored [k, rows] row-major: out[m, n] = sum_k x[k, m] * w[k, n].  The dW
+//             stage runs as dW^T[d, c] = sum_b x_hat[b, d] * G[b, c] this way: x_hat^T stays resident, logit-gradient
+//             columns stream, and an epilogue thread owns one feature d, so its 32 lanes write 128 contiguous bytes
+//             of a dW row.  "B" is then the extent of m (D), "C" of n (classes), "D" of k (the batch).
 struct XwParams {
-  int B, C, D;                          // rows of x, classes of this launch, feature dim
+  int B, C, D;                          // extents of m (rows of x), n (classes of this launch) and k
   int kb_count;                         // ceil(D / 64) <= XW_MAX_KB
   int m_groups, n_tiles, n_chunks;      // row groups of 128*PAIR rows, class tiles of 128*PAIR, class chunks
   uint32_t idesc;
@@ -157,7 +162,7 @@ struct XwItem {                         // what an epilogue thread knows about i
 //     static __device__ void slice(State&, const Params&, const XwParams&, const XwItem&, float (&v)[32], int cls0);
 //         v = accumulators of row it.row for classes [cls0, cls0 + 32) of this launch (warp-uniform cls0 < C)
 //     static __device__ void item_end(State&, const Params&, const XwParams&, const XwItem&, float* scratch); }
-template <int PAIR, class Epi>
+template <int PAIR, bool MN, class Epi>
 __global__ void __launch_bounds__(XW_THREADS, 1)
 xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const XwParams p,
           const typename Epi::Params ep) {
@@ -213,8 +218,15 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
         if (rank == 0) mbar_arrive_expect_tx(x_full, (uint32_t)(PAIR * p.kb_count * XW_TILE_BYTES));
         else mbar_arrive_cluster(x_full, 0);
         const int row0 = (g * PAIR + rank) * XW_M;
-        for (int kb = 0; kb < p.kb_count; ++kb)
-          xw_tma_load<PAIR>(xres + (size_t)kb * XW_TILE_BYTES, &tm_x, x_full, kb * XW_K, row0);
+        for (int kb = 0; kb < p.kb_count; ++kb) {
+          uint8_t* dst = xres + (size_t)kb * XW_TILE_BYTES;
+          if (!MN) {
+            xw_tma_load<PAIR>(dst, &tm_x, x_full, kb * XW_K, row0);
+          } else {                                                // two 64-wide row blocks of 64 k-rows each
+            xw_tma_load<PAIR>(dst, &tm_x, x_full, row0, kb * XW_K);
+            xw_tma_load<PAIR>(dst + XW_TILE_BYTES / 2, &tm_x, x_full, row0 + 64, kb * XW_K);
+          }
+        }
         for (int t = t_begin; t < t_end && ok; ++t) {
           const int n0 = t * TN + rank * XW_WROWS;
           for (int kb = 0; kb < p.kb_count; ++kb) {
@@ -222,7 +234,13 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
             if (!ok) break;
             if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(PAIR * XW_TILE_BYTES));
             else mbar_arrive_cluster(&full_bar[stage], 0);
-            xw_tma_load<PAIR>(ring + (size_t)stage * XW_TILE_BYTES, &tm_w, &full_bar[stage], kb * XW_K, n0);
+            uint8_t* dst = ring + (size_t)stage * XW_TILE_BYTES;
+            if (!MN) {
+              xw_tma_load<PAIR>(dst, &tm_w, &full_bar[stage], kb * XW_K, n0);
+            } else {
+              xw_tma_load<PAIR>(dst, &tm_w, &full_bar[stage], n0, kb * XW_K);
+              xw_tma_load<PAIR>(dst + XW_TILE_BYTES / 2, &tm_w, &full_bar[stage], n0 + 64, kb * XW_K);
+            }
             if (++stage == XW_STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -258,8 +276,9 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
             const uint32_t sb = ring_addr + (uint32_t)stage * XW_TILE_BYTES;
 #pragma unroll
             for (int kk = 0; kk < XW_K / 16; ++kk) {
-              const uint64_t da = make_smem_desc(sa + kk * 32, 0, 1024);
-              const uint64_t db = make_smem_desc(sb + kk * 32, 0, 1024);
+              // K-major: +32 B per 16 k; MN-major: +16 k-rows of 128 B, LBO = next 64-wide row block (8 KB)
+              const uint64_t da = MN ? make_smem_desc(sa + kk * 2048, XW_TILE_BYTES / 2, 1024) : make_smem_desc(sa + kk * 32, 0, 1024);
+              const uint64_t db = MN ? make_smem_desc(sb + kk * 2048, XW_TILE_BYTES / 2, 1024) : make_smem_desc(sb + kk * 32, 0, 1024);
               xw_mma<PAIR>(d_tmem, da, db, p.idesc, (uint32_t)((kb | kk) != 0));
             }
             xw_commit<PAIR>(&empty_bar[stage]);
@@ -296,17 +315,15 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
         const int cls_base = t * TN + col_base;
         float va[32], vb[32];
         tmem_ld32_async(taddr, va);
-#pragma unroll
-        for (int s = 0; s < SLICES; ++s) {
-          if ((s & 1) == 0) {
-            tmem_ld_wait_dep(va);
-            if (s + 1 < SLICES) tmem_ld32_async(taddr + (uint32_t)(s + 1) * 32, vb);
-            if (cls_base + s * 32 < p.C) Epi::slice(stt, ep, p, it, va, cls_base + s * 32);
-          } else {
-            tmem_ld_wait_dep(vb);
-            if (s + 1 < SLICES) tmem_ld32_async(taddr + (uint32_t)(s + 1) * 32, va);
-            if (cls_base + s * 32 < p.C) Epi::slice(stt, ep, p, it, vb, cls_base + s * 32);
-          }
+        // two slices per trip, NOT fully unrolled: the policy code exists twice, not 2 * SLICES times (i-cache)
+#pragma unroll 1
+        for (int s = 0; s < SLICES; s += 2) {
+          tmem_ld_wait_dep(va);
+          tmem_ld32_async(taddr + (uint32_t)(s + 1) * 32, vb);
+          if (cls_base + s * 32 < p.C) Epi::slice(stt, ep, p, it, va, cls_base + s * 32);
+          tmem_ld_wait_dep(vb);
+          if (s + 2 < SLICES) tmem_ld32_async(taddr + (uint32_t)(s + 2) * 32, va);
+          if (cls_base + (s + 1) * 32 < p.C) Epi::slice(stt, ep, p, it, vb, cls_base + (s + 1) * 32);
         }
         tc_fence_before_sync();
         __syncwarp();

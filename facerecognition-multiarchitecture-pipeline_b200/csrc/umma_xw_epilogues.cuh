@@ -114,6 +114,15 @@ struct XwFwd {
         st.bestidx = cls0 + tix;
       }
     } else {
+      // the margin touches ONE element of the slice: evaluate phi once (its acos / cos code is large; 32 inlined
+      // copies per slice made the kernel instruction-fetch bound)
+      float tphi = 0.f;
+      if (has_t) {
+        float ct = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (cls0 + j == st.tgt) ct = v[j] * isc;
+        tphi = ep.hm.phi((ct != ct) ? ct : fminf(fmaxf(ct, lo), hi));
+      }
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         if (j < cc) {
@@ -121,7 +130,7 @@ struct XwFwd {
           st.cmin = fminf(st.cmin, cosv); st.cmax = fmaxf(st.cmax, cosv);
           const float c = (cosv != cosv) ? cosv : fminf(fmaxf(cosv, lo), hi);
           const bool is_t = (cls0 + j == st.tgt);
-          const float tv = is_t ? ep.hm.phi(c) : c;
+          const float tv = is_t ? tphi : c;
           float z = tv * s_eff;
           if (!isfinite(z)) { z = 0.f; st.saw_nan = true; }
           if (is_t) st.ztgt = z;
@@ -164,6 +173,22 @@ struct XwFwd {
   }
 };
 
+// Column sums across the warp: on return lane l holds sum over the 32 lanes of h[l] (31 shuffles: each step
+// halves the columns a lane is responsible for).  Fixed order, so bitwise reproducible.
+__device__ __forceinline__ float warp_column_sums(float (&h)[32], int lane) {
+#pragma unroll
+  for (int step = 16; step >= 1; step >>= 1) {
+    const bool upper = (lane & step) != 0;
+#pragma unroll
+    for (int i = 0; i < step; ++i) {
+      const float send = upper ? h[i] : h[i + step];
+      const float keep = upper ? h[i + step] : h[i];
+      h[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+    }
+  }
+  return h[0];
+}
+
 // -------------------------------------------------------------------------------------------------
 // K3a: recompute the logits of a class chunk and emit the logit gradient as fp16 (one L2-resident buffer
 // that both consumer GEMMs read),
@@ -171,6 +196,8 @@ struct XwFwd {
 // grad4 = {grad_scale, n, kappa, g_scale} from b200f_arcface_hook_scale; g_scale is the power of two that
 // puts |grad_scale| * g_scale in (512, 1024], so a target-column entry (|p-q| <= 1, dphi <~ 30) stays below
 // fp16 max and entries down to p ~ 1e-7 stay normal; the consumers divide it out again.
+// Side output (r_part != NULL): r'_j = sum_i G_ij cos_ij per 32-row block = <w_hat_j, dW_hat_j> * g_scale, the
+// radial part that the normalise-backward of w removes -- so the dW GEMM can finish dW in its own epilogue.
 struct XwBwdG {
   struct Params {
     const int64_t* label; const float* lse; const float* grad4;
@@ -178,6 +205,8 @@ struct XwBwdG {
     HeadMath hm;
     float ls_eps, inv_Ctot, inv_scale;
     uint16_t* G; int64_t ldg;   // G[row, class of this launch]
+    float* r_part; int64_t ldr; // [row blocks of 32, ldr] or NULL
+    int pair;
   };
   struct State { float lse, gs; int tgt; bool row_ok; };
 
@@ -222,20 +251,39 @@ struct XwBwdG {
     bool careful = !(s_eff > 0.f) || has_t || !(tmx * isc <= hi) || !(tmn * isc >= lo) || !isfinite(chk);
     careful = __any_sync(0xffffffffu, careful);
     if (careful) {
+      float tphi = 0.f, tdphi = 0.f;                          // phi / dphi once per slice (see XwFwd)
+      if (has_t) {
+        float ct = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (cls0 + j == st.tgt) ct = v[j] * isc;
+        const float cc_t = (ct != ct) ? ct : fminf(fmaxf(ct, lo), hi);
+        tphi = ep.hm.phi(cc_t); tdphi = ep.hm.dphi(cc_t);
+      }
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const float cosv = v[j] * isc;
         const float c = (cosv != cosv) ? cosv : fminf(fmaxf(cosv, lo), hi);
         const bool is_t = (cls0 + j == st.tgt);
-        const float tv = is_t ? ep.hm.phi(c) : c;
+        const float tv = is_t ? tphi : c;
         float z = tv * s_eff;
-        float f = is_t ? ep.hm.dphi(c) : 1.0f;
+        float f = is_t ? tdphi : 1.0f;
         if (!isfinite(z)) { z = 0.f; f = 0.f; }
         if (!(cosv >= lo && cosv <= hi)) f = 0.f;
         const float pr = exp2f((z - st.lse) * LOG2E);
         const float q = is_t ? (1.0f - ep.ls_eps) + q_off : q_off;
         g[j] = fminf(fmaxf(gs * (pr - q) * f, -65504.f), 65504.f);
       }
+    }
+    if (ep.r_part != nullptr) {
+      float h[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float t = g[j] * v[j];                          // G * S^2 cos; a cut gradient (g = 0) contributes 0
+        h[j] = (st.row_ok && g[j] != 0.f && t == t) ? t : 0.f;
+      }
+      const float colsum = warp_column_sums(h, it.lane);
+      const int rb = (it.group * ep.pair + it.rank) * 4 + it.quad;
+      if (cls0 + it.lane < p.C) ep.r_part[(int64_t)rb * ep.ldr + cls0 + it.lane] = colsum * isc;
     }
     if (st.row_ok) {
       uint16_t* gdst = ep.G + it.row * ep.ldg + cls0;
@@ -254,6 +302,45 @@ struct XwBwdG {
     }
   }
 
+  static __device__ __forceinline__ void item_end(State&, const Params&, const XwParams&, const XwItem&, float*) {}
+};
+
+// -------------------------------------------------------------------------------------------------
+// K3b on the MN-major kernel: acc[d, c] = sum_b x_hat[b, d] S * G'[b, c]  (= dW_hat^T * S * g_scale), finished in
+// place with the normalise-backward of the weight rows (autograd of F.normalize, src/face_models.py:352):
+//   dW[c, d] = inv_nw_c * (dW_hat[c, d] - w_hat[c, d] r_c) = coef_c.x * (acc - wh[c, d] * coef_c.y)
+// coef_c = { inv_nw_c / (S g_scale), r'_c } from reduce_r_kernel; wh = w_hat * S (K1's fp16 rows).
+// The thread owns feature d: for a fixed class its warp writes 128 contiguous bytes of the dW row.
+struct XwDw {
+  struct Params { const float2* coef; const __half* wh; float* dw; int64_t c0; int ld; };
+  struct State { bool row_ok; };
+  static __device__ __forceinline__ void item_begin(State& st, const Params&, const XwParams& p, const XwItem& it) {
+    st.row_ok = it.row < p.B;
+  }
+  static __device__ __forceinline__ void slice(State& st, const Params& ep, const XwParams& p, const XwItem& it,
+                                               float (&v)[32], int cls0) {
+    if (!st.row_ok) return;
+    const int cc = min(32, p.C - cls0);
+    const int64_t base = (ep.c0 + cls0) * ep.ld + it.row;
+    const float2* cf = ep.coef + ep.c0 + cls0;
+    if (cc == 32) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float2 c2 = __ldg(cf + j);
+        const float wv = __half2float(__ldg(ep.wh + base + (int64_t)j * ep.ld));
+        ep.dw[base + (int64_t)j * ep.ld] = c2.x * fmaf(-wv, c2.y, v[j]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (j < cc) {
+          const float2 c2 = __ldg(cf + j);
+          const float wv = __half2float(__ldg(ep.wh + base + (int64_t)j * ep.ld));
+          ep.dw[base + (int64_t)j * ep.ld] = c2.x * fmaf(-wv, c2.y, v[j]);
+        }
+      }
+    }
+  }
   static __device__ __forceinline__ void item_end(State&, const Params&, const XwParams&, const XwItem&, float*) {}
 };
 
