@@ -9,7 +9,7 @@ __path__.append(_PKG_DIR)
 
 from ._lib import lib_path, load_library, LibraryMissingError  # noqa: E402,F401
 from .head import (  # noqa: E402,F401
-    ArcMarginProduct, ArcFaceNet, arcface_loss, head_schedule, HeadStats,
+    ArcMarginProduct, ArcFaceNet, arcface_loss, head_schedule, HeadStats, GraphedHeadStep,
 )
 from .gallery import (  # noqa: E402,F401
     compare_faces, gallery_topk, cosine_class_match, GalleryIndex,
@@ -17,7 +17,7 @@ from .gallery import (  # noqa: E402,F401
 from . import parallel  # noqa: E402,F401
 
 __all__ = [
-    "ArcMarginProduct", "ArcFaceNet", "arcface_loss", "head_schedule", "HeadStats",
+    "ArcMarginProduct", "ArcFaceNet", "arcface_loss", "head_schedule", "HeadStats", "GraphedHeadStep",
     "compare_faces", "gallery_topk", "cosine_class_match", "GalleryIndex",
     "parallel", "lib_path", "load_library", "LibraryMissingError",
 ]

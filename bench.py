@@ -46,6 +46,9 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="launch every stage from Python instead of replaying the captured CUDA graph")
+    ap.add_argument("--pair", type=int, default=0, help="1 = single CTAs, 2 = cta_group::2 CTA pairs (default)")
+    ap.add_argument("--g-chunk-mb", type=int, default=0, help="logit-gradient buffer budget per class chunk (MB)")
     ap.add_argument("--no-gallery", action="store_true")
     return ap.parse_args()
 
@@ -124,7 +127,8 @@ def engine_code(name):
 def run_b200(args):
     import b200face
     from b200face import _lib, parallel
-    from b200face.head import HeadStats, arcface_loss, effective_margin_scale, head_schedule
+    from b200face import head as H
+    from b200face.head import GraphedHeadStep, HeadStats, arcface_loss, effective_margin_scale, head_schedule
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -135,6 +139,10 @@ def run_b200(args):
         torch.distributed.init_process_group("nccl", device_id=dev)
         group = torch.distributed.group.WORLD
     lib = b200face.load_library()
+    if args.pair:
+        lib.b200f_set_tunable(b"pair", args.pair)
+    if args.g_chunk_mb:
+        lib.b200f_set_tunable(b"g_chunk_mb", args.g_chunk_mb)
     cfgw = CFG3 if world == 1 else CFG4
     B, C_total, D = cfgw["B"], cfgw["C"], cfgw["D"]
     c_lo, c_hi = parallel.shard_bounds(C_total, world, rank)
@@ -144,12 +152,14 @@ def run_b200(args):
     mf, sf = head_schedule(EPOCH, 10, True, True, 0.0, 0.3)
     m_eff, s_eff = effective_margin_scale(32.0, 0.5, mf, sf, True)
     eng = engine_code(args.engine)
+    use_graph = not args.eager
+    loss_kw = dict(compute_weight=w, m_eff=m_eff, s_eff=s_eff, label_smoothing=LS, class_offset=c_lo,
+                   num_classes_total=C_total, group=group, engine=eng)
 
-    def step(xin, stats=None):
+    def eager_step(xin, yin):
         xin = xin.detach().requires_grad_(True)
         w_master.grad = None
-        loss = arcface_loss(xin, w_master, y, compute_weight=w, m_eff=m_eff, s_eff=s_eff, label_smoothing=LS,
-                            class_offset=c_lo, num_classes_total=C_total, group=group, stats=stats, engine=eng)
+        loss = arcface_loss(xin, w_master, yin, **loss_kw)
         loss.backward()
         return loss
 
@@ -158,10 +168,19 @@ def run_b200(args):
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
+    launches_per_step = None
+    if use_graph:
+        l0 = lib.b200f_launch_count()
+        gstep = GraphedHeadStep(w_master, B, D, dtype=torch.bfloat16, warmup=1, **loss_kw)
+        launches_per_step = (lib.b200f_launch_count() - l0) // 2          # one warm-up step + the captured step
+        gstep(x, y)
+        step = lambda: gstep.replay()
+    else:
+        step = lambda: eager_step(x, y)
     for _ in range(max(args.warmup, 3)):
-        step(x)
+        step()
     # ---- timed region 1: inputs resident in HBM ------------------------------------------------
-    _lib.TIMERS.clear(); _lib.PROFILE = True
+    _lib.TIMERS.clear(); _lib.PROFILE = not use_graph
     sync_all()
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = lib.b200f_launch_count()
@@ -169,18 +188,18 @@ def run_b200(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        loss = step(x)
+        loss = step()
     e1.record()
     sync_all()
     t_wall1 = time.time()
-    launches = lib.b200f_launch_count() - l0
+    launches = (launches_per_step * args.steps) if use_graph else (lib.b200f_launch_count() - l0)
     _lib.PROFILE = False
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
     ms_total = float(ms)
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
-    kern = {k: statistics.mean(a.elapsed_time(b) for a, b in v) for k, v in _lib.TIMERS.items() if v}
+    loss_val = float(loss.detach())
     # ---- timed region 2: end to end through the public API, host buffers ------------------------
     xh = x.cpu().pin_memory(); yh = y.cpu().pin_memory()
     head = b200face.ArcMarginProduct(D, C_local) if world == 1 else None
@@ -190,16 +209,18 @@ def run_b200(args):
         head.cache_weight_prep = False                                # training changes W every step: K1(W) is timed
         with torch.no_grad():
             head.weight.copy_(w.float())
+        api_step = head.graphed_step(B, LS, torch.bfloat16) if use_graph else None
     def e2e_step():
-        xd = xh.to(dev, non_blocking=True); yd = yh.to(dev, non_blocking=True)
-        if head is not None:
-            head.zero_grad(set_to_none=True)
-            l = head.forward_loss(xd.requires_grad_(True), yd, LS)
+        if use_graph:
+            l = api_step(xh, yh) if head is not None else gstep(xh, yh)  # H2D into the static buffers, then replay
         else:
-            w_master.grad = None
-            l = arcface_loss(xd.requires_grad_(True), w_master, yd, compute_weight=w, m_eff=m_eff, s_eff=s_eff,
-                             label_smoothing=LS, class_offset=c_lo, num_classes_total=C_total, group=group, engine=eng)
-        l.backward()
+            xd = xh.to(dev, non_blocking=True); yd = yh.to(dev, non_blocking=True)
+            if head is not None:
+                head.zero_grad(set_to_none=True)
+                l = head.forward_loss(xd.requires_grad_(True), yd, LS)
+                l.backward()
+            else:
+                l = eager_step(xd, yd)
         return float(l.item())                                        # D2H read of the step's result
     for _ in range(3):
         e2e_step()
@@ -213,6 +234,9 @@ def run_b200(args):
     if world > 1:
         torch.distributed.all_reduce(ms2, op=torch.distributed.ReduceOp.MAX)
     e2e_val = B * args.steps / (float(ms2) * 1e-3)
+    # ---- per-kernel durations: each C-ABI stage alone between CUDA events on the launching stream, L2 flushed
+    # (a 256 MB write) before every launch; these are what the roofline line reports
+    kern = time_stages(H, _lib, x, w, y, m_eff, s_eff, c_lo, C_total, eng, dev, reps=max(5, min(args.steps, 20)))
 
     if rank != 0:
         if world > 1:
@@ -226,10 +250,11 @@ def run_b200(args):
     roof = None
     if k2_ms:
         ach = 2.0 * B * C_local * D / (k2_ms * 1e-3) / 1e12
-        roof = {"kernel": "K2 arcface_fwd (cosine GEMM + margin + softmax-CE statistics)", "bound": "tensor",
-                "achieved": round(ach, 2), "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                "frac": round(ach / pk["tf_sustained"], 4), "traffic": load_traffic("arcface_fwd"),
-                "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step)",
+        roof = {"kernel": "K2 arcface_fwd (cosine GEMM + margin + softmax-CE statistics; includes its 6 us partial-record reduction)",
+                "bound": "tensor",
+                "achieved": round(ach, 2), "peak": pk["tf_burst"], "unit": "TFLOP/s",
+                "frac": round(ach / pk["tf_burst"], 4), "traffic": load_traffic("arcface_fwd"),
+                "peak_source": pk["source"] + ", burst figure (kernel timed alone, L2 flushed before each launch)",
                 "algorithmic_flop_per_launch": 2.0 * B * C_local * D, "avg_launch_ms": round(k2_ms, 4)}
     out = {
         "metric": "arcface_head_samples_per_sec", "value": round(value, 1), "unit": "samples/s",
@@ -241,6 +266,7 @@ def run_b200(args):
                                 f"({C_local} per rank), batch 4096, one all-reduce each way"),
                    "B": B, "C_total": C_total, "C_per_rank": C_local, "D": D, "label_smoothing": LS,
                    "m_eff": round(m_eff, 4), "s_eff": round(s_eff, 4), "engine": args.engine,
+                   "launch": "cuda-graph replay of the captured step" if use_graph else "eager (one C-ABI call per stage)",
                    "grads": "dx fp32, dW fp32", "l2": "inputs_exceed_l2 (W bf16 + dW fp32 = 3 x C x D x 2 B per rank)",
                    "parallelism": "single GPU" if world == 1 else f"class-parallel x{world} (NCCL all-reduce [B,4] fwd, [B,D] bwd)"},
         "algorithmic_tflops": round(flops_step * args.steps / (ms_total * 1e-3) / 1e12, 2),
@@ -251,7 +277,7 @@ def run_b200(args):
         "clocks": clocks,
         "roofline": roof,
         "kernel_ms": {k: round(v, 4) for k, v in kern.items()},
-        "loss": round(float(loss.detach()), 5),
+        "loss": round(loss_val, 5),
     }
     if world == 1 and not args.no_gallery:
         out["gallery"] = bench_gallery(dev, pk, eng)
@@ -260,6 +286,40 @@ def run_b200(args):
     print(json.dumps(out), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+def time_stages(H, _lib, x, w, y, m_eff, s_eff, c_lo, C_total, eng, dev, reps=10):
+    """Average duration of each stage of the step launched alone (CUDA events on the launching stream, a 256 MB
+    L2 flush before every launch): K1 on the weights, K2 (+ its partial reduction), K3 (all backward kernels)."""
+    lib = _lib.load_library()
+    cfg = H._head_cfg(m_eff, s_eff, LS, False, C_total, eng)
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
+    B = x.shape[0]
+    acc = {"l2norm_rows_w": [], "arcface_fwd": [], "arcface_bwd": []}
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    for _ in range(reps + 2):
+        f16n = H.use_tcgen05(x, eng)
+        xo, inv_nx = H._k1(x, f16n)
+        flush.zero_()
+        a0, a1 = ev(), ev(); a0.record(); wo, inv_nw = H._k1(w, f16n); a1.record()
+        flush.zero_()
+        _lib.PROFILE = True; _lib.TIMERS.clear()
+        out = H._fwd_kernels(x, w, y, cfg, c_lo, False)
+        row_stats = out[4]
+        lse = torch.empty(B, dtype=torch.float32, device=dev); out2 = torch.empty(2, dtype=torch.float32, device=dev)
+        _lib.check(lib.b200f_arcface_loss(_lib.ptr(row_stats), B, cfg, _lib.ptr(lse), _lib.ptr(out2), _lib.ptr(out2[1:]),
+                                          _lib.stream_ptr(dev)), "loss")
+        out4 = torch.empty(4, dtype=torch.float32, device=dev)
+        _lib.check(lib.b200f_arcface_hook_scale(_lib.ptr(out2[1:]), None, B, s_eff, 0, 1.0, 1, 0, _lib.ptr(out4),
+                                                _lib.stream_ptr(dev)), "hook")
+        flush.zero_()
+        H._bwd_kernels(out[0], out[1], y, out[2], out[3], lse, out4, cfg, c_lo)
+        _lib.PROFILE = False
+        torch.cuda.synchronize()
+        acc["l2norm_rows_w"].append(a0.elapsed_time(a1))
+        for k in ("arcface_fwd", "arcface_bwd"):
+            acc[k].append(statistics.mean(a.elapsed_time(b) for a, b in _lib.TIMERS[k]))
+    return {k: statistics.mean(v[2:]) for k, v in acc.items()}
 
 
 def load_traffic(kernel):

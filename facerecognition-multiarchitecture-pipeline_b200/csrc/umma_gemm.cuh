@@ -98,7 +98,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
 
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();
       int stage = 0; uint32_t phase = 0;
       bool ok = true;
       for (int w = blockIdx.x; w < total_work && ok; w += gridDim.x) {
@@ -106,33 +107,41 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
         for (int k0 = t.k_begin; k0 < t.k_end && ok; k0 += BLOCK_K) {
           ok = mbar_wait(&empty_bar[stage], phase ^ 1);
           if (!ok) break;
-          uint8_t* sa = tiles + (size_t)stage * STAGE_BYTES;
-          uint8_t* sb = sa + A_TILE_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-          if (!A_MN) {
-            tma_load_2d(sa, &tm_a, &full_bar[stage], k0, t.m0);
-          } else {
+          if (leader) {
+            uint8_t* sa = tiles + (size_t)stage * STAGE_BYTES;
+            uint8_t* sb = sa + A_TILE_BYTES;
+            mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+            if (!A_MN) {
+              tma_load_2d(sa, &tm_a, &full_bar[stage], k0, t.m0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BLOCK_M / 64; ++j)
-              tma_load_2d(sa + j * MN_BLOCK_BYTES, &tm_a, &full_bar[stage], t.m0 + 64 * j, k0);
-          }
-          if (!B_MN) {
-            tma_load_2d(sb, &tm_b, &full_bar[stage], k0, t.n0);
-          } else {
+              for (int j = 0; j < BLOCK_M / 64; ++j)
+                tma_load_2d(sa + j * MN_BLOCK_BYTES, &tm_a, &full_bar[stage], t.m0 + 64 * j, k0);
+            }
+            if (!B_MN) {
+              tma_load_2d(sb, &tm_b, &full_bar[stage], k0, t.n0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BLOCK_N / 64; ++j)
-              tma_load_2d(sb + j * MN_BLOCK_BYTES, &tm_b, &full_bar[stage], t.n0 + 64 * j, k0);
+              for (int j = 0; j < BLOCK_N / 64; ++j)
+                tma_load_2d(sb + j * MN_BLOCK_BYTES, &tm_b, &full_bar[stage], t.n0 + 64 * j, k0);
+            }
           }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
+    // convergent warp, one elected lane issues; descriptors = base descriptor + 14-bit address offset
+    {
+      const bool leader = elect_one();
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       bool ok = true;
+      const uint64_t desc_a0 = make_smem_desc(smem_u32(tiles), p.a_lbo, p.a_sbo);
+      const uint64_t desc_b0 = make_smem_desc(smem_u32(tiles) + A_TILE_BYTES, p.b_lbo, p.b_sbo);
+      const uint32_t a_kstep = p.a_kstep >> 4, b_kstep = p.b_kstep >> 4;
       for (int w = blockIdx.x; w < total_work && ok; w += gridDim.x) {
         const TileCoord t = decode_work(p, w);
         ok = mbar_wait(&acc_empty[acc], acc_phase ^ 1);        // epilogue has drained this accumulator
@@ -144,19 +153,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
           ok = mbar_wait(&full_bar[stage], phase);
           if (!ok) break;
           tc_fence_after_sync();
-          const uint32_t sa = smem_u32(tiles + (size_t)stage * STAGE_BYTES);
-          const uint32_t sb = sa + A_TILE_BYTES;
+          if (leader) {
+            const uint64_t soff = (uint64_t)((uint32_t)stage * (STAGE_BYTES >> 4));
 #pragma unroll
-          for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
-            const uint64_t da = make_smem_desc(sa + kk * p.a_kstep, p.a_lbo, p.a_sbo);
-            const uint64_t db = make_smem_desc(sb + kk * p.b_kstep, p.b_lbo, p.b_sbo);
-            mma_f16_ss(d_tmem, da, db, p.idesc, accumulate);
-            accumulate = 1;
+            for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+              mma_f16_ss(d_tmem, desc_a0 + soff + (uint64_t)(kk * a_kstep), desc_b0 + soff + (uint64_t)(kk * b_kstep),
+                         p.idesc, accumulate);
+              accumulate = 1;
+            }
+            mma_commit(&empty_bar[stage]);                     // smem slot reusable once these MMAs retire
           }
-          mma_commit(&empty_bar[stage]);                       // smem slot reusable once these MMAs retire
+          accumulate = 1;
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        mma_commit(&acc_full[acc]);                            // accumulator ready for the epilogue
+        if (leader) mma_commit(&acc_full[acc]);                // accumulator ready for the epilogue
+        __syncwarp();
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
     }

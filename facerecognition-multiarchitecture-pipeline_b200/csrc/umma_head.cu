@@ -167,6 +167,7 @@ __global__ void reduce_r_kernel(const float* __restrict__ r_part, int n_rb, int6
 
 // ---- X-stationary kernel: launch geometry ---------------------------------------------------------
 static std::atomic<int> g_pair{2};                 // 2 = tcgen05 cta_group::2 CTA pairs, 1 = single CTAs
+static std::atomic<int> g_chunk_mb{112};           // budget of the fp16 logit-gradient buffer G per class chunk
 
 template <int PAIR, bool MN, class Epi>
 static int xw_set_smem() {
@@ -266,8 +267,10 @@ static Plan make_plan(int64_t B, int64_t C, int D) {
   pl.off_part = off; off += align_up(sizeof(float) * part_max * B * PART_COLS, 256);
   pl.off_cos = off;  off += align_up(sizeof(float) * 2 * cos_max, 256);
   const size_t fwd_total = off;
-  // backward: the fp16 logit-gradient chunk should stay L2-resident (126 MB L2): <= 48 MB
-  int64_t cc_max = ((int64_t)(48u << 20) / 2 / B) / BLOCK_N * BLOCK_N;
+  // backward: classes are processed in chunks whose fp16 logit gradient G fits the budget.  G is written once
+  // and read twice, all while the tensor pipe (not HBM) is the bound, so it need not stay L2-resident: cfg3's
+  // 102 MB is ONE chunk (fewer launches, long per-CTA streams); B = 4096 shards use ~12 k-class chunks.
+  int64_t cc_max = ((int64_t)g_chunk_mb.load(std::memory_order_relaxed) * (1 << 20) / 2 / B) / BLOCK_N * BLOCK_N;
   if (cc_max < BLOCK_N) cc_max = BLOCK_N;
   pl.n_chunks = (int)ceil_div(C, cc_max);
   pl.Cc = ceil_div(ceil_div(C, pl.n_chunks), BLOCK_N) * BLOCK_N;
@@ -469,10 +472,37 @@ int b200f_umma_xw_selftest(const void* x, const void* w, float* out, int B, int 
                      : launch_xw<1, false, XwStore>(tx, tw, q, B, C, D, ep, st, "umma xw selftest");
 }
 
+// Pipeline probe (tools/xw_probe.py): same GEMM, but the epilogue only adds every accumulator of a row into
+// rowsum[B] (must be zeroed by the caller): measures the TMA / tcgen05 / TMEM pipeline without epilogue work.
+int b200f_umma_xw_probe(const void* x, const void* w, float* rowsum, int B, int C, int D, int pair, void* stream) {
+  if (!x || !w || !rowsum || B <= 0 || C <= 0 || D <= 0 || (pair != 1 && pair != 2))
+    return fail(B200F_ERR_ARG, "umma_xw_probe: bad argument");
+  if (!device_is_sm100()) return fail(B200F_ERR_UNSUPPORTED, "umma_xw_probe: device is not sm_100");
+  if (D % 8 != 0 || D > XW_MAX_KB * XW_K) return fail(B200F_ERR_UNSUPPORTED, "umma_xw_probe: D %% 8 == 0 and D <= 512");
+  CUtensorMap tx, tw;
+  int rc = tmap_kmajor(&tx, x, B, D, D, XW_M); if (rc) return rc;
+  rc = tmap_kmajor(&tw, w, C, D, D, XW_WROWS); if (rc) return rc;
+  const XwPlan q = xw_plan(B, C, pair);
+  XwNull::Params ep{rowsum};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return (pair == 2) ? launch_xw<2, false, XwNull>(tx, tw, q, B, C, D, ep, st, "umma xw probe (cta pair)")
+                     : launch_xw<1, false, XwNull>(tx, tw, q, B, C, D, ep, st, "umma xw probe");
+}
+
 // Selects single-CTA (1) or CTA-pair (2, default) execution of K2 / K3a; returns the previous setting.
 int b200f_umma_set_pair(int pair) {
   if (pair != 1 && pair != 2) return g_pair.load();
   return g_pair.exchange(pair);
+}
+
+// Tunables (tests / bench sweeps): "pair" (1 | 2) and "g_chunk_mb" (MB of logit-gradient buffer per class chunk).
+// Returns the previous value, or -1 for an unknown name.  Workspaces must be re-queried after a change.
+int b200f_set_tunable(const char* name, int value) {
+  if (!name) return -1;
+  const std::string n(name);
+  if (n == "pair") return b200f_umma_set_pair(value);
+  if (n == "g_chunk_mb") { if (value < 1) return g_chunk_mb.load(); return g_chunk_mb.exchange(value); }
+  return -1;
 }
 
 // Reads (and optionally clears) the pipeline-timeout flag.  Synchronises: test / bench use only.

@@ -159,6 +159,9 @@ struct XwItem {                         // what an epilogue thread knows about i
 // Epilogue policy interface:
 //   struct Epi { struct Params; struct State;
 //     static __device__ void item_begin(State&, const Params&, const XwParams&, const XwItem&);
+//     static __device__ void tile_begin(State&, const Params&, const XwParams&, const XwItem&, int cls0, int next_cls0, int ncols);
+//         once per class tile before its slices: this warp owns classes [cls0, cls0 + ncols) now and
+//         [next_cls0, next_cls0 + ncols) in its next tile (-1: none) -- the place for L2 prefetches
 //     static __device__ void slice(State&, const Params&, const XwParams&, const XwItem&, float (&v)[32], int cls0);
 //         v = accumulators of row it.row for classes [cls0, cls0 + 32) of this launch (warp-uniform cls0 < C)
 //     static __device__ void item_end(State&, const Params&, const XwParams&, const XwItem&, float* scratch); }
@@ -205,8 +208,11 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ================= TMA producer (one lane, both CTAs) =================
-    if (lane == 0) {
+    // ================= TMA producer (both CTAs) =================
+    // The whole warp walks the loops convergently (loop state stays in uniform registers); one elected lane
+    // issues the TMA traffic.
+    {
+      const bool leader = elect_one();
       int stage = 0; uint32_t phase = 0;
       int item_no = 0;
       bool ok = true;
@@ -215,16 +221,18 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
         const int t_begin = (int)((int64_t)chunk * p.n_tiles / p.n_chunks);
         const int t_end = (int)((int64_t)(chunk + 1) * p.n_tiles / p.n_chunks);
         if (item_no > 0) { ok = mbar_wait(x_empty, (uint32_t)((item_no - 1) & 1)); if (!ok) break; }
-        if (rank == 0) mbar_arrive_expect_tx(x_full, (uint32_t)(PAIR * p.kb_count * XW_TILE_BYTES));
-        else mbar_arrive_cluster(x_full, 0);
         const int row0 = (g * PAIR + rank) * XW_M;
-        for (int kb = 0; kb < p.kb_count; ++kb) {
-          uint8_t* dst = xres + (size_t)kb * XW_TILE_BYTES;
-          if (!MN) {
-            xw_tma_load<PAIR>(dst, &tm_x, x_full, kb * XW_K, row0);
-          } else {                                                // two 64-wide row blocks of 64 k-rows each
-            xw_tma_load<PAIR>(dst, &tm_x, x_full, row0, kb * XW_K);
-            xw_tma_load<PAIR>(dst + XW_TILE_BYTES / 2, &tm_x, x_full, row0 + 64, kb * XW_K);
+        if (leader) {
+          if (rank == 0) mbar_arrive_expect_tx(x_full, (uint32_t)(PAIR * p.kb_count * XW_TILE_BYTES));
+          else mbar_arrive_cluster(x_full, 0);
+          for (int kb = 0; kb < p.kb_count; ++kb) {
+            uint8_t* dst = xres + (size_t)kb * XW_TILE_BYTES;
+            if (!MN) {
+              xw_tma_load<PAIR>(dst, &tm_x, x_full, kb * XW_K, row0);
+            } else {                                              // two 64-wide row blocks of 64 k-rows each
+              xw_tma_load<PAIR>(dst, &tm_x, x_full, row0, kb * XW_K);
+              xw_tma_load<PAIR>(dst + XW_TILE_BYTES / 2, &tm_x, x_full, row0 + 64, kb * XW_K);
+            }
           }
         }
         for (int t = t_begin; t < t_end && ok; ++t) {
@@ -232,14 +240,16 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
           for (int kb = 0; kb < p.kb_count; ++kb) {
             ok = mbar_wait(&empty_bar[stage], phase ^ 1);
             if (!ok) break;
-            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(PAIR * XW_TILE_BYTES));
-            else mbar_arrive_cluster(&full_bar[stage], 0);
-            uint8_t* dst = ring + (size_t)stage * XW_TILE_BYTES;
-            if (!MN) {
-              xw_tma_load<PAIR>(dst, &tm_w, &full_bar[stage], kb * XW_K, n0);
-            } else {
-              xw_tma_load<PAIR>(dst, &tm_w, &full_bar[stage], n0, kb * XW_K);
-              xw_tma_load<PAIR>(dst + XW_TILE_BYTES / 2, &tm_w, &full_bar[stage], n0 + 64, kb * XW_K);
+            if (leader) {
+              if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(PAIR * XW_TILE_BYTES));
+              else mbar_arrive_cluster(&full_bar[stage], 0);
+              uint8_t* dst = ring + (size_t)stage * XW_TILE_BYTES;
+              if (!MN) {
+                xw_tma_load<PAIR>(dst, &tm_w, &full_bar[stage], kb * XW_K, n0);
+              } else {
+                xw_tma_load<PAIR>(dst, &tm_w, &full_bar[stage], n0, kb * XW_K);
+                xw_tma_load<PAIR>(dst + XW_TILE_BYTES / 2, &tm_w, &full_bar[stage], n0 + 64, kb * XW_K);
+              }
             }
             if (++stage == XW_STAGES) { stage = 0; phase ^= 1; }
           }
@@ -249,13 +259,21 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
       if (ok && item_no > 0) mbar_wait(x_empty, (uint32_t)((item_no - 1) & 1));
     }
   } else if (warp == 1) {
-    // ================= MMA issuer (one lane of the leader CTA) =================
-    if (lane == 0 && rank == 0) {
+    // ================= MMA issuer (leader CTA of the pair) =================
+    // Convergent warp, one elected lane issues: stage / k-block counters live in uniform registers and a
+    // descriptor is the base descriptor plus a 14-bit address offset, so the issue loop stays far shorter than
+    // the 128 tensor cycles each MMA takes (the first version rebuilt both descriptors per MMA from a divergent
+    // lane and was issue-bound: tensor pipe 49 % active with every queue full).
+    if (rank == 0) {
+      const bool leader = elect_one();
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       int item_no = 0;
       bool ok = true;
-      const uint32_t xres_addr = smem_u32(xres), ring_addr = smem_u32(ring);
+      const uint32_t lbo = MN ? (uint32_t)(XW_TILE_BYTES / 2) : 0u;
+      const uint32_t kstep = MN ? 2048u >> 4 : 32u >> 4;         // descriptor address units (16 B)
+      const uint64_t desc_a0 = make_smem_desc(smem_u32(xres), lbo, 1024);
+      const uint64_t desc_b0 = make_smem_desc(smem_u32(ring), lbo, 1024);
       for (int item = cluster_id; item < items && ok; item += n_clusters, ++item_no) {
         const int chunk = item / p.m_groups;
         const int t_begin = (int)((int64_t)chunk * p.n_tiles / p.n_chunks);
@@ -272,23 +290,25 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
             ok = mbar_wait(&full_bar[stage], phase);
             if (!ok) break;
             tc_fence_after_sync();
-            const uint32_t sa = xres_addr + (uint32_t)kb * XW_TILE_BYTES;
-            const uint32_t sb = ring_addr + (uint32_t)stage * XW_TILE_BYTES;
+            if (leader) {
+              const uint64_t da = desc_a0 + (uint64_t)((uint32_t)kb * (XW_TILE_BYTES >> 4));
+              const uint64_t db = desc_b0 + (uint64_t)((uint32_t)stage * (XW_TILE_BYTES >> 4));
 #pragma unroll
-            for (int kk = 0; kk < XW_K / 16; ++kk) {
-              // K-major: +32 B per 16 k; MN-major: +16 k-rows of 128 B, LBO = next 64-wide row block (8 KB)
-              const uint64_t da = MN ? make_smem_desc(sa + kk * 2048, XW_TILE_BYTES / 2, 1024) : make_smem_desc(sa + kk * 32, 0, 1024);
-              const uint64_t db = MN ? make_smem_desc(sb + kk * 2048, XW_TILE_BYTES / 2, 1024) : make_smem_desc(sb + kk * 32, 0, 1024);
-              xw_mma<PAIR>(d_tmem, da, db, p.idesc, (uint32_t)((kb | kk) != 0));
+              for (int kk = 0; kk < XW_K / 16; ++kk)
+                xw_mma<PAIR>(d_tmem, da + (uint64_t)(kk * kstep), db + (uint64_t)(kk * kstep), p.idesc,
+                             (uint32_t)((kb | kk) != 0));
+              xw_commit<PAIR>(&empty_bar[stage]);
             }
-            xw_commit<PAIR>(&empty_bar[stage]);
+            __syncwarp();
             if (++stage == XW_STAGES) { stage = 0; phase ^= 1; }
           }
           if (!ok) break;
-          xw_commit<PAIR>(&acc_full[acc]);
+          if (leader) xw_commit<PAIR>(&acc_full[acc]);
+          __syncwarp();
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if (ok) xw_commit<PAIR>(x_empty);
+        if (ok && leader) xw_commit<PAIR>(x_empty);
+        __syncwarp();
       }
     }
   } else {
@@ -313,6 +333,7 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
         const int col_base = it.half * (TN / 2);
         const uint32_t taddr = tmem_base + (uint32_t)acc * XW_ACC_STRIDE + ((uint32_t)(it.quad * 32) << 16) + (uint32_t)col_base;
         const int cls_base = t * TN + col_base;
+        Epi::tile_begin(stt, ep, p, it, cls_base, (t + 1 < t_end) ? cls_base + TN : -1, TN / 2);
         float va[32], vb[32];
         tmem_ld32_async(taddr, va);
         // two slices per trip, NOT fully unrolled: the policy code exists twice, not 2 * SLICES times (i-cache)

@@ -187,6 +187,12 @@ int b200f_umma_timeout_flag(int reset);
  * b200f_umma_set_pair: process-wide choice between the two for the head calls (default 2); returns the old one. */
 int b200f_umma_xw_selftest(const void* x, const void* w, float* out, int B, int C, int D, int pair, void* stream);
 int b200f_umma_set_pair(int pair);
+/* pipeline probe: rowsum[b] += sum_c (x . w^T)[b,c] with a do-nothing epilogue (rowsum zeroed by the caller) */
+int b200f_umma_xw_probe(const void* x, const void* w, float* rowsum, int B, int C, int D, int pair, void* stream);
+/* Tunables for tests and bench sweeps: "pair" (1 | 2), "g_chunk_mb" (budget in MB of the fp16 logit-gradient buffer
+ * per class chunk of the backward; default 112).  Returns the previous value, -1 for an unknown name.  Workspace
+ * sizes depend on them: query b200f_head_workspace_bytes again after a change. */
+int b200f_set_tunable(const char* name, int value);
 
 #ifdef __cplusplus
 }

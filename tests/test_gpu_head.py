@@ -333,3 +333,53 @@ def test_cfg3_full_size_properties(cuda_device, dtype):
     ref = oracle.head_forward_backward(x[:64].float().numpy(), w[sub].float().numpy(), ysub.numpy(), cfg)
     assert float(l3) == pytest.approx(float(ref["loss"]), rel=TOL_BF16)
     assert rel_err(head3.weight.grad.cpu().numpy(), ref["dw"]) < TOL_BF16
+
+
+def test_graphed_step_matches_eager(cuda_device):
+    """CUDA-graph replay of the fused step (ArcMarginProduct.graphed_step) == the eager forward_loss + backward,
+    bit for bit (the kernels are deterministic), on two different batches through the same captured graph."""
+    import b200face
+    B, C, D = 256, 6000, 512
+    x, w, y = _random_case(B, C, D, 23)
+    cfg = oracle.HeadConfig(current_epoch=12, training=True, label_smoothing=0.05)
+    head = _head_from_cfg(cfg, C, D, cuda_device, w.bfloat16().float())
+    step = head.graphed_step(B, 0.05, torch.bfloat16)
+    g = torch.Generator().manual_seed(99)
+    for trial in range(2):
+        xb = (x if trial == 0 else torch.randn(B, D, generator=g)).bfloat16().to(cuda_device)
+        yb = (y if trial == 0 else torch.randint(0, C, (B,), generator=g)).to(cuda_device)
+        head.zero_grad(set_to_none=True)
+        xe = xb.clone().requires_grad_(True)
+        le = head.forward_loss(xe, yb, 0.05)
+        le.backward()
+        dw_e = head.weight.grad.clone()
+        head.weight.grad = None
+        lg = step(xb, yb)
+        torch.cuda.synchronize()
+        assert float(lg) == float(le)
+        assert torch.equal(step.dx, xe.grad)
+        assert torch.equal(head.weight.grad, dw_e)
+
+
+@pytest.mark.parametrize("mb", [4, 112])
+def test_backward_chunking_is_invisible(cuda_device, mb):
+    """The class-chunk size of the backward (budget of the fp16 logit-gradient buffer) changes launches, not results."""
+    import b200face
+    from b200face import _lib
+    lib = _lib.load_library()
+    B, C, D = 384, 9000, 512
+    x, w, y = _random_case(B, C, D, 31)
+    cfg = oracle.HeadConfig(current_epoch=12, training=True, label_smoothing=0.05)
+    old = lib.b200f_set_tunable(b"g_chunk_mb", mb)
+    try:
+        head = _head_from_cfg(cfg, C, D, cuda_device, w.bfloat16().float())
+        xg = x.bfloat16().to(cuda_device).requires_grad_(True)
+        loss = head.forward_loss(xg, y.to(cuda_device), 0.05)
+        loss.backward()
+        torch.cuda.synchronize()
+    finally:
+        lib.b200f_set_tunable(b"g_chunk_mb", old)
+    ref = oracle.head_forward_backward(x.bfloat16().float().numpy(), w.bfloat16().float().numpy(), y.numpy(), cfg)
+    assert float(loss) == pytest.approx(float(ref["loss"]), rel=TOL_BF16)
+    assert rel_err(head.weight.grad.cpu().numpy(), ref["dw"]) < TOL_BF16
+    assert rel_err(head.last_stats.dx_f32.cpu().numpy(), ref["dx"]) < TOL_BF16
