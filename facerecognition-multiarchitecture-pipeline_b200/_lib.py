@@ -64,6 +64,12 @@ PROTOTYPES = {
     "b200f_gallery_topk": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int64,
                                    c_int64, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_size_t, c_void_p]),
+    "b200f_gallery_has_tc": (c_int, [c_int]),
+    "b200f_gallery_prepare": (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "b200f_gallery_tc_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int]),
+    "b200f_gallery_topk_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
+                                      c_int64, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_size_t, c_void_p]),
     "b200f_umma_selftest": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                     c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b200f_umma_timeout_flag": (c_int, [c_int]),

@@ -1,6 +1,7 @@
 // C ABI, part 3: the gallery match (K4) and the top-k merge.  Declared in include/b200face.h.
 #include "common.cuh"
 #include "gallery_simt.cuh"
+#include "umma_api.cuh"
 
 using namespace b200f;
 
@@ -51,14 +52,39 @@ static int launch_gallery_k(const gallery::Params& p, const GalleryPlan& pl, cud
 }
 
 static int launch_merge(const int64_t* idx_all, const float* score_all, int P, int64_t Q, int k, int metric,
-                        float thresh, int64_t* idx, float* score, uint8_t* accept, cudaStream_t st) {
+                        float thresh, int64_t* idx, float* score, uint8_t* accept, cudaStream_t st,
+                        const uint8_t* only_rows = nullptr) {
   const unsigned grid = (unsigned)ceil_div(Q, 128);
-  if (k <= 1) gallery::merge_kernel<1><<<grid, 128, 0, st>>>(idx_all, score_all, P, Q, k, metric, thresh, idx, score, accept);
-  else if (k <= 4) gallery::merge_kernel<4><<<grid, 128, 0, st>>>(idx_all, score_all, P, Q, k, metric, thresh, idx, score, accept);
-  else if (k <= 8) gallery::merge_kernel<8><<<grid, 128, 0, st>>>(idx_all, score_all, P, Q, k, metric, thresh, idx, score, accept);
-  else gallery::merge_kernel<16><<<grid, 128, 0, st>>>(idx_all, score_all, P, Q, k, metric, thresh, idx, score, accept);
+  if (k <= 1) gallery::merge_kernel<1><<<grid, 128, 0, st>>>(idx_all, score_all, P, Q, k, metric, thresh, idx, score, accept, only_rows);
+  else if (k <= 4) gallery::merge_kernel<4><<<grid, 128, 0, st>>>(idx_all, score_all, P, Q, k, metric, thresh, idx, score, accept, only_rows);
+  else if (k <= 8) gallery::merge_kernel<8><<<grid, 128, 0, st>>>(idx_all, score_all, P, Q, k, metric, thresh, idx, score, accept, only_rows);
+  else gallery::merge_kernel<16><<<grid, 128, 0, st>>>(idx_all, score_all, P, Q, k, metric, thresh, idx, score, accept, only_rows);
   B200F_LAUNCH_OK("gallery::merge_kernel");
   return B200F_OK;
+}
+
+// exact engine: per-chunk top-k on the fp32 CUDA cores + merge (optionally only the rows flagged in only_rows)
+static int run_exact(const void* q, const void* g, int dtype, const float* q_inv, const float* g_inv, int64_t Q, int64_t N,
+                     int64_t index_offset, int D, int k, int metric, float thresh, int64_t* idx, float* score,
+                     uint8_t* accept, char* ws, const GalleryPlan& pl, const uint8_t* only_rows, cudaStream_t st) {
+  gallery::Params p{};
+  p.q = q; p.g = g; p.q_inv = q_inv; p.g_inv = g_inv; p.Q = Q; p.N = N; p.index_offset = index_offset;
+  p.D = D; p.k = k; p.metric = metric; p.tiles_per_chunk = pl.tiles_per_chunk;
+  p.cand_idx = reinterpret_cast<int64_t*>(ws + pl.off_idx);
+  p.cand_score = reinterpret_cast<float*>(ws + pl.off_score);
+  p.only_rows = only_rows;
+  int rc;
+  if (dtype == B200F_F32) {
+    p.vec_q = simt::vec_friendly<float>(q, D); p.vec_g = simt::vec_friendly<float>(g, D);
+    rc = (metric == B200F_METRIC_COS) ? launch_gallery_k<float, simt::OpFma>(p, pl, st)
+                                      : launch_gallery_k<float, simt::OpL2Eps>(p, pl, st);
+  } else {
+    p.vec_q = simt::vec_friendly<__nv_bfloat16>(q, D); p.vec_g = simt::vec_friendly<__nv_bfloat16>(g, D);
+    rc = (metric == B200F_METRIC_COS) ? launch_gallery_k<__nv_bfloat16, simt::OpFma>(p, pl, st)
+                                      : launch_gallery_k<__nv_bfloat16, simt::OpL2Eps>(p, pl, st);
+  }
+  if (rc) return rc;
+  return launch_merge(p.cand_idx, p.cand_score, pl.n_chunks, Q, k, metric, thresh, idx, score, accept, st, only_rows);
 }
 
 extern "C" {
@@ -84,27 +110,56 @@ int b200f_gallery_topk(const void* q, const void* g, int dtype, const float* q_i
     return launch_merge(nullptr, nullptr, 0, Q, k, metric, thresh, idx, score, accept, st);
   }
   if (!g) return fail(B200F_ERR_ARG, "gallery_topk: null gallery");
-  (void)engine;
+  (void)engine;   // this entry is the exact fp32 CUDA-core engine; the tensor engine is b200f_gallery_topk_tc
   const GalleryPlan pl = plan_gallery(Q, N_local, k);
   if (!workspace || workspace_bytes < pl.total)
     return fail(B200F_ERR_WORKSPACE, "gallery_topk: workspace %zu < %zu", workspace_bytes, pl.total);
-  gallery::Params p{};
-  p.q = q; p.g = g; p.q_inv = q_inv; p.g_inv = g_inv; p.Q = Q; p.N = N_local; p.index_offset = index_offset;
-  p.D = D; p.k = k; p.metric = metric; p.tiles_per_chunk = pl.tiles_per_chunk;
-  p.cand_idx = reinterpret_cast<int64_t*>(static_cast<char*>(workspace) + pl.off_idx);
-  p.cand_score = reinterpret_cast<float*>(static_cast<char*>(workspace) + pl.off_score);
-  int rc;
-  if (dtype == B200F_F32) {
-    p.vec_q = simt::vec_friendly<float>(q, D); p.vec_g = simt::vec_friendly<float>(g, D);
-    rc = (metric == B200F_METRIC_COS) ? launch_gallery_k<float, simt::OpFma>(p, pl, st)
-                                      : launch_gallery_k<float, simt::OpL2Eps>(p, pl, st);
-  } else {
-    p.vec_q = simt::vec_friendly<__nv_bfloat16>(q, D); p.vec_g = simt::vec_friendly<__nv_bfloat16>(g, D);
-    rc = (metric == B200F_METRIC_COS) ? launch_gallery_k<__nv_bfloat16, simt::OpFma>(p, pl, st)
-                                      : launch_gallery_k<__nv_bfloat16, simt::OpL2Eps>(p, pl, st);
-  }
+  return run_exact(q, g, dtype, q_inv, g_inv, Q, N_local, index_offset, D, k, metric, thresh, idx, score, accept,
+                   static_cast<char*>(workspace), pl, nullptr, st);
+}
+
+// ---- K4 on tensor cores ---------------------------------------------------------------------------------
+int b200f_gallery_has_tc(int D) { return umma::gallery_tc_supported(D) ? 1 : 0; }
+
+int b200f_gallery_prepare(const void* g, int dtype, int64_t N, int D, int metric, void* g16, float* bias, void* stream) {
+  if (!dtype_ok(dtype)) return fail(B200F_ERR_ARG, "gallery_prepare: bad dtype");
+  if (N < 0 || D <= 0) return fail(B200F_ERR_ARG, "gallery_prepare: bad shape");
+  if (metric != B200F_METRIC_L2EPS && metric != B200F_METRIC_COS) return fail(B200F_ERR_ARG, "gallery_prepare: bad metric");
+  if (N == 0) return B200F_OK;
+  if (!g || !g16 || !bias) return fail(B200F_ERR_ARG, "gallery_prepare: null pointer");
+  return umma::gallery_prepare(g, dtype, N, D, metric, g16, bias, as_stream(stream));
+}
+
+size_t b200f_gallery_tc_workspace_bytes(int64_t Q, int64_t N_local, int D, int k) {
+  if (Q <= 0 || N_local <= 0 || k <= 0) return 256;
+  return align_up(umma::gallery_scan_workspace(Q, N_local, D, k), 256) + align_up((size_t)Q, 256) +
+         plan_gallery(Q, N_local, k).total + 256;
+}
+
+int b200f_gallery_topk_tc(const void* q, const void* g, const void* g16, const float* bias, const float* q_inv,
+                          const float* g_inv, int64_t Q, int64_t N_local, int64_t index_offset, int D, int k, int metric,
+                          float thresh, int64_t* idx, float* score, uint8_t* accept, int32_t* redo_count,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+  if (Q < 0 || N_local <= 0 || D <= 0) return fail(B200F_ERR_ARG, "gallery_topk_tc: bad shape");
+  if (k < 1 || k > 16) return fail(B200F_ERR_ARG, "gallery_topk_tc: k=%d outside [1,16]", k);
+  if (metric != B200F_METRIC_L2EPS && metric != B200F_METRIC_COS) return fail(B200F_ERR_ARG, "gallery_topk_tc: bad metric");
+  if (Q == 0) return B200F_OK;
+  if (!q || !g || !g16 || !bias || !idx || !score) return fail(B200F_ERR_ARG, "gallery_topk_tc: null pointer");
+  const size_t need = b200f_gallery_tc_workspace_bytes(Q, N_local, D, k);
+  if (!workspace || workspace_bytes < need) return fail(B200F_ERR_WORKSPACE, "gallery_topk_tc: workspace %zu < %zu", workspace_bytes, need);
+  cudaStream_t st = as_stream(stream);
+  char* ws = static_cast<char*>(workspace);
+  const size_t scan_bytes = align_up(umma::gallery_scan_workspace(Q, N_local, D, k), 256);
+  uint8_t* redo = reinterpret_cast<uint8_t*>(ws + scan_bytes);
+  char* exact_ws = ws + scan_bytes + align_up((size_t)Q, 256);
+  int rc = umma::gallery_scan_select(static_cast<const float*>(q), static_cast<const float*>(g), g16, bias, q_inv, g_inv, Q,
+                                     N_local, index_offset, D, k, metric, thresh, idx, score, accept, redo, redo_count,
+                                     ws, scan_bytes, st);
   if (rc) return rc;
-  return launch_merge(p.cand_idx, p.cand_score, pl.n_chunks, Q, k, metric, thresh, idx, score, accept, st);
+  // queries whose top-k could not be proven exact: recomputed by the exact engine, gated on the device-side flags
+  const GalleryPlan pl = plan_gallery(Q, N_local, k);
+  return run_exact(q, g, B200F_F32, q_inv, g_inv, Q, N_local, index_offset, D, k, metric, thresh, idx, score, accept,
+                   exact_ws, pl, redo, st);
 }
 
 int b200f_gallery_merge(const int64_t* idx_all, const float* score_all, int P, int64_t Q, int k, int metric,

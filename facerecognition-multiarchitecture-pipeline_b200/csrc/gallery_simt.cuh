@@ -59,6 +59,8 @@ struct Params {
   int tiles_per_chunk;
   int64_t* cand_idx;    // [n_chunks, Q, k]
   float* cand_score;    // [n_chunks, Q, k]
+  const uint8_t* only_rows;   // optional [Q]: compute only the queries flagged 1 (re-run of the tensor engine's
+                              // unverified queries); blocks without a flagged query leave at once
   bool vec_q, vec_g;
 };
 
@@ -76,6 +78,10 @@ topk_kernel(const Params p) {
   const bool cosine = (p.metric == B200F_METRIC_COS);
 
   const int my_row = threadIdx.x & (BM - 1), my_half = threadIdx.x >> 7;
+  if (p.only_rows != nullptr) {
+    const bool mine = (m0 + my_row < p.Q) && p.only_rows[m0 + my_row] != 0;
+    if (!__syncthreads_or(mine)) return;
+  }
   TopK<K, int32_t> top;
   top.init();
 
@@ -144,9 +150,10 @@ template <int K>
 __global__ void merge_kernel(const int64_t* __restrict__ idx_all, const float* __restrict__ score_all,
                              int P, int64_t Q, int k, int metric, float thresh,
                              int64_t* __restrict__ idx, float* __restrict__ score,
-                             uint8_t* __restrict__ accept) {
+                             uint8_t* __restrict__ accept, const uint8_t* __restrict__ only_rows) {
   const int64_t qid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (qid >= Q) return;
+  if (only_rows != nullptr && only_rows[qid] == 0) return;
   const bool cosine = (metric == B200F_METRIC_COS);
   TopK<K, int64_t> top;
   top.init();

@@ -9,6 +9,7 @@
 #include "umma_api.cuh"
 #include "umma_epilogues.cuh"
 #include "umma_xw_epilogues.cuh"
+#include "umma_xw_topk.cuh"
 #include "rowops.cuh"
 
 #include <cudaTypedefs.h>
@@ -167,6 +168,7 @@ __global__ void reduce_r_kernel(const float* __restrict__ r_part, int n_rb, int6
 
 // ---- X-stationary kernel: launch geometry ---------------------------------------------------------
 static std::atomic<int> g_pair{2};                 // 2 = tcgen05 cta_group::2 CTA pairs, 1 = single CTAs
+static std::atomic<int> g_prefetch{0};             // L2 prefetch distance of the xw producer (stages)
 static std::atomic<int> g_chunk_mb{112};           // budget of the fp16 logit-gradient buffer G per class chunk
 
 template <int PAIR, bool MN, class Epi>
@@ -225,13 +227,14 @@ static XwPlan xw_plan(int64_t B, int64_t C, int pair) {
 
 template <int PAIR, bool MN, class Epi>
 static int launch_xw(const CUtensorMap& tx, const CUtensorMap& tw, const XwPlan& q, int64_t B, int64_t C, int D,
-                     const typename Epi::Params& ep, cudaStream_t st, const char* what) {
+                     const typename Epi::Params& ep, cudaStream_t st, const char* what, uint32_t fmt = FMT_F16) {
   int rc = xw_set_smem<PAIR, MN, Epi>(); if (rc) return rc;
   XwParams p{};
   p.B = (int)B; p.C = (int)C; p.D = D;
   p.kb_count = (int)ceil_div(D, XW_K);
   p.m_groups = q.m_groups; p.n_tiles = q.n_tiles; p.n_chunks = q.n_chunks;
-  p.idesc = make_idesc(FMT_F16, FMT_F16, MN, MN, XW_M * PAIR, XW_WROWS * PAIR);
+  p.prefetch = g_prefetch.load(std::memory_order_relaxed);
+  p.idesc = make_idesc(fmt, fmt, MN, MN, XW_M * PAIR, XW_WROWS * PAIR);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)q.grid); cfg.blockDim = dim3(XW_THREADS); cfg.dynamicSmemBytes = XW_SMEM_BYTES; cfg.stream = st;
   cudaLaunchAttribute at[1];
@@ -418,6 +421,90 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
   return B200F_OK;
 }
 
+// ---- K4 on tensor cores: host side ------------------------------------------------------------------
+struct GalleryScanPlan { XwPlan q; int KT, n_lists; size_t off_q16, off_ckey, off_cidx, total; };
+
+static GalleryScanPlan gallery_scan_plan(int64_t Q, int64_t N, int D, int k) {
+  GalleryScanPlan g{};
+  g.q = xw_plan(Q, N, Q > XW_M ? 2 : 1);                 // one CTA holds up to 128 queries; pairs above that
+  g.KT = k <= 1 ? 8 : (k <= 6 ? 16 : 32);
+  g.n_lists = g.q.n_chunks * 2;
+  size_t off = 0;
+  g.off_q16 = off;  off += align_up(2 * (size_t)Q * D, 1024);
+  g.off_ckey = off; off += align_up(sizeof(float) * (size_t)Q * g.n_lists * g.KT, 256);
+  g.off_cidx = off; off += align_up(sizeof(int32_t) * (size_t)Q * g.n_lists * g.KT, 256);
+  g.total = off + 1024;
+  return g;
+}
+
+bool gallery_tc_supported(int D) { return device_is_sm100() && D % 8 == 0 && D <= XW_MAX_KB * XW_K; }
+
+size_t gallery_scan_workspace(int64_t Q, int64_t N, int D, int k) { return gallery_scan_plan(Q, N, D, k).total; }
+
+int gallery_prepare(const void* g, int dtype, int64_t N, int D, int metric, void* g16, float* bias, cudaStream_t st) {
+  if (D > 512) return fail(B200F_ERR_UNSUPPORTED, "gallery_prepare: D <= 512");
+  if (bias) B200F_CUDA_OK(cudaMemsetAsync(bias + N, 0, sizeof(float), st));
+  const unsigned grid = (unsigned)ceil_div(N, 8);
+  if (dtype == B200F_F32)
+    gallery_prepare_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(g), N, D, metric,
+                                                       static_cast<__nv_bfloat16*>(g16), bias);
+  else
+    gallery_prepare_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(g), N, D, metric,
+                                                               static_cast<__nv_bfloat16*>(g16), bias);
+  B200F_LAUNCH_OK("gallery_prepare_kernel");
+  return B200F_OK;
+}
+
+template <int KT>
+static int gallery_scan_kt(const GalleryScanPlan& gp, const CUtensorMap& tx, const CUtensorMap& tw, const float* q,
+                           const float* g, const float* bias, const float* q_inv, const float* g_inv, int64_t Q, int64_t N,
+                           int64_t index_offset, int D, int k, int metric, float thresh, int64_t* idx, float* score,
+                           uint8_t* accept, uint8_t* redo, int32_t* redo_count, float* ckey, int32_t* cidx, cudaStream_t st) {
+  typename XwTopK<KT>::Params ep{};
+  ep.bias = (metric == B200F_METRIC_COS) ? nullptr : bias;
+  ep.mult = (metric == B200F_METRIC_COS) ? -1.0f : -2.0f;
+  ep.cand_key = ckey; ep.cand_idx = cidx; ep.n_lists = gp.n_lists;
+  int rc = (gp.q.pair == 2) ? launch_xw<2, false, XwTopK<KT>>(tx, tw, gp.q, Q, N, D, ep, st, "umma K4 gallery scan (cta pair)", FMT_BF16)
+                            : launch_xw<1, false, XwTopK<KT>>(tx, tw, gp.q, Q, N, D, ep, st, "umma K4 gallery scan", FMT_BF16);
+  if (rc) return rc;
+  const int n_cand = gp.n_lists * KT;
+  const size_t smem = (size_t)n_cand * 8;
+  auto kern = gallery_select_kernel<float, KT>;
+  B200F_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 160 * 1024 ? 160 * 1024 : (smem < 1024 ? 1024 : smem))));
+  if (smem > 160 * 1024) return fail(B200F_ERR_UNSUPPORTED, "gallery scan: candidate lists do not fit shared memory");
+  kern<<<(unsigned)Q, 128, smem, st>>>(ckey, cidx, n_cand, q, g, q_inv, g_inv, bias ? bias + N : nullptr, Q, D, k, metric,
+                                       thresh, index_offset, idx, score, accept, redo, redo_count);
+  B200F_LAUNCH_OK("gallery_select_kernel");
+  return B200F_OK;
+}
+
+// q, g: fp32 [Q,D], [N,D]; g16 / bias from gallery_prepare (same metric).  Fills idx / score / accept for every
+// query and redo[Q] = 1 where exactness could not be proven (the caller re-runs those on the exact engine).
+int gallery_scan_select(const float* q, const float* g, const void* g16, const float* bias, const float* q_inv,
+                        const float* g_inv, int64_t Q, int64_t N, int64_t index_offset, int D, int k, int metric,
+                        float thresh, int64_t* idx, float* score, uint8_t* accept, uint8_t* redo, int32_t* redo_count,
+                        char* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!gallery_tc_supported(D)) return fail(B200F_ERR_UNSUPPORTED, "gallery scan: needs sm_100, D %% 8 == 0, D <= 512");
+  if (N >= ((int64_t)1 << 31) - 512 || Q >= ((int64_t)1 << 30)) return fail(B200F_ERR_UNSUPPORTED, "gallery scan: N < 2^31, Q < 2^30");
+  const GalleryScanPlan gp = gallery_scan_plan(Q, N, D, k);
+  if (ws_bytes < gp.total) return fail(B200F_ERR_WORKSPACE, "gallery scan: workspace too small");
+  ws = ws_align(ws);
+  __nv_bfloat16* q16 = reinterpret_cast<__nv_bfloat16*>(ws + gp.off_q16);
+  float* ckey = reinterpret_cast<float*>(ws + gp.off_ckey);
+  int32_t* cidx = reinterpret_cast<int32_t*>(ws + gp.off_cidx);
+  gallery_prepare_kernel<float><<<(unsigned)ceil_div(Q, 8), 256, 0, st>>>(q, Q, D, B200F_METRIC_L2EPS, q16, nullptr);
+  B200F_LAUNCH_OK("gallery_prepare_kernel (queries)");
+  CUtensorMap tx, tw;
+  int rc = tmap_kmajor(&tx, q16, Q, D, D, XW_M); if (rc) return rc;
+  rc = tmap_kmajor(&tw, g16, N, D, D, XW_WROWS); if (rc) return rc;
+#define B200F_SCAN(KT) gallery_scan_kt<KT>(gp, tx, tw, q, g, bias, q_inv, g_inv, Q, N, index_offset, D, k, metric, thresh, idx, \
+                                           score, accept, redo, redo_count, ckey, cidx, st)
+  if (gp.KT == 8) return B200F_SCAN(8);
+  if (gp.KT == 16) return B200F_SCAN(16);
+  return B200F_SCAN(32);
+#undef B200F_SCAN
+}
+
 }  // namespace umma
 }  // namespace b200f
 
@@ -501,6 +588,7 @@ int b200f_set_tunable(const char* name, int value) {
   if (!name) return -1;
   const std::string n(name);
   if (n == "pair") return b200f_umma_set_pair(value);
+  if (n == "xw_prefetch") { if (value < 0) return g_prefetch.load(); return g_prefetch.exchange(value); }
   if (n == "g_chunk_mb") { if (value < 1) return g_chunk_mb.load(); return g_chunk_mb.exchange(value); }
   return -1;
 }

@@ -253,23 +253,24 @@ struct XwBwdG {
     const float q_off = ep.ls_eps * ep.inv_Ctot;
     const float gq = gs * q_off;
     float g[32];
-    float mn4[4] = {INFINITY, INFINITY, INFINITY, INFINITY}, mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-    float ck4[4] = {0.f, 0.f, 0.f, 0.f};
+    // One NaN-propagating max over |acc| covers both guards of the fast path: a NaN / Inf accumulator and a cosine
+    // outside the (symmetric) clamp range (max.NaN.xorsign.abs: magnitude = max(|a|,|b|), NaN if either is NaN).
+    float am4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const float tt = v[j + u];
         g[j + u] = fmaf(gs, ex2_approx(fmaf(tt, a, b)), -gq);
-        mn4[u] = fminf(mn4[u], tt); mx4[u] = fmaxf(mx4[u], tt);
-        ck4[u] += tt;
+        asm("max.NaN.xorsign.abs.f32 %0, %0, %1;" : "+f"(am4[u]) : "f"(tt));
       }
     }
-    const float tmn = fminf(fminf(mn4[0], mn4[1]), fminf(mn4[2], mn4[3]));
-    const float tmx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-    const float chk = (ck4[0] + ck4[1]) + (ck4[2] + ck4[3]);
+    float amax = 0.f;
+    asm("max.NaN.xorsign.abs.f32 %0, %1, %2;" : "=f"(amax) : "f"(am4[0]), "f"(am4[1]));
+    asm("max.NaN.xorsign.abs.f32 %0, %0, %1;" : "+f"(amax) : "f"(am4[2]));
+    asm("max.NaN.xorsign.abs.f32 %0, %0, %1;" : "+f"(amax) : "f"(am4[3]));
     const bool has_t = (st.tgt >= cls0) && (st.tgt < cls0 + 32);
-    bool careful = !(s_eff > 0.f) || has_t || !(tmx * isc <= hi) || !(tmn * isc >= lo) || !isfinite(chk);
+    bool careful = !(s_eff > 0.f) || has_t || !(fabsf(amax) * isc <= hi);     // NaN fails the comparison
     careful = __any_sync(0xffffffffu, careful);
     if (careful) {
       float tphi = 0.f, tdphi = 0.f;                          // phi / dphi once per slice (see XwFwd)

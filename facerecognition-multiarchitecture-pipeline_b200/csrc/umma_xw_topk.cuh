@@ -1,0 +1,262 @@
+// K4 on tensor cores: epilogue policy of the X-stationary kernel (umma_xw.cuh) that turns the query x gallery
+// product into per-query candidate lists, plus the prepare / select kernels around it.
+//
+//   scan   : xw_kernel<PAIR, K-major, XwTopK<KT>>  -- queries (bf16) resident in shared memory, gallery rows (bf16)
+//            streamed once from HBM; an epilogue thread owns ONE query and keeps the KT smallest approximate keys
+//            of the gallery columns it sees in registers (sorted insertion, first index wins ties)
+//              L2EPS: a_ij = (|g_j|^2 - 2e-6 sum g_j) - 2 <q_i, g_j>      (= d_ij^2 minus a per-query constant)
+//              COS  : a_ij = - <q_i, g_j / |g_j|>
+//   select : per query, merge the per-(chunk, half) lists to the KT best, RE-SCORE them exactly in fp32 against the
+//            original gallery rows with the reference formula (src/app.py:59: ||q - g + 1e-6||), order by (score,
+//            index), and VERIFY that no row the scan excluded can belong to the top-k: every excluded row has an
+//            approximate key >= the worst kept one, and |approx - exact| <= delta (bf16 operand rounding bound), so
+//            exact_kth < worst_kept - delta proves exactness.  Queries that fail the test are flagged and recomputed
+//            by the exact fp32 CUDA-core engine in the same stream (no host round trip).
+#pragma once
+#include <cuda_bf16.h>
+#include "common.cuh"
+#include "umma_xw.cuh"
+
+namespace b200f {
+namespace umma {
+
+constexpr float GALLERY_EPS = 1e-6f;            // F.pairwise_distance default eps, added to the difference
+// |<q,g> - <bf16(q), bf16(g)>| <= (2u + u^2) |q||g| with u = 2^-9 (round to nearest), plus fp32 accumulation
+constexpr float GALLERY_DOT_ERR = 3.95e-3f;
+
+template <int KT>
+struct XwTopK {
+  struct Params {
+    const float* bias;          // [N] per gallery row (L2EPS) or NULL (COS)
+    float mult;                 // -2 (L2EPS) / -1 (COS)
+    float* cand_key;            // [Q, n_lists, KT]
+    int32_t* cand_idx;          // [Q, n_lists, KT]   gallery row (shard-local), -1 = empty
+    int n_lists;                // n_chunks * 2
+  };
+  struct State { float key[KT]; int32_t idx[KT]; bool row_ok; };
+
+  static __device__ __forceinline__ void item_begin(State& st, const Params&, const XwParams& p, const XwItem& it) {
+#pragma unroll
+    for (int s = 0; s < KT; ++s) { st.key[s] = INFINITY; st.idx[s] = -1; }
+    st.row_ok = it.row < p.B;
+  }
+  static __device__ __forceinline__ void tile_begin(State&, const Params&, const XwParams&, const XwItem&, int, int, int) {}
+
+  static __device__ __forceinline__ void insert(State& st, float k, int32_t id) {
+    st.key[KT - 1] = k; st.idx[KT - 1] = id;
+#pragma unroll
+    for (int s = KT - 1; s > 0; --s) {
+      if (st.key[s] < st.key[s - 1]) {                        // strict: an equal key stays behind the earlier index
+        const float tk = st.key[s]; st.key[s] = st.key[s - 1]; st.key[s - 1] = tk;
+        const int32_t ti = st.idx[s]; st.idx[s] = st.idx[s - 1]; st.idx[s - 1] = ti;
+      }
+    }
+  }
+
+  static __device__ __forceinline__ void slice(State& st, const Params& ep, const XwParams& p, const XwItem&,
+                                               float (&v)[32], int cls0) {
+    const int cc = min(32, p.C - cls0);
+    float a[32];
+    if (ep.bias != nullptr) {
+      if (cc == 32) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) a[j] = fmaf(v[j], ep.mult, __ldg(ep.bias + cls0 + j));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) a[j] = (j < cc) ? fmaf(v[j], ep.mult, __ldg(ep.bias + cls0 + j)) : INFINITY;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) a[j] = (j < cc) ? v[j] * ep.mult : INFINITY;
+    }
+    float m4[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) m4[u] = fminf(m4[u], a[j + u]);
+    }
+    const float smin = fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3]));
+    if (smin < st.key[KT - 1]) {                              // rare once the list has warmed up
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (a[j] < st.key[KT - 1]) insert(st, a[j], cls0 + j); // NaN keys never enter (like `dist < min_dist`)
+    }
+  }
+
+  static __device__ __forceinline__ void item_end(State& st, const Params& ep, const XwParams&, const XwItem& it, float*) {
+    if (!st.row_ok) return;
+    const int64_t base = ((int64_t)it.row * ep.n_lists + it.chunk * 2 + it.half) * KT;
+#pragma unroll
+    for (int s = 0; s < KT; s += 4) {
+      *reinterpret_cast<float4*>(ep.cand_key + base + s) = make_float4(st.key[s], st.key[s + 1], st.key[s + 2], st.key[s + 3]);
+      *reinterpret_cast<int4*>(ep.cand_idx + base + s) = make_int4(st.idx[s], st.idx[s + 1], st.idx[s + 2], st.idx[s + 3]);
+    }
+  }
+};
+
+// ---- prepare: rows -> bf16 scan operand (+ bias, + max row norm) ---------------------------------------
+// One warp per row (D <= 512, D % 8 == 0).  metric COS: out = g / max(|g|, 1e-12); L2EPS: out = g.
+// bias[r] = |g|^2 - 2 eps sum(g) (L2EPS) / 0 (COS); bias[rows] (one extra slot) = max row norm via atomicMax.
+template <typename TI>
+__global__ void __launch_bounds__(256)
+gallery_prepare_kernel(const TI* __restrict__ in, int64_t rows, int dim, int metric, __nv_bfloat16* __restrict__ out,
+                       float* __restrict__ bias) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float v[16];                                                // dim <= 512: 16 elements per lane
+  float ss = 0.f, sm = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int d = lane + 32 * i;
+    v[i] = (d < dim) ? to_f32<TI>(in[row * dim + d]) : 0.f;
+    ss = fmaf(v[i], v[i], ss); sm += v[i];
+  }
+  ss = warp_sum(ss); sm = warp_sum(sm);
+  const float nrm = sqrtf(ss);
+  const float sc = (metric == B200F_METRIC_COS) ? 1.0f / fmaxf(nrm, 1e-12f) : 1.0f;
+  if (out != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int d = lane + 32 * i;
+      if (d < dim) out[row * dim + d] = __float2bfloat16_rn(v[i] * sc);
+    }
+  }
+  if (bias != nullptr && lane == 0) {
+    bias[row] = (metric == B200F_METRIC_COS) ? 0.f : (ss - 2.0f * GALLERY_EPS * sm);
+    const float eff = (metric == B200F_METRIC_COS) ? 1.0f : nrm;
+    if (eff == eff) atomicMax(reinterpret_cast<int*>(bias + rows), __float_as_int(eff));   // norms are >= 0
+  }
+}
+
+// ---- select: merge lists, exact re-rank, verification ----------------------------------------------------
+// One block of 128 threads per query.  Candidates in shared memory; KT rounds of block-wide lexicographic
+// arg-min pick the KT best approximate keys; each is re-scored exactly (thread t owns elements t, t+128, ..).
+template <typename TG, int KT>
+__global__ void __launch_bounds__(128)
+gallery_select_kernel(const float* __restrict__ cand_key, const int32_t* __restrict__ cand_idx, int n_cand,
+                      const float* __restrict__ q, const TG* __restrict__ g, const float* __restrict__ q_inv,
+                      const float* __restrict__ g_inv, const float* __restrict__ gmax_ptr, int64_t Q, int D, int k,
+                      int metric, float thresh, int64_t index_offset, int64_t* __restrict__ idx_out,
+                      float* __restrict__ score_out, uint8_t* __restrict__ accept, uint8_t* __restrict__ redo,
+                      int32_t* __restrict__ redo_count) {
+  extern __shared__ uint8_t sel_smem[];
+  float* ckey = reinterpret_cast<float*>(sel_smem);
+  int32_t* cidx = reinterpret_cast<int32_t*>(ckey + n_cand);
+  __shared__ float red_k[4]; __shared__ int red_i[4]; __shared__ int red_pos[4];
+  __shared__ float win_key[KT]; __shared__ int win_idx[KT]; __shared__ float ex_key[KT];
+  __shared__ float qstat[2];
+  const int64_t qi = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const bool cosine = (metric == B200F_METRIC_COS);
+  for (int i = tid; i < n_cand; i += 128) { ckey[i] = cand_key[qi * n_cand + i]; cidx[i] = cand_idx[qi * n_cand + i]; }
+  // per-query constants: |q|^2, sum q
+  float nq = 0.f, sq = 0.f;
+  for (int d = tid; d < D; d += 128) { const float x = q[qi * D + d]; nq = fmaf(x, x, nq); sq += x; }
+  nq = warp_sum(nq); sq = warp_sum(sq);
+  if (lane == 0) { red_k[wid] = nq; ex_key[wid] = sq; }
+  __syncthreads();
+  if (tid == 0) { qstat[0] = red_k[0] + red_k[1] + red_k[2] + red_k[3]; qstat[1] = ex_key[0] + ex_key[1] + ex_key[2] + ex_key[3]; }
+  __syncthreads();
+  // ---- KT rounds of arg-min over the candidates
+  for (int r = 0; r < KT; ++r) {
+    float bk = INFINITY; int bi = INT32_MAX, bp = -1;
+    for (int i = tid; i < n_cand; i += 128) {
+      const int id = cidx[i]; const float kk = ckey[i];
+      if (id >= 0 && (kk < bk || (kk == bk && id < bi))) { bk = kk; bi = id; bp = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ok = __shfl_xor_sync(0xffffffffu, bk, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o), op = __shfl_xor_sync(0xffffffffu, bp, o);
+      if (op >= 0 && (bp < 0 || ok < bk || (ok == bk && oi < bi))) { bk = ok; bi = oi; bp = op; }
+    }
+    if (lane == 0) { red_k[wid] = bk; red_i[wid] = bi; red_pos[wid] = bp; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < 4; ++w)
+        if (red_pos[w] >= 0 && (bp < 0 || red_k[w] < bk || (red_k[w] == bk && red_i[w] < bi))) { bk = red_k[w]; bi = red_i[w]; bp = red_pos[w]; }
+      win_key[r] = bk; win_idx[r] = (bp >= 0) ? bi : -1;
+      if (bp >= 0) cidx[bp] = -1;                              // taken
+    }
+    __syncthreads();
+  }
+  // ---- exact re-score of the winners (reference formula, fp32)
+  for (int r = 0; r < KT; ++r) {
+    const int id = win_idx[r];
+    float acc = 0.f;
+    if (id >= 0) {
+      const TG* row = g + (int64_t)id * D;
+      for (int d = tid; d < D; d += 128) {
+        const float x = q[qi * D + d], y = to_f32<TG>(row[d]);
+        if (cosine) acc = fmaf(x, y, acc);
+        else { const float df = x - y + GALLERY_EPS; acc = fmaf(df, df, acc); }
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) red_k[wid] = acc;
+    __syncthreads();
+    if (tid == 0) {
+      const float tot = (red_k[0] + red_k[1]) + (red_k[2] + red_k[3]);
+      // ordering key, smaller is better: the distance / minus the cosine (as the exact engine)
+      float e;
+      if (id < 0) e = INFINITY;
+      else if (cosine) e = -(tot * (q_inv ? q_inv[qi] : 1.0f) * (g_inv ? g_inv[id] : 1.0f));
+      else e = sqrtf(tot);
+      ex_key[r] = e;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    // insertion sort of the KT winners by (exact key, index); NaN keys go last
+    for (int a = 1; a < KT; ++a) {
+      const float ka = ex_key[a]; const int ia = win_idx[a]; const float wa = win_key[a];
+      int b = a - 1;
+      while (b >= 0) {
+        const float kb = ex_key[b]; const int ib = win_idx[b];
+        const bool a_first = (ia >= 0) && (ib < 0 || (ka == ka && (kb != kb || ka < kb || (ka == kb && ia < ib))));
+        if (!a_first) break;
+        ex_key[b + 1] = kb; win_idx[b + 1] = ib; win_key[b + 1] = win_key[b];
+        --b;
+      }
+      ex_key[b + 1] = ka; win_idx[b + 1] = ia; win_key[b + 1] = wa;
+    }
+    // worst kept approximate key = lower bound of every excluded row's approximate key
+    float a_excl = -INFINITY; int n_valid = 0;
+    for (int r = 0; r < KT; ++r) if (win_idx[r] >= 0) { a_excl = fmaxf(a_excl, win_key[r]); ++n_valid; }
+    bool verified = true;
+    if (n_valid == KT && n_cand > 0) {                         // something may have been excluded
+      const int kk = min(k, n_valid);
+      const float ek = ex_key[kk - 1];                         // exact k-th best ordering key
+      const float qn = sqrtf(qstat[0]);
+      const float gmax = gmax_ptr ? __int_as_float(*reinterpret_cast<const int*>(gmax_ptr)) : 1.0f;
+      float exact_in_approx_units, delta;
+      if (cosine) {
+        // approx a = -<q, g_hat>; exact ordering key e = -cos * ... = -(<q,g> g_inv) q_inv  ->  -<q,g_hat> = e / q_inv
+        const float qv = q_inv ? q_inv[qi] : 1.0f;
+        exact_in_approx_units = (qv > 0.f) ? ek / qv : -INFINITY;
+        delta = GALLERY_DOT_ERR * qn * 1.01f;
+      } else {
+        // approx a = d^2 - (|q|^2 + 2 eps sum q + D eps^2)
+        exact_in_approx_units = ek * ek - (qstat[0] + 2.0f * GALLERY_EPS * qstat[1] + (float)D * GALLERY_EPS * GALLERY_EPS);
+        delta = 2.0f * GALLERY_DOT_ERR * qn * gmax + 1e-6f * (qstat[0] + gmax * gmax + 1.0f);
+      }
+      verified = (ek == ek) && (exact_in_approx_units < a_excl - delta);
+    }
+    for (int s = 0; s < k; ++s) {
+      const bool ok = (s < KT) && win_idx[s] >= 0 && ex_key[s] == ex_key[s];
+      idx_out[qi * k + s] = ok ? (index_offset + win_idx[s]) : -1;
+      score_out[qi * k + s] = ok ? (cosine ? -ex_key[s] : ex_key[s]) : (cosine ? -INFINITY : INFINITY);
+    }
+    if (accept != nullptr) {
+      const bool ok = win_idx[0] >= 0 && ex_key[0] == ex_key[0];
+      const float best = cosine ? -ex_key[0] : ex_key[0];
+      accept[qi] = ok && (cosine ? (best >= thresh) : (best <= thresh));
+    }
+    redo[qi] = verified ? 0 : 1;
+    if (!verified && redo_count != nullptr) atomicAdd(redo_count, 1);
+  }
+}
+
+}  // namespace umma
+}  // namespace b200f

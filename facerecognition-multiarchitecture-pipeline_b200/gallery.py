@@ -36,14 +36,52 @@ def _inv_norm(t: torch.Tensor) -> torch.Tensor:
     return inv
 
 
+TC_MIN_WORK = 1 << 22        # Q*N below this stays on the exact CUDA-core engine (launch-bound anyway)
+
+
+class PreparedGallery:
+    """Scan operand of the tensor engine for one gallery and one metric (b200f_gallery_prepare): the bf16 rows
+    (L2-normalised for 'cos') and the per-row bias.  Build it once per gallery version; every query batch then
+    streams 2 bytes per gallery element instead of 4."""
+
+    def __init__(self, g: torch.Tensor, metric: str):
+        require_cuda(g)
+        lib = _lib.load_library()
+        self.metric = metric
+        self.N, self.D = g.shape
+        self.key = (g.data_ptr(), g._version, tuple(g.shape), metric)
+        self.g16 = torch.empty(self.N, self.D, dtype=torch.bfloat16, device=g.device)
+        self.bias = torch.empty(self.N + 1, dtype=torch.float32, device=g.device)
+        check(lib.b200f_gallery_prepare(ptr(g), dtype_code(g), self.N, self.D, _METRICS[metric], ptr(self.g16),
+                                        ptr(self.bias), stream_ptr(g.device)), "b200f_gallery_prepare")
+
+    def matches(self, g: torch.Tensor, metric: str) -> bool:
+        return self.key == (g.data_ptr(), g._version, tuple(g.shape), metric)
+
+
+def tensor_engine_ok(q: torch.Tensor, g: torch.Tensor, engine: int) -> bool:
+    """The bf16 tcgen05 scan + exact re-rank takes fp32 inputs with D % 8 == 0, D <= 512 on sm_100; AUTO uses it
+    once the scan is big enough to matter."""
+    if engine == _lib.ENGINE_SIMT or q.dtype != torch.float32 or g.shape[0] == 0:
+        return False
+    if not _lib.load_library().b200f_gallery_has_tc(q.shape[1]):
+        if engine == _lib.ENGINE_TCGEN05:
+            raise RuntimeError("the tensor gallery engine needs sm_100, D % 8 == 0 and D <= 512")
+        return False
+    return engine == _lib.ENGINE_TCGEN05 or q.shape[0] * g.shape[0] >= TC_MIN_WORK
+
+
 def gallery_topk(q: torch.Tensor, g: torch.Tensor, k: int = 1, thresh: float = 1.0, metric: str = "l2eps",
                  *, index_offset: int = 0, g_inv: Optional[torch.Tensor] = None,
-                 engine: int = _lib.ENGINE_AUTO) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+                 engine: int = _lib.ENGINE_AUTO, prepared: Optional[PreparedGallery] = None,
+                 redo_count: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """Per query the k best gallery rows.  q [Q,D], g [N,D] CUDA, same dtype (fp32 / bf16).
     metric 'l2eps': score = ||q - g + 1e-6||_2 ascending, accept = best <= thresh  (app.py:59-64)
     metric 'cos'  : score = cosine of the row-normalised vectors, descending, accept = best >= thresh
     Returns (idx [Q,k] int64 global row ids, -1 = no such neighbour; score [Q,k] fp32; accept [Q] bool).
-    Ties go to the lowest index (strict '<', app.py:60)."""
+    Ties go to the lowest index (strict '<', app.py:60).
+    engine: AUTO = tensor engine for big fp32 scans (results identical to the exact engine), SIMT = exact fp32
+    CUDA-core engine, TCGEN05 = force the tensor engine.  prepared: a PreparedGallery of g to reuse."""
     if metric not in _METRICS:
         raise ValueError(f"metric must be one of {list(_METRICS)}")
     if not 1 <= k <= MAX_K:
@@ -66,6 +104,18 @@ def gallery_topk(q: torch.Tensor, g: torch.Tensor, k: int = 1, thresh: float = 1
     if metric == "cos":
         q_inv = _inv_norm(q)
         gi = g_inv if g_inv is not None else _inv_norm(g)
+    if tensor_engine_ok(q, g, engine):
+        # tensor engine: bf16 tcgen05 scan of the prepared gallery, exact fp32 re-rank, proof of exactness per query
+        # (unproven queries are recomputed by the exact engine on the device; redo_count counts them)
+        if prepared is None or not prepared.matches(g, metric):
+            prepared = PreparedGallery(g, metric)
+        nbytes = lib.b200f_gallery_tc_workspace_bytes(Q, N, D, k)
+        ws = _lib.workspace(nbytes, dev, "gallery_tc")
+        check(lib.b200f_gallery_topk_tc(ptr(q), ptr(g), ptr(prepared.g16), ptr(prepared.bias), ptr(q_inv), ptr(gi), Q, N,
+                                        int(index_offset), D, k, _METRICS[metric], float(thresh), ptr(idx), ptr(score),
+                                        ptr(accept), ptr(redo_count), ptr(ws), ws.numel(), stream_ptr(dev)),
+              "b200f_gallery_topk_tc")
+        return idx, score, accept.bool()
     nbytes = lib.b200f_gallery_workspace_bytes(Q, N, D, k, dtype_code(q), engine)
     ws = _lib.workspace(nbytes, dev, "gallery")
     check(lib.b200f_gallery_topk(ptr(q), ptr(g), dtype_code(q), ptr(q_inv), ptr(gi), Q, N, int(index_offset), D,
@@ -168,10 +218,23 @@ class GalleryIndex:
         return [{'name': n, 'embedding_numpy': emb[i:i + 1].copy(),
                  'image_path': image_paths[i] if image_paths else None} for i, n in enumerate(self.names)]
 
-    def match(self, emb: torch.Tensor, thresh: float = 1.0, k: int = 1, metric: str = "l2eps"):
+    def prepared(self, metric: str = "l2eps") -> PreparedGallery:
+        """The tensor engine's scan operand for the current contents (rebuilt after add / delete)."""
+        g = self.embeddings
+        cache = self.__dict__.setdefault("_prepared", {})
+        pg = cache.get(metric)
+        if pg is None or not pg.matches(g, metric):
+            pg = PreparedGallery(g, metric)
+            cache[metric] = pg
+        return pg
+
+    def match(self, emb: torch.Tensor, thresh: float = 1.0, k: int = 1, metric: str = "l2eps",
+              engine: int = _lib.ENGINE_AUTO):
         """Batched compare_faces: emb [Q,D].  Returns (idx, score, accept) device tensors."""
         q = emb.reshape(-1, self.dim).to(device=self.device, dtype=self.dtype)
-        return gallery_topk(q, self.embeddings, k, thresh, metric)
+        g = self.embeddings
+        pg = self.prepared(metric) if tensor_engine_ok(q, g, engine) else None
+        return gallery_topk(q, g, k, thresh, metric, engine=engine, prepared=pg)
 
     def compare_faces(self, emb: Optional[torch.Tensor], thresh: float):
         """compare_faces(emb, refs, thresh) against the resident gallery."""
