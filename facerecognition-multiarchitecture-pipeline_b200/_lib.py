@@ -14,6 +14,7 @@ import torch
 
 F32, BF16, F16N = 0, 1, 2
 METRIC_L2EPS, METRIC_COS = 0, 1
+OPERAND_BF16, OPERAND_FP16 = 0, 1
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
 STAT_SUMEXP, STAT_SUMEXP2, STAT_ZTARGET, STAT_SUMZ, STAT_COLS = 0, 1, 2, 3, 4
 
@@ -65,10 +66,10 @@ PROTOTYPES = {
                                    c_int64, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_size_t, c_void_p]),
     "b200f_gallery_has_tc": (c_int, [c_int]),
-    "b200f_gallery_prepare": (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "b200f_gallery_prepare": (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "b200f_gallery_tc_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int]),
     "b200f_gallery_topk_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
-                                      c_int64, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_int64, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_size_t, c_void_p]),
     "b200f_umma_selftest": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                     c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),

@@ -121,13 +121,15 @@ int b200f_gallery_topk(const void* q, const void* g, int dtype, const float* q_i
 // ---- K4 on tensor cores ---------------------------------------------------------------------------------
 int b200f_gallery_has_tc(int D) { return umma::gallery_tc_supported(D) ? 1 : 0; }
 
-int b200f_gallery_prepare(const void* g, int dtype, int64_t N, int D, int metric, void* g16, float* bias, void* stream) {
+int b200f_gallery_prepare(const void* g, int dtype, int64_t N, int D, int metric, int operand_fmt, void* g16, float* bias,
+                          void* stream) {
   if (!dtype_ok(dtype)) return fail(B200F_ERR_ARG, "gallery_prepare: bad dtype");
   if (N < 0 || D <= 0) return fail(B200F_ERR_ARG, "gallery_prepare: bad shape");
   if (metric != B200F_METRIC_L2EPS && metric != B200F_METRIC_COS) return fail(B200F_ERR_ARG, "gallery_prepare: bad metric");
   if (N == 0) return B200F_OK;
   if (!g || !g16 || !bias) return fail(B200F_ERR_ARG, "gallery_prepare: null pointer");
-  return umma::gallery_prepare(g, dtype, N, D, metric, g16, bias, as_stream(stream));
+  if (operand_fmt != B200F_OPERAND_BF16 && operand_fmt != B200F_OPERAND_FP16) return fail(B200F_ERR_ARG, "gallery_prepare: bad operand format");
+  return umma::gallery_prepare(g, dtype, N, D, metric, operand_fmt, g16, bias, as_stream(stream));
 }
 
 size_t b200f_gallery_tc_workspace_bytes(int64_t Q, int64_t N_local, int D, int k) {
@@ -138,7 +140,7 @@ size_t b200f_gallery_tc_workspace_bytes(int64_t Q, int64_t N_local, int D, int k
 
 int b200f_gallery_topk_tc(const void* q, const void* g, const void* g16, const float* bias, const float* q_inv,
                           const float* g_inv, int64_t Q, int64_t N_local, int64_t index_offset, int D, int k, int metric,
-                          float thresh, int64_t* idx, float* score, uint8_t* accept, int32_t* redo_count,
+                          int operand_fmt, float thresh, int64_t* idx, float* score, uint8_t* accept, int32_t* redo_count,
                           void* workspace, size_t workspace_bytes, void* stream) {
   if (Q < 0 || N_local <= 0 || D <= 0) return fail(B200F_ERR_ARG, "gallery_topk_tc: bad shape");
   if (k < 1 || k > 16) return fail(B200F_ERR_ARG, "gallery_topk_tc: k=%d outside [1,16]", k);
@@ -153,7 +155,7 @@ int b200f_gallery_topk_tc(const void* q, const void* g, const void* g16, const f
   uint8_t* redo = reinterpret_cast<uint8_t*>(ws + scan_bytes);
   char* exact_ws = ws + scan_bytes + align_up((size_t)Q, 256);
   int rc = umma::gallery_scan_select(static_cast<const float*>(q), static_cast<const float*>(g), g16, bias, q_inv, g_inv, Q,
-                                     N_local, index_offset, D, k, metric, thresh, idx, score, accept, redo, redo_count,
+                                     N_local, index_offset, D, k, metric, operand_fmt, thresh, idx, score, accept, redo, redo_count,
                                      ws, scan_bytes, st);
   if (rc) return rc;
   // queries whose top-k could not be proven exact: recomputed by the exact engine, gated on the device-side flags

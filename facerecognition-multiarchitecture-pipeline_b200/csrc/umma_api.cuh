@@ -19,9 +19,9 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
 // K4 on tensor cores (umma_xw_topk.cuh): bf16 tcgen05 scan + exact fp32 re-rank + verification
 bool gallery_tc_supported(int D);
 size_t gallery_scan_workspace(int64_t Q, int64_t N, int D, int k);
-int gallery_prepare(const void* g, int dtype, int64_t N, int D, int metric, void* g16, float* bias, cudaStream_t st);
+int gallery_prepare(const void* g, int dtype, int64_t N, int D, int metric, int fmt, void* g16, float* bias, cudaStream_t st);
 int gallery_scan_select(const float* q, const float* g, const void* g16, const float* bias, const float* q_inv,
-                        const float* g_inv, int64_t Q, int64_t N, int64_t index_offset, int D, int k, int metric,
+                        const float* g_inv, int64_t Q, int64_t N, int64_t index_offset, int D, int k, int metric, int fmt,
                         float thresh, int64_t* idx, float* score, uint8_t* accept, uint8_t* redo, int32_t* redo_count,
                         char* ws, size_t ws_bytes, cudaStream_t st);
 

@@ -441,16 +441,16 @@ bool gallery_tc_supported(int D) { return device_is_sm100() && D % 8 == 0 && D <
 
 size_t gallery_scan_workspace(int64_t Q, int64_t N, int D, int k) { return gallery_scan_plan(Q, N, D, k).total; }
 
-int gallery_prepare(const void* g, int dtype, int64_t N, int D, int metric, void* g16, float* bias, cudaStream_t st) {
+int gallery_prepare(const void* g, int dtype, int64_t N, int D, int metric, int fmt, void* g16, float* bias, cudaStream_t st) {
   if (D > 512) return fail(B200F_ERR_UNSUPPORTED, "gallery_prepare: D <= 512");
   if (bias) B200F_CUDA_OK(cudaMemsetAsync(bias + N, 0, sizeof(float), st));
   const unsigned grid = (unsigned)ceil_div(N, 8);
   if (dtype == B200F_F32)
-    gallery_prepare_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(g), N, D, metric,
-                                                       static_cast<__nv_bfloat16*>(g16), bias);
+    gallery_prepare_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(g), N, D, metric, fmt,
+                                                       static_cast<uint16_t*>(g16), bias);
   else
-    gallery_prepare_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(g), N, D, metric,
-                                                               static_cast<__nv_bfloat16*>(g16), bias);
+    gallery_prepare_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(g), N, D, metric, fmt,
+                                                               static_cast<uint16_t*>(g16), bias);
   B200F_LAUNCH_OK("gallery_prepare_kernel");
   return B200F_OK;
 }
@@ -458,14 +458,14 @@ int gallery_prepare(const void* g, int dtype, int64_t N, int D, int metric, void
 template <int KT>
 static int gallery_scan_kt(const GalleryScanPlan& gp, const CUtensorMap& tx, const CUtensorMap& tw, const float* q,
                            const float* g, const float* bias, const float* q_inv, const float* g_inv, int64_t Q, int64_t N,
-                           int64_t index_offset, int D, int k, int metric, float thresh, int64_t* idx, float* score,
+                           int64_t index_offset, int D, int k, int metric, int fmt, float thresh, int64_t* idx, float* score,
                            uint8_t* accept, uint8_t* redo, int32_t* redo_count, float* ckey, int32_t* cidx, cudaStream_t st) {
   typename XwTopK<KT>::Params ep{};
   ep.bias = (metric == B200F_METRIC_COS) ? nullptr : bias;
   ep.mult = (metric == B200F_METRIC_COS) ? -1.0f : -2.0f;
   ep.cand_key = ckey; ep.cand_idx = cidx; ep.n_lists = gp.n_lists;
-  int rc = (gp.q.pair == 2) ? launch_xw<2, false, XwTopK<KT>>(tx, tw, gp.q, Q, N, D, ep, st, "umma K4 gallery scan (cta pair)", FMT_BF16)
-                            : launch_xw<1, false, XwTopK<KT>>(tx, tw, gp.q, Q, N, D, ep, st, "umma K4 gallery scan", FMT_BF16);
+  int rc = (gp.q.pair == 2) ? launch_xw<2, false, XwTopK<KT>>(tx, tw, gp.q, Q, N, D, ep, st, "umma K4 gallery scan (cta pair)", fmt == B200F_OPERAND_FP16 ? FMT_F16 : FMT_BF16)
+                            : launch_xw<1, false, XwTopK<KT>>(tx, tw, gp.q, Q, N, D, ep, st, "umma K4 gallery scan", fmt == B200F_OPERAND_FP16 ? FMT_F16 : FMT_BF16);
   if (rc) return rc;
   const int n_cand = gp.n_lists * KT;
   const size_t smem = (size_t)n_cand * 8;
@@ -473,7 +473,7 @@ static int gallery_scan_kt(const GalleryScanPlan& gp, const CUtensorMap& tx, con
   B200F_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 160 * 1024 ? 160 * 1024 : (smem < 1024 ? 1024 : smem))));
   if (smem > 160 * 1024) return fail(B200F_ERR_UNSUPPORTED, "gallery scan: candidate lists do not fit shared memory");
   kern<<<(unsigned)Q, 128, smem, st>>>(ckey, cidx, n_cand, q, g, q_inv, g_inv, bias ? bias + N : nullptr, Q, D, k, metric,
-                                       thresh, index_offset, idx, score, accept, redo, redo_count);
+                                       fmt, thresh, index_offset, idx, score, accept, redo, redo_count);
   B200F_LAUNCH_OK("gallery_select_kernel");
   return B200F_OK;
 }
@@ -481,7 +481,7 @@ static int gallery_scan_kt(const GalleryScanPlan& gp, const CUtensorMap& tx, con
 // q, g: fp32 [Q,D], [N,D]; g16 / bias from gallery_prepare (same metric).  Fills idx / score / accept for every
 // query and redo[Q] = 1 where exactness could not be proven (the caller re-runs those on the exact engine).
 int gallery_scan_select(const float* q, const float* g, const void* g16, const float* bias, const float* q_inv,
-                        const float* g_inv, int64_t Q, int64_t N, int64_t index_offset, int D, int k, int metric,
+                        const float* g_inv, int64_t Q, int64_t N, int64_t index_offset, int D, int k, int metric, int fmt,
                         float thresh, int64_t* idx, float* score, uint8_t* accept, uint8_t* redo, int32_t* redo_count,
                         char* ws, size_t ws_bytes, cudaStream_t st) {
   if (!gallery_tc_supported(D)) return fail(B200F_ERR_UNSUPPORTED, "gallery scan: needs sm_100, D %% 8 == 0, D <= 512");
@@ -489,15 +489,15 @@ int gallery_scan_select(const float* q, const float* g, const void* g16, const f
   const GalleryScanPlan gp = gallery_scan_plan(Q, N, D, k);
   if (ws_bytes < gp.total) return fail(B200F_ERR_WORKSPACE, "gallery scan: workspace too small");
   ws = ws_align(ws);
-  __nv_bfloat16* q16 = reinterpret_cast<__nv_bfloat16*>(ws + gp.off_q16);
+  uint16_t* q16 = reinterpret_cast<uint16_t*>(ws + gp.off_q16);
   float* ckey = reinterpret_cast<float*>(ws + gp.off_ckey);
   int32_t* cidx = reinterpret_cast<int32_t*>(ws + gp.off_cidx);
-  gallery_prepare_kernel<float><<<(unsigned)ceil_div(Q, 8), 256, 0, st>>>(q, Q, D, B200F_METRIC_L2EPS, q16, nullptr);
+  gallery_prepare_kernel<float><<<(unsigned)ceil_div(Q, 8), 256, 0, st>>>(q, Q, D, B200F_METRIC_L2EPS, fmt, q16, nullptr);
   B200F_LAUNCH_OK("gallery_prepare_kernel (queries)");
   CUtensorMap tx, tw;
   int rc = tmap_kmajor(&tx, q16, Q, D, D, XW_M); if (rc) return rc;
   rc = tmap_kmajor(&tw, g16, N, D, D, XW_WROWS); if (rc) return rc;
-#define B200F_SCAN(KT) gallery_scan_kt<KT>(gp, tx, tw, q, g, bias, q_inv, g_inv, Q, N, index_offset, D, k, metric, thresh, idx, \
+#define B200F_SCAN(KT) gallery_scan_kt<KT>(gp, tx, tw, q, g, bias, q_inv, g_inv, Q, N, index_offset, D, k, metric, fmt, thresh, idx, \
                                            score, accept, redo, redo_count, ckey, cidx, st)
   if (gp.KT == 8) return B200F_SCAN(8);
   if (gp.KT == 16) return B200F_SCAN(16);

@@ -344,15 +344,23 @@ struct XwDw {
   static __device__ __forceinline__ void item_begin(State& st, const Params&, const XwParams& p, const XwItem& it) {
     st.row_ok = it.row < p.B;
   }
-  // the epilogue reads w_hat[c, d] straight from global memory: pull the NEXT tile's rows into L2 a tile ahead
-  static __device__ __forceinline__ void tile_begin(State& st, const Params& ep, const XwParams& p, const XwItem& it,
+  // The epilogue reads w_hat[c, d] and coef[c] straight from global memory, and at 24 % L2 hit rate the exposed
+  // DRAM latency of those loads (not their count) bounded the kernel: pull the NEXT tile's operands into L2 one
+  // tile (~5 us) ahead.  Each of the 128 threads that share a column half prefetches ONE class row segment --
+  // this CTA's 128 features = 256 contiguous bytes -- with one bulk prefetch.
+  static __device__ __forceinline__ void tile_begin(State&, const Params& ep, const XwParams& p, const XwItem& it,
                                                     int, int next_cls0, int ncols) {
-    if (next_cls0 < 0 || !st.row_ok) return;
-    const int64_t d0 = it.row - it.lane;                      // first feature of this warp's 64 B segment
-    for (int c = next_cls0 + it.lane; c < next_cls0 + ncols && c < p.C; c += 32) {
-      const __half* a = ep.wh + (ep.c0 + c) * ep.ld + d0;
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
-    }
+    if (next_cls0 < 0) return;
+    const int c = next_cls0 + it.quad * 32 + it.lane;
+    if (it.quad * 32 + it.lane >= ncols || c >= p.C) return;
+    const int64_t d_base = it.row - (it.quad * 32 + it.lane);         // first feature of this CTA
+    int nbytes = (int)min((int64_t)XW_M, (int64_t)p.B - d_base) * 2;
+    nbytes &= ~15;
+    const __half* a = ep.wh + (ep.c0 + c) * ep.ld + d_base;
+    if (nbytes >= 16 && (reinterpret_cast<uintptr_t>(a) & 15) == 0)
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(nbytes) : "memory");
+    if ((c & 15) == 0)                                                // 16 coefficients = one 128 B line
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.coef + ep.c0 + c));
   }
   static __device__ __forceinline__ void slice(State& st, const Params& ep, const XwParams& p, const XwItem& it,
                                                float (&v)[32], int cls0) {

@@ -14,6 +14,7 @@
 //            by the exact fp32 CUDA-core engine in the same stream (no host round trip).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "umma_xw.cuh"
 
@@ -22,7 +23,10 @@ namespace umma {
 
 constexpr float GALLERY_EPS = 1e-6f;            // F.pairwise_distance default eps, added to the difference
 // |<q,g> - <bf16(q), bf16(g)>| <= (2u + u^2) |q||g| with u = 2^-9 (round to nearest), plus fp32 accumulation
-constexpr float GALLERY_DOT_ERR = 3.95e-3f;
+constexpr float GALLERY_DOT_ERR = 3.97e-3f;          // includes the 2^-18 relative index packing of the keys
+// fp16 operands: u = 2^-12 in the normal range, absolute 2^-25 per element below 2^-14
+constexpr float GALLERY_DOT_ERR_FP16 = 4.96e-4f;
+constexpr float GALLERY_ABS_ERR_FP16 = 3.0e-8f;      // per element; enters as abs * sqrt(D) * (|q| + |g|max)
 
 template <int KT>
 struct XwTopK {
@@ -33,12 +37,13 @@ struct XwTopK {
     int32_t* cand_idx;          // [Q, n_lists, KT]   gallery row (shard-local), -1 = empty
     int n_lists;                // n_chunks * 2
   };
-  struct State { float key[KT]; int32_t idx[KT]; bool row_ok; };
+  struct State { float key[KT]; int32_t idx[KT]; bool row_ok, bad; };
 
   static __device__ __forceinline__ void item_begin(State& st, const Params&, const XwParams& p, const XwItem& it) {
 #pragma unroll
     for (int s = 0; s < KT; ++s) { st.key[s] = INFINITY; st.idx[s] = -1; }
     st.row_ok = it.row < p.B;
+    st.bad = false;
   }
   static __device__ __forceinline__ void tile_begin(State&, const Params&, const XwParams&, const XwItem&, int, int, int) {}
 
@@ -53,38 +58,57 @@ struct XwTopK {
     }
   }
 
+  // The slice position j is packed into the 5 low mantissa bits of the key (2^-18 relative: far inside the bf16
+  // error budget of the proof, and it makes every key of a slice distinct), so a min tree yields value AND index.
+  // Qualifying elements are then extracted one per trip of a warp-uniform loop -- smallest first -- instead of
+  // running the 15-step insertion at each of the 32 positions whenever ANY lane of the warp needs it there
+  // (which made the first version 5x slower than the scan's HBM time).
   static __device__ __forceinline__ void slice(State& st, const Params& ep, const XwParams& p, const XwItem&,
                                                float (&v)[32], int cls0) {
     const int cc = min(32, p.C - cls0);
+    constexpr float PAD = 3.0e38f;                            // beyond the gallery: finite, never selected
     float a[32];
     if (ep.bias != nullptr) {
-      if (cc == 32) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) a[j] = fmaf(v[j], ep.mult, __ldg(ep.bias + cls0 + j));
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) a[j] = (j < cc) ? fmaf(v[j], ep.mult, __ldg(ep.bias + cls0 + j)) : INFINITY;
-      }
+      for (int j = 0; j < 32; ++j) a[j] = (j < cc) ? fmaf(v[j], ep.mult, __ldg(ep.bias + cls0 + j)) : PAD;
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) a[j] = (j < cc) ? v[j] * ep.mult : INFINITY;
+      for (int j = 0; j < 32; ++j) a[j] = (j < cc) ? v[j] * ep.mult : PAD;
     }
-    float m4[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+    // NaN-propagating min: a key that is NaN or +inf (its packed pattern is a NaN) cannot be ranked -- operand
+    // overflow, NaN inputs -- so the whole query is marked and goes to the exact engine.
+    float m4[4] = {PAD, PAD, PAD, PAD};
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) m4[u] = fminf(m4[u], a[j + u]);
+      for (int u = 0; u < 4; ++u) {
+        a[j + u] = __uint_as_float((__float_as_uint(a[j + u]) & ~31u) | (uint32_t)(j + u));
+        asm("min.NaN.f32 %0, %0, %1;" : "+f"(m4[u]) : "f"(a[j + u]));
+      }
     }
-    const float smin = fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3]));
-    if (smin < st.key[KT - 1]) {                              // rare once the list has warmed up
+    float smin;
+    asm("min.NaN.f32 %0, %1, %2;" : "=f"(smin) : "f"(m4[0]), "f"(m4[1]));
+    asm("min.NaN.f32 %0, %0, %1;" : "+f"(smin) : "f"(m4[2]));
+    asm("min.NaN.f32 %0, %0, %1;" : "+f"(smin) : "f"(m4[3]));
+    if (smin != smin || smin == -INFINITY) { st.bad = true; smin = PAD; }
+    while (__any_sync(0xffffffffu, smin < st.key[KT - 1])) {
+      const bool mine = smin < st.key[KT - 1];
+      const float taken = smin;
+      if (mine) insert(st, smin, cls0 + (int)(__float_as_uint(smin) & 31u));
+      // next smallest element after the one just taken (lanes that did not insert are done with this slice)
+      float n4[4] = {PAD, PAD, PAD, PAD};
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (a[j] < st.key[KT - 1]) insert(st, a[j], cls0 + j); // NaN keys never enter (like `dist < min_dist`)
+      for (int j = 0; j < 32; j += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) n4[u] = fminf(n4[u], (a[j + u] > taken) ? a[j + u] : PAD);
+      }
+      smin = mine ? fminf(fminf(n4[0], n4[1]), fminf(n4[2], n4[3])) : PAD;
     }
   }
 
   static __device__ __forceinline__ void item_end(State& st, const Params& ep, const XwParams&, const XwItem& it, float*) {
     if (!st.row_ok) return;
+    if (st.bad) { st.key[KT - 1] = INFINITY; st.idx[KT - 1] = -2; }      // marker: this list dropped unrankable keys
     const int64_t base = ((int64_t)it.row * ep.n_lists + it.chunk * 2 + it.half) * KT;
 #pragma unroll
     for (int s = 0; s < KT; s += 4) {
@@ -95,11 +119,13 @@ struct XwTopK {
 };
 
 // ---- prepare: rows -> bf16 scan operand (+ bias, + max row norm) ---------------------------------------
-// One warp per row (D <= 512, D % 8 == 0).  metric COS: out = g / max(|g|, 1e-12); L2EPS: out = g.
+// One warp per row (D <= 512, D % 8 == 0).  metric COS: out = g / max(|g|, 1e-12); L2EPS: out = g; stored as bf16
+// (any range) or fp16 (8x tighter error bound; |values| must stay well inside +-65504 -- an overflow is safe, it only
+// sends the affected queries to the exact engine).
 // bias[r] = |g|^2 - 2 eps sum(g) (L2EPS) / 0 (COS); bias[rows] (one extra slot) = max row norm via atomicMax.
 template <typename TI>
 __global__ void __launch_bounds__(256)
-gallery_prepare_kernel(const TI* __restrict__ in, int64_t rows, int dim, int metric, __nv_bfloat16* __restrict__ out,
+gallery_prepare_kernel(const TI* __restrict__ in, int64_t rows, int dim, int metric, int fmt, uint16_t* __restrict__ out,
                        float* __restrict__ bias) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -119,7 +145,8 @@ gallery_prepare_kernel(const TI* __restrict__ in, int64_t rows, int dim, int met
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       const int d = lane + 32 * i;
-      if (d < dim) out[row * dim + d] = __float2bfloat16_rn(v[i] * sc);
+      if (d < dim) out[row * dim + d] = (fmt == B200F_OPERAND_FP16) ? __half_as_ushort(__float2half_rn(v[i] * sc))
+                                                                    : __bfloat16_as_ushort(__float2bfloat16_rn(v[i] * sc));
     }
   }
   if (bias != nullptr && lane == 0) {
@@ -137,7 +164,7 @@ __global__ void __launch_bounds__(128)
 gallery_select_kernel(const float* __restrict__ cand_key, const int32_t* __restrict__ cand_idx, int n_cand,
                       const float* __restrict__ q, const TG* __restrict__ g, const float* __restrict__ q_inv,
                       const float* __restrict__ g_inv, const float* __restrict__ gmax_ptr, int64_t Q, int D, int k,
-                      int metric, float thresh, int64_t index_offset, int64_t* __restrict__ idx_out,
+                      int metric, int fmt, float thresh, int64_t index_offset, int64_t* __restrict__ idx_out,
                       float* __restrict__ score_out, uint8_t* __restrict__ accept, uint8_t* __restrict__ redo,
                       int32_t* __restrict__ redo_count) {
   extern __shared__ uint8_t sel_smem[];
@@ -149,7 +176,14 @@ gallery_select_kernel(const float* __restrict__ cand_key, const int32_t* __restr
   const int64_t qi = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const bool cosine = (metric == B200F_METRIC_COS);
-  for (int i = tid; i < n_cand; i += 128) { ckey[i] = cand_key[qi * n_cand + i]; cidx[i] = cand_idx[qi * n_cand + i]; }
+  bool marked = false;
+  for (int i = tid; i < n_cand; i += 128) {
+    ckey[i] = cand_key[qi * n_cand + i];
+    int32_t id = cand_idx[qi * n_cand + i];
+    if (id == -2) { marked = true; id = -1; }                  // a scan list dropped NaN / inf keys: no proof possible
+    cidx[i] = id;
+  }
+  const bool any_marked = __syncthreads_or(marked);
   // per-query constants: |q|^2, sum q
   float nq = 0.f, sq = 0.f;
   for (int d = tid; d < D; d += 128) { const float x = q[qi * D + d]; nq = fmaf(x, x, nq); sq += x; }
@@ -224,22 +258,24 @@ gallery_select_kernel(const float* __restrict__ cand_key, const int32_t* __restr
     // worst kept approximate key = lower bound of every excluded row's approximate key
     float a_excl = -INFINITY; int n_valid = 0;
     for (int r = 0; r < KT; ++r) if (win_idx[r] >= 0) { a_excl = fmaxf(a_excl, win_key[r]); ++n_valid; }
-    bool verified = true;
-    if (n_valid == KT && n_cand > 0) {                         // something may have been excluded
+    bool verified = !any_marked;
+    if (verified && n_valid == KT && n_cand > 0) {                         // something may have been excluded
       const int kk = min(k, n_valid);
       const float ek = ex_key[kk - 1];                         // exact k-th best ordering key
       const float qn = sqrtf(qstat[0]);
       const float gmax = gmax_ptr ? __int_as_float(*reinterpret_cast<const int*>(gmax_ptr)) : 1.0f;
       float exact_in_approx_units, delta;
+      const float rel = (fmt == B200F_OPERAND_FP16) ? GALLERY_DOT_ERR_FP16 : GALLERY_DOT_ERR;
+      const float abs_e = (fmt == B200F_OPERAND_FP16) ? GALLERY_ABS_ERR_FP16 * sqrtf((float)D) : 0.f;
       if (cosine) {
         // approx a = -<q, g_hat>; exact ordering key e = -cos * ... = -(<q,g> g_inv) q_inv  ->  -<q,g_hat> = e / q_inv
         const float qv = q_inv ? q_inv[qi] : 1.0f;
         exact_in_approx_units = (qv > 0.f) ? ek / qv : -INFINITY;
-        delta = GALLERY_DOT_ERR * qn * 1.01f;
+        delta = rel * qn * 1.01f + abs_e * (qn + 1.0f);
       } else {
         // approx a = d^2 - (|q|^2 + 2 eps sum q + D eps^2)
         exact_in_approx_units = ek * ek - (qstat[0] + 2.0f * GALLERY_EPS * qstat[1] + (float)D * GALLERY_EPS * GALLERY_EPS);
-        delta = 2.0f * GALLERY_DOT_ERR * qn * gmax + 1e-6f * (qstat[0] + gmax * gmax + 1.0f);
+        delta = 2.0f * (rel * qn * gmax + abs_e * (qn + gmax)) + 1e-6f * (qstat[0] + gmax * gmax + 1.0f);
       }
       verified = (ek == ek) && (exact_in_approx_units < a_excl - delta);
     }

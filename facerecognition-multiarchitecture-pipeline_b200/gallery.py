@@ -44,16 +44,24 @@ class PreparedGallery:
     (L2-normalised for 'cos') and the per-row bias.  Build it once per gallery version; every query batch then
     streams 2 bytes per gallery element instead of 4."""
 
-    def __init__(self, g: torch.Tensor, metric: str):
+    def __init__(self, g: torch.Tensor, metric: str, operand_fmt: Optional[int] = None):
+        """operand_fmt: _lib.OPERAND_FP16 (8x tighter proof margin, values must stay far inside +-65504) or
+        OPERAND_BF16 (any range).  None: fp16 when max|g| <= 1024 -- embeddings and class centres -- else bf16
+        (one host read of the maximum, at build time only)."""
         require_cuda(g)
         lib = _lib.load_library()
         self.metric = metric
         self.N, self.D = g.shape
         self.key = (g.data_ptr(), g._version, tuple(g.shape), metric)
-        self.g16 = torch.empty(self.N, self.D, dtype=torch.bfloat16, device=g.device)
+        if operand_fmt is None:
+            small = metric == "cos" or (self.N > 0 and float(g.abs().max()) <= 1024.0)
+            operand_fmt = _lib.OPERAND_FP16 if small else _lib.OPERAND_BF16
+        self.operand_fmt = operand_fmt
+        self.g16 = torch.empty(self.N, self.D, dtype=torch.float16 if operand_fmt == _lib.OPERAND_FP16 else torch.bfloat16,
+                               device=g.device)
         self.bias = torch.empty(self.N + 1, dtype=torch.float32, device=g.device)
-        check(lib.b200f_gallery_prepare(ptr(g), dtype_code(g), self.N, self.D, _METRICS[metric], ptr(self.g16),
-                                        ptr(self.bias), stream_ptr(g.device)), "b200f_gallery_prepare")
+        check(lib.b200f_gallery_prepare(ptr(g), dtype_code(g), self.N, self.D, _METRICS[metric], operand_fmt,
+                                        ptr(self.g16), ptr(self.bias), stream_ptr(g.device)), "b200f_gallery_prepare")
 
     def matches(self, g: torch.Tensor, metric: str) -> bool:
         return self.key == (g.data_ptr(), g._version, tuple(g.shape), metric)
@@ -112,7 +120,8 @@ def gallery_topk(q: torch.Tensor, g: torch.Tensor, k: int = 1, thresh: float = 1
         nbytes = lib.b200f_gallery_tc_workspace_bytes(Q, N, D, k)
         ws = _lib.workspace(nbytes, dev, "gallery_tc")
         check(lib.b200f_gallery_topk_tc(ptr(q), ptr(g), ptr(prepared.g16), ptr(prepared.bias), ptr(q_inv), ptr(gi), Q, N,
-                                        int(index_offset), D, k, _METRICS[metric], float(thresh), ptr(idx), ptr(score),
+                                        int(index_offset), D, k, _METRICS[metric], prepared.operand_fmt, float(thresh),
+                                        ptr(idx), ptr(score),
                                         ptr(accept), ptr(redo_count), ptr(ws), ws.numel(), stream_ptr(dev)),
               "b200f_gallery_topk_tc")
         return idx, score, accept.bool()

@@ -166,7 +166,7 @@ int b200f_gallery_topk(const void* q, const void* g, int dtype,
                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* K4 on the tensor cores (fp32 queries / gallery, D % 8 == 0, D <= 512, sm_100):
- *   b200f_gallery_prepare   builds the scan operand of a gallery ONCE: g16 [N,D] bf16 (the rows for L2EPS, the
+ *   b200f_gallery_prepare   builds the scan operand of a gallery ONCE: g16 [N,D] bf16 or fp16 (the rows for L2EPS, the
  *                           L2-normalised rows for COS) and bias [N+1] fp32 (|g|^2 - 2e-6 sum g per row for L2EPS, 0 for
  *                           COS; the extra slot holds the largest row norm, used by the error bound).
  *   b200f_gallery_topk_tc   bf16 tcgen05 scan of g16 (queries resident in shared memory, gallery streamed once: HBM-bound
@@ -176,12 +176,15 @@ int b200f_gallery_topk(const void* q, const void* g, int dtype,
  *                           proof are recomputed by the exact CUDA-core engine in the same stream; redo_count (optional
  *                           device int, caller zeroes it) counts them.  Results are those of b200f_gallery_topk. */
 int    b200f_gallery_has_tc(int D);
-int    b200f_gallery_prepare(const void* g, int dtype, int64_t N, int D, int metric, void* g16, float* bias, void* stream);
+#define B200F_OPERAND_BF16 0   /* any value range; proof margin 2 * 3.97e-3 |q||g|                              */
+#define B200F_OPERAND_FP16 1   /* 8x tighter proof margin; for embeddings / class centres with |values| << 65504 */
+int    b200f_gallery_prepare(const void* g, int dtype, int64_t N, int D, int metric, int operand_fmt, void* g16, float* bias,
+                             void* stream);
 size_t b200f_gallery_tc_workspace_bytes(int64_t Q, int64_t N_local, int D, int k);
 int    b200f_gallery_topk_tc(const void* q, const void* g, const void* g16, const float* bias,
                              const float* q_inv, const float* g_inv,
                              int64_t Q, int64_t N_local, int64_t index_offset, int D,
-                             int k, int metric, float thresh,
+                             int k, int metric, int operand_fmt, float thresh,
                              int64_t* idx, float* score, uint8_t* accept, int32_t* redo_count,
                              void* workspace, size_t workspace_bytes, void* stream);
 
