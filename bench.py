@@ -239,8 +239,7 @@ def run_b200(args):
     kern = time_stages(H, _lib, x, w, y, m_eff, s_eff, c_lo, C_total, eng, dev, reps=max(5, min(args.steps, 20)))
 
     if rank != 0:
-        if world > 1:
-            torch.distributed.destroy_process_group()
+        finish(world)
         return
     pk = peaks()
     value = B * args.steps / (ms_total * 1e-3)
@@ -284,8 +283,16 @@ def run_b200(args):
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_head_baseline(CFG3)
     print(json.dumps(out), flush=True)
+    finish(world)
+
+
+def finish(world):
+    """Leave without tearing NCCL down: destroying the process group while captured CUDA graphs still hold NCCL
+    kernels can block forever (seen on 2 GPUs).  Everything is already printed and flushed."""
     if world > 1:
-        torch.distributed.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 def time_stages(H, _lib, x, w, y, m_eff, s_eff, c_lo, C_total, eng, dev, reps=10):

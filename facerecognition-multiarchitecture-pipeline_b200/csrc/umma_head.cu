@@ -253,7 +253,8 @@ struct Plan {
   int64_t Cc, ldg; int n_chunks, dx_splits;
   size_t off_G, off_dxpart, off_rpart, off_coef;
   int n_rb;                 // 32-row blocks of the batch that K3a emits r partials for
-  bool fused_dw;            // B <= 512: dW GEMM on the MN-major X-stationary kernel with the normalise-backward fused
+  bool fused_dw;            // B <= 512: dW GEMM on the MN-major X-stationary kernel (x_hat^T resident); above that
+                            // on the generic core, transposed the same way; the normalise-backward is fused in both
   size_t total;
 };
 
@@ -288,10 +289,10 @@ static Plan make_plan(int64_t B, int64_t C, int D) {
   off = 0;
   pl.off_G = off;      off += align_up(2 * (size_t)B * pl.ldg, 1024);
   pl.off_dxpart = off; off += align_up(sizeof(float) * (size_t)splits * B * D, 256);
-  pl.fused_dw = (B <= (int64_t)XW_MAX_KB * XW_K);
+  pl.fused_dw = (B <= (int64_t)XW_MAX_KB * XW_K);         // x_hat^T resident (else: both operands streamed)
   pl.n_rb = (int)ceil_div(B, 2 * XW_M) * 2 * 4;          // covers either pairing
-  pl.off_rpart = off; off += pl.fused_dw ? align_up(sizeof(float) * (size_t)pl.n_rb * pl.Cc, 256) : 0;
-  pl.off_coef = off;  off += pl.fused_dw ? align_up(sizeof(float2) * (size_t)C, 256) : 0;
+  pl.off_rpart = off; off += align_up(sizeof(float) * (size_t)pl.n_rb * pl.Cc, 256);
+  pl.off_coef = off;  off += align_up(sizeof(float2) * (size_t)C, 256);
   pl.total = (off > fwd_total ? off : fwd_total) + 1024;
   return pl;
 }
@@ -373,7 +374,7 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
     CUtensorMap tw_k;
     rc = tmap_kmajor(&tw_k, wc, cnt, D, D, XW_WROWS); if (rc) return rc;
     const XwPlan qg = xw_plan(B, cnt, pl.fwd.pair);
-    float* r_part = pl.fused_dw ? reinterpret_cast<float*>(ws + pl.off_rpart) : nullptr;
+    float* r_part = reinterpret_cast<float*>(ws + pl.off_rpart);
     XwBwdG::Params eg{label, lse, grad4, class_offset + c0, HeadMath{cfg->m_eff, cfg->s_eff, cfg->easy_margin},
                       cfg->label_smoothing, 1.0f / (float)cfg->num_classes_total, 1.0f / (S * S), G, pl.ldg,
                       r_part, pl.Cc, qg.pair};
@@ -382,22 +383,22 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
     if (rc) return rc;
     CUtensorMap tg_mn;
     rc = tmap_mnmajor(&tg_mn, G, cnt, B, pl.ldg); if (rc) return rc;
-    if (pl.fused_dw) {
-      // --- K3b: dW[c0 + c, d] = inv_nw_c (sum_b G[b, c] x_hat[b, d] - w_hat[c, d] r_c), x_hat^T resident, G streamed
-      float2* coef = reinterpret_cast<float2*>(ws + pl.off_coef);
-      reduce_r_kernel<<<(unsigned)ceil_div(cnt, 256), 256, 0, st>>>(r_part, qg.m_groups * qg.pair * 4, pl.Cc, cnt,
-                                                                  inv_nw + c0, grad4, S, coef + c0);
-      B200F_LAUNCH_OK("umma reduce_r_kernel");
+    // --- K3b: dW[c0 + c, d] = inv_nw_c (sum_b G[b, c] x_hat[b, d] - w_hat[c, d] r_c), computed transposed (the thread
+    //     owns a feature d, so a warp writes 128 contiguous bytes of a dW row) with the normalise-backward fused
+    float2* coef = reinterpret_cast<float2*>(ws + pl.off_coef);
+    reduce_r_kernel<<<(unsigned)ceil_div(cnt, 256), 256, 0, st>>>(r_part, qg.m_groups * qg.pair * 4, pl.Cc, cnt,
+                                                                inv_nw + c0, grad4, S, coef + c0);
+    B200F_LAUNCH_OK("umma reduce_r_kernel");
+    if (pl.fused_dw) {                                      // x_hat^T resident, G columns streamed
       const XwPlan qw = xw_plan(D, cnt, qg.pair);
       XwDw::Params ew{coef, static_cast<const __half*>(wh), dw, c0, D};
       rc = (qw.pair == 2) ? launch_xw<2, true, XwDw>(tx_mn, tg_mn, qw, D, cnt, (int)B, ew, st, "umma K3b dW (cta pair)")
                           : launch_xw<1, true, XwDw>(tx_mn, tg_mn, qw, D, cnt, (int)B, ew, st, "umma K3b dW");
       if (rc) return rc;
-    } else {
-      // --- K3b (batch > 512): dW_hat[c0 + m, :] = sum_b G[b, m] x_hat[b, :] on the generic core
-      GemmParams pw = gemm_params((int)cnt, D, (int)B, 1, true, true, FMT_F16, FMT_F16);
-      EpiStore::Params ew{dw, (int64_t)D, 0, c0, 1.0f / S, grad4 + 3};
-      rc = launch_gemm<true, true, EpiStore>(tg_mn, tx_mn, pw, ew, st, "umma K3b dW");
+    } else {                                                // batch > 512: both operands streamed (generic core)
+      GemmParams pw = gemm_params(D, (int)cnt, (int)B, 1, true, true, FMT_F16, FMT_F16);
+      EpiDwT::Params ew{coef, static_cast<const __half*>(wh), dw, c0, D};
+      rc = launch_gemm<true, true, EpiDwT>(tx_mn, tg_mn, pw, ew, st, "umma K3b dW (streamed)");
       if (rc) return rc;
     }
     // --- K3c: dx_hat partials = G[:, k-range] w_hat[c0 + k-range, :]
@@ -412,11 +413,6 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
     reduce_splits_kernel<<<(unsigned)ceil_div(n / 4, 256), 256, 0, st>>>(dxpart, px.k_splits, n, dxhat, chunk_no > 0,
                                                                         1.0f / S, grad4 + 3);
     B200F_LAUNCH_OK("umma reduce_splits_kernel");
-  }
-  if (!pl.fused_dw) {
-    // normalise-backward of the weight rows, in place: dw <- inv_nw * (dw_hat - w_hat <w_hat, dw_hat>)
-    rowops::launch_l2norm_bwd<__half, true>(static_cast<const __half*>(wh), S, inv_nw, dw, C, D, dw, st);
-    B200F_LAUNCH_OK("l2norm_bwd kernel (weights)");
   }
   return B200F_OK;
 }

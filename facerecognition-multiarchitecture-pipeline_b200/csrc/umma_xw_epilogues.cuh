@@ -389,5 +389,37 @@ struct XwDw {
   static __device__ __forceinline__ void item_end(State&, const Params&, const XwParams&, const XwItem&, float*) {}
 };
 
+// -------------------------------------------------------------------------------------------------
+// The same fused dW epilogue for the generic GEMM core (batches above 512 rows, where x_hat^T cannot stay resident):
+// D[m = d, n = class] with both operands MN-major, finished as in XwDw.
+struct EpiDwT {
+  struct Params { const float2* coef; const __half* wh; float* dw; int64_t c0; int ld; };
+  static __device__ __forceinline__ void run(const Params& ep, const GemmParams& p, const TileCoord& t,
+                                             uint32_t tmem_acc, int quad, int lane, int epi_tid, float* scratch) {
+    const int row = t.m0 + quad * 32 + lane;                  // feature d
+    const int ncols = min(BLOCK_N, p.N - t.n0);
+    for (int ch = 0; ch * 32 < ncols; ++ch) {
+      float v[32];
+      tmem_ld32(tmem_acc + ((uint32_t)(quad * 32) << 16) + ch * 32, v);
+      tmem_ld_wait();
+      if (row < p.M) {
+        const int cls0 = t.n0 + ch * 32;
+        const int cc = min(32, p.N - cls0);
+        const int64_t base = (ep.c0 + cls0) * ep.ld + row;
+        const float2* cf = ep.coef + ep.c0 + cls0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (j < cc) {
+            const float2 c2 = __ldg(cf + j);
+            const float wv = __half2float(__ldg(ep.wh + base + (int64_t)j * ep.ld));
+            ep.dw[base + (int64_t)j * ep.ld] = c2.x * fmaf(-wv, c2.y, v[j]);
+          }
+        }
+      }
+    }
+    (void)epi_tid; (void)scratch;
+  }
+};
+
 }  // namespace umma
 }  // namespace b200f
