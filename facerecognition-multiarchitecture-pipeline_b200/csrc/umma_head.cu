@@ -171,13 +171,22 @@ static std::atomic<int> g_pair{2};                 // 2 = tcgen05 cta_group::2 C
 static std::atomic<int> g_prefetch{0};             // L2 prefetch distance of the xw producer (stages)
 static std::atomic<int> g_chunk_mb{112};           // budget of the fp16 logit-gradient buffer G per class chunk
 
-template <int PAIR, bool MN, class Epi>
+// MODE of the X-stationary kernel: 0 = both operands K-major (K2, gallery scan, probes); 1 = resident operand
+// MN-major, streamed operand K-major (K3b: x_hat^T resident, class-major G rows streamed); 2 = K-major operands with
+// the streamed one on the A side of the MMA (K3a: accumulator lanes = classes).
+enum { XW_KK = 0, XW_MK = 1, XW_SWAP = 2 };
+template <int PAIR, int MODE, class Epi>
+struct XwKernel {
+  static constexpr auto fn = xw_kernel<PAIR, MODE == XW_MK, false, MODE == XW_SWAP, Epi>;
+};
+
+template <int PAIR, int MODE, class Epi>
 static int xw_set_smem() {
   static thread_local int done_dev = -1;
   int dev = 0;
   B200F_CUDA_OK(cudaGetDevice(&dev));
   if (done_dev != dev) {
-    B200F_CUDA_OK(cudaFuncSetAttribute(xw_kernel<PAIR, MN, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XW_SMEM_BYTES));
+    B200F_CUDA_OK(cudaFuncSetAttribute(XwKernel<PAIR, MODE, Epi>::fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XW_SMEM_BYTES));
     done_dev = dev;
   }
   return B200F_OK;
@@ -191,13 +200,13 @@ static int xw_max_clusters(int pair) {
   if (cudaGetDevice(&dev) != cudaSuccess) return num_sms() / 2;
   if (dev != cached_dev) {
     int n = 0;
-    if (xw_set_smem<2, false, XwFwd>() == B200F_OK) {
+    if (xw_set_smem<2, XW_KK, XwFwd>() == B200F_OK) {
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3((unsigned)num_sms() / 2 * 2); cfg.blockDim = dim3(XW_THREADS); cfg.dynamicSmemBytes = XW_SMEM_BYTES;
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
-      if (cudaOccupancyMaxActiveClusters(&n, xw_kernel<2, false, XwFwd>, &cfg) != cudaSuccess) { n = 0; (void)cudaGetLastError(); }
+      if (cudaOccupancyMaxActiveClusters(&n, XwKernel<2, XW_KK, XwFwd>::fn, &cfg) != cudaSuccess) { n = 0; (void)cudaGetLastError(); }
     }
     if (n <= 0 || n > num_sms() / 2) n = num_sms() / 2;
     cached = n; cached_dev = dev;
@@ -225,22 +234,23 @@ static XwPlan xw_plan(int64_t B, int64_t C, int pair) {
   return q;
 }
 
-template <int PAIR, bool MN, class Epi>
+template <int PAIR, int MODE, class Epi>
 static int launch_xw(const CUtensorMap& tx, const CUtensorMap& tw, const XwPlan& q, int64_t B, int64_t C, int D,
                      const typename Epi::Params& ep, cudaStream_t st, const char* what, uint32_t fmt = FMT_F16) {
-  int rc = xw_set_smem<PAIR, MN, Epi>(); if (rc) return rc;
+  int rc = xw_set_smem<PAIR, MODE, Epi>(); if (rc) return rc;
   XwParams p{};
   p.B = (int)B; p.C = (int)C; p.D = D;
   p.kb_count = (int)ceil_div(D, XW_K);
   p.m_groups = q.m_groups; p.n_tiles = q.n_tiles; p.n_chunks = q.n_chunks;
   p.prefetch = g_prefetch.load(std::memory_order_relaxed);
-  p.idesc = make_idesc(fmt, fmt, MN, MN, XW_M * PAIR, XW_WROWS * PAIR);
+  p.tn = XW_WROWS * PAIR;
+  p.idesc = make_idesc(fmt, fmt, MODE == XW_MK, false, XW_M * PAIR, XW_WROWS * PAIR);   // A = resident except XW_SWAP (both K-major)
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)q.grid); cfg.blockDim = dim3(XW_THREADS); cfg.dynamicSmemBytes = XW_SMEM_BYTES; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = PAIR; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, xw_kernel<PAIR, MN, Epi>, tx, tw, p, ep);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, XwKernel<PAIR, MODE, Epi>::fn, tx, tw, p, ep);
   if (e != cudaSuccess) return fail(B200F_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
   B200F_LAUNCH_OK(what);
   return B200F_OK;
@@ -274,12 +284,13 @@ static Plan make_plan(int64_t B, int64_t C, int D) {
   // backward: classes are processed in chunks whose fp16 logit gradient G fits the budget.  G is written once
   // and read twice, all while the tensor pipe (not HBM) is the bound, so it need not stay L2-resident: cfg3's
   // 102 MB is ONE chunk (fewer launches, long per-CTA streams); B = 4096 shards use ~12 k-class chunks.
-  int64_t cc_max = ((int64_t)g_chunk_mb.load(std::memory_order_relaxed) * (1 << 20) / 2 / B) / BLOCK_N * BLOCK_N;
+  const int64_t ldgt = ceil_div(B, 64) * 64;               // G^T[class][batch row], row stride in elements
+  int64_t cc_max = ((int64_t)g_chunk_mb.load(std::memory_order_relaxed) * (1 << 20) / 2 / ldgt) / BLOCK_N * BLOCK_N;
   if (cc_max < BLOCK_N) cc_max = BLOCK_N;
   pl.n_chunks = (int)ceil_div(C, cc_max);
   pl.Cc = ceil_div(ceil_div(C, pl.n_chunks), BLOCK_N) * BLOCK_N;
   pl.n_chunks = (int)ceil_div(C, pl.Cc);
-  pl.ldg = pl.Cc;
+  pl.ldg = ldgt;
   const int out_tiles = m_tiles * (int)ceil_div(D, BLOCK_N);
   int splits = num_sms() / out_tiles;
   if (splits < 1) splits = 1;
@@ -287,7 +298,7 @@ static Plan make_plan(int64_t B, int64_t C, int D) {
   if (splits > kchunks) splits = kchunks;
   pl.dx_splits = splits;
   off = 0;
-  pl.off_G = off;      off += align_up(2 * (size_t)B * pl.ldg, 1024);
+  pl.off_G = off;      off += align_up(2 * (size_t)pl.Cc * pl.ldg, 1024);
   pl.off_dxpart = off; off += align_up(sizeof(float) * (size_t)splits * B * D, 256);
   pl.fused_dw = (B <= (int64_t)XW_MAX_KB * XW_K);         // x_hat^T resident (else: both operands streamed)
   pl.n_rb = (int)ceil_div(B, 2 * XW_M) * 2 * 4;          // covers either pairing
@@ -343,8 +354,8 @@ int head_fwd(const void* xh, const void* wh, const int64_t* label, int64_t B, in
   ep.part = reinterpret_cast<float*>(ws + pl.off_part);
   ep.cos_part = reinterpret_cast<float*>(ws + pl.off_cos);
   ep.nan_flag = nan_flag; ep.pair = q.pair;
-  rc = (q.pair == 2) ? launch_xw<2, false, XwFwd>(tx, tw, q, B, C, D, ep, st, "umma K2 arcface_fwd (cta pair)")
-                     : launch_xw<1, false, XwFwd>(tx, tw, q, B, C, D, ep, st, "umma K2 arcface_fwd");
+  rc = (q.pair == 2) ? launch_xw<2, XW_KK, XwFwd>(tx, tw, q, B, C, D, ep, st, "umma K2 arcface_fwd (cta pair)")
+                     : launch_xw<1, XW_KK, XwFwd>(tx, tw, q, B, C, D, ep, st, "umma K2 arcface_fwd");
   if (rc) return rc;
   reduce_row_partials_kernel<<<(unsigned)ceil_div(B, 8), 256, 0, st>>>(ep.part, q.n_chunks, B, ep.cos_part,
                                                                       q.items * q.pair * XW_EPI_WARPS, row_stats, row_best,
@@ -370,44 +381,47 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
   for (int64_t c0 = 0; c0 < C; c0 += pl.Cc, ++chunk_no) {
     const int64_t cnt = (C - c0 < pl.Cc) ? (C - c0) : pl.Cc;
     const uint16_t* wc = static_cast<const uint16_t*>(wh) + c0 * D;
-    // --- K3a: logit gradient of the chunk (x_hat resident, w_hat rows [c0, c0 + cnt) streamed)
+    // --- K3a: logit gradient of the chunk, class-major: G^T[c, b] (x_hat resident, w_hat rows [c0, c0 + cnt) streamed
+    //     on the A side, so a thread owns a class and r_c = sum_b G cos is a private sum)
     CUtensorMap tw_k;
     rc = tmap_kmajor(&tw_k, wc, cnt, D, D, XW_WROWS); if (rc) return rc;
     const XwPlan qg = xw_plan(B, cnt, pl.fwd.pair);
     float* r_part = reinterpret_cast<float*>(ws + pl.off_rpart);
-    XwBwdG::Params eg{label, lse, grad4, class_offset + c0, HeadMath{cfg->m_eff, cfg->s_eff, cfg->easy_margin},
-                      cfg->label_smoothing, 1.0f / (float)cfg->num_classes_total, 1.0f / (S * S), G, pl.ldg,
-                      r_part, pl.Cc, qg.pair};
-    rc = (qg.pair == 2) ? launch_xw<2, false, XwBwdG>(tx_k, tw_k, qg, B, cnt, D, eg, st, "umma K3a logit-grad (cta pair)")
-                        : launch_xw<1, false, XwBwdG>(tx_k, tw_k, qg, B, cnt, D, eg, st, "umma K3a logit-grad");
+    XwBwdGT::Params eg{label, lse, grad4, class_offset + c0, HeadMath{cfg->m_eff, cfg->s_eff, cfg->easy_margin},
+                       cfg->label_smoothing, 1.0f / (float)cfg->num_classes_total, 1.0f / (S * S), G, pl.ldg,
+                       r_part, pl.Cc};
+    rc = (qg.pair == 2) ? launch_xw<2, XW_SWAP, XwBwdGT>(tx_k, tw_k, qg, B, cnt, D, eg, st, "umma K3a logit-grad (cta pair)")
+                        : launch_xw<1, XW_SWAP, XwBwdGT>(tx_k, tw_k, qg, B, cnt, D, eg, st, "umma K3a logit-grad");
     if (rc) return rc;
-    CUtensorMap tg_mn;
-    rc = tmap_mnmajor(&tg_mn, G, cnt, B, pl.ldg); if (rc) return rc;
-    // --- K3b: dW[c0 + c, d] = inv_nw_c (sum_b G[b, c] x_hat[b, d] - w_hat[c, d] r_c), computed transposed (the thread
+    // --- K3b: dW[c0 + c, d] = inv_nw_c (sum_b G^T[c, b] x_hat[b, d] - w_hat[c, d] r_c), computed transposed (the thread
     //     owns a feature d, so a warp writes 128 contiguous bytes of a dW row) with the normalise-backward fused
     float2* coef = reinterpret_cast<float2*>(ws + pl.off_coef);
-    reduce_r_kernel<<<(unsigned)ceil_div(cnt, 256), 256, 0, st>>>(r_part, qg.m_groups * qg.pair * 4, pl.Cc, cnt,
+    reduce_r_kernel<<<(unsigned)ceil_div(cnt, 256), 256, 0, st>>>(r_part, qg.m_groups * 2, pl.Cc, cnt,
                                                                 inv_nw + c0, grad4, S, coef + c0);
     B200F_LAUNCH_OK("umma reduce_r_kernel");
-    if (pl.fused_dw) {                                      // x_hat^T resident, G columns streamed
+    if (pl.fused_dw) {                                      // x_hat^T resident, G^T rows streamed
+      CUtensorMap tg_k;
+      rc = tmap_kmajor(&tg_k, G, cnt, B, pl.ldg, XW_WROWS); if (rc) return rc;
       const XwPlan qw = xw_plan(D, cnt, qg.pair);
       XwDw::Params ew{coef, static_cast<const __half*>(wh), dw, c0, D};
-      rc = (qw.pair == 2) ? launch_xw<2, true, XwDw>(tx_mn, tg_mn, qw, D, cnt, (int)B, ew, st, "umma K3b dW (cta pair)")
-                          : launch_xw<1, true, XwDw>(tx_mn, tg_mn, qw, D, cnt, (int)B, ew, st, "umma K3b dW");
+      rc = (qw.pair == 2) ? launch_xw<2, XW_MK, XwDw>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW (cta pair)")
+                          : launch_xw<1, XW_MK, XwDw>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW");
       if (rc) return rc;
     } else {                                                // batch > 512: both operands streamed (generic core)
-      GemmParams pw = gemm_params(D, (int)cnt, (int)B, 1, true, true, FMT_F16, FMT_F16);
+      CUtensorMap tg_kb;
+      rc = tmap_kmajor(&tg_kb, G, cnt, B, pl.ldg, BLOCK_N); if (rc) return rc;
+      GemmParams pw = gemm_params(D, (int)cnt, (int)B, 1, true, false, FMT_F16, FMT_F16);
       EpiDwT::Params ew{coef, static_cast<const __half*>(wh), dw, c0, D};
-      rc = launch_gemm<true, true, EpiDwT>(tx_mn, tg_mn, pw, ew, st, "umma K3b dW (streamed)");
+      rc = launch_gemm<true, false, EpiDwT>(tx_mn, tg_kb, pw, ew, st, "umma K3b dW (streamed)");
       if (rc) return rc;
     }
-    // --- K3c: dx_hat partials = G[:, k-range] w_hat[c0 + k-range, :]
-    CUtensorMap tg_k, tw_mn;
-    rc = tmap_kmajor(&tg_k, G, B, cnt, pl.ldg, BLOCK_M); if (rc) return rc;
+    // --- K3c: dx_hat partials = G[:, k-range] w_hat[c0 + k-range, :]   (A = G read MN-major from G^T)
+    CUtensorMap tg_mn, tw_mn;
+    rc = tmap_mnmajor(&tg_mn, G, B, cnt, pl.ldg); if (rc) return rc;
     rc = tmap_mnmajor(&tw_mn, wc, D, cnt, D); if (rc) return rc;
-    GemmParams px = gemm_params((int)B, D, (int)cnt, pl.dx_splits, false, true, FMT_F16, FMT_F16);
+    GemmParams px = gemm_params((int)B, D, (int)cnt, pl.dx_splits, true, true, FMT_F16, FMT_F16);
     EpiStore::Params ex{dxpart, (int64_t)D, B * (int64_t)D, 0, 1.0f, nullptr};
-    rc = launch_gemm<false, true, EpiStore>(tg_k, tw_mn, px, ex, st, "umma K3c dX");
+    rc = launch_gemm<true, true, EpiStore>(tg_mn, tw_mn, px, ex, st, "umma K3c dX");
     if (rc) return rc;
     const int64_t n = B * (int64_t)D;
     reduce_splits_kernel<<<(unsigned)ceil_div(n / 4, 256), 256, 0, st>>>(dxpart, px.k_splits, n, dxhat, chunk_no > 0,
@@ -460,11 +474,11 @@ static int gallery_scan_kt(const GalleryScanPlan& gp, const CUtensorMap& tx, con
   ep.bias = (metric == B200F_METRIC_COS) ? nullptr : bias;
   ep.mult = (metric == B200F_METRIC_COS) ? -1.0f : -2.0f;
   ep.cand_key = ckey; ep.cand_idx = cidx; ep.n_lists = gp.n_lists;
-  int rc = (gp.q.pair == 2) ? launch_xw<2, false, XwTopK<KT>>(tx, tw, gp.q, Q, N, D, ep, st, "umma K4 gallery scan (cta pair)", fmt == B200F_OPERAND_FP16 ? FMT_F16 : FMT_BF16)
-                            : launch_xw<1, false, XwTopK<KT>>(tx, tw, gp.q, Q, N, D, ep, st, "umma K4 gallery scan", fmt == B200F_OPERAND_FP16 ? FMT_F16 : FMT_BF16);
+  int rc = (gp.q.pair == 2) ? launch_xw<2, XW_KK, XwTopK<KT>>(tx, tw, gp.q, Q, N, D, ep, st, "umma K4 gallery scan (cta pair)", fmt == B200F_OPERAND_FP16 ? FMT_F16 : FMT_BF16)
+                            : launch_xw<1, XW_KK, XwTopK<KT>>(tx, tw, gp.q, Q, N, D, ep, st, "umma K4 gallery scan", fmt == B200F_OPERAND_FP16 ? FMT_F16 : FMT_BF16);
   if (rc) return rc;
   const int n_cand = gp.n_lists * KT;
-  const size_t smem = (size_t)n_cand * 8;
+  const size_t smem = (size_t)n_cand * 16;                 // candidates + survivors, (key, idx) each
   auto kern = gallery_select_kernel<float, KT>;
   B200F_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 160 * 1024 ? 160 * 1024 : (smem < 1024 ? 1024 : smem))));
   if (smem > 160 * 1024) return fail(B200F_ERR_UNSUPPORTED, "gallery scan: candidate lists do not fit shared memory");
@@ -535,7 +549,7 @@ int b200f_umma_selftest(const void* a, const void* b, float* out, int M, int N, 
   if (!a_mn && !b_mn) return launch_gemm<false, false, EpiStore>(ta, tb, p, ep, st, "umma selftest KK");
   if (a_mn && b_mn) return launch_gemm<true, true, EpiStore>(ta, tb, p, ep, st, "umma selftest MM");
   if (!a_mn && b_mn) return launch_gemm<false, true, EpiStore>(ta, tb, p, ep, st, "umma selftest KM");
-  return fail(B200F_ERR_UNSUPPORTED, "umma_selftest: A MN-major with B K-major is not instantiated");
+  return launch_gemm<true, false, EpiStore>(ta, tb, p, ep, st, "umma selftest MK");
 }
 
 // Self-test of the X-stationary kernel: out[B,C] (fp32) = x[B,D] . w[C,D]^T with fp16 operands, on single CTAs
@@ -551,8 +565,8 @@ int b200f_umma_xw_selftest(const void* x, const void* w, float* out, int B, int 
   const XwPlan q = xw_plan(B, C, pair);
   XwStore::Params ep{out, (int64_t)C};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return (pair == 2) ? launch_xw<2, false, XwStore>(tx, tw, q, B, C, D, ep, st, "umma xw selftest (cta pair)")
-                     : launch_xw<1, false, XwStore>(tx, tw, q, B, C, D, ep, st, "umma xw selftest");
+  return (pair == 2) ? launch_xw<2, XW_KK, XwStore>(tx, tw, q, B, C, D, ep, st, "umma xw selftest (cta pair)")
+                     : launch_xw<1, XW_KK, XwStore>(tx, tw, q, B, C, D, ep, st, "umma xw selftest");
 }
 
 // Pipeline probe (tools/xw_probe.py): same GEMM, but the epilogue only adds every accumulator of a row into
@@ -568,8 +582,8 @@ int b200f_umma_xw_probe(const void* x, const void* w, float* rowsum, int B, int 
   const XwPlan q = xw_plan(B, C, pair);
   XwNull::Params ep{rowsum};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return (pair == 2) ? launch_xw<2, false, XwNull>(tx, tw, q, B, C, D, ep, st, "umma xw probe (cta pair)")
-                     : launch_xw<1, false, XwNull>(tx, tw, q, B, C, D, ep, st, "umma xw probe");
+  return (pair == 2) ? launch_xw<2, XW_KK, XwNull>(tx, tw, q, B, C, D, ep, st, "umma xw probe (cta pair)")
+                     : launch_xw<1, XW_KK, XwNull>(tx, tw, q, B, C, D, ep, st, "umma xw probe");
 }
 
 // Selects single-CTA (1) or CTA-pair (2, default) execution of K2 / K3a; returns the previous setting.

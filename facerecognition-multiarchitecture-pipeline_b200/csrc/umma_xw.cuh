@@ -146,15 +146,20 @@ __device__ __forceinline__ void epi_bar_sync() {      // the 256 epilogue thread
   asm volatile("bar.sync 1, 256;" ::: "memory");
 }
 
-// MN = false: both operands K-major (x[B, D], w[C, D] row-major: the cosine-logit stages).
-// MN = true : both operands MN-major, i.e. stored [k, rows] row-major: out[m, n] = sum_k x[k, m] * w[k, n].  The dW
-//             stage runs as dW^T[d, c] = sum_b x_hat[b, d] * G[b, c] this way: x_hat^T stays resident, logit-gradient
-//             columns stream, and an epilogue thread owns one feature d, so its 32 lanes write 128 contiguous bytes
-//             of a dW row.  "B" is then the extent of m (D), "C" of n (classes), "D" of k (the batch).
+// X_MN / W_MN: layout of the resident ("x") and the streamed ("w") operand: false = K-major (rows x k, row-major),
+//   true = MN-major (stored [k, rows] row-major).  The dW stage runs as dW^T[d, c] = sum_b x_hat[b, d] * G^T[c, b]:
+//   x_hat (MN-major view of x_hat^T) stays resident, logit-gradient rows stream, and an epilogue thread owns one
+//   feature d, so its 32 lanes write 128 contiguous bytes of a dW row.  "B" is then the extent of m (D), "C" of n
+//   (classes), "D" of k (the batch).
+// SWAP: the streamed operand feeds the A side of the MMA, so accumulator LANES are streamed rows (classes) and COLUMNS
+//   are the resident rows (batch).  K3a runs this way: a thread owns one class, so the column sums over the batch that
+//   the normalise-backward of W needs (r_j = sum_i G_ij cos_ij) are a private running sum instead of a 31-shuffle
+//   butterfly per 32 classes, and G is emitted class-major.
 struct XwParams {
   int B, C, D;                          // extents of m (rows of x), n (classes of this launch) and k
   int kb_count;                         // ceil(D / 64) <= XW_MAX_KB
   int m_groups, n_tiles, n_chunks;      // row groups of 128*PAIR rows, class tiles of 128*PAIR, class chunks
+  int tn;                               // 128 * PAIR: tile width = rows of a resident group
   int prefetch;                         // stages of L2 prefetch issued ahead of the ring (0 = off, the default:
                                         // measured slower -- the ring alone already sustains 91 % of HBM peak)
   uint32_t idesc;
@@ -175,7 +180,7 @@ struct XwItem {                         // what an epilogue thread knows about i
 //     static __device__ void slice(State&, const Params&, const XwParams&, const XwItem&, float (&v)[32], int cls0);
 //         v = accumulators of row it.row for classes [cls0, cls0 + 32) of this launch (warp-uniform cls0 < C)
 //     static __device__ void item_end(State&, const Params&, const XwParams&, const XwItem&, float* scratch); }
-template <int PAIR, bool MN, class Epi>
+template <int PAIR, bool X_MN, bool W_MN, bool SWAP, class Epi>
 __global__ void __launch_bounds__(XW_THREADS, 1)
 xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const XwParams p,
           const typename Epi::Params ep) {
@@ -237,7 +242,7 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
           else mbar_arrive_cluster(x_full, 0);
           for (int kb = 0; kb < p.kb_count; ++kb) {
             uint8_t* dst = xres + (size_t)kb * XW_TILE_BYTES;
-            if (!MN) {
+            if (!X_MN) {
               xw_tma_load<PAIR>(dst, &tm_x, x_full, kb * XW_K, row0);
             } else {                                              // two 64-wide row blocks of 64 k-rows each
               xw_tma_load<PAIR>(dst, &tm_x, x_full, row0, kb * XW_K);
@@ -250,7 +255,7 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
         if (leader) {
           for (int i = 0; i < p.prefetch && pt < t_end; ++i) {
             const int pn0 = pt * TN + rank * XW_WROWS;
-            if (!MN) tma_prefetch_l2_2d(&tm_w, pkb * XW_K, pn0);
+            if (!W_MN) tma_prefetch_l2_2d(&tm_w, pkb * XW_K, pn0);
             else { tma_prefetch_l2_2d(&tm_w, pn0, pkb * XW_K); tma_prefetch_l2_2d(&tm_w, pn0 + 64, pkb * XW_K); }
             if (++pkb == p.kb_count) { pkb = 0; ++pt; }
           }
@@ -263,14 +268,14 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
             if (leader) {
               if (p.prefetch > 0 && pt < t_end) {
                 const int pn0 = pt * TN + rank * XW_WROWS;
-                if (!MN) tma_prefetch_l2_2d(&tm_w, pkb * XW_K, pn0);
+                if (!W_MN) tma_prefetch_l2_2d(&tm_w, pkb * XW_K, pn0);
                 else { tma_prefetch_l2_2d(&tm_w, pn0, pkb * XW_K); tma_prefetch_l2_2d(&tm_w, pn0 + 64, pkb * XW_K); }
                 if (++pkb == p.kb_count) { pkb = 0; ++pt; }
               }
               if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(PAIR * XW_TILE_BYTES));
               else mbar_arrive_cluster(&full_bar[stage], 0);
               uint8_t* dst = ring + (size_t)stage * XW_TILE_BYTES;
-              if (!MN) {
+              if (!W_MN) {
                 xw_tma_load<PAIR>(dst, &tm_w, &full_bar[stage], kb * XW_K, n0);
               } else {
                 xw_tma_load<PAIR>(dst, &tm_w, &full_bar[stage], n0, kb * XW_K);
@@ -296,10 +301,11 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
       int acc = 0; uint32_t acc_phase = 0;
       int item_no = 0;
       bool ok = true;
-      const uint32_t lbo = MN ? (uint32_t)(XW_TILE_BYTES / 2) : 0u;
-      const uint32_t kstep = MN ? 2048u >> 4 : 32u >> 4;         // descriptor address units (16 B)
-      const uint64_t desc_a0 = make_smem_desc(smem_u32(xres), lbo, 1024);
-      const uint64_t desc_b0 = make_smem_desc(smem_u32(ring), lbo, 1024);
+      // K-major: +32 B per 16 k; MN-major: +16 k-rows of 128 B, LBO = next 64-wide row block (8 KB)
+      const uint32_t x_kstep = X_MN ? 2048u >> 4 : 32u >> 4;     // descriptor address units (16 B)
+      const uint32_t w_kstep = W_MN ? 2048u >> 4 : 32u >> 4;
+      const uint64_t desc_x0 = make_smem_desc(smem_u32(xres), X_MN ? (uint32_t)(XW_TILE_BYTES / 2) : 0u, 1024);
+      const uint64_t desc_w0 = make_smem_desc(smem_u32(ring), W_MN ? (uint32_t)(XW_TILE_BYTES / 2) : 0u, 1024);
       for (int item = cluster_id; item < items && ok; item += n_clusters, ++item_no) {
         const int chunk = item / p.m_groups;
         const int t_begin = (int)((int64_t)chunk * p.n_tiles / p.n_chunks);
@@ -317,12 +323,16 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
             if (!ok) break;
             tc_fence_after_sync();
             if (leader) {
-              const uint64_t da = desc_a0 + (uint64_t)((uint32_t)kb * (XW_TILE_BYTES >> 4));
-              const uint64_t db = desc_b0 + (uint64_t)((uint32_t)stage * (XW_TILE_BYTES >> 4));
+              const uint64_t dx = desc_x0 + (uint64_t)((uint32_t)kb * (XW_TILE_BYTES >> 4));
+              const uint64_t dw = desc_w0 + (uint64_t)((uint32_t)stage * (XW_TILE_BYTES >> 4));
 #pragma unroll
-              for (int kk = 0; kk < XW_K / 16; ++kk)
-                xw_mma<PAIR>(d_tmem, da + (uint64_t)(kk * kstep), db + (uint64_t)(kk * kstep), p.idesc,
-                             (uint32_t)((kb | kk) != 0));
+              for (int kk = 0; kk < XW_K / 16; ++kk) {
+                // SWAP: the streamed operand is A (accumulator lanes = streamed rows), the resident one is B
+                if (!SWAP) xw_mma<PAIR>(d_tmem, dx + (uint64_t)(kk * x_kstep), dw + (uint64_t)(kk * w_kstep), p.idesc,
+                                        (uint32_t)((kb | kk) != 0));
+                else xw_mma<PAIR>(d_tmem, dw + (uint64_t)(kk * w_kstep), dx + (uint64_t)(kk * x_kstep), p.idesc,
+                                  (uint32_t)((kb | kk) != 0));
+              }
               xw_commit<PAIR>(&empty_bar[stage]);
             }
             __syncwarp();
@@ -344,6 +354,47 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
     int acc = 0; uint32_t acc_phase = 0;
     bool ok = true;
     constexpr int SLICES = TN / 64;                            // 32-column slices per warp per tile
+    if constexpr (SWAP) {
+      // Accumulator lanes = streamed rows (classes), columns = the resident operand's rows (the batch rows of the
+      // group): the thread owns ONE class per tile and sees half of the group's batch rows.
+      for (int item = cluster_id; item < items && ok; item += n_clusters) {
+        it.item = item; it.group = item % p.m_groups; it.chunk = item / p.m_groups;
+        const int t_begin = (int)((int64_t)it.chunk * p.n_tiles / p.n_chunks);
+        const int t_end = (int)((int64_t)(it.chunk + 1) * p.n_tiles / p.n_chunks);
+        typename Epi::State stt;
+        Epi::item_begin(stt, ep, p, it, scratch, TN);          // per-column tables of the group -> shared memory
+        const int col_base = it.half * (TN / 2);
+        for (int t = t_begin; t < t_end; ++t) {
+          ok = mbar_wait(&acc_full[acc], acc_phase);
+          ok = __all_sync(0xffffffffu, ok);
+          if (!ok) break;
+          tc_fence_after_sync();
+          it.row = (int64_t)t * TN + rank * XW_WROWS + it.quad * 32 + lane;   // the class this thread owns in tile t
+          const uint32_t taddr = tmem_base + (uint32_t)acc * XW_ACC_STRIDE + ((uint32_t)(it.quad * 32) << 16) + (uint32_t)col_base;
+          Epi::tile_begin(stt, ep, p, it);
+          float va[32], vb[32];
+          tmem_ld32_async(taddr, va);
+#pragma unroll 1
+          for (int s = 0; s < SLICES; s += 2) {
+            tmem_ld_wait_dep(va);
+            tmem_ld32_async(taddr + (uint32_t)(s + 1) * 32, vb);
+            Epi::slice(stt, ep, p, it, va, col_base + s * 32, scratch);
+            tmem_ld_wait_dep(vb);
+            if (s + 2 < SLICES) tmem_ld32_async(taddr + (uint32_t)(s + 2) * 32, va);
+            Epi::slice(stt, ep, p, it, vb, col_base + (s + 1) * 32, scratch);
+          }
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) {
+            if (PAIR == 2) mbar_arrive_cluster(&acc_empty[acc], 0);
+            else mbar_arrive(&acc_empty[acc]);
+          }
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          Epi::tile_end(stt, ep, p, it);
+        }
+        if (!ok) break;
+      }
+    } else
     for (int item = cluster_id; item < items && ok; item += n_clusters) {
       it.item = item; it.group = item % p.m_groups; it.chunk = item / p.m_groups;
       it.row = (int64_t)(it.group * PAIR + rank) * XW_M + it.quad * 32 + lane;

@@ -333,6 +333,142 @@ struct XwBwdG {
 };
 
 // -------------------------------------------------------------------------------------------------
+// K3a, class-major (xw_kernel SWAP mode): the thread owns ONE class of the tile, the 32 columns of a slice are batch
+// rows of the resident group.  Per-column quantities (-lse_b log2 e, the row's target class) sit in shared memory
+// (item_begin); r_j = sum_i G_ij cos_ij is a private running sum; G leaves class-major, G^T[class][batch row], 64
+// contiguous bytes per thread and slice.  Same fast / careful split as XwBwdG; phi / dphi are ONE out-of-line copy.
+__device__ __noinline__ void head_phi_dphi(HeadMath hm, float c, float* phi, float* dphi) {
+  *phi = hm.phi(c);
+  *dphi = hm.dphi(c);
+}
+
+struct XwBwdGT {
+  struct Params {
+    const int64_t* label; const float* lse; const float* grad4;
+    int64_t class_offset;       // global id of this launch's class 0
+    HeadMath hm;
+    float ls_eps, inv_Ctot, inv_scale;
+    uint16_t* GT; int64_t ldgt; // G^T[class of this launch, batch row]
+    float* r_part; int64_t ldr; // [2 * m_groups, ldr]: one partial per (row group, column half)
+  };
+  struct State { float gs, r; int cls; bool row_ok; };
+
+  static __device__ __forceinline__ void item_begin(State& st, const Params& ep, const XwParams& p, const XwItem& it,
+                                                    float* scratch, int TN) {
+    epi_bar_sync();                                           // the previous item's readers are done
+    const int e = it.ew * 32 + it.lane;
+    if (e < TN) {
+      const int64_t b = (int64_t)it.group * TN + e;
+      float bneg = -INFINITY; int lab = -1;                    // beyond the batch: p = 0, no target
+      if (b < p.B) {
+        bneg = -__ldg(ep.lse + b) * LOG2E;
+        const int64_t tg = __ldg(ep.label + b) - ep.class_offset;
+        if (tg >= 0 && tg < p.C) lab = (int)tg;
+      }
+      scratch[e] = bneg;
+      reinterpret_cast<int*>(scratch)[TN + e] = lab;
+    }
+    epi_bar_sync();
+    st.gs = __ldg(ep.grad4) * __ldg(ep.grad4 + 3);
+    st.r = 0.f; st.cls = 0; st.row_ok = false;
+  }
+  static __device__ __forceinline__ void tile_begin(State& st, const Params&, const XwParams& p, const XwItem& it) {
+    st.cls = (int)it.row; st.row_ok = it.row < p.C; st.r = 0.f;
+  }
+
+  static __device__ __forceinline__ void slice(State& st, const Params& ep, const XwParams& p, const XwItem& it,
+                                               float (&v)[32], int col0, float* scratch) {
+    const float s_eff = ep.hm.s_eff;
+    const float isc = ep.inv_scale;
+    const float a = isc * s_eff * LOG2E;                      // p = 2^(acc * a - lse log2 e)
+    const float lo = cos_lo(), hi = cos_hi();
+    const float gs = st.gs;
+    const float q_off = ep.ls_eps * ep.inv_Ctot;
+    const float gq = gs * q_off;
+    const float* tb = scratch + col0;
+    float bb[32];
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 t4 = *reinterpret_cast<const float4*>(tb + j);
+      bb[j] = t4.x; bb[j + 1] = t4.y; bb[j + 2] = t4.z; bb[j + 3] = t4.w;
+    }
+    float g[32];
+    float am4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float tt = v[j + u];
+        g[j + u] = fmaf(gs, ex2_approx(fmaf(tt, a, bb[j + u])), -gq);
+        asm("max.NaN.xorsign.abs.f32 %0, %0, %1;" : "+f"(am4[u]) : "f"(tt));
+      }
+    }
+    float amax = 0.f;
+    asm("max.NaN.xorsign.abs.f32 %0, %1, %2;" : "=f"(amax) : "f"(am4[0]), "f"(am4[1]));
+    asm("max.NaN.xorsign.abs.f32 %0, %0, %1;" : "+f"(amax) : "f"(am4[2]));
+    asm("max.NaN.xorsign.abs.f32 %0, %0, %1;" : "+f"(amax) : "f"(am4[3]));
+    // a target element sits in this slice iff one of its 32 batch rows is labelled with one of the warp's 32 classes
+    const int* tl = reinterpret_cast<const int*>(scratch) + p_tn(p) + col0;
+    const int lab_l = tl[it.lane];
+    const int c_w0 = st.cls - it.lane;
+    bool careful = !(s_eff > 0.f) || (lab_l >= c_w0 && lab_l < c_w0 + 32) || !(fabsf(amax) * isc <= hi);
+    careful = __any_sync(0xffffffffu, careful);
+    float racc = 0.f;
+    if (!careful) {
+      float r4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) r4[u] = fmaf(g[j + u], v[j + u], r4[u]);
+      }
+      racc = (r4[0] + r4[1]) + (r4[2] + r4[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float cosv = v[j] * isc;
+        const float c = (cosv != cosv) ? cosv : fminf(fmaxf(cosv, lo), hi);
+        const bool is_t = st.row_ok && (tl[j] == st.cls);
+        float tv = c, f = 1.0f;
+        if (is_t) head_phi_dphi(ep.hm, c, &tv, &f);
+        float z = tv * s_eff;
+        if (!isfinite(z)) { z = 0.f; f = 0.f; }
+        if (!(cosv >= lo && cosv <= hi)) f = 0.f;
+        const float pr = exp2f(fmaf(z, LOG2E, bb[j]));
+        const float q = is_t ? (1.0f - ep.ls_eps) + q_off : q_off;
+        g[j] = fminf(fmaxf(gs * (pr - q) * f, -65504.f), 65504.f);
+        const float t = g[j] * v[j];
+        racc += (g[j] != 0.f && t == t) ? t : 0.f;
+      }
+    }
+    st.r += racc;
+    if (st.row_ok) {
+      const int64_t b0 = (int64_t)it.group * p_tn(p) + col0;
+      uint16_t* gdst = ep.GT + (int64_t)st.cls * ep.ldgt + b0;
+      if (b0 + 32 <= p.B) {
+        uint32_t w1[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) w1[j] = pack_f16(g[2 * j], g[2 * j + 1]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(gdst + 8 * j) = make_uint4(w1[4 * j], w1[4 * j + 1], w1[4 * j + 2], w1[4 * j + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (b0 + j < p.B) gdst[j] = (uint16_t)(pack_f16(g[j], 0.f) & 0xffff);
+      }
+    }
+  }
+
+  static __device__ __forceinline__ void tile_end(State& st, const Params& ep, const XwParams&, const XwItem& it) {
+    if (st.row_ok && ep.r_part != nullptr)
+      ep.r_part[(int64_t)(it.group * 2 + it.half) * ep.ldr + st.cls] = st.r * ep.inv_scale;
+  }
+
+  // rows of the resident group = width of the column space = 128 * PAIR; carried in XwParams.tn
+  static __device__ __forceinline__ int p_tn(const XwParams& p) { return p.tn; }
+};
+
+// -------------------------------------------------------------------------------------------------
 // K3b on the MN-major kernel: acc[d, c] = sum_b x_hat[b, d] S * G'[b, c]  (= dW_hat^T * S * g_scale), finished in
 // place with the normalise-backward of the weight rows (autograd of F.normalize, src/face_models.py:352):
 //   dW[c, d] = inv_nw_c * (dW_hat[c, d] - w_hat[c, d] r_c) = coef_c.x * (acc - wh[c, d] * coef_c.y)

@@ -192,29 +192,63 @@ gallery_select_kernel(const float* __restrict__ cand_key, const int32_t* __restr
   __syncthreads();
   if (tid == 0) { qstat[0] = red_k[0] + red_k[1] + red_k[2] + red_k[3]; qstat[1] = ex_key[0] + ex_key[1] + ex_key[2] + ex_key[3]; }
   __syncthreads();
-  // ---- KT rounds of arg-min over the candidates
-  for (int r = 0; r < KT; ++r) {
-    float bk = INFINITY; int bi = INT32_MAX, bp = -1;
-    for (int i = tid; i < n_cand; i += 128) {
-      const int id = cidx[i]; const float kk = ckey[i];
-      if (id >= 0 && (kk < bk || (kk == bk && id < bi))) { bk = kk; bi = id; bp = i; }
-    }
+  // ---- the KT best approximate keys.  Every list is sorted, so the KT-th smallest list HEAD bounds the answer:
+  // the KT smallest heads are already KT candidates <= it.  Warp 0 finds that bound over the heads (KT rounds of
+  // shuffle arg-min, no block barrier), all threads compact the few candidates under it, warp 0 ranks the survivors.
+  __shared__ float bound_s; __shared__ int n_surv;
+  const int n_heads = n_cand / KT;
+  if (tid == 0) n_surv = 0;
+  if (wid == 0) {
+    float taken_k = -INFINITY; int taken_i = -1;
+    float hb = INFINITY;
+    for (int r = 0; r < KT; ++r) {
+      float bk = INFINITY; int bi = INT32_MAX;
+      for (int h = lane; h < n_heads; h += 32) {
+        const int id = cidx[h * KT]; const float kk = ckey[h * KT];
+        const bool after = (kk > taken_k) || (kk == taken_k && id > taken_i);
+        if (id >= 0 && after && (kk < bk || (kk == bk && id < bi))) { bk = kk; bi = id; }
+      }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ok = __shfl_xor_sync(0xffffffffu, bk, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o), op = __shfl_xor_sync(0xffffffffu, bp, o);
-      if (op >= 0 && (bp < 0 || ok < bk || (ok == bk && oi < bi))) { bk = ok; bi = oi; bp = op; }
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ok = __shfl_xor_sync(0xffffffffu, bk, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ok < bk || (ok == bk && oi < bi)) { bk = ok; bi = oi; }
+      }
+      if (bi == INT32_MAX) { hb = INFINITY; break; }          // fewer than KT non-empty lists: keep everything
+      taken_k = bk; taken_i = bi; hb = bk;
     }
-    if (lane == 0) { red_k[wid] = bk; red_i[wid] = bi; red_pos[wid] = bp; }
-    __syncthreads();
-    if (tid == 0) {
-      for (int w = 1; w < 4; ++w)
-        if (red_pos[w] >= 0 && (bp < 0 || red_k[w] < bk || (red_k[w] == bk && red_i[w] < bi))) { bk = red_k[w]; bi = red_i[w]; bp = red_pos[w]; }
-      win_key[r] = bk; win_idx[r] = (bp >= 0) ? bi : -1;
-      if (bp >= 0) cidx[bp] = -1;                              // taken
-    }
-    __syncthreads();
+    if (lane == 0) bound_s = hb;
   }
+  __syncthreads();
+  const float bound = bound_s;
+  float* skey = reinterpret_cast<float*>(cidx + n_cand);       // survivors (capacity n_cand)
+  int32_t* sidx = reinterpret_cast<int32_t*>(skey + n_cand);
+  for (int i = tid; i < n_cand; i += 128) {
+    const int id = cidx[i]; const float kk = ckey[i];
+    if (id >= 0 && kk <= bound) { const int pos = atomicAdd(&n_surv, 1); skey[pos] = kk; sidx[pos] = id; }
+  }
+  __syncthreads();
+  if (wid == 0) {
+    const int ns = n_surv;
+    float taken_k = -INFINITY; int taken_i = -1;
+    for (int r = 0; r < KT; ++r) {
+      float bk = INFINITY; int bi = INT32_MAX;
+      for (int i = lane; i < ns; i += 32) {
+        const float kk = skey[i]; const int id = sidx[i];
+        const bool after = (kk > taken_k) || (kk == taken_k && id > taken_i);
+        if (after && (kk < bk || (kk == bk && id < bi))) { bk = kk; bi = id; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ok = __shfl_xor_sync(0xffffffffu, bk, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ok < bk || (ok == bk && oi < bi)) { bk = ok; bi = oi; }
+      }
+      if (lane == 0) { win_key[r] = bk; win_idx[r] = (bi == INT32_MAX) ? -1 : bi; }
+      if (bi != INT32_MAX) { taken_k = bk; taken_i = bi; }
+    }
+  }
+  __syncthreads();
   // ---- exact re-score of the winners (reference formula, fp32)
   for (int r = 0; r < KT; ++r) {
     const int id = win_idx[r];

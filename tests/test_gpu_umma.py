@@ -27,7 +27,7 @@ def _run(dev, M, N, K, a_mn, b_mn, fmt=2, k_splits=1):
     return float((out.sum(0) - ref).norm() / ref.norm())
 
 
-@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1), (1, 0)])
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (512, 1024, 512), (296, 704, 192), (8, 8, 8), (1000, 264, 72)])
 @pytest.mark.parametrize("fmt", [0, 2])
 def test_gemm_core_layouts(cuda_device, a_mn, b_mn, M, N, K, fmt):
