@@ -110,6 +110,15 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 32-byte global store: one full sector per lane and instruction.  Row-per-thread epilogues that wrote their
+// 64-128 contiguous bytes as 16-byte pieces produced two partial-sector writes per sector in L2.
+__device__ __forceinline__ void st_global_256(void* p, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4,
+                                              uint32_t a5, uint32_t a6, uint32_t a7) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(a4), "r"(a5), "r"(a6), "r"(a7)
+               : "memory");
+}
+
 // ---- descriptors -------------------------------------------------------------------------------
 // Shared-memory matrix descriptor (64-bit), SWIZZLE_128B canonical layouts:
 //   bits [0,14)  start address >> 4        bits [16,30) leading-dim byte offset >> 4

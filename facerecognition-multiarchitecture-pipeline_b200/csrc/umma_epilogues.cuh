@@ -38,7 +38,13 @@ struct EpiStore {
       tmem_ld_wait();
       if (row < p.M) {
         const int cc = min(32, ncols - ch * 32);
-        if (cc == 32 && (ep.ld % 4 == 0)) {
+        if (cc == 32 && (ep.ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(dst) & 31) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8)
+            st_global_256(dst + ch * 32 + j, __float_as_uint(v[j] * sc), __float_as_uint(v[j + 1] * sc),
+                          __float_as_uint(v[j + 2] * sc), __float_as_uint(v[j + 3] * sc), __float_as_uint(v[j + 4] * sc),
+                          __float_as_uint(v[j + 5] * sc), __float_as_uint(v[j + 6] * sc), __float_as_uint(v[j + 7] * sc));
+        } else if (cc == 32 && (ep.ld % 4 == 0)) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
             *reinterpret_cast<float4*>(dst + ch * 32 + j) = make_float4(v[j] * sc, v[j + 1] * sc, v[j + 2] * sc, v[j + 3] * sc);

@@ -165,11 +165,24 @@ struct XwParams {
   uint32_t idesc;
 };
 
+struct XwItem;
+struct XwParams;
+// policies may take the epilogue scratch (warp-private staging) in slice(): detected at compile time
+template <class Epi, class = void> struct xw_slice_wants_scratch { static constexpr bool value = false; };
+template <class Epi> struct xw_slice_wants_scratch<Epi, decltype((void)Epi::kSliceScratch)> { static constexpr bool value = true; };
+
 struct XwItem {                         // what an epilogue thread knows about its work item
   int item, chunk, group;
   int rank, ew, quad, half, lane;       // CTA rank in the pair, epilogue warp 0..7, TMEM quadrant, column half, lane
   int64_t row;                          // global row of x owned by this thread
 };
+
+template <class Epi, class State, class Params>
+__device__ __forceinline__ void xw_call_slice(State& st, const Params& ep, const XwParams& p, const XwItem& it,
+                                              float (&v)[32], int cls0, float* scratch) {
+  if constexpr (xw_slice_wants_scratch<Epi>::value) Epi::slice(st, ep, p, it, v, cls0, scratch);
+  else Epi::slice(st, ep, p, it, v, cls0);
+}
 
 // Epilogue policy interface:
 //   struct Epi { struct Params; struct State;
@@ -418,10 +431,10 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
         for (int s = 0; s < SLICES; s += 2) {
           tmem_ld_wait_dep(va);
           tmem_ld32_async(taddr + (uint32_t)(s + 1) * 32, vb);
-          if (cls_base + s * 32 < p.C) Epi::slice(stt, ep, p, it, va, cls_base + s * 32);
+          if (cls_base + s * 32 < p.C) xw_call_slice<Epi>(stt, ep, p, it, va, cls_base + s * 32, scratch);
           tmem_ld_wait_dep(vb);
           if (s + 2 < SLICES) tmem_ld32_async(taddr + (uint32_t)(s + 2) * 32, va);
-          if (cls_base + (s + 1) * 32 < p.C) Epi::slice(stt, ep, p, it, vb, cls_base + (s + 1) * 32);
+          if (cls_base + (s + 1) * 32 < p.C) xw_call_slice<Epi>(stt, ep, p, it, vb, cls_base + (s + 1) * 32, scratch);
         }
         tc_fence_before_sync();
         __syncwarp();

@@ -448,9 +448,8 @@ struct XwBwdGT {
         uint32_t w1[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) w1[j] = pack_f16(g[2 * j], g[2 * j + 1]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<uint4*>(gdst + 8 * j) = make_uint4(w1[4 * j], w1[4 * j + 1], w1[4 * j + 2], w1[4 * j + 3]);
+        st_global_256(gdst, w1[0], w1[1], w1[2], w1[3], w1[4], w1[5], w1[6], w1[7]);
+        st_global_256(gdst + 16, w1[8], w1[9], w1[10], w1[11], w1[12], w1[13], w1[14], w1[15]);
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
@@ -474,6 +473,8 @@ struct XwBwdGT {
 //   dW[c, d] = inv_nw_c * (dW_hat[c, d] - w_hat[c, d] r_c) = coef_c.x * (acc - wh[c, d] * coef_c.y)
 // coef_c = { inv_nw_c / (S g_scale), r'_c } from reduce_r_kernel; wh = w_hat * S (K1's fp16 rows).
 // The thread owns feature d: for a fixed class its warp writes 128 contiguous bytes of the dW row.
+// (Measured and rejected: fetching the w_hat values one slice ahead -- into registers, or as 16 B vectors through
+//  warp-private shared memory -- made this kernel 50 % slower than loading them where they are used.)
 struct XwDw {
   struct Params { const float2* coef; const __half* wh; float* dw; int64_t c0; int ld; };
   struct State { bool row_ok; };
