@@ -249,29 +249,42 @@ gallery_select_kernel(const float* __restrict__ cand_key, const int32_t* __restr
     }
   }
   __syncthreads();
-  // ---- exact re-score of the winners (reference formula, fp32)
-  for (int r = 0; r < KT; ++r) {
-    const int id = win_idx[r];
-    float acc = 0.f;
-    if (id >= 0) {
-      const TG* row = g + (int64_t)id * D;
-      for (int d = tid; d < D; d += 128) {
-        const float x = q[qi * D + d], y = to_f32<TG>(row[d]);
-        if (cosine) acc = fmaf(x, y, acc);
-        else { const float df = x - y + GALLERY_EPS; acc = fmaf(df, df, acc); }
+  // ---- exact re-score of the winners (reference formula, fp32).  All KT rows are read before anything is reduced:
+  // they are random 2 KB reads from HBM, and one row at a time their latencies added up to a third of the kernel.
+  {
+    float acc[KT];
+#pragma unroll
+    for (int r = 0; r < KT; ++r) acc[r] = 0.f;
+    for (int d = tid; d < D; d += 128) {
+      const float x = q[qi * D + d];
+      float y[KT];
+#pragma unroll
+      for (int r = 0; r < KT; ++r) {
+        const int id = win_idx[r];
+        y[r] = (id >= 0) ? to_f32<TG>(g[(int64_t)id * D + d]) : 0.f;
+      }
+#pragma unroll
+      for (int r = 0; r < KT; ++r) {
+        if (cosine) acc[r] = fmaf(x, y[r], acc[r]);
+        else { const float df = x - y[r] + GALLERY_EPS; acc[r] = fmaf(df, df, acc[r]); }
       }
     }
-    acc = warp_sum(acc);
-    if (lane == 0) red_k[wid] = acc;
+    __shared__ float red_acc[4][KT];
+#pragma unroll
+    for (int r = 0; r < KT; ++r) {
+      const float a = warp_sum(acc[r]);
+      if (lane == 0) red_acc[wid][r] = a;
+    }
     __syncthreads();
-    if (tid == 0) {
-      const float tot = (red_k[0] + red_k[1]) + (red_k[2] + red_k[3]);
+    if (tid < KT) {
+      const int id = win_idx[tid];
+      const float tot = (red_acc[0][tid] + red_acc[1][tid]) + (red_acc[2][tid] + red_acc[3][tid]);
       // ordering key, smaller is better: the distance / minus the cosine (as the exact engine)
       float e;
       if (id < 0) e = INFINITY;
       else if (cosine) e = -(tot * (q_inv ? q_inv[qi] : 1.0f) * (g_inv ? g_inv[id] : 1.0f));
       else e = sqrtf(tot);
-      ex_key[r] = e;
+      ex_key[tid] = e;
     }
     __syncthreads();
   }
