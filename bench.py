@@ -34,6 +34,7 @@ CFG3 = dict(B=512, C=100_000, D=512)
 CFG4 = dict(B=4096, C=1_000_000, D=512)
 CFG2 = dict(Q=1000, N=10_000, D=512, k=1)
 STREAM = dict(Q=128, N=1_000_000, D=512, k=5)
+CFG5 = dict(Q=8192, N=1_000_000, D=512, k=5)
 EPOCH = 10            # post-warm-up schedule state: m_eff = 0.45, s_eff = 6.72
 LS = 0.05
 
@@ -237,6 +238,10 @@ def run_b200(args):
     # ---- per-kernel durations: each C-ABI stage alone between CUDA events on the launching stream, L2 flushed
     # (a 256 MB write) before every launch; these are what the roofline line reports
     kern = time_stages(H, _lib, x, w, y, m_eff, s_eff, c_lo, C_total, eng, dev, reps=max(5, min(args.steps, 20)))
+    gal_sharded = None
+    if world > 1 and not args.no_gallery:
+        del gstep
+        gal_sharded = bench_gallery_sharded(dev, world, rank, group, eng, sync_all)
 
     if rank != 0:
         finish(world)
@@ -280,6 +285,8 @@ def run_b200(args):
     }
     if world == 1 and not args.no_gallery:
         out["gallery"] = bench_gallery(dev, pk, eng)
+    if world > 1 and gal_sharded is not None:
+        out["gallery"] = gal_sharded
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_head_baseline(CFG3)
     print(json.dumps(out), flush=True)
@@ -333,7 +340,10 @@ def load_traffic(kernel):
     """dram bytes per launch of the named kernel from the committed ncu capture (profiles/), else null."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
-        return json.load(open(p)).get(kernel)
+        rec = json.load(open(p)).get(kernel)
+        if isinstance(rec, dict):
+            return rec.get("dram_bytes")
+        return rec
     return None
 
 
@@ -395,6 +405,42 @@ def bench_gallery(dev, pk, eng):
                      "algorithmic_tflops": round(2.0 * c["Q"] * c["N"] * c["D"] / (ms * 1e-3) / 1e12, 2)}
         del G, Q, prep
     return res
+
+
+def bench_gallery_sharded(dev, world, rank, group, eng, sync_all):
+    """cfg5: 1M x 512 gallery rows split contiguously over the ranks, 8192 queries on every rank, top-5:
+    per-shard tensor-engine top-k (exact), ONE all-gather of [Q,5] x 12 B per rank, merge (lowest global index wins
+    ties).  Device time, max over ranks."""
+    import b200face
+    from b200face import parallel
+    c = CFG5
+    lo, hi = parallel.shard_bounds(c["N"], world, rank)
+    g = torch.Generator(device=dev).manual_seed(4321 + rank)
+    G = torch.nn.functional.normalize(torch.randn(hi - lo, c["D"], generator=g, device=dev), dim=1)
+    gq = torch.Generator(device=dev).manual_seed(1234)
+    Q = torch.nn.functional.normalize(torch.randn(c["Q"], c["D"], generator=gq, device=dev), dim=1)
+    prep = b200face.PreparedGallery(G, "l2eps")
+    local = lambda q, gs, k, thr, metric, index_offset=0: b200face.gallery_topk(q, gs, k, thr, metric, index_offset=index_offset,
+                                                                          engine=eng, prepared=prep)[:2]
+    call = lambda: parallel.sharded_gallery_topk(Q, G, c["k"], 1.0, "l2eps", index_offset=lo, group=group, local_topk=local,
+                                                 merge=b200face.gallery.merge_topk)
+    for _ in range(3):
+        call()
+    sync_all()
+    reps = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        idx, score, acc = call()
+    e1.record()
+    sync_all()
+    ms = torch.tensor([e0.elapsed_time(e1) / reps], device=dev)
+    torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+    ms = float(ms)
+    return {"cfg5": {"queries_per_sec": round(c["Q"] / (ms * 1e-3), 1), "ms": round(ms, 4), "Q": c["Q"], "N_total": c["N"],
+                     "N_per_rank": hi - lo, "k": c["k"],
+                     "algorithmic_tflops": round(2.0 * c["Q"] * c["N"] * c["D"] / (ms * 1e-3) / 1e12, 2),
+                     "comm": "one all-gather of [Q,k] (score fp32, index int64) per rank + merge kernel"}}
 
 
 def cpu_head_baseline(c, budget_s=20.0):

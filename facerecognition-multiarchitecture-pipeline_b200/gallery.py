@@ -222,6 +222,21 @@ class GalleryIndex:
         refs = [{'name': r['name'], 'embedding': torch.as_tensor(r['embedding_numpy'])} for r in saved]
         return cls.from_refs(refs, device, dtype)
 
+    def save(self, path: str, image_paths: Optional[Sequence[str]] = None):
+        """Write the store as the pickle the reference's save_refs writes (src/app.py:82-91): a list of
+        {'name', 'embedding_numpy' (1,D) float32, 'image_path'}; load_refs (:104-123) and this class read it back."""
+        import pickle
+        with open(path, "wb") as f:
+            pickle.dump(self.to_saved(image_paths), f)
+
+    @classmethod
+    def load(cls, path: str, device=None, dtype=torch.float32):
+        """Read a face_references.pkl written by the reference (or by save)."""
+        import pickle
+        with open(path, "rb") as f:
+            saved = pickle.load(f)
+        return cls.from_saved(saved, device, dtype)
+
     def to_saved(self, image_paths: Optional[Sequence[str]] = None) -> List[dict]:
         emb = self.embeddings.float().cpu().numpy()
         return [{'name': n, 'embedding_numpy': emb[i:i + 1].copy(),

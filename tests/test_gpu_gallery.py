@@ -158,6 +158,27 @@ def test_gallery_index_edit_operations(cuda_device):
     assert again.names == gi.names and torch.equal(again.embeddings, gi.embeddings)
 
 
+def test_gallery_index_pickle_is_the_reference_format(cuda_device, tmp_path):
+    """save() writes what the reference's save_refs writes (src/app.py:82-91: list of {'name','embedding_numpy'
+    (1,D) float32,'image_path'}), and load() reads the reference's own face_references.pkl layout back."""
+    import pickle
+    import b200face
+    d = golden("gallery_fixture.npz")
+    emb = torch.tensor(d["emb"])
+    refs = [{"name": str(n), "embedding": emb[i:i + 1]} for i, n in enumerate(d["names"])]
+    gi = b200face.GalleryIndex.from_refs(refs, device=cuda_device)
+    path = tmp_path / "face_references.pkl"
+    gi.save(str(path), image_paths=[f"face_references/{n}_{i}.jpg" for i, n in enumerate(gi.names)])
+    saved = pickle.load(open(path, "rb"))
+    assert isinstance(saved, list) and set(saved[0]) == {"name", "embedding_numpy", "image_path"}
+    assert saved[0]["embedding_numpy"].shape == (1, emb.shape[1]) and saved[0]["embedding_numpy"].dtype == np.float32
+    again = b200face.GalleryIndex.load(str(path), device=cuda_device)
+    assert again.names == [str(n) for n in d["names"]]
+    assert torch.equal(again.embeddings.cpu(), emb)
+    for i in range(len(refs)):
+        assert again.compare_faces(emb[i:i + 1], 1.0)[::2] == (str(d["self_name"][i]), int(d["self_idx"][i]))
+
+
 def test_cfg5_scale_properties(cuda_device):
     """A 1M x 512 gallery shard layout at reduced Q: every gallery row queried against the gallery
     finds itself first at distance sqrt(D)*1e-6 (the eps term), the result is independent of how the
