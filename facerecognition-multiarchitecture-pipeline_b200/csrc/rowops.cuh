@@ -145,6 +145,62 @@ l2norm_rows_vec_kernel(const TI* __restrict__ in, int64_t rows, int dim, float e
   }
 }
 
+// K1, 512-wide 16-bit rows (the head's shape): each lane owns 32 contiguous bytes of a row -- ONE 256-bit load and
+// ONE 256-bit store per lane and row (full 32 B sectors), 4 rows per warp in flight.
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+l2norm_rows_512x16_kernel(const TI* __restrict__ in, int64_t rows, float eps, float out_scale,
+                          float* __restrict__ inv_norm, TO* __restrict__ out) {
+  static_assert(sizeof(TI) == 2 && sizeof(TO) == 2, "16-bit rows only");
+  const int lane = threadIdx.x & 31;
+  const int64_t row0 = ((int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5)) * ROWS_PER_WARP;
+  if (row0 >= rows) return;
+  uint32_t raw[ROWS_PER_WARP][8];
+#pragma unroll
+  for (int r = 0; r < ROWS_PER_WARP; ++r) {
+    if (row0 + r < rows) {
+      const TI* src = in + (row0 + r) * 512 + lane * 16;
+      asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                   : "=r"(raw[r][0]), "=r"(raw[r][1]), "=r"(raw[r][2]), "=r"(raw[r][3]), "=r"(raw[r][4]), "=r"(raw[r][5]),
+                     "=r"(raw[r][6]), "=r"(raw[r][7])
+                   : "l"(src));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) raw[r][i] = 0u;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < ROWS_PER_WARP; ++r) {
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const TI* h = reinterpret_cast<const TI*>(&raw[r][i]);
+      v[2 * i] = to_f32<TI>(h[0]); v[2 * i + 1] = to_f32<TI>(h[1]);
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) ss = fmaf(v[i], v[i], ss);
+    ss = warp_sum(ss);
+    if (row0 + r >= rows) continue;
+    const float inv = 1.0f / fmaxf(sqrtf(ss), eps);
+    if (lane == 0 && inv_norm != nullptr) inv_norm[row0 + r] = inv;
+    if (out != nullptr) {
+      const float s = inv * out_scale;
+      uint32_t o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        TO pr[2];
+        store_elem<TO>(&pr[0], v[2 * i] * s); store_elem<TO>(&pr[1], v[2 * i + 1] * s);
+        o[i] = *reinterpret_cast<uint32_t*>(pr);
+      }
+      asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                   ::"l"(out + (row0 + r) * 512 + lane * 16), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]),
+                     "r"(o[6]), "r"(o[7])
+                   : "memory");
+    }
+  }
+}
+
 // K1, generic path (any dim / alignment): one warp per row, scalar accesses.
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
@@ -236,6 +292,13 @@ template <typename TI, typename TO>
 static inline void launch_l2norm_rows(const TI* in, int64_t rows, int dim, float eps, float out_scale, float* inv_norm,
                                       TO* out, cudaStream_t st) {
   constexpr int N = Vec16<TI>::N;
+  if constexpr (sizeof(TI) == 2 && sizeof(TO) == 2) {
+    if (dim == 512 && reinterpret_cast<uintptr_t>(in) % 32 == 0 && (!out || reinterpret_cast<uintptr_t>(out) % 32 == 0)) {
+      l2norm_rows_512x16_kernel<TI, TO><<<(unsigned)ceil_div(rows, ROWS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, st>>>(
+          in, rows, eps, out_scale, inv_norm, out);
+      return;
+    }
+  }
   bool vec = (dim % N == 0) && (reinterpret_cast<uintptr_t>(in) % 16 == 0) && (dim <= 32 * N * 4);
   if (out) vec = vec && (reinterpret_cast<uintptr_t>(out) % 16 == 0);
   if (vec) {

@@ -285,7 +285,10 @@ static Plan make_plan(int64_t B, int64_t C, int D) {
   // and read twice, all while the tensor pipe (not HBM) is the bound, so it need not stay L2-resident: cfg3's
   // 102 MB is ONE chunk (fewer launches, long per-CTA streams); B = 4096 shards use ~12 k-class chunks.
   const int64_t ldgt = ceil_div(B, 64) * 64;               // G^T[class][batch row], row stride in elements
-  int64_t cc_max = ((int64_t)g_chunk_mb.load(std::memory_order_relaxed) * (1 << 20) / 2 / ldgt) / BLOCK_N * BLOCK_N;
+  // batches above 512 rows get 4x the budget: long chunks keep the per-launch fill / drain and the wave quantisation
+  // of the streamed K3b small (memory is not the constraint on a 180 GB part)
+  const int64_t budget_mb = (int64_t)g_chunk_mb.load(std::memory_order_relaxed) * (B > (int64_t)XW_MAX_KB * XW_K ? 4 : 1);
+  int64_t cc_max = (budget_mb * (1 << 20) / 2 / ldgt) / BLOCK_N * BLOCK_N;
   if (cc_max < BLOCK_N) cc_max = BLOCK_N;
   pl.n_chunks = (int)ceil_div(C, cc_max);
   pl.Cc = ceil_div(ceil_div(C, pl.n_chunks), BLOCK_N) * BLOCK_N;
@@ -407,12 +410,16 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
       rc = (qw.pair == 2) ? launch_xw<2, XW_MK, XwDw>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW (cta pair)")
                           : launch_xw<1, XW_MK, XwDw>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW");
       if (rc) return rc;
-    } else {                                                // batch > 512: both operands streamed (generic core)
-      CUtensorMap tg_kb;
-      rc = tmap_kmajor(&tg_kb, G, cnt, B, pl.ldg, BLOCK_N); if (rc) return rc;
-      GemmParams pw = gemm_params(D, (int)cnt, (int)B, 1, true, false, FMT_F16, FMT_F16);
-      EpiDwT::Params ew{coef, static_cast<const __half*>(wh), dw, c0, D};
-      rc = launch_gemm<true, false, EpiDwT>(tx_mn, tg_kb, pw, ew, st, "umma K3b dW (streamed)");
+    } else {
+      // batch > 512: x_hat^T cannot stay resident, both operands stream through the generic core:
+      // dW_hat[c0 + m, :] = sum_b G^T[m, b] x_hat[b, :], normalise-backward afterwards (one pass over dW).
+      // (The fused transposed epilogue on this core, EpiDwT, measured 2.3x slower at B = 4096: 4 epilogue warps,
+      //  unpipelined TMEM reads, per-element global loads.)
+      CUtensorMap tg_km;
+      rc = tmap_kmajor(&tg_km, G, cnt, B, pl.ldg, BLOCK_M); if (rc) return rc;
+      GemmParams pw = gemm_params((int)cnt, D, (int)B, 1, false, true, FMT_F16, FMT_F16);
+      EpiStore::Params ew{dw, (int64_t)D, 0, c0, 1.0f / S, grad4 + 3};
+      rc = launch_gemm<false, true, EpiStore>(tg_km, tx_mn, pw, ew, st, "umma K3b dW (streamed)");
       if (rc) return rc;
     }
     // --- K3c: dx_hat partials = G[:, k-range] w_hat[c0 + k-range, :]   (A = G read MN-major from G^T)
@@ -427,6 +434,11 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
     reduce_splits_kernel<<<(unsigned)ceil_div(n / 4, 256), 256, 0, st>>>(dxpart, px.k_splits, n, dxhat, chunk_no > 0,
                                                                         1.0f / S, grad4 + 3);
     B200F_LAUNCH_OK("umma reduce_splits_kernel");
+  }
+  if (!pl.fused_dw) {
+    // normalise-backward of the weight rows, in place: dw <- inv_nw * (dw_hat - w_hat <w_hat, dw_hat>)
+    rowops::launch_l2norm_bwd<__half, true>(static_cast<const __half*>(wh), S, inv_nw, dw, C, D, dw, st);
+    B200F_LAUNCH_OK("l2norm_bwd kernel (weights)");
   }
   return B200F_OK;
 }

@@ -1,0 +1,22 @@
+#!/usr/bin/env python
+"""A few eager fused head steps at an arbitrary shape (env HB, HC) for ncu launch lists -- e.g. one rank's share of
+cfg4 (HB=4096 HC=125000).  Development aid."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import b200face
+from b200face.head import arcface_loss
+B, C, D = int(os.environ.get("HB", 4096)), int(os.environ.get("HC", 125000)), 512
+dev = torch.device("cuda:0")
+g = torch.Generator(device=dev).manual_seed(1)
+w = (torch.randn(C, D, generator=g, device=dev) * 0.006).bfloat16()
+wm = w.float().requires_grad_(True)
+x = torch.randn(B, D, generator=g, device=dev).bfloat16()
+y = torch.randint(0, C, (B,), generator=g, device=dev)
+for i in range(3):
+    wm.grad = None
+    xi = x.clone().requires_grad_(True)
+    loss = arcface_loss(xi, wm, y, compute_weight=w, m_eff=0.45, s_eff=6.72, label_smoothing=0.05)
+    loss.backward()
+torch.cuda.synchronize()
+print("loss", float(loss))
