@@ -222,15 +222,31 @@ def run_b200(args):
                 l.backward()
             else:
                 l = eager_step(xd, yd)
-        return float(l.item())                                        # D2H read of the step's result
-    for _ in range(3):
-        e2e_step()
+        return l
+    # The loss of EVERY step is read back to the host, through pinned memory with a one-step lag: the D2H copy of
+    # step i is enqueued behind it and read while step i+1 runs, so the host never idles the GPU (a training loop
+    # that logs its loss does exactly this).
+    loss_host = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ev = [torch.cuda.Event() for _ in range(2)]
+    losses_read = []
+    def e2e_loop(n):
+        for i in range(n):
+            l = e2e_step()
+            loss_host[i & 1].copy_(l.detach(), non_blocking=True)
+            loss_ev[i & 1].record()
+            if i > 0:
+                loss_ev[(i - 1) & 1].synchronize()
+                losses_read.append(float(loss_host[(i - 1) & 1]))
+        loss_ev[(n - 1) & 1].synchronize()
+        losses_read.append(float(loss_host[(n - 1) & 1]))
+    e2e_loop(3)
     sync_all()
+    losses_read.clear()
     e0.record()
-    for _ in range(args.steps):
-        e2e_step()
+    e2e_loop(args.steps)
     e1.record()
     sync_all()
+    assert len(losses_read) == args.steps
     ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         torch.distributed.all_reduce(ms2, op=torch.distributed.ReduceOp.MAX)
@@ -276,7 +292,7 @@ def run_b200(args):
         "algorithmic_tflops": round(flops_step * args.steps / (ms_total * 1e-3) / 1e12, 2),
         "frac_of_bf16_peak": round(flops_step * args.steps / (ms_total * 1e-3) / 1e12 / (pk["tf_sustained"] * world), 4),
         "e2e": {"value": round(e2e_val, 1), "unit": "samples/s", "h2d_bytes_per_step": int(xh.numel() * 2 + yh.numel() * 8),
-                "d2h_bytes_per_step": 4},
+                "d2h_bytes_per_step": 4, "d2h": "loss of every step, pinned buffer, read with a one-step lag"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roof,
