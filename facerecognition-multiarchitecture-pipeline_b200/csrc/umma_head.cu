@@ -1,10 +1,12 @@
-// tcgen05 / TMEM / TMA engine for the ArcFace head: host side.
-// Operands are the fp16, L2-normalised, power-of-two-scaled rows K1 emits (dtype B200F_F16N).
-//   K2  forward statistics : xw_kernel<PAIR, XwFwd>            x_hat[B,D] . w_hat[C,D]^T, x_hat resident in smem
-//   K3a logit gradient     : xw_kernel<PAIR, XwBwdG>           recompute + G (fp16, L2-resident chunk)
-//   K3b dW_hat = G^T x_hat : gemm_kernel<MN,MN,EpiStore>       then normalise-backward in place
-//   K3c dx_hat = G w_hat   : gemm_kernel<K,MN,EpiStore> split-K, then a fixed-order reduction
-// PAIR = 2 runs K2 / K3a on tcgen05 cta_group::2 CTA pairs (clusters of two), PAIR = 1 on single CTAs.
+// tcgen05 / TMEM / TMA engine: host side (ArcFace head K2 / K3, gallery scan K4t, probes).
+// Operands of the head are the fp16, L2-normalised, power-of-two-scaled rows K1 emits (dtype B200F_F16N).
+//   K2  forward statistics : xw_kernel<PAIR, XW_KK,   XwFwd>    x_hat[B,D] . w_hat[C,D]^T, x_hat resident in smem
+//   K3a logit gradient     : xw_kernel<PAIR, XW_SWAP, XwBwdGT>  recompute, class-major G^T (fp16) + r column sums
+//   K3b dW                 : xw_kernel<PAIR, XW_MK,   XwDw>     dW^T = x_hat^T . G, normalise-backward fused (B <= 512)
+//                            gemm_kernel<K,MN,EpiStore> + l2norm_bwd (B > 512: both operands streamed)
+//   K3c dx_hat = G w_hat   : gemm_kernel<MN,MN,EpiStore> split-K, then a fixed-order reduction
+//   K4t gallery scan       : xw_kernel<PAIR, XW_KK,   XwTopK<KT>> + gallery_select_kernel
+// PAIR = 2 runs the xw kernels on tcgen05 cta_group::2 CTA pairs (clusters of two), PAIR = 1 on single CTAs.
 // ALL tcgen05 kernels of the library live in this one translation unit (g_umma_timeout_flag).
 #include "umma_api.cuh"
 #include "umma_epilogues.cuh"
@@ -413,8 +415,8 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
     } else {
       // batch > 512: x_hat^T cannot stay resident, both operands stream through the generic core:
       // dW_hat[c0 + m, :] = sum_b G^T[m, b] x_hat[b, :], normalise-backward afterwards (one pass over dW).
-      // (The fused transposed epilogue on this core, EpiDwT, measured 2.3x slower at B = 4096: 4 epilogue warps,
-      //  unpipelined TMEM reads, per-element global loads.)
+      // (A fused transposed epilogue on this core measured 2.3x slower at B = 4096: 4 epilogue warps, unpipelined
+      //  TMEM reads, per-element global loads.)
       CUtensorMap tg_km;
       rc = tmap_kmajor(&tg_km, G, cnt, B, pl.ldg, BLOCK_M); if (rc) return rc;
       GemmParams pw = gemm_params((int)cnt, D, (int)B, 1, false, true, FMT_F16, FMT_F16);

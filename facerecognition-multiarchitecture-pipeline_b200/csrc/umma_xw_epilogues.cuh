@@ -193,150 +193,15 @@ struct XwFwd {
   }
 };
 
-// Column sums across the warp: on return lane l holds sum over the 32 lanes of h[l] (31 shuffles: each step
-// halves the columns a lane is responsible for).  Fixed order, so bitwise reproducible.
-__device__ __forceinline__ float warp_column_sums(float (&h)[32], int lane) {
-#pragma unroll
-  for (int step = 16; step >= 1; step >>= 1) {
-    const bool upper = (lane & step) != 0;
-#pragma unroll
-    for (int i = 0; i < step; ++i) {
-      const float send = upper ? h[i] : h[i + step];
-      const float keep = upper ? h[i + step] : h[i];
-      h[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
-    }
-  }
-  return h[0];
-}
-
-// -------------------------------------------------------------------------------------------------
-// K3a: recompute the logits of a class chunk and emit the logit gradient as fp16 (one L2-resident buffer
-// that both consumer GEMMs read),
-//   G_ij = g_scale * grad_scale * (p_ij - q_ij) * dphi/dc * 1[lo <= cos <= hi]      (SURVEY 8a closed form)
-// grad4 = {grad_scale, n, kappa, g_scale} from b200f_arcface_hook_scale; g_scale is the power of two that
-// puts |grad_scale| * g_scale in (512, 1024], so a target-column entry (|p-q| <= 1, dphi <~ 30) stays below
-// fp16 max and entries down to p ~ 1e-7 stay normal; the consumers divide it out again.
-// Side output (r_part != NULL): r'_j = sum_i G_ij cos_ij per 32-row block = <w_hat_j, dW_hat_j> * g_scale, the
-// radial part that the normalise-backward of w removes -- so the dW GEMM can finish dW in its own epilogue.
-struct XwBwdG {
-  struct Params {
-    const int64_t* label; const float* lse; const float* grad4;
-    int64_t class_offset;       // global id of this launch's class 0
-    HeadMath hm;
-    float ls_eps, inv_Ctot, inv_scale;
-    uint16_t* G; int64_t ldg;   // G[row, class of this launch]
-    float* r_part; int64_t ldr; // [row blocks of 32, ldr] or NULL
-    int pair;
-  };
-  struct State { float lse, gs; int tgt; bool row_ok; };
-
-  static __device__ __forceinline__ void item_begin(State& st, const Params& ep, const XwParams& p, const XwItem& it) {
-    st.row_ok = it.row < p.B;
-    st.lse = st.row_ok ? __ldg(ep.lse + it.row) : 0.f;
-    st.gs = __ldg(ep.grad4) * __ldg(ep.grad4 + 3);
-    st.tgt = -1;
-    if (st.row_ok) {
-      const int64_t tg = __ldg(ep.label + it.row) - ep.class_offset;
-      if (tg >= 0 && tg < p.C) st.tgt = (int)tg;
-    }
-  }
-
-  static __device__ __forceinline__ void tile_begin(State&, const Params&, const XwParams&, const XwItem&, int, int, int) {}
-  static __device__ __forceinline__ void slice(State& st, const Params& ep, const XwParams& p, const XwItem& it,
-                                               float (&v)[32], int cls0) {
-    const int cc = min(32, p.C - cls0);
-    const float s_eff = ep.hm.s_eff;
-    const float isc = ep.inv_scale;
-    const float a = isc * s_eff * LOG2E, b = -st.lse * LOG2E; // p = 2^(acc*a + b)
-    const float lo = cos_lo(), hi = cos_hi();
-    const float gs = st.gs;
-    const float q_off = ep.ls_eps * ep.inv_Ctot;
-    const float gq = gs * q_off;
-    float g[32];
-    // One NaN-propagating max over |acc| covers both guards of the fast path: a NaN / Inf accumulator and a cosine
-    // outside the (symmetric) clamp range (max.NaN.xorsign.abs: magnitude = max(|a|,|b|), NaN if either is NaN).
-    float am4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float tt = v[j + u];
-        g[j + u] = fmaf(gs, ex2_approx(fmaf(tt, a, b)), -gq);
-        asm("max.NaN.xorsign.abs.f32 %0, %0, %1;" : "+f"(am4[u]) : "f"(tt));
-      }
-    }
-    float amax = 0.f;
-    asm("max.NaN.xorsign.abs.f32 %0, %1, %2;" : "=f"(amax) : "f"(am4[0]), "f"(am4[1]));
-    asm("max.NaN.xorsign.abs.f32 %0, %0, %1;" : "+f"(amax) : "f"(am4[2]));
-    asm("max.NaN.xorsign.abs.f32 %0, %0, %1;" : "+f"(amax) : "f"(am4[3]));
-    const bool has_t = (st.tgt >= cls0) && (st.tgt < cls0 + 32);
-    bool careful = !(s_eff > 0.f) || has_t || !(fabsf(amax) * isc <= hi);     // NaN fails the comparison
-    careful = __any_sync(0xffffffffu, careful);
-    if (careful) {
-      float tphi = 0.f, tdphi = 0.f;                          // phi / dphi once per slice (see XwFwd)
-      if (has_t) {
-        float ct = 0.f;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) if (cls0 + j == st.tgt) ct = v[j] * isc;
-        const float cc_t = (ct != ct) ? ct : fminf(fmaxf(ct, lo), hi);
-        tphi = ep.hm.phi(cc_t); tdphi = ep.hm.dphi(cc_t);
-      }
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float cosv = v[j] * isc;
-        const float c = (cosv != cosv) ? cosv : fminf(fmaxf(cosv, lo), hi);
-        const bool is_t = (cls0 + j == st.tgt);
-        const float tv = is_t ? tphi : c;
-        float z = tv * s_eff;
-        float f = is_t ? tdphi : 1.0f;
-        if (!isfinite(z)) { z = 0.f; f = 0.f; }
-        if (!(cosv >= lo && cosv <= hi)) f = 0.f;
-        const float pr = exp2f((z - st.lse) * LOG2E);
-        const float q = is_t ? (1.0f - ep.ls_eps) + q_off : q_off;
-        g[j] = fminf(fmaxf(gs * (pr - q) * f, -65504.f), 65504.f);
-      }
-    }
-    if (ep.r_part != nullptr) {
-      float h[32];                                            // G * S^2 cos; a cut gradient (g = 0) contributes 0
-      if (!careful) {                                         // finite by construction; rows >= B have v = 0
-#pragma unroll
-        for (int j = 0; j < 32; ++j) h[j] = g[j] * v[j];
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float t = g[j] * v[j];
-          h[j] = (st.row_ok && g[j] != 0.f && t == t) ? t : 0.f;
-        }
-      }
-      const float colsum = warp_column_sums(h, it.lane);
-      const int rb = (it.group * ep.pair + it.rank) * 4 + it.quad;
-      if (cls0 + it.lane < p.C) ep.r_part[(int64_t)rb * ep.ldr + cls0 + it.lane] = colsum * isc;
-    }
-    if (st.row_ok) {
-      uint16_t* gdst = ep.G + it.row * ep.ldg + cls0;
-      if (cc == 32) {
-        uint32_t w1[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) w1[j] = pack_f16(g[2 * j], g[2 * j + 1]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<uint4*>(gdst + 8 * j) = make_uint4(w1[4 * j], w1[4 * j + 1], w1[4 * j + 2], w1[4 * j + 3]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < cc) gdst[j] = (uint16_t)(pack_f16(g[j], 0.f) & 0xffff);
-      }
-    }
-  }
-
-  static __device__ __forceinline__ void item_end(State&, const Params&, const XwParams&, const XwItem&, float*) {}
-};
-
 // -------------------------------------------------------------------------------------------------
 // K3a, class-major (xw_kernel SWAP mode): the thread owns ONE class of the tile, the 32 columns of a slice are batch
 // rows of the resident group.  Per-column quantities (-lse_b log2 e, the row's target class) sit in shared memory
 // (item_begin); r_j = sum_i G_ij cos_ij is a private running sum; G leaves class-major, G^T[class][batch row], 64
-// contiguous bytes per thread and slice.  Same fast / careful split as XwBwdG; phi / dphi are ONE out-of-line copy.
+// contiguous bytes per thread and slice.  Fast / careful slices as in XwFwd; phi / dphi are ONE out-of-line copy.
+// (The batch-major predecessor needed a 31-shuffle butterfly per 32 classes for r and twice the instructions.)
+// grad4 = {grad_scale, n, kappa, g_scale} from b200f_arcface_hook_scale; g_scale is the power of two that puts
+// |grad_scale| * g_scale in (512, 1024], so a target-column entry (|p-q| <= 1, dphi <~ 30) stays below fp16 max and
+// entries down to p ~ 1e-7 stay normal; the consumers divide it out again.
 __device__ __noinline__ void head_phi_dphi(HeadMath hm, float c, float* phi, float* dphi) {
   *phi = hm.phi(c);
   *dphi = hm.dphi(c);
@@ -524,38 +389,6 @@ struct XwDw {
     }
   }
   static __device__ __forceinline__ void item_end(State&, const Params&, const XwParams&, const XwItem&, float*) {}
-};
-
-// -------------------------------------------------------------------------------------------------
-// The same fused dW epilogue for the generic GEMM core (batches above 512 rows, where x_hat^T cannot stay resident):
-// D[m = d, n = class] with both operands MN-major, finished as in XwDw.
-struct EpiDwT {
-  struct Params { const float2* coef; const __half* wh; float* dw; int64_t c0; int ld; };
-  static __device__ __forceinline__ void run(const Params& ep, const GemmParams& p, const TileCoord& t,
-                                             uint32_t tmem_acc, int quad, int lane, int epi_tid, float* scratch) {
-    const int row = t.m0 + quad * 32 + lane;                  // feature d
-    const int ncols = min(BLOCK_N, p.N - t.n0);
-    for (int ch = 0; ch * 32 < ncols; ++ch) {
-      float v[32];
-      tmem_ld32(tmem_acc + ((uint32_t)(quad * 32) << 16) + ch * 32, v);
-      tmem_ld_wait();
-      if (row < p.M) {
-        const int cls0 = t.n0 + ch * 32;
-        const int cc = min(32, p.N - cls0);
-        const int64_t base = (ep.c0 + cls0) * ep.ld + row;
-        const float2* cf = ep.coef + ep.c0 + cls0;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (j < cc) {
-            const float2 c2 = __ldg(cf + j);
-            const float wv = __half2float(__ldg(ep.wh + base + (int64_t)j * ep.ld));
-            ep.dw[base + (int64_t)j * ep.ld] = c2.x * fmaf(-wv, c2.y, v[j]);
-          }
-        }
-      }
-    }
-    (void)epi_tid; (void)scratch;
-  }
 };
 
 }  // namespace umma
