@@ -220,12 +220,18 @@ static int gcd_int(int a, int b) { while (b) { int t = a % b; a = b; b = t; } re
 
 struct XwPlan { int pair, m_groups, n_tiles, n_clusters, n_chunks, items, grid; };
 
-static XwPlan xw_plan(int64_t B, int64_t C, int pair) {
+static XwPlan xw_plan(int64_t B, int64_t C, int pair, int max_chunks = 0) {
   XwPlan q{};
   q.pair = pair;
   q.m_groups = (int)ceil_div(B, (int64_t)XW_M * pair);
   q.n_tiles = (int)ceil_div(C, (int64_t)XW_WROWS * pair);
   q.n_clusters = xw_max_clusters(pair);
+  if (max_chunks > 0) {                                   // few, long chunks (the gallery's sample pre-pass)
+    q.n_chunks = max_chunks < q.n_tiles ? max_chunks : q.n_tiles;
+    q.items = q.m_groups * q.n_chunks;
+    q.grid = pair * (q.items < q.n_clusters ? q.items : q.n_clusters);
+    return q;
+  }
   // items = m_groups * n_chunks is a multiple of the cluster count whenever the class range allows it
   int nc = q.n_clusters / gcd_int(q.n_clusters, q.m_groups);
   if (nc > q.n_tiles) nc = q.n_tiles;
@@ -446,7 +452,16 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
 }
 
 // ---- K4 on tensor cores: host side ------------------------------------------------------------------
-struct GalleryScanPlan { XwPlan q; int KT, n_lists; size_t off_q16, off_ckey, off_cidx, total; };
+// Sample pre-pass of the gallery scan.  One row group (Q <= 128 * PAIR): 128 chunks of one tile -- every CTA scans one
+// tile of the first 16 k (32 k) rows.  Several row groups: 4 chunks of 8 tiles, so that a work item amortises its
+// x load over 8 tiles (one-tile items made the pre-pass cost a quarter of the scan at Q = 8192).
+constexpr int GALLERY_SAMPLE_MAX_LISTS = 32 * GALLERY_TAU_LISTS_PER_LANE;
+struct GalleryScanPlan {
+  XwPlan q, qs;                 // main scan / sample pre-pass
+  int KT, n_lists;
+  int64_t n_sample;             // gallery rows of the sample (0: no pre-pass)
+  size_t off_q16, off_ckey, off_cidx, off_skey, off_sidx, off_tau, off_qbad, total;
+};
 
 static GalleryScanPlan gallery_scan_plan(int64_t Q, int64_t N, int D, int k) {
   GalleryScanPlan g{};
@@ -457,6 +472,17 @@ static GalleryScanPlan gallery_scan_plan(int64_t Q, int64_t N, int D, int k) {
   g.off_q16 = off;  off += align_up(2 * (size_t)Q * D, 1024);
   g.off_ckey = off; off += align_up(sizeof(float) * (size_t)Q * g.n_lists * g.KT, 256);
   g.off_cidx = off; off += align_up(sizeof(int32_t) * (size_t)Q * g.n_lists * g.KT, 256);
+  // sample pre-pass over the first rows of the gallery (skipped when that is a quarter of it or more)
+  const int s_chunks = (g.q.m_groups == 1) ? GALLERY_SAMPLE_MAX_LISTS / 2 : 4;
+  const int s_tiles = (g.q.m_groups == 1) ? 1 : 8;
+  const int64_t ns = (int64_t)s_chunks * s_tiles * XW_WROWS * g.q.pair;
+  g.n_sample = (N >= 4 * ns) ? ns : 0;
+  g.qs = xw_plan(Q, g.n_sample > 0 ? g.n_sample : 1, g.q.pair, s_chunks);
+  const size_t sl = (size_t)Q * GALLERY_SAMPLE_MAX_LISTS * g.KT;
+  g.off_skey = off; off += align_up(sizeof(float) * sl, 256);
+  g.off_sidx = off; off += align_up(sizeof(int32_t) * sl, 256);
+  g.off_tau = off;  off += align_up(sizeof(float) * (size_t)Q, 256);
+  g.off_qbad = off; off += align_up((size_t)Q, 256);
   g.total = off + 1024;
   return g;
 }
@@ -467,14 +493,14 @@ size_t gallery_scan_workspace(int64_t Q, int64_t N, int D, int k) { return galle
 
 int gallery_prepare(const void* g, int dtype, int64_t N, int D, int metric, int fmt, void* g16, float* bias, cudaStream_t st) {
   if (D > 512) return fail(B200F_ERR_UNSUPPORTED, "gallery_prepare: D <= 512");
-  if (bias) B200F_CUDA_OK(cudaMemsetAsync(bias + N, 0, sizeof(float), st));
+  if (bias) B200F_CUDA_OK(cudaMemsetAsync(bias + N, 0, 2 * sizeof(float), st));
   const unsigned grid = (unsigned)ceil_div(N, 8);
   if (dtype == B200F_F32)
     gallery_prepare_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(g), N, D, metric, fmt,
-                                                       static_cast<uint16_t*>(g16), bias);
+                                                       static_cast<uint16_t*>(g16), bias, nullptr);
   else
     gallery_prepare_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(g), N, D, metric, fmt,
-                                                               static_cast<uint16_t*>(g16), bias);
+                                                               static_cast<uint16_t*>(g16), bias, nullptr);
   B200F_LAUNCH_OK("gallery_prepare_kernel");
   return B200F_OK;
 }
@@ -483,20 +509,33 @@ template <int KT>
 static int gallery_scan_kt(const GalleryScanPlan& gp, const CUtensorMap& tx, const CUtensorMap& tw, const float* q,
                            const float* g, const float* bias, const float* q_inv, const float* g_inv, int64_t Q, int64_t N,
                            int64_t index_offset, int D, int k, int metric, int fmt, float thresh, int64_t* idx, float* score,
-                           uint8_t* accept, uint8_t* redo, int32_t* redo_count, float* ckey, int32_t* cidx, cudaStream_t st) {
+                           uint8_t* accept, uint8_t* redo, int32_t* redo_count, float* ckey, int32_t* cidx, float* skey,
+                           int32_t* sidx, float* tau0, const uint8_t* qbad, cudaStream_t st) {
+  const uint32_t mfmt = fmt == B200F_OPERAND_FP16 ? FMT_F16 : FMT_BF16;
   typename XwTopK<KT>::Params ep{};
   ep.bias = (metric == B200F_METRIC_COS) ? nullptr : bias;
   ep.mult = (metric == B200F_METRIC_COS) ? -1.0f : -2.0f;
+  if (gp.n_sample > 0) {
+    // sample pre-pass: the same scan over the first n_sample rows with few long chunks, then tau0[q] = KT-th best key
+    typename XwTopK<KT>::Params es = ep;
+    es.cand_key = skey; es.cand_idx = sidx; es.n_lists = gp.qs.n_chunks * 2; es.tau0 = nullptr;
+    int rcs = (gp.qs.pair == 2) ? launch_xw<2, XW_KK, XwTopK<KT>>(tx, tw, gp.qs, Q, gp.n_sample, D, es, st, "umma K4 gallery sample scan (cta pair)", mfmt)
+                                : launch_xw<1, XW_KK, XwTopK<KT>>(tx, tw, gp.qs, Q, gp.n_sample, D, es, st, "umma K4 gallery sample scan", mfmt);
+    if (rcs) return rcs;
+    gallery_tau_kernel<KT><<<(unsigned)ceil_div(Q, 4), 128, 0, st>>>(skey, sidx, es.n_lists, Q, tau0);
+    B200F_LAUNCH_OK("gallery_tau_kernel");
+    ep.tau0 = tau0;
+  }
   ep.cand_key = ckey; ep.cand_idx = cidx; ep.n_lists = gp.n_lists;
-  int rc = (gp.q.pair == 2) ? launch_xw<2, XW_KK, XwTopK<KT>>(tx, tw, gp.q, Q, N, D, ep, st, "umma K4 gallery scan (cta pair)", fmt == B200F_OPERAND_FP16 ? FMT_F16 : FMT_BF16)
-                            : launch_xw<1, XW_KK, XwTopK<KT>>(tx, tw, gp.q, Q, N, D, ep, st, "umma K4 gallery scan", fmt == B200F_OPERAND_FP16 ? FMT_F16 : FMT_BF16);
+  int rc = (gp.q.pair == 2) ? launch_xw<2, XW_KK, XwTopK<KT>>(tx, tw, gp.q, Q, N, D, ep, st, "umma K4 gallery scan (cta pair)", mfmt)
+                            : launch_xw<1, XW_KK, XwTopK<KT>>(tx, tw, gp.q, Q, N, D, ep, st, "umma K4 gallery scan", mfmt);
   if (rc) return rc;
   const int n_cand = gp.n_lists * KT;
   const size_t smem = (size_t)n_cand * 16;                 // candidates + survivors, (key, idx) each
   auto kern = gallery_select_kernel<float, KT>;
   B200F_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 160 * 1024 ? 160 * 1024 : (smem < 1024 ? 1024 : smem))));
   if (smem > 160 * 1024) return fail(B200F_ERR_UNSUPPORTED, "gallery scan: candidate lists do not fit shared memory");
-  kern<<<(unsigned)Q, 128, smem, st>>>(ckey, cidx, n_cand, q, g, q_inv, g_inv, bias ? bias + N : nullptr, Q, D, k, metric,
+  kern<<<(unsigned)Q, 128, smem, st>>>(ckey, cidx, n_cand, q, g, q_inv, g_inv, bias ? bias + N : nullptr, qbad, Q, D, k, metric,
                                        fmt, thresh, index_offset, idx, score, accept, redo, redo_count);
   B200F_LAUNCH_OK("gallery_select_kernel");
   return B200F_OK;
@@ -516,13 +555,17 @@ int gallery_scan_select(const float* q, const float* g, const void* g16, const f
   uint16_t* q16 = reinterpret_cast<uint16_t*>(ws + gp.off_q16);
   float* ckey = reinterpret_cast<float*>(ws + gp.off_ckey);
   int32_t* cidx = reinterpret_cast<int32_t*>(ws + gp.off_cidx);
-  gallery_prepare_kernel<float><<<(unsigned)ceil_div(Q, 8), 256, 0, st>>>(q, Q, D, B200F_METRIC_L2EPS, fmt, q16, nullptr);
+  float* skey = reinterpret_cast<float*>(ws + gp.off_skey);
+  int32_t* sidx = reinterpret_cast<int32_t*>(ws + gp.off_sidx);
+  float* tau0 = reinterpret_cast<float*>(ws + gp.off_tau);
+  uint8_t* qbad = reinterpret_cast<uint8_t*>(ws + gp.off_qbad);
+  gallery_prepare_kernel<float><<<(unsigned)ceil_div(Q, 8), 256, 0, st>>>(q, Q, D, B200F_METRIC_L2EPS, fmt, q16, nullptr, qbad);
   B200F_LAUNCH_OK("gallery_prepare_kernel (queries)");
   CUtensorMap tx, tw;
   int rc = tmap_kmajor(&tx, q16, Q, D, D, XW_M); if (rc) return rc;
   rc = tmap_kmajor(&tw, g16, N, D, D, XW_WROWS); if (rc) return rc;
 #define B200F_SCAN(KT) gallery_scan_kt<KT>(gp, tx, tw, q, g, bias, q_inv, g_inv, Q, N, index_offset, D, k, metric, fmt, thresh, idx, \
-                                           score, accept, redo, redo_count, ckey, cidx, st)
+                                           score, accept, redo, redo_count, ckey, cidx, skey, sidx, tau0, qbad, st)
   if (gp.KT == 8) return B200F_SCAN(8);
   if (gp.KT == 16) return B200F_SCAN(16);
   return B200F_SCAN(32);

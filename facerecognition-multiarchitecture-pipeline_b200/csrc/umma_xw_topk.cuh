@@ -36,14 +36,25 @@ struct XwTopK {
     float* cand_key;            // [Q, n_lists, KT]
     int32_t* cand_idx;          // [Q, n_lists, KT]   gallery row (shard-local), -1 = empty
     int n_lists;                // n_chunks * 2
+    const float* tau0;          // [Q] upper bound of each query's KT-th best key from a scanned SAMPLE of the
+                                // gallery (gallery_tau_kernel), or NULL
   };
-  struct State { float key[KT]; int32_t idx[KT]; bool row_ok, bad; };
+  struct State { float key[KT]; int32_t idx[KT]; float lim0; bool row_ok; };
 
-  static __device__ __forceinline__ void item_begin(State& st, const Params&, const XwParams& p, const XwItem& it) {
+  static __device__ __forceinline__ void item_begin(State& st, const Params& ep, const XwParams& p, const XwItem& it) {
 #pragma unroll
     for (int s = 0; s < KT; ++s) { st.key[s] = INFINITY; st.idx[s] = -1; }
     st.row_ok = it.row < p.B;
-    st.bad = false;
+    // Nothing above the sample's KT-th best key can be among the KT best of the whole gallery.  Without this bound each
+    // of a query's ~300 lists (one per CTA and column half) warms up alone -- ~100 insertions each, serialised over the
+    // warp: 87 % of the scan's instructions; with it a list only ever takes the few globally competitive elements.
+    // A few ulps of slack keep the sample's own KT best inside, so the merged candidates still number >= KT and the
+    // proof's bound (every dropped key >= merged KT-th key) holds unchanged.
+    st.lim0 = 3.0e38f;
+    if (ep.tau0 != nullptr && st.row_ok) {
+      const float t0 = __ldg(ep.tau0 + it.row);
+      st.lim0 = t0 + fabsf(t0) * 1.6e-5f + 1e-30f;
+    }
   }
   static __device__ __forceinline__ void tile_begin(State&, const Params&, const XwParams&, const XwItem&, int, int, int) {}
 
@@ -75,24 +86,20 @@ struct XwTopK {
 #pragma unroll
       for (int j = 0; j < 32; ++j) a[j] = (j < cc) ? v[j] * ep.mult : PAD;
     }
-    // NaN-propagating min: a key that is NaN or +inf (its packed pattern is a NaN) cannot be ranked -- operand
-    // overflow, NaN inputs -- so the whole query is marked and goes to the exact engine.
+    // (NaN keys never win an fminf and never enter a list -- the exact engine drops NaN distances too.  Operands that
+    //  turn non-finite only in 16 bits are caught when they are prepared, see gallery_prepare_kernel.)
     float m4[4] = {PAD, PAD, PAD, PAD};
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         a[j + u] = __uint_as_float((__float_as_uint(a[j + u]) & ~31u) | (uint32_t)(j + u));
-        asm("min.NaN.f32 %0, %0, %1;" : "+f"(m4[u]) : "f"(a[j + u]));
+        m4[u] = fminf(m4[u], a[j + u]);
       }
     }
-    float smin;
-    asm("min.NaN.f32 %0, %1, %2;" : "=f"(smin) : "f"(m4[0]), "f"(m4[1]));
-    asm("min.NaN.f32 %0, %0, %1;" : "+f"(smin) : "f"(m4[2]));
-    asm("min.NaN.f32 %0, %0, %1;" : "+f"(smin) : "f"(m4[3]));
-    if (smin != smin || smin == -INFINITY) { st.bad = true; smin = PAD; }
-    while (__any_sync(0xffffffffu, smin < st.key[KT - 1])) {
-      const bool mine = smin < st.key[KT - 1];
+    float smin = fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3]));
+    while (__any_sync(0xffffffffu, smin < fminf(st.key[KT - 1], st.lim0))) {
+      const bool mine = smin < fminf(st.key[KT - 1], st.lim0);
       const float taken = smin;
       if (mine) insert(st, smin, cls0 + (int)(__float_as_uint(smin) & 31u));
       // next smallest element after the one just taken (lanes that did not insert are done with this slice)
@@ -108,7 +115,6 @@ struct XwTopK {
 
   static __device__ __forceinline__ void item_end(State& st, const Params& ep, const XwParams&, const XwItem& it, float*) {
     if (!st.row_ok) return;
-    if (st.bad) { st.key[KT - 1] = INFINITY; st.idx[KT - 1] = -2; }      // marker: this list dropped unrankable keys
     const int64_t base = ((int64_t)it.row * ep.n_lists + it.chunk * 2 + it.half) * KT;
 #pragma unroll
     for (int s = 0; s < KT; s += 4) {
@@ -122,11 +128,12 @@ struct XwTopK {
 // One warp per row (D <= 512, D % 8 == 0).  metric COS: out = g / max(|g|, 1e-12); L2EPS: out = g; stored as bf16
 // (any range) or fp16 (8x tighter error bound; |values| must stay well inside +-65504 -- an overflow is safe, it only
 // sends the affected queries to the exact engine).
-// bias[r] = |g|^2 - 2 eps sum(g) (L2EPS) / 0 (COS); bias[rows] (one extra slot) = max row norm via atomicMax.
+// bias[r] = |g|^2 - 2 eps sum(g) (L2EPS) / 0 (COS); two extra slots: bias[rows] = max row norm (atomicMax),
+// bias[rows + 1] = number of rows the 16-bit operand cannot represent (int).  row_bad (optional): the per-row flag.
 template <typename TI>
 __global__ void __launch_bounds__(256)
 gallery_prepare_kernel(const TI* __restrict__ in, int64_t rows, int dim, int metric, int fmt, uint16_t* __restrict__ out,
-                       float* __restrict__ bias) {
+                       float* __restrict__ bias, uint8_t* __restrict__ row_bad) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -141,19 +148,78 @@ gallery_prepare_kernel(const TI* __restrict__ in, int64_t rows, int dim, int met
   ss = warp_sum(ss); sm = warp_sum(sm);
   const float nrm = sqrtf(ss);
   const float sc = (metric == B200F_METRIC_COS) ? 1.0f / fmaxf(nrm, 1e-12f) : 1.0f;
+  // a row that is finite in fp32 but not in its 16-bit form (fp16 overflow), or that holds an infinity, cannot be
+  // ranked by the scan the way the exact engine ranks it: flag it (all-NaN-distance rows are dropped by both)
+  bool lost = false;
   if (out != nullptr) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       const int d = lane + 32 * i;
-      if (d < dim) out[row * dim + d] = (fmt == B200F_OPERAND_FP16) ? __half_as_ushort(__float2half_rn(v[i] * sc))
-                                                                    : __bfloat16_as_ushort(__float2bfloat16_rn(v[i] * sc));
+      if (d < dim) {
+        const float f = v[i] * sc;
+        const uint16_t h = (fmt == B200F_OPERAND_FP16) ? __half_as_ushort(__float2half_rn(f)) : __bfloat16_as_ushort(__float2bfloat16_rn(f));
+        const float back = (fmt == B200F_OPERAND_FP16) ? __half2float(__ushort_as_half(h)) : __bfloat162float(__ushort_as_bfloat16(h));
+        lost = lost || ((back - back != 0.f) && (f == f));    // non-finite result from a non-NaN input
+        out[row * dim + d] = h;
+      }
     }
   }
+  lost = __any_sync(0xffffffffu, lost);
+  if (lane == 0 && row_bad != nullptr) row_bad[row] = lost ? 1 : 0;
   if (bias != nullptr && lane == 0) {
     bias[row] = (metric == B200F_METRIC_COS) ? 0.f : (ss - 2.0f * GALLERY_EPS * sm);
     const float eff = (metric == B200F_METRIC_COS) ? 1.0f : nrm;
     if (eff == eff) atomicMax(reinterpret_cast<int*>(bias + rows), __float_as_int(eff));   // norms are >= 0
+    if (lost) atomicAdd(reinterpret_cast<int*>(bias + rows + 1), 1);                       // unrankable rows
   }
+}
+
+// ---- sample bound: KT-th smallest key over a query's (<= 256) sorted sample lists ------------------------------
+// One warp per query, lane l walks lists l, l + 32, ..: KT rounds of a shuffle arg-min pop the global order.
+// tau0 = +inf when the sample holds fewer than KT ranked elements (no bound).
+constexpr int GALLERY_TAU_LISTS_PER_LANE = 8;
+template <int KT>
+__global__ void __launch_bounds__(128)
+gallery_tau_kernel(const float* __restrict__ cand_key, const int32_t* __restrict__ cand_idx, int n_lists, int64_t Q,
+                   float* __restrict__ tau0) {
+  constexpr int L = GALLERY_TAU_LISTS_PER_LANE;
+  const int lane = threadIdx.x & 31;
+  const int64_t qi = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (qi >= Q) return;
+  const float* lk = cand_key + qi * n_lists * KT;
+  const int32_t* li = cand_idx + qi * n_lists * KT;
+  int pos[L];
+  float head[L];                                             // current head of each of my lists (+inf: exhausted)
+#pragma unroll
+  for (int u = 0; u < L; ++u) {
+    pos[u] = 0;
+    const int l = lane + 32 * u;
+    head[u] = (l < n_lists && li[l * KT] >= 0) ? lk[l * KT] : INFINITY;
+  }
+  float last = INFINITY;
+  bool short_of = false;
+  for (int r = 0; r < KT; ++r) {
+    float k = INFINITY; int who = 1 << 20;
+#pragma unroll
+    for (int u = 0; u < L; ++u)
+      if (head[u] < k) { k = head[u]; who = lane + 32 * u; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ok = __shfl_xor_sync(0xffffffffu, k, o);
+      const int ow = __shfl_xor_sync(0xffffffffu, who, o);
+      if (ok < k || (ok == k && ow < who)) { k = ok; who = ow; }
+    }
+    if (who >= (1 << 20)) { short_of = true; break; }
+#pragma unroll
+    for (int u = 0; u < L; ++u) {
+      if (who == lane + 32 * u) {                             // pop my list
+        ++pos[u];
+        head[u] = (pos[u] < KT && li[who * KT + pos[u]] >= 0) ? lk[who * KT + pos[u]] : INFINITY;
+      }
+    }
+    last = k;
+  }
+  if (lane == 0) tau0[qi] = short_of ? INFINITY : last;
 }
 
 // ---- select: merge lists, exact re-rank, verification ----------------------------------------------------
@@ -163,7 +229,8 @@ template <typename TG, int KT>
 __global__ void __launch_bounds__(128)
 gallery_select_kernel(const float* __restrict__ cand_key, const int32_t* __restrict__ cand_idx, int n_cand,
                       const float* __restrict__ q, const TG* __restrict__ g, const float* __restrict__ q_inv,
-                      const float* __restrict__ g_inv, const float* __restrict__ gmax_ptr, int64_t Q, int D, int k,
+                      const float* __restrict__ g_inv, const float* __restrict__ gmax_ptr,
+                      const uint8_t* __restrict__ q_bad, int64_t Q, int D, int k,
                       int metric, int fmt, float thresh, int64_t index_offset, int64_t* __restrict__ idx_out,
                       float* __restrict__ score_out, uint8_t* __restrict__ accept, uint8_t* __restrict__ redo,
                       int32_t* __restrict__ redo_count) {
@@ -176,14 +243,10 @@ gallery_select_kernel(const float* __restrict__ cand_key, const int32_t* __restr
   const int64_t qi = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const bool cosine = (metric == B200F_METRIC_COS);
-  bool marked = false;
-  for (int i = tid; i < n_cand; i += 128) {
-    ckey[i] = cand_key[qi * n_cand + i];
-    int32_t id = cand_idx[qi * n_cand + i];
-    if (id == -2) { marked = true; id = -1; }                  // a scan list dropped NaN / inf keys: no proof possible
-    cidx[i] = id;
-  }
-  const bool any_marked = __syncthreads_or(marked);
+  for (int i = tid; i < n_cand; i += 128) { ckey[i] = cand_key[qi * n_cand + i]; cidx[i] = cand_idx[qi * n_cand + i]; }
+  // no proof is possible for a query or a gallery whose 16-bit operand lost values (overflow, infinities)
+  const bool any_marked = (q_bad != nullptr && q_bad[qi] != 0) ||
+                          (gmax_ptr != nullptr && reinterpret_cast<const int*>(gmax_ptr)[1] != 0);
   // per-query constants: |q|^2, sum q
   float nq = 0.f, sq = 0.f;
   for (int d = tid; d < D; d += 128) { const float x = q[qi * D + d]; nq = fmaf(x, x, nq); sq += x; }
@@ -249,42 +312,40 @@ gallery_select_kernel(const float* __restrict__ cand_key, const int32_t* __restr
     }
   }
   __syncthreads();
-  // ---- exact re-score of the winners (reference formula, fp32).  All KT rows are read before anything is reduced:
-  // they are random 2 KB reads from HBM, and one row at a time their latencies added up to a third of the kernel.
-  {
-    float acc[KT];
+  // ---- exact re-score of the winners (reference formula, fp32), four rows at a time: the rows are random 2 KB reads
+  // from HBM, and one row per barrier round their latencies added up to half of this kernel
+  __shared__ float red_acc[4][4];
+  for (int r0 = 0; r0 < KT; r0 += 4) {
+    int id[4];
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int r = 0; r < KT; ++r) acc[r] = 0.f;
+    for (int u = 0; u < 4; ++u) id[u] = win_idx[r0 + u];
     for (int d = tid; d < D; d += 128) {
       const float x = q[qi * D + d];
-      float y[KT];
+      float y[4];
 #pragma unroll
-      for (int r = 0; r < KT; ++r) {
-        const int id = win_idx[r];
-        y[r] = (id >= 0) ? to_f32<TG>(g[(int64_t)id * D + d]) : 0.f;
-      }
+      for (int u = 0; u < 4; ++u) y[u] = (id[u] >= 0) ? to_f32<TG>(g[(int64_t)id[u] * D + d]) : 0.f;
 #pragma unroll
-      for (int r = 0; r < KT; ++r) {
-        if (cosine) acc[r] = fmaf(x, y[r], acc[r]);
-        else { const float df = x - y[r] + GALLERY_EPS; acc[r] = fmaf(df, df, acc[r]); }
+      for (int u = 0; u < 4; ++u) {
+        if (cosine) acc[u] = fmaf(x, y[u], acc[u]);
+        else { const float df = x - y[u] + GALLERY_EPS; acc[u] = fmaf(df, df, acc[u]); }
       }
     }
-    __shared__ float red_acc[4][KT];
 #pragma unroll
-    for (int r = 0; r < KT; ++r) {
-      const float a = warp_sum(acc[r]);
-      if (lane == 0) red_acc[wid][r] = a;
+    for (int u = 0; u < 4; ++u) {
+      const float a = warp_sum(acc[u]);
+      if (lane == 0) red_acc[wid][u] = a;
     }
     __syncthreads();
-    if (tid < KT) {
-      const int id = win_idx[tid];
+    if (tid < 4) {
+      const int idt = win_idx[r0 + tid];
       const float tot = (red_acc[0][tid] + red_acc[1][tid]) + (red_acc[2][tid] + red_acc[3][tid]);
       // ordering key, smaller is better: the distance / minus the cosine (as the exact engine)
       float e;
-      if (id < 0) e = INFINITY;
-      else if (cosine) e = -(tot * (q_inv ? q_inv[qi] : 1.0f) * (g_inv ? g_inv[id] : 1.0f));
+      if (idt < 0) e = INFINITY;
+      else if (cosine) e = -(tot * (q_inv ? q_inv[qi] : 1.0f) * (g_inv ? g_inv[idt] : 1.0f));
       else e = sqrtf(tot);
-      ex_key[tid] = e;
+      ex_key[r0 + tid] = e;
     }
     __syncthreads();
   }

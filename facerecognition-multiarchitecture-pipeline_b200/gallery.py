@@ -59,7 +59,7 @@ class PreparedGallery:
         self.operand_fmt = operand_fmt
         self.g16 = torch.empty(self.N, self.D, dtype=torch.float16 if operand_fmt == _lib.OPERAND_FP16 else torch.bfloat16,
                                device=g.device)
-        self.bias = torch.empty(self.N + 1, dtype=torch.float32, device=g.device)
+        self.bias = torch.empty(self.N + 2, dtype=torch.float32, device=g.device)
         check(lib.b200f_gallery_prepare(ptr(g), dtype_code(g), self.N, self.D, _METRICS[metric], operand_fmt,
                                         ptr(self.g16), ptr(self.bias), stream_ptr(g.device)), "b200f_gallery_prepare")
 

@@ -167,8 +167,9 @@ int b200f_gallery_topk(const void* q, const void* g, int dtype,
 
 /* K4 on the tensor cores (fp32 queries / gallery, D % 8 == 0, D <= 512, sm_100):
  *   b200f_gallery_prepare   builds the scan operand of a gallery ONCE: g16 [N,D] bf16 or fp16 (the rows for L2EPS, the
- *                           L2-normalised rows for COS) and bias [N+1] fp32 (|g|^2 - 2e-6 sum g per row for L2EPS, 0 for
- *                           COS; the extra slot holds the largest row norm, used by the error bound).
+ *                           L2-normalised rows for COS) and bias [N+2] fp32 (|g|^2 - 2e-6 sum g per row for L2EPS, 0 for
+ *                           COS; two extra slots: the largest row norm, used by the error bound, and the number of
+ *                           rows the 16-bit operand cannot represent -- if non-zero every query goes to the exact engine).
  *   b200f_gallery_topk_tc   bf16 tcgen05 scan of g16 (queries resident in shared memory, gallery streamed once: HBM-bound
  *                           for Q <= ~250) keeping 8/16/32 candidates per query, exact fp32 re-rank of the candidates
  *                           against g with the reference formula, and a proof per query that nothing outside the
