@@ -414,9 +414,15 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
       CUtensorMap tg_k;
       rc = tmap_kmajor(&tg_k, G, cnt, B, pl.ldg, XW_WROWS); if (rc) return rc;
       const XwPlan qw = xw_plan(D, cnt, qg.pair);
-      XwDw::Params ew{coef, static_cast<const __half*>(wh), dw, c0, D};
-      rc = (qw.pair == 2) ? launch_xw<2, XW_MK, XwDw>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW (cta pair)")
-                          : launch_xw<1, XW_MK, XwDw>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW");
+      if (D == 512) {                                       // the head's shape: constant row stride in the epilogue
+        XwDw<512>::Params ew{coef, static_cast<const __half*>(wh), dw, c0, D};
+        rc = (qw.pair == 2) ? launch_xw<2, XW_MK, XwDw<512>>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW (cta pair)")
+                            : launch_xw<1, XW_MK, XwDw<512>>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW");
+      } else {
+        XwDw<0>::Params ew{coef, static_cast<const __half*>(wh), dw, c0, D};
+        rc = (qw.pair == 2) ? launch_xw<2, XW_MK, XwDw<0>>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW (cta pair)")
+                            : launch_xw<1, XW_MK, XwDw<0>>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW");
+      }
       if (rc) return rc;
     } else {
       // batch > 512: x_hat^T cannot stay resident, both operands stream through the generic core:

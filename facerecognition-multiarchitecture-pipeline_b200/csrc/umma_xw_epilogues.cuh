@@ -340,7 +340,9 @@ struct XwBwdGT {
 // The thread owns feature d: for a fixed class its warp writes 128 contiguous bytes of the dW row.
 // (Measured and rejected: fetching the w_hat values one slice ahead -- into registers, or as 16 B vectors through
 //  warp-private shared memory -- made this kernel 50 % slower than loading them where they are used.)
+template <int LD>                                             // row stride of dW / w_hat known at compile time (512), or 0
 struct XwDw {
+  static __device__ __forceinline__ int64_t stride(int ld) { return LD ? (int64_t)LD : (int64_t)ld; }
   struct Params { const float2* coef; const __half* wh; float* dw; int64_t c0; int ld; };
   struct State { bool row_ok; };
   static __device__ __forceinline__ void item_begin(State& st, const Params&, const XwParams& p, const XwItem& it) {
@@ -358,7 +360,7 @@ struct XwDw {
     const int64_t d_base = it.row - (it.quad * 32 + it.lane);         // first feature of this CTA
     int nbytes = (int)min((int64_t)XW_M, (int64_t)p.B - d_base) * 2;
     nbytes &= ~15;
-    const __half* a = ep.wh + (ep.c0 + c) * ep.ld + d_base;
+    const __half* a = ep.wh + (ep.c0 + c) * stride(ep.ld) + d_base;
     if (nbytes >= 16 && (reinterpret_cast<uintptr_t>(a) & 15) == 0)
       asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(nbytes) : "memory");
     if ((c & 15) == 0)                                                // 16 coefficients = one 128 B line
@@ -368,22 +370,25 @@ struct XwDw {
                                                float (&v)[32], int cls0) {
     if (!st.row_ok) return;
     const int cc = min(32, p.C - cls0);
-    const int64_t base = (ep.c0 + cls0) * ep.ld + it.row;
+    const int64_t ldw = stride(ep.ld);                        // constant stride: loads / stores use immediate offsets
+    const int64_t base = (ep.c0 + cls0) * ldw + it.row;
     const float2* cf = ep.coef + ep.c0 + cls0;
     if (cc == 32) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float2 c2 = __ldg(cf + j);
-        const float wv = __half2float(__ldg(ep.wh + base + (int64_t)j * ep.ld));
-        ep.dw[base + (int64_t)j * ep.ld] = c2.x * fmaf(-wv, c2.y, v[j]);
+      for (int j = 0; j < 32; j += 2) {
+        const float4 c4 = __ldg(reinterpret_cast<const float4*>(cf + j));   // two classes' coefficients per load
+        const float w0 = __half2float(__ldg(ep.wh + base + (int64_t)j * ldw));
+        const float w1 = __half2float(__ldg(ep.wh + base + (int64_t)(j + 1) * ldw));
+        ep.dw[base + (int64_t)j * ldw] = c4.x * fmaf(-w0, c4.y, v[j]);
+        ep.dw[base + (int64_t)(j + 1) * ldw] = c4.z * fmaf(-w1, c4.w, v[j + 1]);
       }
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         if (j < cc) {
           const float2 c2 = __ldg(cf + j);
-          const float wv = __half2float(__ldg(ep.wh + base + (int64_t)j * ep.ld));
-          ep.dw[base + (int64_t)j * ep.ld] = c2.x * fmaf(-wv, c2.y, v[j]);
+          const float wv = __half2float(__ldg(ep.wh + base + (int64_t)j * ldw));
+          ep.dw[base + (int64_t)j * ldw] = c2.x * fmaf(-wv, c2.y, v[j]);
         }
       }
     }
