@@ -33,6 +33,30 @@ void count_launch();   // diagnostic counter behind b200f_launch_count()
     ::b200f::count_launch();                                                         \
   } while (0)
 
+// ---- programmatic dependent launch -----------------------------------------------------------------------
+// Every kernel of the head step is short (3-100 us) and the step is a chain of a dozen of them: with plain stream
+// order each boundary costs the launch latency plus the next kernel's prologue (barrier init, TMEM allocation,
+// descriptor prefetch).  Kernels therefore (1) allow their successor to be scheduled right away -- pdl_trigger() at
+// their top -- and (2) run their prologue, then pdl_wait(), which returns once the predecessor grid has completed and
+// its memory is visible, before the first access to anything a predecessor wrote.  Launches carry the
+// programmatic-stream-serialization attribute (launch_pdl); without it both calls are no-ops.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled();            // tunable "pdl" (default on)
+void pdl_set(bool on);
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -103,6 +103,7 @@ template <typename TI, typename TO, int VPL>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 l2norm_rows_vec_kernel(const TI* __restrict__ in, int64_t rows, int dim, float eps, float out_scale,
                        float* __restrict__ inv_norm, TO* __restrict__ out) {
+  pdl_trigger(); pdl_wait();
   constexpr int N = Vec16<TI>::N;
   const int lane = threadIdx.x & 31;
   const int64_t row0 = ((int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5)) * ROWS_PER_WARP;
@@ -151,6 +152,7 @@ template <typename TI, typename TO>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 l2norm_rows_512x16_kernel(const TI* __restrict__ in, int64_t rows, float eps, float out_scale,
                           float* __restrict__ inv_norm, TO* __restrict__ out) {
+  pdl_trigger(); pdl_wait();
   static_assert(sizeof(TI) == 2 && sizeof(TO) == 2, "16-bit rows only");
   const int lane = threadIdx.x & 31;
   const int64_t row0 = ((int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5)) * ROWS_PER_WARP;
@@ -206,6 +208,7 @@ template <typename TI, typename TO>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 l2norm_rows_generic_kernel(const TI* __restrict__ in, int64_t rows, int dim, float eps, float out_scale,
                            float* __restrict__ inv_norm, TO* __restrict__ out) {
+  pdl_trigger(); pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -227,6 +230,7 @@ template <typename T, bool PRENORM, int VPL>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 l2norm_bwd_vec_kernel(const T* __restrict__ v, float v_scale, const float* __restrict__ inv_norm, const float* dvhat,
                       int64_t rows, int dim, float* dv) {
+  pdl_trigger(); pdl_wait();
   constexpr int N = Vec16<T>::N;                // 8 (16-bit) or 4 (fp32) elements per 16-byte vector of v
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
@@ -273,6 +277,7 @@ template <typename T, bool PRENORM>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 l2norm_bwd_generic_kernel(const T* __restrict__ v, float v_scale, const float* __restrict__ inv_norm,
                           const float* dvhat, int64_t rows, int dim, float* dv) {
+  pdl_trigger(); pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -294,7 +299,7 @@ static inline void launch_l2norm_rows(const TI* in, int64_t rows, int dim, float
   constexpr int N = Vec16<TI>::N;
   if constexpr (sizeof(TI) == 2 && sizeof(TO) == 2) {
     if (dim == 512 && reinterpret_cast<uintptr_t>(in) % 32 == 0 && (!out || reinterpret_cast<uintptr_t>(out) % 32 == 0)) {
-      l2norm_rows_512x16_kernel<TI, TO><<<(unsigned)ceil_div(rows, ROWS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, st>>>(
+      launch_pdl(l2norm_rows_512x16_kernel<TI, TO>, dim3((unsigned)ceil_div(rows, ROWS_PER_BLOCK)), dim3(WARPS_PER_BLOCK * 32), 0, st, 
           in, rows, eps, out_scale, inv_norm, out);
       return;
     }
@@ -304,11 +309,11 @@ static inline void launch_l2norm_rows(const TI* in, int64_t rows, int dim, float
   if (vec) {
     const int nvec = dim / N;
     const unsigned grid = (unsigned)ceil_div(rows, ROWS_PER_BLOCK);
-    if (nvec <= 32) l2norm_rows_vec_kernel<TI, TO, 1><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(in, rows, dim, eps, out_scale, inv_norm, out);
-    else if (nvec <= 64) l2norm_rows_vec_kernel<TI, TO, 2><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(in, rows, dim, eps, out_scale, inv_norm, out);
-    else l2norm_rows_vec_kernel<TI, TO, 4><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(in, rows, dim, eps, out_scale, inv_norm, out);
+    if (nvec <= 32) launch_pdl(l2norm_rows_vec_kernel<TI, TO, 1>, dim3(grid), dim3(WARPS_PER_BLOCK * 32), 0, st, in, rows, dim, eps, out_scale, inv_norm, out);
+    else if (nvec <= 64) launch_pdl(l2norm_rows_vec_kernel<TI, TO, 2>, dim3(grid), dim3(WARPS_PER_BLOCK * 32), 0, st, in, rows, dim, eps, out_scale, inv_norm, out);
+    else launch_pdl(l2norm_rows_vec_kernel<TI, TO, 4>, dim3(grid), dim3(WARPS_PER_BLOCK * 32), 0, st, in, rows, dim, eps, out_scale, inv_norm, out);
   } else {
-    l2norm_rows_generic_kernel<TI, TO><<<(unsigned)ceil_div(rows, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, 0, st>>>(
+    launch_pdl(l2norm_rows_generic_kernel<TI, TO>, dim3((unsigned)ceil_div(rows, WARPS_PER_BLOCK)), dim3(WARPS_PER_BLOCK * 32), 0, st, 
         in, rows, dim, eps, out_scale, inv_norm, out);
   }
 }
@@ -323,11 +328,11 @@ static inline void launch_l2norm_bwd(const T* v, float v_scale, const float* inv
   const unsigned grid = (unsigned)ceil_div(rows, WARPS_PER_BLOCK);
   if (vec) {
     const int nvec = dim / N;
-    if (nvec <= 32) l2norm_bwd_vec_kernel<T, PRENORM, 1><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(v, v_scale, inv_norm, dvhat, rows, dim, dv);
-    else if (nvec <= 64) l2norm_bwd_vec_kernel<T, PRENORM, 2><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(v, v_scale, inv_norm, dvhat, rows, dim, dv);
-    else l2norm_bwd_vec_kernel<T, PRENORM, 4><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(v, v_scale, inv_norm, dvhat, rows, dim, dv);
+    if (nvec <= 32) launch_pdl(l2norm_bwd_vec_kernel<T, PRENORM, 1>, dim3(grid), dim3(WARPS_PER_BLOCK * 32), 0, st, v, v_scale, inv_norm, dvhat, rows, dim, dv);
+    else if (nvec <= 64) launch_pdl(l2norm_bwd_vec_kernel<T, PRENORM, 2>, dim3(grid), dim3(WARPS_PER_BLOCK * 32), 0, st, v, v_scale, inv_norm, dvhat, rows, dim, dv);
+    else launch_pdl(l2norm_bwd_vec_kernel<T, PRENORM, 4>, dim3(grid), dim3(WARPS_PER_BLOCK * 32), 0, st, v, v_scale, inv_norm, dvhat, rows, dim, dv);
   } else {
-    l2norm_bwd_generic_kernel<T, PRENORM><<<grid, WARPS_PER_BLOCK * 32, 0, st>>>(v, v_scale, inv_norm, dvhat, rows, dim, dv);
+    launch_pdl(l2norm_bwd_generic_kernel<T, PRENORM>, dim3(grid), dim3(WARPS_PER_BLOCK * 32), 0, st, v, v_scale, inv_norm, dvhat, rows, dim, dv);
   }
 }
 
@@ -337,6 +342,7 @@ static __global__ void __launch_bounds__(1024)
 loss_kernel(const float* __restrict__ row_stats, int64_t B, float s_eff, float ls_eps,
             double C_total, float* __restrict__ lse_out, float* __restrict__ loss_out,
             float* __restrict__ pq_norm2_out) {
+  pdl_trigger(); pdl_wait();
   __shared__ double sh_loss[32], sh_pq[32];
   double loss = 0.0, pq = 0.0;
   const double eps = (double)ls_eps;
@@ -372,6 +378,7 @@ loss_kernel(const float* __restrict__ row_stats, int64_t B, float s_eff, float l
 static __global__ void hook_scale_kernel(const float* __restrict__ pq_norm2, const float* __restrict__ upstream,
                                          double B, float s_eff, int hook_enabled, float max_grad_norm,
                                          int phase, int epoch, float* __restrict__ out3) {
+  pdl_trigger(); pdl_wait();
   const double up = (upstream != nullptr) ? (double)*upstream : 1.0;
   const double base = (double)s_eff / B;
   const double n = fabs(up) * base * sqrt((double)*pq_norm2);

@@ -23,6 +23,10 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+static std::atomic<int> g_pdl{1};
+bool pdl_enabled() { return g_pdl.load(std::memory_order_relaxed) != 0; }
+void pdl_set(bool on) { g_pdl.store(on ? 1 : 0, std::memory_order_relaxed); }
+
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 unsigned long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
@@ -115,8 +119,8 @@ int b200f_l2norm_bwd(const void* v, int dtype, float v_scale, const float* inv_n
 int b200f_arcface_loss(const float* row_stats, int64_t B, const b200f_head_cfg* cfg, float* lse, float* loss,
                        float* pq_norm2, void* stream) {
   if (!row_stats || !cfg || B <= 0) return fail(B200F_ERR_ARG, "arcface_loss: bad argument");
-  rowops::loss_kernel<<<1, 1024, 0, as_stream(stream)>>>(row_stats, B, cfg->s_eff, cfg->label_smoothing,
-                                                         (double)cfg->num_classes_total, lse, loss, pq_norm2);
+  launch_pdl(rowops::loss_kernel, dim3(1), dim3(1024), 0, as_stream(stream), row_stats, B, cfg->s_eff,
+             cfg->label_smoothing, (double)cfg->num_classes_total, lse, loss, pq_norm2);
   B200F_LAUNCH_OK("loss_kernel");
   return B200F_OK;
 }
@@ -125,8 +129,8 @@ int b200f_arcface_hook_scale(const float* pq_norm2, const float* upstream, int64
                              int hook_enabled, float max_grad_norm, int phase, int epoch, float* out4,
                              void* stream) {
   if (!pq_norm2 || !out4 || B <= 0) return fail(B200F_ERR_ARG, "arcface_hook_scale: bad argument");
-  rowops::hook_scale_kernel<<<1, 1, 0, as_stream(stream)>>>(pq_norm2, upstream, (double)B, s_eff, hook_enabled,
-                                                            max_grad_norm, phase, epoch, out4);
+  launch_pdl(rowops::hook_scale_kernel, dim3(1), dim3(1), 0, as_stream(stream), pq_norm2, upstream, (double)B, s_eff,
+             hook_enabled, max_grad_norm, phase, epoch, out4);
   B200F_LAUNCH_OK("hook_scale_kernel");
   return B200F_OK;
 }

@@ -15,6 +15,7 @@
 // Work items are (m_tile, n_tile, k_split) with m fastest so CTAs that run concurrently share the same
 // B tiles through L2.  The stage-specific work lives in the Epilogue policy.
 #pragma once
+#include "common.cuh"
 #include "umma_core.cuh"
 
 namespace b200f {
@@ -83,6 +84,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
   const int lane = threadIdx.x & 31;
   const int total_work = p.m_tiles * p.n_tiles * p.k_splits;
 
+  pdl_trigger();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
@@ -95,6 +97,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp == 0) {
     // ================= TMA producer =================

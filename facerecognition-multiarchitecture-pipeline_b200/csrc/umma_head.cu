@@ -91,7 +91,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   const int work = p.m_tiles * p.n_tiles * p.k_splits;
   int grid = num_sms();
   if (grid > work) grid = work;
-  kern<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tb, p, ep);
+  cudaError_t e = launch_pdl(kern, dim3((unsigned)grid), dim3(NUM_THREADS), SMEM_BYTES, st, ta, tb, p, ep);
+  if (e != cudaSuccess) return fail(B200F_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
   B200F_LAUNCH_OK(what);
   return B200F_OK;
 }
@@ -101,6 +102,7 @@ __global__ void __launch_bounds__(256)
 reduce_row_partials_kernel(const float* __restrict__ part, int n_parts, int64_t B, const float* __restrict__ cos_part,
                            int n_cos, float* __restrict__ row_stats, float* __restrict__ row_best,
                            int64_t* __restrict__ row_argmax, float* __restrict__ cos_minmax) {
+  pdl_trigger(); pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row < B) {
@@ -144,6 +146,7 @@ reduce_row_partials_kernel(const float* __restrict__ part, int n_parts, int64_t 
 // dst (=|+=) scale / *dev_scale * sum_s part[s], fixed order
 __global__ void reduce_splits_kernel(const float* __restrict__ part, int n_splits, int64_t n, float* __restrict__ dst,
                                      int accumulate, float scale, const float* __restrict__ dev_scale) {
+  pdl_trigger(); pdl_wait();
   const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
   const float sc = (dev_scale != nullptr) ? scale / __ldg(dev_scale) : scale;
@@ -161,6 +164,7 @@ __global__ void reduce_splits_kernel(const float* __restrict__ part, int n_split
 __global__ void reduce_r_kernel(const float* __restrict__ r_part, int n_rb, int64_t ldr, int64_t cnt,
                                 const float* __restrict__ inv_nw, const float* __restrict__ grad4, float S,
                                 float2* __restrict__ coef) {
+  pdl_trigger(); pdl_wait();
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cnt) return;
   float s = 0.f;
@@ -255,9 +259,10 @@ static int launch_xw(const CUtensorMap& tx, const CUtensorMap& tw, const XwPlan&
   p.idesc = make_idesc(fmt, fmt, MODE == XW_MK, false, XW_M * PAIR, XW_WROWS * PAIR);   // A = resident except XW_SWAP (both K-major)
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)q.grid); cfg.blockDim = dim3(XW_THREADS); cfg.dynamicSmemBytes = XW_SMEM_BYTES; cfg.stream = st;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = PAIR; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, XwKernel<PAIR, MODE, Epi>::fn, tx, tw, p, ep);
   if (e != cudaSuccess) return fail(B200F_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
   B200F_LAUNCH_OK(what);
@@ -368,7 +373,7 @@ int head_fwd(const void* xh, const void* wh, const int64_t* label, int64_t B, in
   rc = (q.pair == 2) ? launch_xw<2, XW_KK, XwFwd>(tx, tw, q, B, C, D, ep, st, "umma K2 arcface_fwd (cta pair)")
                      : launch_xw<1, XW_KK, XwFwd>(tx, tw, q, B, C, D, ep, st, "umma K2 arcface_fwd");
   if (rc) return rc;
-  reduce_row_partials_kernel<<<(unsigned)ceil_div(B, 8), 256, 0, st>>>(ep.part, q.n_chunks, B, ep.cos_part,
+  launch_pdl(reduce_row_partials_kernel, dim3((unsigned)ceil_div(B, 8)), dim3(256), 0, st, ep.part, q.n_chunks, B, ep.cos_part,
                                                                       q.items * q.pair * XW_EPI_WARPS, row_stats, row_best,
                                                                       row_argmax, cos_minmax);
   B200F_LAUNCH_OK("reduce_row_partials_kernel");
@@ -407,7 +412,7 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
     // --- K3b: dW[c0 + c, d] = inv_nw_c (sum_b G^T[c, b] x_hat[b, d] - w_hat[c, d] r_c), computed transposed (the thread
     //     owns a feature d, so a warp writes 128 contiguous bytes of a dW row) with the normalise-backward fused
     float2* coef = reinterpret_cast<float2*>(ws + pl.off_coef);
-    reduce_r_kernel<<<(unsigned)ceil_div(cnt, 256), 256, 0, st>>>(r_part, qg.m_groups * 2, pl.Cc, cnt,
+    launch_pdl(reduce_r_kernel, dim3((unsigned)ceil_div(cnt, 256)), dim3(256), 0, st, r_part, qg.m_groups * 2, pl.Cc, cnt,
                                                                 inv_nw + c0, grad4, S, coef + c0);
     B200F_LAUNCH_OK("umma reduce_r_kernel");
     if (pl.fused_dw) {                                      // x_hat^T resident, G^T rows streamed
@@ -445,7 +450,7 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
     rc = launch_gemm<true, true, EpiStore>(tg_mn, tw_mn, px, ex, st, "umma K3c dX");
     if (rc) return rc;
     const int64_t n = B * (int64_t)D;
-    reduce_splits_kernel<<<(unsigned)ceil_div(n / 4, 256), 256, 0, st>>>(dxpart, px.k_splits, n, dxhat, chunk_no > 0,
+    launch_pdl(reduce_splits_kernel, dim3((unsigned)ceil_div(n / 4, 256)), dim3(256), 0, st, dxpart, px.k_splits, n, dxhat, chunk_no > 0,
                                                                         1.0f / S, grad4 + 3);
     B200F_LAUNCH_OK("umma reduce_splits_kernel");
   }
@@ -502,10 +507,10 @@ int gallery_prepare(const void* g, int dtype, int64_t N, int D, int metric, int 
   if (bias) B200F_CUDA_OK(cudaMemsetAsync(bias + N, 0, 2 * sizeof(float), st));
   const unsigned grid = (unsigned)ceil_div(N, 8);
   if (dtype == B200F_F32)
-    gallery_prepare_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(g), N, D, metric, fmt,
+    launch_pdl(gallery_prepare_kernel<float>, dim3(grid), dim3(256), 0, st, static_cast<const float*>(g), N, D, metric, fmt,
                                                        static_cast<uint16_t*>(g16), bias, nullptr);
   else
-    gallery_prepare_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(g), N, D, metric, fmt,
+    launch_pdl(gallery_prepare_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(g), N, D, metric, fmt,
                                                                static_cast<uint16_t*>(g16), bias, nullptr);
   B200F_LAUNCH_OK("gallery_prepare_kernel");
   return B200F_OK;
@@ -528,7 +533,7 @@ static int gallery_scan_kt(const GalleryScanPlan& gp, const CUtensorMap& tx, con
     int rcs = (gp.qs.pair == 2) ? launch_xw<2, XW_KK, XwTopK<KT>>(tx, tw, gp.qs, Q, gp.n_sample, D, es, st, "umma K4 gallery sample scan (cta pair)", mfmt)
                                 : launch_xw<1, XW_KK, XwTopK<KT>>(tx, tw, gp.qs, Q, gp.n_sample, D, es, st, "umma K4 gallery sample scan", mfmt);
     if (rcs) return rcs;
-    gallery_tau_kernel<KT><<<(unsigned)ceil_div(Q, 4), 128, 0, st>>>(skey, sidx, es.n_lists, Q, tau0);
+    launch_pdl(gallery_tau_kernel<KT>, dim3((unsigned)ceil_div(Q, 4)), dim3(128), 0, st, skey, sidx, es.n_lists, Q, tau0);
     B200F_LAUNCH_OK("gallery_tau_kernel");
     ep.tau0 = tau0;
   }
@@ -565,7 +570,7 @@ int gallery_scan_select(const float* q, const float* g, const void* g16, const f
   int32_t* sidx = reinterpret_cast<int32_t*>(ws + gp.off_sidx);
   float* tau0 = reinterpret_cast<float*>(ws + gp.off_tau);
   uint8_t* qbad = reinterpret_cast<uint8_t*>(ws + gp.off_qbad);
-  gallery_prepare_kernel<float><<<(unsigned)ceil_div(Q, 8), 256, 0, st>>>(q, Q, D, B200F_METRIC_L2EPS, fmt, q16, nullptr, qbad);
+  launch_pdl(gallery_prepare_kernel<float>, dim3((unsigned)ceil_div(Q, 8)), dim3(256), 0, st, q, Q, D, B200F_METRIC_L2EPS, fmt, q16, nullptr, qbad);
   B200F_LAUNCH_OK("gallery_prepare_kernel (queries)");
   CUtensorMap tx, tw;
   int rc = tmap_kmajor(&tx, q16, Q, D, D, XW_M); if (rc) return rc;
@@ -661,6 +666,7 @@ int b200f_set_tunable(const char* name, int value) {
   if (!name) return -1;
   const std::string n(name);
   if (n == "pair") return b200f_umma_set_pair(value);
+  if (n == "pdl") { const int old_v = pdl_enabled() ? 1 : 0; if (value == 0 || value == 1) pdl_set(value != 0); return old_v; }
   if (n == "xw_prefetch") { if (value < 0) return g_prefetch.load(); return g_prefetch.exchange(value); }
   if (n == "g_chunk_mb") { if (value < 1) return g_chunk_mb.load(); return g_chunk_mb.exchange(value); }
   return -1;

@@ -19,6 +19,7 @@
 // The Epilogue policy sees every 32-column slice of the accumulators plus item begin / end hooks, so per-row
 // statistics stay in registers across all class tiles of an item (one partial record per row and chunk).
 #pragma once
+#include "common.cuh"
 #include "umma_core.cuh"
 
 namespace b200f {
@@ -219,6 +220,7 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
   const int n_clusters = gridDim.x / PAIR;
   const int items = p.m_groups * p.n_chunks;
 
+  pdl_trigger();                                             // the next kernel may be scheduled behind this one
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x);
     tma_prefetch_desc(&tm_w);
@@ -234,6 +236,7 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
   if (PAIR == 2) cluster_sync_all();                         // the peer's barriers exist before anyone signals them
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                                // prologue done; predecessor grids complete from here on
 
   if (warp == 0) {
     // ================= TMA producer (both CTAs) =================

@@ -134,6 +134,7 @@ template <typename TI>
 __global__ void __launch_bounds__(256)
 gallery_prepare_kernel(const TI* __restrict__ in, int64_t rows, int dim, int metric, int fmt, uint16_t* __restrict__ out,
                        float* __restrict__ bias, uint8_t* __restrict__ row_bad) {
+  pdl_trigger(); pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -182,6 +183,7 @@ template <int KT>
 __global__ void __launch_bounds__(128)
 gallery_tau_kernel(const float* __restrict__ cand_key, const int32_t* __restrict__ cand_idx, int n_lists, int64_t Q,
                    float* __restrict__ tau0) {
+  pdl_trigger(); pdl_wait();
   constexpr int L = GALLERY_TAU_LISTS_PER_LANE;
   const int lane = threadIdx.x & 31;
   const int64_t qi = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -234,6 +236,7 @@ gallery_select_kernel(const float* __restrict__ cand_key, const int32_t* __restr
                       int metric, int fmt, float thresh, int64_t index_offset, int64_t* __restrict__ idx_out,
                       float* __restrict__ score_out, uint8_t* __restrict__ accept, uint8_t* __restrict__ redo,
                       int32_t* __restrict__ redo_count) {
+  pdl_trigger(); pdl_wait();
   extern __shared__ uint8_t sel_smem[];
   float* ckey = reinterpret_cast<float*>(sel_smem);
   int32_t* cidx = reinterpret_cast<int32_t*>(ckey + n_cand);
