@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--pair", type=int, default=0, help="1 = single CTAs, 2 = cta_group::2 CTA pairs (default)")
     ap.add_argument("--g-chunk-mb", type=int, default=0, help="logit-gradient buffer budget per class chunk (MB)")
     ap.add_argument("--pdl", type=int, default=-1, help="0 / 1: programmatic dependent launch between the step's kernels (default on)")
+    ap.add_argument("--tune", action="append", default=[], metavar="NAME=INT",
+                    help="b200f_set_tunable(NAME, INT) before the run (experiments; see csrc/umma_head.cu)")
     ap.add_argument("--no-gallery", action="store_true")
     return ap.parse_args()
 
@@ -147,6 +149,9 @@ def run_b200(args):
         lib.b200f_set_tunable(b"g_chunk_mb", args.g_chunk_mb)
     if args.pdl in (0, 1):
         lib.b200f_set_tunable(b"pdl", args.pdl)
+    for kv in args.tune:
+        name, _, val = kv.partition("=")
+        lib.b200f_set_tunable(name.encode(), int(val))
     cfgw = CFG3 if world == 1 else CFG4
     B, C_total, D = cfgw["B"], cfgw["C"], cfgw["D"]
     c_lo, c_hi = parallel.shard_bounds(C_total, world, rank)

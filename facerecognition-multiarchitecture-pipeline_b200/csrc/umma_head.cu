@@ -174,16 +174,19 @@ __global__ void reduce_r_kernel(const float* __restrict__ r_part, int n_rb, int6
 
 // ---- X-stationary kernel: launch geometry ---------------------------------------------------------
 static std::atomic<int> g_pair{2};                 // 2 = tcgen05 cta_group::2 CTA pairs, 1 = single CTAs
+static std::atomic<int> g_k3b_class_major{1};       // K3b epilogue: 1 = thread owns a class row (XwDwT), 0 = a feature (XwDw)
+static std::atomic<int> g_k3b_ablate{0};            // probe: 1 = no w_hat loads, 2 = no dW stores (WRONG results)
+static std::atomic<int> g_k3b_reverse{1};           // K3b walks each chunk last tile first
 static std::atomic<int> g_prefetch{0};             // L2 prefetch distance of the xw producer (stages)
 static std::atomic<int> g_chunk_mb{112};           // budget of the fp16 logit-gradient buffer G per class chunk
 
 // MODE of the X-stationary kernel: 0 = both operands K-major (K2, gallery scan, probes); 1 = resident operand
 // MN-major, streamed operand K-major (K3b: x_hat^T resident, class-major G rows streamed); 2 = K-major operands with
 // the streamed one on the A side of the MMA (K3a: accumulator lanes = classes).
-enum { XW_KK = 0, XW_MK = 1, XW_SWAP = 2 };
+enum { XW_KK = 0, XW_MK = 1, XW_SWAP = 2, XW_SWAP_MK = 3 };   // _MK: resident operand MN-major; SWAP: streamed rows on the A side
 template <int PAIR, int MODE, class Epi>
 struct XwKernel {
-  static constexpr auto fn = xw_kernel<PAIR, MODE == XW_MK, false, MODE == XW_SWAP, Epi>;
+  static constexpr auto fn = xw_kernel<PAIR, MODE == XW_MK || MODE == XW_SWAP_MK, false, MODE == XW_SWAP || MODE == XW_SWAP_MK, Epi>;
 };
 
 template <int PAIR, int MODE, class Epi>
@@ -248,7 +251,8 @@ static XwPlan xw_plan(int64_t B, int64_t C, int pair, int max_chunks = 0) {
 
 template <int PAIR, int MODE, class Epi>
 static int launch_xw(const CUtensorMap& tx, const CUtensorMap& tw, const XwPlan& q, int64_t B, int64_t C, int D,
-                     const typename Epi::Params& ep, cudaStream_t st, const char* what, uint32_t fmt = FMT_F16) {
+                     const typename Epi::Params& ep, cudaStream_t st, const char* what, uint32_t fmt = FMT_F16,
+                     bool reverse = false) {
   int rc = xw_set_smem<PAIR, MODE, Epi>(); if (rc) return rc;
   XwParams p{};
   p.B = (int)B; p.C = (int)C; p.D = D;
@@ -256,7 +260,8 @@ static int launch_xw(const CUtensorMap& tx, const CUtensorMap& tw, const XwPlan&
   p.m_groups = q.m_groups; p.n_tiles = q.n_tiles; p.n_chunks = q.n_chunks;
   p.prefetch = g_prefetch.load(std::memory_order_relaxed);
   p.tn = XW_WROWS * PAIR;
-  p.idesc = make_idesc(fmt, fmt, MODE == XW_MK, false, XW_M * PAIR, XW_WROWS * PAIR);   // A = resident except XW_SWAP (both K-major)
+  p.reverse = reverse ? 1 : 0;
+  p.idesc = make_idesc(fmt, fmt, MODE == XW_MK, MODE == XW_SWAP_MK, XW_M * PAIR, XW_WROWS * PAIR);   // A = resident, except SWAP modes
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)q.grid); cfg.blockDim = dim3(XW_THREADS); cfg.dynamicSmemBytes = XW_SMEM_BYTES; cfg.stream = st;
   cudaLaunchAttribute at[2];
@@ -419,14 +424,20 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
       CUtensorMap tg_k;
       rc = tmap_kmajor(&tg_k, G, cnt, B, pl.ldg, XW_WROWS); if (rc) return rc;
       const XwPlan qw = xw_plan(D, cnt, qg.pair);
+      const bool k3b_rev = g_k3b_reverse.load(std::memory_order_relaxed) != 0;   // read K3a's freshest G^T rows first
+      if (g_k3b_class_major.load(std::memory_order_relaxed)) {   // thread owns a class row: vector loads / stores
+        XwDwT::Params ew{coef, static_cast<const __half*>(wh), dw, c0, D, g_k3b_ablate.load(std::memory_order_relaxed)};
+        rc = (qw.pair == 2) ? launch_xw<2, XW_SWAP_MK, XwDwT>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW class-major (cta pair)", FMT_F16, k3b_rev)
+                            : launch_xw<1, XW_SWAP_MK, XwDwT>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW class-major", FMT_F16, k3b_rev);
+      } else
       if (D == 512) {                                       // the head's shape: constant row stride in the epilogue
         XwDw<512>::Params ew{coef, static_cast<const __half*>(wh), dw, c0, D};
-        rc = (qw.pair == 2) ? launch_xw<2, XW_MK, XwDw<512>>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW (cta pair)")
-                            : launch_xw<1, XW_MK, XwDw<512>>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW");
+        rc = (qw.pair == 2) ? launch_xw<2, XW_MK, XwDw<512>>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW (cta pair)", FMT_F16, k3b_rev)
+                            : launch_xw<1, XW_MK, XwDw<512>>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW", FMT_F16, k3b_rev);
       } else {
         XwDw<0>::Params ew{coef, static_cast<const __half*>(wh), dw, c0, D};
-        rc = (qw.pair == 2) ? launch_xw<2, XW_MK, XwDw<0>>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW (cta pair)")
-                            : launch_xw<1, XW_MK, XwDw<0>>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW");
+        rc = (qw.pair == 2) ? launch_xw<2, XW_MK, XwDw<0>>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW (cta pair)", FMT_F16, k3b_rev)
+                            : launch_xw<1, XW_MK, XwDw<0>>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW", FMT_F16, k3b_rev);
       }
       if (rc) return rc;
     } else {
@@ -667,6 +678,9 @@ int b200f_set_tunable(const char* name, int value) {
   const std::string n(name);
   if (n == "pair") return b200f_umma_set_pair(value);
   if (n == "pdl") { const int old_v = pdl_enabled() ? 1 : 0; if (value == 0 || value == 1) pdl_set(value != 0); return old_v; }
+  if (n == "k3b_class_major") { if (value != 0 && value != 1) return g_k3b_class_major.load(); return g_k3b_class_major.exchange(value); }
+  if (n == "k3b_ablate") { if (value < 0) return g_k3b_ablate.load(); return g_k3b_ablate.exchange(value); }
+  if (n == "k3b_reverse") { if (value != 0 && value != 1) return g_k3b_reverse.load(); return g_k3b_reverse.exchange(value); }
   if (n == "xw_prefetch") { if (value < 0) return g_prefetch.load(); return g_prefetch.exchange(value); }
   if (n == "g_chunk_mb") { if (value < 1) return g_chunk_mb.load(); return g_chunk_mb.exchange(value); }
   return -1;

@@ -161,6 +161,8 @@ struct XwParams {
   int kb_count;                         // ceil(D / 64) <= XW_MAX_KB
   int m_groups, n_tiles, n_chunks;      // row groups of 128*PAIR rows, class tiles of 128*PAIR, class chunks
   int tn;                               // 128 * PAIR: tile width = rows of a resident group
+  int reverse;                          // walk the tiles of a chunk last-to-first: a consumer of what the previous
+                                        // kernel just wrote finds the freshest part still in L2
   int prefetch;                         // stages of L2 prefetch issued ahead of the ring (0 = off, the default:
                                         // measured slower -- the ring alone already sustains 91 % of HBM peak)
   uint32_t idesc;
@@ -276,7 +278,8 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
             if (++pkb == p.kb_count) { pkb = 0; ++pt; }
           }
         }
-        for (int t = t_begin; t < t_end && ok; ++t) {
+        for (int ti = t_begin; ti < t_end && ok; ++ti) {
+          const int t = p.reverse ? (t_end - 1 - (ti - t_begin)) : ti;
           const int n0 = t * TN + rank * XW_WROWS;
           for (int kb = 0; kb < p.kb_count; ++kb) {
             ok = mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -380,7 +383,8 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
         typename Epi::State stt;
         Epi::item_begin(stt, ep, p, it, scratch, TN);          // per-column tables of the group -> shared memory
         const int col_base = it.half * (TN / 2);
-        for (int t = t_begin; t < t_end; ++t) {
+        for (int ti = t_begin; ti < t_end; ++ti) {
+          const int t = p.reverse ? (t_end - 1 - (ti - t_begin)) : ti;
           ok = mbar_wait(&acc_full[acc], acc_phase);
           ok = __all_sync(0xffffffffu, ok);
           if (!ok) break;
@@ -418,7 +422,8 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
       const int t_end = (int)((int64_t)(it.chunk + 1) * p.n_tiles / p.n_chunks);
       typename Epi::State stt;
       Epi::item_begin(stt, ep, p, it);
-      for (int t = t_begin; t < t_end; ++t) {
+      for (int ti = t_begin; ti < t_end; ++ti) {
+        const int t = p.reverse ? (t_end - 1 - (ti - t_begin)) : ti;
         ok = mbar_wait(&acc_full[acc], acc_phase);
         ok = __all_sync(0xffffffffu, ok);
         if (!ok) break;
@@ -426,7 +431,7 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
         const int col_base = it.half * (TN / 2);
         const uint32_t taddr = tmem_base + (uint32_t)acc * XW_ACC_STRIDE + ((uint32_t)(it.quad * 32) << 16) + (uint32_t)col_base;
         const int cls_base = t * TN + col_base;
-        Epi::tile_begin(stt, ep, p, it, cls_base, (t + 1 < t_end) ? cls_base + TN : -1, TN / 2);
+        Epi::tile_begin(stt, ep, p, it, cls_base, (ti + 1 < t_end) ? cls_base + (p.reverse ? -TN : TN) : -1, TN / 2);
         float va[32], vb[32];
         tmem_ld32_async(taddr, va);
         // two slices per trip, NOT fully unrolled: the policy code exists twice, not 2 * SLICES times (i-cache)

@@ -396,5 +396,108 @@ struct XwDw {
   static __device__ __forceinline__ void item_end(State&, const Params&, const XwParams&, const XwItem&, float*) {}
 };
 
+// ---- K3b, class-major: dW[c, d] = coef.x * (acc[c, d] - w_hat16[c, d] * coef.y) --------------------------------
+// SWAP side of the kernel (G^T rows streamed as the A operand, x_hat resident MN-major as B): the thread owns ONE
+// class row per tile and 128 of the group's 256 features.  Everything the feature-major XwDw does per element this
+// one does per 32-feature slice: 4 x 16 B loads of w_hat, one coefficient pair per TILE, 4 x 32 B stores of 128
+// contiguous bytes -- an eighth of the memory instructions -- and since a row segment is contiguous, the next
+// slice's w_hat (and, across tiles, the next tile's first slice and coefficients) is fetched one slice ahead.
+struct XwDwT {
+  struct Params { const float2* coef; const __half* wh; float* dw; int64_t c0; int ld; int ablate; };   // ablate: probe only
+  struct State { uint4 w[4]; float2 cf; float2 cf_next; int64_t next_row; bool row_ok; };
+
+  static __device__ __forceinline__ void load_w(uint4 (&w)[4], const Params& ep, int64_t cls, int d0) {
+    if (ep.ablate & 1) { w[0] = w[1] = w[2] = w[3] = make_uint4(0, 0, 0, 0); return; }
+    const __half* src = ep.wh + (ep.c0 + cls) * (int64_t)ep.ld + d0;
+    if ((ep.ld & 15) == 0) {                                  // 32-byte aligned segments: two 256-bit loads
+      asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                   : "=r"(w[0].x), "=r"(w[0].y), "=r"(w[0].z), "=r"(w[0].w), "=r"(w[1].x), "=r"(w[1].y), "=r"(w[1].z), "=r"(w[1].w)
+                   : "l"(src));
+      asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                   : "=r"(w[2].x), "=r"(w[2].y), "=r"(w[2].z), "=r"(w[2].w), "=r"(w[3].x), "=r"(w[3].y), "=r"(w[3].z), "=r"(w[3].w)
+                   : "l"(src + 16));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) w[i] = __ldg(reinterpret_cast<const uint4*>(src) + i);
+    }
+  }
+  // pull the 256 bytes of w_hat this thread will need for row `cls` (its half of the group's features) into L2
+  static __device__ __forceinline__ void prefetch_row(const Params& ep, const XwParams& p, const XwItem& it, int64_t cls) {
+    if (cls < 0 || cls >= p.C || (ep.ablate & 1)) return;
+    const int d0 = it.group * p.tn + it.half * (p.tn / 2);
+    int nbytes = (min(p.tn / 2, p.B - d0) * 2) & ~15;
+    const __half* a = ep.wh + (ep.c0 + cls) * (int64_t)ep.ld + d0;
+    if (nbytes >= 16 && (reinterpret_cast<uintptr_t>(a) & 15) == 0)
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(nbytes) : "memory");
+  }
+  static __device__ __forceinline__ void item_begin(State& st, const Params&, const XwParams&, const XwItem&, float*, int) {
+    st.next_row = -1; st.row_ok = false;
+  }
+  static __device__ __forceinline__ void tile_begin(State& st, const Params& ep, const XwParams& p, const XwItem& it) {
+    st.row_ok = it.row < p.C;
+    // two tiles ahead: by the time the register prefetch of the last slice asks for it, the segment is an L2 hit
+    prefetch_row(ep, p, it, it.row + 2 * (p.reverse ? -(int64_t)p.tn : (int64_t)p.tn));
+    if (!st.row_ok) return;
+    const int d0 = it.group * p.tn + it.half * (p.tn / 2);
+    if (st.next_row == it.row) {
+      st.cf = st.cf_next;                                    // fetched during the previous tile's last slice
+    } else {
+      st.cf = __ldg(ep.coef + ep.c0 + it.row);
+      if (d0 + 32 <= p.B) load_w(st.w, ep, it.row, d0);
+    }
+  }
+  static __device__ __forceinline__ void slice(State& st, const Params& ep, const XwParams& p, const XwItem& it,
+                                               float (&v)[32], int col0, float*) {
+    if (!st.row_ok) return;
+    const int d0 = it.group * p.tn + col0;                   // first of this slice's 32 features
+    float* dst = ep.dw + (ep.c0 + it.row) * (int64_t)ep.ld + d0;
+    const float cx = st.cf.x, cy = st.cf.y;
+    if (d0 + 32 <= p.B) {
+      uint4 w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) w[i] = st.w[i];
+      // one slice ahead: the next 32 features of this row, or the first slice of the row this thread owns next
+      const bool last = ((col0 + 32) & (p.tn / 2 - 1)) == 0;
+      if (!last) {
+        if (d0 + 64 <= p.B) load_w(st.w, ep, it.row, d0 + 32);
+      } else {
+        const int64_t nr = it.row + (p.reverse ? -(int64_t)p.tn : (int64_t)p.tn);
+        st.next_row = -1;
+        const int dn = it.group * p.tn + it.half * (p.tn / 2);
+        if (nr >= 0 && nr < p.C && dn + 32 <= p.B) {
+          st.next_row = nr;
+          st.cf_next = __ldg(ep.coef + ep.c0 + nr);
+          load_w(st.w, ep, nr, dn);
+        }
+      }
+      float o[32];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t q[4] = {w[i].x, w[i].y, w[i].z, w[i].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&q[j]));
+          o[i * 8 + j * 2] = cx * fmaf(-f.x, cy, v[i * 8 + j * 2]);
+          o[i * 8 + j * 2 + 1] = cx * fmaf(-f.y, cy, v[i * 8 + j * 2 + 1]);
+        }
+      }
+      if ((ep.ablate & 2) && o[0] != 12345.678f) return;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        st_global_256(dst + i * 8, __float_as_uint(o[i * 8]), __float_as_uint(o[i * 8 + 1]), __float_as_uint(o[i * 8 + 2]),
+                      __float_as_uint(o[i * 8 + 3]), __float_as_uint(o[i * 8 + 4]), __float_as_uint(o[i * 8 + 5]),
+                      __float_as_uint(o[i * 8 + 6]), __float_as_uint(o[i * 8 + 7]));
+    } else {
+      // ragged feature count (D % 32 != 0): element by element, nothing fetched ahead
+      st.next_row = -1;
+      const __half* wsrc = ep.wh + (ep.c0 + it.row) * (int64_t)ep.ld + d0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (d0 + j < p.B) dst[j] = cx * fmaf(-__half2float(__ldg(wsrc + j)), cy, v[j]);
+    }
+  }
+  static __device__ __forceinline__ void tile_end(State&, const Params&, const XwParams&, const XwItem&) {}
+};
+
 }  // namespace umma
 }  // namespace b200f
