@@ -41,7 +41,7 @@ static EncodeTiledFn encode_fn() {
 
 // 2-D row-major 16-bit tensor [outer, inner] (inner contiguous, row stride ld elements), 128B swizzle.
 static int make_tmap(CUtensorMap* m, const void* base, int64_t inner, int64_t outer, int64_t ld, int box_inner,
-                     int box_outer) {
+                     int box_outer, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(B200F_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld % 8))
@@ -51,7 +51,7 @@ static int make_tmap(CUtensorMap* m, const void* base, int64_t inner, int64_t ou
   cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(B200F_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   return B200F_OK;
@@ -426,7 +426,9 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
       const XwPlan qw = xw_plan(D, cnt, qg.pair);
       const bool k3b_rev = g_k3b_reverse.load(std::memory_order_relaxed) != 0;   // read K3a's freshest G^T rows first
       if (g_k3b_class_major.load(std::memory_order_relaxed)) {   // thread owns a class row: vector loads / stores
-        XwDwT::Params ew{coef, static_cast<const __half*>(wh), dw, c0, D, g_k3b_ablate.load(std::memory_order_relaxed)};
+        XwDwT::Params ew{};
+        rc = make_tmap(&ew.tm_wh, wc, D, cnt, D, 32, 32, CU_TENSOR_MAP_SWIZZLE_NONE); if (rc) return rc;
+        ew.coef = coef; ew.dw = dw; ew.c0 = c0; ew.ld = D; ew.ablate = g_k3b_ablate.load(std::memory_order_relaxed);
         rc = (qw.pair == 2) ? launch_xw<2, XW_SWAP_MK, XwDwT>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW class-major (cta pair)", FMT_F16, k3b_rev)
                             : launch_xw<1, XW_SWAP_MK, XwDwT>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW class-major", FMT_F16, k3b_rev);
       } else

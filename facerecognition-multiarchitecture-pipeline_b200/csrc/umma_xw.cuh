@@ -174,10 +174,19 @@ struct XwParams;
 template <class Epi, class = void> struct xw_slice_wants_scratch { static constexpr bool value = false; };
 template <class Epi> struct xw_slice_wants_scratch<Epi, decltype((void)Epi::kSliceScratch)> { static constexpr bool value = true; };
 
+// A policy may trade ring stages for warp-private staging ("aux") space: with kRingStages = S < XW_STAGES the
+// streamed operand gets S stages and every epilogue warp owns (XW_STAGES - S) * 16 KB / 8 bytes at XwItem::aux plus two
+// mbarriers (count 1) at XwItem::aux_bar -- e.g. for epilogue operands it fetches with its own TMA loads.
+template <class Epi, class = void> struct xw_ring_stages { static constexpr int value = XW_STAGES; };
+template <class Epi> struct xw_ring_stages<Epi, decltype((void)Epi::kRingStages)> { static constexpr int value = Epi::kRingStages; };
+
 struct XwItem {                         // what an epilogue thread knows about its work item
   int item, chunk, group;
   int rank, ew, quad, half, lane;       // CTA rank in the pair, epilogue warp 0..7, TMEM quadrant, column half, lane
   int64_t row;                          // global row of x owned by this thread
+  uint8_t* aux;                         // this warp's staging bytes (nullptr unless the policy reserves them)
+  uint64_t* aux_bar;                    // its two mbarriers
+  mutable uint32_t aux_phase;           // their parity bits; lives across the items of the kernel
 };
 
 template <class Epi, class State, class Params>
@@ -199,8 +208,10 @@ __device__ __forceinline__ void xw_call_slice(State& st, const Params& ep, const
 template <int PAIR, bool X_MN, bool W_MN, bool SWAP, class Epi>
 __global__ void __launch_bounds__(XW_THREADS, 1)
 xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const XwParams p,
-          const typename Epi::Params ep) {
+          const __grid_constant__ typename Epi::Params ep) {
   constexpr int TN = XW_WROWS * PAIR;                        // class-tile width of the cluster
+  constexpr int STAGES = xw_ring_stages<Epi>::value;         // ring stages of the streamed operand
+  static_assert(STAGES >= 2 && STAGES <= XW_STAGES, "ring stages");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* xres = smem;                                      // XW_MAX_KB x 16 KB
@@ -214,6 +225,9 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
   uint64_t* acc_full = bars + 2 + 2 * XW_STAGES;             // [2] MMA -> epilogue (both CTAs)
   uint64_t* acc_empty = acc_full + 2;                        // [2] epilogue (both CTAs) -> MMA (leader)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + XW_NUM_BARS);
+  uint8_t* aux = ring + (size_t)STAGES * XW_TILE_BYTES;       // (XW_STAGES - STAGES) x 16 KB of warp-private staging
+  uint64_t* aux_bar = reinterpret_cast<uint64_t*>(scratch);   // 2 per epilogue warp (such policies leave scratch alone)
+  constexpr int AUX_WARP_BYTES = (XW_STAGES - STAGES) * XW_TILE_BYTES / XW_EPI_WARPS;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -230,6 +244,7 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
     mbar_init(x_empty, 1);
     for (int s = 0; s < XW_STAGES; ++s) { mbar_init(&full_bar[s], PAIR); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], PAIR * XW_EPI_WARPS); }
+    if (STAGES < XW_STAGES) for (int s = 0; s < 2 * XW_EPI_WARPS; ++s) mbar_init(&aux_bar[s], 1);
     fence_barrier_init();
   }
   if (warp == 1) xw_tmem_alloc<PAIR>(tmem_slot, 512);
@@ -301,7 +316,7 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
                 xw_tma_load<PAIR>(dst + XW_TILE_BYTES / 2, &tm_w, &full_bar[stage], n0 + 64, kb * XW_K);
               }
             }
-            if (++stage == XW_STAGES) { stage = 0; phase ^= 1; }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -355,7 +370,7 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
               xw_commit<PAIR>(&empty_bar[stage]);
             }
             __syncwarp();
-            if (++stage == XW_STAGES) { stage = 0; phase ^= 1; }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
           if (!ok) break;
           if (leader) xw_commit<PAIR>(&acc_full[acc]);
@@ -370,6 +385,8 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
     // ================= epilogue (8 warps, both CTAs) =================
     XwItem it;
     it.rank = rank; it.ew = warp - 2; it.quad = warp & 3; it.half = (warp - 2) >> 2; it.lane = lane;
+    it.aux = (STAGES < XW_STAGES) ? aux + (size_t)it.ew * AUX_WARP_BYTES : nullptr;
+    it.aux_bar = aux_bar + 2 * it.ew; it.aux_phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
     bool ok = true;
     constexpr int SLICES = TN / 64;                            // 32-column slices per warp per tile

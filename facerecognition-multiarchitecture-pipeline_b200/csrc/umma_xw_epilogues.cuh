@@ -398,78 +398,75 @@ struct XwDw {
 
 // ---- K3b, class-major: dW[c, d] = coef.x * (acc[c, d] - w_hat16[c, d] * coef.y) --------------------------------
 // SWAP side of the kernel (G^T rows streamed as the A operand, x_hat resident MN-major as B): the thread owns ONE
-// class row per tile and 128 of the group's 256 features.  Everything the feature-major XwDw does per element this
-// one does per 32-feature slice: 4 x 16 B loads of w_hat, one coefficient pair per TILE, 4 x 32 B stores of 128
-// contiguous bytes -- an eighth of the memory instructions -- and since a row segment is contiguous, the next
-// slice's w_hat (and, across tiles, the next tile's first slice and coefficients) is fetched one slice ahead.
+// class row per tile and 128 of the group's 256 features; it stores 128 contiguous bytes per 32-feature slice.
+//
+// w_hat reaches the epilogue through TMA, not through the load/store unit.  Measured on B200
+// (tools/microbench/store_bw.cu): row-per-lane 64-byte global loads deliver 2.0-2.2 TB/s however many warps issue
+// them -- the 102 MB of w_hat alone would take 46 us -- and the feature-major variant (XwDw, coalesced 64 B requests)
+// was bound by the same loads.  Here every epilogue warp runs a private two-deep pipeline of [32 classes x 32
+// features] boxes (2 KB, one cp.async.bulk.tensor per slice, issued two slices ahead by lane 0) into staging space
+// taken from the operand ring: G^T needs a third of the HBM rate, so 3 ring stages suffice and the other 32 KB are
+// 8 warps x 2 buffers x 2 KB.
 struct XwDwT {
-  struct Params { const float2* coef; const __half* wh; float* dw; int64_t c0; int ld; int ablate; };   // ablate: probe only
-  struct State { uint4 w[4]; float2 cf; float2 cf_next; int64_t next_row; bool row_ok; };
+  static constexpr int kRingStages = 3;
+  struct Params {
+    alignas(64) CUtensorMap tm_wh;      // w_hat16 rows of this launch [classes, D], box 32 features x 32 classes, no swizzle
+    const float2* coef; float* dw; int64_t c0; int ld; int ablate;   // ablate: probe only
+  };
+  struct State { float2 cf, cf_next; int64_t next_row; int seq, n_seq, row0, row_step; bool row_ok; };
 
-  static __device__ __forceinline__ void load_w(uint4 (&w)[4], const Params& ep, int64_t cls, int d0) {
-    if (ep.ablate & 1) { w[0] = w[1] = w[2] = w[3] = make_uint4(0, 0, 0, 0); return; }
-    const __half* src = ep.wh + (ep.c0 + cls) * (int64_t)ep.ld + d0;
-    if ((ep.ld & 15) == 0) {                                  // 32-byte aligned segments: two 256-bit loads
-      asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                   : "=r"(w[0].x), "=r"(w[0].y), "=r"(w[0].z), "=r"(w[0].w), "=r"(w[1].x), "=r"(w[1].y), "=r"(w[1].z), "=r"(w[1].w)
-                   : "l"(src));
-      asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                   : "=r"(w[2].x), "=r"(w[2].y), "=r"(w[2].z), "=r"(w[2].w), "=r"(w[3].x), "=r"(w[3].y), "=r"(w[3].z), "=r"(w[3].w)
-                   : "l"(src + 16));
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) w[i] = __ldg(reinterpret_cast<const uint4*>(src) + i);
+  // slice n of this warp's item = column slice (n % spt) of its (n / spt)-th tile; buffer n & 1
+  static __device__ __forceinline__ void issue(const State& st, const Params& ep, const XwParams& p, const XwItem& it, int n) {
+    const int spt = p.tn >> 6;
+    if (n >= st.n_seq || (ep.ablate & 1)) return;
+    const int d0 = it.group * p.tn + it.half * (p.tn >> 1) + (n % spt) * 32;
+    if (d0 >= p.B) return;                                    // ragged feature count: nothing there (the reader skips too)
+    if (it.lane == 0) {
+      uint64_t* bar = it.aux_bar + (n & 1);
+      mbar_arrive_expect_tx(bar, 2048);
+      tma_load_2d(it.aux + (n & 1) * 2048, &ep.tm_wh, bar, d0, st.row0 + (n / spt) * st.row_step);
     }
   }
-  // pull the 256 bytes of w_hat this thread will need for row `cls` (its half of the group's features) into L2
-  static __device__ __forceinline__ void prefetch_row(const Params& ep, const XwParams& p, const XwItem& it, int64_t cls) {
-    if (cls < 0 || cls >= p.C || (ep.ablate & 1)) return;
-    const int d0 = it.group * p.tn + it.half * (p.tn / 2);
-    int nbytes = (min(p.tn / 2, p.B - d0) * 2) & ~15;
-    const __half* a = ep.wh + (ep.c0 + cls) * (int64_t)ep.ld + d0;
-    if (nbytes >= 16 && (reinterpret_cast<uintptr_t>(a) & 15) == 0)
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(nbytes) : "memory");
-  }
-  static __device__ __forceinline__ void item_begin(State& st, const Params&, const XwParams&, const XwItem&, float*, int) {
-    st.next_row = -1; st.row_ok = false;
+  static __device__ __forceinline__ void item_begin(State& st, const Params& ep, const XwParams& p, const XwItem& it,
+                                                    float*, int) {
+    const int t_begin = (int)((int64_t)it.chunk * p.n_tiles / p.n_chunks);
+    const int t_end = (int)((int64_t)(it.chunk + 1) * p.n_tiles / p.n_chunks);
+    st.n_seq = (t_end - t_begin) * (p.tn >> 6);
+    st.row0 = (p.reverse ? t_end - 1 : t_begin) * p.tn + it.rank * XW_WROWS + it.quad * 32;
+    st.row_step = p.reverse ? -p.tn : p.tn;
+    st.seq = 0; st.next_row = -1; st.row_ok = false;
+    issue(st, ep, p, it, 0);
+    issue(st, ep, p, it, 1);
   }
   static __device__ __forceinline__ void tile_begin(State& st, const Params& ep, const XwParams& p, const XwItem& it) {
     st.row_ok = it.row < p.C;
-    // two tiles ahead: by the time the register prefetch of the last slice asks for it, the segment is an L2 hit
-    prefetch_row(ep, p, it, it.row + 2 * (p.reverse ? -(int64_t)p.tn : (int64_t)p.tn));
     if (!st.row_ok) return;
-    const int d0 = it.group * p.tn + it.half * (p.tn / 2);
-    if (st.next_row == it.row) {
-      st.cf = st.cf_next;                                    // fetched during the previous tile's last slice
-    } else {
-      st.cf = __ldg(ep.coef + ep.c0 + it.row);
-      if (d0 + 32 <= p.B) load_w(st.w, ep, it.row, d0);
-    }
+    st.cf = (st.next_row == it.row) ? st.cf_next : __ldg(ep.coef + ep.c0 + it.row);
+    const int64_t nr = it.row + st.row_step;                  // next tile's coefficients, one tile ahead
+    st.next_row = -1;
+    if (nr >= 0 && nr < p.C) { st.next_row = nr; st.cf_next = __ldg(ep.coef + ep.c0 + nr); }
   }
   static __device__ __forceinline__ void slice(State& st, const Params& ep, const XwParams& p, const XwItem& it,
                                                float (&v)[32], int col0, float*) {
-    if (!st.row_ok) return;
+    const int n = st.seq++;
     const int d0 = it.group * p.tn + col0;                   // first of this slice's 32 features
-    float* dst = ep.dw + (ep.c0 + it.row) * (int64_t)ep.ld + d0;
-    const float cx = st.cf.x, cy = st.cf.y;
-    if (d0 + 32 <= p.B) {
-      uint4 w[4];
+    if (d0 >= p.B) return;
+    uint4 w[4];
+    if (ep.ablate & 1) {
+      w[0] = w[1] = w[2] = w[3] = make_uint4(0, 0, 0, 0);
+    } else {
+      const uint32_t b = (uint32_t)n & 1u;
+      mbar_wait(it.aux_bar + b, (it.aux_phase >> b) & 1u);
+      it.aux_phase ^= 1u << b;
+      const uint32_t src = smem_u32(it.aux + b * 2048 + it.lane * 64);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) w[i] = st.w[i];
-      // one slice ahead: the next 32 features of this row, or the first slice of the row this thread owns next
-      const bool last = ((col0 + 32) & (p.tn / 2 - 1)) == 0;
-      if (!last) {
-        if (d0 + 64 <= p.B) load_w(st.w, ep, it.row, d0 + 32);
-      } else {
-        const int64_t nr = it.row + (p.reverse ? -(int64_t)p.tn : (int64_t)p.tn);
-        st.next_row = -1;
-        const int dn = it.group * p.tn + it.half * (p.tn / 2);
-        if (nr >= 0 && nr < p.C && dn + 32 <= p.B) {
-          st.next_row = nr;
-          st.cf_next = __ldg(ep.coef + ep.c0 + nr);
-          load_w(st.w, ep, nr, dn);
-        }
-      }
+      for (int i = 0; i < 4; ++i)
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(w[i].x), "=r"(w[i].y), "=r"(w[i].z), "=r"(w[i].w) : "r"(src + i * 16) : "memory");
+    }
+    if (st.row_ok) {
+      float* dst = ep.dw + (ep.c0 + it.row) * (int64_t)ep.ld + d0;
+      const float cx = st.cf.x, cy = st.cf.y;
       float o[32];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -481,20 +478,27 @@ struct XwDwT {
           o[i * 8 + j * 2 + 1] = cx * fmaf(-f.y, cy, v[i * 8 + j * 2 + 1]);
         }
       }
-      if ((ep.ablate & 2) && o[0] != 12345.678f) return;
+      if ((ep.ablate & 2) && o[0] != 12345.678f) {
+      } else if (d0 + 32 <= p.B && (ep.ld & 7) == 0) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-        st_global_256(dst + i * 8, __float_as_uint(o[i * 8]), __float_as_uint(o[i * 8 + 1]), __float_as_uint(o[i * 8 + 2]),
-                      __float_as_uint(o[i * 8 + 3]), __float_as_uint(o[i * 8 + 4]), __float_as_uint(o[i * 8 + 5]),
-                      __float_as_uint(o[i * 8 + 6]), __float_as_uint(o[i * 8 + 7]));
+        for (int i = 0; i < 4; ++i)
+          st_global_256(dst + i * 8, __float_as_uint(o[i * 8]), __float_as_uint(o[i * 8 + 1]), __float_as_uint(o[i * 8 + 2]),
+                        __float_as_uint(o[i * 8 + 3]), __float_as_uint(o[i * 8 + 4]), __float_as_uint(o[i * 8 + 5]),
+                        __float_as_uint(o[i * 8 + 6]), __float_as_uint(o[i * 8 + 7]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (d0 + j < p.B) dst[j] = o[j];
+      }
     } else {
-      // ragged feature count (D % 32 != 0): element by element, nothing fetched ahead
-      st.next_row = -1;
-      const __half* wsrc = ep.wh + (ep.c0 + it.row) * (int64_t)ep.ld + d0;
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (d0 + j < p.B) dst[j] = cx * fmaf(-__half2float(__ldg(wsrc + j)), cy, v[j]);
+      // a lane without a row still has to have RECEIVED its shared-memory reads before the buffer is handed back
+      asm volatile("" :: "r"(w[0].x ^ w[1].x ^ w[2].x ^ w[3].x) : "memory");
     }
+    // Refill only now: the stores above consumed w[], so every lane's reads of the buffer have completed.  (Issuing
+    // the refill right after the ld.shared instructions let the TMA write overtake reads still queued in the
+    // load/store unit behind this kernel's global stores: single 16-byte pieces of the NEXT box showed up.)
+    __syncwarp();
+    issue(st, ep, p, it, n + 2);
   }
   static __device__ __forceinline__ void tile_end(State&, const Params&, const XwParams&, const XwItem&) {}
 };
