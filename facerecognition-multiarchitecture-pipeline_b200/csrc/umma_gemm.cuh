@@ -1,6 +1,12 @@
-// Persistent, warp-specialised tcgen05 GEMM core (1 CTA per SM, cta_group::1):
+// Persistent, warp-specialised tcgen05 GEMM core (1 CTA per SM), both operands streamed:
 //
 //   D[m, n] = sum_k A(m, k) * B(n, k)      bf16 (or fp16) operands, fp32 accumulation in TMEM
+//
+// PAIR = 1: cta_group::1, one CTA per 128 x 256 tile, 4 stages of (16 KB A | 32 KB B).
+// PAIR = 2: the two CTAs of a cluster form a cta_group::2 pair on one 256 x 256 tile: each loads ITS 128 rows of A
+//           and ITS 128 of the tile's 256 B rows (6 stages of 16 KB | 16 KB), the leader issues 256 x 256 x 16 MMAs that
+//           read both CTAs' shared memory.  Per k-block a CTA now ingests 32 KB for the work it took 48 KB for:
+//           the single-CTA core is L2->SM bound (615 MB for cfg3's dX GEMM, 13.7 TB/s), the pair moves 2/3 of that.
 //
 //   warp 0      : TMA producer   (global -> 128B-swizzled shared tiles, 4-stage mbarrier ring)
 //   warp 1      : MMA issuer     (one elected lane issues tcgen05.mma 128x256x16; accumulators are
@@ -25,7 +31,7 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_N = 256;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 4;
+constexpr int STAGES = 4;                                // PAIR = 1; see gemm_stages()
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = 512;
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;      // 16 KB
@@ -37,6 +43,10 @@ constexpr int EPI_THREADS = 128;
 constexpr int MN_BLOCK_BYTES = 64 * BLOCK_K * 2;          // one 64-wide MN block of 64 k-rows: 8 KB
 constexpr int EPI_SMEM_FLOATS = 1024;                     // scratch for the epilogue policy
 constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + EPI_SMEM_FLOATS * 4 + 256;
+constexpr int MAX_STAGES = 6;
+__host__ __device__ constexpr int gemm_b_rows(int pair) { return BLOCK_N / pair; }                  // B rows a CTA loads
+__host__ __device__ constexpr int gemm_stage_bytes(int pair) { return A_TILE_BYTES + gemm_b_rows(pair) * BLOCK_K * 2; }
+__host__ __device__ constexpr int gemm_stages(int pair) { return STAGES * STAGE_BYTES / gemm_stage_bytes(pair); }   // 4 | 6
 
 struct GemmParams {
   int M, N, K;              // extents of the m, n and k index spaces
@@ -47,14 +57,17 @@ struct GemmParams {
   uint32_t idesc;
 };
 
-struct TileCoord { int m0, n0, split, k_begin, k_end; };
+struct TileCoord { int m0, n0, split, k_begin, k_end, nb0; };   // m0: first row of THIS CTA; nb0: first B row it loads
 
-__device__ __forceinline__ TileCoord decode_work(const GemmParams& p, int w) {
+// m_tiles counts tiles of 128 * PAIR rows
+template <int PAIR>
+__device__ __forceinline__ TileCoord decode_work(const GemmParams& p, int w, int rank) {
   TileCoord t;
   const int m = w % p.m_tiles;
   const int n = (w / p.m_tiles) % p.n_tiles;
   t.split = w / (p.m_tiles * p.n_tiles);
-  t.m0 = m * BLOCK_M; t.n0 = n * BLOCK_N;
+  t.m0 = (m * PAIR + rank) * BLOCK_M; t.n0 = n * BLOCK_N;
+  t.nb0 = t.n0 + rank * gemm_b_rows(PAIR);
   t.k_begin = t.split * p.k_per_split;
   t.k_end = min(p.K, t.k_begin + p.k_per_split);
   return t;
@@ -65,79 +78,87 @@ __device__ __forceinline__ TileCoord decode_work(const GemmParams& p, int w) {
 //                uint32_t tmem_acc /*lane 0, first column of this accumulator stage*/, int quad /*warp%4*/,
 //                int lane, int epi_tid /*0..127*/, float* scratch /*EPI_SMEM_FLOATS, epilogue-only smem*/); }
 // run() must finish all its tcgen05.ld (tmem_ld_wait) before returning.
-template <bool A_MN, bool B_MN, class Epi>
+template <int PAIR, bool A_MN, bool B_MN, class Epi>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
             const GemmParams p, const typename Epi::Params ep) {
+  constexpr int NST = gemm_stages(PAIR);
+  constexpr int STG_BYTES = gemm_stage_bytes(PAIR);
+  constexpr int B_ROWS = gemm_b_rows(PAIR);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* tiles = smem;                                        // STAGES x (A | B), 1024 B aligned
+  uint8_t* tiles = smem;                                        // NST x (A | B), 1024 B aligned
   float* scratch = reinterpret_cast<float*>(smem + (size_t)STAGES * STAGE_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + EPI_SMEM_FLOATS);
-  uint64_t* full_bar = bars;                                    // [STAGES]   TMA -> MMA
-  uint64_t* empty_bar = bars + STAGES;                          // [STAGES]   MMA -> TMA
-  uint64_t* acc_full = bars + 2 * STAGES;                       // [ACC_STAGES] MMA -> epilogue
-  uint64_t* acc_empty = bars + 2 * STAGES + ACC_STAGES;         // [ACC_STAGES] epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * ACC_STAGES);
+  uint64_t* full_bar = bars;                                    // [NST]   TMA -> MMA (leader CTA)
+  uint64_t* empty_bar = bars + MAX_STAGES;                      // [NST]   MMA -> TMA (both CTAs)
+  uint64_t* acc_full = bars + 2 * MAX_STAGES;                   // [ACC_STAGES] MMA -> epilogue (both CTAs)
+  uint64_t* acc_empty = bars + 2 * MAX_STAGES + ACC_STAGES;     // [ACC_STAGES] epilogue (both CTAs) -> MMA (leader)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 2 * ACC_STAGES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int rank = (PAIR == 2) ? (int)cluster_ctarank() : 0;
+  const int cluster_id = blockIdx.x / PAIR;
+  const int n_clusters = gridDim.x / PAIR;
   const int total_work = p.m_tiles * p.n_tiles * p.k_splits;
 
   pdl_trigger();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], EPI_THREADS / 32); }
+    for (int s = 0; s < NST; ++s) { mbar_init(&full_bar[s], PAIR); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < ACC_STAGES; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], PAIR * EPI_THREADS / 32); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 1) xw_tmem_alloc<PAIR>(tmem_slot, TMEM_COLS);
   tc_fence_before_sync();
   __syncthreads();
+  if (PAIR == 2) cluster_sync_all();                           // the peer's barriers exist before anyone signals them
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
 
   if (warp == 0) {
-    // ================= TMA producer =================
+    // ================= TMA producer (both CTAs) =================
     {
       const bool leader = elect_one();
       int stage = 0; uint32_t phase = 0;
       bool ok = true;
-      for (int w = blockIdx.x; w < total_work && ok; w += gridDim.x) {
-        const TileCoord t = decode_work(p, w);
+      for (int w = cluster_id; w < total_work && ok; w += n_clusters) {
+        const TileCoord t = decode_work<PAIR>(p, w, rank);
         for (int k0 = t.k_begin; k0 < t.k_end && ok; k0 += BLOCK_K) {
           ok = mbar_wait(&empty_bar[stage], phase ^ 1);
           if (!ok) break;
           if (leader) {
-            uint8_t* sa = tiles + (size_t)stage * STAGE_BYTES;
+            uint8_t* sa = tiles + (size_t)stage * STG_BYTES;
             uint8_t* sb = sa + A_TILE_BYTES;
-            mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], PAIR * STG_BYTES);
+            else mbar_arrive_cluster(&full_bar[stage], 0);
             if (!A_MN) {
-              tma_load_2d(sa, &tm_a, &full_bar[stage], k0, t.m0);
+              xw_tma_load<PAIR>(sa, &tm_a, &full_bar[stage], k0, t.m0);
             } else {
 #pragma unroll
               for (int j = 0; j < BLOCK_M / 64; ++j)
-                tma_load_2d(sa + j * MN_BLOCK_BYTES, &tm_a, &full_bar[stage], t.m0 + 64 * j, k0);
+                xw_tma_load<PAIR>(sa + j * MN_BLOCK_BYTES, &tm_a, &full_bar[stage], t.m0 + 64 * j, k0);
             }
             if (!B_MN) {
-              tma_load_2d(sb, &tm_b, &full_bar[stage], k0, t.n0);
+              xw_tma_load<PAIR>(sb, &tm_b, &full_bar[stage], k0, t.nb0);
             } else {
 #pragma unroll
-              for (int j = 0; j < BLOCK_N / 64; ++j)
-                tma_load_2d(sb + j * MN_BLOCK_BYTES, &tm_b, &full_bar[stage], t.n0 + 64 * j, k0);
+              for (int j = 0; j < B_ROWS / 64; ++j)
+                xw_tma_load<PAIR>(sb + j * MN_BLOCK_BYTES, &tm_b, &full_bar[stage], t.nb0 + 64 * j, k0);
             }
           }
           __syncwarp();
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == NST) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
+    // ================= MMA issuer (leader CTA of a pair) =================
     // convergent warp, one elected lane issues; descriptors = base descriptor + 14-bit address offset
-    {
+    if (rank == 0) {
       const bool leader = elect_one();
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
@@ -145,8 +166,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
       const uint64_t desc_a0 = make_smem_desc(smem_u32(tiles), p.a_lbo, p.a_sbo);
       const uint64_t desc_b0 = make_smem_desc(smem_u32(tiles) + A_TILE_BYTES, p.b_lbo, p.b_sbo);
       const uint32_t a_kstep = p.a_kstep >> 4, b_kstep = p.b_kstep >> 4;
-      for (int w = blockIdx.x; w < total_work && ok; w += gridDim.x) {
-        const TileCoord t = decode_work(p, w);
+      for (int w = cluster_id; w < total_work && ok; w += n_clusters) {
+        const TileCoord t = decode_work<PAIR>(p, w, rank);
         ok = mbar_wait(&acc_empty[acc], acc_phase ^ 1);        // epilogue has drained this accumulator
         if (!ok) break;
         tc_fence_after_sync();
@@ -157,32 +178,32 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
           if (!ok) break;
           tc_fence_after_sync();
           if (leader) {
-            const uint64_t soff = (uint64_t)((uint32_t)stage * (STAGE_BYTES >> 4));
+            const uint64_t soff = (uint64_t)((uint32_t)stage * (STG_BYTES >> 4));
 #pragma unroll
             for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
-              mma_f16_ss(d_tmem, desc_a0 + soff + (uint64_t)(kk * a_kstep), desc_b0 + soff + (uint64_t)(kk * b_kstep),
-                         p.idesc, accumulate);
+              xw_mma<PAIR>(d_tmem, desc_a0 + soff + (uint64_t)(kk * a_kstep), desc_b0 + soff + (uint64_t)(kk * b_kstep),
+                           p.idesc, accumulate);
               accumulate = 1;
             }
-            mma_commit(&empty_bar[stage]);                     // smem slot reusable once these MMAs retire
+            xw_commit<PAIR>(&empty_bar[stage]);                // smem slot reusable (in both CTAs) once these MMAs retire
           }
           accumulate = 1;
           __syncwarp();
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == NST) { stage = 0; phase ^= 1; }
         }
-        if (leader) mma_commit(&acc_full[acc]);                // accumulator ready for the epilogue
+        if (leader) xw_commit<PAIR>(&acc_full[acc]);           // accumulator ready for the epilogues
         __syncwarp();
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
-    // ================= epilogue =================
+    // ================= epilogue (both CTAs: own 128 rows x 256 columns) =================
     const int quad = warp & 3;                                 // TMEM lanes [32*quad, 32*quad+32)
     const int epi_tid = (warp - EPI_WARP0) * 32 + lane;
     int acc = 0; uint32_t acc_phase = 0;
     bool ok = true;
-    for (int w = blockIdx.x; w < total_work && ok; w += gridDim.x) {
-      const TileCoord t = decode_work(p, w);
+    for (int w = cluster_id; w < total_work && ok; w += n_clusters) {
+      const TileCoord t = decode_work<PAIR>(p, w, rank);
       ok = mbar_wait(&acc_full[acc], acc_phase);
       ok = __all_sync(0xffffffffu, ok);
       if (!ok) break;
@@ -191,13 +212,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
       Epi::run(ep, p, t, tmem_acc, quad, lane, epi_tid, scratch);
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (lane == 0) {
+        if (PAIR == 2) mbar_arrive_cluster(&acc_empty[acc], 0);
+        else mbar_arrive(&acc_empty[acc]);
+      }
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) { tc_fence_after_sync(); tmem_dealloc(tmem_base, TMEM_COLS); }
+  if (PAIR == 2) cluster_sync_all();                           // nobody leaves while the leader may still signal it
+  if (warp == 1) { tc_fence_after_sync(); xw_tmem_dealloc<PAIR>(tmem_base, TMEM_COLS); }
 }
 
 }  // namespace umma

@@ -65,10 +65,11 @@ static int tmap_mnmajor(CUtensorMap* m, const void* base, int64_t MN, int64_t K,
   return make_tmap(m, base, MN, K, ld, 64, BLOCK_K);
 }
 
-static GemmParams gemm_params(int M, int N, int K, int k_splits, bool a_mn, bool b_mn, uint32_t a_fmt, uint32_t b_fmt) {
+static GemmParams gemm_params(int M, int N, int K, int k_splits, bool a_mn, bool b_mn, uint32_t a_fmt, uint32_t b_fmt,
+                              int pair = 1) {
   GemmParams p{};
   p.M = M; p.N = N; p.K = K;
-  p.m_tiles = (int)ceil_div(M, BLOCK_M);
+  p.m_tiles = (int)ceil_div(M, BLOCK_M * pair);           // tiles of 128 * pair rows
   p.n_tiles = (int)ceil_div(N, BLOCK_N);
   int kchunks = (int)ceil_div(K, BLOCK_K);
   if (k_splits > kchunks) k_splits = kchunks;
@@ -79,19 +80,29 @@ static GemmParams gemm_params(int M, int N, int K, int k_splits, bool a_mn, bool
   // SBO = 1024 (next 8 k-rows), k-step = 16 rows x 128 B.   (validated on B200 by tools/umma_probe.py)
   p.a_lbo = a_mn ? MN_BLOCK_BYTES : 0; p.a_sbo = 1024; p.a_kstep = a_mn ? 2048 : 32;
   p.b_lbo = b_mn ? MN_BLOCK_BYTES : 0; p.b_sbo = 1024; p.b_kstep = b_mn ? 2048 : 32;
-  p.idesc = make_idesc(a_fmt, b_fmt, a_mn, b_mn, BLOCK_M, BLOCK_N);
+  p.idesc = make_idesc(a_fmt, b_fmt, a_mn, b_mn, BLOCK_M * pair, BLOCK_N);
   return p;
 }
 
-template <bool A_MN, bool B_MN, class Epi>
+static int xw_max_clusters(int pair);
+
+// PAIR = 2: clusters of two CTAs on 256 x 256 tiles (p from gemm_params(..., pair = 2); a K-major B map needs
+// 128-row boxes: gemm_b_rows(2))
+template <int PAIR, bool A_MN, bool B_MN, class Epi>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
                        const typename Epi::Params& ep, cudaStream_t st, const char* what) {
-  auto kern = gemm_kernel<A_MN, B_MN, Epi>;
+  auto kern = gemm_kernel<PAIR, A_MN, B_MN, Epi>;
   B200F_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   const int work = p.m_tiles * p.n_tiles * p.k_splits;
-  int grid = num_sms();
-  if (grid > work) grid = work;
-  cudaError_t e = launch_pdl(kern, dim3((unsigned)grid), dim3(NUM_THREADS), SMEM_BYTES, st, ta, tb, p, ep);
+  int clusters = (PAIR == 2) ? xw_max_clusters(2) : num_sms();
+  if (clusters > work) clusters = work;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(clusters * PAIR)); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = PAIR; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, p, ep);
   if (e != cudaSuccess) return fail(B200F_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
   B200F_LAUNCH_OK(what);
   return B200F_OK;
@@ -312,15 +323,19 @@ static Plan make_plan(int64_t B, int64_t C, int D) {
   pl.Cc = ceil_div(ceil_div(C, pl.n_chunks), BLOCK_N) * BLOCK_N;
   pl.n_chunks = (int)ceil_div(C, pl.Cc);
   pl.ldg = ldgt;
-  const int out_tiles = m_tiles * (int)ceil_div(D, BLOCK_N);
-  int splits = num_sms() / out_tiles;
+  // split-K of the dX GEMM: one wave of CTAs (pair = 1) or of clusters (pair = 2) over m-tiles x n-tiles x splits
+  const int out_tiles = (int)ceil_div(B, BLOCK_M * pair) * (int)ceil_div(D, BLOCK_N);
+  int splits = (pair == 2 ? xw_max_clusters(2) : num_sms()) / out_tiles;
   if (splits < 1) splits = 1;
   const int kchunks = (int)(pl.Cc / BLOCK_K);
   if (splits > kchunks) splits = kchunks;
   pl.dx_splits = splits;
   off = 0;
   pl.off_G = off;      off += align_up(2 * (size_t)pl.Cc * pl.ldg, 1024);
-  pl.off_dxpart = off; off += align_up(sizeof(float) * (size_t)splits * B * D, 256);
+  int splits_max = num_sms() / ((int)ceil_div(B, BLOCK_M) * (int)ceil_div(D, BLOCK_N));   // either pairing fits
+  if (splits_max < splits) splits_max = splits;
+  if (splits_max < 1) splits_max = 1;
+  pl.off_dxpart = off; off += align_up(sizeof(float) * (size_t)splits_max * B * D, 256);
   pl.fused_dw = (B <= (int64_t)XW_MAX_KB * XW_K);         // x_hat^T resident (else: both operands streamed)
   pl.n_rb = (int)ceil_div(B, 2 * XW_M) * 2 * 4;          // covers either pairing
   pl.off_rpart = off; off += align_up(sizeof(float) * (size_t)pl.n_rb * pl.Cc, 256);
@@ -398,6 +413,7 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
   CUtensorMap tx_k, tx_mn;
   rc = tmap_kmajor(&tx_k, xh, B, D, D, XW_M); if (rc) return rc;
   rc = tmap_mnmajor(&tx_mn, xh, D, B, D); if (rc) return rc;
+  const int gpair = pl.fwd.pair;                            // generic core: single CTAs or cta_group::2 pairs, like K2 / K3a
   int chunk_no = 0;
   for (int64_t c0 = 0; c0 < C; c0 += pl.Cc, ++chunk_no) {
     const int64_t cnt = (C - c0 < pl.Cc) ? (C - c0) : pl.Cc;
@@ -449,18 +465,20 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
       //  TMEM reads, per-element global loads.)
       CUtensorMap tg_km;
       rc = tmap_kmajor(&tg_km, G, cnt, B, pl.ldg, BLOCK_M); if (rc) return rc;
-      GemmParams pw = gemm_params((int)cnt, D, (int)B, 1, false, true, FMT_F16, FMT_F16);
+      GemmParams pw = gemm_params((int)cnt, D, (int)B, 1, false, true, FMT_F16, FMT_F16, gpair);
       EpiStore::Params ew{dw, (int64_t)D, 0, c0, 1.0f / S, grad4 + 3};
-      rc = launch_gemm<false, true, EpiStore>(tg_km, tx_mn, pw, ew, st, "umma K3b dW (streamed)");
+      rc = (gpair == 2) ? launch_gemm<2, false, true, EpiStore>(tg_km, tx_mn, pw, ew, st, "umma K3b dW (streamed, cta pair)")
+                        : launch_gemm<1, false, true, EpiStore>(tg_km, tx_mn, pw, ew, st, "umma K3b dW (streamed)");
       if (rc) return rc;
     }
     // --- K3c: dx_hat partials = G[:, k-range] w_hat[c0 + k-range, :]   (A = G read MN-major from G^T)
     CUtensorMap tg_mn, tw_mn;
     rc = tmap_mnmajor(&tg_mn, G, B, cnt, pl.ldg); if (rc) return rc;
     rc = tmap_mnmajor(&tw_mn, wc, D, cnt, D); if (rc) return rc;
-    GemmParams px = gemm_params((int)B, D, (int)cnt, pl.dx_splits, true, true, FMT_F16, FMT_F16);
+    GemmParams px = gemm_params((int)B, D, (int)cnt, pl.dx_splits, true, true, FMT_F16, FMT_F16, gpair);
     EpiStore::Params ex{dxpart, (int64_t)D, B * (int64_t)D, 0, 1.0f, nullptr};
-    rc = launch_gemm<true, true, EpiStore>(tg_mn, tw_mn, px, ex, st, "umma K3c dX");
+    rc = (gpair == 2) ? launch_gemm<2, true, true, EpiStore>(tg_mn, tw_mn, px, ex, st, "umma K3c dX (cta pair)")
+                      : launch_gemm<1, true, true, EpiStore>(tg_mn, tw_mn, px, ex, st, "umma K3c dX");
     if (rc) return rc;
     const int64_t n = B * (int64_t)D;
     launch_pdl(reduce_splits_kernel, dim3((unsigned)ceil_div(n / 4, 256)), dim3(256), 0, st, dxpart, px.k_splits, n, dxhat, chunk_no > 0,
@@ -612,13 +630,14 @@ int b200f_umma_selftest(const void* a, const void* b, float* out, int M, int N, 
                         int b_kstep, void* stream) {
   if (!a || !b || !out || M <= 0 || N <= 0 || K <= 0) return fail(B200F_ERR_ARG, "umma_selftest: bad argument");
   if (!device_is_sm100()) return fail(B200F_ERR_UNSUPPORTED, "umma_selftest: device is not sm_100");
+  const int pair = g_pair.load(std::memory_order_relaxed);  // the "pair" tunable selects cta_group::1 or ::2 here too
   CUtensorMap ta, tb;
   int rc = a_mn ? tmap_mnmajor(&ta, a, M, K, M) : tmap_kmajor(&ta, a, M, K, K, BLOCK_M);
   if (rc) return rc;
-  rc = b_mn ? tmap_mnmajor(&tb, b, N, K, N) : tmap_kmajor(&tb, b, N, K, K, BLOCK_N);
+  rc = b_mn ? tmap_mnmajor(&tb, b, N, K, N) : tmap_kmajor(&tb, b, N, K, K, gemm_b_rows(pair));
   if (rc) return rc;
   GemmParams p = gemm_params(M, N, K, k_splits, a_mn != 0, b_mn != 0, fmt >= 1 ? FMT_F16 : FMT_BF16,
-                             fmt == 2 ? FMT_F16 : FMT_BF16);
+                             fmt == 2 ? FMT_F16 : FMT_BF16, pair);
   if (a_lbo >= 0) p.a_lbo = a_lbo;
   if (a_sbo >= 0) p.a_sbo = a_sbo;
   if (a_kstep >= 0) p.a_kstep = a_kstep;
@@ -627,10 +646,16 @@ int b200f_umma_selftest(const void* a, const void* b, float* out, int M, int N, 
   if (b_kstep >= 0) p.b_kstep = b_kstep;
   EpiStore::Params ep{out, (int64_t)N, (int64_t)M * N, 0, 1.0f, nullptr};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (!a_mn && !b_mn) return launch_gemm<false, false, EpiStore>(ta, tb, p, ep, st, "umma selftest KK");
-  if (a_mn && b_mn) return launch_gemm<true, true, EpiStore>(ta, tb, p, ep, st, "umma selftest MM");
-  if (!a_mn && b_mn) return launch_gemm<false, true, EpiStore>(ta, tb, p, ep, st, "umma selftest KM");
-  return launch_gemm<true, false, EpiStore>(ta, tb, p, ep, st, "umma selftest MK");
+  if (pair == 2) {
+    if (!a_mn && !b_mn) return launch_gemm<2, false, false, EpiStore>(ta, tb, p, ep, st, "umma selftest KK (cta pair)");
+    if (a_mn && b_mn) return launch_gemm<2, true, true, EpiStore>(ta, tb, p, ep, st, "umma selftest MM (cta pair)");
+    if (!a_mn && b_mn) return launch_gemm<2, false, true, EpiStore>(ta, tb, p, ep, st, "umma selftest KM (cta pair)");
+    return launch_gemm<2, true, false, EpiStore>(ta, tb, p, ep, st, "umma selftest MK (cta pair)");
+  }
+  if (!a_mn && !b_mn) return launch_gemm<1, false, false, EpiStore>(ta, tb, p, ep, st, "umma selftest KK");
+  if (a_mn && b_mn) return launch_gemm<1, true, true, EpiStore>(ta, tb, p, ep, st, "umma selftest MM");
+  if (!a_mn && b_mn) return launch_gemm<1, false, true, EpiStore>(ta, tb, p, ep, st, "umma selftest KM");
+  return launch_gemm<1, true, false, EpiStore>(ta, tb, p, ep, st, "umma selftest MK");
 }
 
 // Self-test of the X-stationary kernel: out[B,C] (fp32) = x[B,D] . w[C,D]^T with fp16 operands, on single CTAs

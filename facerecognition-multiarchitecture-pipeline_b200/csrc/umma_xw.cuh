@@ -39,84 +39,6 @@ constexpr int XW_NUM_BARS = 2 + 2 * XW_STAGES + 4;
 constexpr size_t XW_SMEM_BYTES = 1024 + (size_t)(XW_MAX_KB + XW_STAGES) * XW_TILE_BYTES + XW_SCRATCH_FLOATS * 4 + 256;
 constexpr uint32_t XW_ACC_STRIDE = 256;         // TMEM columns between the two accumulator stages
 
-// ---- cluster / CTA-pair primitives ------------------------------------------------------------------
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// arrive on the mbarrier that sits at the same shared-memory offset in CTA `cta` of the cluster
-__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
-  asm volatile(
-      "{\n\t.reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
-      ::"r"(smem_u32(bar)), "r"(cta)
-      : "memory");
-}
-// TMA load issued by either CTA of a pair; the transaction bytes land on the LEADER CTA's barrier
-// (peer bit of the shared::cluster address cleared).
-__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
-      : "memory");
-}
-// pull a tensor-map box into L2 only (no shared memory, no barrier): hides the HBM latency the 5-stage ring
-// (80 KB in flight per SM) cannot cover on its own when the streamed operand is not L2-resident
-__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int c0, int c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
-               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1)
-               : "memory");
-}
-template <int PAIR>
-__device__ __forceinline__ void xw_tma_load(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
-  if (PAIR == 2) tma_load_2d_pair(smem_dst, m, bar, c0, c1);
-  else tma_load_2d(smem_dst, m, bar, c0, c1);
-}
-template <int PAIR>
-__device__ __forceinline__ void xw_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-  if (PAIR == 2) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-        : "memory");
-  } else {
-    mma_f16_ss(tmem_d, da, db, idesc, accumulate);
-  }
-}
-// completion of all MMAs issued so far -> arrive on `bar` (in BOTH CTAs of a pair)
-template <int PAIR>
-__device__ __forceinline__ void xw_commit(uint64_t* bar) {
-  if (PAIR == 2) {
-    const uint16_t mask = 3;
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(smem_u32(bar)), "h"(mask)
-                 : "memory");
-  } else {
-    mma_commit(bar);
-  }
-}
-template <int PAIR>
-__device__ __forceinline__ void xw_tmem_alloc(uint32_t* slot, uint32_t ncols) {   // whole warp
-  if (PAIR == 2) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-  } else {
-    tmem_alloc(slot, ncols);
-  }
-}
-template <int PAIR>
-__device__ __forceinline__ void xw_tmem_dealloc(uint32_t taddr, uint32_t ncols) {  // whole warp
-  if (PAIR == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-  else tmem_dealloc(taddr, ncols);
-}
-
 // tcgen05.ld without the wait (software pipelining), and a wait that carries the registers as operands so
 // the compiler cannot schedule their uses above it.
 __device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, float (&v)[32]) {

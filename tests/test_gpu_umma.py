@@ -7,10 +7,18 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _run(dev, M, N, K, a_mn, b_mn, fmt=2, k_splits=1):
+def _run(dev, M, N, K, a_mn, b_mn, fmt=2, k_splits=1, pair=2):
     import b200face
     from b200face import _lib
     lib = b200face.load_library()
+    old_pair = lib.b200f_umma_set_pair(pair)
+    try:
+        return _run_pair(lib, _lib, dev, M, N, K, a_mn, b_mn, fmt, k_splits)
+    finally:
+        lib.b200f_umma_set_pair(old_pair)
+
+
+def _run_pair(lib, _lib, dev, M, N, K, a_mn, b_mn, fmt, k_splits):
     g = torch.Generator(device=dev).manual_seed(M + N + K)
     a = torch.randn(M, K, generator=g, device=dev)
     b = torch.randn(N, K, generator=g, device=dev)
@@ -30,17 +38,22 @@ def _run(dev, M, N, K, a_mn, b_mn, fmt=2, k_splits=1):
 @pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1), (1, 0)])
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (512, 1024, 512), (296, 704, 192), (8, 8, 8), (1000, 264, 72)])
 @pytest.mark.parametrize("fmt", [0, 2])
-def test_gemm_core_layouts(cuda_device, a_mn, b_mn, M, N, K, fmt):
-    assert _run(cuda_device, M, N, K, a_mn, b_mn, fmt) < 2e-6
+@pytest.mark.parametrize("pair", [1, 2])
+def test_gemm_core_layouts(cuda_device, a_mn, b_mn, M, N, K, fmt, pair):
+    """pair = 1: cta_group::1 on 128 x 256 tiles; pair = 2: cta_group::2 CTA pairs on 256 x 256 tiles."""
+    assert _run(cuda_device, M, N, K, a_mn, b_mn, fmt, pair=pair) < 2e-6
 
 
-def test_gemm_core_split_k(cuda_device):
-    assert _run(cuda_device, 512, 512, 8192, 0, 1, 2, k_splits=16) < 2e-6
+@pytest.mark.parametrize("pair", [1, 2])
+def test_gemm_core_split_k(cuda_device, pair):
+    assert _run(cuda_device, 512, 512, 8192, 0, 1, 2, k_splits=16, pair=pair) < 2e-6
+    assert _run(cuda_device, 512, 512, 20000, 1, 1, 2, k_splits=18, pair=pair) < 2e-6     # the dX GEMM's layouts
 
 
-def test_gemm_core_many_tiles_persistent(cuda_device):
+@pytest.mark.parametrize("pair", [1, 2])
+def test_gemm_core_many_tiles_persistent(cuda_device, pair):
     """More work items than SMs: the persistent loop, both accumulator stages and the smem ring wrap."""
-    assert _run(cuda_device, 1024, 148 * 256 + 512, 256, 0, 0, 2) < 2e-6
+    assert _run(cuda_device, 1024, 148 * 256 + 512, 256, 0, 0, 2, pair=pair) < 2e-6
 
 
 @pytest.mark.parametrize("pair", [1, 2])
