@@ -16,6 +16,7 @@ the 126 MB L2, so no explicit flush is needed between iterations (config.l2 = "i
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import statistics
@@ -273,17 +274,43 @@ def run_b200(args):
     pk = peaks()
     value = B * args.steps / (ms_total * 1e-3)
     flops_step = 6.0 * B * C_total * D
-    # dominant kernel = the fused forward GEMM+epilogue (K2): 2*B*C_local*D algorithmic FLOP per launch
-    k2_ms = kern.get("arcface_fwd")
+    # Roofline of the DOMINANT kernel of the step (the longest of the four GEMM kernels, each timed alone between
+    # CUDA events the library records on the launching stream, L2 flushed before the stage).  Algorithmic work per
+    # launch: K2 / K3a / K3c 2*B*C*D FLOP; K3b is bounded by bytes: it reads G^T (2 B per
+    # batch row and class, rows padded to 64) and w_hat16 (2*D B per class) and writes dW fp32 (4*D B per class).
+    n_cls = C_local                                           # event pairs are summed over the class chunks of a call
+    roofs = {}
+    gemm_flop = 2.0 * B * C_local * D
+    for k, label in (("k2", "K2 arcface_fwd: cosine GEMM + margin + softmax-CE statistics"),
+                     ("k3a", "K3a logit gradient: cosine GEMM recompute + G^T (fp16) + column sums"),
+                     ("k3c", "K3c dX = G . w_hat (split-K)"),
+                     ("k3b", "K3b dW_hat = G^T . x_hat (batch > 512: both operands streamed, normalise-backward separate)")):
+        if k == "k3b" and B <= 512:
+            continue                                           # fused, byte-bound form: below
+        if kern.get(k) and n_cls:
+            ach = gemm_flop / (kern[k] * 1e-3) / 1e12
+            roofs[k] = {"kernel": label, "bound": "tensor", "achieved": round(ach, 2), "peak": pk["tf_burst"], "unit": "TFLOP/s",
+                        "frac": round(ach / pk["tf_burst"], 4), "traffic": load_traffic(k),
+                        "algorithmic_flop_per_launch": gemm_flop, "avg_launch_ms": round(kern[k], 4)}
+    if kern.get("k3b") and n_cls and B <= 512:
+        ldg = (B + 63) // 64 * 64
+        k3b_bytes = C_local * (2.0 * ldg + 2.0 * D + 4.0 * D) + 2.0 * B * D
+        ach = k3b_bytes / (kern["k3b"] * 1e-3) / 1e9
+        roofs["k3b"] = {"kernel": "K3b dW = G^T . x_hat with the normalise-backward of W fused (reads G^T + w_hat16, writes dW fp32)",
+                        "bound": "hbm", "achieved": round(ach, 1), "peak": pk["hbm"], "unit": "GB/s",
+                        "frac": round(ach / pk["hbm"], 4), "traffic": load_traffic("k3b"),
+                        "algorithmic_bytes_per_launch": k3b_bytes, "avg_launch_ms": round(kern["k3b"], 4)}
     roof = None
-    if k2_ms:
-        ach = 2.0 * B * C_local * D / (k2_ms * 1e-3) / 1e12
-        roof = {"kernel": "K2 arcface_fwd (cosine GEMM + margin + softmax-CE statistics; includes its 6 us partial-record reduction)",
-                "bound": "tensor",
-                "achieved": round(ach, 2), "peak": pk["tf_burst"], "unit": "TFLOP/s",
-                "frac": round(ach / pk["tf_burst"], 4), "traffic": load_traffic("arcface_fwd"),
-                "peak_source": pk["source"] + ", burst figure (kernel timed alone, L2 flushed before each launch)",
-                "algorithmic_flop_per_launch": 2.0 * B * C_local * D, "avg_launch_ms": round(k2_ms, 4)}
+    if roofs:
+        dom = max(roofs, key=lambda k: roofs[k]["avg_launch_ms"])
+        roof = dict(roofs[dom])
+        roof["peak_source"] = pk["source"] + (", burst figure (kernel timed alone)" if roof["bound"] == "tensor" else ", measured copy bandwidth")
+        roof["share_of_step"] = round(roof["avg_launch_ms"] / (ms_total / args.steps), 3)
+    elif kern.get("arcface_fwd"):                              # CUDA-core engine: the fused forward stage as a whole
+        ach = gemm_flop / (kern["arcface_fwd"] * 1e-3) / 1e12
+        roof = {"kernel": "arcface_fwd stage", "bound": "tensor", "achieved": round(ach, 2), "peak": pk["tf_burst"],
+                "unit": "TFLOP/s", "frac": round(ach / pk["tf_burst"], 4), "traffic": None,
+                "avg_launch_ms": round(kern["arcface_fwd"], 4)}
     out = {
         "metric": "arcface_head_samples_per_sec", "value": round(value, 1), "unit": "samples/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -304,6 +331,7 @@ def run_b200(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roof,
+        "roofline_all": {k: {kk: v[kk] for kk in ("bound", "achieved", "peak", "unit", "frac", "avg_launch_ms")} for k, v in roofs.items()},
         "kernel_ms": {k: round(v, 4) for k, v in kern.items()},
         "loss": round(loss_val, 5),
     }
@@ -333,7 +361,9 @@ def time_stages(H, _lib, x, w, y, m_eff, s_eff, c_lo, C_total, eng, dev, reps=10
     cfg = H._head_cfg(m_eff, s_eff, LS, False, C_total, eng)
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
     B = x.shape[0]
-    acc = {"l2norm_rows_w": [], "arcface_fwd": [], "arcface_bwd": []}
+    acc = {"l2norm_rows_w": [], "arcface_fwd": [], "arcface_bwd": [], "k2": [], "k3a": [], "k3b": [], "k3c": []}
+    have_events = H.use_tcgen05(x, eng)                       # the tensor engine records per-kernel event pairs on request
+    ms_c = ctypes.c_float()
     ev = lambda: torch.cuda.Event(enable_timing=True)
     for _ in range(reps + 2):
         f16n = H.use_tcgen05(x, eng)
@@ -342,6 +372,8 @@ def time_stages(H, _lib, x, w, y, m_eff, s_eff, c_lo, C_total, eng, dev, reps=10
         a0, a1 = ev(), ev(); a0.record(); wo, inv_nw = H._k1(w, f16n); a1.record()
         flush.zero_()
         _lib.PROFILE = True; _lib.TIMERS.clear()
+        if have_events:
+            lib.b200f_set_tunable(b"stage_events", 1)
         out = H._fwd_kernels(x, w, y, cfg, c_lo, False)
         row_stats = out[4]
         lse = torch.empty(B, dtype=torch.float32, device=dev); out2 = torch.empty(2, dtype=torch.float32, device=dev)
@@ -354,10 +386,15 @@ def time_stages(H, _lib, x, w, y, m_eff, s_eff, c_lo, C_total, eng, dev, reps=10
         H._bwd_kernels(out[0], out[1], y, out[2], out[3], lse, out4, cfg, c_lo)
         _lib.PROFILE = False
         torch.cuda.synchronize()
+        if have_events:
+            lib.b200f_set_tunable(b"stage_events", 0)
+            for k in ("k2", "k3a", "k3b", "k3c"):
+                _lib.check(lib.b200f_stage_ms(k.encode(), ctypes.byref(ms_c)), "stage_ms")
+                acc[k].append(float(ms_c.value))
         acc["l2norm_rows_w"].append(a0.elapsed_time(a1))
         for k in ("arcface_fwd", "arcface_bwd"):
             acc[k].append(statistics.mean(a.elapsed_time(b) for a, b in _lib.TIMERS[k]))
-    return {k: statistics.mean(v[2:]) for k, v in acc.items()}
+    return {k: statistics.mean(v[2:]) for k, v in acc.items() if v}
 
 
 def load_traffic(kernel):

@@ -78,6 +78,7 @@ PROTOTYPES = {
     "b200f_umma_set_pair": (c_int, [c_int]),
     "b200f_umma_xw_probe": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b200f_set_tunable": (c_int, [c_char_p, c_int]),
+    "b200f_stage_ms": (c_int, [c_char_p, c_void_p]),
     "b200f_gallery_merge": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_float,
                                     c_void_p, c_void_p, c_void_p, c_void_p]),
 }

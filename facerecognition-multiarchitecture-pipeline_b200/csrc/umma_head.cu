@@ -187,7 +187,28 @@ __global__ void reduce_r_kernel(const float* __restrict__ r_part, int n_rb, int6
 static std::atomic<int> g_pair{2};                 // 2 = tcgen05 cta_group::2 CTA pairs, 1 = single CTAs
 static std::atomic<int> g_k3b_class_major{1};       // K3b epilogue: 1 = thread owns a class row (XwDwT), 0 = a feature (XwDw)
 static std::atomic<int> g_k3b_ablate{0};            // probe: 1 = no w_hat loads, 2 = no dW stores (WRONG results)
-static std::atomic<int> g_k3b_reverse{1};           // K3b walks each chunk last tile first
+static std::atomic<int> g_k3b_reverse{1};
+// "stage_events" tunable: record a CUDA event pair around each GEMM kernel of the head on the launching stream
+// (bench.py's per-kernel durations; eager launches only -- never inside a graph capture).
+static std::atomic<int> g_stage_events{0};
+enum { EV_K2 = 0, EV_K3A, EV_K3B, EV_K3C, EV_COUNT };
+static const char* const kEvNames[EV_COUNT] = {"k2", "k3a", "k3b", "k3c"};
+constexpr int EV_MAX_CHUNKS = 32;                       // class chunks of one backward call that get their own event pair
+struct StageEvents { cudaEvent_t beg[EV_COUNT][EV_MAX_CHUNKS], end[EV_COUNT][EV_MAX_CHUNKS]; int n[EV_COUNT] = {}; bool made = false; };
+static thread_local StageEvents g_ev;
+static void stage_reset(int which) { g_ev.n[which] = 0; }
+static void stage_event(int which, bool is_end, cudaStream_t st) {
+  if (!g_stage_events.load(std::memory_order_relaxed)) return;
+  if (!g_ev.made) {
+    for (int i = 0; i < EV_COUNT; ++i)
+      for (int j = 0; j < EV_MAX_CHUNKS; ++j) { cudaEventCreate(&g_ev.beg[i][j]); cudaEventCreate(&g_ev.end[i][j]); }
+    g_ev.made = true;
+  }
+  const int j = g_ev.n[which];
+  if (j >= EV_MAX_CHUNKS) return;
+  cudaEventRecord(is_end ? g_ev.end[which][j] : g_ev.beg[which][j], st);
+  if (is_end) g_ev.n[which] = j + 1;
+}           // K3b walks each chunk last tile first
 static std::atomic<int> g_prefetch{0};             // L2 prefetch distance of the xw producer (stages)
 static std::atomic<int> g_chunk_mb{112};           // budget of the fp16 logit-gradient buffer G per class chunk
 
@@ -390,8 +411,11 @@ int head_fwd(const void* xh, const void* wh, const int64_t* label, int64_t B, in
   ep.part = reinterpret_cast<float*>(ws + pl.off_part);
   ep.cos_part = reinterpret_cast<float*>(ws + pl.off_cos);
   ep.nan_flag = nan_flag; ep.pair = q.pair;
+  stage_reset(EV_K2);
+  stage_event(EV_K2, false, st);
   rc = (q.pair == 2) ? launch_xw<2, XW_KK, XwFwd>(tx, tw, q, B, C, D, ep, st, "umma K2 arcface_fwd (cta pair)")
                      : launch_xw<1, XW_KK, XwFwd>(tx, tw, q, B, C, D, ep, st, "umma K2 arcface_fwd");
+  stage_event(EV_K2, true, st);
   if (rc) return rc;
   launch_pdl(reduce_row_partials_kernel, dim3((unsigned)ceil_div(B, 8)), dim3(256), 0, st, ep.part, q.n_chunks, B, ep.cos_part,
                                                                       q.items * q.pair * XW_EPI_WARPS, row_stats, row_best,
@@ -413,6 +437,7 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
   CUtensorMap tx_k, tx_mn;
   rc = tmap_kmajor(&tx_k, xh, B, D, D, XW_M); if (rc) return rc;
   rc = tmap_mnmajor(&tx_mn, xh, D, B, D); if (rc) return rc;
+  stage_reset(EV_K3A); stage_reset(EV_K3B); stage_reset(EV_K3C);
   const int gpair = pl.fwd.pair;                            // generic core: single CTAs or cta_group::2 pairs, like K2 / K3a
   int chunk_no = 0;
   for (int64_t c0 = 0; c0 < C; c0 += pl.Cc, ++chunk_no) {
@@ -427,8 +452,10 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
     XwBwdGT::Params eg{label, lse, grad4, class_offset + c0, HeadMath{cfg->m_eff, cfg->s_eff, cfg->easy_margin},
                        cfg->label_smoothing, 1.0f / (float)cfg->num_classes_total, 1.0f / (S * S), G, pl.ldg,
                        r_part, pl.Cc};
+    stage_event(EV_K3A, false, st);
     rc = (qg.pair == 2) ? launch_xw<2, XW_SWAP, XwBwdGT>(tx_k, tw_k, qg, B, cnt, D, eg, st, "umma K3a logit-grad (cta pair)")
                         : launch_xw<1, XW_SWAP, XwBwdGT>(tx_k, tw_k, qg, B, cnt, D, eg, st, "umma K3a logit-grad");
+    stage_event(EV_K3A, true, st);
     if (rc) return rc;
     // --- K3b: dW[c0 + c, d] = inv_nw_c (sum_b G^T[c, b] x_hat[b, d] - w_hat[c, d] r_c), computed transposed (the thread
     //     owns a feature d, so a warp writes 128 contiguous bytes of a dW row) with the normalise-backward fused
@@ -436,6 +463,7 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
     launch_pdl(reduce_r_kernel, dim3((unsigned)ceil_div(cnt, 256)), dim3(256), 0, st, r_part, qg.m_groups * 2, pl.Cc, cnt,
                                                                 inv_nw + c0, grad4, S, coef + c0);
     B200F_LAUNCH_OK("umma reduce_r_kernel");
+    stage_event(EV_K3B, false, st);
     if (pl.fused_dw) {                                      // x_hat^T resident, G^T rows streamed
       CUtensorMap tg_k;
       rc = tmap_kmajor(&tg_k, G, cnt, B, pl.ldg, XW_WROWS); if (rc) return rc;
@@ -471,14 +499,17 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
                         : launch_gemm<1, false, true, EpiStore>(tg_km, tx_mn, pw, ew, st, "umma K3b dW (streamed)");
       if (rc) return rc;
     }
+    stage_event(EV_K3B, true, st);
     // --- K3c: dx_hat partials = G[:, k-range] w_hat[c0 + k-range, :]   (A = G read MN-major from G^T)
     CUtensorMap tg_mn, tw_mn;
     rc = tmap_mnmajor(&tg_mn, G, B, cnt, pl.ldg); if (rc) return rc;
     rc = tmap_mnmajor(&tw_mn, wc, D, cnt, D); if (rc) return rc;
     GemmParams px = gemm_params((int)B, D, (int)cnt, pl.dx_splits, true, true, FMT_F16, FMT_F16, gpair);
     EpiStore::Params ex{dxpart, (int64_t)D, B * (int64_t)D, 0, 1.0f, nullptr};
+    stage_event(EV_K3C, false, st);
     rc = (gpair == 2) ? launch_gemm<2, true, true, EpiStore>(tg_mn, tw_mn, px, ex, st, "umma K3c dX (cta pair)")
                       : launch_gemm<1, true, true, EpiStore>(tg_mn, tw_mn, px, ex, st, "umma K3c dX");
+    stage_event(EV_K3C, true, st);
     if (rc) return rc;
     const int64_t n = B * (int64_t)D;
     launch_pdl(reduce_splits_kernel, dim3((unsigned)ceil_div(n / 4, 256)), dim3(256), 0, st, dxpart, px.k_splits, n, dxhat, chunk_no > 0,
@@ -706,11 +737,32 @@ int b200f_set_tunable(const char* name, int value) {
   if (n == "pair") return b200f_umma_set_pair(value);
   if (n == "pdl") { const int old_v = pdl_enabled() ? 1 : 0; if (value == 0 || value == 1) pdl_set(value != 0); return old_v; }
   if (n == "k3b_class_major") { if (value != 0 && value != 1) return g_k3b_class_major.load(); return g_k3b_class_major.exchange(value); }
+  if (n == "stage_events") { if (value != 0 && value != 1) return g_stage_events.load(); return g_stage_events.exchange(value); }
   if (n == "k3b_ablate") { if (value < 0) return g_k3b_ablate.load(); return g_k3b_ablate.exchange(value); }
   if (n == "k3b_reverse") { if (value != 0 && value != 1) return g_k3b_reverse.load(); return g_k3b_reverse.exchange(value); }
   if (n == "xw_prefetch") { if (value < 0) return g_prefetch.load(); return g_prefetch.exchange(value); }
   if (n == "g_chunk_mb") { if (value < 1) return g_chunk_mb.load(); return g_chunk_mb.exchange(value); }
   return -1;
+}
+
+// Duration (ms) of the "k2" | "k3a" | "k3b" | "k3c" kernel(s) of the last head call this thread made while the
+// "stage_events" tunable was 1 (summed over the call's class chunks).  Synchronises on the kernels' end events.
+int b200f_stage_ms(const char* name, float* ms) {
+  if (!name || !ms) return fail(B200F_ERR_ARG, "stage_ms: null argument");
+  for (int i = 0; i < EV_COUNT; ++i) {
+    if (std::string(name) != kEvNames[i]) continue;
+    if (!g_ev.made || g_ev.n[i] == 0) return fail(B200F_ERR_ARG, "stage_ms: no '%s' kernel was recorded on this thread", name);
+    float total = 0.f;
+    for (int j = 0; j < g_ev.n[i]; ++j) {                     // one launch per class chunk of the call: summed
+      float t = 0.f;
+      B200F_CUDA_OK(cudaEventSynchronize(g_ev.end[i][j]));
+      B200F_CUDA_OK(cudaEventElapsedTime(&t, g_ev.beg[i][j], g_ev.end[i][j]));
+      total += t;
+    }
+    *ms = total;
+    return B200F_OK;
+  }
+  return fail(B200F_ERR_ARG, "stage_ms: unknown stage '%s'", name);
 }
 
 // Reads (and optionally clears) the pipeline-timeout flag.  Synchronises: test / bench use only.

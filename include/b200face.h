@@ -214,9 +214,15 @@ int b200f_umma_set_pair(int pair);
 /* pipeline probe: rowsum[b] += sum_c (x . w^T)[b,c] with a do-nothing epilogue (rowsum zeroed by the caller) */
 int b200f_umma_xw_probe(const void* x, const void* w, float* rowsum, int B, int C, int D, int pair, void* stream);
 /* Tunables for tests and bench sweeps: "pair" (1 | 2), "g_chunk_mb" (budget in MB of the fp16 logit-gradient buffer
- * per class chunk of the backward; default 112).  Returns the previous value, -1 for an unknown name.  Workspace
+ * per class chunk of the backward; default 112), "pdl" (0 | 1), "k3b_class_major" (0 | 1), "k3b_reverse" (0 | 1),
+ * "xw_prefetch" (stages), "stage_events" (0 | 1).  Returns the previous value, -1 for an unknown name.  Workspace
  * sizes depend on them: query b200f_head_workspace_bytes again after a change. */
 int b200f_set_tunable(const char* name, int value);
+/* With the tunable "stage_events" = 1 the head calls record a CUDA event pair around each of their GEMM kernels on
+ * the caller's stream (eager launches only, never under graph capture).  b200f_stage_ms returns the duration in ms
+ * of the "k2" (fused forward), "k3a" (logit gradient), "k3b" (dW) or "k3c" (dX) kernels of the calling thread's last
+ * head call, summed over its class chunks; it waits for those kernels.  Measurement aid for bench.py's roofline line. */
+int b200f_stage_ms(const char* name, float* ms);
 
 #ifdef __cplusplus
 }

@@ -19,4 +19,16 @@ for i in range(3):
     loss = arcface_loss(xi, wm, y, compute_weight=w, m_eff=0.45, s_eff=6.72, label_smoothing=0.05)
     loss.backward()
 torch.cuda.synchronize()
-print("loss", float(loss))
+print("loss", float(loss.detach()))
+if os.environ.get("HTIME"):                                  # eager step time, CUDA events (not for use under ncu)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 20
+    e0.record()
+    for i in range(n):
+        wm.grad = None
+        xi = x.clone().requires_grad_(True)
+        loss = arcface_loss(xi, wm, y, compute_weight=w, m_eff=0.45, s_eff=6.72, label_smoothing=0.05)
+        loss.backward()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    print(f"B={B} C={C}: {ms * 1e3:.1f} us per eager step, {3 * 2.0 * B * C * D / ms / 1e9:.0f} TFLOP/s")
