@@ -186,6 +186,7 @@ __global__ void reduce_r_kernel(const float* __restrict__ r_part, int n_rb, int6
 // ---- X-stationary kernel: launch geometry ---------------------------------------------------------
 static std::atomic<int> g_pair{2};                 // 2 = tcgen05 cta_group::2 CTA pairs, 1 = single CTAs
 static std::atomic<int> g_k3b_class_major{1};       // K3b epilogue: 1 = thread owns a class row (XwDwT), 0 = a feature (XwDw)
+static std::atomic<int> g_k3a_ablate{0};            // probe: 2 = no G^T stores (WRONG results)
 static std::atomic<int> g_k3b_ablate{0};            // probe: 1 = no w_hat loads, 2 = no dW stores (WRONG results)
 static std::atomic<int> g_k3b_reverse{1};
 // "stage_events" tunable: record a CUDA event pair around each GEMM kernel of the head on the launching stream
@@ -449,9 +450,11 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
     rc = tmap_kmajor(&tw_k, wc, cnt, D, D, XW_WROWS); if (rc) return rc;
     const XwPlan qg = xw_plan(B, cnt, pl.fwd.pair);
     float* r_part = reinterpret_cast<float*>(ws + pl.off_rpart);
-    XwBwdGT::Params eg{label, lse, grad4, class_offset + c0, HeadMath{cfg->m_eff, cfg->s_eff, cfg->easy_margin},
-                       cfg->label_smoothing, 1.0f / (float)cfg->num_classes_total, 1.0f / (S * S), G, pl.ldg,
-                       r_part, pl.Cc};
+    XwBwdGT::Params eg{};
+    eg.label = label; eg.lse = lse; eg.grad4 = grad4; eg.class_offset = class_offset + c0;
+    eg.hm = HeadMath{cfg->m_eff, cfg->s_eff, cfg->easy_margin};
+    eg.ls_eps = cfg->label_smoothing; eg.inv_Ctot = 1.0f / (float)cfg->num_classes_total; eg.inv_scale = 1.0f / (S * S);
+    eg.GT = G; eg.ldgt = pl.ldg; eg.r_part = r_part; eg.ldr = pl.Cc; eg.ablate = g_k3a_ablate.load(std::memory_order_relaxed);
     stage_event(EV_K3A, false, st);
     rc = (qg.pair == 2) ? launch_xw<2, XW_SWAP, XwBwdGT>(tx_k, tw_k, qg, B, cnt, D, eg, st, "umma K3a logit-grad (cta pair)")
                         : launch_xw<1, XW_SWAP, XwBwdGT>(tx_k, tw_k, qg, B, cnt, D, eg, st, "umma K3a logit-grad");
@@ -738,6 +741,7 @@ int b200f_set_tunable(const char* name, int value) {
   if (n == "pdl") { const int old_v = pdl_enabled() ? 1 : 0; if (value == 0 || value == 1) pdl_set(value != 0); return old_v; }
   if (n == "k3b_class_major") { if (value != 0 && value != 1) return g_k3b_class_major.load(); return g_k3b_class_major.exchange(value); }
   if (n == "stage_events") { if (value != 0 && value != 1) return g_stage_events.load(); return g_stage_events.exchange(value); }
+  if (n == "k3a_ablate") { if (value < 0) return g_k3a_ablate.load(); return g_k3a_ablate.exchange(value); }
   if (n == "k3b_ablate") { if (value < 0) return g_k3b_ablate.load(); return g_k3b_ablate.exchange(value); }
   if (n == "k3b_reverse") { if (value != 0 && value != 1) return g_k3b_reverse.load(); return g_k3b_reverse.exchange(value); }
   if (n == "xw_prefetch") { if (value < 0) return g_prefetch.load(); return g_prefetch.exchange(value); }

@@ -148,7 +148,8 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
   uint64_t* acc_empty = acc_full + 2;                        // [2] epilogue (both CTAs) -> MMA (leader)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + XW_NUM_BARS);
   uint8_t* aux = ring + (size_t)STAGES * XW_TILE_BYTES;       // (XW_STAGES - STAGES) x 16 KB of warp-private staging
-  uint64_t* aux_bar = reinterpret_cast<uint64_t*>(scratch);   // 2 per epilogue warp (such policies leave scratch alone)
+  uint64_t* aux_bar = reinterpret_cast<uint64_t*>(scratch + XW_SCRATCH_FLOATS) - 2 * XW_EPI_WARPS;   // 2 per epilogue
+                                                              // warp, in the last 128 B of the scratch area
   constexpr int AUX_WARP_BYTES = (XW_STAGES - STAGES) * XW_TILE_BYTES / XW_EPI_WARPS;
 
   const int warp = threadIdx.x >> 5;

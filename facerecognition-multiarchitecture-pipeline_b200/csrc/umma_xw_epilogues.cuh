@@ -207,6 +207,9 @@ __device__ __noinline__ void head_phi_dphi(HeadMath hm, float c, float* phi, flo
   *dphi = hm.dphi(c);
 }
 
+// (Measured and rejected: G^T through per-warp TMA tensor stores -- 2 KB staged slices, one ring stage given up --
+//  ran within noise of the 32-byte global stores kept here, 2225 vs 2186 us on one rank's cfg4 step.  Removing the
+//  stores altogether (k3a_ablate = 2) takes 313 us off that step although the kernel moves only 1.6 TB/s.)
 struct XwBwdGT {
   struct Params {
     const int64_t* label; const float* lse; const float* grad4;
@@ -215,6 +218,7 @@ struct XwBwdGT {
     float ls_eps, inv_Ctot, inv_scale;
     uint16_t* GT; int64_t ldgt; // G^T[class of this launch, batch row]
     float* r_part; int64_t ldr; // [2 * m_groups, ldr]: one partial per (row group, column half)
+    int ablate;                 // probe only: 2 = no G^T stores (WRONG results)
   };
   struct State { float gs, r; int cls; bool row_ok; };
 
@@ -250,13 +254,14 @@ struct XwBwdGT {
     const float gs = st.gs;
     const float q_off = ep.ls_eps * ep.inv_Ctot;
     const float gq = gs * q_off;
-    const float* tb = scratch + col0;
+    // explicit ld.shared: through the generic pointer these compile to LD.E, which queues in the global load/store
+    // path behind this kernel's own G^T stores
+    const uint32_t tb_s = smem_u32(scratch + col0);
     float bb[32];
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 t4 = *reinterpret_cast<const float4*>(tb + j);
-      bb[j] = t4.x; bb[j + 1] = t4.y; bb[j + 2] = t4.z; bb[j + 3] = t4.w;
-    }
+    for (int j = 0; j < 32; j += 4)
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(bb[j]), "=f"(bb[j + 1]), "=f"(bb[j + 2]), "=f"(bb[j + 3]) : "r"(tb_s + j * 4));
     float g[32];
     float am4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -274,7 +279,8 @@ struct XwBwdGT {
     asm("max.NaN.xorsign.abs.f32 %0, %0, %1;" : "+f"(amax) : "f"(am4[3]));
     // a target element sits in this slice iff one of its 32 batch rows is labelled with one of the warp's 32 classes
     const int* tl = reinterpret_cast<const int*>(scratch) + p_tn(p) + col0;
-    const int lab_l = tl[it.lane];
+    int lab_l;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(lab_l) : "r"(smem_u32(tl + it.lane)));
     const int c_w0 = st.cls - it.lane;
     bool careful = !(s_eff > 0.f) || (lab_l >= c_w0 && lab_l < c_w0 + 32) || !(fabsf(amax) * isc <= hi);
     careful = __any_sync(0xffffffffu, careful);
@@ -306,7 +312,7 @@ struct XwBwdGT {
       }
     }
     st.r += racc;
-    if (st.row_ok) {
+    if (st.row_ok && !((ep.ablate & 2) && g[0] != 12345.678f)) {
       const int64_t b0 = (int64_t)it.group * p_tn(p) + col0;
       uint16_t* gdst = ep.GT + (int64_t)st.cls * ep.ldgt + b0;
       if (b0 + 32 <= p.B) {

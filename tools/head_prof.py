@@ -7,6 +7,9 @@ import torch
 import b200face
 from b200face.head import arcface_loss
 B, C, D = int(os.environ.get("HB", 4096)), int(os.environ.get("HC", 125000)), 512
+for kv in os.environ.get("HTUNE", "").split(","):            # e.g. HTUNE=k3a_ablate=2,pair=1
+    if "=" in kv:
+        b200face.load_library().b200f_set_tunable(kv.split("=")[0].encode(), int(kv.split("=")[1]))
 dev = torch.device("cuda:0")
 g = torch.Generator(device=dev).manual_seed(1)
 w = (torch.randn(C, D, generator=g, device=dev) * 0.006).bfloat16()

@@ -95,6 +95,48 @@ static int run(const char* name, float* out, uint16_t* in, int64_t rows, int thr
   return 0;
 }
 
+// G^T pattern of K3a: fp16 matrix [rows, ld bytes]; a warp owns 32 rows and walks `span / 2` bytes of each in pieces of
+// PIECE bytes per lane (64 = one 32-column slice, 128 = two); `span` bytes of every row per work item (the 512 B a CTA
+// pair covers per tile), items of the same rows on consecutive CTAs like the kernel's row groups.
+template <int PIECE>
+__global__ void __launch_bounds__(256, 1) gt_kernel(uint16_t* __restrict__ out, int64_t rows, int64_t ld_bytes, int span) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t groups = ld_bytes / span;
+  const int64_t n_items = (rows / 128) * groups;             // item = (128-row block, group), group fastest
+  for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int64_t rb = item / groups, g = item % groups;
+    const int quad = warp & 3, half = warp >> 2;
+    const int64_t row = rb * 128 + quad * 32 + lane;
+    uint8_t* base = reinterpret_cast<uint8_t*>(out) + row * ld_bytes + g * span + half * (span / 2);
+    for (int off = 0; off < span / 2; off += PIECE) {
+#pragma unroll
+      for (int i = 0; i < PIECE / 32; ++i) {
+        const uint32_t a = (uint32_t)(off + i);
+        asm volatile("st.global.v8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"l"(base + off + i * 32), "r"(a) : "memory");
+      }
+    }
+  }
+}
+
+template <int PIECE>
+static int run_gt(const char* name, uint16_t* out, int64_t rows, int64_t ld_bytes, int span, float* flush, size_t flush_n) {
+  CK(cudaFuncSetAttribute(gt_kernel<PIECE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  float best = 1e9f;
+  for (int it = 0; it < 5; ++it) {
+    CK(cudaMemsetAsync(flush, 0, flush_n));
+    CK(cudaEventRecord(e0));
+    gt_kernel<PIECE><<<148, 256, 200 * 1024>>>(out, rows, ld_bytes, span);
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (it > 0 && ms < best) best = ms;
+  }
+  printf("%-26s rows=%6lld ld=%5lld B span=%4d  %7.1f us  %6.2f TB/s\n", name, (long long)rows, (long long)ld_bytes, span,
+         best * 1e3, (double)rows * ld_bytes / best / 1e9);
+  return 0;
+}
+
 int main() {
   const int64_t rows = 100000 / 32 * 32;
   float* out; uint16_t* in; float* flush; const size_t flush_n = 256u << 20;
@@ -106,6 +148,15 @@ int main() {
     if (run<2>("v2 staged, 128 B bulk per lane", out, in, rows, threads, flush, flush_n)) return 1;
     if (run<3>("v3 staged, 4 KB bulk per warp", out, in, rows, threads, flush, flush_n)) return 1;
     if (run<4>("v4 row-per-lane loads 64 B", out, in, rows, threads, flush, flush_n)) return 1;
+  }
+  {
+    uint16_t* gt; CK(cudaMalloc(&gt, (size_t)99968 * 8192));
+    for (int span : {512, 1024, 8192}) {
+      if (run_gt<64>("gt 64 B pieces", gt, 41728, 8192, span, flush, flush_n)) return 1;
+      if (run_gt<128>("gt 128 B pieces", gt, 41728, 8192, span, flush, flush_n)) return 1;
+    }
+    if (run_gt<64>("gt 64 B pieces (cfg3)", gt, 99968, 1024, 512, flush, flush_n)) return 1;
+    if (run_gt<128>("gt 128 B pieces (cfg3)", gt, 99968, 1024, 512, flush, flush_n)) return 1;
   }
   return 0;
 }
