@@ -197,6 +197,7 @@ def run_b200(args):
     # ---- burst figure: 20 steps from an idle GPU (full clocks); the timed region below is long enough for the
     # board power cap to pull the SM clock down (sw_power_cap: 1965 -> ~1670 MHz after 1 s of this step)
     sync_all()
+    sampler = ClockSampler(local) if rank == 0 else None      # started here: nvidia-smi needs ~0.3 s before its first line
     time.sleep(0.5)
     eb0, eb1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     eb0.record()
@@ -211,7 +212,6 @@ def run_b200(args):
     # ---- timed region 1: inputs resident in HBM ------------------------------------------------
     _lib.TIMERS.clear(); _lib.PROFILE = not use_graph
     sync_all()
-    sampler = ClockSampler(local) if rank == 0 else None
     l0 = lib.b200f_launch_count()
     t_wall0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

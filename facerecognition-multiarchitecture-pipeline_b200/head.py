@@ -332,8 +332,37 @@ class GraphedHeadStep:
         self.dx = self.x.grad
 
     def __call__(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        if x.device.type == "cpu":
+            return self._call_from_host(x, y)
         self.x.data.copy_(x, non_blocking=True)
         self.y.copy_(y, non_blocking=True)
+        return self.replay()
+
+    def _call_from_host(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        """Host (pinned) batch: the H2D copies run on a private copy stream into one of two staging slots, so the
+        copy of batch i+1 overlaps the replay of batch i; the replay stream only adds a device-to-device copy of the
+        0.5 MB slot into the graph's static inputs.  As with any non_blocking copy the caller must not overwrite
+        the host tensors of a batch before that batch's copy has run (keep two host buffers, or sync)."""
+        dev = self.weight.device
+        cur = torch.cuda.current_stream(dev)
+        if getattr(self, "_stage", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._stage = []
+            for _ in range(2):
+                free = torch.cuda.Event(); free.record(cur)
+                self._stage.append((torch.empty_like(self.x.data), torch.empty_like(self.y), torch.cuda.Event(), free))
+            self._slot = 0
+        xs, ys, ready, free = self._stage[self._slot]
+        self._slot ^= 1
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(free)            # the replay that consumed this slot two batches ago
+            xs.copy_(x, non_blocking=True)
+            ys.copy_(y, non_blocking=True)
+            ready.record(self._copy_stream)
+        cur.wait_event(ready)
+        self.x.data.copy_(xs, non_blocking=True)
+        self.y.copy_(ys, non_blocking=True)
+        free.record(cur)
         return self.replay()
 
     def replay(self) -> torch.Tensor:

@@ -361,6 +361,35 @@ def test_graphed_step_matches_eager(cuda_device):
         assert torch.equal(head.weight.grad, dw_e)
 
 
+def test_graphed_step_from_pinned_host_batches(cuda_device):
+    """Host batches go through the copy stream and the two staging slots: six different batches issued back to back
+    (no sync in between, one pinned buffer per batch) give the losses / gradients of the same batches fed from the
+    device."""
+    import b200face
+    B, C, D = 128, 3000, 512
+    x, w, y = _random_case(B, C, D, 41)
+    cfg = oracle.HeadConfig(current_epoch=12, training=True, label_smoothing=0.05)
+    head = _head_from_cfg(cfg, C, D, cuda_device, w.bfloat16().float())
+    step = head.graphed_step(B, 0.05, torch.bfloat16)
+    g = torch.Generator().manual_seed(7)
+    xs = [torch.randn(B, D, generator=g).bfloat16() for _ in range(6)]
+    ys = [torch.randint(0, C, (B,), generator=g) for _ in range(6)]
+    want = []
+    for xb, yb in zip(xs, ys):
+        l = step(xb.to(cuda_device), yb.to(cuda_device))
+        torch.cuda.synchronize()
+        want.append((float(l), step.dx.clone(), head.weight.grad.clone()))
+    xh = [t.pin_memory() for t in xs]; yh = [t.pin_memory() for t in ys]
+    got = []
+    for xb, yb in zip(xh, yh):                               # no synchronisation between the calls
+        l = step(xb, yb)
+        got.append((l.clone(), step.dx.clone(), head.weight.grad.clone()))
+    torch.cuda.synchronize()
+    for (lw, dxw, dww), (lg, dxg, dwg) in zip(want, got):
+        assert float(lg) == lw
+        assert torch.equal(dxg, dxw) and torch.equal(dwg, dww)
+
+
 @pytest.mark.parametrize("mb", [4, 112])
 def test_backward_chunking_is_invisible(cuda_device, mb):
     """The class-chunk size of the backward (budget of the fp16 logit-gradient buffer) changes launches, not results."""
