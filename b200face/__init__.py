@@ -14,10 +14,11 @@ from .head import (  # noqa: E402,F401
 from .gallery import (  # noqa: E402,F401
     compare_faces, gallery_topk, cosine_class_match, GalleryIndex, PreparedGallery,
 )
+from .optim import HeadAdamW  # noqa: E402,F401
 from . import parallel  # noqa: E402,F401
 
 __all__ = [
     "ArcMarginProduct", "ArcFaceNet", "arcface_loss", "head_schedule", "HeadStats", "GraphedHeadStep",
     "compare_faces", "gallery_topk", "cosine_class_match", "GalleryIndex", "PreparedGallery",
-    "parallel", "lib_path", "load_library", "LibraryMissingError",
+    "HeadAdamW", "parallel", "lib_path", "load_library", "LibraryMissingError",
 ]

@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--tune", action="append", default=[], metavar="NAME=INT",
                     help="b200f_set_tunable(NAME, INT) before the run (experiments; see csrc/umma_head.cu)")
     ap.add_argument("--no-gallery", action="store_true")
+    ap.add_argument("--no-train-step", action="store_true", help="skip the head + optimizer (K5) measurement")
     return ap.parse_args()
 
 
@@ -353,6 +354,8 @@ def run_b200(args):
         "kernel_ms": {k: round(v, 4) for k, v in kern.items()},
         "loss": round(loss_val, 5),
     }
+    if world == 1 and not args.no_train_step and use_graph and H.use_tcgen05(x, eng):
+        out["train_step"] = bench_train_step(dev, pk, eng, w, x, y)
     if world == 1 and not args.no_gallery:
         out["gallery"] = bench_gallery(dev, pk, eng)
     if world > 1 and gal_sharded is not None:
@@ -424,6 +427,74 @@ def load_traffic(kernel):
             return rec.get("dram_bytes")
         return rec
     return None
+
+
+def bench_train_step(dev, pk, eng, w_bf16, x, y):
+    """SURVEY 8f rank 3 -- the optimizer step right behind the head.  One training step of the head's weights =
+    fwd + bwd (CUDA-graph replay) + AdamW(amsgrad) on the fp32 master [C, D]:
+      unfused: graph with K1 over W inside + torch.optim.AdamW(fused=True) (the reference's optimizer, torch's best kernel)
+      fused  : graph WITHOUT K1 over W + b200f_head_adamw, which also writes next step's normalised fp16 operands.
+    Optimizer kernels are also timed alone (L2 flushed); bytes per launch = C*D*(9*4 + 2) + C*4."""
+    import b200face
+    B, D = x.shape
+    C = w_bf16.shape[0]
+
+    def make_head():
+        h = b200face.ArcMarginProduct(D, C).to(dev)
+        h.update_epoch(EPOCH); h.train(); h.engine = eng; h.compute_dtype = torch.bfloat16
+        with torch.no_grad():
+            h.weight.copy_(w_bf16.float())
+        return h
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
+    res = {}
+
+    def timed_loop(body, n=60):
+        for _ in range(5):
+            body()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            body()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    def timed_alone(fn, n=10):
+        ts = []
+        for _ in range(n + 2):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return statistics.mean(ts[2:])
+    # ---- unfused
+    h = make_head(); h.cache_weight_prep = False
+    opt_t = torch.optim.AdamW([h.weight], lr=1e-3, weight_decay=1e-4, amsgrad=True, fused=True)
+    step = h.graphed_step(B, LS, torch.bfloat16)
+    def unfused():
+        step(x, y); opt_t.step()
+    res["unfused_ms"] = round(timed_loop(unfused), 4)
+    res["torch_fused_adamw_ms"] = round(timed_alone(opt_t.step), 4)
+    del step, opt_t, h
+    torch.cuda.empty_cache()
+    # ---- fused
+    h = make_head()
+    opt_f = b200face.HeadAdamW(h, lr=1e-3, weight_decay=1e-4, amsgrad=True)
+    step = h.graphed_step(B, LS, torch.bfloat16, optimizer=opt_f)
+    def fused():
+        step(x, y); opt_f.step()
+    res["fused_ms"] = round(timed_loop(fused), 4)
+    k5 = timed_alone(opt_f.step)
+    res["b200f_head_adamw_ms"] = round(k5, 4)
+    byt = C * D * (9 * 4 + 2) + C * 4
+    res["k5_algorithmic_bytes"] = byt
+    res["k5_GBps"] = round(byt / (k5 * 1e-3) / 1e9, 1)
+    res["k5_frac_of_hbm_peak"] = round(byt / (k5 * 1e-3) / 1e9 / pk["hbm"], 4)
+    res["samples_per_sec_fused"] = round(B / (res["fused_ms"] * 1e-3), 1)
+    res["samples_per_sec_unfused"] = round(B / (res["unfused_ms"] * 1e-3), 1)
+    res["note"] = ("head fwd+bwd (graph replay) + AdamW(amsgrad) of the fp32 class weights, inputs resident; "
+                   "unfused = K1(W) in the graph + torch.optim.AdamW(fused=True)")
+    return res
 
 
 def bench_gallery(dev, pk, eng):

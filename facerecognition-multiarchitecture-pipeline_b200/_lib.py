@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t,
+from ctypes import (POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t,
                     c_void_p)
 
 import torch
@@ -79,6 +79,9 @@ PROTOTYPES = {
     "b200f_umma_xw_probe": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b200f_set_tunable": (c_int, [c_char_p, c_int]),
     "b200f_stage_ms": (c_int, [c_char_p, c_void_p]),
+    "b200f_head_adamw": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_double, c_double,
+                                 c_double, c_double, c_double, c_int64, c_void_p, c_void_p, c_float, c_float, c_void_p,
+                                 c_void_p]),
     "b200f_gallery_merge": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_float,
                                     c_void_p, c_void_p, c_void_p, c_void_p]),
 }

@@ -336,6 +336,106 @@ static inline void launch_l2norm_bwd(const T* v, float v_scale, const float* inv
   }
 }
 
+// K5 -- AdamW (+ AMSGrad) step of the class-weight rows fused with next step's K1 (the reference
+// trains the head with torch.optim.AdamW(amsgrad=True), src/training.py:343-348, after an optional clip_grad_norm_,
+// :528-533).  Per element, in torch's _single_tensor_adamw order:
+//   p *= 1 - lr * wd;  m += (g - m) * (1 - b1);  v = v * b2 + (1 - b2) * g * g;  vmax = max(vmax, v)
+//   p -= (lr / bc1) * m / (sqrt(vmax or v) / sqrt(bc2) + eps)            with g = dw * grad_scale (the clip coefficient)
+// One warp per row with the whole updated row in registers (dim <= 1024, dim % 4 == 0), so the row norm of the NEW
+// weights is at hand and w_hat16 = w * inv_norm * out_scale and inv_norm leave in the same pass: 9 fp32 streams
+// + 2 B per element (38 B) against 36 B for an unfused AdamW + 6 B for K1 -- and no second kernel on the step's
+// critical path.
+struct AdamWParams {               // scalars rounded to fp32 from the double expressions torch evaluates on the host
+  float decay, one_m_b1, beta2, one_m_b2, step_size, bc2_sqrt, eps;
+  const float* grad_scale;    // device scalar multiplied into the gradient, or NULL
+  float norm_eps, out_scale;
+};
+
+template <bool AMSGRAD, int NV>                               // NV float4 per lane
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+adamw_rows_kernel(float* __restrict__ w, const float* __restrict__ dw, float* __restrict__ m, float* __restrict__ v,
+                  float* __restrict__ vmax, int64_t rows, int dim, AdamWParams p, __half* __restrict__ w_hat,
+                  float* __restrict__ inv_norm) {
+  pdl_trigger(); pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nvec = dim >> 2;
+  const float gs = p.grad_scale ? __ldg(p.grad_scale) : 1.0f;
+  const float decay = p.decay;
+  const float step_size = p.step_size;
+  float4 wv[NV], gv[NV], mv[NV], vv[NV], xv[NV];
+  const int64_t base = row * (int64_t)dim;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {                              // all loads in flight before the first use
+    const int c = lane + 32 * i;
+    if (c < nvec) {
+      wv[i] = *reinterpret_cast<const float4*>(w + base + 4 * c);
+      gv[i] = __ldg(reinterpret_cast<const float4*>(dw + base + 4 * c));
+      mv[i] = *reinterpret_cast<const float4*>(m + base + 4 * c);
+      vv[i] = *reinterpret_cast<const float4*>(v + base + 4 * c);
+      if (AMSGRAD) xv[i] = *reinterpret_cast<const float4*>(vmax + base + 4 * c);
+    }
+  }
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nvec) {
+      float* pw = reinterpret_cast<float*>(&wv[i]); float* pg = reinterpret_cast<float*>(&gv[i]);
+      float* pm = reinterpret_cast<float*>(&mv[i]); float* pv = reinterpret_cast<float*>(&vv[i]);
+      float* px = reinterpret_cast<float*>(&xv[i]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float g = pg[e] * gs;
+        float wn = pw[e] * decay;
+        const float mn = pm[e] + (g - pm[e]) * p.one_m_b1;
+        const float vn = fmaf(pv[e], p.beta2, p.one_m_b2 * g * g);         // mul_(b2).addcmul_(g, g, 1 - b2)
+        float den;
+        if (AMSGRAD) { const float xn = fmaxf(px[e], vn); px[e] = xn; den = sqrtf(xn) / p.bc2_sqrt + p.eps; }
+        else den = sqrtf(vn) / p.bc2_sqrt + p.eps;
+        wn = wn - step_size * (mn / den);
+        pw[e] = wn; pm[e] = mn; pv[e] = vn;
+        ss = fmaf(wn, wn, ss);
+      }
+      *reinterpret_cast<float4*>(w + base + 4 * c) = wv[i];
+      *reinterpret_cast<float4*>(m + base + 4 * c) = mv[i];
+      *reinterpret_cast<float4*>(v + base + 4 * c) = vv[i];
+      if (AMSGRAD) *reinterpret_cast<float4*>(vmax + base + 4 * c) = xv[i];
+    }
+  }
+  if (w_hat == nullptr && inv_norm == nullptr) return;
+  ss = warp_sum(ss);
+  const float inv = 1.0f / fmaxf(sqrtf(ss), p.norm_eps);
+  if (lane == 0 && inv_norm != nullptr) inv_norm[row] = inv;
+  if (w_hat != nullptr) {
+    const float s = inv * p.out_scale;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nvec) {
+        const __half2 lo = __floats2half2_rn(wv[i].x * s, wv[i].y * s), hi = __floats2half2_rn(wv[i].z * s, wv[i].w * s);
+        uint2 o; o.x = *reinterpret_cast<const uint32_t*>(&lo); o.y = *reinterpret_cast<const uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(w_hat + base + 4 * c) = o;
+      }
+    }
+  }
+}
+
+template <bool AMSGRAD>
+static inline bool launch_adamw_rows(float* w, const float* dw, float* m, float* v, float* vmax, int64_t rows, int dim,
+                                     const AdamWParams& p, __half* w_hat, float* inv_norm, cudaStream_t st) {
+  const int nvec = dim >> 2;
+  const unsigned grid = (unsigned)ceil_div(rows, WARPS_PER_BLOCK);
+  const dim3 blk(WARPS_PER_BLOCK * 32);
+  if (nvec <= 32) launch_pdl(adamw_rows_kernel<AMSGRAD, 1>, dim3(grid), blk, 0, st, w, dw, m, v, vmax, rows, dim, p, w_hat, inv_norm);
+  else if (nvec <= 64) launch_pdl(adamw_rows_kernel<AMSGRAD, 2>, dim3(grid), blk, 0, st, w, dw, m, v, vmax, rows, dim, p, w_hat, inv_norm);
+  else if (nvec <= 128) launch_pdl(adamw_rows_kernel<AMSGRAD, 4>, dim3(grid), blk, 0, st, w, dw, m, v, vmax, rows, dim, p, w_hat, inv_norm);
+  else if (nvec <= 256) launch_pdl(adamw_rows_kernel<AMSGRAD, 8>, dim3(grid), blk, 0, st, w, dw, m, v, vmax, rows, dim, p, w_hat, inv_norm);
+  else return false;
+  return true;
+}
+
 // Single block.  row_stats [B,4] -> lse[B], loss (mean), pq_norm2.  Arithmetic in double: only B
 // rows, and sum_j (p-q)^2 cancels badly in fp32 once the target probability approaches 1.
 static __global__ void __launch_bounds__(1024)

@@ -1,5 +1,6 @@
 // C ABI, part 1: runtime (errors, version) and the HBM-bound row kernels (K1, normalise-backward,
 // loss finalize, hook scalar).  Declared in include/b200face.h.
+#include <cmath>
 #include <stdarg.h>
 #include <atomic>
 
@@ -132,6 +133,34 @@ int b200f_arcface_hook_scale(const float* pq_norm2, const float* upstream, int64
   launch_pdl(rowops::hook_scale_kernel, dim3(1), dim3(1), 0, as_stream(stream), pq_norm2, upstream, (double)B, s_eff,
              hook_enabled, max_grad_norm, phase, epoch, out4);
   B200F_LAUNCH_OK("hook_scale_kernel");
+  return B200F_OK;
+}
+
+int b200f_head_adamw(float* w, const float* dw, float* m, float* v, float* vmax, int64_t rows, int dim, double lr,
+                     double beta1, double beta2, double eps, double weight_decay, int64_t step, const float* grad_scale,
+                     void* w_hat_out, float out_scale, float norm_eps, float* inv_norm, void* stream) {
+  if (rows < 0 || dim <= 0 || step < 1) return fail(B200F_ERR_ARG, "head_adamw: bad shape / step (rows=%lld dim=%d step=%lld)",
+                                                    (long long)rows, dim, (long long)step);
+  if (rows == 0) return B200F_OK;
+  if (!w || !dw || !m || !v) return fail(B200F_ERR_ARG, "head_adamw: null pointer");
+  if (dim % 4 != 0 || dim > 1024) return fail(B200F_ERR_UNSUPPORTED, "head_adamw: dim %% 4 == 0 and dim <= 1024 (got %d)", dim);
+  const uintptr_t al = reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(dw) | reinterpret_cast<uintptr_t>(m) |
+                       reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(vmax) | (reinterpret_cast<uintptr_t>(w_hat_out) << 1);
+  if (al & 15) return fail(B200F_ERR_ARG, "head_adamw: buffers must be 16-byte aligned (w_hat 8-byte)");
+  if (!(beta1 >= 0.0 && beta1 < 1.0 && beta2 >= 0.0 && beta2 < 1.0)) return fail(B200F_ERR_ARG, "head_adamw: betas must be in [0, 1)");
+  // torch evaluates these scalar expressions in double on the host and hands each to its kernel as one fp32 value
+  rowops::AdamWParams p{};
+  p.decay = (float)(1.0 - lr * weight_decay);
+  p.one_m_b1 = (float)(1.0 - beta1); p.beta2 = (float)beta2; p.one_m_b2 = (float)(1.0 - beta2);
+  p.step_size = (float)(lr / (1.0 - std::pow(beta1, (double)step)));
+  p.bc2_sqrt = (float)std::sqrt(1.0 - std::pow(beta2, (double)step));
+  p.eps = (float)eps;
+  p.grad_scale = grad_scale; p.norm_eps = norm_eps; p.out_scale = out_scale;
+  cudaStream_t st = as_stream(stream);
+  const bool ok = vmax ? rowops::launch_adamw_rows<true>(w, dw, m, v, vmax, rows, dim, p, static_cast<__half*>(w_hat_out), inv_norm, st)
+                       : rowops::launch_adamw_rows<false>(w, dw, m, v, nullptr, rows, dim, p, static_cast<__half*>(w_hat_out), inv_norm, st);
+  if (!ok) return fail(B200F_ERR_UNSUPPORTED, "head_adamw: unsupported row length %d", dim);
+  B200F_LAUNCH_OK("adamw_rows kernel");
   return B200F_OK;
 }
 

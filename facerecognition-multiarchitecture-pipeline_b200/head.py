@@ -122,6 +122,8 @@ def use_tcgen05(x: torch.Tensor, engine: int, wants_logits: bool = False) -> boo
 def _prepare_weight(w: torch.Tensor, f16n: bool, cache: Optional[dict]):
     """K1 on the class weights; with a cache dict the result is reused until the tensor's version changes
     (optimizer step / load_state_dict).  Training steps change it every step, so bench.py passes no cache."""
+    if cache is not None and f16n and "static" in cache:
+        return cache["static"]                    # operands an optimizer keeps current in place (optim.HeadAdamW)
     key = (w.data_ptr(), w._version, tuple(w.shape), w.dtype, f16n)
     if cache is not None and cache.get("key") == key:
         return cache["val"]
@@ -458,24 +460,27 @@ class ArcMarginProduct(nn.Module):
             return loss, self.last_stats.row_argmax
         return loss
 
-    def graphed_step(self, B, label_smoothing=0.05, dtype=torch.bfloat16):
+    def graphed_step(self, B, label_smoothing=0.05, dtype=torch.bfloat16, optimizer=None):
         """CUDA-graph version of ``loss = forward_loss(x, y, label_smoothing); loss.backward()`` for a fixed batch
         size: returns ``step`` with ``loss = step(x, y)``, ``step.dx`` and ``self.weight.grad`` filled in place.
         The graph bakes in the schedule's (m_eff, s_eff) and the hook state; it is rebuilt when they change
-        (once per epoch during the warm-up, never afterwards)."""
+        (once per epoch during the warm-up, never afterwards).
+        optimizer: an ``optim.HeadAdamW`` on this head -- the graph then reads the normalised operands that optimizer
+        refreshes with every ``step()`` and contains no K1 over the weights."""
         cache = self.__dict__.setdefault("_graphed", {})
+        extra = {} if optimizer is None else {"weight_cache": optimizer.weight_cache}
 
         def step(x, y):
             m_eff, s_eff = self._step_schedule()
             hook = self._hook
             key = (B, float(label_smoothing), dtype, m_eff, s_eff, bool(self.easy_margin), self.engine, hook.enabled,
-                   hook.max_grad_norm, hook.phase, hook.epoch, self.weight.data_ptr())
+                   hook.max_grad_norm, hook.phase, hook.epoch, self.weight.data_ptr(), id(optimizer))
             g = cache.get("step")
             if g is None or cache.get("key") != key:
                 g = GraphedHeadStep(self.weight, B, self.in_feats, dtype=dtype, m_eff=m_eff, s_eff=s_eff,
                                     label_smoothing=label_smoothing, easy_margin=self.easy_margin,
                                     hook=_Hook(hook.enabled, hook.max_grad_norm, hook.phase, hook.epoch),
-                                    engine=self.engine)
+                                    engine=self.engine, **extra)
                 cache["step"], cache["key"] = g, key
             self.last_stats = g.stats
             step.dx = g.dx

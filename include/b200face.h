@@ -151,6 +151,20 @@ int b200f_arcface_bwd(const void* x, const void* w, int dtype,
 int b200f_l2norm_bwd(const void* v, int dtype, float v_scale, const float* inv_norm, const float* dvhat,
                      int64_t rows, int dim, float* dv, void* stream);
 
+/* K5 -- optimizer step of the class-weight rows: torch.optim.AdamW (amsgrad when vmax != NULL) exactly as the
+ * reference trains the head (src/training.py:343-348; default betas (0.9, 0.999), eps 1e-8), after the optional
+ * clip_grad_norm_ of :528-533, whose coefficient the caller passes as the device scalar grad_scale (NULL = 1):
+ *   g = dw * grad_scale;  w *= 1 - lr*wd;  m += (g - m)(1 - b1);  v = b2 v + (1 - b2) g^2;  vmax = max(vmax, v)
+ *   w -= lr / (1 - b1^step) * m / (sqrt(vmax or v) / sqrt(1 - b2^step) + eps)              (step counts from 1)
+ * Fused with NEXT step's K1: when w_hat_out / inv_norm are given they receive, for the updated rows,
+ * inv_norm[r] = 1 / max(||w[r,:]||, norm_eps) and w_hat_out = w * inv_norm * out_scale as B200F_F16N rows -- the
+ * operands b200f_arcface_fwd / _bwd take -- so the head's next forward needs no b200f_l2norm_rows over W.
+ * Hyper-parameters are doubles like torch's Python scalars (1 - beta2 etc. are formed in double, then rounded once).
+ * All tensors fp32, [rows, dim] row-major, dim % 4 == 0, dim <= 1024, 16-byte aligned; w, m, v, vmax updated in place. */
+int b200f_head_adamw(float* w, const float* dw, float* m, float* v, float* vmax, int64_t rows, int dim, double lr,
+                     double beta1, double beta2, double eps, double weight_decay, int64_t step, const float* grad_scale,
+                     void* w_hat_out, float out_scale, float norm_eps, float* inv_norm, void* stream);
+
 /* K4 -- gallery match: for each query the k best rows of this gallery shard.
  *   metric L2EPS: score = || q - g + 1e-6 ||_2 ascending, accept = best <= thresh (src/app.py:50-64)
  *   metric COS  : score = <q,g> * q_inv[i] * g_inv[j] descending, accept = best >= thresh
