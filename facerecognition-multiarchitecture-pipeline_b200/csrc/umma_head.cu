@@ -611,8 +611,9 @@ static int gallery_scan_kt(const GalleryScanPlan& gp, const CUtensorMap& tx, con
   auto kern = gallery_select_kernel<float, KT>;
   B200F_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 160 * 1024 ? 160 * 1024 : (smem < 1024 ? 1024 : smem))));
   if (smem > 160 * 1024) return fail(B200F_ERR_UNSUPPORTED, "gallery scan: candidate lists do not fit shared memory");
-  kern<<<(unsigned)Q, 128, smem, st>>>(ckey, cidx, n_cand, q, g, q_inv, g_inv, bias ? bias + N : nullptr, qbad, Q, D, k, metric,
-                                       fmt, thresh, index_offset, idx, score, accept, redo, redo_count);
+  launch_pdl(kern, dim3((unsigned)Q), dim3(128), smem, st, ckey, cidx, n_cand, q, g, q_inv, g_inv,
+             (const float*)(bias ? bias + N : nullptr), qbad, Q, D, k, metric, fmt, thresh, index_offset, idx, score, accept, redo,
+             redo_count);
   B200F_LAUNCH_OK("gallery_select_kernel");
   return B200F_OK;
 }
