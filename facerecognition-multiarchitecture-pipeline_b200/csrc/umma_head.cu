@@ -336,9 +336,10 @@ static Plan make_plan(int64_t B, int64_t C, int D) {
   // and read twice, all while the tensor pipe (not HBM) is the bound, so it need not stay L2-resident: cfg3's
   // 102 MB is ONE chunk (fewer launches, long per-CTA streams); B = 4096 shards use ~12 k-class chunks.
   const int64_t ldgt = ceil_div(B, 64) * 64;               // G^T[class][batch row], row stride in elements
-  // batches above 512 rows get 4x the budget: long chunks keep the per-launch fill / drain and the wave quantisation
-  // of the streamed K3b small (memory is not the constraint on a 180 GB part)
-  const int64_t budget_mb = (int64_t)g_chunk_mb.load(std::memory_order_relaxed) * (B > (int64_t)XW_MAX_KB * XW_K ? 4 : 1);
+  // batches above 512 rows get 12x the budget (1.3 GB: one rank's share of cfg4 at 8 GPUs is ONE chunk): long chunks
+  // keep the per-launch fill / drain and the wave quantisation small (memory is not the constraint on a 180 GB part;
+  // measured at B = 4096 x 125 k classes: 1 chunk 2147 us, 3 chunks 2193 us, 6 chunks 2322 us)
+  const int64_t budget_mb = (int64_t)g_chunk_mb.load(std::memory_order_relaxed) * (B > (int64_t)XW_MAX_KB * XW_K ? 12 : 1);
   int64_t cc_max = (budget_mb * (1 << 20) / 2 / ldgt) / BLOCK_N * BLOCK_N;
   if (cc_max < BLOCK_N) cc_max = BLOCK_N;
   pl.n_chunks = (int)ceil_div(C, cc_max);

@@ -390,13 +390,14 @@ def test_graphed_step_from_pinned_host_batches(cuda_device):
         assert torch.equal(dxg, dxw) and torch.equal(dwg, dww)
 
 
-@pytest.mark.parametrize("mb", [4, 112])
-def test_backward_chunking_is_invisible(cuda_device, mb):
-    """The class-chunk size of the backward (budget of the fp16 logit-gradient buffer) changes launches, not results."""
+@pytest.mark.parametrize("mb,B,C", [(4, 384, 9000), (112, 384, 9000), (1, 640, 24000)])
+def test_backward_chunking_is_invisible(cuda_device, mb, B, C):
+    """The class-chunk size of the backward (budget of the fp16 logit-gradient buffer) changes launches, not results.
+    (1, 640, 24000): three chunks on the batch > 512 path (both dW operands streamed, separate normalise-backward)."""
     import b200face
     from b200face import _lib
     lib = _lib.load_library()
-    B, C, D = 384, 9000, 512
+    D = 512
     x, w, y = _random_case(B, C, D, 31)
     cfg = oracle.HeadConfig(current_epoch=12, training=True, label_smoothing=0.05)
     old = lib.b200f_set_tunable(b"g_chunk_mb", mb)
