@@ -58,5 +58,63 @@ struct EpiStore {
   }
 };
 
+// -------------------------------------------------------------------------------------------------
+// dW GEMM with both operands streamed (batch > 512): A = G^T rows, so an epilogue thread owns a class row and 256 of
+// its features, and the normalise-backward of W is finished here like in the X-stationary K3b:
+//   dW[c, d] = coef_c.x * (acc[c, d] - wh[c, d] * coef_c.y)      coef from reduce_r_kernel, wh = K1's fp16 rows.
+// A tile's main loop runs K = batch >= 576 deep (>= 9 k-blocks of 256 x 256 x 64), so the 128 x 256 epilogue with its
+// row-per-lane loads of wh is a small fraction of the tile: fusing it removes the separate pass over dW (read + write of
+// 4 B per element plus the wh read) that used to follow.
+struct EpiDwNorm {
+  struct Params { float* out; int64_t ld; int64_t row_offset; const float2* coef; const __half* wh; };
+  static __device__ __forceinline__ void run(const Params& ep, const GemmParams& p, const TileCoord& t,
+                                             uint32_t tmem_acc, int quad, int lane, int epi_tid, float* scratch) {
+    const int row = t.m0 + quad * 32 + lane;
+    const int ncols = min(BLOCK_N, p.N - t.n0);
+    const bool row_ok = row < p.M;
+    float2 cf = make_float2(0.f, 0.f);
+    if (row_ok) cf = __ldg(ep.coef + ep.row_offset + row);
+    const int64_t base = (ep.row_offset + row) * ep.ld + t.n0;
+    const bool vec = (ep.ld % 8 == 0);
+    for (int ch = 0; ch * 32 < ncols; ++ch) {
+      float v[32];
+      tmem_ld32(tmem_acc + ((uint32_t)(quad * 32) << 16) + ch * 32, v);
+      uint4 w4[4];
+      const int cc = min(32, ncols - ch * 32);
+      const bool full = row_ok && cc == 32 && vec;
+      if (full) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w4[i] = __ldg(reinterpret_cast<const uint4*>(ep.wh + base + ch * 32) + i);
+      }
+      tmem_ld_wait();
+      if (!row_ok) continue;
+      float* dst = ep.out + base + ch * 32;
+      if (full) {
+        float o[32];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t q[4] = {w4[i].x, w4[i].y, w4[i].z, w4[i].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&q[j]));
+            o[i * 8 + 2 * j] = cf.x * fmaf(-f.x, cf.y, v[i * 8 + 2 * j]);
+            o[i * 8 + 2 * j + 1] = cf.x * fmaf(-f.y, cf.y, v[i * 8 + 2 * j + 1]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 8)
+          st_global_256(dst + j, __float_as_uint(o[j]), __float_as_uint(o[j + 1]), __float_as_uint(o[j + 2]),
+                        __float_as_uint(o[j + 3]), __float_as_uint(o[j + 4]), __float_as_uint(o[j + 5]),
+                        __float_as_uint(o[j + 6]), __float_as_uint(o[j + 7]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < cc) dst[j] = cf.x * fmaf(-__half2float(__ldg(ep.wh + base + ch * 32 + j)), cf.y, v[j]);
+      }
+    }
+    (void)epi_tid; (void)scratch;
+  }
+};
+
 }  // namespace umma
 }  // namespace b200f

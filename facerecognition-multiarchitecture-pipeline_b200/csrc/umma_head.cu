@@ -492,15 +492,15 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
       if (rc) return rc;
     } else {
       // batch > 512: x_hat^T cannot stay resident, both operands stream through the generic core:
-      // dW_hat[c0 + m, :] = sum_b G^T[m, b] x_hat[b, :], normalise-backward afterwards (one pass over dW).
-      // (A fused transposed epilogue on this core measured 2.3x slower at B = 4096: 4 epilogue warps, unpipelined
-      //  TMEM reads, per-element global loads.)
+      // acc[m, :] = sum_b G^T[m, b] x_hat[b, :] with the class rows on the M side, so the epilogue thread owns a class
+      // row and finishes the normalise-backward in place (EpiDwNorm) -- no separate pass over dW.
+      // (An earlier TRANSPOSED fused epilogue on this core measured 2.3x slower at B = 4096: per-element global loads.)
       CUtensorMap tg_km;
       rc = tmap_kmajor(&tg_km, G, cnt, B, pl.ldg, BLOCK_M); if (rc) return rc;
       GemmParams pw = gemm_params((int)cnt, D, (int)B, 1, false, true, FMT_F16, FMT_F16, gpair);
-      EpiStore::Params ew{dw, (int64_t)D, 0, c0, 1.0f / S, grad4 + 3};
-      rc = (gpair == 2) ? launch_gemm<2, false, true, EpiStore>(tg_km, tx_mn, pw, ew, st, "umma K3b dW (streamed, cta pair)")
-                        : launch_gemm<1, false, true, EpiStore>(tg_km, tx_mn, pw, ew, st, "umma K3b dW (streamed)");
+      EpiDwNorm::Params ew{dw, (int64_t)D, c0, coef, static_cast<const __half*>(wh)};
+      rc = (gpair == 2) ? launch_gemm<2, false, true, EpiDwNorm>(tg_km, tx_mn, pw, ew, st, "umma K3b dW (streamed, cta pair)")
+                        : launch_gemm<1, false, true, EpiDwNorm>(tg_km, tx_mn, pw, ew, st, "umma K3b dW (streamed)");
       if (rc) return rc;
     }
     stage_event(EV_K3B, true, st);
@@ -519,11 +519,6 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
     launch_pdl(reduce_splits_kernel, dim3((unsigned)ceil_div(n / 4, 256)), dim3(256), 0, st, dxpart, px.k_splits, n, dxhat, chunk_no > 0,
                                                                         1.0f / S, grad4 + 3);
     B200F_LAUNCH_OK("umma reduce_splits_kernel");
-  }
-  if (!pl.fused_dw) {
-    // normalise-backward of the weight rows, in place: dw <- inv_nw * (dw_hat - w_hat <w_hat, dw_hat>)
-    rowops::launch_l2norm_bwd<__half, true>(static_cast<const __half*>(wh), S, inv_nw, dw, C, D, dw, st);
-    B200F_LAUNCH_OK("l2norm_bwd kernel (weights)");
   }
   return B200F_OK;
 }
