@@ -98,30 +98,24 @@ struct XwFwd {
     const float lo = cos_lo(), hi = cos_hi();
     // four independent accumulator lanes: the dependent chains are 8 long, not 32 (latency, not issue, bounds
     // a lone epilogue warp); the summation order is still fixed, so results are bitwise reproducible
-    // The FMA-pipe work runs as packed fp32x2 instructions (sm_100 FFMA2 / FADD2): the FMA pipe takes one warp
-    // instruction per two cycles and scheduler, and at four FMA-pipe operations per logit it, not the issue port, was
-    // the epilogue's largest single cost.  Element j still lands in accumulator lane j % 4 and the lanes are combined
-    // in the same order, so the sums are bit-identical to the scalar version.
-    float2 ce2v[2] = {{0.f, 0.f}, {0.f, 0.f}}, cq2v[2] = {{0.f, 0.f}, {0.f, 0.f}}, ct2v[2] = {{0.f, 0.f}, {0.f, 0.f}};
+    float ce4[4] = {0.f, 0.f, 0.f, 0.f}, cq4[4] = {0.f, 0.f, 0.f, 0.f}, ct4[4] = {0.f, 0.f, 0.f, 0.f};
     float mn4[4] = {INFINITY, INFINITY, INFINITY, INFINITY}, mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-    const float2 a2 = make_float2(a, a), b2 = make_float2(b, b);
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const float2 t2 = make_float2(v[j + 2 * u], v[j + 2 * u + 1]);
-        const float2 arg = __ffma2_rn(t2, a2, b2);
-        const float2 e2 = make_float2(ex2_approx(arg.x), ex2_approx(arg.y));
-        ce2v[u] = __fadd2_rn(ce2v[u], e2);
-        cq2v[u] = __ffma2_rn(e2, e2, cq2v[u]);
-        ct2v[u] = __fadd2_rn(ct2v[u], t2);
-        mn4[2 * u] = fminf(mn4[2 * u], t2.x); mn4[2 * u + 1] = fminf(mn4[2 * u + 1], t2.y);
-        mx4[2 * u] = fmaxf(mx4[2 * u], t2.x); mx4[2 * u + 1] = fmaxf(mx4[2 * u + 1], t2.y);
+      for (int u = 0; u < 4; ++u) {
+        const float tt = v[j + u];
+        const float e = ex2_approx(fmaf(tt, a, b));
+        ce4[u] += e;
+        cq4[u] = fmaf(e, e, cq4[u]);
+        ct4[u] += tt;
+        mn4[u] = fminf(mn4[u], tt);
+        mx4[u] = fmaxf(mx4[u], tt);
       }
     }
-    const float ce = (ce2v[0].x + ce2v[0].y) + (ce2v[1].x + ce2v[1].y);
-    const float ce2 = (cq2v[0].x + cq2v[0].y) + (cq2v[1].x + cq2v[1].y);
-    const float ct = (ct2v[0].x + ct2v[0].y) + (ct2v[1].x + ct2v[1].y);
+    const float ce = (ce4[0] + ce4[1]) + (ce4[2] + ce4[3]);
+    const float ce2 = (cq4[0] + cq4[1]) + (cq4[2] + cq4[3]);
+    const float ct = (ct4[0] + ct4[1]) + (ct4[2] + ct4[3]);
     const float tmn = fminf(fminf(mn4[0], mn4[1]), fminf(mn4[2], mn4[3]));
     const float tmx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
     const bool has_t = (st.tgt >= cls0) && (st.tgt < cls0 + 32);
@@ -270,17 +264,13 @@ struct XwBwdGT {
                    : "=f"(bb[j]), "=f"(bb[j + 1]), "=f"(bb[j + 2]), "=f"(bb[j + 3]) : "r"(tb_s + j * 4));
     float g[32];
     float am4[4] = {0.f, 0.f, 0.f, 0.f};
-    const float2 a2 = make_float2(a, a), gs2 = make_float2(gs, gs), ngq2 = make_float2(-gq, -gq);
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {                            // packed fp32x2 on the FMA pipe (see XwFwd::slice)
-        const float2 t2 = make_float2(v[j + 2 * u], v[j + 2 * u + 1]);
-        const float2 arg = __ffma2_rn(t2, a2, make_float2(bb[j + 2 * u], bb[j + 2 * u + 1]));
-        const float2 g2 = __ffma2_rn(gs2, make_float2(ex2_approx(arg.x), ex2_approx(arg.y)), ngq2);
-        g[j + 2 * u] = g2.x; g[j + 2 * u + 1] = g2.y;
-        asm("max.NaN.xorsign.abs.f32 %0, %0, %1;" : "+f"(am4[2 * u]) : "f"(t2.x));
-        asm("max.NaN.xorsign.abs.f32 %0, %0, %1;" : "+f"(am4[2 * u + 1]) : "f"(t2.y));
+      for (int u = 0; u < 4; ++u) {
+        const float tt = v[j + u];
+        g[j + u] = fmaf(gs, ex2_approx(fmaf(tt, a, bb[j + u])), -gq);
+        asm("max.NaN.xorsign.abs.f32 %0, %0, %1;" : "+f"(am4[u]) : "f"(tt));
       }
     }
     float amax = 0.f;
@@ -296,14 +286,13 @@ struct XwBwdGT {
     careful = __any_sync(0xffffffffu, careful);
     float racc = 0.f;
     if (!careful) {
-      float2 r2[2] = {{0.f, 0.f}, {0.f, 0.f}};
+      float r4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
 #pragma unroll
-        for (int u = 0; u < 2; ++u)
-          r2[u] = __ffma2_rn(make_float2(g[j + 2 * u], g[j + 2 * u + 1]), make_float2(v[j + 2 * u], v[j + 2 * u + 1]), r2[u]);
+        for (int u = 0; u < 4; ++u) r4[u] = fmaf(g[j + u], v[j + u], r4[u]);
       }
-      racc = (r2[0].x + r2[0].y) + (r2[1].x + r2[1].y);
+      racc = (r4[0] + r4[1]) + (r4[2] + r4[3]);
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
