@@ -334,6 +334,35 @@ def test_cfg3_full_size_properties(cuda_device, dtype):
     assert float(l3) == pytest.approx(float(ref["loss"]), rel=TOL_BF16)
     assert rel_err(head3.weight.grad.cpu().numpy(), ref["dw"]) < TOL_BF16
 
+def test_cfg4_rank_shape_tensor_engine_vs_fp32_engine(cuda_device):
+    """One rank's share of cfg4 (batch 4096 x 125 000 classes x 512): too large for the CPU oracle, so the tcgen05
+    engine (16 row groups, one 1 GB class chunk of G^T, dW through the streamed pair GEMM with the fused
+    normalise-backward) is held against the fp32 CUDA-core engine -- itself oracle-checked at small sizes -- on the
+    same bf16-rounded inputs, to the bf16 tolerance."""
+    import b200face
+    from b200face import _lib
+    B, C, D = 4096, 125_000, 512
+    x, w, y = _random_case(B, C, D, 4096)                     # 12.5 % of the rows planted near their class centre
+    x, w = x.bfloat16(), w.bfloat16()
+    out = {}
+    for name, eng, dt in (("tc", _lib.ENGINE_AUTO, torch.bfloat16), ("fp32", _lib.ENGINE_SIMT, torch.float32)):
+        head = b200face.ArcMarginProduct(D, C).to(cuda_device)
+        head.update_epoch(12); head.train(); head.engine = eng
+        with torch.no_grad():
+            head.weight.copy_(w.float())
+        xg = x.to(dt).to(cuda_device).requires_grad_(True)
+        loss = head.forward_loss(xg, y.to(cuda_device), 0.05)
+        loss.backward()
+        torch.cuda.synchronize()
+        out[name] = (float(loss), head.last_stats.dx_f32.clone(), head.weight.grad.clone(), head.last_stats.row_argmax.clone())
+        del head
+    assert _lib.load_library().b200f_umma_timeout_flag(1) == 0
+    (lt, dxt, dwt, at), (lf, dxf, dwf, af) = out["tc"], out["fp32"]
+    assert lt == pytest.approx(lf, rel=TOL_BF16)
+    assert float((dxt - dxf).norm() / dxf.norm()) < TOL_BF16
+    assert float((dwt - dwf).norm() / dwf.norm()) < TOL_BF16
+    assert float((at == af).float().mean()) > 0.995
+
 
 def test_graphed_step_matches_eager(cuda_device):
     """CUDA-graph replay of the fused step (ArcMarginProduct.graphed_step) == the eager forward_loss + backward,
