@@ -56,6 +56,7 @@ def parse():
                     help="b200f_set_tunable(NAME, INT) before the run (experiments; see csrc/umma_head.cu)")
     ap.add_argument("--no-gallery", action="store_true")
     ap.add_argument("--no-train-step", action="store_true", help="skip the head + optimizer (K5) measurement")
+    ap.add_argument("--no-cfg4", action="store_true", help="skip the 1-GPU run of cfg4 (the scaling anchor) on the N = 1 line")
     return ap.parse_args()
 
 
@@ -358,6 +359,12 @@ def run_b200(args):
     }
     if world == 1 and not args.no_train_step and use_graph and H.use_tcgen05(x, eng):
         out["train_step"] = bench_train_step(dev, pk, eng, w, x, y)
+    if world == 1 and not args.no_cfg4 and use_graph and H.use_tcgen05(x, eng):
+        del gstep
+        torch.cuda.empty_cache()
+        out["cfg4_single_gpu"] = bench_cfg4_single_gpu(dev, eng, m_eff, s_eff)
+    out["scaling_note"] = ("N = 1 runs cfg3 (100k classes, batch 512) and N >= 2 run cfg4 (1M classes class-sharded, batch 4096), "
+                           "as BASELINE.json's configs name them; cfg4's own 1-GPU anchor is `cfg4_single_gpu` on the N = 1 line")
     if gal_single is not None:
         out["gallery"] = gal_single
     if world > 1 and gal_sharded is not None:
@@ -429,6 +436,31 @@ def load_traffic(kernel):
             return rec.get("dram_bytes")
         return rec
     return None
+
+
+def bench_cfg4_single_gpu(dev, eng, m_eff, s_eff):
+    """cfg4 (1 M classes, batch 4096) on ONE GPU: the 1-GPU anchor of the class-parallel scaling line (the N = 1 bench
+    line itself is cfg3, as BASELINE.json's configs prescribe).  20 graph replays after 3, device-resident inputs."""
+    from b200face.head import GraphedHeadStep
+    c = CFG4
+    x, w, y = synth_head(c["B"], c["C"], c["D"], 0, dev, 0, c["C"])
+    w_master = w.float().requires_grad_(True)
+    g = GraphedHeadStep(w_master, c["B"], c["D"], dtype=torch.bfloat16, warmup=1, compute_weight=w, m_eff=m_eff, s_eff=s_eff,
+                        label_smoothing=LS, class_offset=0, num_classes_total=c["C"], group=None, engine=eng)
+    g(x, y)
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 20
+    e0.record()
+    for _ in range(n):
+        g.replay()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    return {"workload": "cfg4 on 1 GPU: ArcFace head 512-d, 1M classes (unsharded), batch 4096, bf16 fwd+bwd",
+            "ms_per_step": round(ms, 4), "value": round(c["B"] / (ms * 1e-3), 1), "unit": "samples/s", "steps": n,
+            "algorithmic_tflops": round(6.0 * c["B"] * c["C"] * c["D"] / (ms * 1e-3) / 1e12, 1)}
 
 
 def bench_train_step(dev, pk, eng, w_bf16, x, y):
