@@ -16,6 +16,7 @@
 
 #include <cudaTypedefs.h>
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 
 namespace b200f {
@@ -738,6 +739,8 @@ int b200f_set_tunable(const char* name, int value) {
   if (n == "pdl") { const int old_v = pdl_enabled() ? 1 : 0; if (value == 0 || value == 1) pdl_set(value != 0); return old_v; }
   if (n == "k3b_class_major") { if (value != 0 && value != 1) return g_k3b_class_major.load(); return g_k3b_class_major.exchange(value); }
   if (n == "stage_events") { if (value != 0 && value != 1) return g_stage_events.load(); return g_stage_events.exchange(value); }
+  // probes that make the backward skip memory traffic (WRONG results): refused unless the process opts in
+  if ((n == "k3a_ablate" || n == "k3b_ablate") && std::getenv("B200F_ALLOW_PROBES") == nullptr) return -1;
   if (n == "k3a_ablate") { if (value < 0) return g_k3a_ablate.load(); return g_k3a_ablate.exchange(value); }
   if (n == "k3b_ablate") { if (value < 0) return g_k3b_ablate.load(); return g_k3b_ablate.exchange(value); }
   if (n == "k3b_reverse") { if (value != 0 && value != 1) return g_k3b_reverse.load(); return g_k3b_reverse.exchange(value); }

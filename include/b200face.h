@@ -229,7 +229,8 @@ int b200f_umma_set_pair(int pair);
 int b200f_umma_xw_probe(const void* x, const void* w, float* rowsum, int B, int C, int D, int pair, void* stream);
 /* Tunables for tests and bench sweeps: "pair" (1 | 2), "g_chunk_mb" (budget in MB of the fp16 logit-gradient buffer
  * per class chunk of the backward; default 112), "pdl" (0 | 1), "k3b_class_major" (0 | 1), "k3b_reverse" (0 | 1),
- * "xw_prefetch" (stages), "stage_events" (0 | 1).  Returns the previous value, -1 for an unknown name.  Workspace
+ * "xw_prefetch" (stages), "stage_events" (0 | 1).  "k3a_ablate" / "k3b_ablate" are measurement probes that skip memory
+ * traffic and produce WRONG gradients: refused (-1) unless the environment variable B200F_ALLOW_PROBES is set.  Returns the previous value, -1 for an unknown name.  Workspace
  * sizes depend on them: query b200f_head_workspace_bytes again after a change. */
 int b200f_set_tunable(const char* name, int value);
 /* With the tunable "stage_events" = 1 the head calls record a CUDA event pair around each of their GEMM kernels on
