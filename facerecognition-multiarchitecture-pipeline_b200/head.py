@@ -567,13 +567,22 @@ class ArcFaceNet(nn.Module):
     def set_max_grad_norm(self, max_norm):
         self.max_grad_norm = max_norm
 
-    def _tail(self, x, training):
+    def _tail(self, x, training, normalize=True):
+        """features -> Linear(512,512) -> BatchNorm1d -> dropout (train) -> F.normalize (src/face_models.py:516-525).
+        normalize=False returns the row BEFORE the L2 normalise: the head's K1 normalises its input anyway
+        (face_models.py:351), and normalising a unit vector again is the identity in value and in gradient, so the
+        training paths hand the head the un-normalised row and the reference's double normalise (:525 + :351)
+        costs one fused kernel each way instead of a chain of eight torch kernels."""
         x = self.features(x)
         x = x.view(x.size(0), -1)
         x = self.embedding(x)
         x = self.bn(x)
         if training:
             x = self.dropout(x)
+        if not normalize:
+            return x
+        if not torch.is_grad_enabled() and x.is_cuda and x.dtype in (torch.float32, torch.bfloat16):
+            return l2_normalize(x)[0]                         # K1 (no autograd needed)
         return F.normalize(x, p=2, dim=1, eps=1e-12)
 
     def _arm_hook(self):
@@ -583,13 +592,14 @@ class ArcFaceNet(nn.Module):
         self._hook_armed = True
 
     def forward(self, x, labels=None):
-        emb = self._tail(x, self.training)
         if self.training:
             if labels is None:
                 raise ValueError("Labels must be provided during training")
+            pre = self._tail(x, True, normalize=not x.is_cuda)   # CUDA: the head's K1 does the (single) normalise
             self.arcface.update_epoch(self.current_epoch)
             self._arm_hook()
-            return self.arcface(emb, labels)
+            return self.arcface(pre, labels)
+        emb = self._tail(x, False)
         self.val_classifier.weight.data = F.normalize(self.val_classifier.weight.data, p=2, dim=1, eps=1e-12)
         if labels is not None:
             return self.val_classifier(emb)
@@ -599,17 +609,13 @@ class ArcFaceNet(nn.Module):
         """Fused training step head: == criterion(self(x, labels), labels) incl. the hook."""
         if labels is None:
             raise ValueError("Labels must be provided during training")
-        emb = self._tail(x, self.training)
+        pre = self._tail(x, self.training, normalize=not x.is_cuda)
         self.arcface.update_epoch(self.current_epoch)
         self._arm_hook()
-        return self.arcface.forward_loss(emb, labels, label_smoothing, return_pred)
+        return self.arcface.forward_loss(pre, labels, label_smoothing, return_pred)
 
     def get_embedding(self, x):
-        x = self.features(x)
-        x = x.view(x.size(0), -1)
-        x = self.embedding(x)
-        x = self.bn(x)
-        return F.normalize(x, p=2, dim=1, eps=1e-12)
+        return self._tail(x, False)                           # no dropout (src/face_models.py:584-590)
 
     def update_epoch(self, epoch):
         self.current_epoch = epoch

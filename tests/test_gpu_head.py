@@ -135,6 +135,35 @@ def test_arcfacenet_hook_arms_after_first_forward(cuda_device):
     with pytest.raises(ValueError, match="Labels must be provided during training"):
         net(img)
 
+def test_arcfacenet_single_normalise_equals_double(cuda_device):
+    """ArcFaceNet hands the head the row BEFORE F.normalize (the head's K1 normalises it): same loss and the same
+    gradients as the reference's normalise-then-normalise-again chain (src/face_models.py:525 + :351)."""
+    import b200face
+    import torch.nn.functional as F
+    torch.manual_seed(1)
+    net = b200face.ArcFaceNet(num_classes=12).to(cuda_device).train()
+    net.dropout.p = 0.0                                       # deterministic
+    img = torch.randn(8, 3, 64, 64, device=cuda_device)
+    y = torch.tensor([0, 3, 5, 11, 2, 2, 7, 9], device=cuda_device)
+    net.zero_grad()
+    l1 = net.forward_loss(img, y)
+    l1.backward()
+    g1 = net.embedding.weight.grad.clone(); gw1 = net.arcface.weight.grad.clone()
+    net.zero_grad()
+    emb = net._tail(img, True)                                # the reference chain: normalised embedding ...
+    assert torch.allclose(emb.norm(dim=1), torch.ones(8, device=cuda_device), atol=1e-5)
+    l2 = net.arcface.forward_loss(emb, y, 0.05)               # ... normalised again inside the head
+    l2.backward()
+    assert float(l1) == pytest.approx(float(l2), rel=1e-6)
+    assert rel_err(g1.cpu().numpy(), net.embedding.weight.grad.cpu().numpy()) < 1e-5
+    assert rel_err(gw1.cpu().numpy(), net.arcface.weight.grad.cpu().numpy()) < 1e-5
+    net.eval()
+    with torch.no_grad():
+        e = net.get_embedding(img)                            # K1 path
+        e_ref = F.normalize(net.bn(net.embedding(net.features(img).view(8, -1))), p=2, dim=1, eps=1e-12)
+    assert torch.allclose(e, e_ref, atol=1e-6)
+
+
 
 # ------------------------------------------------------------------ oracle on seeded inputs
 def _random_case(B, C, D, seed, planted=0.125, noise=1.0):
