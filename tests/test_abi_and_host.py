@@ -131,6 +131,25 @@ def test_arcfacenet_surface_and_errors():
     st = net.get_arcface_stats()
     assert st["grad_norm"] == 0.0 and st["max_grad_norm"] == 1.0 and st["phase"] == 2
 
+def test_head_adamw_argument_validation_and_no_cpu_fallback(lib):
+    """b200f_head_adamw rejects bad arguments before touching a device; HeadAdamW refuses CPU tensors."""
+    import ctypes
+    import b200face
+    from b200face import _lib
+    one = ctypes.c_void_p(16)                                   # non-null, 16-byte aligned, never dereferenced
+    call = lambda rows, dim, step, w=one, b1=0.9: lib.b200f_head_adamw(
+        w, one, one, one, None, rows, dim, 1e-3, b1, 0.999, 1e-8, 1e-2, step, None, None, 256.0, 1e-12, None, None)
+    assert call(0, 512, 1) == 0                                  # nothing to do
+    assert call(4, 510, 1) < 0 and b"dim" in lib.b200f_last_error()
+    assert call(4, 2048, 1) < 0
+    assert call(4, 512, 0) < 0                                   # steps count from 1
+    assert call(4, 512, 1, w=None) < 0
+    assert call(4, 512, 1, w=ctypes.c_void_p(8)) < 0             # misaligned
+    assert call(4, 512, 1, b1=1.0) < 0
+    with pytest.raises(RuntimeError, match="CUDA"):
+        b200face.HeadAdamW(torch.zeros(4, 16))
+
+
 
 def test_shard_bounds_cover_everything():
     from b200face.parallel import shard_bounds
