@@ -35,9 +35,10 @@ constexpr int XW_TILE_BYTES = XW_M * XW_K * 2;  // 16 KB: one k-block of x, or o
 constexpr int XW_EPI_WARPS = 8;
 constexpr int XW_THREADS = 64 + 32 * XW_EPI_WARPS;   // 320
 constexpr int XW_SCRATCH_FLOATS = 2048;
-constexpr int XW_NUM_BARS = 2 + 2 * XW_STAGES + 4;
+constexpr int XW_MAX_ACC = 4;                     // accumulator stages: 2 x 256 columns (CTA pair) or 4 x 128 (single CTA)
+constexpr int XW_NUM_BARS = 2 + 2 * XW_STAGES + 2 * XW_MAX_ACC;
 constexpr size_t XW_SMEM_BYTES = 1024 + (size_t)(XW_MAX_KB + XW_STAGES) * XW_TILE_BYTES + XW_SCRATCH_FLOATS * 4 + 256;
-constexpr uint32_t XW_ACC_STRIDE = 256;         // TMEM columns between the two accumulator stages
+constexpr uint32_t XW_ACC_STRIDE = 256;         // TMEM columns between accumulator stages of a CTA pair (single CTA: 128)
 
 // tcgen05.ld without the wait (software pipelining), and a wait that carries the registers as operands so
 // the compiler cannot schedule their uses above it.
@@ -144,8 +145,12 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
   uint64_t* x_empty = bars + 1;                              // MMA -> TMA (both CTAs)
   uint64_t* full_bar = bars + 2;                             // [STAGES] TMA -> MMA (leader)
   uint64_t* empty_bar = bars + 2 + XW_STAGES;                // [STAGES] MMA -> TMA (both CTAs)
-  uint64_t* acc_full = bars + 2 + 2 * XW_STAGES;             // [2] MMA -> epilogue (both CTAs)
-  uint64_t* acc_empty = acc_full + 2;                        // [2] epilogue (both CTAs) -> MMA (leader)
+  // A single CTA's tile is 128 columns wide: its 512 TMEM columns hold FOUR accumulator stages, so the MMA issuer can run
+  // two tiles ahead of the slowest epilogue warp (with two stages every hand-off latency sits on the critical path).
+  constexpr int ACC = (PAIR == 1) ? 4 : 2;
+  constexpr uint32_t ACC_STRIDE = 512 / ACC;
+  uint64_t* acc_full = bars + 2 + 2 * XW_STAGES;             // [ACC] MMA -> epilogue (both CTAs)
+  uint64_t* acc_empty = acc_full + XW_MAX_ACC;               // [ACC] epilogue (both CTAs) -> MMA (leader)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + XW_NUM_BARS);
   uint8_t* aux = ring + (size_t)STAGES * XW_TILE_BYTES;       // (XW_STAGES - STAGES) x 16 KB of warp-private staging
   uint64_t* aux_bar = reinterpret_cast<uint64_t*>(scratch + XW_SCRATCH_FLOATS) - 2 * XW_EPI_WARPS;   // 2 per epilogue
@@ -166,7 +171,7 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
     mbar_init(x_full, PAIR);
     mbar_init(x_empty, 1);
     for (int s = 0; s < XW_STAGES; ++s) { mbar_init(&full_bar[s], PAIR); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], PAIR * XW_EPI_WARPS); }
+    for (int s = 0; s < ACC; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], PAIR * XW_EPI_WARPS); }
     if (STAGES < XW_STAGES) for (int s = 0; s < 2 * XW_EPI_WARPS; ++s) mbar_init(&aux_bar[s], 1);
     fence_barrier_init();
   }
@@ -274,7 +279,7 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
           ok = mbar_wait(&acc_empty[acc], acc_phase ^ 1);
           if (!ok) break;
           tc_fence_after_sync();
-          const uint32_t d_tmem = tmem_base + (uint32_t)acc * XW_ACC_STRIDE;
+          const uint32_t d_tmem = tmem_base + (uint32_t)acc * ACC_STRIDE;
           for (int kb = 0; kb < p.kb_count; ++kb) {
             ok = mbar_wait(&full_bar[stage], phase);
             if (!ok) break;
@@ -298,7 +303,7 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
           if (!ok) break;
           if (leader) xw_commit<PAIR>(&acc_full[acc]);
           __syncwarp();
-          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          if (++acc == ACC) { acc = 0; acc_phase ^= 1; }
         }
         if (ok && leader) xw_commit<PAIR>(x_empty);
         __syncwarp();
@@ -330,7 +335,7 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
           if (!ok) break;
           tc_fence_after_sync();
           it.row = (int64_t)t * TN + rank * XW_WROWS + it.quad * 32 + lane;   // the class this thread owns in tile t
-          const uint32_t taddr = tmem_base + (uint32_t)acc * XW_ACC_STRIDE + ((uint32_t)(it.quad * 32) << 16) + (uint32_t)col_base;
+          const uint32_t taddr = tmem_base + (uint32_t)acc * ACC_STRIDE + ((uint32_t)(it.quad * 32) << 16) + (uint32_t)col_base;
           Epi::tile_begin(stt, ep, p, it);
           float va[32], vb[32];
           tmem_ld32_async(taddr, va);
@@ -349,7 +354,7 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
             if (PAIR == 2) mbar_arrive_cluster(&acc_empty[acc], 0);
             else mbar_arrive(&acc_empty[acc]);
           }
-          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          if (++acc == ACC) { acc = 0; acc_phase ^= 1; }
           Epi::tile_end(stt, ep, p, it);
         }
         if (!ok) break;
@@ -369,7 +374,7 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
         if (!ok) break;
         tc_fence_after_sync();
         const int col_base = it.half * (TN / 2);
-        const uint32_t taddr = tmem_base + (uint32_t)acc * XW_ACC_STRIDE + ((uint32_t)(it.quad * 32) << 16) + (uint32_t)col_base;
+        const uint32_t taddr = tmem_base + (uint32_t)acc * ACC_STRIDE + ((uint32_t)(it.quad * 32) << 16) + (uint32_t)col_base;
         const int cls_base = t * TN + col_base;
         Epi::tile_begin(stt, ep, p, it, cls_base, (ti + 1 < t_end) ? cls_base + (p.reverse ? -TN : TN) : -1, TN / 2);
         float va[32], vb[32];
@@ -390,7 +395,7 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
           if (PAIR == 2) mbar_arrive_cluster(&acc_empty[acc], 0);
           else mbar_arrive(&acc_empty[acc]);
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == ACC) { acc = 0; acc_phase ^= 1; }
       }
       if (!ok) break;
       Epi::item_end(stt, ep, p, it, scratch);
