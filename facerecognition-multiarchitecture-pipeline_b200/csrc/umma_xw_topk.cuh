@@ -192,12 +192,19 @@ gallery_tau_kernel(const float* __restrict__ cand_key, const int32_t* __restrict
   const int32_t* li = cand_idx + qi * n_lists * KT;
   int pos[L];
   float head[L];                                             // current head of each of my lists (+inf: exhausted)
+  // both loads of every head are issued before any is used: guarded by the index (`id >= 0 ? key : inf`) the key load
+  // depended on the index load and the eight heads of a lane cost sixteen serial global-memory latencies (11 of 14 us)
+  int hid[L];
 #pragma unroll
   for (int u = 0; u < L; ++u) {
     pos[u] = 0;
     const int l = lane + 32 * u;
-    head[u] = (l < n_lists && li[l * KT] >= 0) ? lk[l * KT] : INFINITY;
+    const bool in = l < n_lists;
+    hid[u] = in ? __ldg(li + (in ? l : 0) * KT) : -1;
+    head[u] = in ? __ldg(lk + (in ? l : 0) * KT) : INFINITY;
   }
+#pragma unroll
+  for (int u = 0; u < L; ++u) head[u] = (hid[u] >= 0) ? head[u] : INFINITY;
   float last = INFINITY;
   bool short_of = false;
   // With many lists (>= 4 KT: the one-row-group pre-pass has 256) the KT-th smallest list HEAD is used: KT distinct
@@ -250,7 +257,23 @@ gallery_select_kernel(const float* __restrict__ cand_key, const int32_t* __restr
   const int64_t qi = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const bool cosine = (metric == B200F_METRIC_COS);
-  for (int i = tid; i < n_cand; i += 128) { ckey[i] = cand_key[qi * n_cand + i]; cidx[i] = cand_idx[qi * n_cand + i]; }
+  // The list heads are also kept as a dense array: read from ckey[h * KT] they sit KT words apart, a 16-way bank
+  // conflict on every read of the KT selection rounds below.
+  constexpr int MAX_HEADS = 512;
+  __shared__ float head_k[MAX_HEADS]; __shared__ int head_i[MAX_HEADS];
+  const bool dense_heads = (n_cand / KT) <= MAX_HEADS && (n_cand & 3) == 0;
+  if ((n_cand & 3) == 0) {                                   // n_cand = n_lists * KT: 16-byte copies
+    const float4* gk = reinterpret_cast<const float4*>(cand_key + qi * n_cand);
+    const int4* gi = reinterpret_cast<const int4*>(cand_idx + qi * n_cand);
+    for (int i = tid; i < n_cand / 4; i += 128) {
+      const float4 kv = __ldg(gk + i); const int4 iv = __ldg(gi + i);
+      reinterpret_cast<float4*>(ckey)[i] = kv;
+      reinterpret_cast<int4*>(cidx)[i] = iv;
+      if (dense_heads && (i % (KT / 4)) == 0) { head_k[i / (KT / 4)] = kv.x; head_i[i / (KT / 4)] = iv.x; }
+    }
+  } else {
+    for (int i = tid; i < n_cand; i += 128) { ckey[i] = cand_key[qi * n_cand + i]; cidx[i] = cand_idx[qi * n_cand + i]; }
+  }
   // no proof is possible for a query or a gallery whose 16-bit operand lost values (overflow, infinities)
   const bool any_marked = (q_bad != nullptr && q_bad[qi] != 0) ||
                           (gmax_ptr != nullptr && reinterpret_cast<const int*>(gmax_ptr)[1] != 0);
@@ -274,7 +297,7 @@ gallery_select_kernel(const float* __restrict__ cand_key, const int32_t* __restr
     for (int r = 0; r < KT; ++r) {
       float bk = INFINITY; int bi = INT32_MAX;
       for (int h = lane; h < n_heads; h += 32) {
-        const int id = cidx[h * KT]; const float kk = ckey[h * KT];
+        const int id = dense_heads ? head_i[h] : cidx[h * KT]; const float kk = dense_heads ? head_k[h] : ckey[h * KT];
         const bool after = (kk > taken_k) || (kk == taken_k && id > taken_i);
         if (id >= 0 && after && (kk < bk || (kk == bk && id < bi))) { bk = kk; bi = id; }
       }
