@@ -12,13 +12,13 @@ from .head import (  # noqa: E402,F401
     ArcMarginProduct, ArcFaceNet, arcface_loss, head_schedule, HeadStats, GraphedHeadStep,
 )
 from .gallery import (  # noqa: E402,F401
-    compare_faces, gallery_topk, cosine_class_match, GalleryIndex, PreparedGallery,
+    compare_faces, gallery_topk, gallery_topk_batches, cosine_class_match, GalleryIndex, PreparedGallery,
 )
 from .optim import HeadAdamW  # noqa: E402,F401
 from . import parallel  # noqa: E402,F401
 
 __all__ = [
     "ArcMarginProduct", "ArcFaceNet", "arcface_loss", "head_schedule", "HeadStats", "GraphedHeadStep",
-    "compare_faces", "gallery_topk", "cosine_class_match", "GalleryIndex", "PreparedGallery",
+    "compare_faces", "gallery_topk", "gallery_topk_batches", "cosine_class_match", "GalleryIndex", "PreparedGallery",
     "HeadAdamW", "parallel", "lib_path", "load_library", "LibraryMissingError",
 ]

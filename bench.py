@@ -587,6 +587,27 @@ def bench_gallery(dev, pk, eng):
                      "frac_of_hbm_peak": round(byt / (ms * 1e-3) / 1e9 / pk["hbm"], 4),
                      "fp32_equivalent_GBps": round((c["N"] * c["D"] * 4) / (ms * 1e-3) / 1e9, 1),
                      "algorithmic_tflops": round(2.0 * c["Q"] * c["N"] * c["D"] / (ms * 1e-3) / 1e12, 2)}
+        if name != "cfg2" and tc:
+            # several batches in flight (b200face.gallery_topk_batches, private streams): the latency-bound head and
+            # tail of one call overlap the HBM-bound main scan of another.  Every batch streams the 1 GB operand
+            # again (8x the L2), so no flush between them.
+            depth, nb = b200face.gallery.PIPELINE_DEPTH, 24
+            perms = [Q[torch.randperm(c["Q"], generator=g, device=dev)] for _ in range(6)]
+            batches = [perms[i % 6] for i in range(nb)]
+            pcall = lambda: b200face.gallery_topk_batches(batches, G, c["k"], 1.0, "l2eps", depth=depth, engine=eng, prepared=prep,
+                                                          redo_count=redo)
+            pcall()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); outs = pcall(); e1.record()
+            torch.cuda.synchronize()
+            ms_b = e0.elapsed_time(e1) / nb
+            res[name]["pipelined"] = {"depth": depth, "batches": nb, "ms_per_batch": round(ms_b, 4),
+                                      "queries_per_sec": round(c["Q"] / (ms_b * 1e-3), 1),
+                                      "algorithmic_GBps": round(byt / (ms_b * 1e-3) / 1e9, 1),
+                                      "frac_of_hbm_peak": round(byt / (ms_b * 1e-3) / 1e9 / pk["hbm"], 4),
+                                      "note": "same kernels and results as the serial calls; up to `depth` batches in flight"}
+            del outs, batches, perms
         del G, Q, prep
     return res
 

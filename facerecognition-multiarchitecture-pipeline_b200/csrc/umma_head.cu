@@ -564,16 +564,22 @@ bool gallery_tc_supported(int D) { return device_is_sm100() && D % 8 == 0 && D <
 
 size_t gallery_scan_workspace(int64_t Q, int64_t N, int D, int k) { return gallery_scan_plan(Q, N, D, k).total; }
 
+// rows of 8-element chunks at 16-byte aligned addresses: the vector form of the prepare kernel applies
+static bool prepare_vec_ok(const void* in, const void* out, int D) {
+  return D % 8 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+}
+
 int gallery_prepare(const void* g, int dtype, int64_t N, int D, int metric, int fmt, void* g16, float* bias, cudaStream_t st) {
   if (D > 512) return fail(B200F_ERR_UNSUPPORTED, "gallery_prepare: D <= 512");
   if (bias) B200F_CUDA_OK(cudaMemsetAsync(bias + N, 0, 2 * sizeof(float), st));
   const unsigned grid = (unsigned)ceil_div(N, 8);
+  const bool vec = prepare_vec_ok(g, g16, D);
   if (dtype == B200F_F32)
-    launch_pdl(gallery_prepare_kernel<float>, dim3(grid), dim3(256), 0, st, static_cast<const float*>(g), N, D, metric, fmt,
-                                                       static_cast<uint16_t*>(g16), bias, nullptr);
+    launch_pdl(vec ? gallery_prepare_vec8_kernel<float> : gallery_prepare_kernel<float>, dim3(grid), dim3(256), 0, st,
+               static_cast<const float*>(g), N, D, metric, fmt, static_cast<uint16_t*>(g16), bias, (uint8_t*)nullptr);
   else
-    launch_pdl(gallery_prepare_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(g), N, D, metric, fmt,
-                                                               static_cast<uint16_t*>(g16), bias, nullptr);
+    launch_pdl(vec ? gallery_prepare_vec8_kernel<__nv_bfloat16> : gallery_prepare_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, st,
+               static_cast<const __nv_bfloat16*>(g), N, D, metric, fmt, static_cast<uint16_t*>(g16), bias, (uint8_t*)nullptr);
   B200F_LAUNCH_OK("gallery_prepare_kernel");
   return B200F_OK;
 }
@@ -633,7 +639,8 @@ int gallery_scan_select(const float* q, const float* g, const void* g16, const f
   int32_t* sidx = reinterpret_cast<int32_t*>(ws + gp.off_sidx);
   float* tau0 = reinterpret_cast<float*>(ws + gp.off_tau);
   uint8_t* qbad = reinterpret_cast<uint8_t*>(ws + gp.off_qbad);
-  launch_pdl(gallery_prepare_kernel<float>, dim3((unsigned)ceil_div(Q, 8)), dim3(256), 0, st, q, Q, D, B200F_METRIC_L2EPS, fmt, q16, nullptr, qbad);
+  launch_pdl(prepare_vec_ok(q, q16, D) ? gallery_prepare_vec8_kernel<float> : gallery_prepare_kernel<float>, dim3((unsigned)ceil_div(Q, 8)),
+             dim3(256), 0, st, q, Q, D, B200F_METRIC_L2EPS, fmt, q16, (float*)nullptr, qbad);
   B200F_LAUNCH_OK("gallery_prepare_kernel (queries)");
   CUtensorMap tx, tw;
   int rc = tmap_kmajor(&tx, q16, Q, D, D, XW_M); if (rc) return rc;

@@ -130,6 +130,15 @@ struct XwTopK {
 // sends the affected queries to the exact engine).
 // bias[r] = |g|^2 - 2 eps sum(g) (L2EPS) / 0 (COS); two extra slots: bias[rows] = max row norm (atomicMax),
 // bias[rows + 1] = number of rows the 16-bit operand cannot represent (int).  row_bad (optional): the per-row flag.
+// Largest row norm through an atomicMax on the int view (norms are >= 0), attempted only when the value beats what the
+// slot already holds: one unconditional atomic per row on ONE address serialised in the L2 and made the kernel take
+// 1.65 ms on a 1 M x 512 gallery, against 0.5 ms of HBM time (profiles/r01_rowops_full.md).  A stale read only costs
+// an extra atomic.
+__device__ __forceinline__ void raise_max_norm(float* slot, float eff) {
+  if (eff == eff && __float_as_int(eff) > __ldcg(reinterpret_cast<const int*>(slot)))
+    atomicMax(reinterpret_cast<int*>(slot), __float_as_int(eff));
+}
+
 template <typename TI>
 __global__ void __launch_bounds__(256)
 gallery_prepare_kernel(const TI* __restrict__ in, int64_t rows, int dim, int metric, int fmt, uint16_t* __restrict__ out,
@@ -170,7 +179,73 @@ gallery_prepare_kernel(const TI* __restrict__ in, int64_t rows, int dim, int met
   if (bias != nullptr && lane == 0) {
     bias[row] = (metric == B200F_METRIC_COS) ? 0.f : (ss - 2.0f * GALLERY_EPS * sm);
     const float eff = (metric == B200F_METRIC_COS) ? 1.0f : nrm;
-    if (eff == eff) atomicMax(reinterpret_cast<int*>(bias + rows), __float_as_int(eff));   // norms are >= 0
+    raise_max_norm(bias + rows, eff);
+    if (lost) atomicAdd(reinterpret_cast<int*>(bias + rows + 1), 1);                       // unrankable rows
+  }
+}
+
+// The same for dim % 8 == 0 with 16-byte aligned rows (what the tensor engine takes anyway): a lane owns chunks of 8
+// consecutive elements (chunks lane and lane + 32), loaded as 32-byte (fp32) / 16-byte (bf16) vectors and stored as
+// one 16-byte vector of 16-bit values each.  The scalar kernel above issues 2-byte stores and ran at 1.9 TB/s on a
+// 1 M x 512 gallery (profiles/r01_rowops_full.md).
+template <typename TI>
+__global__ void __launch_bounds__(256)
+gallery_prepare_vec8_kernel(const TI* __restrict__ in, int64_t rows, int dim, int metric, int fmt, uint16_t* __restrict__ out,
+                            float* __restrict__ bias, uint8_t* __restrict__ row_bad) {
+  pdl_trigger(); pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int chunks = dim >> 3;                                // <= 64
+  float v[2][8];
+  float ss = 0.f, sm = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int c = lane + 32 * i;
+    if (c < chunks) {
+      load8<TI>(in + row * dim + 8 * c, 8, true, v[i]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[i][e] = 0.f;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { ss = fmaf(v[i][e], v[i][e], ss); sm += v[i][e]; }
+  }
+  ss = warp_sum(ss); sm = warp_sum(sm);
+  const float nrm = sqrtf(ss);
+  const float sc = (metric == B200F_METRIC_COS) ? 1.0f / fmaxf(nrm, 1e-12f) : 1.0f;
+  bool lost = false;
+  if (out != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int c = lane + 32 * i;
+      if (c < chunks) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+          uint16_t h2[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const float f = v[i][e + u] * sc;
+            h2[u] = (fmt == B200F_OPERAND_FP16) ? __half_as_ushort(__float2half_rn(f)) : __bfloat16_as_ushort(__float2bfloat16_rn(f));
+            const float back = (fmt == B200F_OPERAND_FP16) ? __half2float(__ushort_as_half(h2[u])) : __bfloat162float(__ushort_as_bfloat16(h2[u]));
+            lost = lost || ((back - back != 0.f) && (f == f));  // non-finite result from a non-NaN input
+          }
+          pk[e >> 1] = (uint32_t)h2[0] | ((uint32_t)h2[1] << 16);
+        }
+        *reinterpret_cast<uint4*>(out + row * dim + 8 * c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+    }
+  }
+  lost = __any_sync(0xffffffffu, lost);
+  if (lane == 0 && row_bad != nullptr) row_bad[row] = lost ? 1 : 0;
+  if (bias != nullptr && lane == 0) {
+    bias[row] = (metric == B200F_METRIC_COS) ? 0.f : (ss - 2.0f * GALLERY_EPS * sm);
+    const float eff = (metric == B200F_METRIC_COS) ? 1.0f : nrm;
+    raise_max_norm(bias + rows, eff);
     if (lost) atomicAdd(reinterpret_cast<int*>(bias + rows + 1), 1);                       // unrankable rows
   }
 }

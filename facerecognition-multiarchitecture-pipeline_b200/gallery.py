@@ -133,6 +133,54 @@ def gallery_topk(q: torch.Tensor, g: torch.Tensor, k: int = 1, thresh: float = 1
     return idx, score, accept.bool()
 
 
+_pipe_streams = {}
+PIPELINE_DEPTH = 3      # measured at Q = 128 vs 1 M x 512: 270 us per call serial, 239 at depth 2, 233 at depth 3
+
+
+def gallery_topk_batches(batches: Sequence[torch.Tensor], g: torch.Tensor, k: int = 1, thresh: float = 1.0,
+                         metric: str = "l2eps", *, depth: int = PIPELINE_DEPTH, index_offset: int = 0,
+                         engine: int = _lib.ENGINE_AUTO, prepared: Optional[PreparedGallery] = None,
+                         redo_count: Optional[torch.Tensor] = None) -> List[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]]:
+    """gallery_topk for several query batches against ONE gallery with up to `depth` calls in flight on private CUDA
+    streams.  One call is a chain of dependent kernels (query prepare -> sample scan -> bound -> main scan -> select);
+    with several batches in flight the latency-bound head and tail of one call run beside the HBM-bound main scan of
+    another.  The results are those of the serial calls, element for element (each call owns its scratch: the
+    workspace cache is keyed by stream).  Returns [(idx, score, accept)] in the order of `batches`, ready for use on
+    the caller's current stream."""
+    batches = list(batches)
+    if not batches:
+        return []
+    require_cuda(g, *batches)
+    dev = g.device
+    g = g.contiguous()
+    if depth <= 1 or len(batches) == 1:
+        return [gallery_topk(q, g, k, thresh, metric, index_offset=index_offset, engine=engine, prepared=prepared,
+                             redo_count=redo_count) for q in batches]
+    # what every call shares is built once, on the caller's stream, before the side streams fork from it
+    if prepared is None and any(tensor_engine_ok(q, g, engine) for q in batches if q.dtype == g.dtype):
+        prepared = PreparedGallery(g, metric)
+    g_inv = _inv_norm(g) if metric == "cos" else None
+    cur = torch.cuda.current_stream(dev)
+    depth = min(depth, len(batches))
+    key = (str(dev), depth)
+    streams = _pipe_streams.get(key)
+    if streams is None:
+        streams = _pipe_streams[key] = [torch.cuda.Stream(dev) for _ in range(depth)]
+    for s in streams:
+        s.wait_stream(cur)
+    outs = []
+    for i, q in enumerate(batches):
+        with torch.cuda.stream(streams[i % depth]):
+            res = gallery_topk(q, g, k, thresh, metric, index_offset=index_offset, g_inv=g_inv, engine=engine,
+                               prepared=prepared, redo_count=redo_count)
+        for t in res:
+            t.record_stream(cur)                  # allocated on a side stream, consumed on the caller's
+        outs.append(res)
+    for s in streams:
+        cur.wait_stream(s)
+    return outs
+
+
 def merge_topk(idx_all: torch.Tensor, score_all: torch.Tensor, thresh: float, metric: str):
     """Merge P per-shard lists [P,Q,k] (global ids) into the global top-k (lowest id wins ties)."""
     require_cuda(idx_all, score_all)
@@ -259,6 +307,14 @@ class GalleryIndex:
         g = self.embeddings
         pg = self.prepared(metric) if tensor_engine_ok(q, g, engine) else None
         return gallery_topk(q, g, k, thresh, metric, engine=engine, prepared=pg)
+
+    def match_batches(self, embs: Sequence[torch.Tensor], thresh: float = 1.0, k: int = 1, metric: str = "l2eps",
+                      engine: int = _lib.ENGINE_AUTO, depth: int = PIPELINE_DEPTH):
+        """match() for several query batches with up to `depth` of them in flight (gallery_topk_batches)."""
+        qs = [e.reshape(-1, self.dim).to(device=self.device, dtype=self.dtype) for e in embs]
+        g = self.embeddings
+        pg = self.prepared(metric) if any(tensor_engine_ok(q, g, engine) for q in qs) else None
+        return gallery_topk_batches(qs, g, k, thresh, metric, depth=depth, engine=engine, prepared=pg)
 
     def compare_faces(self, emb: Optional[torch.Tensor], thresh: float):
         """compare_faces(emb, refs, thresh) against the resident gallery."""

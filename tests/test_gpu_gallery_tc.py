@@ -143,3 +143,73 @@ def test_unscaled_gallery_uses_bf16_and_stays_exact(cuda_device):
     _check_same(b200face.gallery_topk(Qm, G, 5, 1.0e9, "l2eps", engine=_lib.ENGINE_TCGEN05, prepared=auto), ex, rtol=1e-5)
     forced = b200face.PreparedGallery(G, "l2eps", _lib.OPERAND_FP16)
     _check_same(b200face.gallery_topk(Qm, G, 5, 1.0e9, "l2eps", engine=_lib.ENGINE_TCGEN05, prepared=forced), ex, rtol=1e-5)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("fmt", ["fp16", "bf16"])
+@pytest.mark.parametrize("D", [512, 64, 100])                 # 100: not a multiple of 8 -> the scalar prepare kernel
+def test_prepared_operand_matches_torch(cuda_device, D, fmt, dtype):
+    """b200f_gallery_prepare (vector and scalar kernels): the 16-bit rows are the round-to-nearest cast of the fp32
+    values (L2EPS) / of the normalised rows (COS); bias = |g|^2 - 2e-6 sum(g); the two trailing slots hold the largest
+    row norm and the count of rows the 16-bit format lost."""
+    import b200face
+    from b200face import _lib
+    gen = torch.Generator().manual_seed(D)
+    N = 1003
+    g = (torch.randn(N, D, generator=gen) * 0.3).to(dtype).to(cuda_device)
+    t16 = torch.float16 if fmt == "fp16" else torch.bfloat16
+    code = _lib.OPERAND_FP16 if fmt == "fp16" else _lib.OPERAND_BF16
+    gf = g.float()
+    pg = b200face.PreparedGallery(g, "l2eps", code)
+    torch.cuda.synchronize()
+    assert torch.equal(pg.g16, gf.to(t16))
+    ref_bias = (gf.double() ** 2).sum(1) - 2e-6 * gf.double().sum(1)
+    np.testing.assert_allclose(pg.bias[:N].cpu().numpy(), ref_bias.cpu().numpy(), rtol=3e-6, atol=1e-7)
+    np.testing.assert_allclose(float(pg.bias[N]), float(gf.double().norm(dim=1).max()), rtol=3e-6)
+    assert int(pg.bias[N + 1:].view(torch.int32)[0]) == 0
+    pc = b200face.PreparedGallery(g, "cos", code)
+    torch.cuda.synchronize()
+    ghat = (gf / gf.norm(dim=1, keepdim=True).clamp_min(1e-12))
+    ulp = 2.0 ** -10 if fmt == "fp16" else 2.0 ** -7          # one unit in the last place of values below 1
+    assert float((pc.g16.float() - ghat).abs().max()) <= ulp
+    assert float(pc.bias[:N].abs().max()) == 0.0
+
+
+def test_prepared_operand_flags_fp16_overflow(cuda_device):
+    import b200face
+    from b200face import _lib
+    g = torch.randn(64, 512, device=cuda_device)
+    g[5, 7] = 1.0e5                                           # finite in fp32, infinite in fp16
+    g[9, 500] = -7.0e4
+    pg = b200face.PreparedGallery(g, "l2eps", _lib.OPERAND_FP16)
+    torch.cuda.synchronize()
+    assert int(pg.bias[64 + 1:].view(torch.int32)[0]) == 2
+
+
+@pytest.mark.parametrize("metric", ["l2eps", "cos"])
+@pytest.mark.parametrize("depth", [2, 3])
+def test_batches_in_flight_equal_serial_calls(cuda_device, metric, depth):
+    """gallery_topk_batches / GalleryIndex.match_batches: several query batches in flight on private streams give,
+    element for element, what the serial calls give (tensor engine and exact engine)."""
+    import b200face
+    from b200face import _lib
+    q, g = _case(5 * 96, 30000, 512, 11, cuda_device)
+    thr = 1.0 if metric == "l2eps" else 0.5
+    batches = [q[i * 96:(i + 1) * 96] for i in range(5)] + [q[:7]]
+    for engine in (_lib.ENGINE_TCGEN05, _lib.ENGINE_SIMT):
+        serial = [b200face.gallery_topk(b, g, 5, thr, metric, engine=engine) for b in batches]
+        for _ in range(3):                                    # repeated: scratch of a stream is reused across rounds
+            piped = b200face.gallery_topk_batches(batches, g, 5, thr, metric, depth=depth, engine=engine)
+        torch.cuda.synchronize()
+        assert len(piped) == len(batches)
+        for a, b in zip(piped, serial):
+            assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    assert b200face.gallery_topk_batches([], g, 5, thr, metric) == []
+    index = b200face.GalleryIndex(512, cuda_device, capacity=g.shape[0])
+    index._buf[:] = g
+    index.names = [f"id{i}" for i in range(g.shape[0])]
+    got = index.match_batches(batches, thr, 5, metric, depth=depth)
+    want = [index.match(b, thr, 5, metric) for b in batches]
+    torch.cuda.synchronize()
+    for a, b in zip(got, want):
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])

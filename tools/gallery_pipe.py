@@ -29,7 +29,7 @@ ref = [b200face.gallery_topk(b, G, k, 1.0, "l2eps", engine=_lib.ENGINE_TCGEN05, 
 torch.cuda.synchronize()
 byt = N * D * 2 + N * 4 + Q * D * 4 + Q * k * 12
 res = {}
-for depth in (1, 2, 3):
+for depth in (1, 2, 3, 4):
     streams = [torch.cuda.Stream(dev) for _ in range(depth)]
     outs = [None] * len(batches)
 
