@@ -124,13 +124,13 @@ def gallery_topk(q: torch.Tensor, g: torch.Tensor, k: int = 1, thresh: float = 1
                                         ptr(idx), ptr(score),
                                         ptr(accept), ptr(redo_count), ptr(ws), ws.numel(), stream_ptr(dev)),
               "b200f_gallery_topk_tc")
-        return idx, score, accept.bool()
+        return idx, score, accept.view(torch.bool)
     nbytes = lib.b200f_gallery_workspace_bytes(Q, N, D, k, dtype_code(q), engine)
     ws = _lib.workspace(nbytes, dev, "gallery")
     check(lib.b200f_gallery_topk(ptr(q), ptr(g), dtype_code(q), ptr(q_inv), ptr(gi), Q, N, int(index_offset), D,
                                  k, _METRICS[metric], float(thresh), engine, ptr(idx), ptr(score), ptr(accept),
                                  ptr(ws), ws.numel(), stream_ptr(dev)), "b200f_gallery_topk")
-    return idx, score, accept.bool()
+    return idx, score, accept.view(torch.bool)
 
 
 _pipe_streams = {}
@@ -193,7 +193,7 @@ def merge_topk(idx_all: torch.Tensor, score_all: torch.Tensor, thresh: float, me
     check(lib.b200f_gallery_merge(ptr(idx_all.contiguous()), ptr(score_all.contiguous()), P, Q, k,
                                   _METRICS[metric], float(thresh), ptr(idx), ptr(score), ptr(accept),
                                   stream_ptr(dev)), "b200f_gallery_merge")
-    return idx, score, accept.bool()
+    return idx, score, accept.view(torch.bool)
 
 
 def compare_faces(emb, refs, thresh):
