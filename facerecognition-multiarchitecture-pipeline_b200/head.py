@@ -60,6 +60,9 @@ class HeadStats:
     row_argmax: Optional[torch.Tensor] = None    # [B] its global class index
     cos_minmax: Optional[torch.Tensor] = None    # [2] {min, max} raw cosine (face_models.py:358-360)
     nan_flag: Optional[torch.Tensor] = None      # [1] int32, 1 if a logit was scrubbed (:423-427)
+    # A caller-owned flag the forward sets instead of a freshly zeroed one: a captured step then holds no fill kernel
+    # for it.  It stays set across replays until ArcMarginProduct.nan_seen reads (and clears) it.
+    sticky_nan_flag: Optional[torch.Tensor] = None
     hook_out: Optional[torch.Tensor] = None      # [3] grad_scale, ||dL/dt||_F, kappa (after backward)
     lse: Optional[torch.Tensor] = None           # [B]
     dx_f32: Optional[torch.Tensor] = None        # [B,D] fp32 dL/dx before the cast to x.dtype (after backward)
@@ -134,7 +137,7 @@ def _prepare_weight(w: torch.Tensor, f16n: bool, cache: Optional[dict]):
     return val
 
 
-def _fwd_kernels(x, w, label, cfg: HeadCfg, class_offset, want_logits, w_cache=None):
+def _fwd_kernels(x, w, label, cfg: HeadCfg, class_offset, want_logits, w_cache=None, nan_flag=None):
     lib = _lib.load_library()
     B, D = x.shape
     C = w.shape[0]
@@ -148,7 +151,8 @@ def _fwd_kernels(x, w, label, cfg: HeadCfg, class_offset, want_logits, w_cache=N
     row_best = torch.empty(B, dtype=torch.float32, device=dev)
     row_argmax = torch.empty(B, dtype=torch.int64, device=dev)
     cos_minmax = torch.empty(2, dtype=torch.float32, device=dev)
-    nan_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+    if nan_flag is None:
+        nan_flag = torch.zeros(1, dtype=torch.int32, device=dev)
     logits = torch.empty(B, C, dtype=torch.float32, device=dev) if want_logits else None
     nbytes = lib.b200f_head_workspace_bytes(B, C, D, dtype_code(xo), cfg.engine)
     ws = _lib.workspace(nbytes, dev, "head")
@@ -196,7 +200,7 @@ class _ArcFaceLossFn(torch.autograd.Function):
         # w: what K1 reads (== weight, or a bf16 compute copy of it)
         ctx.w_dtype, ctx.x_dtype = weight.dtype, x.dtype
         x, w, inv_nx, inv_nw, row_stats, row_best, row_argmax, cos_minmax, nan_flag, _ = _fwd_kernels(
-            x, w, label, cfg, class_offset, False, w_cache)
+            x, w, label, cfg, class_offset, False, w_cache, stats.sticky_nan_flag)
         if group is not None:
             from . import parallel
             parallel.reduce_row_stats(row_stats, group)          # one SUM all-reduce of [B,4]
@@ -316,6 +320,11 @@ class GraphedHeadStep:
         # stream the leaf was first used on; the parameter itself has usually been used on the (uncapturable)
         # default stream already.  Warm-up and capture both run on `side`, so no cross-stream edge is recorded.
         self.w_leaf = weight.detach().requires_grad_(True)
+        # static inputs of the capture that torch would otherwise create with a fill kernel inside the graph (each one
+        # a launch without the programmatic-serialization attribute between two of ours): the NaN flag K2 sets, and
+        # the root gradient of loss.backward()
+        self.stats.sticky_nan_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._root_grad = torch.ones((), dtype=torch.float32, device=dev)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):                 # warm-up off the capture: library load, workspaces, attributes
@@ -329,7 +338,7 @@ class GraphedHeadStep:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph, stream=side):
             self.loss = arcface_loss(self.x, self.w_leaf, self.y, stats=self.stats, **loss_kw)
-            self.loss.backward()
+            torch.autograd.backward(self.loss, grad_tensors=self._root_grad)
         self.dw = self.w_leaf.grad
         self.dx = self.x.grad
 
@@ -510,6 +519,8 @@ class ArcMarginProduct(nn.Module):
         seen = bool(t.item()) if t is not None else False
         if seen:
             print("Uh oh! NaN or Inf in ArcFace output!")      # face_models.py:427
+            if t is self.last_stats.sticky_nan_flag:
+                t.zero_()                                      # a captured step's flag: set until read
         return seen
 
     def get_margin_stats(self):

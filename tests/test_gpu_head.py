@@ -419,6 +419,29 @@ def test_graphed_step_matches_eager(cuda_device):
         assert torch.equal(head.weight.grad, dw_e)
 
 
+def test_graphed_step_nan_flag_is_set_until_read(cuda_device):
+    """The captured step holds no fill kernel for the NaN flag (face_models.py:423-427): a replay that scrubs a
+    non-finite logit sets it, it stays set across replays, and reading head.nan_seen reports and clears it."""
+    import b200face
+    B, C, D = 128, 3000, 512
+    x, w, y = _random_case(B, C, D, 31)
+    cfg = oracle.HeadConfig(current_epoch=12, training=True, label_smoothing=0.05)
+    head = _head_from_cfg(cfg, C, D, cuda_device, w.bfloat16().float())
+    step = head.graphed_step(B, 0.05, torch.bfloat16)
+    xb, yb = x.bfloat16().to(cuda_device), y.to(cuda_device)
+    clean = float(step(xb, yb))
+    assert not head.nan_seen
+    bad = xb.clone()
+    bad[5, 9] = float("inf")
+    step(bad, yb)
+    again = float(step(xb, yb))                               # a clean replay does not clear the flag
+    assert again == clean
+    assert head.nan_seen                                      # reported once ...
+    assert not head.nan_seen                                  # ... and cleared by the read
+    step(xb, yb)
+    assert not head.nan_seen
+
+
 def test_graphed_step_from_pinned_host_batches(cuda_device):
     """Host batches go through the copy stream and the two staging slots: six different batches issued back to back
     (no sync in between, one pinned buffer per batch) give the losses / gradients of the same batches fed from the
