@@ -207,23 +207,26 @@ class _ArcFaceLossFn(torch.autograd.Function):
         lib = _lib.load_library()
         B = x.shape[0]
         lse = torch.empty(B, dtype=torch.float32, device=x.device)
-        out2 = torch.empty(2, dtype=torch.float32, device=x.device)   # loss, pq_norm2
-        check(lib.b200f_arcface_loss(ptr(row_stats), B, cfg, ptr(lse), ptr(out2), ptr(out2[1:]),
+        # two separate outputs: the loss is returned as the kernel wrote it (a clone of one slot of a shared buffer was
+        # a copy node between loss_kernel and the hook scalar in every captured step)
+        loss = torch.empty((), dtype=torch.float32, device=x.device)
+        pq_norm2 = torch.empty(1, dtype=torch.float32, device=x.device)
+        check(lib.b200f_arcface_loss(ptr(row_stats), B, cfg, ptr(lse), ptr(loss), ptr(pq_norm2),
                                      stream_ptr(x.device)), "b200f_arcface_loss")
         stats.row_best, stats.row_argmax = row_best, row_argmax
         stats.cos_minmax, stats.nan_flag, stats.lse = cos_minmax, nan_flag, lse
-        ctx.save_for_backward(x, w, label, inv_nx, inv_nw, lse, out2)
+        ctx.save_for_backward(x, w, label, inv_nx, inv_nw, lse, pq_norm2)
         ctx.cfg, ctx.class_offset, ctx.group, ctx.hook, ctx.stats = cfg, class_offset, group, hook, stats
-        return out2[0].clone()
+        return loss
 
     @staticmethod
     def backward(ctx, grad_out):
-        x, w, label, inv_nx, inv_nw, lse, out2 = ctx.saved_tensors
+        x, w, label, inv_nx, inv_nw, lse, pq_norm2 = ctx.saved_tensors
         cfg, hook = ctx.cfg, ctx.hook
         lib = _lib.load_library()
         up = grad_out.to(torch.float32).contiguous()
         out3 = torch.empty(4, dtype=torch.float32, device=x.device)
-        check(lib.b200f_arcface_hook_scale(ptr(out2[1:]), ptr(up), x.shape[0], cfg.s_eff, int(hook.enabled),
+        check(lib.b200f_arcface_hook_scale(ptr(pq_norm2), ptr(up), x.shape[0], cfg.s_eff, int(hook.enabled),
                                            float(hook.max_grad_norm), int(hook.phase), int(hook.epoch),
                                            ptr(out3), stream_ptr(x.device)), "b200f_arcface_hook_scale")
         ctx.stats.hook_out = out3
