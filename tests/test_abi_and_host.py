@@ -161,3 +161,45 @@ def test_shard_bounds_cover_everything():
                 assert lo == prev and hi >= lo
                 prev = hi
             assert prev == total
+
+
+def test_gallery_batches_host_logic():
+    """gallery_topk_batches: nothing to do for no batches; CPU tensors are refused like everywhere else (no fallback);
+    the stream-keyed workspace cache is what lets several calls be in flight."""
+    import b200face
+    from b200face import gallery
+    g = torch.randn(10, 8)
+    assert b200face.gallery_topk_batches([], g) == []
+    with pytest.raises(RuntimeError, match="CUDA"):
+        b200face.gallery_topk_batches([torch.randn(2, 8), torch.randn(3, 8)], g, 1, 1.0, "l2eps")
+    assert gallery.PIPELINE_DEPTH >= 2
+    import inspect
+    assert "current_stream" in inspect.getsource(b200face._lib.workspace)      # scratch keyed by (device, stream, tag)
+
+
+def test_head_stats_sticky_flag_defaults_off():
+    from b200face.head import HeadStats
+    assert HeadStats().sticky_nan_flag is None and HeadStats().nan_flag is None
+
+
+def test_condense_launches_tool(tmp_path):
+    """tools/condense_launches.py: ncu CSV launch list -> id,kernel,grid,block,duration_ns (our kernels up to the argument
+    list, torch's cut to 60 characters, units normalised to ns)."""
+    import subprocess
+    import sys
+    raw = tmp_path / "raw.csv"
+    raw.write_text(
+        "==PROF== Connected to process 1\n"
+        '"ID","Process ID","Process Name","Host Name","Kernel Name","Context","Stream","Block Size","Grid Size","Device","CC",'
+        '"Section Name","Metric Name","Metric Unit","Metric Value"\n'
+        '"0","1","python","h","void at::native::vectorized_elementwise_kernel<4, at::native::FillFunctor<float>, std::array<char *, 1>>(int, T2, T3)",'
+        '"1","7","(128, 1, 1)","(65536, 1, 1)","0","10.0","Command line profiler metrics","gpu__time_duration.sum","us","36.83"\n'
+        '"1","1","python","h","umma::xw_kernel<2, 0, 0, 0, umma::XwFwd>(CUtensorMap_st, CUtensorMap_st, umma::XwParams)",'
+        '"1","7","(320, 1, 1)","(148, 1, 1)","0","10.0","Command line profiler metrics","gpu__time_duration.sum","ns","57,184"\n')
+    out = tmp_path / "out.csv"
+    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "condense_launches.py"), str(raw), str(out), "ncu ... cmd"],
+                   check=True)
+    lines = out.read_text().splitlines()
+    assert lines[0] == "# ncu ... cmd" and lines[2] == "id,kernel,grid,block,duration_ns"
+    assert lines[3].endswith(',"(65536, 1, 1)","(128, 1, 1)",36830') and len(lines[3].split('"')[1]) == 60
+    assert lines[4] == '1,"umma::xw_kernel<2, 0, 0, 0, umma::XwFwd>","(148, 1, 1)","(320, 1, 1)",57184'
