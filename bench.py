@@ -111,6 +111,16 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def claim_stdout():
+    """stdout must carry exactly ONE JSON line, and libraries print there too (with N > 1 NCCL writes
+    "NCCL version ..." on file descriptor 1 whatever NCCL_DEBUG_FILE says).  Returns a file object on the original
+    stdout and points descriptor 1 -- for this process, its C libraries and its children -- at stderr."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def synth_head(B, C_local, D, rank_seed, dev, c_lo, C_total):
     """SURVEY 8d recipe: x ~ N(0,1) -> bf16, W xavier_normal(gain sqrt2) -> bf16 compute copy,
     y ~ U{0..C-1}; 12.5 % of the rows planted near their class centre so the margin is exercised."""
@@ -142,7 +152,9 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     group = None
+    result_out = sys.stdout
     if world > 1:
+        result_out = claim_stdout()                           # NCCL prints its version banner on stdout
         torch.distributed.init_process_group("nccl", device_id=dev)
         group = torch.distributed.group.WORLD
     lib = b200face.load_library()
@@ -371,7 +383,7 @@ def run_b200(args):
         out["gallery"] = gal_sharded
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_head_baseline(CFG3)
-    print(json.dumps(out), flush=True)
+    print(json.dumps(out), file=result_out, flush=True)
     finish(world)
 
 

@@ -203,3 +203,20 @@ def test_condense_launches_tool(tmp_path):
     assert lines[0] == "# ncu ... cmd" and lines[2] == "id,kernel,grid,block,duration_ns"
     assert lines[3].endswith(',"(65536, 1, 1)","(128, 1, 1)",36830') and len(lines[3].split('"')[1]) == 60
     assert lines[4] == '1,"umma::xw_kernel<2, 0, 0, 0, umma::XwFwd>","(148, 1, 1)","(320, 1, 1)",57184'
+
+
+def test_bench_claims_stdout_for_the_json_line(tmp_path):
+    """bench.py with N > 1: whatever libraries (NCCL's version banner) or children write on descriptor 1 after
+    claim_stdout() lands on stderr; only what is printed to the returned file reaches stdout."""
+    import subprocess
+    import sys
+    code = ("import os, sys, json\n"
+            f"sys.path.insert(0, {ROOT!r})\n"
+            "import bench\n"
+            "out = bench.claim_stdout()\n"
+            "os.system('echo banner-from-a-library')\n"
+            "print('stray python print')\n"
+            "print(json.dumps({'ok': 1}), file=out, flush=True)\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, check=True)
+    assert r.stdout == '{"ok": 1}\n'
+    assert "banner-from-a-library" in r.stderr and "stray python print" in r.stderr
