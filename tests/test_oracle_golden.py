@@ -143,3 +143,35 @@ def test_topk_merge_equals_global():
         mi, ms = oracle.merge_topk_shards(parts_i, parts_s, 5, largest)
         assert np.array_equal(mi, gi)
         np.testing.assert_allclose(ms, gs, rtol=1e-6)   # BLAS blocking differs per shard shape
+
+
+@pytest.mark.parametrize("easy", [False, True])
+@pytest.mark.parametrize("epoch,ls", [(0, 0.05), (12, 0.0), (12, 0.15)])
+def test_closed_form_gradients_match_finite_differences(easy, epoch, ls):
+    """A pin of the oracle that does not go through autograd at all: the closed-form dL/dx and dL/dW of
+    head_forward_backward against central differences of its own loss in fp64 (size-independent property; the golden
+    vectors above pin the same quantities to the reference's autograd)."""
+    rng = np.random.default_rng(7 + epoch + int(easy))
+    B, C, D = 5, 7, 6
+    x = rng.standard_normal((B, D))
+    w = rng.standard_normal((C, D)) * 0.5
+    y = rng.integers(0, C, size=B)
+    x[0] = 2.0 * w[y[0]] + 0.1 * rng.standard_normal(D)       # a row near its class centre: the margin branch matters
+    cfg = oracle.HeadConfig(current_epoch=epoch, training=True, label_smoothing=ls, easy_margin=easy)
+    ref = oracle.head_forward_backward(x, w, y, cfg, dtype=np.float64)
+    loss = lambda xx, ww: float(oracle.head_forward_backward(xx, ww, y, cfg, dtype=np.float64)["loss"])
+    h = 1e-6
+    fd_x = np.zeros_like(x)
+    for i in range(B):
+        for j in range(D):
+            xp, xm = x.copy(), x.copy()
+            xp[i, j] += h; xm[i, j] -= h
+            fd_x[i, j] = (loss(xp, w) - loss(xm, w)) / (2 * h)
+    fd_w = np.zeros_like(w)
+    for i in range(C):
+        for j in range(D):
+            wp, wm = w.copy(), w.copy()
+            wp[i, j] += h; wm[i, j] -= h
+            fd_w[i, j] = (loss(x, wp) - loss(x, wm)) / (2 * h)
+    assert rel_err(ref["dx"], fd_x) < 1e-6
+    assert rel_err(ref["dw"], fd_w) < 1e-6
