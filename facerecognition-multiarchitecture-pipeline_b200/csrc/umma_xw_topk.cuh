@@ -124,8 +124,9 @@ struct XwTopK {
   }
 };
 
-// ---- prepare: rows -> bf16 scan operand (+ bias, + max row norm) ---------------------------------------
-// One warp per row (D <= 512, D % 8 == 0).  metric COS: out = g / max(|g|, 1e-12); L2EPS: out = g; stored as bf16
+// ---- prepare: rows -> 16-bit scan operand (+ bias, + max row norm) -------------------------------------
+// One warp per row (D <= 512).  This scalar form takes any D; rows of whole 8-element chunks at 16-byte aligned
+// addresses -- everything the tensor engine scans -- go through gallery_prepare_vec8_kernel below.  metric COS: out = g / max(|g|, 1e-12); L2EPS: out = g; stored as bf16
 // (any range) or fp16 (8x tighter error bound; |values| must stay well inside +-65504 -- an overflow is safe, it only
 // sends the affected queries to the exact engine).
 // bias[r] = |g|^2 - 2 eps sum(g) (L2EPS) / 0 (COS); two extra slots: bias[rows] = max row norm (atomicMax),
