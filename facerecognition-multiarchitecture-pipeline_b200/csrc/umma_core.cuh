@@ -9,7 +9,11 @@
 namespace b200f {
 namespace umma {
 
-// ---- error flag raised by bounded waits (a pipeline bug must never hang the GPU box) ----------
+// ---- bounded waits (a pipeline bug must never hang the GPU box, and must never go unnoticed) ----------------------
+// A wait that expires raises this flag (diagnostics: b200f_umma_timeout_flag) and then TRAPS: the kernel is aborted,
+// the stream's next CUDA call returns an error, and torch raises -- partial accumulators never reach a loss, a
+// gradient or a top-k list.  2^24 polls of mbarrier.try_wait (each blocks for the hardware's time limit first) are
+// seconds; the longest kernel of the library runs for milliseconds.
 __device__ unsigned int g_umma_timeout_flag;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -54,13 +58,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: returns false (and raises the global flag) instead of spinning forever.
+// Bounded wait: true when the phase completed; on expiry raises the flag and aborts the kernel (never returns false
+// to a caller that would go on with partial data; the bool is kept so call sites read as before).
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
 #pragma unroll 1
   for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
     if (mbar_try_wait(bar, parity)) return true;
   }
   atomicExch(&g_umma_timeout_flag, 1u);
+  __threadfence_system();
+  __trap();
   return false;
 }
 

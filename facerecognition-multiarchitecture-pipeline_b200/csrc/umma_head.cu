@@ -187,8 +187,11 @@ __global__ void reduce_r_kernel(const float* __restrict__ r_part, int n_rb, int6
 // ---- X-stationary kernel: launch geometry ---------------------------------------------------------
 static std::atomic<int> g_pair{2};                 // 2 = tcgen05 cta_group::2 CTA pairs, 1 = single CTAs
 static std::atomic<int> g_k3b_class_major{1};       // K3b epilogue: 1 = thread owns a class row (XwDwT), 0 = a feature (XwDw)
+static std::atomic<int> g_epi_groups{2};            // K2 / K3a: 2 = two epilogue groups of 8 warps (16-column slices), 1 = one group
+#ifdef B200F_PROBES                                 // tools/ builds only; the shipped library has neither the branch nor the switch
 static std::atomic<int> g_k3a_ablate{0};            // probe: 2 = no G^T stores (WRONG results)
 static std::atomic<int> g_k3b_ablate{0};            // probe: 1 = no w_hat loads, 2 = no dW stores (WRONG results)
+#endif
 static std::atomic<int> g_k3b_reverse{1};
 // "stage_events" tunable: record a CUDA event pair around each GEMM kernel of the head on the launching stream
 // (bench.py's per-kernel durations; eager launches only -- never inside a graph capture).
@@ -297,7 +300,7 @@ static int launch_xw(const CUtensorMap& tx, const CUtensorMap& tw, const XwPlan&
   p.reverse = reverse ? 1 : 0;
   p.idesc = make_idesc(fmt, fmt, MODE == XW_MK, MODE == XW_SWAP_MK, XW_M * PAIR, XW_WROWS * PAIR);   // A = resident, except SWAP modes
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)q.grid); cfg.blockDim = dim3(XW_THREADS); cfg.dynamicSmemBytes = XW_SMEM_BYTES; cfg.stream = st;
+  cfg.gridDim = dim3((unsigned)q.grid); cfg.blockDim = dim3((unsigned)xw_threads<Epi>()); cfg.dynamicSmemBytes = XW_SMEM_BYTES; cfg.stream = st;
   cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = PAIR; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
@@ -330,8 +333,8 @@ static Plan make_plan(int64_t B, int64_t C, int D) {
   const XwPlan p1 = xw_plan(B, C, 1), p2 = xw_plan(B, C, 2);
   const size_t part_max = (size_t)(p1.n_chunks > p2.n_chunks ? p1.n_chunks : p2.n_chunks);
   const size_t cos_max = (size_t)(p1.items > 2 * p2.items ? p1.items : 2 * p2.items) * XW_EPI_WARPS;
-  pl.off_part = off; off += align_up(sizeof(float) * part_max * B * PART_COLS, 256);
-  pl.off_cos = off;  off += align_up(sizeof(float) * 2 * cos_max, 256);
+  pl.off_part = off; off += align_up(sizeof(float) * part_max * XW_MAX_EPI_GROUPS * B * PART_COLS, 256);   // one record per epilogue group
+  pl.off_cos = off;  off += align_up(sizeof(float) * 2 * cos_max * XW_MAX_EPI_GROUPS, 256);
   const size_t fwd_total = off;
   // backward: classes are processed in chunks whose fp16 logit gradient G fits the budget.  G is written once
   // and read twice, all while the tensor pipe (not HBM) is the bound, so it need not stay L2-resident: cfg3's
@@ -414,14 +417,23 @@ int head_fwd(const void* xh, const void* wh, const int64_t* label, int64_t B, in
   ep.part = reinterpret_cast<float*>(ws + pl.off_part);
   ep.cos_part = reinterpret_cast<float*>(ws + pl.off_cos);
   ep.nan_flag = nan_flag; ep.pair = q.pair;
+  const int eg = g_epi_groups.load(std::memory_order_relaxed);
   stage_reset(EV_K2);
   stage_event(EV_K2, false, st);
-  rc = (q.pair == 2) ? launch_xw<2, XW_KK, XwFwd>(tx, tw, q, B, C, D, ep, st, "umma K2 arcface_fwd (cta pair)")
-                     : launch_xw<1, XW_KK, XwFwd>(tx, tw, q, B, C, D, ep, st, "umma K2 arcface_fwd");
+  if (eg == 2) {
+    XwFwd2::Params ep2{};
+    ep2.label = ep.label; ep2.class_offset = ep.class_offset; ep2.hm = ep.hm; ep2.inv_scale = ep.inv_scale; ep2.part = ep.part;
+    ep2.cos_part = ep.cos_part; ep2.nan_flag = ep.nan_flag; ep2.pair = ep.pair;
+    rc = (q.pair == 2) ? launch_xw<2, XW_KK, XwFwd2>(tx, tw, q, B, C, D, ep2, st, "umma K2 arcface_fwd (cta pair, 2 epilogue groups)")
+                       : launch_xw<1, XW_KK, XwFwd2>(tx, tw, q, B, C, D, ep2, st, "umma K2 arcface_fwd (2 epilogue groups)");
+  } else {
+    rc = (q.pair == 2) ? launch_xw<2, XW_KK, XwFwd>(tx, tw, q, B, C, D, ep, st, "umma K2 arcface_fwd (cta pair)")
+                       : launch_xw<1, XW_KK, XwFwd>(tx, tw, q, B, C, D, ep, st, "umma K2 arcface_fwd");
+  }
   stage_event(EV_K2, true, st);
   if (rc) return rc;
-  launch_pdl(reduce_row_partials_kernel, dim3((unsigned)ceil_div(B, 8)), dim3(256), 0, st, ep.part, q.n_chunks, B, ep.cos_part,
-                                                                      q.items * q.pair * XW_EPI_WARPS, row_stats, row_best,
+  launch_pdl(reduce_row_partials_kernel, dim3((unsigned)ceil_div(B, 8)), dim3(256), 0, st, ep.part, q.n_chunks * eg, B, ep.cos_part,
+                                                                      q.items * q.pair * XW_EPI_WARPS * eg, row_stats, row_best,
                                                                       row_argmax, cos_minmax);
   B200F_LAUNCH_OK("reduce_row_partials_kernel");
   return B200F_OK;
@@ -456,10 +468,25 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
     eg.label = label; eg.lse = lse; eg.grad4 = grad4; eg.class_offset = class_offset + c0;
     eg.hm = HeadMath{cfg->m_eff, cfg->s_eff, cfg->easy_margin};
     eg.ls_eps = cfg->label_smoothing; eg.inv_Ctot = 1.0f / (float)cfg->num_classes_total; eg.inv_scale = 1.0f / (S * S);
-    eg.GT = G; eg.ldgt = pl.ldg; eg.r_part = r_part; eg.ldr = pl.Cc; eg.ablate = g_k3a_ablate.load(std::memory_order_relaxed);
+    eg.GT = G; eg.ldgt = pl.ldg; eg.r_part = r_part; eg.ldr = pl.Cc;
+#ifdef B200F_PROBES
+    eg.ablate = g_k3a_ablate.load(std::memory_order_relaxed);
+#endif
     stage_event(EV_K3A, false, st);
-    rc = (qg.pair == 2) ? launch_xw<2, XW_SWAP, XwBwdGT>(tx_k, tw_k, qg, B, cnt, D, eg, st, "umma K3a logit-grad (cta pair)")
-                        : launch_xw<1, XW_SWAP, XwBwdGT>(tx_k, tw_k, qg, B, cnt, D, eg, st, "umma K3a logit-grad");
+    if (g_epi_groups.load(std::memory_order_relaxed) == 2) {
+      XwBwdGT2::Params e2{};
+      e2.label = eg.label; e2.lse = eg.lse; e2.grad4 = eg.grad4; e2.class_offset = eg.class_offset; e2.hm = eg.hm;
+      e2.ls_eps = eg.ls_eps; e2.inv_Ctot = eg.inv_Ctot; e2.inv_scale = eg.inv_scale; e2.GT = eg.GT; e2.ldgt = eg.ldgt;
+      e2.r_part = eg.r_part; e2.ldr = eg.ldr;
+#ifdef B200F_PROBES
+      e2.ablate = eg.ablate;
+#endif
+      rc = (qg.pair == 2) ? launch_xw<2, XW_SWAP, XwBwdGT2>(tx_k, tw_k, qg, B, cnt, D, e2, st, "umma K3a logit-grad (cta pair, 2 epilogue groups)")
+                          : launch_xw<1, XW_SWAP, XwBwdGT2>(tx_k, tw_k, qg, B, cnt, D, e2, st, "umma K3a logit-grad (2 epilogue groups)");
+    } else {
+      rc = (qg.pair == 2) ? launch_xw<2, XW_SWAP, XwBwdGT>(tx_k, tw_k, qg, B, cnt, D, eg, st, "umma K3a logit-grad (cta pair)")
+                          : launch_xw<1, XW_SWAP, XwBwdGT>(tx_k, tw_k, qg, B, cnt, D, eg, st, "umma K3a logit-grad");
+    }
     stage_event(EV_K3A, true, st);
     if (rc) return rc;
     // --- K3b: dW[c0 + c, d] = inv_nw_c (sum_b G^T[c, b] x_hat[b, d] - w_hat[c, d] r_c), computed transposed (the thread
@@ -477,7 +504,10 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
       if (g_k3b_class_major.load(std::memory_order_relaxed)) {   // thread owns a class row: vector loads / stores
         XwDwT::Params ew{};
         rc = make_tmap(&ew.tm_wh, wc, D, cnt, D, 32, 32, CU_TENSOR_MAP_SWIZZLE_NONE); if (rc) return rc;
-        ew.coef = coef; ew.dw = dw; ew.c0 = c0; ew.ld = D; ew.ablate = g_k3b_ablate.load(std::memory_order_relaxed);
+        ew.coef = coef; ew.dw = dw; ew.c0 = c0; ew.ld = D;
+#ifdef B200F_PROBES
+        ew.ablate = g_k3b_ablate.load(std::memory_order_relaxed);
+#endif
         rc = (qw.pair == 2) ? launch_xw<2, XW_SWAP_MK, XwDwT>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW class-major (cta pair)", FMT_F16, k3b_rev)
                             : launch_xw<1, XW_SWAP_MK, XwDwT>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW class-major", FMT_F16, k3b_rev);
       } else
@@ -746,10 +776,12 @@ int b200f_set_tunable(const char* name, int value) {
   if (n == "pdl") { const int old_v = pdl_enabled() ? 1 : 0; if (value == 0 || value == 1) pdl_set(value != 0); return old_v; }
   if (n == "k3b_class_major") { if (value != 0 && value != 1) return g_k3b_class_major.load(); return g_k3b_class_major.exchange(value); }
   if (n == "stage_events") { if (value != 0 && value != 1) return g_stage_events.load(); return g_stage_events.exchange(value); }
-  // probes that make the backward skip memory traffic (WRONG results): refused unless the process opts in
-  if ((n == "k3a_ablate" || n == "k3b_ablate") && std::getenv("B200F_ALLOW_PROBES") == nullptr) return -1;
+  if (n == "epi_groups") { if (value != 1 && value != 2) return g_epi_groups.load(); return g_epi_groups.exchange(value); }
+#ifdef B200F_PROBES
+  // probes that make the backward skip memory traffic (WRONG results): -DB200F_PROBES builds only (tools/)
   if (n == "k3a_ablate") { if (value < 0) return g_k3a_ablate.load(); return g_k3a_ablate.exchange(value); }
   if (n == "k3b_ablate") { if (value < 0) return g_k3b_ablate.load(); return g_k3b_ablate.exchange(value); }
+#endif
   if (n == "k3b_reverse") { if (value != 0 && value != 1) return g_k3b_reverse.load(); return g_k3b_reverse.exchange(value); }
   if (n == "xw_prefetch") { if (value < 0) return g_prefetch.load(); return g_prefetch.exchange(value); }
   if (n == "g_chunk_mb") { if (value < 1) return g_chunk_mb.load(); return g_chunk_mb.exchange(value); }

@@ -32,8 +32,9 @@ constexpr int XW_MAX_KB = 8;                    // D <= 512 stays resident
 constexpr int XW_STAGES = 5;
 
 constexpr int XW_TILE_BYTES = XW_M * XW_K * 2;  // 16 KB: one k-block of x, or one stage of w
-constexpr int XW_EPI_WARPS = 8;
-constexpr int XW_THREADS = 64 + 32 * XW_EPI_WARPS;   // 320
+constexpr int XW_EPI_WARPS = 8;                   // epilogue warps of ONE group (two per TMEM lane quadrant)
+constexpr int XW_THREADS = 64 + 32 * XW_EPI_WARPS;   // 320: producer + MMA issuer + one epilogue group
+constexpr int XW_MAX_EPI_GROUPS = 2;
 constexpr int XW_SCRATCH_FLOATS = 2048;
 constexpr int XW_MAX_ACC = 4;                     // accumulator stages: 2 x 256 columns (CTA pair) or 4 x 128 (single CTA)
 constexpr int XW_NUM_BARS = 2 + 2 * XW_STAGES + 2 * XW_MAX_ACC;
@@ -66,8 +67,29 @@ __device__ __forceinline__ void tmem_ld_wait_dep(float (&v)[32]) {
       :
       : "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() {      // the 256 epilogue threads only
-  asm volatile("bar.sync 1, 256;" ::: "memory");
+// 16-column forms (policies with kSliceCols = 16: half the live accumulator registers per slice)
+__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, float (&v)[16]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait_dep(float (&v)[16]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.wait::ld.sync.aligned;"
+      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+        "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+      :
+      : "memory");
+}
+// barrier over the 256 threads of ONE epilogue group (ids 1, 2: the groups run at their own pace)
+__device__ __forceinline__ void epi_bar_sync(int grp = 0) {
+  asm volatile("bar.sync %0, 256;" ::"r"(1 + grp) : "memory");
 }
 
 // X_MN / W_MN: layout of the resident ("x") and the streamed ("w") operand: false = K-major (rows x k, row-major),
@@ -103,18 +125,35 @@ template <class Epi> struct xw_slice_wants_scratch<Epi, decltype((void)Epi::kSli
 template <class Epi, class = void> struct xw_ring_stages { static constexpr int value = XW_STAGES; };
 template <class Epi> struct xw_ring_stages<Epi, decltype((void)Epi::kRingStages)> { static constexpr int value = Epi::kRingStages; };
 
+// Epilogue groups.  A policy with kEpiGroups = 2 runs TWO groups of 8 epilogue warps (576 threads, <= 112 registers):
+// group g takes the tiles whose running number n has n % 2 == g, i.e. with two accumulator stages each group owns one
+// stage.  Why: with one group every tile costs E (epilogue) + hand-over latency in series with the next-but-one tile's
+// MMAs (measured at cfg3: E = 4400 busy cycles, M = 4100 tensor cycles, period 6140); with two groups Epi(t) and
+// Epi(t + 1) overlap and the period is max(M, (E + M) / 2).  Per-row state is per group: item_end emits one partial
+// record per (row, chunk, group).
+template <class Epi, class = void> struct xw_epi_groups { static constexpr int value = 1; };
+template <class Epi> struct xw_epi_groups<Epi, decltype((void)Epi::kEpiGroups)> { static constexpr int value = Epi::kEpiGroups; };
+// columns per slice() call: 32 (default) or 16 (kSliceCols = 16)
+template <class Epi, class = void> struct xw_slice_cols { static constexpr int value = 32; };
+template <class Epi> struct xw_slice_cols<Epi, decltype((void)Epi::kSliceCols)> { static constexpr int value = Epi::kSliceCols; };
+template <class Epi> __host__ __device__ constexpr int xw_threads() { return 64 + 32 * XW_EPI_WARPS * xw_epi_groups<Epi>::value; }
+// registers per thread: 1 CTA per SM either way (shared memory).  10 warps x 168 and 18 warps x 112 both fit the 64 K file;
+// __launch_bounds__(576, 1) alone makes ptxas stop at 96.
+template <class Epi> __host__ __device__ constexpr int xw_maxnreg() { return xw_epi_groups<Epi>::value == 1 ? 168 : 112; }
+
 struct XwItem {                         // what an epilogue thread knows about its work item
   int item, chunk, group;
-  int rank, ew, quad, half, lane;       // CTA rank in the pair, epilogue warp 0..7, TMEM quadrant, column half, lane
+  int rank, ew, quad, half, lane;       // CTA rank in the pair, epilogue warp 0..7 of its group, TMEM quadrant, column half, lane
+  int grp;                              // epilogue group 0..kEpiGroups-1
   int64_t row;                          // global row of x owned by this thread
   uint8_t* aux;                         // this warp's staging bytes (nullptr unless the policy reserves them)
   uint64_t* aux_bar;                    // its two mbarriers
   mutable uint32_t aux_phase;           // their parity bits; lives across the items of the kernel
 };
 
-template <class Epi, class State, class Params>
+template <class Epi, class State, class Params, int SC>
 __device__ __forceinline__ void xw_call_slice(State& st, const Params& ep, const XwParams& p, const XwItem& it,
-                                              float (&v)[32], int cls0, float* scratch) {
+                                              float (&v)[SC], int cls0, float* scratch) {
   if constexpr (xw_slice_wants_scratch<Epi>::value) Epi::slice(st, ep, p, it, v, cls0, scratch);
   else Epi::slice(st, ep, p, it, v, cls0);
 }
@@ -129,7 +168,7 @@ __device__ __forceinline__ void xw_call_slice(State& st, const Params& ep, const
 //         v = accumulators of row it.row for classes [cls0, cls0 + 32) of this launch (warp-uniform cls0 < C)
 //     static __device__ void item_end(State&, const Params&, const XwParams&, const XwItem&, float* scratch); }
 template <int PAIR, bool X_MN, bool W_MN, bool SWAP, class Epi>
-__global__ void __launch_bounds__(XW_THREADS, 1)
+__global__ void __maxnreg__(xw_maxnreg<Epi>())
 xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const XwParams p,
           const __grid_constant__ typename Epi::Params ep) {
   constexpr int TN = XW_WROWS * PAIR;                        // class-tile width of the cluster
@@ -310,14 +349,19 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
       }
     }
   } else {
-    // ================= epilogue (8 warps, both CTAs) =================
+    // ================= epilogue (8 warps per group, both CTAs) =================
+    constexpr int EG = xw_epi_groups<Epi>::value;
+    constexpr int SC = xw_slice_cols<Epi>::value;
+    static_assert(EG >= 1 && EG <= XW_MAX_EPI_GROUPS && (SC == 16 || SC == 32), "epilogue geometry");
     XwItem it;
-    it.rank = rank; it.ew = warp - 2; it.quad = warp & 3; it.half = (warp - 2) >> 2; it.lane = lane;
+    it.rank = rank; it.grp = (warp - 2) / XW_EPI_WARPS; it.ew = (warp - 2) % XW_EPI_WARPS;
+    it.quad = warp & 3; it.half = it.ew >> 2; it.lane = lane;
     it.aux = (STAGES < XW_STAGES) ? aux + (size_t)it.ew * AUX_WARP_BYTES : nullptr;
     it.aux_bar = aux_bar + 2 * it.ew; it.aux_phase = 0;
-    int acc = 0; uint32_t acc_phase = 0;
+    float* const gscratch = scratch + it.grp * (XW_SCRATCH_FLOATS / XW_MAX_EPI_GROUPS);   // this group's half of the scratch
+    uint32_t tile_no = 0;                                      // running tile number of this CTA (all groups count alike)
     bool ok = true;
-    constexpr int SLICES = TN / 64;                            // 32-column slices per warp per tile
+    constexpr int SLICES = TN / 2 / SC;                        // slices per warp per tile
     if constexpr (SWAP) {
       // Accumulator lanes = streamed rows (classes), columns = the resident operand's rows (the batch rows of the
       // group): the thread owns ONE class per tile and sees half of the group's batch rows.
@@ -326,9 +370,12 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
         const int t_begin = (int)((int64_t)it.chunk * p.n_tiles / p.n_chunks);
         const int t_end = (int)((int64_t)(it.chunk + 1) * p.n_tiles / p.n_chunks);
         typename Epi::State stt;
-        Epi::item_begin(stt, ep, p, it, scratch, TN);          // per-column tables of the group -> shared memory
+        Epi::item_begin(stt, ep, p, it, gscratch, TN);         // per-column tables of the group -> shared memory
         const int col_base = it.half * (TN / 2);
         for (int ti = t_begin; ti < t_end; ++ti) {
+          const uint32_t n = tile_no++;
+          if (EG > 1 && (int)(n % EG) != it.grp) continue;     // the other group's tile
+          const int acc = (int)(n % ACC); const uint32_t acc_phase = (n / ACC) & 1u;
           const int t = p.reverse ? (t_end - 1 - (ti - t_begin)) : ti;
           ok = mbar_wait(&acc_full[acc], acc_phase);
           ok = __all_sync(0xffffffffu, ok);
@@ -337,16 +384,16 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
           it.row = (int64_t)t * TN + rank * XW_WROWS + it.quad * 32 + lane;   // the class this thread owns in tile t
           const uint32_t taddr = tmem_base + (uint32_t)acc * ACC_STRIDE + ((uint32_t)(it.quad * 32) << 16) + (uint32_t)col_base;
           Epi::tile_begin(stt, ep, p, it);
-          float va[32], vb[32];
+          float va[SC], vb[SC];
           tmem_ld32_async(taddr, va);
 #pragma unroll 1
           for (int s = 0; s < SLICES; s += 2) {
             tmem_ld_wait_dep(va);
-            tmem_ld32_async(taddr + (uint32_t)(s + 1) * 32, vb);
-            Epi::slice(stt, ep, p, it, va, col_base + s * 32, scratch);
+            tmem_ld32_async(taddr + (uint32_t)(s + 1) * SC, vb);
+            Epi::slice(stt, ep, p, it, va, col_base + s * SC, gscratch);
             tmem_ld_wait_dep(vb);
-            if (s + 2 < SLICES) tmem_ld32_async(taddr + (uint32_t)(s + 2) * 32, va);
-            Epi::slice(stt, ep, p, it, vb, col_base + (s + 1) * 32, scratch);
+            if (s + 2 < SLICES) tmem_ld32_async(taddr + (uint32_t)(s + 2) * SC, va);
+            Epi::slice(stt, ep, p, it, vb, col_base + (s + 1) * SC, gscratch);
           }
           tc_fence_before_sync();
           __syncwarp();
@@ -354,7 +401,6 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
             if (PAIR == 2) mbar_arrive_cluster(&acc_empty[acc], 0);
             else mbar_arrive(&acc_empty[acc]);
           }
-          if (++acc == ACC) { acc = 0; acc_phase ^= 1; }
           Epi::tile_end(stt, ep, p, it);
         }
         if (!ok) break;
@@ -368,6 +414,9 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
       typename Epi::State stt;
       Epi::item_begin(stt, ep, p, it);
       for (int ti = t_begin; ti < t_end; ++ti) {
+        const uint32_t n = tile_no++;
+        if (EG > 1 && (int)(n % EG) != it.grp) continue;       // the other group's tile
+        const int acc = (int)(n % ACC); const uint32_t acc_phase = (n / ACC) & 1u;
         const int t = p.reverse ? (t_end - 1 - (ti - t_begin)) : ti;
         ok = mbar_wait(&acc_full[acc], acc_phase);
         ok = __all_sync(0xffffffffu, ok);
@@ -377,17 +426,17 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
         const uint32_t taddr = tmem_base + (uint32_t)acc * ACC_STRIDE + ((uint32_t)(it.quad * 32) << 16) + (uint32_t)col_base;
         const int cls_base = t * TN + col_base;
         Epi::tile_begin(stt, ep, p, it, cls_base, (ti + 1 < t_end) ? cls_base + (p.reverse ? -TN : TN) : -1, TN / 2);
-        float va[32], vb[32];
+        float va[SC], vb[SC];
         tmem_ld32_async(taddr, va);
         // two slices per trip, NOT fully unrolled: the policy code exists twice, not 2 * SLICES times (i-cache)
 #pragma unroll 1
         for (int s = 0; s < SLICES; s += 2) {
           tmem_ld_wait_dep(va);
-          tmem_ld32_async(taddr + (uint32_t)(s + 1) * 32, vb);
-          if (cls_base + s * 32 < p.C) xw_call_slice<Epi>(stt, ep, p, it, va, cls_base + s * 32, scratch);
+          tmem_ld32_async(taddr + (uint32_t)(s + 1) * SC, vb);
+          if (cls_base + s * SC < p.C) xw_call_slice<Epi>(stt, ep, p, it, va, cls_base + s * SC, gscratch);
           tmem_ld_wait_dep(vb);
-          if (s + 2 < SLICES) tmem_ld32_async(taddr + (uint32_t)(s + 2) * 32, va);
-          if (cls_base + (s + 1) * 32 < p.C) xw_call_slice<Epi>(stt, ep, p, it, vb, cls_base + (s + 1) * 32, scratch);
+          if (s + 2 < SLICES) tmem_ld32_async(taddr + (uint32_t)(s + 2) * SC, va);
+          if (cls_base + (s + 1) * SC < p.C) xw_call_slice<Epi>(stt, ep, p, it, vb, cls_base + (s + 1) * SC, gscratch);
         }
         tc_fence_before_sync();
         __syncwarp();
@@ -395,10 +444,9 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
           if (PAIR == 2) mbar_arrive_cluster(&acc_empty[acc], 0);
           else mbar_arrive(&acc_empty[acc]);
         }
-        if (++acc == ACC) { acc = 0; acc_phase ^= 1; }
       }
       if (!ok) break;
-      Epi::item_end(stt, ep, p, it, scratch);
+      Epi::item_end(stt, ep, p, it, gscratch);
     }
   }
   tc_fence_before_sync();

@@ -57,14 +57,17 @@ struct XwNull {
 // -------------------------------------------------------------------------------------------------
 // K2: cosine logits -> margin -> scale -> softmax / cross-entropy statistics (src/face_models.py:355-427,
 // training.py:515).  Nothing B x C is stored: ONE partial record per (row, class chunk).
-struct XwFwd {
+template <int EG, int SC>
+struct XwFwdT {
+  static constexpr int kEpiGroups = EG;
+  static constexpr int kSliceCols = SC;
   struct Params {
     const int64_t* label;
     int64_t class_offset;       // global id of this launch's class 0
     HeadMath hm;
     float inv_scale;            // 1 / S^2 : cos = acc * inv_scale
-    float* part;                // [B, n_chunks, PART_COLS]
-    float* cos_part;            // [items * PAIR * 8, 2]
+    float* part;                // [B, n_chunks * EG, PART_COLS]
+    float* cos_part;            // [items * PAIR * 8 * EG, 2]
     int32_t* nan_flag;
     int pair;
   };
@@ -89,19 +92,19 @@ struct XwFwd {
 
   static __device__ __forceinline__ void tile_begin(State&, const Params&, const XwParams&, const XwItem&, int, int, int) {}
   static __device__ __forceinline__ void slice(State& st, const Params& ep, const XwParams& p, const XwItem& it,
-                                               float (&v)[32], int cls0) {
-    const int cc = min(32, p.C - cls0);
+                                               float (&v)[SC], int cls0) {
+    const int cc = min(SC, p.C - cls0);
     const float s_eff = ep.hm.s_eff;
     const float isc = ep.inv_scale;
     const float zs = isc * s_eff;                             // z = acc * zs off the target column
     const float a = zs * LOG2E, b = -s_eff * LOG2E;           // exp(z - s_eff) = 2^(acc*a + b)
     const float lo = cos_lo(), hi = cos_hi();
-    // four independent accumulator lanes: the dependent chains are 8 long, not 32 (latency, not issue, bounds
+    // four independent accumulator lanes: the dependent chains are SC / 4 long, not SC (latency, not issue, bounds
     // a lone epilogue warp); the summation order is still fixed, so results are bitwise reproducible
     float ce4[4] = {0.f, 0.f, 0.f, 0.f}, cq4[4] = {0.f, 0.f, 0.f, 0.f}, ct4[4] = {0.f, 0.f, 0.f, 0.f};
     float mn4[4] = {INFINITY, INFINITY, INFINITY, INFINITY}, mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
+    for (int j = 0; j < SC; j += 4) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const float tt = v[j + u];
@@ -118,8 +121,8 @@ struct XwFwd {
     const float ct = (ct4[0] + ct4[1]) + (ct4[2] + ct4[3]);
     const float tmn = fminf(fminf(mn4[0], mn4[1]), fminf(mn4[2], mn4[3]));
     const float tmx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-    const bool has_t = (st.tgt >= cls0) && (st.tgt < cls0 + 32);
-    bool careful = !(s_eff > 0.f) || has_t || (cc < 32) || !(tmx * isc <= hi) || !(tmn * isc >= lo) ||
+    const bool has_t = (st.tgt >= cls0) && (st.tgt < cls0 + SC);
+    bool careful = !(s_eff > 0.f) || has_t || (cc < SC) || !(tmx * isc <= hi) || !(tmn * isc >= lo) ||
                    !isfinite(ct) || !isfinite(ce);
     careful = __any_sync(0xffffffffu, careful);               // warp stays convergent for the next tcgen05.ld
     if (!careful) {
@@ -128,9 +131,9 @@ struct XwFwd {
       const float bz = tmx * zs;
       if (bz > st.best) {                                     // rare after the first few slices
         st.best = bz;
-        int tix = 31;
+        int tix = SC - 1;
 #pragma unroll
-        for (int j = 30; j >= 0; --j) if (v[j] == tmx) tix = j;   // first index of the maximum
+        for (int j = SC - 2; j >= 0; --j) if (v[j] == tmx) tix = j;   // first index of the maximum
         st.bestidx = cls0 + tix;
       }
     } else {
@@ -140,11 +143,11 @@ struct XwFwd {
       if (has_t) {
         float ct = 0.f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) if (cls0 + j == st.tgt) ct = v[j] * isc;
+        for (int j = 0; j < SC; ++j) if (cls0 + j == st.tgt) ct = v[j] * isc;
         tphi = ep.hm.phi((ct != ct) ? ct : fminf(fmaxf(ct, lo), hi));
       }
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
+      for (int j = 0; j < SC; ++j) {
         if (j < cc) {
           const float cosv = v[j] * isc;
           st.cmin = fminf(st.cmin, cosv); st.cmax = fmaxf(st.cmax, cosv);
@@ -171,13 +174,13 @@ struct XwFwd {
       slot[0] = st.sumexp; slot[1] = st.sumexp2; slot[2] = st.ztgt; slot[3] = st.sumz; slot[4] = st.best;
       reinterpret_cast<int*>(slot)[5] = st.bestidx;
     }
-    epi_bar_sync();
+    epi_bar_sync(it.grp);
     if (it.half == 0 && st.row_ok) {
       const float ob = slot[4];
       const int oi = reinterpret_cast<const int*>(slot)[5];
       float best = st.best; int bi = st.bestidx;
       if (oi >= 0 && (bi < 0 || ob > best || (ob == best && oi < bi))) { best = ob; bi = oi; }
-      float* dst = ep.part + (it.row * p.n_chunks + it.chunk) * PART_COLS;
+      float* dst = ep.part + (it.row * (p.n_chunks * EG) + it.chunk * EG + it.grp) * PART_COLS;
       dst[0] = st.sumexp + slot[0]; dst[1] = st.sumexp2 + slot[1]; dst[2] = st.ztgt + slot[2];
       dst[3] = st.sumz + slot[3]; dst[4] = best;
       reinterpret_cast<int32_t*>(dst)[5] = (bi < 0) ? -1 : (int32_t)(ep.class_offset + bi);
@@ -185,13 +188,15 @@ struct XwFwd {
     float cmin = st.row_ok ? st.cmin : INFINITY, cmax = st.row_ok ? st.cmax : -INFINITY;
     cmin = warp_min(cmin); cmax = warp_max(cmax);
     if (it.lane == 0) {
-      float* cp = ep.cos_part + 2 * (((int64_t)it.item * ep.pair + it.rank) * XW_EPI_WARPS + it.ew);
+      float* cp = ep.cos_part + 2 * (((int64_t)it.item * ep.pair + it.rank) * (XW_EPI_WARPS * EG) + it.grp * XW_EPI_WARPS + it.ew);
       cp[0] = cmin; cp[1] = cmax;
     }
     if (__any_sync(0xffffffffu, st.saw_nan) && it.lane == 0) atomicExch(ep.nan_flag, 1);
-    epi_bar_sync();
+    epi_bar_sync(it.grp);
   }
 };
+using XwFwd = XwFwdT<1, 32>;        // one epilogue group, 32-column slices (round 1)
+using XwFwd2 = XwFwdT<2, 16>;       // two epilogue groups (16 warps), 16-column slices
 
 // -------------------------------------------------------------------------------------------------
 // K3a, class-major (xw_kernel SWAP mode): the thread owns ONE class of the tile, the 32 columns of a slice are batch
@@ -210,7 +215,20 @@ __device__ __noinline__ void head_phi_dphi(HeadMath hm, float c, float* phi, flo
 // (Measured and rejected: G^T through per-warp TMA tensor stores -- 2 KB staged slices, one ring stage given up --
 //  ran within noise of the 32-byte global stores kept here, 2225 vs 2186 us on one rank's cfg4 step.  Removing the
 //  stores altogether (k3a_ablate = 2) takes 313 us off that step although the kernel moves only 1.6 TB/s.)
-struct XwBwdGT {
+// Probes that skip memory traffic (WRONG results) exist only in -DB200F_PROBES builds (tools/): the shipped library
+// carries neither the branch nor the ABI to switch it on.
+#ifdef B200F_PROBES
+#define B200F_PROBE_FIELD int ablate;
+#define B200F_PROBE_ON(ep, bit) (((ep).ablate & (bit)) != 0)
+#else
+#define B200F_PROBE_FIELD
+#define B200F_PROBE_ON(ep, bit) false
+#endif
+
+template <int EG, int SC>
+struct XwBwdGTT {
+  static constexpr int kEpiGroups = EG;
+  static constexpr int kSliceCols = SC;
   struct Params {
     const int64_t* label; const float* lse; const float* grad4;
     int64_t class_offset;       // global id of this launch's class 0
@@ -218,13 +236,13 @@ struct XwBwdGT {
     float ls_eps, inv_Ctot, inv_scale;
     uint16_t* GT; int64_t ldgt; // G^T[class of this launch, batch row]
     float* r_part; int64_t ldr; // [2 * m_groups, ldr]: one partial per (row group, column half)
-    int ablate;                 // probe only: 2 = no G^T stores (WRONG results)
+    B200F_PROBE_FIELD           // probe builds only: 2 = no G^T stores (WRONG results)
   };
   struct State { float gs, r; int cls; bool row_ok; };
 
   static __device__ __forceinline__ void item_begin(State& st, const Params& ep, const XwParams& p, const XwItem& it,
                                                     float* scratch, int TN) {
-    epi_bar_sync();                                           // the previous item's readers are done
+    epi_bar_sync(it.grp);                                     // the previous item's readers (of this group) are done
     const int e = it.ew * 32 + it.lane;
     if (e < TN) {
       const int64_t b = (int64_t)it.group * TN + e;
@@ -237,7 +255,7 @@ struct XwBwdGT {
       scratch[e] = bneg;
       reinterpret_cast<int*>(scratch)[TN + e] = lab;
     }
-    epi_bar_sync();
+    epi_bar_sync(it.grp);
     st.gs = __ldg(ep.grad4) * __ldg(ep.grad4 + 3);
     st.r = 0.f; st.cls = 0; st.row_ok = false;
   }
@@ -246,7 +264,7 @@ struct XwBwdGT {
   }
 
   static __device__ __forceinline__ void slice(State& st, const Params& ep, const XwParams& p, const XwItem& it,
-                                               float (&v)[32], int col0, float* scratch) {
+                                               float (&v)[SC], int col0, float* scratch) {
     const float s_eff = ep.hm.s_eff;
     const float isc = ep.inv_scale;
     const float a = isc * s_eff * LOG2E;                      // p = 2^(acc * a - lse log2 e)
@@ -257,15 +275,15 @@ struct XwBwdGT {
     // explicit ld.shared: through the generic pointer these compile to LD.E, which queues in the global load/store
     // path behind this kernel's own G^T stores
     const uint32_t tb_s = smem_u32(scratch + col0);
-    float bb[32];
+    float bb[SC];
 #pragma unroll
-    for (int j = 0; j < 32; j += 4)
+    for (int j = 0; j < SC; j += 4)
       asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                    : "=f"(bb[j]), "=f"(bb[j + 1]), "=f"(bb[j + 2]), "=f"(bb[j + 3]) : "r"(tb_s + j * 4));
-    float g[32];
+    float g[SC];
     float am4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
+    for (int j = 0; j < SC; j += 4) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const float tt = v[j + u];
@@ -277,10 +295,10 @@ struct XwBwdGT {
     asm("max.NaN.xorsign.abs.f32 %0, %1, %2;" : "=f"(amax) : "f"(am4[0]), "f"(am4[1]));
     asm("max.NaN.xorsign.abs.f32 %0, %0, %1;" : "+f"(amax) : "f"(am4[2]));
     asm("max.NaN.xorsign.abs.f32 %0, %0, %1;" : "+f"(amax) : "f"(am4[3]));
-    // a target element sits in this slice iff one of its 32 batch rows is labelled with one of the warp's 32 classes
+    // a target element sits in this slice iff one of its SC batch rows is labelled with one of the warp's 32 classes
     const int* tl = reinterpret_cast<const int*>(scratch) + p_tn(p) + col0;
     int lab_l;
-    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(lab_l) : "r"(smem_u32(tl + it.lane)));
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(lab_l) : "r"(smem_u32(tl + (it.lane & (SC - 1)))));
     const int c_w0 = st.cls - it.lane;
     bool careful = !(s_eff > 0.f) || (lab_l >= c_w0 && lab_l < c_w0 + 32) || !(fabsf(amax) * isc <= hi);
     careful = __any_sync(0xffffffffu, careful);
@@ -288,14 +306,14 @@ struct XwBwdGT {
     if (!careful) {
       float r4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
+      for (int j = 0; j < SC; j += 4) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) r4[u] = fmaf(g[j + u], v[j + u], r4[u]);
       }
       racc = (r4[0] + r4[1]) + (r4[2] + r4[3]);
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
+      for (int j = 0; j < SC; ++j) {
         const float cosv = v[j] * isc;
         const float c = (cosv != cosv) ? cosv : fminf(fmaxf(cosv, lo), hi);
         const bool is_t = st.row_ok && (tl[j] == st.cls);
@@ -312,18 +330,19 @@ struct XwBwdGT {
       }
     }
     st.r += racc;
-    if (st.row_ok && !((ep.ablate & 2) && g[0] != 12345.678f)) {
+    if (st.row_ok && !(B200F_PROBE_ON(ep, 2) && g[0] != 12345.678f)) {
       const int64_t b0 = (int64_t)it.group * p_tn(p) + col0;
       uint16_t* gdst = ep.GT + (int64_t)st.cls * ep.ldgt + b0;
-      if (b0 + 32 <= p.B) {
-        uint32_t w1[16];
+      if (b0 + SC <= p.B) {
+        uint32_t w1[SC / 2];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) w1[j] = pack_f16(g[2 * j], g[2 * j + 1]);
-        st_global_256(gdst, w1[0], w1[1], w1[2], w1[3], w1[4], w1[5], w1[6], w1[7]);
-        st_global_256(gdst + 16, w1[8], w1[9], w1[10], w1[11], w1[12], w1[13], w1[14], w1[15]);
+        for (int j = 0; j < SC / 2; ++j) w1[j] = pack_f16(g[2 * j], g[2 * j + 1]);
+#pragma unroll
+        for (int j = 0; j < SC / 2; j += 8)
+          st_global_256(gdst + 2 * j, w1[j], w1[j + 1], w1[j + 2], w1[j + 3], w1[j + 4], w1[j + 5], w1[j + 6], w1[j + 7]);
       } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
+        for (int j = 0; j < SC; ++j)
           if (b0 + j < p.B) gdst[j] = (uint16_t)(pack_f16(g[j], 0.f) & 0xffff);
       }
     }
@@ -337,6 +356,8 @@ struct XwBwdGT {
   // rows of the resident group = width of the column space = 128 * PAIR; carried in XwParams.tn
   static __device__ __forceinline__ int p_tn(const XwParams& p) { return p.tn; }
 };
+using XwBwdGT = XwBwdGTT<1, 32>;
+using XwBwdGT2 = XwBwdGTT<2, 16>;
 
 // -------------------------------------------------------------------------------------------------
 // K3b on the MN-major kernel: acc[d, c] = sum_b x_hat[b, d] S * G'[b, c]  (= dW_hat^T * S * g_scale), finished in
@@ -417,14 +438,15 @@ struct XwDwT {
   static constexpr int kRingStages = 3;
   struct Params {
     alignas(64) CUtensorMap tm_wh;      // w_hat16 rows of this launch [classes, D], box 32 features x 32 classes, no swizzle
-    const float2* coef; float* dw; int64_t c0; int ld; int ablate;   // ablate: probe only
+    const float2* coef; float* dw; int64_t c0; int ld;
+    B200F_PROBE_FIELD                   // probe builds only: 1 = no w_hat loads, 2 = no dW stores (WRONG results)
   };
   struct State { float2 cf, cf_next; int64_t next_row; int seq, n_seq, row0, row_step; bool row_ok; };
 
   // slice n of this warp's item = column slice (n % spt) of its (n / spt)-th tile; buffer n & 1
   static __device__ __forceinline__ void issue(const State& st, const Params& ep, const XwParams& p, const XwItem& it, int n) {
     const int spt = p.tn >> 6;
-    if (n >= st.n_seq || (ep.ablate & 1)) return;
+    if (n >= st.n_seq || B200F_PROBE_ON(ep, 1)) return;
     const int d0 = it.group * p.tn + it.half * (p.tn >> 1) + (n % spt) * 32;
     if (d0 >= p.B) return;                                    // ragged feature count: nothing there (the reader skips too)
     if (it.lane == 0) {
@@ -458,7 +480,7 @@ struct XwDwT {
     const int d0 = it.group * p.tn + col0;                   // first of this slice's 32 features
     if (d0 >= p.B) return;
     uint4 w[4];
-    if (ep.ablate & 1) {
+    if (B200F_PROBE_ON(ep, 1)) {
       w[0] = w[1] = w[2] = w[3] = make_uint4(0, 0, 0, 0);
     } else {
       const uint32_t b = (uint32_t)n & 1u;
@@ -484,7 +506,7 @@ struct XwDwT {
           o[i * 8 + j * 2 + 1] = cx * fmaf(-f.y, cy, v[i * 8 + j * 2 + 1]);
         }
       }
-      if ((ep.ablate & 2) && o[0] != 12345.678f) {
+      if (B200F_PROBE_ON(ep, 2) && o[0] != 12345.678f) {
       } else if (d0 + 32 <= p.B && (ep.ld & 7) == 0) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)

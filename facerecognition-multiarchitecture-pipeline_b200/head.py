@@ -137,8 +137,31 @@ def _prepare_weight(w: torch.Tensor, f16n: bool, cache: Optional[dict]):
     return val
 
 
+def _check_head_inputs(x, w, label, dlogits=None):
+    """Shape / dtype / device checks the kernels cannot make (they see raw pointers): a mismatch here would be an
+    out-of-bounds device read or a host pointer handed to a kernel.  The reference raises a Python error in each of
+    these cases too (F.linear shape error, scatter_ index error, device mismatch)."""
+    if x.dim() != 2 or w.dim() != 2:
+        raise ValueError(f"head: input must be [B, D] and weight [C, D]; got {tuple(x.shape)} and {tuple(w.shape)}")
+    if x.shape[1] != w.shape[1]:
+        raise ValueError(f"head: input has {x.shape[1]} features, weight has {w.shape[1]}")
+    if label.dim() != 1 or label.shape[0] != x.shape[0]:
+        raise ValueError(f"head: label must be [B] = [{x.shape[0]}]; got {tuple(label.shape)}")
+    if label.dtype != torch.int64:
+        raise TypeError(f"head: label must be int64, got {label.dtype}")
+    require_cuda(x, w, label, dlogits)
+    if not (x.device == w.device == label.device):
+        raise RuntimeError(f"head: input ({x.device}), weight ({w.device}) and label ({label.device}) must share a device")
+    if not (x.is_contiguous() and w.is_contiguous() and label.is_contiguous()):
+        raise ValueError("head: kernels take contiguous tensors")
+    if dlogits is not None and (dlogits.dim() != 2 or dlogits.shape[0] != x.shape[0] or dlogits.shape[1] != w.shape[0]
+                                or dlogits.device != x.device or not dlogits.is_contiguous()):
+        raise ValueError(f"head: dlogits must be a contiguous [B, C] = [{x.shape[0]}, {w.shape[0]}] tensor on {x.device}")
+
+
 def _fwd_kernels(x, w, label, cfg: HeadCfg, class_offset, want_logits, w_cache=None, nan_flag=None):
     lib = _lib.load_library()
+    _check_head_inputs(x, w, label)
     B, D = x.shape
     C = w.shape[0]
     dev = x.device
@@ -166,6 +189,7 @@ def _fwd_kernels(x, w, label, cfg: HeadCfg, class_offset, want_logits, w_cache=N
 
 def _bwd_kernels(xo, wo, label, inv_nx, inv_nw, lse, grad4, cfg: HeadCfg, class_offset, dlogits=None):
     lib = _lib.load_library()
+    _check_head_inputs(xo, wo, label, dlogits)
     B, D = xo.shape
     C = wo.shape[0]
     dev = xo.device
@@ -385,6 +409,15 @@ class GraphedHeadStep:
         self.weight.grad = self.dw                    # the same tensor every call, refreshed in place by the replay
         return self.loss
 
+    def close(self):
+        """Wait for the replays in flight and destroy the captured graph.  With a process group in the step the graph
+        holds NCCL kernels of that communicator: torch.distributed.destroy_process_group() must not run before this
+        (round 1's bench left with os._exit because the teardown blocked)."""
+        if getattr(self, "graph", None) is not None:
+            torch.cuda.synchronize(self.weight.device)
+            self.graph.reset()
+            self.graph = None
+
 
 class ArcMarginProduct(nn.Module):
     """Drop-in for the reference ArcMarginProduct (face_models.py:297-445): same constructor, the
@@ -414,7 +447,27 @@ class ArcMarginProduct(nn.Module):
         self._hook = _Hook()
         self._w_shadow = None
         self._w_prep = {}                  # K1 output for the current weight version
-        self.cache_weight_prep = True      # reuse K1(weight) until the parameter changes
+        # Reuse K1(weight) while the parameter is unchanged.  Only in eval mode (or when an optimizer keeps the operands
+        # current in place, optim.HeadAdamW): training changes the rows every step, and the (data_ptr, _version) key
+        # cannot see writes through ``weight.data`` (EMA updates, manual renormalisation) -- a stale normalised copy
+        # would silently train on old weights.  load_state_dict clears the cache (hook below).
+        self.cache_weight_prep = True
+        self.validate_labels = False       # debug: check 0 <= label < C on the host (one sync), like scatter_ would
+        # class-parallel placement (parallel.ShardedArcMarginProduct sets these): this module owns the class rows
+        # [_class_offset, _class_offset + out_feats) of a [_num_classes_total, D] matrix sharded over _group
+        self._class_offset = 0
+        self._num_classes_total = None
+        self._group = None
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._drop_weight_caches())
+
+    def _drop_weight_caches(self):
+        """Forget every derived copy of the weights (K1 operands, bf16 shadow).  Called after load_state_dict; call it
+        yourself after writing through ``weight.data``."""
+        static = self._w_prep.get("static_refresh")
+        self._w_prep.pop("key", None); self._w_prep.pop("val", None)
+        self._w_shadow = None
+        if static is not None:
+            static()                       # an attached HeadAdamW re-derives its in-place operands
 
     # -- schedule + effective parameters (host logic, stateful exactly like the reference) --------
     def _step_schedule(self):
@@ -463,12 +516,21 @@ class ArcMarginProduct(nn.Module):
         (hyperparameter_tuning.py:1001)."""
         m_eff, s_eff = self._step_schedule()
         x, weight, w = self._operands(input)
+        if self.validate_labels:
+            c_tot = self._num_classes_total or self.out_feats
+            if label.numel() and (int(label.min()) < 0 or int(label.max()) >= c_tot):
+                raise IndexError(f"label out of range [0, {c_tot})")      # the reference's scatter_ raises here (:381)
         self.last_stats = HeadStats()
+        use_cache = self.cache_weight_prep and (not self.training or self._w_prep.get("optimizer_current", False))
         loss = arcface_loss(x, weight, label, m_eff=m_eff, s_eff=s_eff, label_smoothing=label_smoothing,
                             easy_margin=self.easy_margin, hook=self._hook, stats=self.last_stats,
-                            engine=self.engine, compute_weight=w,
-                            weight_cache=self._w_prep if self.cache_weight_prep else None)
+                            engine=self.engine, compute_weight=w, class_offset=self._class_offset,
+                            num_classes_total=self._num_classes_total, group=self._group,
+                            weight_cache=self._w_prep if use_cache else None)
         if return_pred:
+            if self._group is not None:
+                from . import parallel
+                return loss, parallel.merge_row_argmax(self.last_stats.row_best, self.last_stats.row_argmax, self._group)[1]
             return loss, self.last_stats.row_argmax
         return loss
 
@@ -486,20 +548,40 @@ class ArcMarginProduct(nn.Module):
             m_eff, s_eff = self._step_schedule()
             hook = self._hook
             key = (B, float(label_smoothing), dtype, m_eff, s_eff, bool(self.easy_margin), self.engine, hook.enabled,
-                   hook.max_grad_norm, hook.phase, hook.epoch, self.weight.data_ptr(), id(optimizer))
+                   hook.max_grad_norm, hook.phase, hook.epoch, self.weight.data_ptr(), id(optimizer),
+                   self._class_offset, self._num_classes_total, id(self._group))
             g = cache.get("step")
             if g is None or cache.get("key") != key:
+                if g is not None:
+                    g.close()
                 g = GraphedHeadStep(self.weight, B, self.in_feats, dtype=dtype, m_eff=m_eff, s_eff=s_eff,
                                     label_smoothing=label_smoothing, easy_margin=self.easy_margin,
                                     hook=_Hook(hook.enabled, hook.max_grad_norm, hook.phase, hook.epoch),
-                                    engine=self.engine, **extra)
+                                    engine=self.engine, class_offset=self._class_offset,
+                                    num_classes_total=self._num_classes_total, group=self._group, **extra)
                 cache["step"], cache["key"] = g, key
             self.last_stats = g.stats
             step.dx = g.dx
             return g(x, y)
 
+        def close():
+            g = cache.pop("step", None)
+            cache.pop("key", None)
+            if g is not None:
+                g.close()
+
         step.dx = None
+        step.close = close
         return step
+
+    def release_graphs(self):
+        """Destroy every CUDA graph this head captured (graphed_step).  Call before
+        torch.distributed.destroy_process_group(): a captured NCCL all-reduce keeps the communicator busy."""
+        cache = self.__dict__.get("_graphed", {})
+        g = cache.pop("step", None)
+        cache.pop("key", None)
+        if g is not None:
+            g.close()
 
     def update_epoch(self, epoch):
         self.current_epoch = epoch

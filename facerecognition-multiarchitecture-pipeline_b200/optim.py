@@ -69,6 +69,10 @@ class HeadAdamW:
             w = self.weight.detach()
             head._w_prep["key"] = (w.data_ptr(), w._version, tuple(w.shape), w.dtype, True)
             head._w_prep["val"] = (self.w_hat, self.inv_norm)
+            # the head may use the cached operands in training mode too: this optimizer keeps them current, and
+            # re-derives them when the head's weights are replaced (load_state_dict -> _drop_weight_caches)
+            head._w_prep["optimizer_current"] = True
+            head._w_prep["static_refresh"] = self.refresh_operands
 
     # -- the step ------------------------------------------------------------------------------------------------------
     @torch.no_grad()

@@ -87,13 +87,36 @@ def sharded_gallery_topk(q: torch.Tensor, g_shard: torch.Tensor, k: int, thresh:
     return merge(idx_all, score_all, thresh, metric)
 
 
+INIT_BLOCK_ROWS = 4096
+
+
+def full_matrix_init_rows(lo: int, hi: int, out_feats: int, in_feats: int, seed: int = 0) -> torch.Tensor:
+    """Rows [lo, hi) of a [out_feats, in_feats] matrix initialised like the reference's FULL head
+    (``nn.init.xavier_normal_(weight, gain=sqrt 2)``, src/face_models.py:324: std = sqrt(2) * sqrt(2 / (C + D)) with
+    the TOTAL class count as fan-out), drawn block by block from generators seeded with (seed, block): the matrix is
+    the same whatever the number of ranks, no rank draws rows it does not own, and no two ranks hold duplicate rows."""
+    std = (2.0 ** 0.5) * (2.0 / (out_feats + in_feats)) ** 0.5
+    out = torch.empty(hi - lo, in_feats, dtype=torch.float32)
+    b = lo // INIT_BLOCK_ROWS
+    while b * INIT_BLOCK_ROWS < hi:
+        r0, r1 = b * INIT_BLOCK_ROWS, min((b + 1) * INIT_BLOCK_ROWS, out_feats)
+        g = torch.Generator().manual_seed(seed * 1_000_003 + b)
+        blk = torch.randn(r1 - r0, in_feats, generator=g) * std
+        s0, s1 = max(r0, lo), min(r1, hi)
+        out[s0 - lo:s1 - lo] = blk[s0 - r0:s1 - r0]
+        b += 1
+    return out
+
+
 class ShardedArcMarginProduct(torch.nn.Module):
     """Class-parallel ArcMarginProduct: rank r owns weight rows [lo_r, hi_r) of the [C,D] matrix.
-    Every rank sees the full batch of embeddings and labels (global class ids).  forward_loss runs
-    K1-K3 on the shard with one all-reduce each way.  state_dict interop with the reference layout:
-    gather_weight() / load_full_weight()."""
+    Every rank sees the full batch of embeddings and labels (global class ids).  ``forward_loss`` / ``graphed_step``
+    run K1-K3 on the shard with one all-reduce each way (``self.local`` is an ordinary ArcMarginProduct placed at
+    class offset lo_r).  Interop with the reference's checkpoint layout (``arcface.weight`` [C,512], strict load at
+    src/testing.py:124): ``gather_weight()`` / ``load_full_weight()`` / ``full_state_dict()``.
+    Call ``close()`` before ``torch.distributed.destroy_process_group()`` when graphed steps were used."""
 
-    def __init__(self, in_feats, out_feats, s=32.0, m=0.5, use_warm_up=True, easy_margin=False, group=None):
+    def __init__(self, in_feats, out_feats, s=32.0, m=0.5, use_warm_up=True, easy_margin=False, group=None, seed=0):
         super().__init__()
         from .head import ArcMarginProduct
         self.group = group
@@ -103,24 +126,28 @@ class ShardedArcMarginProduct(torch.nn.Module):
         self.lo, self.hi = shard_bounds(out_feats, self.world, self.rank)
         self.local = ArcMarginProduct(in_feats, self.hi - self.lo, s=s, m=m, use_warm_up=use_warm_up,
                                       easy_margin=easy_margin)
+        with torch.no_grad():                      # the shard of the FULL matrix's init, not an init of a small matrix
+            self.local.weight.copy_(full_matrix_init_rows(self.lo, self.hi, out_feats, in_feats, seed))
+        self.local._class_offset = self.lo
+        self.local._num_classes_total = out_feats
+        self.local._group = group
 
     def update_epoch(self, epoch):
         self.local.update_epoch(epoch)
 
+    @property
+    def weight(self):
+        return self.local.weight
+
     def forward_loss(self, input, label, label_smoothing=0.05, return_pred=False):
-        from .head import arcface_loss, HeadStats
-        hd = self.local
-        m_eff, s_eff = hd._step_schedule()
-        x, weight, w = hd._operands(input)
-        hd.last_stats = HeadStats()
-        loss = arcface_loss(x, weight, label, compute_weight=w, m_eff=m_eff, s_eff=s_eff, label_smoothing=label_smoothing,
-                            easy_margin=hd.easy_margin, class_offset=self.lo,
-                            num_classes_total=self.out_feats_total, group=self.group, hook=hd._hook,
-                            stats=hd.last_stats, engine=hd.engine)
-        if return_pred:
-            _, pred = merge_row_argmax(hd.last_stats.row_best, hd.last_stats.row_argmax, self.group)
-            return loss, pred
-        return loss
+        return self.local.forward_loss(input, label, label_smoothing, return_pred)
+
+    def graphed_step(self, B, label_smoothing=0.05, dtype=torch.bfloat16, optimizer=None):
+        """CUDA-graph form of forward_loss + backward for a fixed batch size, both all-reduces captured inside."""
+        return self.local.graphed_step(B, label_smoothing, dtype, optimizer)
+
+    def close(self):
+        self.local.release_graphs()
 
     def gather_weight(self) -> torch.Tensor:
         """Full [C,D] weight in the reference's layout (checkpoint save)."""
@@ -131,7 +158,14 @@ class ShardedArcMarginProduct(torch.nn.Module):
         dist.all_gather(parts, self.local.weight.detach().contiguous(), group=self.group)
         return torch.cat(parts, dim=0)
 
+    def full_state_dict(self) -> dict:
+        """state_dict of the equivalent unsharded reference module: {'weight': [C,D], 'u': [1]}."""
+        return {"weight": self.gather_weight(), "u": self.local.u.detach().clone()}
+
     def load_full_weight(self, weight: torch.Tensor):
         """Take this rank's rows of a reference-layout [C,D] weight (checkpoint load)."""
+        if tuple(weight.shape) != (self.out_feats_total, self.local.in_feats):
+            raise ValueError(f"expected a [{self.out_feats_total}, {self.local.in_feats}] weight, got {tuple(weight.shape)}")
         with torch.no_grad():
             self.local.weight.copy_(weight[self.lo:self.hi].to(self.local.weight.device))
+        self.local._drop_weight_caches()

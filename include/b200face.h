@@ -12,8 +12,15 @@
  *   - all data pointers are DEVICE pointers, row-major, borrowed for the call; the caller
  *     (PyTorch) owns every buffer including the workspace;
  *   - the last argument is the cudaStream_t to launch on (void* so no CUDA header is needed);
- *   - no allocation, no implicit synchronisation, no global mutable state;
- *   - return 0 on success, <0 on error; b200f_last_error() gives the thread-local message.
+ *   - no allocation, no implicit synchronisation; results depend only on the arguments.  The only process-wide
+ *     state is the set of performance tunables (b200f_set_tunable, tests / bench sweeps): they select between
+ *     kernel variants with identical results, a workspace queried under one setting is valid under every other
+ *     (sizes are the maximum over the variants), so a thread that changes one cannot invalidate another thread's
+ *     call (the Streamlit UI thread + webcam thread of src/app.py:331-335,639 may both be inside the library);
+ *   - return 0 on success, <0 on error; b200f_last_error() gives the thread-local message;
+ *   - a pipeline wait inside a tcgen05 kernel that expires (seconds; a bug, a stalled peer CTA) ABORTS the kernel
+ *     with a trap: the next CUDA call on the stream returns an error, nothing computed from partial accumulators
+ *     is ever handed back as a result.
  * Element types: B200F_F32 / B200F_BF16 run the head on the fp32 CUDA-core engine (fp32 products: the
  * 1e-5 bar); B200F_F16N (K1's normalised fp16 output, made from bf16 or fp32 inputs) runs it on the
  * tcgen05/TMEM/TMA engine.  All arithmetic accumulates in fp32.
@@ -214,7 +221,8 @@ int b200f_gallery_merge(const int64_t* idx_all, const float* score_all, int P, i
  *   for K-major (x_mn = 0: [rows,K] row-major) and MN-major (x_mn = 1: [K,rows] row-major) operands,
  *   fmt 0 = bf16 x bf16, 2 = fp16 x fp16 (1 = fp16 x bf16 faults: not a hardware format pair); with k_splits > 1 out is [k_splits, M, N] partial sums.
  *   Descriptor byte offsets < 0 select the defaults.
- * b200f_umma_timeout_flag: 1 if a bounded pipeline wait ever expired (synchronises; reset clears it).
+ * b200f_umma_timeout_flag: 1 if a bounded pipeline wait ever expired (synchronises; reset clears it).  The kernel
+ *   that raised it has trapped, so the context reports a launch failure as well; the flag only says why.
  */
 int b200f_umma_selftest(const void* a, const void* b, float* out, int M, int N, int K, int a_mn, int b_mn,
                         int fmt, int k_splits, int a_lbo, int a_sbo, int a_kstep, int b_lbo, int b_sbo,
@@ -229,9 +237,11 @@ int b200f_umma_set_pair(int pair);
 int b200f_umma_xw_probe(const void* x, const void* w, float* rowsum, int B, int C, int D, int pair, void* stream);
 /* Tunables for tests and bench sweeps: "pair" (1 | 2), "g_chunk_mb" (budget in MB of the fp16 logit-gradient buffer
  * per class chunk of the backward; default 112), "pdl" (0 | 1), "k3b_class_major" (0 | 1), "k3b_reverse" (0 | 1),
- * "xw_prefetch" (stages), "stage_events" (0 | 1).  "k3a_ablate" / "k3b_ablate" are measurement probes that skip memory
- * traffic and produce WRONG gradients: refused (-1) unless the environment variable B200F_ALLOW_PROBES is set.  Returns the previous value, -1 for an unknown name.  Workspace
- * sizes depend on them: query b200f_head_workspace_bytes again after a change. */
+ * "xw_prefetch" (stages), "stage_events" (0 | 1), "epi_groups" (1 | 2: epilogue warp groups of K2 / K3a, default 2).
+ * Returns the previous value, -1 for an unknown name.  Every setting computes the same results ("g_chunk_mb" changes the
+ * workspace size: query b200f_head_workspace_bytes again after changing it).  The measurement probes that skip memory
+ * traffic ("k3a_ablate" / "k3b_ablate", WRONG gradients) exist only in -DB200F_PROBES builds made by tools/: the
+ * shipped library answers -1 for them. */
 int b200f_set_tunable(const char* name, int value);
 /* With the tunable "stage_events" = 1 the head calls record a CUDA event pair around each of their GEMM kernels on
  * the caller's stream (eager launches only, never under graph capture).  b200f_stage_ms returns the duration in ms

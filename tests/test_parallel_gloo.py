@@ -129,3 +129,17 @@ def test_gallery_sharded_allgather_merge():
             assert np.array_equal(idx, gi)                    # incl. the planted duplicate rows 17/150
             np.testing.assert_allclose(score, gs, rtol=1e-6)
             assert np.array_equal(acc, ga)
+
+
+def test_full_matrix_init_is_world_size_independent():
+    """ShardedArcMarginProduct draws its rows from ONE full-matrix xavier_normal(gain sqrt 2) distribution
+    (src/face_models.py:324): std uses the TOTAL class count, shards of any partition tile the same matrix."""
+    from b200face import parallel
+    C, D = 10_001, 64
+    full = parallel.full_matrix_init_rows(0, C, C, D, seed=3)
+    assert float(full.std()) == pytest.approx((2.0 ** 0.5) * (2.0 / (C + D)) ** 0.5, rel=0.02)
+    for world in (2, 3, 8):
+        parts = [parallel.full_matrix_init_rows(*parallel.shard_bounds(C, world, r), C, D, seed=3) for r in range(world)]
+        assert torch.equal(torch.cat(parts), full)
+    assert not torch.equal(full[:4096], full[4096:8192])              # blocks are not copies of each other
+    assert not torch.equal(full, parallel.full_matrix_init_rows(0, C, C, D, seed=4))
