@@ -137,9 +137,9 @@ template <class Epi> struct xw_epi_groups<Epi, decltype((void)Epi::kEpiGroups)> 
 template <class Epi, class = void> struct xw_slice_cols { static constexpr int value = 32; };
 template <class Epi> struct xw_slice_cols<Epi, decltype((void)Epi::kSliceCols)> { static constexpr int value = Epi::kSliceCols; };
 template <class Epi> __host__ __device__ constexpr int xw_threads() { return 64 + 32 * XW_EPI_WARPS * xw_epi_groups<Epi>::value; }
-// registers per thread: 1 CTA per SM either way (shared memory).  10 warps x 168 and 18 warps x 112 both fit the 64 K file;
-// __launch_bounds__(576, 1) alone makes ptxas stop at 96.
-template <class Epi> __host__ __device__ constexpr int xw_maxnreg() { return xw_epi_groups<Epi>::value == 1 ? 168 : 112; }
+// registers per thread: 1 CTA per SM either way (shared memory).  The register file is handed out per FOUR warps:
+// 10 warps count as 12 (168 registers), 18 warps as 20 (96 registers; 112 is refused at launch: "too many resources").
+template <class Epi> __host__ __device__ constexpr int xw_maxnreg() { return xw_epi_groups<Epi>::value == 1 ? 168 : 96; }
 
 struct XwItem {                         // what an epilogue thread knows about its work item
   int item, chunk, group;

@@ -275,19 +275,17 @@ struct XwBwdGTT {
     // explicit ld.shared: through the generic pointer these compile to LD.E, which queues in the global load/store
     // path behind this kernel's own G^T stores
     const uint32_t tb_s = smem_u32(scratch + col0);
-    float bb[SC];
-#pragma unroll
-    for (int j = 0; j < SC; j += 4)
-      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                   : "=f"(bb[j]), "=f"(bb[j + 1]), "=f"(bb[j + 2]), "=f"(bb[j + 3]) : "r"(tb_s + j * 4));
     float g[SC];
     float am4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int j = 0; j < SC; j += 4) {
+      float bb[4];                                             // -lse_b log2 e of the four batch rows (columns)
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(bb[0]), "=f"(bb[1]), "=f"(bb[2]), "=f"(bb[3]) : "r"(tb_s + j * 4));
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const float tt = v[j + u];
-        g[j + u] = fmaf(gs, ex2_approx(fmaf(tt, a, bb[j + u])), -gq);
+        g[j + u] = fmaf(gs, ex2_approx(fmaf(tt, a, bb[u])), -gq);
         asm("max.NaN.xorsign.abs.f32 %0, %0, %1;" : "+f"(am4[u]) : "f"(tt));
       }
     }
@@ -322,7 +320,7 @@ struct XwBwdGTT {
         float z = tv * s_eff;
         if (!isfinite(z)) { z = 0.f; f = 0.f; }
         if (!(cosv >= lo && cosv <= hi)) f = 0.f;
-        const float pr = exp2f(fmaf(z, LOG2E, bb[j]));
+        const float pr = exp2f(fmaf(z, LOG2E, scratch[col0 + j]));
         const float q = is_t ? (1.0f - ep.ls_eps) + q_off : q_off;
         g[j] = fminf(fmaxf(gs * (pr - q) * f, -65504.f), 65504.f);
         const float t = g[j] * v[j];
