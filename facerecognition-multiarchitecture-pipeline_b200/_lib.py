@@ -26,6 +26,11 @@ class LibraryMissingError(RuntimeError):
     pass
 
 
+class HookCfg(Structure):
+    """struct b200f_hook_cfg"""
+    _fields_ = [("enabled", c_int32), ("max_grad_norm", c_float), ("phase", c_int32), ("epoch", c_int32)]
+
+
 class HeadCfg(Structure):
     """struct b200f_head_cfg"""
     _fields_ = [("m_eff", c_float), ("s_eff", c_float), ("label_smoothing", c_float),
@@ -60,7 +65,19 @@ PROTOTYPES = {
                                   c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, POINTER(HeadCfg),
                                   c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "b200f_l2norm_bwd": (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p, c_int64, c_int, c_void_p,
-                                 c_void_p]),
+                                 c_void_p, c_void_p]),
+    "b200f_l2norm_rows_pair": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                                       c_int, c_int, c_float, c_int, c_float, c_void_p]),
+    "b200f_arcface_fwd_loss": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                       c_int64, c_int64, c_int64, c_int, POINTER(HeadCfg), POINTER(HookCfg),
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "b200f_arcface_loss_hook": (c_int, [c_void_p, c_int64, POINTER(HeadCfg), POINTER(HookCfg), c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_void_p]),
+    "b200f_arcface_bwd_dx": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, POINTER(HeadCfg),
+                                     c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
+                                     c_void_p]),
     "b200f_gallery_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int, c_int, c_int]),
     "b200f_gallery_topk": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int64,
                                    c_int64, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p,

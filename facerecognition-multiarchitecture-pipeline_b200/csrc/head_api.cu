@@ -2,6 +2,7 @@
 // carving and engine dispatch.  No allocation, no synchronisation.  Declared in include/b200face.h.
 #include "common.cuh"
 #include "head_simt.cuh"
+#include "rowops.cuh"
 #include "umma_api.cuh"
 
 namespace b200f {
@@ -159,32 +160,101 @@ static int check_head_args(const char* who, const void* x, const void* w, int dt
   return B200F_OK;
 }
 
+static int arcface_fwd_impl(const char* who, const void* x, const void* w, int dtype, const float* inv_nx, const float* inv_nw,
+                            const int64_t* label, int64_t B, int64_t C_local, int64_t class_offset, int D,
+                            const b200f_head_cfg* cfg, float* row_stats, float* row_best, int64_t* row_argmax,
+                            float* cos_minmax, int32_t* nan_flag, float* logits_or_null, int64_t ld_logits,
+                            const umma::HeadFinal* fin, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_head_args(who, x, w, dtype, inv_nx, inv_nw, label, B, C_local, D, cfg);
+  if (rc) return rc;
+  if (!row_stats || !nan_flag) return fail(B200F_ERR_ARG, "%s: null output", who);
+  if (logits_or_null && ld_logits < C_local) return fail(B200F_ERR_ARG, "%s: ld_logits < C_local", who);
+  const size_t need = b200f_head_workspace_bytes(B, C_local, D, dtype, cfg->engine);
+  if (!workspace || workspace_bytes < need)
+    return fail(B200F_ERR_WORKSPACE, "%s: workspace %zu < %zu", who, workspace_bytes, need);
+  cudaStream_t st = as_stream(stream);
+  if (dtype == B200F_F16N) {
+    if (logits_or_null) return fail(B200F_ERR_UNSUPPORTED, "%s: the tcgen05 engine never stores logits", who);
+    return umma::head_fwd(x, w, label, B, C_local, class_offset, D, cfg, row_stats, row_best, row_argmax, cos_minmax,
+                          nan_flag, fin, static_cast<char*>(workspace), workspace_bytes, st);
+  }
+  const HeadPlan pl = plan_head(B, C_local, D);
+  if (dtype == B200F_F32)
+    rc = head_fwd_simt<float>(x, w, inv_nx, inv_nw, label, B, C_local, class_offset, D, cfg, row_stats, row_best,
+                              row_argmax, cos_minmax, nan_flag, logits_or_null, ld_logits,
+                              static_cast<char*>(workspace), pl, st);
+  else
+    rc = head_fwd_simt<__nv_bfloat16>(x, w, inv_nx, inv_nw, label, B, C_local, class_offset, D, cfg, row_stats,
+                                      row_best, row_argmax, cos_minmax, nan_flag, logits_or_null, ld_logits,
+                                      static_cast<char*>(workspace), pl, st);
+  if (rc || fin == nullptr) return rc;
+  launch_pdl(rowops::loss_kernel, dim3(1), dim3(1024), 0, st, (const float*)row_stats, B, cfg->s_eff, cfg->label_smoothing,
+             (double)cfg->num_classes_total, fin->lse, fin->loss, fin->pq_norm2,
+             rowops::HookCfg{fin->hook_enabled, fin->max_grad_norm, fin->phase, fin->epoch}, fin->out4);
+  B200F_LAUNCH_OK("loss_kernel");
+  return B200F_OK;
+}
+
+static int arcface_bwd_impl(const char* who, const void* x, const void* w, int dtype, const float* inv_nx, const float* inv_nw,
+                            const int64_t* label, const float* lse, const float* grad_scale,
+                            const float* dlogits_or_null, int64_t ld_dlogits, int64_t B, int64_t C_local,
+                            int64_t class_offset, int D, const b200f_head_cfg* cfg, float* dxhat, float* dw,
+                            const umma::HeadDx* hdx, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_head_args(who, x, w, dtype, inv_nx, inv_nw, label, B, C_local, D, cfg);
+  if (rc) return rc;
+  if (!lse || !grad_scale || !dxhat || !dw) return fail(B200F_ERR_ARG, "%s: null pointer", who);
+  const size_t need = b200f_head_workspace_bytes(B, C_local, D, dtype, cfg->engine);
+  if (!workspace || workspace_bytes < need)
+    return fail(B200F_ERR_WORKSPACE, "%s: workspace %zu < %zu", who, workspace_bytes, need);
+  cudaStream_t st = as_stream(stream);
+  if (dlogits_or_null && ld_dlogits < C_local) return fail(B200F_ERR_ARG, "%s: ld_dlogits < C_local", who);
+  if (dtype == B200F_F16N) {
+    if (dlogits_or_null) return fail(B200F_ERR_UNSUPPORTED, "%s: the tcgen05 engine has no dlogits path", who);
+    if (!inv_nw) return fail(B200F_ERR_ARG, "%s: inv_nw required", who);
+    return umma::head_bwd(x, w, inv_nw, label, lse, grad_scale, B, C_local, class_offset, D, cfg, dxhat, dw, hdx,
+                          static_cast<char*>(workspace), workspace_bytes, st);
+  }
+  const HeadPlan pl = plan_head(B, C_local, D);
+  if (dtype == B200F_F32)
+    rc = head_bwd_simt<float>(x, w, inv_nx, inv_nw, label, lse, grad_scale, dlogits_or_null, ld_dlogits, B,
+                              C_local, class_offset, D, cfg, dxhat, dw, static_cast<char*>(workspace), pl, st);
+  else
+    rc = head_bwd_simt<__nv_bfloat16>(x, w, inv_nx, inv_nw, label, lse, grad_scale, dlogits_or_null, ld_dlogits,
+                                      B, C_local, class_offset, D, cfg, dxhat, dw,
+                                      static_cast<char*>(workspace), pl, st);
+  if (rc || hdx == nullptr || hdx->dx == nullptr) return rc;
+  // CUDA-core engine: its operands ARE the raw rows
+  __nv_bfloat16* lowp = static_cast<__nv_bfloat16*>(hdx->dx_bf16);
+  if (dtype == B200F_F32)
+    rowops::launch_l2norm_bwd<float, false>(static_cast<const float*>(x), 1.f, inv_nx, dxhat, B, D, hdx->dx, st, lowp);
+  else
+    rowops::launch_l2norm_bwd<__nv_bfloat16, false>(static_cast<const __nv_bfloat16*>(x), 1.f, inv_nx, dxhat, B, D, hdx->dx, st, lowp);
+  B200F_LAUNCH_OK("l2norm_bwd kernel (dx)");
+  return B200F_OK;
+}
+
 int b200f_arcface_fwd(const void* x, const void* w, int dtype, const float* inv_nx, const float* inv_nw,
                       const int64_t* label, int64_t B, int64_t C_local, int64_t class_offset, int D,
                       const b200f_head_cfg* cfg, float* row_stats, float* row_best, int64_t* row_argmax,
                       float* cos_minmax, int32_t* nan_flag, float* logits_or_null, int64_t ld_logits,
                       void* workspace, size_t workspace_bytes, void* stream) {
-  int rc = check_head_args("arcface_fwd", x, w, dtype, inv_nx, inv_nw, label, B, C_local, D, cfg);
-  if (rc) return rc;
-  if (!row_stats || !nan_flag) return fail(B200F_ERR_ARG, "arcface_fwd: null output");
-  if (logits_or_null && ld_logits < C_local) return fail(B200F_ERR_ARG, "arcface_fwd: ld_logits < C_local");
-  const size_t need = b200f_head_workspace_bytes(B, C_local, D, dtype, cfg->engine);
-  if (!workspace || workspace_bytes < need)
-    return fail(B200F_ERR_WORKSPACE, "arcface_fwd: workspace %zu < %zu", workspace_bytes, need);
-  cudaStream_t st = as_stream(stream);
-  if (dtype == B200F_F16N) {
-    if (logits_or_null) return fail(B200F_ERR_UNSUPPORTED, "arcface_fwd: the tcgen05 engine never stores logits");
-    return umma::head_fwd(x, w, label, B, C_local, class_offset, D, cfg, row_stats, row_best, row_argmax, cos_minmax,
-                          nan_flag, static_cast<char*>(workspace), workspace_bytes, st);
-  }
-  const HeadPlan pl = plan_head(B, C_local, D);
-  if (dtype == B200F_F32)
-    return head_fwd_simt<float>(x, w, inv_nx, inv_nw, label, B, C_local, class_offset, D, cfg, row_stats, row_best,
-                                row_argmax, cos_minmax, nan_flag, logits_or_null, ld_logits,
-                                static_cast<char*>(workspace), pl, st);
-  return head_fwd_simt<__nv_bfloat16>(x, w, inv_nx, inv_nw, label, B, C_local, class_offset, D, cfg, row_stats,
-                                      row_best, row_argmax, cos_minmax, nan_flag, logits_or_null, ld_logits,
-                                      static_cast<char*>(workspace), pl, st);
+  return arcface_fwd_impl("arcface_fwd", x, w, dtype, inv_nx, inv_nw, label, B, C_local, class_offset, D, cfg, row_stats,
+                          row_best, row_argmax, cos_minmax, nan_flag, logits_or_null, ld_logits, nullptr, workspace,
+                          workspace_bytes, stream);
+}
+
+int b200f_arcface_fwd_loss(const void* x, const void* w, int dtype, const float* inv_nx, const float* inv_nw,
+                           const int64_t* label, int64_t B, int64_t C_local, int64_t class_offset, int D,
+                           const b200f_head_cfg* cfg, const b200f_hook_cfg* hook, float* row_stats, float* row_best,
+                           int64_t* row_argmax, float* cos_minmax, int32_t* nan_flag, float* lse, float* loss,
+                           float* pq_norm2, float* out4, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!hook || !lse || !loss || !pq_norm2 || !out4) return fail(B200F_ERR_ARG, "arcface_fwd_loss: null pointer");
+  if (cfg && C_local != cfg->num_classes_total)
+    return fail(B200F_ERR_ARG, "arcface_fwd_loss: a class shard needs the cross-shard sum first (b200f_arcface_fwd, "
+                               "all-reduce, b200f_arcface_loss_hook)");
+  const umma::HeadFinal fin{lse, loss, pq_norm2, hook->enabled, hook->max_grad_norm, hook->phase, hook->epoch, out4};
+  return arcface_fwd_impl("arcface_fwd_loss", x, w, dtype, inv_nx, inv_nw, label, B, C_local, class_offset, D, cfg, row_stats,
+                          row_best, row_argmax, cos_minmax, nan_flag, nullptr, 0, &fin, workspace, workspace_bytes, stream);
 }
 
 int b200f_arcface_bwd(const void* x, const void* w, int dtype, const float* inv_nx, const float* inv_nw,
@@ -192,27 +262,21 @@ int b200f_arcface_bwd(const void* x, const void* w, int dtype, const float* inv_
                       const float* dlogits_or_null, int64_t ld_dlogits, int64_t B,
                       int64_t C_local, int64_t class_offset, int D, const b200f_head_cfg* cfg, float* dxhat,
                       float* dw, void* workspace, size_t workspace_bytes, void* stream) {
-  int rc = check_head_args("arcface_bwd", x, w, dtype, inv_nx, inv_nw, label, B, C_local, D, cfg);
-  if (rc) return rc;
-  if (!lse || !grad_scale || !dxhat || !dw) return fail(B200F_ERR_ARG, "arcface_bwd: null pointer");
-  const size_t need = b200f_head_workspace_bytes(B, C_local, D, dtype, cfg->engine);
-  if (!workspace || workspace_bytes < need)
-    return fail(B200F_ERR_WORKSPACE, "arcface_bwd: workspace %zu < %zu", workspace_bytes, need);
-  cudaStream_t st = as_stream(stream);
-  if (dlogits_or_null && ld_dlogits < C_local) return fail(B200F_ERR_ARG, "arcface_bwd: ld_dlogits < C_local");
-  if (dtype == B200F_F16N) {
-    if (dlogits_or_null) return fail(B200F_ERR_UNSUPPORTED, "arcface_bwd: the tcgen05 engine has no dlogits path");
-    if (!inv_nw) return fail(B200F_ERR_ARG, "arcface_bwd: inv_nw required");
-    return umma::head_bwd(x, w, inv_nw, label, lse, grad_scale, B, C_local, class_offset, D, cfg, dxhat, dw,
-                          static_cast<char*>(workspace), workspace_bytes, st);
-  }
-  const HeadPlan pl = plan_head(B, C_local, D);
-  if (dtype == B200F_F32)
-    return head_bwd_simt<float>(x, w, inv_nx, inv_nw, label, lse, grad_scale, dlogits_or_null, ld_dlogits, B,
-                                C_local, class_offset, D, cfg, dxhat, dw, static_cast<char*>(workspace), pl, st);
-  return head_bwd_simt<__nv_bfloat16>(x, w, inv_nx, inv_nw, label, lse, grad_scale, dlogits_or_null, ld_dlogits,
-                                      B, C_local, class_offset, D, cfg, dxhat, dw,
-                                      static_cast<char*>(workspace), pl, st);
+  return arcface_bwd_impl("arcface_bwd", x, w, dtype, inv_nx, inv_nw, label, lse, grad_scale, dlogits_or_null, ld_dlogits, B,
+                          C_local, class_offset, D, cfg, dxhat, dw, nullptr, workspace, workspace_bytes, stream);
+}
+
+int b200f_arcface_bwd_dx(const void* x, const void* w, int dtype, const float* inv_nx, const float* inv_nw,
+                         const int64_t* label, const float* lse, const float* grad_scale,
+                         const float* dlogits_or_null, int64_t ld_dlogits, int64_t B,
+                         int64_t C_local, int64_t class_offset, int D, const b200f_head_cfg* cfg, float* dxhat,
+                         float* dw, const void* x_raw_or_null, int x_raw_dtype, float* dx, void* dx_bf16_or_null,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  if (!dx || !inv_nx) return fail(B200F_ERR_ARG, "arcface_bwd_dx: dx and inv_nx are required");
+  if (x_raw_or_null && !dtype_ok(x_raw_dtype)) return fail(B200F_ERR_ARG, "arcface_bwd_dx: bad x_raw dtype %d", x_raw_dtype);
+  const umma::HeadDx hdx{x_raw_or_null, x_raw_dtype, inv_nx, dx, dx_bf16_or_null};
+  return arcface_bwd_impl("arcface_bwd_dx", x, w, dtype, inv_nx, inv_nw, label, lse, grad_scale, dlogits_or_null, ld_dlogits, B,
+                          C_local, class_offset, D, cfg, dxhat, dw, &hdx, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

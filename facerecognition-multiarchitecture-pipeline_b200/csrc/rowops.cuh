@@ -149,13 +149,11 @@ l2norm_rows_vec_kernel(const TI* __restrict__ in, int64_t rows, int dim, float e
 // K1, 512-wide 16-bit rows (the head's shape): each lane owns 32 contiguous bytes of a row -- ONE 256-bit load and
 // ONE 256-bit store per lane and row (full 32 B sectors), 4 rows per warp in flight.
 template <typename TI, typename TO>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-l2norm_rows_512x16_kernel(const TI* __restrict__ in, int64_t rows, float eps, float out_scale,
-                          float* __restrict__ inv_norm, TO* __restrict__ out) {
-  pdl_trigger(); pdl_wait();
+__device__ __forceinline__ void l2norm_rows_512x16_body(const TI* __restrict__ in, int64_t rows, float eps, float out_scale,
+                                                        float* __restrict__ inv_norm, TO* __restrict__ out, int64_t block) {
   static_assert(sizeof(TI) == 2 && sizeof(TO) == 2, "16-bit rows only");
   const int lane = threadIdx.x & 31;
-  const int64_t row0 = ((int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5)) * ROWS_PER_WARP;
+  const int64_t row0 = (block * WARPS_PER_BLOCK + (threadIdx.x >> 5)) * ROWS_PER_WARP;
   if (row0 >= rows) return;
   uint32_t raw[ROWS_PER_WARP][8];
 #pragma unroll
@@ -202,6 +200,25 @@ l2norm_rows_512x16_kernel(const TI* __restrict__ in, int64_t rows, float eps, fl
     }
   }
 }
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+l2norm_rows_512x16_kernel(const TI* __restrict__ in, int64_t rows, float eps, float out_scale,
+                          float* __restrict__ inv_norm, TO* __restrict__ out) {
+  pdl_trigger(); pdl_wait();
+  l2norm_rows_512x16_body<TI, TO>(in, rows, eps, out_scale, inv_norm, out, (int64_t)blockIdx.x);
+}
+// Two row sets in ONE launch (the head's K1 over the batch rows and over the class weights: the 16-block launch for
+// x otherwise costs a launch latency of its own in front of the 3125-block launch for W).  Blocks [0, blocks0) take
+// set 0, the rest set 1.
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+l2norm_rows_512x16_pair_kernel(const TI* __restrict__ in0, int64_t rows0, float* __restrict__ inv0, TO* __restrict__ out0,
+                               int blocks0, const TI* __restrict__ in1, int64_t rows1, float* __restrict__ inv1,
+                               TO* __restrict__ out1, float eps, float out_scale) {
+  pdl_trigger(); pdl_wait();
+  if ((int)blockIdx.x < blocks0) l2norm_rows_512x16_body<TI, TO>(in0, rows0, eps, out_scale, inv0, out0, (int64_t)blockIdx.x);
+  else l2norm_rows_512x16_body<TI, TO>(in1, rows1, eps, out_scale, inv1, out1, (int64_t)blockIdx.x - blocks0);
+}
 
 // K1, generic path (any dim / alignment): one warp per row, scalar accesses.
 template <typename TI, typename TO>
@@ -229,7 +246,7 @@ l2norm_rows_generic_kernel(const TI* __restrict__ in, int64_t rows, int dim, flo
 template <typename T, bool PRENORM, int VPL>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 l2norm_bwd_vec_kernel(const T* __restrict__ v, float v_scale, const float* __restrict__ inv_norm, const float* dvhat,
-                      int64_t rows, int dim, float* dv) {
+                      int64_t rows, int dim, float* dv, __nv_bfloat16* __restrict__ dv_bf16) {
   pdl_trigger(); pdl_wait();
   constexpr int N = Vec16<T>::N;                // 8 (16-bit) or 4 (fp32) elements per 16-byte vector of v
   const int lane = threadIdx.x & 31;
@@ -265,10 +282,13 @@ l2norm_bwd_vec_kernel(const T* __restrict__ v, float v_scale, const float* __res
     const int k = lane + it * 32;
     if (k < nvec) {
 #pragma unroll
-      for (int e = 0; e < N; e += 4)
-        *reinterpret_cast<float4*>(dv + row * dim + k * N + e) =
-            make_float4(inv * (gv[it][e] - xv[it][e] * dot), inv * (gv[it][e + 1] - xv[it][e + 1] * dot),
-                        inv * (gv[it][e + 2] - xv[it][e + 2] * dot), inv * (gv[it][e + 3] - xv[it][e + 3] * dot));
+      for (int e = 0; e < N; e += 4) {
+        const float4 o = make_float4(inv * (gv[it][e] - xv[it][e] * dot), inv * (gv[it][e + 1] - xv[it][e + 1] * dot),
+                                     inv * (gv[it][e + 2] - xv[it][e + 2] * dot), inv * (gv[it][e + 3] - xv[it][e + 3] * dot));
+        *reinterpret_cast<float4*>(dv + row * dim + k * N + e) = o;
+        if (dv_bf16 != nullptr)                               // the autograd cast of dL/dx to a bf16 input's dtype, fused
+          *reinterpret_cast<uint2*>(dv_bf16 + row * dim + k * N + e) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+      }
     }
   }
 }
@@ -276,7 +296,7 @@ l2norm_bwd_vec_kernel(const T* __restrict__ v, float v_scale, const float* __res
 template <typename T, bool PRENORM>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 l2norm_bwd_generic_kernel(const T* __restrict__ v, float v_scale, const float* __restrict__ inv_norm,
-                          const float* dvhat, int64_t rows, int dim, float* dv) {
+                          const float* dvhat, int64_t rows, int dim, float* dv, __nv_bfloat16* __restrict__ dv_bf16) {
   pdl_trigger(); pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
@@ -289,7 +309,11 @@ l2norm_bwd_generic_kernel(const T* __restrict__ v, float v_scale, const float* _
   for (int d = lane; d < dim; d += 32) dot = fmaf(to_f32<T>(src[d]) * vmul, g[d], dot);
   dot = warp_sum(dot);
   float* o = dv + row * dim;
-  for (int d = lane; d < dim; d += 32) o[d] = inv * (g[d] - to_f32<T>(src[d]) * vmul * dot);
+  for (int d = lane; d < dim; d += 32) {
+    const float val = inv * (g[d] - to_f32<T>(src[d]) * vmul * dot);
+    o[d] = val;
+    if (dv_bf16 != nullptr) dv_bf16[row * dim + d] = __float2bfloat16_rn(val);
+  }
 }
 
 // Host-side dispatch helpers (used by runtime.cu and by the tcgen05 engine).
@@ -320,19 +344,19 @@ static inline void launch_l2norm_rows(const TI* in, int64_t rows, int dim, float
 
 template <typename T, bool PRENORM>
 static inline void launch_l2norm_bwd(const T* v, float v_scale, const float* inv_norm, const float* dvhat, int64_t rows,
-                                     int dim, float* dv, cudaStream_t st) {
+                                     int dim, float* dv, cudaStream_t st, __nv_bfloat16* dv_bf16 = nullptr) {
   constexpr int N = Vec16<T>::N;
   const bool vec = (dim % N == 0) && (dim % 4 == 0) && (reinterpret_cast<uintptr_t>(v) % 16 == 0) &&
                    (reinterpret_cast<uintptr_t>(dvhat) % 16 == 0) && (reinterpret_cast<uintptr_t>(dv) % 16 == 0) &&
-                   (dim <= 32 * N * 4);
+                   (reinterpret_cast<uintptr_t>(dv_bf16) % 8 == 0) && (dim <= 32 * N * 4);
   const unsigned grid = (unsigned)ceil_div(rows, WARPS_PER_BLOCK);
   if (vec) {
     const int nvec = dim / N;
-    if (nvec <= 32) launch_pdl(l2norm_bwd_vec_kernel<T, PRENORM, 1>, dim3(grid), dim3(WARPS_PER_BLOCK * 32), 0, st, v, v_scale, inv_norm, dvhat, rows, dim, dv);
-    else if (nvec <= 64) launch_pdl(l2norm_bwd_vec_kernel<T, PRENORM, 2>, dim3(grid), dim3(WARPS_PER_BLOCK * 32), 0, st, v, v_scale, inv_norm, dvhat, rows, dim, dv);
-    else launch_pdl(l2norm_bwd_vec_kernel<T, PRENORM, 4>, dim3(grid), dim3(WARPS_PER_BLOCK * 32), 0, st, v, v_scale, inv_norm, dvhat, rows, dim, dv);
+    if (nvec <= 32) launch_pdl(l2norm_bwd_vec_kernel<T, PRENORM, 1>, dim3(grid), dim3(WARPS_PER_BLOCK * 32), 0, st, v, v_scale, inv_norm, dvhat, rows, dim, dv, dv_bf16);
+    else if (nvec <= 64) launch_pdl(l2norm_bwd_vec_kernel<T, PRENORM, 2>, dim3(grid), dim3(WARPS_PER_BLOCK * 32), 0, st, v, v_scale, inv_norm, dvhat, rows, dim, dv, dv_bf16);
+    else launch_pdl(l2norm_bwd_vec_kernel<T, PRENORM, 4>, dim3(grid), dim3(WARPS_PER_BLOCK * 32), 0, st, v, v_scale, inv_norm, dvhat, rows, dim, dv, dv_bf16);
   } else {
-    launch_pdl(l2norm_bwd_generic_kernel<T, PRENORM>, dim3(grid), dim3(WARPS_PER_BLOCK * 32), 0, st, v, v_scale, inv_norm, dvhat, rows, dim, dv);
+    launch_pdl(l2norm_bwd_generic_kernel<T, PRENORM>, dim3(grid), dim3(WARPS_PER_BLOCK * 32), 0, st, v, v_scale, inv_norm, dvhat, rows, dim, dv, dv_bf16);
   }
 }
 
@@ -436,30 +460,52 @@ static inline bool launch_adamw_rows(float* w, const float* dw, float* m, float*
   return true;
 }
 
-// Single block.  row_stats [B,4] -> lse[B], loss (mean), pq_norm2.  Arithmetic in double: only B
-// rows, and sum_j (p-q)^2 cancels badly in fp32 once the target probability approaches 1.
-static __global__ void __launch_bounds__(1024)
-loss_kernel(const float* __restrict__ row_stats, int64_t B, float s_eff, float ls_eps,
-            double C_total, float* __restrict__ lse_out, float* __restrict__ loss_out,
-            float* __restrict__ pq_norm2_out) {
-  pdl_trigger(); pdl_wait();
-  __shared__ double sh_loss[32], sh_pq[32];
+// src/face_models.py:538-567 on scalars: out4 = {grad_scale, n, kappa, g_scale}.
+struct HookCfg { int enabled; float max_grad_norm; int phase, epoch; };
+__device__ __forceinline__ void hook_scalars(double pq_norm2, double up, double B, float s_eff, const HookCfg& h,
+                                             float* __restrict__ out4) {
+  const double base = (double)s_eff / B;
+  const double n = fabs(up) * base * sqrt(pq_norm2);
+  double kappa = 1.0;
+  if (h.enabled) {
+    double thr = (double)h.max_grad_norm;
+    if (h.phase == 1) thr = fmin(0.5, (double)h.max_grad_norm);
+    if (h.epoch < 10) thr = fmin(thr, 0.5 + 0.05 * (double)h.epoch);
+    if (n > 3.0) thr = fmin(thr, 0.5);
+    if (n > thr) kappa = thr / (n + 1e-8);
+  }
+  const double gs = up * kappa * base;
+  out4[0] = (float)gs;
+  out4[1] = (float)n;
+  out4[2] = (float)kappa;
+  // power of two that puts |grad_scale| * g_scale in (512, 1024]: the fp16 range centring of the
+  // tcgen05 engine's logit-gradient buffer (exact to undo)
+  out4[3] = (gs != 0.0 && isfinite(gs)) ? (float)exp2(10.0 - ceil(log2(fabs(gs)))) : 1.0f;
+}
+
+// One block: row_stats [B,4] -> lse[B], loss (mean), pq_norm2 and (hook_out4 != NULL) the hook scalars for an
+// upstream gradient of 1.  Arithmetic in double: only B rows, and sum_j (p-q)^2 cancels badly in fp32 once the
+// target probability approaches 1.  Reads bypass L1 (__ldcg): the fused caller runs this in the LAST block of a grid
+// whose other blocks wrote row_stats.  Fixed-order tree: bitwise reproducible.
+__device__ __forceinline__ void loss_block(const float* row_stats, int64_t B, float s_eff, float ls_eps, double C_total,
+                                           float* __restrict__ lse_out, float* __restrict__ loss_out,
+                                           float* __restrict__ pq_norm2_out, const HookCfg* hook, float* __restrict__ hook_out4,
+                                           double* sh_loss, double* sh_pq) {
   double loss = 0.0, pq = 0.0;
   const double eps = (double)ls_eps;
   const double q_off = eps / C_total;
   const double q_sq = (1.0 - eps + q_off) * (1.0 - eps + q_off) + (C_total - 1.0) * q_off * q_off;
   for (int64_t r = threadIdx.x; r < B; r += blockDim.x) {
-    const float* st = row_stats + r * B200F_STAT_COLS;
-    const double se = (double)st[B200F_STAT_SUMEXP];
+    const float4 st4 = __ldcg(reinterpret_cast<const float4*>(row_stats + r * B200F_STAT_COLS));
+    const double se = (double)st4.x;                          // B200F_STAT_SUMEXP, _SUMEXP2, _ZTARGET, _SUMZ
     const double lse = (double)s_eff + log(se);
-    const double zt = (double)st[B200F_STAT_ZTARGET];
-    loss += lse - (1.0 - eps) * zt - q_off * (double)st[B200F_STAT_SUMZ];
+    const double zt = (double)st4.z;
+    loss += lse - (1.0 - eps) * zt - q_off * (double)st4.w;
     const double pt = exp(zt - lse);
-    const double p_sq = (double)st[B200F_STAT_SUMEXP2] / (se * se);
+    const double p_sq = (double)st4.y / (se * se);
     pq += p_sq - 2.0 * ((1.0 - eps) * pt + q_off) + q_sq;
     if (lse_out != nullptr) lse_out[r] = (float)lse;
   }
-  // fixed-order tree: bitwise reproducible
   for (int o = 16; o > 0; o >>= 1) {
     loss += __shfl_down_sync(0xffffffffu, loss, o);
     pq += __shfl_down_sync(0xffffffffu, pq, o);
@@ -469,34 +515,96 @@ loss_kernel(const float* __restrict__ row_stats, int64_t B, float s_eff, float l
   if (threadIdx.x == 0) {
     double l = 0.0, q = 0.0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { l += sh_loss[w]; q += sh_pq[w]; }
+    q = fmax(q, 0.0);
     if (loss_out != nullptr) *loss_out = (float)(l / (double)B);
-    if (pq_norm2_out != nullptr) *pq_norm2_out = (float)fmax(q, 0.0);
+    if (pq_norm2_out != nullptr) *pq_norm2_out = (float)q;
+    if (hook_out4 != nullptr) hook_scalars((double)(float)q, 1.0, (double)B, s_eff, *hook, hook_out4);
   }
 }
+static_assert(B200F_STAT_SUMEXP == 0 && B200F_STAT_SUMEXP2 == 1 && B200F_STAT_ZTARGET == 2 && B200F_STAT_SUMZ == 3 &&
+              B200F_STAT_COLS == 4, "loss_block reads a row of statistics as one float4");
 
-// src/face_models.py:538-567 on device scalars.
+static __global__ void __launch_bounds__(1024)
+loss_kernel(const float* __restrict__ row_stats, int64_t B, float s_eff, float ls_eps,
+            double C_total, float* __restrict__ lse_out, float* __restrict__ loss_out,
+            float* __restrict__ pq_norm2_out, HookCfg hook, float* __restrict__ hook_out4) {
+  pdl_trigger(); pdl_wait();
+  __shared__ double sh_loss[32], sh_pq[32];
+  loss_block(row_stats, B, s_eff, ls_eps, C_total, lse_out, loss_out, pq_norm2_out, &hook, hook_out4, sh_loss, sh_pq);
+}
+
 static __global__ void hook_scale_kernel(const float* __restrict__ pq_norm2, const float* __restrict__ upstream,
-                                         double B, float s_eff, int hook_enabled, float max_grad_norm,
-                                         int phase, int epoch, float* __restrict__ out3) {
+                                         double B, float s_eff, HookCfg hook, float* __restrict__ out4) {
   pdl_trigger(); pdl_wait();
   const double up = (upstream != nullptr) ? (double)*upstream : 1.0;
-  const double base = (double)s_eff / B;
-  const double n = fabs(up) * base * sqrt((double)*pq_norm2);
-  double kappa = 1.0;
-  if (hook_enabled) {
-    double thr = (double)max_grad_norm;
-    if (phase == 1) thr = fmin(0.5, (double)max_grad_norm);
-    if (epoch < 10) thr = fmin(thr, 0.5 + 0.05 * (double)epoch);
-    if (n > 3.0) thr = fmin(thr, 0.5);
-    if (n > thr) kappa = thr / (n + 1e-8);
+  hook_scalars((double)*pq_norm2, up, B, s_eff, hook, out4);
+}
+
+// dx_hat[row] = scale * sum_s part[s][row]  followed at once by the normalise-backward of that row of x
+// (dx = inv_nx (dx_hat - x_hat <x_hat, dx_hat>), autograd of F.normalize, src/face_models.py:351): one warp per row,
+// the row never leaves registers between the two.  v = the rows the projection uses: the RAW input rows (x_hat = v *
+// inv_nx, exact to fp32 -- preferred: K1's fp16 copy carries a 2^-12 rounding that the projection of a row nearly
+// parallel to its class centre amplifies ~3x) or, PRENORM, K1's fp16 rows (x_hat * v_scale).  Optional outputs: dxhat
+// (the un-projected sum), dx_bf16 (the cast autograd applies for a bf16 input).  dim % 8 == 0, dim <= 512.
+template <typename T, bool PRENORM>
+static __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+reduce_splits_normbwd_kernel(const float* __restrict__ part, int n_splits, int64_t rows, int dim, float scale,
+                             const float* __restrict__ dev_scale, const T* __restrict__ v, float v_scale,
+                             const float* __restrict__ inv_nx, float* __restrict__ dxhat, float* __restrict__ dx,
+                             __nv_bfloat16* __restrict__ dx_bf16) {
+  pdl_trigger(); pdl_wait();
+  constexpr int N = Vec16<T>::N;                              // elements per 16-byte vector of v: 4 (fp32) or 8
+  constexpr int NV = 512 / (32 * N);                          // vectors per lane: 4 or 2
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float sc = (dev_scale != nullptr) ? scale / __ldg(dev_scale) : scale;
+  const int nvec = dim / N;
+  const int64_t n = rows * (int64_t)dim;
+  const float inv = __ldg(inv_nx + row);
+  const float vmul = PRENORM ? (1.0f / v_scale) : inv;
+  float g[NV][N], xh[NV][N];
+  float dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+#pragma unroll
+    for (int e = 0; e < N; ++e) { g[i][e] = 0.f; xh[i][e] = 0.f; }
+    if (c < nvec) {
+      const int64_t off = row * dim + (int64_t)c * N;
+      for (int k = 0; k < n_splits; ++k) {
+#pragma unroll
+        for (int e = 0; e < N; e += 4) {
+          const float4 pv = __ldcg(reinterpret_cast<const float4*>(part + (int64_t)k * n + off + e));
+          g[i][e] += pv.x; g[i][e + 1] += pv.y; g[i][e + 2] += pv.z; g[i][e + 3] += pv.w;
+        }
+      }
+      Vec16<T>::load(v + off, xh[i]);
+#pragma unroll
+      for (int e = 0; e < N; ++e) { g[i][e] *= sc; xh[i][e] *= vmul; dot = fmaf(xh[i][e], g[i][e], dot); }
+      if (dxhat != nullptr) {
+#pragma unroll
+        for (int e = 0; e < N; e += 4)
+          *reinterpret_cast<float4*>(dxhat + off + e) = make_float4(g[i][e], g[i][e + 1], g[i][e + 2], g[i][e + 3]);
+      }
+    }
   }
-  const double gs = up * kappa * base;
-  out3[0] = (float)gs;
-  out3[1] = (float)n;
-  out3[2] = (float)kappa;
-  // power of two that puts |grad_scale| * g_scale in (512, 1024]: the fp16 range centring of the
-  // tcgen05 engine's logit-gradient buffer (exact to undo)
-  out3[3] = (gs != 0.0 && isfinite(gs)) ? (float)exp2(10.0 - ceil(log2(fabs(gs)))) : 1.0f;
+  dot = warp_sum(dot);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nvec) {
+      const int64_t off = row * dim + (int64_t)c * N;
+#pragma unroll
+      for (int e = 0; e < N; e += 4) {
+        const float4 o = make_float4(inv * (g[i][e] - xh[i][e] * dot), inv * (g[i][e + 1] - xh[i][e + 1] * dot),
+                                     inv * (g[i][e + 2] - xh[i][e + 2] * dot), inv * (g[i][e + 3] - xh[i][e + 3] * dot));
+        *reinterpret_cast<float4*>(dx + off + e) = o;
+        if (dx_bf16 != nullptr)
+          *reinterpret_cast<uint2*>(dx_bf16 + off + e) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+      }
+    }
+  }
 }
 
 }  // namespace rowops

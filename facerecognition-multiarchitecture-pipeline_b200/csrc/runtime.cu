@@ -99,20 +99,42 @@ int b200f_l2norm_rows(const void* in, int in_dtype, int64_t rows, int dim, float
   return B200F_OK;
 }
 
+int b200f_l2norm_rows_pair(const void* in0, int64_t rows0, float* inv0, void* out0, const void* in1, int64_t rows1,
+                           float* inv1, void* out1, int in_dtype, int dim, float eps, int out_dtype, float out_scale,
+                           void* stream) {
+  if (rows0 <= 0 || rows1 <= 0 || !in0 || !in1 || !inv0 || !inv1 || !out0 || !out1)
+    return fail(B200F_ERR_ARG, "l2norm_rows_pair: both row sets need input, inverse norms and output");
+  const bool al = ((reinterpret_cast<uintptr_t>(in0) | reinterpret_cast<uintptr_t>(in1) | reinterpret_cast<uintptr_t>(out0) |
+                    reinterpret_cast<uintptr_t>(out1)) & 31) == 0;
+  if (in_dtype == B200F_BF16 && out_dtype == B200F_F16N && dim == 512 && al) {   // the head's shape: ONE launch
+    const int64_t b0 = ceil_div(rows0, rowops::ROWS_PER_BLOCK), b1 = ceil_div(rows1, rowops::ROWS_PER_BLOCK);
+    launch_pdl(rowops::l2norm_rows_512x16_pair_kernel<__nv_bfloat16, __half>, dim3((unsigned)(b0 + b1)),
+               dim3(rowops::WARPS_PER_BLOCK * 32), 0, as_stream(stream), static_cast<const __nv_bfloat16*>(in0), rows0, inv0,
+               static_cast<__half*>(out0), (int)b0, static_cast<const __nv_bfloat16*>(in1), rows1, inv1,
+               static_cast<__half*>(out1), eps, out_scale);
+    B200F_LAUNCH_OK("l2norm_rows pair kernel");
+    return B200F_OK;
+  }
+  int rc = b200f_l2norm_rows(in0, in_dtype, rows0, dim, eps, inv0, out0, out_dtype, out_scale, stream);
+  if (rc) return rc;
+  return b200f_l2norm_rows(in1, in_dtype, rows1, dim, eps, inv1, out1, out_dtype, out_scale, stream);
+}
+
 int b200f_l2norm_bwd(const void* v, int dtype, float v_scale, const float* inv_norm, const float* dvhat, int64_t rows,
-                     int dim, float* dv, void* stream) {
+                     int dim, float* dv, void* dv_bf16_or_null, void* stream) {
   if (!dtype_ok(dtype) && dtype != B200F_F16N) return fail(B200F_ERR_ARG, "l2norm_bwd: bad dtype");
   if (rows < 0 || dim <= 0) return fail(B200F_ERR_ARG, "l2norm_bwd: bad shape");
   if (rows == 0) return B200F_OK;
   if (!v || !inv_norm || !dvhat || !dv) return fail(B200F_ERR_ARG, "l2norm_bwd: null pointer");
   if (dtype == B200F_F16N && !(v_scale > 0.f)) return fail(B200F_ERR_ARG, "l2norm_bwd: v_scale must be > 0");
   cudaStream_t st = as_stream(stream);
+  __nv_bfloat16* lowp = static_cast<__nv_bfloat16*>(dv_bf16_or_null);
   if (dtype == B200F_F32)
-    rowops::launch_l2norm_bwd<float, false>(static_cast<const float*>(v), 1.f, inv_norm, dvhat, rows, dim, dv, st);
+    rowops::launch_l2norm_bwd<float, false>(static_cast<const float*>(v), 1.f, inv_norm, dvhat, rows, dim, dv, st, lowp);
   else if (dtype == B200F_BF16)
-    rowops::launch_l2norm_bwd<__nv_bfloat16, false>(static_cast<const __nv_bfloat16*>(v), 1.f, inv_norm, dvhat, rows, dim, dv, st);
+    rowops::launch_l2norm_bwd<__nv_bfloat16, false>(static_cast<const __nv_bfloat16*>(v), 1.f, inv_norm, dvhat, rows, dim, dv, st, lowp);
   else
-    rowops::launch_l2norm_bwd<__half, true>(static_cast<const __half*>(v), v_scale, inv_norm, dvhat, rows, dim, dv, st);
+    rowops::launch_l2norm_bwd<__half, true>(static_cast<const __half*>(v), v_scale, inv_norm, dvhat, rows, dim, dv, st, lowp);
   B200F_LAUNCH_OK("l2norm_bwd kernel");
   return B200F_OK;
 }
@@ -121,8 +143,19 @@ int b200f_arcface_loss(const float* row_stats, int64_t B, const b200f_head_cfg* 
                        float* pq_norm2, void* stream) {
   if (!row_stats || !cfg || B <= 0) return fail(B200F_ERR_ARG, "arcface_loss: bad argument");
   launch_pdl(rowops::loss_kernel, dim3(1), dim3(1024), 0, as_stream(stream), row_stats, B, cfg->s_eff,
-             cfg->label_smoothing, (double)cfg->num_classes_total, lse, loss, pq_norm2);
+             cfg->label_smoothing, (double)cfg->num_classes_total, lse, loss, pq_norm2, rowops::HookCfg{0, 1.f, 1, 0},
+             (float*)nullptr);
   B200F_LAUNCH_OK("loss_kernel");
+  return B200F_OK;
+}
+
+int b200f_arcface_loss_hook(const float* row_stats, int64_t B, const b200f_head_cfg* cfg, const b200f_hook_cfg* hook,
+                            float* lse, float* loss, float* pq_norm2, float* out4, void* stream) {
+  if (!row_stats || !cfg || !hook || !out4 || B <= 0) return fail(B200F_ERR_ARG, "arcface_loss_hook: bad argument");
+  launch_pdl(rowops::loss_kernel, dim3(1), dim3(1024), 0, as_stream(stream), row_stats, B, cfg->s_eff,
+             cfg->label_smoothing, (double)cfg->num_classes_total, lse, loss, pq_norm2,
+             rowops::HookCfg{hook->enabled, hook->max_grad_norm, hook->phase, hook->epoch}, out4);
+  B200F_LAUNCH_OK("loss_kernel (+ hook scalars)");
   return B200F_OK;
 }
 
@@ -131,7 +164,7 @@ int b200f_arcface_hook_scale(const float* pq_norm2, const float* upstream, int64
                              void* stream) {
   if (!pq_norm2 || !out4 || B <= 0) return fail(B200F_ERR_ARG, "arcface_hook_scale: bad argument");
   launch_pdl(rowops::hook_scale_kernel, dim3(1), dim3(1), 0, as_stream(stream), pq_norm2, upstream, (double)B, s_eff,
-             hook_enabled, max_grad_norm, phase, epoch, out4);
+             rowops::HookCfg{hook_enabled, max_grad_norm, phase, epoch}, out4);
   B200F_LAUNCH_OK("hook_scale_kernel");
   return B200F_OK;
 }

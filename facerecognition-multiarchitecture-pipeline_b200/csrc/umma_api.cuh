@@ -8,13 +8,23 @@ namespace umma {
 bool available();                                    // current device is sm_100
 size_t head_workspace_bytes(int64_t B, int64_t C, int D);
 
+// Optional tail of the forward (single shard): loss, lse, ||p-q||^2 and the hook scalars for an upstream gradient of 1
+// come out of the statistics reduction's last block.
+struct HeadFinal { float* lse; float* loss; float* pq_norm2; int hook_enabled; float max_grad_norm; int phase, epoch; float* out4; };
+// Optional tail of the backward (single shard): dL/dx = normalise-backward of dx_hat, against the RAW input rows when
+// given (x_hat = x * inv_nx exactly; else against K1's fp16 rows), plus its bf16 copy.
+struct HeadDx { const void* x_raw; int x_raw_dtype; const float* inv_nx; float* dx; void* dx_bf16; };
+
 int head_fwd(const void* xh, const void* wh, const int64_t* label, int64_t B, int64_t C, int64_t class_offset, int D,
              const b200f_head_cfg* cfg, float* row_stats, float* row_best, int64_t* row_argmax, float* cos_minmax,
-             int32_t* nan_flag, char* ws, size_t ws_bytes, cudaStream_t st);
+             int32_t* nan_flag, const HeadFinal* fin, char* ws, size_t ws_bytes, cudaStream_t st);
 
 int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t* label, const float* lse,
              const float* grad4, int64_t B, int64_t C, int64_t class_offset, int D, const b200f_head_cfg* cfg,
-             float* dxhat, float* dw, char* ws, size_t ws_bytes, cudaStream_t st);
+             float* dxhat, float* dw, const HeadDx* hdx, char* ws, size_t ws_bytes, cudaStream_t st);
+
+// dx = normalise-backward(dxhat) with the rows HeadDx names (one launch of rowops::l2norm_bwd)
+int head_dx_finish(const void* xh, float S, const HeadDx* hdx, const float* dxhat, int64_t B, int D, cudaStream_t st);
 
 // K4 on tensor cores (umma_xw_topk.cuh): bf16 tcgen05 scan + exact fp32 re-rank + verification
 bool gallery_tc_supported(int D);

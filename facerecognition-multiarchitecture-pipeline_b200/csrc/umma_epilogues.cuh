@@ -59,6 +59,23 @@ struct EpiStore {
 };
 
 // -------------------------------------------------------------------------------------------------
+// Coefficients of the normalise-backward of a class row, formed where they are used (this replaced a reduce_r kernel
+// between K3a and K3b):  coef_c = { inv_nw_c / (S g_scale),  r_c = sum_rb r_part[rb, c] }  -- K3a leaves one partial of
+// r_c = sum_b G_bc cos_bc per (row group, column half); the sum runs in a fixed order (bitwise reproducible).
+struct CoefSrc {
+  const float* r_part; int n_rb; int64_t ldr;   // [n_rb, ldr], classes of THIS chunk
+  const float* inv_nw;                          // [classes of the launch], indexed by the class id of the whole call
+  const float* grad4; float S;                  // grad4[3] = g_scale
+  __device__ __forceinline__ float inv_sg() const { return 1.0f / (S * __ldg(grad4 + 3)); }
+  // c_chunk: class within the chunk, c_call: class within the call (= chunk offset + c_chunk)
+  __device__ __forceinline__ float2 load(int64_t c_chunk, int64_t c_call, float inv_sg_v) const {
+    float s = 0.f;
+    for (int rb = 0; rb < n_rb; ++rb) s += __ldg(r_part + (int64_t)rb * ldr + c_chunk);
+    return make_float2(__ldg(inv_nw + c_call) * inv_sg_v, s);
+  }
+};
+
+// -------------------------------------------------------------------------------------------------
 // dW GEMM with both operands streamed (batch > 512): A = G^T rows, so an epilogue thread owns a class row and 256 of
 // its features, and the normalise-backward of W is finished here like in the X-stationary K3b:
 //   dW[c, d] = coef_c.x * (acc[c, d] - wh[c, d] * coef_c.y)      coef from reduce_r_kernel, wh = K1's fp16 rows.
@@ -66,14 +83,14 @@ struct EpiStore {
 // row-per-lane loads of wh is a small fraction of the tile: fusing it removes the separate pass over dW (read + write of
 // 4 B per element plus the wh read) that used to follow.
 struct EpiDwNorm {
-  struct Params { float* out; int64_t ld; int64_t row_offset; const float2* coef; const __half* wh; };
+  struct Params { float* out; int64_t ld; int64_t row_offset; CoefSrc coef; const __half* wh; };
   static __device__ __forceinline__ void run(const Params& ep, const GemmParams& p, const TileCoord& t,
                                              uint32_t tmem_acc, int quad, int lane, int epi_tid, float* scratch) {
     const int row = t.m0 + quad * 32 + lane;
     const int ncols = min(BLOCK_N, p.N - t.n0);
     const bool row_ok = row < p.M;
     float2 cf = make_float2(0.f, 0.f);
-    if (row_ok) cf = __ldg(ep.coef + ep.row_offset + row);
+    if (row_ok) cf = ep.coef.load(row, ep.row_offset + row, ep.coef.inv_sg());
     const int64_t base = (ep.row_offset + row) * ep.ld + t.n0;
     const bool vec = (ep.ld % 8 == 0);
     for (int ch = 0; ch * 32 < ncols; ++ch) {

@@ -109,11 +109,22 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   return B200F_OK;
 }
 
+// What the LAST block of reduce_row_partials_kernel does when the caller wants the loss in the same launch (single
+// shard: no all-reduce sits between the statistics and the loss): loss, lse, ||p - q||^2 and the hook scalars for an
+// upstream gradient of 1 (rowops::loss_block).  counter: a zeroed word of the workspace (K2 zeroes it; the last
+// block leaves it zero again).
+struct FwdFinal {
+  unsigned int* counter;      // NULL: statistics only
+  float s_eff, ls_eps; double C_total;
+  float* lse; float* loss; float* pq_norm2;
+  rowops::HookCfg hook; float* out4;
+};
+
 // One warp per row: sum the per-tile partial records in a fixed order (bitwise reproducible).
 __global__ void __launch_bounds__(256)
 reduce_row_partials_kernel(const float* __restrict__ part, int n_parts, int64_t B, const float* __restrict__ cos_part,
-                           int n_cos, float* __restrict__ row_stats, float* __restrict__ row_best,
-                           int64_t* __restrict__ row_argmax, float* __restrict__ cos_minmax) {
+                           int n_cos, float* row_stats, float* __restrict__ row_best,
+                           int64_t* __restrict__ row_argmax, float* __restrict__ cos_minmax, FwdFinal fin) {
   pdl_trigger(); pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -153,6 +164,20 @@ reduce_row_partials_kernel(const float* __restrict__ part, int n_parts, int64_t 
       cos_minmax[0] = cmin; cos_minmax[1] = cmax;
     }
   }
+  if (fin.counter != nullptr) {                               // uniform over the grid
+    __shared__ bool is_last;
+    __shared__ double sh_loss[8], sh_pq[8];
+    __threadfence();                                          // this block's row_stats are visible device-wide ...
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(fin.counter, 1u) == gridDim.x - 1);   // ... before it is counted
+    __syncthreads();
+    if (is_last) {
+      __threadfence();
+      if (threadIdx.x == 0) *fin.counter = 0u;
+      rowops::loss_block(row_stats, B, fin.s_eff, fin.ls_eps, fin.C_total, fin.lse, fin.loss, fin.pq_norm2, &fin.hook,
+                         fin.out4, sh_loss, sh_pq);
+    }
+  }
 }
 
 // dst (=|+=) scale / *dev_scale * sum_s part[s], fixed order
@@ -172,21 +197,8 @@ __global__ void reduce_splits_kernel(const float* __restrict__ part, int n_split
   *reinterpret_cast<float4*>(dst + i) = s;
 }
 
-// coef[c] = { inv_nw[c] / (S g_scale), sum_rb r_part[rb, c] } for the classes of one chunk (fixed order)
-__global__ void reduce_r_kernel(const float* __restrict__ r_part, int n_rb, int64_t ldr, int64_t cnt,
-                                const float* __restrict__ inv_nw, const float* __restrict__ grad4, float S,
-                                float2* __restrict__ coef) {
-  pdl_trigger(); pdl_wait();
-  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cnt) return;
-  float s = 0.f;
-  for (int rb = 0; rb < n_rb; ++rb) s += r_part[(int64_t)rb * ldr + c];
-  coef[c] = make_float2(__ldg(inv_nw + c) / (S * __ldg(grad4 + 3)), s);
-}
-
 // ---- X-stationary kernel: launch geometry ---------------------------------------------------------
 static std::atomic<int> g_pair{2};                 // 2 = tcgen05 cta_group::2 CTA pairs, 1 = single CTAs
-static std::atomic<int> g_k3b_class_major{1};       // K3b epilogue: 1 = thread owns a class row (XwDwT), 0 = a feature (XwDw)
 static std::atomic<int> g_epi_groups{2};            // K2 / K3a: 2 = two epilogue groups of 8 warps (16-column slices), 1 = one group
 #ifdef B200F_PROBES                                 // tools/ builds only; the shipped library has neither the branch nor the switch
 static std::atomic<int> g_k3a_ablate{0};            // probe: 2 = no G^T stores (WRONG results)
@@ -214,7 +226,7 @@ static void stage_event(int which, bool is_end, cudaStream_t st) {
   cudaEventRecord(is_end ? g_ev.end[which][j] : g_ev.beg[which][j], st);
   if (is_end) g_ev.n[which] = j + 1;
 }           // K3b walks each chunk last tile first
-static std::atomic<int> g_prefetch{0};             // L2 prefetch distance of the xw producer (stages)
+static std::atomic<int> g_prefetch{2};             // L2 prefetch distance of the xw producer (tiles of the streamed operand)
 static std::atomic<int> g_chunk_mb{112};           // budget of the fp16 logit-gradient buffer G per class chunk
 
 // MODE of the X-stationary kernel: 0 = both operands K-major (K2, gallery scan, probes); 1 = resident operand
@@ -289,13 +301,14 @@ static XwPlan xw_plan(int64_t B, int64_t C, int pair, int max_chunks = 0) {
 template <int PAIR, int MODE, class Epi>
 static int launch_xw(const CUtensorMap& tx, const CUtensorMap& tw, const XwPlan& q, int64_t B, int64_t C, int D,
                      const typename Epi::Params& ep, cudaStream_t st, const char* what, uint32_t fmt = FMT_F16,
-                     bool reverse = false) {
+                     bool reverse = false, const void* w_base = nullptr, int64_t w_row_bytes = 0) {
   int rc = xw_set_smem<PAIR, MODE, Epi>(); if (rc) return rc;
   XwParams p{};
   p.B = (int)B; p.C = (int)C; p.D = D;
   p.kb_count = (int)ceil_div(D, XW_K);
   p.m_groups = q.m_groups; p.n_tiles = q.n_tiles; p.n_chunks = q.n_chunks;
-  p.prefetch = g_prefetch.load(std::memory_order_relaxed);
+  p.prefetch = (w_base != nullptr) ? g_prefetch.load(std::memory_order_relaxed) : 0;
+  p.w_base = w_base; p.w_row_bytes = w_row_bytes;
   p.tn = XW_WROWS * PAIR;
   p.reverse = reverse ? 1 : 0;
   p.idesc = make_idesc(fmt, fmt, MODE == XW_MK, MODE == XW_SWAP_MK, XW_M * PAIR, XW_WROWS * PAIR);   // A = resident, except SWAP modes
@@ -314,9 +327,9 @@ static int launch_xw(const CUtensorMap& tx, const CUtensorMap& tw, const XwPlan&
 // ---- plan -------------------------------------------------------------------------------------------
 struct Plan {
   XwPlan fwd;
-  size_t off_part, off_cos;
+  size_t off_part, off_cos, off_counter;
   int64_t Cc, ldg; int n_chunks, dx_splits;
-  size_t off_G, off_dxpart, off_rpart, off_coef;
+  size_t off_G, off_dxpart, off_rpart;
   int n_rb;                 // 32-row blocks of the batch that K3a emits r partials for
   bool fused_dw;            // B <= 512: dW GEMM on the MN-major X-stationary kernel (x_hat^T resident); above that
                             // on the generic core, transposed the same way; the normalise-backward is fused in both
@@ -335,6 +348,7 @@ static Plan make_plan(int64_t B, int64_t C, int D) {
   const size_t cos_max = (size_t)(p1.items > 2 * p2.items ? p1.items : 2 * p2.items) * XW_EPI_WARPS;
   pl.off_part = off; off += align_up(sizeof(float) * part_max * XW_MAX_EPI_GROUPS * B * PART_COLS, 256);   // one record per epilogue group
   pl.off_cos = off;  off += align_up(sizeof(float) * 2 * cos_max * XW_MAX_EPI_GROUPS, 256);
+  pl.off_counter = off; off += 256;                       // the fused loss finalize counts its blocks here
   const size_t fwd_total = off;
   // backward: classes are processed in chunks whose fp16 logit gradient G fits the budget.  G is written once
   // and read twice, all while the tensor pipe (not HBM) is the bound, so it need not stay L2-resident: cfg3's
@@ -366,7 +380,6 @@ static Plan make_plan(int64_t B, int64_t C, int D) {
   pl.fused_dw = (B <= (int64_t)XW_MAX_KB * XW_K);         // x_hat^T resident (else: both operands streamed)
   pl.n_rb = (int)ceil_div(B, 2 * XW_M) * 2 * 4;          // covers either pairing
   pl.off_rpart = off; off += align_up(sizeof(float) * (size_t)pl.n_rb * pl.Cc, 256);
-  pl.off_coef = off;  off += align_up(sizeof(float2) * (size_t)C, 256);
   pl.total = (off > fwd_total ? off : fwd_total) + 1024;
   return pl;
 }
@@ -399,9 +412,21 @@ static int check_shape(int64_t B, int64_t C, int D, const b200f_head_cfg* cfg) {
   return B200F_OK;
 }
 
+int head_dx_finish(const void* xh, float S, const HeadDx* hdx, const float* dxhat, int64_t B, int D, cudaStream_t st) {
+  __nv_bfloat16* lowp = static_cast<__nv_bfloat16*>(hdx->dx_bf16);
+  if (hdx->x_raw != nullptr && hdx->x_raw_dtype == B200F_BF16)
+    rowops::launch_l2norm_bwd<__nv_bfloat16, false>(static_cast<const __nv_bfloat16*>(hdx->x_raw), 1.f, hdx->inv_nx, dxhat, B, D, hdx->dx, st, lowp);
+  else if (hdx->x_raw != nullptr && hdx->x_raw_dtype == B200F_F32)
+    rowops::launch_l2norm_bwd<float, false>(static_cast<const float*>(hdx->x_raw), 1.f, hdx->inv_nx, dxhat, B, D, hdx->dx, st, lowp);
+  else
+    rowops::launch_l2norm_bwd<__half, true>(static_cast<const __half*>(xh), S, hdx->inv_nx, dxhat, B, D, hdx->dx, st, lowp);
+  B200F_LAUNCH_OK("l2norm_bwd kernel (dx)");
+  return B200F_OK;
+}
+
 int head_fwd(const void* xh, const void* wh, const int64_t* label, int64_t B, int64_t C, int64_t class_offset, int D,
              const b200f_head_cfg* cfg, float* row_stats, float* row_best, int64_t* row_argmax, float* cos_minmax,
-             int32_t* nan_flag, char* ws, size_t ws_bytes, cudaStream_t st) {
+             int32_t* nan_flag, const HeadFinal* fin, char* ws, size_t ws_bytes, cudaStream_t st) {
   int rc = check_shape(B, C, D, cfg); if (rc) return rc;
   const Plan pl = make_plan(B, C, D);
   if (ws_bytes < pl.total) return fail(B200F_ERR_WORKSPACE, "umma head_fwd: workspace too small");
@@ -417,31 +442,39 @@ int head_fwd(const void* xh, const void* wh, const int64_t* label, int64_t B, in
   ep.part = reinterpret_cast<float*>(ws + pl.off_part);
   ep.cos_part = reinterpret_cast<float*>(ws + pl.off_cos);
   ep.nan_flag = nan_flag; ep.pair = q.pair;
+  ep.zero_word = reinterpret_cast<unsigned int*>(ws + pl.off_counter);
   const int eg = g_epi_groups.load(std::memory_order_relaxed);
+  const int64_t wrb = (int64_t)D * 2;
   stage_reset(EV_K2);
   stage_event(EV_K2, false, st);
   if (eg == 2) {
     XwFwd2::Params ep2{};
     ep2.label = ep.label; ep2.class_offset = ep.class_offset; ep2.hm = ep.hm; ep2.inv_scale = ep.inv_scale; ep2.part = ep.part;
-    ep2.cos_part = ep.cos_part; ep2.nan_flag = ep.nan_flag; ep2.pair = ep.pair;
-    rc = (q.pair == 2) ? launch_xw<2, XW_KK, XwFwd2>(tx, tw, q, B, C, D, ep2, st, "umma K2 arcface_fwd (cta pair, 2 epilogue groups)")
-                       : launch_xw<1, XW_KK, XwFwd2>(tx, tw, q, B, C, D, ep2, st, "umma K2 arcface_fwd (2 epilogue groups)");
+    ep2.cos_part = ep.cos_part; ep2.nan_flag = ep.nan_flag; ep2.pair = ep.pair; ep2.zero_word = ep.zero_word;
+    rc = (q.pair == 2) ? launch_xw<2, XW_KK, XwFwd2>(tx, tw, q, B, C, D, ep2, st, "umma K2 arcface_fwd (cta pair, 2 epilogue groups)", FMT_F16, false, wh, wrb)
+                       : launch_xw<1, XW_KK, XwFwd2>(tx, tw, q, B, C, D, ep2, st, "umma K2 arcface_fwd (2 epilogue groups)", FMT_F16, false, wh, wrb);
   } else {
-    rc = (q.pair == 2) ? launch_xw<2, XW_KK, XwFwd>(tx, tw, q, B, C, D, ep, st, "umma K2 arcface_fwd (cta pair)")
-                       : launch_xw<1, XW_KK, XwFwd>(tx, tw, q, B, C, D, ep, st, "umma K2 arcface_fwd");
+    rc = (q.pair == 2) ? launch_xw<2, XW_KK, XwFwd>(tx, tw, q, B, C, D, ep, st, "umma K2 arcface_fwd (cta pair)", FMT_F16, false, wh, wrb)
+                       : launch_xw<1, XW_KK, XwFwd>(tx, tw, q, B, C, D, ep, st, "umma K2 arcface_fwd", FMT_F16, false, wh, wrb);
   }
   stage_event(EV_K2, true, st);
   if (rc) return rc;
+  FwdFinal ff{};
+  if (fin != nullptr) {                                     // single shard: the loss comes out of the same launch
+    ff.counter = ep.zero_word; ff.s_eff = cfg->s_eff; ff.ls_eps = cfg->label_smoothing; ff.C_total = (double)cfg->num_classes_total;
+    ff.lse = fin->lse; ff.loss = fin->loss; ff.pq_norm2 = fin->pq_norm2;
+    ff.hook = rowops::HookCfg{fin->hook_enabled, fin->max_grad_norm, fin->phase, fin->epoch}; ff.out4 = fin->out4;
+  }
   launch_pdl(reduce_row_partials_kernel, dim3((unsigned)ceil_div(B, 8)), dim3(256), 0, st, ep.part, q.n_chunks * eg, B, ep.cos_part,
                                                                       q.items * q.pair * XW_EPI_WARPS * eg, row_stats, row_best,
-                                                                      row_argmax, cos_minmax);
+                                                                      row_argmax, cos_minmax, ff);
   B200F_LAUNCH_OK("reduce_row_partials_kernel");
   return B200F_OK;
 }
 
 int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t* label, const float* lse,
              const float* grad4, int64_t B, int64_t C, int64_t class_offset, int D, const b200f_head_cfg* cfg,
-             float* dxhat, float* dw, char* ws, size_t ws_bytes, cudaStream_t st) {
+             float* dxhat, float* dw, const HeadDx* hdx, char* ws, size_t ws_bytes, cudaStream_t st) {
   int rc = check_shape(B, C, D, cfg); if (rc) return rc;
   const Plan pl = make_plan(B, C, D);
   if (ws_bytes < pl.total) return fail(B200F_ERR_WORKSPACE, "umma head_bwd: workspace too small");
@@ -454,9 +487,11 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
   rc = tmap_mnmajor(&tx_mn, xh, D, B, D); if (rc) return rc;
   stage_reset(EV_K3A); stage_reset(EV_K3B); stage_reset(EV_K3C);
   const int gpair = pl.fwd.pair;                            // generic core: single CTAs or cta_group::2 pairs, like K2 / K3a
+  const int64_t wrb = (int64_t)D * 2;
   int chunk_no = 0;
   for (int64_t c0 = 0; c0 < C; c0 += pl.Cc, ++chunk_no) {
     const int64_t cnt = (C - c0 < pl.Cc) ? (C - c0) : pl.Cc;
+    const bool last_chunk = c0 + pl.Cc >= C;
     const uint16_t* wc = static_cast<const uint16_t*>(wh) + c0 * D;
     // --- K3a: logit gradient of the chunk, class-major: G^T[c, b] (x_hat resident, w_hat rows [c0, c0 + cnt) streamed
     //     on the A side, so a thread owns a class and r_c = sum_b G cos is a private sum)
@@ -481,45 +516,32 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
 #ifdef B200F_PROBES
       e2.ablate = eg.ablate;
 #endif
-      rc = (qg.pair == 2) ? launch_xw<2, XW_SWAP, XwBwdGT2>(tx_k, tw_k, qg, B, cnt, D, e2, st, "umma K3a logit-grad (cta pair, 2 epilogue groups)")
-                          : launch_xw<1, XW_SWAP, XwBwdGT2>(tx_k, tw_k, qg, B, cnt, D, e2, st, "umma K3a logit-grad (2 epilogue groups)");
+      rc = (qg.pair == 2) ? launch_xw<2, XW_SWAP, XwBwdGT2>(tx_k, tw_k, qg, B, cnt, D, e2, st, "umma K3a logit-grad (cta pair, 2 epilogue groups)", FMT_F16, false, wc, wrb)
+                          : launch_xw<1, XW_SWAP, XwBwdGT2>(tx_k, tw_k, qg, B, cnt, D, e2, st, "umma K3a logit-grad (2 epilogue groups)", FMT_F16, false, wc, wrb);
     } else {
-      rc = (qg.pair == 2) ? launch_xw<2, XW_SWAP, XwBwdGT>(tx_k, tw_k, qg, B, cnt, D, eg, st, "umma K3a logit-grad (cta pair)")
-                          : launch_xw<1, XW_SWAP, XwBwdGT>(tx_k, tw_k, qg, B, cnt, D, eg, st, "umma K3a logit-grad");
+      rc = (qg.pair == 2) ? launch_xw<2, XW_SWAP, XwBwdGT>(tx_k, tw_k, qg, B, cnt, D, eg, st, "umma K3a logit-grad (cta pair)", FMT_F16, false, wc, wrb)
+                          : launch_xw<1, XW_SWAP, XwBwdGT>(tx_k, tw_k, qg, B, cnt, D, eg, st, "umma K3a logit-grad", FMT_F16, false, wc, wrb);
     }
     stage_event(EV_K3A, true, st);
     if (rc) return rc;
-    // --- K3b: dW[c0 + c, d] = inv_nw_c (sum_b G^T[c, b] x_hat[b, d] - w_hat[c, d] r_c), computed transposed (the thread
-    //     owns a feature d, so a warp writes 128 contiguous bytes of a dW row) with the normalise-backward fused
-    float2* coef = reinterpret_cast<float2*>(ws + pl.off_coef);
-    launch_pdl(reduce_r_kernel, dim3((unsigned)ceil_div(cnt, 256)), dim3(256), 0, st, r_part, qg.m_groups * 2, pl.Cc, cnt,
-                                                                inv_nw + c0, grad4, S, coef + c0);
-    B200F_LAUNCH_OK("umma reduce_r_kernel");
+    // --- K3b: dW[c0 + c, d] = inv_nw_c (sum_b G^T[c, b] x_hat[b, d] - w_hat[c, d] r_c), class-major (the thread owns a
+    //     class row), normalise-backward fused; its coefficients { inv_nw_c / (S g_scale), r_c } are formed in the epilogue
+    //     from K3a's partials (CoefSrc)
+    const CoefSrc coef{r_part, qg.m_groups * 2, pl.Cc, inv_nw, grad4, S};
     stage_event(EV_K3B, false, st);
     if (pl.fused_dw) {                                      // x_hat^T resident, G^T rows streamed
       CUtensorMap tg_k;
       rc = tmap_kmajor(&tg_k, G, cnt, B, pl.ldg, XW_WROWS); if (rc) return rc;
       const XwPlan qw = xw_plan(D, cnt, qg.pair);
       const bool k3b_rev = g_k3b_reverse.load(std::memory_order_relaxed) != 0;   // read K3a's freshest G^T rows first
-      if (g_k3b_class_major.load(std::memory_order_relaxed)) {   // thread owns a class row: vector loads / stores
-        XwDwT::Params ew{};
-        rc = make_tmap(&ew.tm_wh, wc, D, cnt, D, 32, 32, CU_TENSOR_MAP_SWIZZLE_NONE); if (rc) return rc;
-        ew.coef = coef; ew.dw = dw; ew.c0 = c0; ew.ld = D;
+      XwDwT::Params ew{};
+      rc = make_tmap(&ew.tm_wh, wc, D, cnt, D, 32, 32, CU_TENSOR_MAP_SWIZZLE_NONE); if (rc) return rc;
+      ew.coef = coef; ew.dw = dw; ew.c0 = c0; ew.ld = D;
 #ifdef B200F_PROBES
-        ew.ablate = g_k3b_ablate.load(std::memory_order_relaxed);
+      ew.ablate = g_k3b_ablate.load(std::memory_order_relaxed);
 #endif
-        rc = (qw.pair == 2) ? launch_xw<2, XW_SWAP_MK, XwDwT>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW class-major (cta pair)", FMT_F16, k3b_rev)
-                            : launch_xw<1, XW_SWAP_MK, XwDwT>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW class-major", FMT_F16, k3b_rev);
-      } else
-      if (D == 512) {                                       // the head's shape: constant row stride in the epilogue
-        XwDw<512>::Params ew{coef, static_cast<const __half*>(wh), dw, c0, D};
-        rc = (qw.pair == 2) ? launch_xw<2, XW_MK, XwDw<512>>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW (cta pair)", FMT_F16, k3b_rev)
-                            : launch_xw<1, XW_MK, XwDw<512>>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW", FMT_F16, k3b_rev);
-      } else {
-        XwDw<0>::Params ew{coef, static_cast<const __half*>(wh), dw, c0, D};
-        rc = (qw.pair == 2) ? launch_xw<2, XW_MK, XwDw<0>>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW (cta pair)", FMT_F16, k3b_rev)
-                            : launch_xw<1, XW_MK, XwDw<0>>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW", FMT_F16, k3b_rev);
-      }
+      rc = (qw.pair == 2) ? launch_xw<2, XW_SWAP_MK, XwDwT>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW class-major (cta pair)", FMT_F16, k3b_rev, G, pl.ldg * 2)
+                          : launch_xw<1, XW_SWAP_MK, XwDwT>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW class-major", FMT_F16, k3b_rev, G, pl.ldg * 2);
       if (rc) return rc;
     } else {
       // batch > 512: x_hat^T cannot stay resident, both operands stream through the generic core:
@@ -547,9 +569,30 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
     stage_event(EV_K3C, true, st);
     if (rc) return rc;
     const int64_t n = B * (int64_t)D;
-    launch_pdl(reduce_splits_kernel, dim3((unsigned)ceil_div(n / 4, 256)), dim3(256), 0, st, dxpart, px.k_splits, n, dxhat, chunk_no > 0,
-                                                                        1.0f / S, grad4 + 3);
-    B200F_LAUNCH_OK("umma reduce_splits_kernel");
+    if (hdx != nullptr && hdx->dx != nullptr && pl.n_chunks == 1) {
+      // single chunk, single shard: the split reduction finishes dL/dx itself (normalise-backward of the row, and the
+      // bf16 copy autograd would make), no round trip of dx_hat through HBM and two launches fewer
+      const unsigned grid = (unsigned)ceil_div(B, rowops::WARPS_PER_BLOCK);
+      const dim3 blk(rowops::WARPS_PER_BLOCK * 32);
+      __nv_bfloat16* lowp = static_cast<__nv_bfloat16*>(hdx->dx_bf16);
+      if (hdx->x_raw != nullptr && hdx->x_raw_dtype == B200F_BF16)
+        launch_pdl(rowops::reduce_splits_normbwd_kernel<__nv_bfloat16, false>, dim3(grid), blk, 0, st, dxpart, px.k_splits, B, D, 1.0f / S,
+                   grad4 + 3, static_cast<const __nv_bfloat16*>(hdx->x_raw), 1.0f, hdx->inv_nx, dxhat, hdx->dx, lowp);
+      else if (hdx->x_raw != nullptr && hdx->x_raw_dtype == B200F_F32)
+        launch_pdl(rowops::reduce_splits_normbwd_kernel<float, false>, dim3(grid), blk, 0, st, dxpart, px.k_splits, B, D, 1.0f / S,
+                   grad4 + 3, static_cast<const float*>(hdx->x_raw), 1.0f, hdx->inv_nx, dxhat, hdx->dx, lowp);
+      else
+        launch_pdl(rowops::reduce_splits_normbwd_kernel<__half, true>, dim3(grid), blk, 0, st, dxpart, px.k_splits, B, D, 1.0f / S,
+                   grad4 + 3, static_cast<const __half*>(xh), S, hdx->inv_nx, dxhat, hdx->dx, lowp);
+      B200F_LAUNCH_OK("umma reduce_splits_normbwd_kernel");
+    } else {
+      launch_pdl(reduce_splits_kernel, dim3((unsigned)ceil_div(n / 4, 256)), dim3(256), 0, st, dxpart, px.k_splits, n, dxhat, chunk_no > 0,
+                                                                          1.0f / S, grad4 + 3);
+      B200F_LAUNCH_OK("umma reduce_splits_kernel");
+      if (last_chunk && hdx != nullptr && hdx->dx != nullptr) {
+        rc = head_dx_finish(xh, S, hdx, dxhat, B, D, st); if (rc) return rc;
+      }
+    }
   }
   return B200F_OK;
 }
@@ -615,7 +658,7 @@ int gallery_prepare(const void* g, int dtype, int64_t N, int D, int metric, int 
 }
 
 template <int KT>
-static int gallery_scan_kt(const GalleryScanPlan& gp, const CUtensorMap& tx, const CUtensorMap& tw, const float* q,
+static int gallery_scan_kt(const GalleryScanPlan& gp, const void* g16, const CUtensorMap& tx, const CUtensorMap& tw, const float* q,
                            const float* g, const float* bias, const float* q_inv, const float* g_inv, int64_t Q, int64_t N,
                            int64_t index_offset, int D, int k, int metric, int fmt, float thresh, int64_t* idx, float* score,
                            uint8_t* accept, uint8_t* redo, int32_t* redo_count, float* ckey, int32_t* cidx, float* skey,
@@ -636,8 +679,8 @@ static int gallery_scan_kt(const GalleryScanPlan& gp, const CUtensorMap& tx, con
     ep.tau0 = tau0;
   }
   ep.cand_key = ckey; ep.cand_idx = cidx; ep.n_lists = gp.n_lists;
-  int rc = (gp.q.pair == 2) ? launch_xw<2, XW_KK, XwTopK<KT>>(tx, tw, gp.q, Q, N, D, ep, st, "umma K4 gallery scan (cta pair)", mfmt)
-                            : launch_xw<1, XW_KK, XwTopK<KT>>(tx, tw, gp.q, Q, N, D, ep, st, "umma K4 gallery scan", mfmt);
+  int rc = (gp.q.pair == 2) ? launch_xw<2, XW_KK, XwTopK<KT>>(tx, tw, gp.q, Q, N, D, ep, st, "umma K4 gallery scan (cta pair)", mfmt, false, g16, (int64_t)D * 2)
+                            : launch_xw<1, XW_KK, XwTopK<KT>>(tx, tw, gp.q, Q, N, D, ep, st, "umma K4 gallery scan", mfmt, false, g16, (int64_t)D * 2);
   if (rc) return rc;
   const int n_cand = gp.n_lists * KT;
   const size_t smem = (size_t)n_cand * 16;                 // candidates + survivors, (key, idx) each
@@ -675,7 +718,7 @@ int gallery_scan_select(const float* q, const float* g, const void* g16, const f
   CUtensorMap tx, tw;
   int rc = tmap_kmajor(&tx, q16, Q, D, D, XW_M); if (rc) return rc;
   rc = tmap_kmajor(&tw, g16, N, D, D, XW_WROWS); if (rc) return rc;
-#define B200F_SCAN(KT) gallery_scan_kt<KT>(gp, tx, tw, q, g, bias, q_inv, g_inv, Q, N, index_offset, D, k, metric, fmt, thresh, idx, \
+#define B200F_SCAN(KT) gallery_scan_kt<KT>(gp, g16, tx, tw, q, g, bias, q_inv, g_inv, Q, N, index_offset, D, k, metric, fmt, thresh, idx, \
                                            score, accept, redo, redo_count, ckey, cidx, skey, sidx, tau0, qbad, st)
   if (gp.KT == 8) return B200F_SCAN(8);
   if (gp.KT == 16) return B200F_SCAN(16);
@@ -774,7 +817,6 @@ int b200f_set_tunable(const char* name, int value) {
   const std::string n(name);
   if (n == "pair") return b200f_umma_set_pair(value);
   if (n == "pdl") { const int old_v = pdl_enabled() ? 1 : 0; if (value == 0 || value == 1) pdl_set(value != 0); return old_v; }
-  if (n == "k3b_class_major") { if (value != 0 && value != 1) return g_k3b_class_major.load(); return g_k3b_class_major.exchange(value); }
   if (n == "stage_events") { if (value != 0 && value != 1) return g_stage_events.load(); return g_stage_events.exchange(value); }
   if (n == "epi_groups") { if (value != 1 && value != 2) return g_epi_groups.load(); return g_epi_groups.exchange(value); }
 #ifdef B200F_PROBES

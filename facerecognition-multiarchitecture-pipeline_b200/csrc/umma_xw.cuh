@@ -108,8 +108,13 @@ struct XwParams {
   int tn;                               // 128 * PAIR: tile width = rows of a resident group
   int reverse;                          // walk the tiles of a chunk last-to-first: a consumer of what the previous
                                         // kernel just wrote finds the freshest part still in L2
-  int prefetch;                         // stages of L2 prefetch issued ahead of the ring (0 = off, the default:
-                                        // measured slower -- the ring alone already sustains 91 % of HBM peak)
+  int prefetch;                         // TILES of the streamed operand pulled into L2 ahead of the ring (0 = off) with ONE
+                                        // contiguous cp.async.bulk.prefetch.L2 per CTA and tile (K-major rows are contiguous:
+                                        // a CTA's 128 rows x D are one block of memory).  Why: the ring holds 5 of a tile's 8
+                                        // k-blocks (80 KB in flight per SM); against HBM latency under load (~2 us) that
+                                        // sustains ~40 GB/s per SM where a tensor-bound K2 at cfg3 needs 60.
+  const void* w_base;                   // streamed operand: first row of this launch, row pitch in bytes (prefetch only)
+  int64_t w_row_bytes;
   uint32_t idesc;
 };
 
@@ -250,16 +255,19 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
             }
           }
         }
-        // L2 prefetch cursor: XW_PREFETCH stages ahead of the loads
-        int pt = t_begin, pkb = 0;
-        if (leader) {
-          for (int i = 0; i < p.prefetch && pt < t_end; ++i) {
-            const int pn0 = pt * TN + rank * XW_WROWS;
-            if (!W_MN) tma_prefetch_l2_2d(&tm_w, pkb * XW_K, pn0);
-            else { tma_prefetch_l2_2d(&tm_w, pn0, pkb * XW_K); tma_prefetch_l2_2d(&tm_w, pn0 + 64, pkb * XW_K); }
-            if (++pkb == p.kb_count) { pkb = 0; ++pt; }
-          }
-        }
+        // L2 prefetch of whole tiles ahead of the ring (K-major streamed operand only)
+        auto prefetch_tile = [&](int tj) {                      // tj: position in the walk order of this item
+          if (W_MN || p.prefetch <= 0 || tj >= t_end) return;
+          const int tt = p.reverse ? (t_end - 1 - (tj - t_begin)) : tj;
+          const int64_t r0 = (int64_t)tt * TN + rank * XW_WROWS;
+          int64_t nrows = (int64_t)p.C - r0; if (nrows > XW_WROWS) nrows = XW_WROWS;
+          if (nrows <= 0) return;
+          const char* a = static_cast<const char*>(p.w_base) + r0 * p.w_row_bytes;
+          const uint32_t nbytes = (uint32_t)(nrows * p.w_row_bytes) & ~15u;
+          if (nbytes >= 16 && (reinterpret_cast<uintptr_t>(a) & 15) == 0)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(nbytes) : "memory");
+        };
+        if (leader) for (int i = 1; i < p.prefetch; ++i) prefetch_tile(t_begin + i);
         for (int ti = t_begin; ti < t_end && ok; ++ti) {
           const int t = p.reverse ? (t_end - 1 - (ti - t_begin)) : ti;
           const int n0 = t * TN + rank * XW_WROWS;
@@ -267,12 +275,7 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
             ok = mbar_wait(&empty_bar[stage], phase ^ 1);
             if (!ok) break;
             if (leader) {
-              if (p.prefetch > 0 && pt < t_end) {
-                const int pn0 = pt * TN + rank * XW_WROWS;
-                if (!W_MN) tma_prefetch_l2_2d(&tm_w, pkb * XW_K, pn0);
-                else { tma_prefetch_l2_2d(&tm_w, pn0, pkb * XW_K); tma_prefetch_l2_2d(&tm_w, pn0 + 64, pkb * XW_K); }
-                if (++pkb == p.kb_count) { pkb = 0; ++pt; }
-              }
+              if (kb == 0) prefetch_tile(ti + p.prefetch);
               if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(PAIR * XW_TILE_BYTES));
               else mbar_arrive_cluster(&full_bar[stage], 0);
               uint8_t* dst = ring + (size_t)stage * XW_TILE_BYTES;

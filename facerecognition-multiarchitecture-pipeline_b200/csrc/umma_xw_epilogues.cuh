@@ -70,6 +70,7 @@ struct XwFwdT {
     float* cos_part;            // [items * PAIR * 8 * EG, 2]
     int32_t* nan_flag;
     int pair;
+    unsigned int* zero_word;    // a word of the workspace the kernel clears (block counter of the fused loss finalize)
   };
   struct State {
     float sumexp, sumexp2, sumz, ztgt, best, cmin, cmax;
@@ -84,6 +85,7 @@ struct XwFwdT {
     st.saw_nan = false;
     st.row_ok = it.row < p.B;
     st.tgt = -1;
+    if (it.item == 0 && it.rank == 0 && it.grp == 0 && it.ew == 0 && it.lane == 0 && ep.zero_word != nullptr) *ep.zero_word = 0u;
     if (st.row_ok) {
       const int64_t tg = __ldg(ep.label + it.row) - ep.class_offset;
       if (tg >= 0 && tg < p.C) st.tgt = (int)tg;
@@ -358,69 +360,6 @@ using XwBwdGT = XwBwdGTT<1, 32>;
 using XwBwdGT2 = XwBwdGTT<2, 16>;
 
 // -------------------------------------------------------------------------------------------------
-// K3b on the MN-major kernel: acc[d, c] = sum_b x_hat[b, d] S * G'[b, c]  (= dW_hat^T * S * g_scale), finished in
-// place with the normalise-backward of the weight rows (autograd of F.normalize, src/face_models.py:352):
-//   dW[c, d] = inv_nw_c * (dW_hat[c, d] - w_hat[c, d] r_c) = coef_c.x * (acc - wh[c, d] * coef_c.y)
-// coef_c = { inv_nw_c / (S g_scale), r'_c } from reduce_r_kernel; wh = w_hat * S (K1's fp16 rows).
-// The thread owns feature d: for a fixed class its warp writes 128 contiguous bytes of the dW row.
-// (Measured and rejected: fetching the w_hat values one slice ahead -- into registers, or as 16 B vectors through
-//  warp-private shared memory -- made this kernel 50 % slower than loading them where they are used.)
-template <int LD>                                             // row stride of dW / w_hat known at compile time (512), or 0
-struct XwDw {
-  static __device__ __forceinline__ int64_t stride(int ld) { return LD ? (int64_t)LD : (int64_t)ld; }
-  struct Params { const float2* coef; const __half* wh; float* dw; int64_t c0; int ld; };
-  struct State { bool row_ok; };
-  static __device__ __forceinline__ void item_begin(State& st, const Params&, const XwParams& p, const XwItem& it) {
-    st.row_ok = it.row < p.B;
-  }
-  // The epilogue reads w_hat[c, d] and coef[c] straight from global memory, and at 24 % L2 hit rate the exposed
-  // DRAM latency of those loads (not their count) bounded the kernel: pull the NEXT tile's operands into L2 one
-  // tile (~5 us) ahead.  Each of the 128 threads that share a column half prefetches ONE class row segment --
-  // this CTA's 128 features = 256 contiguous bytes -- with one bulk prefetch.
-  static __device__ __forceinline__ void tile_begin(State&, const Params& ep, const XwParams& p, const XwItem& it,
-                                                    int, int next_cls0, int ncols) {
-    if (next_cls0 < 0) return;
-    const int c = next_cls0 + it.quad * 32 + it.lane;
-    if (it.quad * 32 + it.lane >= ncols || c >= p.C) return;
-    const int64_t d_base = it.row - (it.quad * 32 + it.lane);         // first feature of this CTA
-    int nbytes = (int)min((int64_t)XW_M, (int64_t)p.B - d_base) * 2;
-    nbytes &= ~15;
-    const __half* a = ep.wh + (ep.c0 + c) * stride(ep.ld) + d_base;
-    if (nbytes >= 16 && (reinterpret_cast<uintptr_t>(a) & 15) == 0)
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(nbytes) : "memory");
-    if ((c & 15) == 0)                                                // 16 coefficients = one 128 B line
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.coef + ep.c0 + c));
-  }
-  static __device__ __forceinline__ void slice(State& st, const Params& ep, const XwParams& p, const XwItem& it,
-                                               float (&v)[32], int cls0) {
-    if (!st.row_ok) return;
-    const int cc = min(32, p.C - cls0);
-    const int64_t ldw = stride(ep.ld);                        // constant stride: loads / stores use immediate offsets
-    const int64_t base = (ep.c0 + cls0) * ldw + it.row;
-    const float2* cf = ep.coef + ep.c0 + cls0;
-    if (cc == 32) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 2) {
-        const float4 c4 = __ldg(reinterpret_cast<const float4*>(cf + j));   // two classes' coefficients per load
-        const float w0 = __half2float(__ldg(ep.wh + base + (int64_t)j * ldw));
-        const float w1 = __half2float(__ldg(ep.wh + base + (int64_t)(j + 1) * ldw));
-        ep.dw[base + (int64_t)j * ldw] = c4.x * fmaf(-w0, c4.y, v[j]);
-        ep.dw[base + (int64_t)(j + 1) * ldw] = c4.z * fmaf(-w1, c4.w, v[j + 1]);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        if (j < cc) {
-          const float2 c2 = __ldg(cf + j);
-          const float wv = __half2float(__ldg(ep.wh + base + (int64_t)j * ldw));
-          ep.dw[base + (int64_t)j * ldw] = c2.x * fmaf(-wv, c2.y, v[j]);
-        }
-      }
-    }
-  }
-  static __device__ __forceinline__ void item_end(State&, const Params&, const XwParams&, const XwItem&, float*) {}
-};
-
 // ---- K3b, class-major: dW[c, d] = coef.x * (acc[c, d] - w_hat16[c, d] * coef.y) --------------------------------
 // SWAP side of the kernel (G^T rows streamed as the A operand, x_hat resident MN-major as B): the thread owns ONE
 // class row per tile and 128 of the group's 256 features; it stores 128 contiguous bytes per 32-feature slice.
@@ -436,10 +375,10 @@ struct XwDwT {
   static constexpr int kRingStages = 3;
   struct Params {
     alignas(64) CUtensorMap tm_wh;      // w_hat16 rows of this launch [classes, D], box 32 features x 32 classes, no swizzle
-    const float2* coef; float* dw; int64_t c0; int ld;
+    CoefSrc coef; float* dw; int64_t c0; int ld;
     B200F_PROBE_FIELD                   // probe builds only: 1 = no w_hat loads, 2 = no dW stores (WRONG results)
   };
-  struct State { float2 cf, cf_next; int64_t next_row; int seq, n_seq, row0, row_step; bool row_ok; };
+  struct State { float2 cf, cf_next; int64_t next_row; float inv_sg; int seq, n_seq, row0, row_step; bool row_ok; };
 
   // slice n of this warp's item = column slice (n % spt) of its (n / spt)-th tile; buffer n & 1
   static __device__ __forceinline__ void issue(const State& st, const Params& ep, const XwParams& p, const XwItem& it, int n) {
@@ -461,16 +400,17 @@ struct XwDwT {
     st.row0 = (p.reverse ? t_end - 1 : t_begin) * p.tn + it.rank * XW_WROWS + it.quad * 32;
     st.row_step = p.reverse ? -p.tn : p.tn;
     st.seq = 0; st.next_row = -1; st.row_ok = false;
+    st.inv_sg = ep.coef.inv_sg();
     issue(st, ep, p, it, 0);
     issue(st, ep, p, it, 1);
   }
   static __device__ __forceinline__ void tile_begin(State& st, const Params& ep, const XwParams& p, const XwItem& it) {
     st.row_ok = it.row < p.C;
     if (!st.row_ok) return;
-    st.cf = (st.next_row == it.row) ? st.cf_next : __ldg(ep.coef + ep.c0 + it.row);
+    st.cf = (st.next_row == it.row) ? st.cf_next : ep.coef.load(it.row, ep.c0 + it.row, st.inv_sg);
     const int64_t nr = it.row + st.row_step;                  // next tile's coefficients, one tile ahead
     st.next_row = -1;
-    if (nr >= 0 && nr < p.C) { st.next_row = nr; st.cf_next = __ldg(ep.coef + ep.c0 + nr); }
+    if (nr >= 0 && nr < p.C) { st.next_row = nr; st.cf_next = ep.coef.load(nr, ep.c0 + nr, st.inv_sg); }
   }
   static __device__ __forceinline__ void slice(State& st, const Params& ep, const XwParams& p, const XwItem& it,
                                                float (&v)[32], int col0, float*) {

@@ -23,7 +23,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib
-from ._lib import HeadCfg, check, dtype_code, ptr, require_cuda, stream_ptr
+from ._lib import HeadCfg, HookCfg, check, dtype_code, ptr, require_cuda, stream_ptr
 
 MAX_SCALE = 24.0        # face_models.py:403
 NORM_EPS = 1e-12        # face_models.py:351
@@ -122,19 +122,49 @@ def use_tcgen05(x: torch.Tensor, engine: int, wants_logits: bool = False) -> boo
     return engine == _lib.ENGINE_TCGEN05 or x.dtype == torch.bfloat16
 
 
-def _prepare_weight(w: torch.Tensor, f16n: bool, cache: Optional[dict]):
-    """K1 on the class weights; with a cache dict the result is reused until the tensor's version changes
-    (optimizer step / load_state_dict).  Training steps change it every step, so bench.py passes no cache."""
-    if cache is not None and f16n and "static" in cache:
-        return cache["static"]                    # operands an optimizer keeps current in place (optim.HeadAdamW)
-    key = (w.data_ptr(), w._version, tuple(w.shape), w.dtype, f16n)
-    if cache is not None and cache.get("key") == key:
+def _weight_key(w: torch.Tensor, f16n: bool):
+    return (w.data_ptr(), w._version, tuple(w.shape), w.dtype, f16n)
+
+
+def _cached_weight(w: torch.Tensor, f16n: bool, cache: Optional[dict]):
+    """K1(weight) from the cache, or None.  Reused until the tensor's version changes (optimizer step /
+    load_state_dict); "static" = operands an optimizer keeps current in place (optim.HeadAdamW)."""
+    if cache is None:
+        return None
+    if f16n and "static" in cache:
+        return cache["static"]
+    if cache.get("key") == _weight_key(w, f16n):
         return cache["val"]
+    return None
+
+
+def _prepare_weight(w: torch.Tensor, f16n: bool, cache: Optional[dict]):
+    """K1 on the class weights (cached when a cache dict is given: see _cached_weight)."""
+    val = _cached_weight(w, f16n, cache)
+    if val is not None:
+        return val
     with _lib.timed("l2norm_rows_w", w.device):
         val = _k1(w, f16n)
     if cache is not None:
-        cache["key"], cache["val"] = key, val
+        cache["key"], cache["val"] = _weight_key(w, f16n), val
     return val
+
+
+def _k1_pair(x: torch.Tensor, w: torch.Tensor, cache: Optional[dict]):
+    """K1 over the batch rows AND the class weights in one launch (tcgen05 operands; b200f_l2norm_rows_pair)."""
+    lib = _lib.load_library()
+    dev = x.device
+    xo = torch.empty(x.shape, dtype=torch.float16, device=dev)
+    wo = torch.empty(w.shape, dtype=torch.float16, device=dev)
+    inv_nx = torch.empty(x.shape[0], dtype=torch.float32, device=dev)
+    inv_nw = torch.empty(w.shape[0], dtype=torch.float32, device=dev)
+    with _lib.timed("l2norm_rows_w", dev):
+        check(lib.b200f_l2norm_rows_pair(ptr(x), x.shape[0], ptr(inv_nx), ptr(xo), ptr(w), w.shape[0], ptr(inv_nw), ptr(wo),
+                                         dtype_code(x), x.shape[1], NORM_EPS, _lib.F16N, OPERAND_SCALE, stream_ptr(dev)),
+              "b200f_l2norm_rows_pair")
+    if cache is not None:
+        cache["key"], cache["val"] = _weight_key(w, True), (wo, inv_nw)
+    return xo, inv_nx, wo, inv_nw
 
 
 def _check_head_inputs(x, w, label, dlogits=None):
@@ -159,7 +189,11 @@ def _check_head_inputs(x, w, label, dlogits=None):
         raise ValueError(f"head: dlogits must be a contiguous [B, C] = [{x.shape[0]}, {w.shape[0]}] tensor on {x.device}")
 
 
-def _fwd_kernels(x, w, label, cfg: HeadCfg, class_offset, want_logits, w_cache=None, nan_flag=None):
+def _fwd_kernels(x, w, label, cfg: HeadCfg, class_offset, want_logits, w_cache=None, nan_flag=None,
+                 fused_hook: Optional[HookCfg] = None):
+    """K1 (x and W) + K2.  fused_hook (an unsharded head that wants its loss): K2b and the hook scalars for an upstream
+    gradient of 1 come out of the same launch chain (b200f_arcface_fwd_loss); the tuple then ends with
+    (lse, loss, pq_norm2, out4)."""
     lib = _lib.load_library()
     _check_head_inputs(x, w, label)
     B, D = x.shape
@@ -168,8 +202,11 @@ def _fwd_kernels(x, w, label, cfg: HeadCfg, class_offset, want_logits, w_cache=N
     f16n = use_tcgen05(x, cfg.engine, want_logits)
     if not f16n and x.dtype != w.dtype:
         raise TypeError(f"CUDA-core engine: x ({x.dtype}) and weight ({w.dtype}) must share a dtype")
-    xo, inv_nx = _k1(x, f16n)
-    wo, inv_nw = _prepare_weight(w, f16n, w_cache)
+    if f16n and x.dtype == w.dtype and _cached_weight(w, f16n, w_cache) is None:
+        xo, inv_nx, wo, inv_nw = _k1_pair(x, w, w_cache)
+    else:
+        xo, inv_nx = _k1(x, f16n)
+        wo, inv_nw = _prepare_weight(w, f16n, w_cache)
     row_stats = torch.empty(B, _lib.STAT_COLS, dtype=torch.float32, device=dev)
     row_best = torch.empty(B, dtype=torch.float32, device=dev)
     row_argmax = torch.empty(B, dtype=torch.int64, device=dev)
@@ -179,6 +216,20 @@ def _fwd_kernels(x, w, label, cfg: HeadCfg, class_offset, want_logits, w_cache=N
     logits = torch.empty(B, C, dtype=torch.float32, device=dev) if want_logits else None
     nbytes = lib.b200f_head_workspace_bytes(B, C, D, dtype_code(xo), cfg.engine)
     ws = _lib.workspace(nbytes, dev, "head")
+    if fused_hook is not None:
+        lse = torch.empty(B, dtype=torch.float32, device=dev)
+        # separate outputs: the loss is returned as the kernel wrote it (a clone of one slot of a shared buffer was a
+        # copy node between the loss and the backward in every captured step)
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        pq_norm2 = torch.empty(1, dtype=torch.float32, device=dev)
+        out4 = torch.empty(4, dtype=torch.float32, device=dev)
+        with _lib.timed("arcface_fwd", dev):
+            check(lib.b200f_arcface_fwd_loss(ptr(xo), ptr(wo), dtype_code(xo), ptr(inv_nx), ptr(inv_nw), ptr(label), B, C,
+                                             int(class_offset), D, cfg, fused_hook, ptr(row_stats), ptr(row_best),
+                                             ptr(row_argmax), ptr(cos_minmax), ptr(nan_flag), ptr(lse), ptr(loss),
+                                             ptr(pq_norm2), ptr(out4), ptr(ws), ws.numel(), stream_ptr(dev)),
+                  "b200f_arcface_fwd_loss")
+        return xo, wo, inv_nx, inv_nw, row_stats, row_best, row_argmax, cos_minmax, nan_flag, logits, lse, loss, pq_norm2, out4
     with _lib.timed("arcface_fwd", dev):
         check(lib.b200f_arcface_fwd(ptr(xo), ptr(wo), dtype_code(xo), ptr(inv_nx), ptr(inv_nw), ptr(label), B, C,
                                     int(class_offset), D, cfg, ptr(row_stats), ptr(row_best), ptr(row_argmax),
@@ -187,7 +238,18 @@ def _fwd_kernels(x, w, label, cfg: HeadCfg, class_offset, want_logits, w_cache=N
     return xo, wo, inv_nx, inv_nw, row_stats, row_best, row_argmax, cos_minmax, nan_flag, logits
 
 
-def _bwd_kernels(xo, wo, label, inv_nx, inv_nw, lse, grad4, cfg: HeadCfg, class_offset, dlogits=None):
+def _raw_rows(x_raw, xo):
+    """(pointer, dtype code) of the rows the normalise-backward projects with: the raw input when the operand is K1's
+    fp16 copy of it, else nothing (the operand IS the raw input)."""
+    if x_raw is not None and x_raw is not xo and x_raw.dtype in (torch.float32, torch.bfloat16):
+        return ptr(x_raw), dtype_code(x_raw)
+    return None, 0
+
+
+def _bwd_kernels(xo, wo, label, inv_nx, inv_nw, lse, grad4, cfg: HeadCfg, class_offset, dlogits=None, finish_dx=False,
+                 x_raw=None, dx_bf16=False):
+    """K3.  finish_dx (unsharded head): dL/dx comes out of the same call (b200f_arcface_bwd_dx) -- returns
+    (dxhat, dw, dx, dx_lowp or None)."""
     lib = _lib.load_library()
     _check_head_inputs(xo, wo, label, dlogits)
     B, D = xo.shape
@@ -197,6 +259,16 @@ def _bwd_kernels(xo, wo, label, inv_nx, inv_nw, lse, grad4, cfg: HeadCfg, class_
     dw = torch.empty(C, D, dtype=torch.float32, device=dev)
     nbytes = lib.b200f_head_workspace_bytes(B, C, D, dtype_code(xo), cfg.engine)
     ws = _lib.workspace(nbytes, dev, "head")
+    if finish_dx:
+        dx = torch.empty(B, D, dtype=torch.float32, device=dev)
+        lowp = torch.empty(B, D, dtype=torch.bfloat16, device=dev) if dx_bf16 else None
+        rp, rd = _raw_rows(x_raw, xo)
+        with _lib.timed("arcface_bwd", dev):
+            check(lib.b200f_arcface_bwd_dx(ptr(xo), ptr(wo), dtype_code(xo), ptr(inv_nx), ptr(inv_nw), ptr(label), ptr(lse),
+                                           ptr(grad4), ptr(dlogits), (dlogits.shape[1] if dlogits is not None else 0),
+                                           B, C, int(class_offset), D, cfg, ptr(dxhat), ptr(dw), rp, rd, ptr(dx), ptr(lowp),
+                                           ptr(ws), ws.numel(), stream_ptr(dev)), "b200f_arcface_bwd_dx")
+        return dxhat, dw, dx, lowp
     with _lib.timed("arcface_bwd", dev):
         check(lib.b200f_arcface_bwd(ptr(xo), ptr(wo), dtype_code(xo), ptr(inv_nx), ptr(inv_nw), ptr(label), ptr(lse),
                                     ptr(grad4), ptr(dlogits), (dlogits.shape[1] if dlogits is not None else 0),
@@ -205,62 +277,84 @@ def _bwd_kernels(xo, wo, label, inv_nx, inv_nw, lse, grad4, cfg: HeadCfg, class_
     return dxhat, dw
 
 
-def _normalize_bwd(xo, inv_nx, dxhat):
+def _normalize_bwd(xo, inv_nx, dxhat, x_raw=None, dx_bf16=False):
+    """dL/dx = normalise-backward of dxhat, projected with the raw input rows when given (exact x_hat = x * inv_nx)
+    else with the operand rows.  dx_bf16: also return the rows rounded to bf16 -> (dx, dx_lowp)."""
     lib = _lib.load_library()
     dx = torch.empty_like(dxhat)
-    check(lib.b200f_l2norm_bwd(ptr(xo), dtype_code(xo), OPERAND_SCALE, ptr(inv_nx), ptr(dxhat), xo.shape[0],
-                               xo.shape[1], ptr(dx), stream_ptr(xo.device)), "b200f_l2norm_bwd")
-    return dx
+    lowp = torch.empty(dxhat.shape, dtype=torch.bfloat16, device=dxhat.device) if dx_bf16 else None
+    v = x_raw if (x_raw is not None and x_raw.dtype in (torch.float32, torch.bfloat16)) else xo
+    check(lib.b200f_l2norm_bwd(ptr(v), dtype_code(v), OPERAND_SCALE, ptr(inv_nx), ptr(dxhat), v.shape[0],
+                               v.shape[1], ptr(dx), ptr(lowp), stream_ptr(v.device)), "b200f_l2norm_bwd")
+    return (dx, lowp) if dx_bf16 else dx
 
 
 class _ArcFaceLossFn(torch.autograd.Function):
-    """loss = CE_labelsmooth(ArcMargin(x, w, y), y) fused: K1 + K2 (+ all-reduce) + K2b forward,
-    hook scalar + K3 (+ all-reduce) + normalise-backward in backward."""
+    """loss = CE_labelsmooth(ArcMargin(x, w, y), y) fused.
+    Unsharded: K1(x, W) -> K2 -> statistics + loss + hook scalars | K3a -> K3b -> K3c -> split reduction + dL/dx.
+    Class-sharded: ... K2 -> statistics -> all-reduce [B,4] -> loss + hook scalars | ... K3c -> split reduction ->
+    all-reduce [B,D] -> normalise-backward."""
 
     @staticmethod
     def forward(ctx, x, weight, w, label, cfg: HeadCfg, class_offset, group, hook: _Hook, stats: HeadStats,
-                w_cache):
+                w_cache, unit_upstream):
         # weight: the tensor autograd differentiates (fp32 master or already x.dtype);
         # w: what K1 reads (== weight, or a bf16 compute copy of it)
         ctx.w_dtype, ctx.x_dtype = weight.dtype, x.dtype
-        x, w, inv_nx, inv_nw, row_stats, row_best, row_argmax, cos_minmax, nan_flag, _ = _fwd_kernels(
-            x, w, label, cfg, class_offset, False, w_cache, stats.sticky_nan_flag)
-        if group is not None:
+        x_raw = x
+        hk = HookCfg(int(hook.enabled), float(hook.max_grad_norm), int(hook.phase), int(hook.epoch))
+        lib = _lib.load_library()
+        if group is None:
+            (x, w, inv_nx, inv_nw, row_stats, row_best, row_argmax, cos_minmax, nan_flag, _, lse, loss, pq_norm2,
+             out4) = _fwd_kernels(x, w, label, cfg, class_offset, False, w_cache, stats.sticky_nan_flag, fused_hook=hk)
+        else:
+            x, w, inv_nx, inv_nw, row_stats, row_best, row_argmax, cos_minmax, nan_flag, _ = _fwd_kernels(
+                x, w, label, cfg, class_offset, False, w_cache, stats.sticky_nan_flag)
             from . import parallel
             parallel.reduce_row_stats(row_stats, group)          # one SUM all-reduce of [B,4]
-        lib = _lib.load_library()
-        B = x.shape[0]
-        lse = torch.empty(B, dtype=torch.float32, device=x.device)
-        # two separate outputs: the loss is returned as the kernel wrote it (a clone of one slot of a shared buffer was
-        # a copy node between loss_kernel and the hook scalar in every captured step)
-        loss = torch.empty((), dtype=torch.float32, device=x.device)
-        pq_norm2 = torch.empty(1, dtype=torch.float32, device=x.device)
-        check(lib.b200f_arcface_loss(ptr(row_stats), B, cfg, ptr(lse), ptr(loss), ptr(pq_norm2),
-                                     stream_ptr(x.device)), "b200f_arcface_loss")
+            B = x.shape[0]
+            lse = torch.empty(B, dtype=torch.float32, device=x.device)
+            loss = torch.empty((), dtype=torch.float32, device=x.device)
+            pq_norm2 = torch.empty(1, dtype=torch.float32, device=x.device)
+            out4 = torch.empty(4, dtype=torch.float32, device=x.device)
+            check(lib.b200f_arcface_loss_hook(ptr(row_stats), B, cfg, hk, ptr(lse), ptr(loss), ptr(pq_norm2), ptr(out4),
+                                              stream_ptr(x.device)), "b200f_arcface_loss_hook")
         stats.row_best, stats.row_argmax = row_best, row_argmax
         stats.cos_minmax, stats.nan_flag, stats.lse = cos_minmax, nan_flag, lse
-        ctx.save_for_backward(x, w, label, inv_nx, inv_nw, lse, pq_norm2)
+        ctx.save_for_backward(x, w, label, inv_nx, inv_nw, lse, pq_norm2, out4, x_raw)
         ctx.cfg, ctx.class_offset, ctx.group, ctx.hook, ctx.stats = cfg, class_offset, group, hook, stats
+        ctx.unit_upstream = bool(unit_upstream)
         return loss
 
     @staticmethod
     def backward(ctx, grad_out):
-        x, w, label, inv_nx, inv_nw, lse, pq_norm2 = ctx.saved_tensors
+        x, w, label, inv_nx, inv_nw, lse, pq_norm2, out4, x_raw = ctx.saved_tensors
         cfg, hook = ctx.cfg, ctx.hook
         lib = _lib.load_library()
-        up = grad_out.to(torch.float32).contiguous()
-        out3 = torch.empty(4, dtype=torch.float32, device=x.device)
-        check(lib.b200f_arcface_hook_scale(ptr(pq_norm2), ptr(up), x.shape[0], cfg.s_eff, int(hook.enabled),
-                                           float(hook.max_grad_norm), int(hook.phase), int(hook.epoch),
-                                           ptr(out3), stream_ptr(x.device)), "b200f_arcface_hook_scale")
-        ctx.stats.hook_out = out3
-        dxhat, dw = _bwd_kernels(x, w, label, inv_nx, inv_nw, lse, out3, cfg, ctx.class_offset)
-        if ctx.group is not None:
+        if ctx.unit_upstream:
+            grad4 = out4                                         # the forward already formed the scalars for dL/dloss = 1
+        else:
+            up = grad_out.to(torch.float32).contiguous()
+            grad4 = torch.empty(4, dtype=torch.float32, device=x.device)
+            check(lib.b200f_arcface_hook_scale(ptr(pq_norm2), ptr(up), x.shape[0], cfg.s_eff, int(hook.enabled),
+                                               float(hook.max_grad_norm), int(hook.phase), int(hook.epoch),
+                                               ptr(grad4), stream_ptr(x.device)), "b200f_arcface_hook_scale")
+        ctx.stats.hook_out = grad4
+        want_bf16 = ctx.x_dtype == torch.bfloat16
+        if ctx.group is None:
+            _, dw, dx, lowp = _bwd_kernels(x, w, label, inv_nx, inv_nw, lse, grad4, cfg, ctx.class_offset, finish_dx=True,
+                                           x_raw=x_raw, dx_bf16=want_bf16)
+        else:
+            dxhat, dw = _bwd_kernels(x, w, label, inv_nx, inv_nw, lse, grad4, cfg, ctx.class_offset)
             from . import parallel
             parallel.reduce_dxhat(dxhat, ctx.group)              # one SUM all-reduce of [B,D]
-        dx = _normalize_bwd(x, inv_nx, dxhat)
+            if want_bf16:
+                dx, lowp = _normalize_bwd(x, inv_nx, dxhat, x_raw, dx_bf16=True)
+            else:
+                dx, lowp = _normalize_bwd(x, inv_nx, dxhat, x_raw), None
         ctx.stats.dx_f32 = dx
-        return dx.to(ctx.x_dtype), dw.to(ctx.w_dtype), None, None, None, None, None, None, None, None
+        gx = lowp if lowp is not None else dx.to(ctx.x_dtype)
+        return gx, dw.to(ctx.w_dtype), None, None, None, None, None, None, None, None, None
 
 
 class _ArcLogitsFn(torch.autograd.Function):
@@ -306,11 +400,15 @@ class _ArcLogitsFn(torch.autograd.Function):
 def arcface_loss(x, weight, label, *, m_eff, s_eff, label_smoothing=0.05, easy_margin=False,
                  class_offset=0, num_classes_total=None, group=None, hook: Optional[_Hook] = None,
                  stats: Optional[HeadStats] = None, engine=_lib.ENGINE_AUTO,
-                 compute_weight: Optional[torch.Tensor] = None, weight_cache: Optional[dict] = None):
+                 compute_weight: Optional[torch.Tensor] = None, weight_cache: Optional[dict] = None,
+                 unit_upstream: bool = False):
     """Functional fused head: mean label-smoothed CE of the ArcFace logits of (x, weight).
     x [B,D] fp32 / bf16 CUDA, weight [C_local,D] (the tensor that receives the gradient: an fp32 master
     keeps an fp32 dW even when the kernels compute in bf16), label [B] int64 global ids.
-    compute_weight: the copy of weight in x.dtype the kernels read (default: weight itself, or a cast)."""
+    compute_weight: the copy of weight in x.dtype the kernels read (default: weight itself, or a cast).
+    unit_upstream: the caller promises that backward's upstream gradient is exactly 1 (``loss.backward()`` of the bare
+    loss; GraphedHeadStep's static root gradient): the hook scalars the forward formed are used as they are and the
+    backward launches no scalar kernel."""
     require_cuda(x, weight, label, compute_weight)
     if compute_weight is None:
         if weight.dtype == x.dtype or use_tcgen05(x, engine):
@@ -321,7 +419,7 @@ def arcface_loss(x, weight, label, *, m_eff, s_eff, label_smoothing=0.05, easy_m
                     num_classes_total if num_classes_total is not None else weight.shape[0], engine)
     return _ArcFaceLossFn.apply(x.contiguous(), weight, compute_weight.contiguous(),
                                 label.contiguous().to(torch.int64), cfg, class_offset, group, hook or _Hook(),
-                                stats if stats is not None else HeadStats(), weight_cache)
+                                stats if stats is not None else HeadStats(), weight_cache, unit_upstream)
 
 
 class GraphedHeadStep:
@@ -339,6 +437,7 @@ class GraphedHeadStep:
         require_cuda(weight)
         dev = weight.device
         self.weight = weight
+        loss_kw = dict(loss_kw, unit_upstream=True)   # the root gradient below is the constant 1
         self.loss_kw = loss_kw
         self.x = torch.zeros(B, D, dtype=dtype, device=dev).requires_grad_(True)
         self.y = torch.zeros(B, dtype=torch.int64, device=dev)

@@ -94,6 +94,12 @@ int         b200f_has_tcgen05(void);
 int b200f_l2norm_rows(const void* in, int in_dtype, int64_t rows, int dim, float eps,
                       float* inv_norm, void* out_or_null, int out_dtype, float out_scale, void* stream);
 
+/* K1 over TWO row sets in one launch (the head's batch rows and class weights: saves the launch of the small set).
+ * Same arithmetic as two b200f_l2norm_rows calls with the shared in_dtype / dim / eps / out_dtype / out_scale. */
+int b200f_l2norm_rows_pair(const void* in0, int64_t rows0, float* inv0, void* out0,
+                           const void* in1, int64_t rows1, float* inv1, void* out1,
+                           int in_dtype, int dim, float eps, int out_dtype, float out_scale, void* stream);
+
 /* Bytes of workspace the head calls need for (B, C_local, D). */
 size_t b200f_head_workspace_bytes(int64_t B, int64_t C_local, int D, int dtype, int engine);
 
@@ -116,12 +122,38 @@ int b200f_arcface_fwd(const void* x, const void* w, int dtype,
                       float* logits_or_null, int64_t ld_logits,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* State of the ArcFaceNet backward hook (src/face_models.py:538-570) as its closure would read it at backward time. */
+typedef struct b200f_hook_cfg {
+  int32_t enabled;        /* 0 until the second training forward (the reference registers the hook after the first) */
+  float   max_grad_norm;  /* model.max_grad_norm (1.0)                                                      :544 */
+  int32_t phase;          /* 1 -> thr = min(0.5, max_grad_norm)                                             :546 */
+  int32_t epoch;          /* current_epoch: thr = min(thr, 0.5 + 0.05 epoch) while < 10                     :549 */
+} b200f_hook_cfg;
+
+/* K2 + K2b in one call for an UNSHARDED head (C_local == cfg->num_classes_total): everything b200f_arcface_fwd
+ * computes, and -- out of the last block of the statistics reduction, no extra launch on the tcgen05 engine -- what
+ * b200f_arcface_loss and b200f_arcface_hook_scale(upstream = NULL) would: lse [B], loss [1], pq_norm2 [1], out4 [4].
+ * A backward whose upstream gradient is the constant 1 (loss.backward()) can take out4 as its grad_scale directly. */
+int b200f_arcface_fwd_loss(const void* x, const void* w, int dtype,
+                           const float* inv_nx, const float* inv_nw, const int64_t* label,
+                           int64_t B, int64_t C_local, int64_t class_offset, int D,
+                           const b200f_head_cfg* cfg, const b200f_hook_cfg* hook,
+                           float* row_stats, float* row_best, int64_t* row_argmax,
+                           float* cos_minmax, int32_t* nan_flag,
+                           float* lse, float* loss, float* pq_norm2, float* out4,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
 /* K2b -- after the (optional) cross-shard SUM of row_stats: lse[i] = s_eff + log(sumexp_i),
  * loss = mean_i[ lse_i - (1-eps) z_target_i - (eps/C) sum_z_i ]  (CrossEntropyLoss with
  * label smoothing, mean reduction), pq_norm2 = sum_ij (p_ij - q_ij)^2  (the Frobenius norm the
  * ArcFaceNet hook clips on, src/face_models.py:541). */
 int b200f_arcface_loss(const float* row_stats, int64_t B, const b200f_head_cfg* cfg,
                        float* lse, float* loss, float* pq_norm2, void* stream);
+
+/* b200f_arcface_loss and b200f_arcface_hook_scale(upstream = NULL, i.e. 1) in ONE launch: the class-sharded forward
+ * calls it after the all-reduce of row_stats. */
+int b200f_arcface_loss_hook(const float* row_stats, int64_t B, const b200f_head_cfg* cfg, const b200f_hook_cfg* hook,
+                            float* lse, float* loss, float* pq_norm2, float* out4, void* stream);
 
 /* Hook scalar (src/face_models.py:538-567), on the device, no host sync:
  *   n = |upstream| * s_eff / B * sqrt(pq_norm2);  kappa = thr/(n+1e-8) if n > thr else 1
@@ -152,11 +184,29 @@ int b200f_arcface_bwd(const void* x, const void* w, int dtype,
                       float* dxhat, float* dw,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* K3 for an unsharded head, finished: b200f_arcface_bwd, then dL/dx = normalise-backward of dxhat (below) written to
+ * dx [B,D] fp32 and, optionally, as bf16 (the cast autograd applies for a bf16 input) -- on the tcgen05 engine inside
+ * the split reduction of dxhat when the call is one class chunk (no extra launch, no round trip of dxhat).
+ * x_raw_or_null: the RAW input rows (B200F_F32 / B200F_BF16) the projection should use, x_hat = x_raw * inv_nx;
+ * NULL = the operand rows x.  With B200F_F16N operands pass the raw rows: their fp16 copy carries a 2^-12 rounding
+ * that the projection of an embedding nearly parallel to its class centre amplifies (measured: dx error 9.8e-4 ->
+ * 3e-4 of the bf16 bar at cfg3).  inv_nx is required. */
+int b200f_arcface_bwd_dx(const void* x, const void* w, int dtype,
+                         const float* inv_nx, const float* inv_nw, const int64_t* label,
+                         const float* lse, const float* grad_scale,
+                         const float* dlogits_or_null, int64_t ld_dlogits,
+                         int64_t B, int64_t C_local, int64_t class_offset, int D,
+                         const b200f_head_cfg* cfg,
+                         float* dxhat, float* dw,
+                         const void* x_raw_or_null, int x_raw_dtype, float* dx, void* dx_bf16_or_null,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
 /* Normalise-backward for rows: dv = inv_n * (dvhat - vhat * <vhat, dvhat>), vhat = v * inv_n
- * (autograd of F.normalize, src/face_models.py:351,525).  dv fp32 [rows, dim].  With dtype B200F_F16N
- * v holds v_hat * v_scale already (v_scale ignored otherwise).  dv may alias dvhat. */
+ * (autograd of F.normalize, src/face_models.py:351,525).  dv fp32 [rows, dim]; dv_bf16_or_null: the same rows
+ * rounded to bf16.  With dtype B200F_F16N v holds v_hat * v_scale already (v_scale ignored otherwise).
+ * dv may alias dvhat. */
 int b200f_l2norm_bwd(const void* v, int dtype, float v_scale, const float* inv_norm, const float* dvhat,
-                     int64_t rows, int dim, float* dv, void* stream);
+                     int64_t rows, int dim, float* dv, void* dv_bf16_or_null, void* stream);
 
 /* K5 -- optimizer step of the class-weight rows: torch.optim.AdamW (amsgrad when vmax != NULL) exactly as the
  * reference trains the head (src/training.py:343-348; default betas (0.9, 0.999), eps 1e-8), after the optional
@@ -236,8 +286,8 @@ int b200f_umma_set_pair(int pair);
 /* pipeline probe: rowsum[b] += sum_c (x . w^T)[b,c] with a do-nothing epilogue (rowsum zeroed by the caller) */
 int b200f_umma_xw_probe(const void* x, const void* w, float* rowsum, int B, int C, int D, int pair, void* stream);
 /* Tunables for tests and bench sweeps: "pair" (1 | 2), "g_chunk_mb" (budget in MB of the fp16 logit-gradient buffer
- * per class chunk of the backward; default 112), "pdl" (0 | 1), "k3b_class_major" (0 | 1), "k3b_reverse" (0 | 1),
- * "xw_prefetch" (stages), "stage_events" (0 | 1), "epi_groups" (1 | 2: epilogue warp groups of K2 / K3a, default 2).
+ * per class chunk of the backward; default 112), "pdl" (0 | 1), "k3b_reverse" (0 | 1),
+ * "xw_prefetch" (tiles of the streamed operand pulled into L2 ahead of the TMA ring; default 2), "stage_events" (0 | 1), "epi_groups" (1 | 2: epilogue warp groups of K2 / K3a, default 2).
  * Returns the previous value, -1 for an unknown name.  Every setting computes the same results ("g_chunk_mb" changes the
  * workspace size: query b200f_head_workspace_bytes again after changing it).  The measurement probes that skip memory
  * traffic ("k3a_ablate" / "k3b_ablate", WRONG gradients) exist only in -DB200F_PROBES builds made by tools/: the
