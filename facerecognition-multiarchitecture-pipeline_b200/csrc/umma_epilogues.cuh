@@ -69,9 +69,16 @@ struct CoefSrc {
   __device__ __forceinline__ float inv_sg() const { return 1.0f / (S * __ldg(grad4 + 3)); }
   // c_chunk: class within the chunk, c_call: class within the call (= chunk offset + c_chunk)
   __device__ __forceinline__ float2 load(int64_t c_chunk, int64_t c_call, float inv_sg_v) const {
+    const float inw = __ldg(inv_nw + c_call);
     float s = 0.f;
-    for (int rb = 0; rb < n_rb; ++rb) s += __ldg(r_part + (int64_t)rb * ldr + c_chunk);
-    return make_float2(__ldg(inv_nw + c_call) * inv_sg_v, s);
+    int rb = 0;
+    for (; rb + 4 <= n_rb; rb += 4) {                       // four loads in flight, summed in ascending order
+      const float a = __ldg(r_part + (int64_t)rb * ldr + c_chunk), b = __ldg(r_part + (int64_t)(rb + 1) * ldr + c_chunk);
+      const float c = __ldg(r_part + (int64_t)(rb + 2) * ldr + c_chunk), d = __ldg(r_part + (int64_t)(rb + 3) * ldr + c_chunk);
+      s = (((s + a) + b) + c) + d;
+    }
+    for (; rb < n_rb; ++rb) s += __ldg(r_part + (int64_t)rb * ldr + c_chunk);
+    return make_float2(inw * inv_sg_v, s);
   }
 };
 

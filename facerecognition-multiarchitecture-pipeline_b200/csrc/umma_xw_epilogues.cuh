@@ -378,7 +378,7 @@ struct XwDwT {
     CoefSrc coef; float* dw; int64_t c0; int ld;
     B200F_PROBE_FIELD                   // probe builds only: 1 = no w_hat loads, 2 = no dW stores (WRONG results)
   };
-  struct State { float2 cf, cf_next; int64_t next_row; float inv_sg; int seq, n_seq, row0, row_step; bool row_ok; };
+  struct State { float2 cf; float rp_next[4]; float inw_next; int64_t next_row; float inv_sg; int seq, n_seq, row0, row_step; bool row_ok; };
 
   // slice n of this warp's item = column slice (n % spt) of its (n / spt)-th tile; buffer n & 1
   static __device__ __forceinline__ void issue(const State& st, const Params& ep, const XwParams& p, const XwItem& it, int n) {
@@ -407,10 +407,21 @@ struct XwDwT {
   static __device__ __forceinline__ void tile_begin(State& st, const Params& ep, const XwParams& p, const XwItem& it) {
     st.row_ok = it.row < p.C;
     if (!st.row_ok) return;
-    st.cf = (st.next_row == it.row) ? st.cf_next : ep.coef.load(it.row, ep.c0 + it.row, st.inv_sg);
-    const int64_t nr = it.row + st.row_step;                  // next tile's coefficients, one tile ahead
+    // this tile's coefficients were REQUESTED one tile ago (raw loads, consumed only here: the warp never waits for them
+    // in the middle of a tile; forming the sum where the loads are issued blocked it once per partial)
+    if (st.next_row == it.row)
+      st.cf = make_float2(st.inw_next * st.inv_sg, ((st.rp_next[0] + st.rp_next[1]) + st.rp_next[2]) + st.rp_next[3]);
+    else
+      st.cf = ep.coef.load(it.row, ep.c0 + it.row, st.inv_sg);
+    const int64_t nr = it.row + st.row_step;
     st.next_row = -1;
-    if (nr >= 0 && nr < p.C) { st.next_row = nr; st.cf_next = ep.coef.load(nr, ep.c0 + nr, st.inv_sg); }
+    if (nr >= 0 && nr < p.C && ep.coef.n_rb <= 4) {
+      st.next_row = nr;
+#pragma unroll
+      for (int rb = 0; rb < 4; ++rb)
+        st.rp_next[rb] = (rb < ep.coef.n_rb) ? __ldg(ep.coef.r_part + (int64_t)rb * ep.coef.ldr + nr) : 0.f;
+      st.inw_next = __ldg(ep.coef.inv_nw + ep.c0 + nr);
+    }
   }
   static __device__ __forceinline__ void slice(State& st, const Params& ep, const XwParams& p, const XwItem& it,
                                                float (&v)[32], int col0, float*) {

@@ -92,3 +92,39 @@ def gallery_vectorised(q: torch.Tensor, g: torch.Tensor, k: int, thresh: float):
     d = torch.cdist(q, g)
     score, idx = d.topk(k, dim=1, largest=False)
     return idx, score, score[:, 0] <= thresh
+
+
+class ArcFaceNetPort(torch.nn.Module):
+    """cfg1's model for the CPU timing arm: the reference ArcFaceNet (face_models.py:447-535) restated --
+    torchvision ResNet18 trunk (random init: the ImageNet weights cannot be downloaded offline; same FLOPs),
+    Linear(512,512,no bias) -> BatchNorm1d -> dropout(0.2, train) -> F.normalize -> ArcMarginProduct (HeadPort).
+    The backward hook (:538-570) rescales a [B,36] gradient: no measurable cost, left out of the timing port."""
+
+    def __init__(self, num_classes=36, dropout_rate=0.2, s=32.0, m=0.5):
+        super().__init__()
+        import torchvision.models as models
+        backbone = models.resnet18(weights=None)
+        self.features = torch.nn.Sequential(*list(backbone.children())[:-1])
+        self.embedding = torch.nn.Linear(512, 512, bias=False)
+        self.bn = torch.nn.BatchNorm1d(512, eps=1e-5)
+        self.dropout = torch.nn.Dropout(p=dropout_rate)
+        self.arcface = HeadPort(512, num_classes, s=s, m=m)
+        self.current_epoch = 0
+
+    def forward(self, x, labels):
+        x = self.features(x).view(x.size(0), -1)                              # :511-512
+        x = self.bn(self.embedding(x))                                        # :515-516
+        if self.training:
+            x = self.dropout(x)                                               # :519-520
+        emb = F.normalize(x, p=2, dim=1, eps=1e-12)                           # :524
+        self.arcface.current_epoch = self.current_epoch                       # :531
+        return self.arcface(emb, labels)                                      # :534
+
+
+def arcfacenet_train_step(model: ArcFaceNetPort, opt, x, y, label_smoothing=0.05):
+    """One full training step as src/training.py:505-546 drives it (zero_grad, forward, CE, backward, AdamW step)."""
+    opt.zero_grad()
+    loss = torch.nn.CrossEntropyLoss(label_smoothing=label_smoothing)(model(x, y), y)
+    loss.backward()
+    opt.step()
+    return loss.detach()
