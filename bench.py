@@ -121,19 +121,43 @@ def claim_stdout():
     return real
 
 
-def synth_head(B, C_local, D, rank_seed, dev, c_lo, C_total):
-    """SURVEY 8d recipe: x ~ N(0,1) -> bf16, W xavier_normal(gain sqrt2) -> bf16 compute copy,
-    y ~ U{0..C-1}; 12.5 % of the rows planted near their class centre so the margin is exercised."""
+W_BLOCK = 4096
+
+
+def synth_w_rows(lo, hi, C_total, D, dev, seed=4321):
+    """Rows [lo, hi) of THE class-weight matrix of the run: xavier_normal(gain sqrt 2) of the full [C_total, D] matrix
+    (SURVEY 8d), bf16, drawn block by block from generators seeded with (seed, block) -- every world size sees the same
+    matrix (losses of the N = 1, 2, 4, 8 lines are comparable), any rank can materialise any row."""
+    std = (2.0 ** 0.5) * (2.0 / (C_total + D)) ** 0.5
+    out = torch.empty(hi - lo, D, dtype=torch.bfloat16, device=dev)
+    b = lo // W_BLOCK
+    while b * W_BLOCK < hi:
+        r0, r1 = b * W_BLOCK, min((b + 1) * W_BLOCK, C_total)
+        g = torch.Generator(device=dev).manual_seed(seed * 1_000_003 + b)
+        blk = (torch.randn(r1 - r0, D, generator=g, device=dev) * std).to(torch.bfloat16)
+        s0, s1 = max(r0, lo), min(r1, hi)
+        out[s0 - lo:s1 - lo] = blk[s0 - r0:s1 - r0]
+        b += 1
+    return out
+
+
+def synth_head(B, C_total, D, dev, lo, hi):
+    """SURVEY 8d recipe: x ~ N(0,1) -> bf16, W xavier_normal(gain sqrt2) -> bf16 compute copy, y ~ U{0..C-1}; 12.5 % of
+    the rows planted near their class centre (cos ~ 0.95) so that the margin is exercised.  x and y are the same on every
+    rank; w = rows [lo, hi) of the global matrix."""
     g = torch.Generator(device=dev).manual_seed(1234)
     std = (2.0 ** 0.5) * (2.0 / (C_total + D)) ** 0.5
-    gw = torch.Generator(device=dev).manual_seed(4321 + rank_seed)
-    w = (torch.randn(C_local, D, generator=gw, device=dev) * std).to(torch.bfloat16)
     x = torch.randn(B, D, generator=g, device=dev)
     y = torch.randint(0, C_total, (B,), generator=g, device=dev)
-    if C_local == C_total:                        # single shard: plant rows near their own class centre
-        n = B // 8
-        x[:n] = 3.0 * w[y[:n]].float() + 0.3 * std * torch.randn(n, D, generator=g, device=dev)
-    return x.to(torch.bfloat16), w, y
+    n = B // 8
+    centres = torch.cat([synth_w_rows(int(c), int(c) + 1, C_total, D, dev) for c in y[:n].tolist()]).float()
+    x[:n] = 3.0 * centres + 1.0 * std * torch.randn(n, D, generator=g, device=dev)
+    return x.to(torch.bfloat16), synth_w_rows(lo, hi, C_total, D, dev), y
+
+
+def rel_err(a, b):
+    a = a.double().flatten(); b = b.double().flatten()
+    return float((a - b).norm() / b.norm())
 
 
 def engine_code(name):
@@ -171,12 +195,27 @@ def run_b200(args):
     B, C_total, D = cfgw["B"], cfgw["C"], cfgw["D"]
     c_lo, c_hi = parallel.shard_bounds(C_total, world, rank)
     C_local = c_hi - c_lo
-    x, w, y = synth_head(B, C_local, D, rank, dev, c_lo, C_total)
-    w_master = w.float().requires_grad_(True)        # fp32 master receives the fp32 dW; kernels read the bf16 copy
     mf, sf = head_schedule(EPOCH, 10, True, True, 0.0, 0.3)
     m_eff, s_eff = effective_margin_scale(32.0, 0.5, mf, sf, True)
     eng = engine_code(args.engine)
     use_graph = not args.eager
+
+    def sync_all():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # ---- N > 1 first: (1) sharded-vs-unsharded parity on a reduced class count, (2) cfg4 UNSHARDED on rank 0 = the
+    # 1-GPU anchor of the scaling line, measured in this job (same box, same clocks)
+    parity, anchor = None, None
+    if world > 1:
+        parity = parity_sharded(dev, world, rank, group, eng, not args.no_cpu_baseline)
+        sync_all()
+        if rank == 0 and not args.no_cfg4:
+            anchor = bench_cfg4_single_gpu(dev, eng, m_eff, s_eff, steps=5)
+        sync_all()
+    x, w, y = synth_head(B, C_total, D, dev, c_lo, c_hi)
+    w_master = w.float().requires_grad_(True)        # fp32 master receives the fp32 dW; kernels read the bf16 copy
     loss_kw = dict(compute_weight=w, m_eff=m_eff, s_eff=s_eff, label_smoothing=LS, class_offset=c_lo,
                    num_classes_total=C_total, group=group, engine=eng)
 
@@ -186,11 +225,6 @@ def run_b200(args):
         loss = arcface_loss(xin, w_master, yin, **loss_kw)
         loss.backward()
         return loss
-
-    def sync_all():
-        if world > 1:
-            torch.distributed.barrier()
-        torch.cuda.synchronize()
 
     launches_per_step = None
     if use_graph:
@@ -246,26 +280,31 @@ def run_b200(args):
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     loss_val = float(loss.detach())
     # ---- timed region 2: end to end through the public API, host buffers ------------------------
+    # the public modules: ArcMarginProduct on one GPU, parallel.ShardedArcMarginProduct (class-parallel) on several
     xh = x.cpu().pin_memory(); yh = y.cpu().pin_memory()
-    head = b200face.ArcMarginProduct(D, C_local) if world == 1 else None
-    if head is not None:
-        head = head.to(dev); head.update_epoch(EPOCH); head.train(); head.engine = eng
-        head.compute_dtype = torch.bfloat16
-        head.cache_weight_prep = False                                # training changes W every step: K1(W) is timed
-        with torch.no_grad():
-            head.weight.copy_(w.float())
-        api_step = head.graphed_step(B, LS, torch.bfloat16) if use_graph else None
+    if use_graph:
+        gstep.close()                                                 # frees the first graph's buffers (and its NCCL nodes)
+        del gstep
+    if world == 1:
+        head = b200face.ArcMarginProduct(D, C_local).to(dev)
+    else:
+        head = parallel.ShardedArcMarginProduct(D, C_total, group=group).to(dev)
+    head.update_epoch(EPOCH); head.train()
+    hl = head if world == 1 else head.local
+    hl.engine = eng
+    hl.compute_dtype = torch.bfloat16
+    hl.cache_weight_prep = False                                      # training changes W every step: K1(W) is timed
+    with torch.no_grad():
+        hl.weight.copy_(w.float())
+    api_step = head.graphed_step(B, LS, torch.bfloat16) if use_graph else None
     def e2e_step():
         if use_graph:
-            l = api_step(xh, yh) if head is not None else gstep(xh, yh)  # H2D into the static buffers, then replay
+            l = api_step(xh, yh)                                      # H2D into the static buffers, then replay
         else:
             xd = xh.to(dev, non_blocking=True); yd = yh.to(dev, non_blocking=True)
-            if head is not None:
-                head.zero_grad(set_to_none=True)
-                l = head.forward_loss(xd.requires_grad_(True), yd, LS)
-                l.backward()
-            else:
-                l = eager_step(xd, yd)
+            hl.zero_grad(set_to_none=True)
+            l = head.forward_loss(xd.requires_grad_(True), yd, LS)
+            l.backward()
         return l
     # The loss of EVERY step is read back to the host, through pinned memory with a one-step lag: the D2H copy of
     # step i is enqueued behind it and read while step i+1 runs, so the host never idles the GPU (a training loop
@@ -295,10 +334,12 @@ def run_b200(args):
     if world > 1:
         torch.distributed.all_reduce(ms2, op=torch.distributed.ReduceOp.MAX)
     e2e_val = B * args.steps / (float(ms2) * 1e-3)
+    e2e_loss = losses_read[-1]
+    if use_graph:
+        api_step.close()
     gal_sharded = None
     if world > 1 and not args.no_gallery:
-        del gstep
-        gal_sharded = bench_gallery_sharded(dev, world, rank, group, eng, sync_all)
+        gal_sharded = bench_gallery_sharded(dev, world, rank, group, eng, sync_all, peaks())
 
     if rank != 0:
         finish(world)
@@ -367,12 +408,20 @@ def run_b200(args):
         "roofline": roof,
         "roofline_all": {k: {kk: v[kk] for kk in ("bound", "achieved", "peak", "unit", "frac", "avg_launch_ms")} for k, v in roofs.items()},
         "kernel_ms": {k: round(v, 4) for k, v in kern.items()},
-        "loss": round(loss_val, 5),
+        "loss": round(loss_val, 5), "e2e_loss": round(e2e_loss, 5),
     }
+    if anchor is not None:
+        # the driver's efficiency formula divides by the N = 1 LINE, which is cfg3 (another workload): this is cfg4 against
+        # cfg4 on one GPU, measured by rank 0 of this very job before the sharded run
+        out["anchor_1gpu_ms"] = anchor["ms_per_step"]
+        out["anchor_1gpu"] = anchor
+        out["efficiency_vs_cfg4_1gpu"] = round(anchor["ms_per_step"] / (world * ms_burst), 4)
+        out["efficiency_vs_cfg4_1gpu_sustained"] = round(anchor["ms_per_step"] / (world * ms_total / args.steps), 4)
+    if parity is not None:
+        out["parity"] = parity
     if world == 1 and not args.no_train_step and use_graph and H.use_tcgen05(x, eng):
         out["train_step"] = bench_train_step(dev, pk, eng, w, x, y)
     if world == 1 and not args.no_cfg4 and use_graph and H.use_tcgen05(x, eng):
-        del gstep
         torch.cuda.empty_cache()
         out["cfg4_single_gpu"] = bench_cfg4_single_gpu(dev, eng, m_eff, s_eff)
     out["scaling_note"] = ("N = 1 runs cfg3 (100k classes, batch 512) and N >= 2 run cfg4 (1M classes class-sharded, batch 4096), "
@@ -382,18 +431,78 @@ def run_b200(args):
     if world > 1 and gal_sharded is not None:
         out["gallery"] = gal_sharded
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_head_baseline(CFG3)
+        # CPU arm on the SAME inputs as the GPU arm: its first step is also the parity reference of this line
+        gpu_out = public_api_step(hl, x, y)
+        out["cpu_baseline"], cpu_out = cpu_head_baseline(CFG3, x.cpu(), w.cpu(), y.cpu())
+        out["parity"] = {"what": "this line's GPU step (ArcMarginProduct.forward_loss + backward, tcgen05 engine) against the CPU "
+                                 "port of the reference (fp32) on the identical bf16-rounded x, W, y",
+                         "loss_rel": abs(gpu_out[0] - cpu_out[0]) / abs(cpu_out[0]),
+                         "dx_rel": rel_err(gpu_out[1], cpu_out[1]), "dw_rel": rel_err(gpu_out[2], cpu_out[2]),
+                         "loss_gpu": gpu_out[0], "loss_cpu": cpu_out[0], "tolerance": 1e-3,
+                         "graph_replay_loss": round(loss_val, 6)}
+        del gpu_out, cpu_out
+        if not args.no_gallery:
+            out.setdefault("gallery", {})["cpu_baseline"] = cpu_gallery_baselines()
+        out["cfg1_cpu"] = cpu_cfg1_baseline()
     print(json.dumps(out), file=result_out, flush=True)
     finish(world)
 
 
 def finish(world):
-    """Leave without tearing NCCL down: destroying the process group while captured CUDA graphs still hold NCCL
-    kernels can block forever (seen on 2 GPUs).  Everything is already printed and flushed."""
+    """Every captured graph has been closed by now (GraphedHeadStep.close releases the NCCL kernels it holds), so the
+    process group can be torn down normally."""
     if world > 1:
         torch.cuda.synchronize()
-        sys.stdout.flush(); sys.stderr.flush()
-        os._exit(0)
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+def public_api_step(head, x, y):
+    """One eager step through the public module on device tensors -> (loss, dx fp32, dW) on the CPU."""
+    head.zero_grad(set_to_none=True)
+    xg = x.detach().clone().requires_grad_(True)
+    loss = head.forward_loss(xg, y, LS)
+    loss.backward()
+    torch.cuda.synchronize()
+    return float(loss), head.last_stats.dx_f32.cpu(), head.weight.grad.cpu()
+
+
+def parity_sharded(dev, world, rank, group, eng, with_cpu):
+    """N > 1: the class-parallel head across the REAL NCCL ranks against (a) the unsharded head on rank 0's GPU and (b) the
+    CPU port of the reference, on a reduced class count (B = 4096 x C = 8192 per rank) so that both references finish
+    in seconds.  Every rank takes part; rank 0 returns the record."""
+    import b200face
+    from b200face import parallel
+    B, D = CFG4["B"], CFG4["D"]
+    C = 8192 * world
+    lo, hi = parallel.shard_bounds(C, world, rank)
+    x, w, y = synth_head(B, C, D, dev, lo, hi)
+    sh = parallel.ShardedArcMarginProduct(D, C, group=group).to(dev)
+    sh.update_epoch(EPOCH); sh.train(); sh.local.engine = eng; sh.local.compute_dtype = torch.bfloat16
+    with torch.no_grad():
+        sh.local.weight.copy_(w.float())
+    l_s, dx_s, dw_s = public_api_step(sh.local, x, y)
+    full_w = sh.gather_weight()                                # the reference's [C, D] layout (all ranks take part)
+    rec = None
+    if rank == 0:
+        full = b200face.ArcMarginProduct(D, C).to(dev)
+        full.update_epoch(EPOCH); full.train(); full.engine = eng; full.compute_dtype = torch.bfloat16
+        full.load_state_dict({"weight": full_w, "u": torch.zeros(1)}, strict=True)
+        l_u, dx_u, dw_u = public_api_step(full, x, y)
+        rec = {"what": f"class-parallel head over {world} NCCL ranks vs the unsharded head on one GPU vs the CPU port; "
+                       f"B = {B}, C = {C} ({hi - lo} per rank), D = {D}, same seeded bf16 inputs",
+               "sharded_vs_unsharded": {"loss_rel": abs(l_s - l_u) / abs(l_u), "dx_rel": rel_err(dx_s, dx_u),
+                                        "dw_rel_rank0_rows": rel_err(dw_s, dw_u[lo:hi])},
+               "loss_sharded": l_s, "loss_unsharded": l_u, "tolerance": 1e-3}
+        if with_cpu:
+            _, cpu = cpu_head_baseline(dict(B=B, C=C, D=D), x.cpu(), full_w.cpu().bfloat16(), y.cpu(), budget_s=0.0)
+            rec["sharded_vs_cpu_port"] = {"loss_rel": abs(l_s - cpu[0]) / abs(cpu[0]), "dx_rel": rel_err(dx_s, cpu[1]),
+                                          "dw_rel_rank0_rows": rel_err(dw_s, cpu[2][lo:hi])}
+            rec["loss_cpu"] = cpu[0]
+        del full
+    del sh, full_w
+    torch.cuda.empty_cache()
+    return rec
 
 
 def time_stages(H, _lib, x, w, y, m_eff, s_eff, c_lo, C_total, eng, dev, reps=10):
@@ -450,12 +559,12 @@ def load_traffic(kernel):
     return None
 
 
-def bench_cfg4_single_gpu(dev, eng, m_eff, s_eff):
+def bench_cfg4_single_gpu(dev, eng, m_eff, s_eff, steps=20):
     """cfg4 (1 M classes, batch 4096) on ONE GPU: the 1-GPU anchor of the class-parallel scaling line (the N = 1 bench
-    line itself is cfg3, as BASELINE.json's configs prescribe).  20 graph replays after 3, device-resident inputs."""
+    line itself is cfg3, as BASELINE.json's configs prescribe).  `steps` graph replays after 3, device-resident inputs."""
     from b200face.head import GraphedHeadStep
     c = CFG4
-    x, w, y = synth_head(c["B"], c["C"], c["D"], 0, dev, 0, c["C"])
+    x, w, y = synth_head(c["B"], c["C"], c["D"], dev, 0, c["C"])
     w_master = w.float().requires_grad_(True)
     g = GraphedHeadStep(w_master, c["B"], c["D"], dtype=torch.bfloat16, warmup=1, compute_weight=w, m_eff=m_eff, s_eff=s_eff,
                         label_smoothing=LS, class_offset=0, num_classes_total=c["C"], group=None, engine=eng)
@@ -464,15 +573,19 @@ def bench_cfg4_single_gpu(dev, eng, m_eff, s_eff):
         g.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n = 20
+    n = steps
     e0.record()
     for _ in range(n):
-        g.replay()
+        loss = g.replay()
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
-    return {"workload": "cfg4 on 1 GPU: ArcFace head 512-d, 1M classes (unsharded), batch 4096, bf16 fwd+bwd",
-            "ms_per_step": round(ms, 4), "value": round(c["B"] / (ms * 1e-3), 1), "unit": "samples/s", "steps": n,
-            "algorithmic_tflops": round(6.0 * c["B"] * c["C"] * c["D"] / (ms * 1e-3) / 1e12, 1)}
+    out = {"workload": "cfg4 on 1 GPU: ArcFace head 512-d, 1M classes (unsharded), batch 4096, bf16 fwd+bwd",
+           "ms_per_step": round(ms, 4), "value": round(c["B"] / (ms * 1e-3), 1), "unit": "samples/s", "steps": n,
+           "algorithmic_tflops": round(6.0 * c["B"] * c["C"] * c["D"] / (ms * 1e-3) / 1e12, 1), "loss": round(float(loss), 5)}
+    g.close()
+    del g, w_master, w, x
+    torch.cuda.empty_cache()
+    return out
 
 
 def bench_train_step(dev, pk, eng, w_bf16, x, y):
@@ -624,7 +737,7 @@ def bench_gallery(dev, pk, eng):
     return res
 
 
-def bench_gallery_sharded(dev, world, rank, group, eng, sync_all):
+def bench_gallery_sharded(dev, world, rank, group, eng, sync_all, pk):
     """cfg5: 1M x 512 gallery rows split contiguously over the ranks, 8192 queries on every rank, top-5:
     per-shard tensor-engine top-k (exact), ONE all-gather of [Q,5] x 12 B per rank, merge (lowest global index wins
     ties).  Device time, max over ranks."""
@@ -654,45 +767,120 @@ def bench_gallery_sharded(dev, world, rank, group, eng, sync_all):
     ms = torch.tensor([e0.elapsed_time(e1) / reps], device=dev)
     torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
     ms = float(ms)
+    tf = 2.0 * c["Q"] * c["N"] * c["D"] / (ms * 1e-3) / 1e12
     return {"cfg5": {"queries_per_sec": round(c["Q"] / (ms * 1e-3), 1), "ms": round(ms, 4), "Q": c["Q"], "N_total": c["N"],
                      "N_per_rank": hi - lo, "k": c["k"],
-                     "algorithmic_tflops": round(2.0 * c["Q"] * c["N"] * c["D"] / (ms * 1e-3) / 1e12, 2),
+                     "algorithmic_tflops": round(tf, 2),
+                     "roofline": {"bound": "tensor", "achieved": round(tf, 2), "peak": pk["tf_burst"] * world, "unit": "TFLOP/s",
+                                  "frac": round(tf / (pk["tf_burst"] * world), 4),
+                                  "note": "Q = 8192 is tensor-bound (intensity 2Q/2 B = 8192 FLOP/B): 2 Q N D against the "
+                                          "burst bf16 peak of the N GPUs; the HBM-bound regime is stream_q128_n1m on the N = 1 line"},
                      "comm": "one all-gather of [Q,k] (score fp32, index int64) per rank + merge kernel"}}
 
 
-def cpu_head_baseline(c, budget_s=20.0):
-    """The reference algorithm on this box's host cores (oracle/torch_port.py, kind 'port': the
-    reference is pure Python and is not on the GPU box).  Bounded: full cfg3 steps until ~budget_s."""
+def cpu_head_baseline(c, x, w, y, budget_s=20.0):
+    """The reference algorithm on this box's host cores (oracle/torch_port.py, kind 'port': the reference is pure Python
+    and is not on the GPU box), on the SAME x / W / y as the GPU arm.  Bounded: full steps until ~budget_s.
+    Returns (cpu_baseline record, (loss, dx, dW) of the first step: the parity reference)."""
     from oracle import torch_port
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    g = torch.Generator().manual_seed(1234)
     head = torch_port.HeadPort(c["D"], c["C"])
     head.current_epoch = EPOCH
     head.train()
-    x = torch.randn(c["B"], c["D"], generator=g)
-    y = torch.randint(0, c["C"], (c["B"],), generator=g)
-    torch_port.head_step(head, x, y, LS)                     # warm-up
+    with torch.no_grad():
+        head.weight.copy_(w.float())
+    xf = x.float()
+    loss, dx, dw = torch_port.head_step(head, xf, y, LS)     # warm-up = the parity reference
+    first = (float(loss), dx.clone(), dw.clone())
     t0 = time.time(); n = 0
-    while True:
-        torch_port.head_step(head, x, y, LS); n += 1
+    while budget_s > 0:
+        torch_port.head_step(head, xf, y, LS); n += 1
         if time.time() - t0 > budget_s or n >= 10:
             break
+    if n == 0:
+        return None, first
     dt = (time.time() - t0) / n
-    return {"value": round(c["B"] / dt, 1), "unit": "samples/s", "cores": threads, "kind": "port",
-            "sample": f"{n} full cfg3 head steps (B={c['B']}, C={c['C']}, fp32 torch CPU, fwd+bwd), {dt:.2f} s each"}
+    rec = {"value": round(c["B"] / dt, 1), "unit": "samples/s", "cores": threads, "kind": "port",
+           "sample": f"{n} full cfg3 head steps (B={c['B']}, C={c['C']}, fp32 torch CPU, fwd+bwd, the GPU arm's inputs), {dt:.2f} s each"}
+    return rec, first
+
+
+def cpu_gallery_baselines():
+    """SURVEY 8d / BASELINE.md 4.2: (i) the reference's own compare_faces loop (src/app.py:50-64: one F.pairwise_distance
+    + .item() per reference, a Python loop, 1 thread by construction) and (ii) the vectorised stand-in the north star
+    names, torch.cdist + topk on all cores -- for cfg2 and for ONE rank's shard of cfg5 (125 k rows; the whole of cfg5 is
+    8 such shards).  Bounded samples, stated."""
+    from oracle import torch_port
+    threads = os.cpu_count() or 1
+    g = torch.Generator().manual_seed(1234)
+    out = {"cores": threads, "kind": "port"}
+    for name, N, Qv, nq_loop, k in (("cfg2", CFG2["N"], CFG2["Q"], 8, 1), ("cfg5_one_shard_of_8", CFG5["N"] // 8, 2048, 2, 5)):
+        G = torch.nn.functional.normalize(torch.randn(N, 512, generator=g), dim=1)
+        Q = torch.nn.functional.normalize(torch.randn(Qv, 512, generator=g), dim=1)
+        refs = [{"name": str(i), "embedding": G[i:i + 1]} for i in range(N)]
+        torch.set_num_threads(1)
+        t0 = time.time()
+        for i in range(nq_loop):
+            torch_port.compare_faces_loop(Q[i:i + 1], refs, 1.0)
+        t_loop = (time.time() - t0) / nq_loop
+        torch.set_num_threads(threads)
+        torch_port.gallery_vectorised(Q[:64], G, k, 1.0)
+        t0 = time.time()
+        torch_port.gallery_vectorised(Q, G, k, 1.0)
+        t_vec = time.time() - t0
+        out[name] = {"compare_faces_loop_queries_per_sec": round(1.0 / t_loop, 2), "loop_threads": 1,
+                     "loop_sample": f"{nq_loop} queries x {N} references, verbatim Python loop",
+                     "cdist_topk_queries_per_sec": round(Qv / t_vec, 1), "cdist_threads": threads,
+                     "cdist_sample": f"one call, {Qv} queries x {N} rows, top-{k}"}
+        del refs, G, Q
+    out["cfg5_note"] = "cfg5 = 8 shards of 125 k rows: whole-gallery CPU throughput is 1/8 of the per-shard figures (extrapolated)"
+    return out
+
+
+def cpu_cfg1_baseline(steps=4):
+    """cfg1, the reference's own CPU-runnable case: ResNet18 + ArcFace head, 36 classes, 512-d, batch 32, 224 x 224, one
+    full training step (forward, CE with label smoothing 0.05, backward, AdamW-amsgrad) -- oracle/torch_port.ArcFaceNetPort
+    (random-init trunk: the ImageNet weights cannot be downloaded; same FLOPs) -- and the head alone at that shape."""
+    from oracle import torch_port
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    m = torch_port.ArcFaceNetPort(36).train()
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-3, weight_decay=1e-4, amsgrad=True)
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(32, 3, 224, 224, generator=g); y = torch.randint(0, 36, (32,), generator=g)
+    torch_port.arcfacenet_train_step(m, opt, x, y)
+    t0 = time.time()
+    for _ in range(steps):
+        torch_port.arcfacenet_train_step(m, opt, x, y)
+    dt = (time.time() - t0) / steps
+    head = torch_port.HeadPort(512, 36).train()
+    emb = torch.randn(32, 512, generator=g)
+    torch_port.head_step(head, emb, y, LS)
+    t0 = time.time()
+    for _ in range(50):
+        torch_port.head_step(head, emb, y, LS)
+    dth = (time.time() - t0) / 50
+    return {"workload": "cfg1: ResNet18 + ArcFace head, 36 classes, 512-d, batch 32, 224x224, full train step on CPU (port)",
+            "samples_per_sec": round(32 / dt, 2), "ms_per_step": round(dt * 1e3, 1), "steps": steps, "cores": threads, "kind": "port",
+            "head_only_ms": round(dth * 1e3, 3), "head_only_samples_per_sec": round(32 / dth, 1),
+            "head_share_of_step": round(dth / dt, 5)}
 
 
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (torch port of
-    src/face_models.py:334-429 + CrossEntropyLoss + autograd), all host threads, cfg3."""
+    src/face_models.py:334-429 + CrossEntropyLoss + autograd), all host threads.
+    N = 1: cfg3 as is.  N > 1: the b200 arm runs cfg4 (1 M classes, batch 4096); the CPU arm times ONE of its 8 class
+    shards at the FULL batch (B = 4096 x C = 125 000: like-for-like per row and per class) and reports
+    samples/s of the whole of cfg4 as 4096 / (8 x shard time) -- an extrapolation, labelled as such."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import torch_port
-    # N = 1: cfg3 as is.  N > 1: the b200 arm runs cfg4 (1 M classes, batch 4096), whose [B, C] fp32 logits alone are
-    # 16 GB on the host: the bounded sample is 128 of the 4096 rows against all 1 M classes (samples/s = rows / time).
-    c = dict(CFG3) if args.gpus <= 1 else dict(CFG4, B=128)
+    multi = args.gpus > 1
+    c = dict(CFG3) if not multi else dict(CFG4, C=CFG4["C"] // 8)
+    shards = 8 if multi else 1
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     g = torch.Generator().manual_seed(1234)
@@ -703,27 +891,27 @@ def run_reference(args):
     y = torch.randint(0, c["C"], (c["B"],), generator=g)
     # bounded: the whole run must end within a few minutes whatever K is asked
     t0 = time.time(); torch_port.head_step(head, x, y, LS); probe = time.time() - t0
-    steps = max(1, min(args.steps, int(150.0 / max(probe, 1e-3))))
-    warm = max(0, min(args.warmup, int(30.0 / max(probe, 1e-3)) ))
+    steps = max(1, min(args.steps, int(120.0 / max(probe, 1e-3))))
+    warm = max(0, min(args.warmup, int(30.0 / max(probe, 1e-3))))
     for _ in range(warm):
         torch_port.head_step(head, x, y, LS)
     t0 = time.time()
     for _ in range(steps):
         loss, _, _ = torch_port.head_step(head, x, y, LS)
-    dt = time.time() - t0
-    val = c["B"] * steps / dt
-    name = "cfg3" if args.gpus <= 1 else "cfg4"
+    dt = (time.time() - t0) / steps
+    val = c["B"] / (dt * shards)
     sample = (f"{steps} full cfg3 head steps (B={c['B']}, C={c['C']}, fp32, fwd+bwd) of the reference algorithm on CPU"
-              if args.gpus <= 1 else
-              f"{steps} steps of {c['B']} of cfg4's 4096 batch rows against all {c['C']} classes (fp32, fwd+bwd incl. the full dW) "
-              f"of the reference algorithm on CPU")
+              if not multi else
+              f"{steps} steps of ONE of cfg4's 8 class shards at the full batch (B={c['B']}, C={c['C']}, fp32, fwd+bwd), {dt:.2f} s each; "
+              f"value = {c['B']} / (8 x that): the whole of cfg4 extrapolated from one shard")
     print(json.dumps({
         "impl": "reference", "metric": "arcface_head_samples_per_sec", "value": round(val, 1), "unit": "samples/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": warm + 1, "ms_per_step": round(dt / steps * 1e3, 2),
-        "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": ("cfg3: ArcFace head 512-d, 100k classes, batch 512 fwd+bwd (reference CPU path)" if args.gpus <= 1 else
-                                "cfg4: ArcFace head 512-d, 1M classes, batch 4096 fwd+bwd (reference CPU path, bounded sample of the batch)"),
-                   "B": c["B"], "C_total": c["C"], "D": c["D"], "label_smoothing": LS},
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm + 1, "ms_per_step": round(dt * shards * 1e3, 2),
+        "higher_is_better": True, "scaling": "strong" if multi else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": ("cfg3: ArcFace head 512-d, 100k classes, batch 512 bf16 fwd+bwd, 1 B200" if not multi else
+                                "cfg4: ArcFace partial-FC 512-d, 1M classes, batch 4096 (reference CPU path: one 125k-class shard "
+                                "timed at the full batch, x8)"),
+                   "B": c["B"], "C_total": c["C"] * shards, "C_timed": c["C"], "D": c["D"], "label_smoothing": LS},
         "cpu_baseline": {"value": round(val, 1), "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": round(val, 1), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "loss": round(float(loss), 5)}), flush=True)

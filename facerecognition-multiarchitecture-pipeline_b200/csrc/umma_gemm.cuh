@@ -55,6 +55,10 @@ struct GemmParams {
   // descriptor knobs (bytes); defaults in default_params(); the self-test can override them
   uint32_t a_lbo, a_sbo, b_lbo, b_sbo, a_kstep, b_kstep;
   uint32_t idesc;
+  int early;                // 1: neither operand nor the output is touched by the predecessor grid (K3c behind K3b: both only READ
+                            // G^T): nobody waits for it up front -- CTAs start on SMs the predecessor has left -- and the epilogue
+                            // warps wait at their END, so that this grid still completes after its predecessor (stream order holds
+                            // for everything behind it)
 };
 
 struct TileCoord { int m0, n0, split, k_begin, k_end, nb0; };   // m0: first row of THIS CTA; nb0: first B row it loads
@@ -117,7 +121,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
   if (PAIR == 2) cluster_sync_all();                           // the peer's barriers exist before anyone signals them
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();
+  if (!p.early) pdl_wait();
 
   if (warp == 0) {
     // ================= TMA producer (both CTAs) =================
@@ -218,6 +222,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
       }
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
+    if (p.early) pdl_wait();
   }
   tc_fence_before_sync();
   __syncthreads();

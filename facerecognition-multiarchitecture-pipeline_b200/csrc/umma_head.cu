@@ -199,6 +199,7 @@ __global__ void reduce_splits_kernel(const float* __restrict__ part, int n_split
 
 // ---- X-stationary kernel: launch geometry ---------------------------------------------------------
 static std::atomic<int> g_pair{2};                 // 2 = tcgen05 cta_group::2 CTA pairs, 1 = single CTAs
+static std::atomic<int> g_early{1};                 // K3a / K3c start their loads and MMAs without waiting for the predecessor grid
 static std::atomic<int> g_epi_groups{2};            // K2 / K3a: 2 = two epilogue groups of 8 warps (16-column slices), 1 = one group
 #ifdef B200F_PROBES                                 // tools/ builds only; the shipped library has neither the branch nor the switch
 static std::atomic<int> g_k3a_ablate{0};            // probe: 2 = no G^T stores (WRONG results)
@@ -301,7 +302,7 @@ static XwPlan xw_plan(int64_t B, int64_t C, int pair, int max_chunks = 0) {
 template <int PAIR, int MODE, class Epi>
 static int launch_xw(const CUtensorMap& tx, const CUtensorMap& tw, const XwPlan& q, int64_t B, int64_t C, int D,
                      const typename Epi::Params& ep, cudaStream_t st, const char* what, uint32_t fmt = FMT_F16,
-                     bool reverse = false, const void* w_base = nullptr, int64_t w_row_bytes = 0) {
+                     bool reverse = false, const void* w_base = nullptr, int64_t w_row_bytes = 0, bool early = false) {
   int rc = xw_set_smem<PAIR, MODE, Epi>(); if (rc) return rc;
   XwParams p{};
   p.B = (int)B; p.C = (int)C; p.D = D;
@@ -309,6 +310,7 @@ static int launch_xw(const CUtensorMap& tx, const CUtensorMap& tw, const XwPlan&
   p.m_groups = q.m_groups; p.n_tiles = q.n_tiles; p.n_chunks = q.n_chunks;
   p.prefetch = (w_base != nullptr) ? g_prefetch.load(std::memory_order_relaxed) : 0;
   p.w_base = w_base; p.w_row_bytes = w_row_bytes;
+  p.early_operands = (early && g_early.load(std::memory_order_relaxed)) ? 1 : 0;
   p.tn = XW_WROWS * PAIR;
   p.reverse = reverse ? 1 : 0;
   p.idesc = make_idesc(fmt, fmt, MODE == XW_MK, MODE == XW_SWAP_MK, XW_M * PAIR, XW_WROWS * PAIR);   // A = resident, except SWAP modes
@@ -516,11 +518,11 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
 #ifdef B200F_PROBES
       e2.ablate = eg.ablate;
 #endif
-      rc = (qg.pair == 2) ? launch_xw<2, XW_SWAP, XwBwdGT2>(tx_k, tw_k, qg, B, cnt, D, e2, st, "umma K3a logit-grad (cta pair, 2 epilogue groups)", FMT_F16, false, wc, wrb)
-                          : launch_xw<1, XW_SWAP, XwBwdGT2>(tx_k, tw_k, qg, B, cnt, D, e2, st, "umma K3a logit-grad (2 epilogue groups)", FMT_F16, false, wc, wrb);
+      rc = (qg.pair == 2) ? launch_xw<2, XW_SWAP, XwBwdGT2>(tx_k, tw_k, qg, B, cnt, D, e2, st, "umma K3a logit-grad (cta pair, 2 epilogue groups)", FMT_F16, false, wc, wrb, true)
+                          : launch_xw<1, XW_SWAP, XwBwdGT2>(tx_k, tw_k, qg, B, cnt, D, e2, st, "umma K3a logit-grad (2 epilogue groups)", FMT_F16, false, wc, wrb, true);
     } else {
-      rc = (qg.pair == 2) ? launch_xw<2, XW_SWAP, XwBwdGT>(tx_k, tw_k, qg, B, cnt, D, eg, st, "umma K3a logit-grad (cta pair)", FMT_F16, false, wc, wrb)
-                          : launch_xw<1, XW_SWAP, XwBwdGT>(tx_k, tw_k, qg, B, cnt, D, eg, st, "umma K3a logit-grad", FMT_F16, false, wc, wrb);
+      rc = (qg.pair == 2) ? launch_xw<2, XW_SWAP, XwBwdGT>(tx_k, tw_k, qg, B, cnt, D, eg, st, "umma K3a logit-grad (cta pair)", FMT_F16, false, wc, wrb, true)
+                          : launch_xw<1, XW_SWAP, XwBwdGT>(tx_k, tw_k, qg, B, cnt, D, eg, st, "umma K3a logit-grad", FMT_F16, false, wc, wrb, true);
     }
     stage_event(EV_K3A, true, st);
     if (rc) return rc;
@@ -562,6 +564,7 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
     rc = tmap_mnmajor(&tg_mn, G, B, cnt, pl.ldg); if (rc) return rc;
     rc = tmap_mnmajor(&tw_mn, wc, D, cnt, D); if (rc) return rc;
     GemmParams px = gemm_params((int)B, D, (int)cnt, pl.dx_splits, true, true, FMT_F16, FMT_F16, gpair);
+    px.early = g_early.load(std::memory_order_relaxed);       // K3c reads G^T (K3a) and w_hat, writes dxpart: nothing of K3b's
     EpiStore::Params ex{dxpart, (int64_t)D, B * (int64_t)D, 0, 1.0f, nullptr};
     stage_event(EV_K3C, false, st);
     rc = (gpair == 2) ? launch_gemm<2, true, true, EpiStore>(tg_mn, tw_mn, px, ex, st, "umma K3c dX (cta pair)")
@@ -818,6 +821,7 @@ int b200f_set_tunable(const char* name, int value) {
   if (n == "pair") return b200f_umma_set_pair(value);
   if (n == "pdl") { const int old_v = pdl_enabled() ? 1 : 0; if (value == 0 || value == 1) pdl_set(value != 0); return old_v; }
   if (n == "stage_events") { if (value != 0 && value != 1) return g_stage_events.load(); return g_stage_events.exchange(value); }
+  if (n == "early") { if (value != 0 && value != 1) return g_early.load(); return g_early.exchange(value); }
   if (n == "epi_groups") { if (value != 1 && value != 2) return g_epi_groups.load(); return g_epi_groups.exchange(value); }
 #ifdef B200F_PROBES
   // probes that make the backward skip memory traffic (WRONG results): -DB200F_PROBES builds only (tools/)

@@ -115,6 +115,10 @@ struct XwParams {
                                         // sustains ~40 GB/s per SM where a tensor-bound K2 at cfg3 needs 60.
   const void* w_base;                   // streamed operand: first row of this launch, row pitch in bytes (prefetch only)
   int64_t w_row_bytes;
+  int early_operands;                   // 1: BOTH operands were complete before the predecessor grid started (K3a: x_hat / w_hat
+                                        // come from K1, the predecessor only supplies lse / grad4 to the epilogue), so the TMA and
+                                        // MMA warps do not wait for the predecessor: loads and MMAs of the first tiles overlap its
+                                        // tail.  The epilogue warps wait (griddepcontrol.wait) before they touch anything.
   uint32_t idesc;
 };
 
@@ -208,7 +212,6 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
   const int n_clusters = gridDim.x / PAIR;
   const int items = p.m_groups * p.n_chunks;
 
-  pdl_trigger();                                             // the next kernel may be scheduled behind this one
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x);
     tma_prefetch_desc(&tm_w);
@@ -225,7 +228,13 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
   if (PAIR == 2) cluster_sync_all();                         // the peer's barriers exist before anyone signals them
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();                                                // prologue done; predecessor grids complete from here on
+  // prologue done; predecessor grids complete from here on -- for everyone, or (early_operands) for the epilogue warps only:
+  // every CTA has epilogue warps, so no CTA (hence not the grid) completes before its predecessor has.
+  if (!p.early_operands || warp >= 2) pdl_wait();
+  // Dependents may be scheduled from here on -- AFTER the wait, not at the top of the kernel: a dependent that starts
+  // "early" (above) relies on everything older than its predecessor being complete, and that holds only if the
+  // predecessor could not release it before having waited itself (K1 -> K2 -> statistics -> K3a: K3a reads K1's output).
+  pdl_trigger();
 
   if (warp == 0) {
     // ================= TMA producer (both CTAs) =================
