@@ -126,6 +126,35 @@ __device__ __forceinline__ void st_global_256(void* p, uint32_t a0, uint32_t a1,
                : "memory");
 }
 
+// ---- L2 cache-policy hints ---------------------------------------------------------------------------
+// The step streams more than the 126 MB L2 holds (w_hat 102 MB, G^T 102 MB, dW 205 MB per cfg3 step) and re-reads
+// two of them: a hint per access says what should stay.  hint: 0 = none, 1 = evict_first (streamed once), 2 = evict_last
+// (will be read again by the next kernel).
+__device__ __forceinline__ uint64_t l2_policy(int hint) {
+  uint64_t pol = 0;
+  if (hint == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  else if (hint == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void st_global_256_hint(void* p, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4,
+                                                   uint32_t a5, uint32_t a6, uint32_t a7, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8}, %9;"
+               ::"l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(a4), "r"(a5), "r"(a6), "r"(a7), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair_hint(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "l"(pol)
+      : "memory");
+}
+
 // ---- descriptors -------------------------------------------------------------------------------
 // Shared-memory matrix descriptor (64-bit), SWIZZLE_128B canonical layouts:
 //   bits [0,14)  start address >> 4        bits [16,30) leading-dim byte offset >> 4
@@ -208,6 +237,11 @@ template <int PAIR>
 __device__ __forceinline__ void xw_tma_load(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
   if (PAIR == 2) tma_load_2d_pair(smem_dst, m, bar, c0, c1);
   else tma_load_2d(smem_dst, m, bar, c0, c1);
+}
+template <int PAIR>
+__device__ __forceinline__ void xw_tma_load_hint(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint64_t pol) {
+  if (PAIR == 2) tma_load_2d_pair_hint(smem_dst, m, bar, c0, c1, pol);
+  else tma_load_2d_hint(smem_dst, m, bar, c0, c1, pol);
 }
 template <int PAIR>
 __device__ __forceinline__ void xw_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {

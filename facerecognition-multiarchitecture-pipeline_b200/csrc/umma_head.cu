@@ -199,6 +199,9 @@ __global__ void reduce_splits_kernel(const float* __restrict__ part, int n_split
 
 // ---- X-stationary kernel: launch geometry ---------------------------------------------------------
 static std::atomic<int> g_pair{2};                 // 2 = tcgen05 cta_group::2 CTA pairs, 1 = single CTAs
+// L2 policy hints, a bit mask: 1 K3a streams w_hat evict_first; 2 K3a stores G^T evict_last; 4 K3b stores dW evict_first;
+// 8 K3b fetches its w_hat boxes evict_first; 16 K2 streams w_hat evict_last (K3a reads it again); 32 K3b streams G^T evict_last
+static std::atomic<int> g_l2_hints{0};
 static std::atomic<int> g_early{1};                 // K3a / K3c start their loads and MMAs without waiting for the predecessor grid
 static std::atomic<int> g_epi_groups{2};            // K2 / K3a: 2 = two epilogue groups of 8 warps (16-column slices), 1 = one group
 #ifdef B200F_PROBES                                 // tools/ builds only; the shipped library has neither the branch nor the switch
@@ -302,7 +305,8 @@ static XwPlan xw_plan(int64_t B, int64_t C, int pair, int max_chunks = 0) {
 template <int PAIR, int MODE, class Epi>
 static int launch_xw(const CUtensorMap& tx, const CUtensorMap& tw, const XwPlan& q, int64_t B, int64_t C, int D,
                      const typename Epi::Params& ep, cudaStream_t st, const char* what, uint32_t fmt = FMT_F16,
-                     bool reverse = false, const void* w_base = nullptr, int64_t w_row_bytes = 0, bool early = false) {
+                     bool reverse = false, const void* w_base = nullptr, int64_t w_row_bytes = 0, bool early = false,
+                     int w_hint = 0) {
   int rc = xw_set_smem<PAIR, MODE, Epi>(); if (rc) return rc;
   XwParams p{};
   p.B = (int)B; p.C = (int)C; p.D = D;
@@ -311,6 +315,7 @@ static int launch_xw(const CUtensorMap& tx, const CUtensorMap& tw, const XwPlan&
   p.prefetch = (w_base != nullptr) ? g_prefetch.load(std::memory_order_relaxed) : 0;
   p.w_base = w_base; p.w_row_bytes = w_row_bytes;
   p.early_operands = (early && g_early.load(std::memory_order_relaxed)) ? 1 : 0;
+  p.w_hint = w_hint;
   p.tn = XW_WROWS * PAIR;
   p.reverse = reverse ? 1 : 0;
   p.idesc = make_idesc(fmt, fmt, MODE == XW_MK, MODE == XW_SWAP_MK, XW_M * PAIR, XW_WROWS * PAIR);   // A = resident, except SWAP modes
@@ -447,17 +452,18 @@ int head_fwd(const void* xh, const void* wh, const int64_t* label, int64_t B, in
   ep.zero_word = reinterpret_cast<unsigned int*>(ws + pl.off_counter);
   const int eg = g_epi_groups.load(std::memory_order_relaxed);
   const int64_t wrb = (int64_t)D * 2;
+  const int k2_hint = (g_l2_hints.load(std::memory_order_relaxed) & 16) ? 2 : 0;
   stage_reset(EV_K2);
   stage_event(EV_K2, false, st);
   if (eg == 2) {
     XwFwd2::Params ep2{};
     ep2.label = ep.label; ep2.class_offset = ep.class_offset; ep2.hm = ep.hm; ep2.inv_scale = ep.inv_scale; ep2.part = ep.part;
     ep2.cos_part = ep.cos_part; ep2.nan_flag = ep.nan_flag; ep2.pair = ep.pair; ep2.zero_word = ep.zero_word;
-    rc = (q.pair == 2) ? launch_xw<2, XW_KK, XwFwd2>(tx, tw, q, B, C, D, ep2, st, "umma K2 arcface_fwd (cta pair, 2 epilogue groups)", FMT_F16, false, wh, wrb)
-                       : launch_xw<1, XW_KK, XwFwd2>(tx, tw, q, B, C, D, ep2, st, "umma K2 arcface_fwd (2 epilogue groups)", FMT_F16, false, wh, wrb);
+    rc = (q.pair == 2) ? launch_xw<2, XW_KK, XwFwd2>(tx, tw, q, B, C, D, ep2, st, "umma K2 arcface_fwd (cta pair, 2 epilogue groups)", FMT_F16, false, wh, wrb, false, k2_hint)
+                       : launch_xw<1, XW_KK, XwFwd2>(tx, tw, q, B, C, D, ep2, st, "umma K2 arcface_fwd (2 epilogue groups)", FMT_F16, false, wh, wrb, false, k2_hint);
   } else {
-    rc = (q.pair == 2) ? launch_xw<2, XW_KK, XwFwd>(tx, tw, q, B, C, D, ep, st, "umma K2 arcface_fwd (cta pair)", FMT_F16, false, wh, wrb)
-                       : launch_xw<1, XW_KK, XwFwd>(tx, tw, q, B, C, D, ep, st, "umma K2 arcface_fwd", FMT_F16, false, wh, wrb);
+    rc = (q.pair == 2) ? launch_xw<2, XW_KK, XwFwd>(tx, tw, q, B, C, D, ep, st, "umma K2 arcface_fwd (cta pair)", FMT_F16, false, wh, wrb, false, k2_hint)
+                       : launch_xw<1, XW_KK, XwFwd>(tx, tw, q, B, C, D, ep, st, "umma K2 arcface_fwd", FMT_F16, false, wh, wrb, false, k2_hint);
   }
   stage_event(EV_K2, true, st);
   if (rc) return rc;
@@ -506,6 +512,9 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
     eg.hm = HeadMath{cfg->m_eff, cfg->s_eff, cfg->easy_margin};
     eg.ls_eps = cfg->label_smoothing; eg.inv_Ctot = 1.0f / (float)cfg->num_classes_total; eg.inv_scale = 1.0f / (S * S);
     eg.GT = G; eg.ldgt = pl.ldg; eg.r_part = r_part; eg.ldr = pl.Cc;
+    const int hints = g_l2_hints.load(std::memory_order_relaxed);
+    eg.gt_hint = (hints & 2) ? 2 : 0;
+    const int k3a_whint = (hints & 1) ? 1 : 0;
 #ifdef B200F_PROBES
     eg.ablate = g_k3a_ablate.load(std::memory_order_relaxed);
 #endif
@@ -514,15 +523,15 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
       XwBwdGT2::Params e2{};
       e2.label = eg.label; e2.lse = eg.lse; e2.grad4 = eg.grad4; e2.class_offset = eg.class_offset; e2.hm = eg.hm;
       e2.ls_eps = eg.ls_eps; e2.inv_Ctot = eg.inv_Ctot; e2.inv_scale = eg.inv_scale; e2.GT = eg.GT; e2.ldgt = eg.ldgt;
-      e2.r_part = eg.r_part; e2.ldr = eg.ldr;
+      e2.r_part = eg.r_part; e2.ldr = eg.ldr; e2.gt_hint = eg.gt_hint;
 #ifdef B200F_PROBES
       e2.ablate = eg.ablate;
 #endif
-      rc = (qg.pair == 2) ? launch_xw<2, XW_SWAP, XwBwdGT2>(tx_k, tw_k, qg, B, cnt, D, e2, st, "umma K3a logit-grad (cta pair, 2 epilogue groups)", FMT_F16, false, wc, wrb, true)
-                          : launch_xw<1, XW_SWAP, XwBwdGT2>(tx_k, tw_k, qg, B, cnt, D, e2, st, "umma K3a logit-grad (2 epilogue groups)", FMT_F16, false, wc, wrb, true);
+      rc = (qg.pair == 2) ? launch_xw<2, XW_SWAP, XwBwdGT2>(tx_k, tw_k, qg, B, cnt, D, e2, st, "umma K3a logit-grad (cta pair, 2 epilogue groups)", FMT_F16, false, wc, wrb, true, k3a_whint)
+                          : launch_xw<1, XW_SWAP, XwBwdGT2>(tx_k, tw_k, qg, B, cnt, D, e2, st, "umma K3a logit-grad (2 epilogue groups)", FMT_F16, false, wc, wrb, true, k3a_whint);
     } else {
-      rc = (qg.pair == 2) ? launch_xw<2, XW_SWAP, XwBwdGT>(tx_k, tw_k, qg, B, cnt, D, eg, st, "umma K3a logit-grad (cta pair)", FMT_F16, false, wc, wrb, true)
-                          : launch_xw<1, XW_SWAP, XwBwdGT>(tx_k, tw_k, qg, B, cnt, D, eg, st, "umma K3a logit-grad", FMT_F16, false, wc, wrb, true);
+      rc = (qg.pair == 2) ? launch_xw<2, XW_SWAP, XwBwdGT>(tx_k, tw_k, qg, B, cnt, D, eg, st, "umma K3a logit-grad (cta pair)", FMT_F16, false, wc, wrb, true, k3a_whint)
+                          : launch_xw<1, XW_SWAP, XwBwdGT>(tx_k, tw_k, qg, B, cnt, D, eg, st, "umma K3a logit-grad", FMT_F16, false, wc, wrb, true, k3a_whint);
     }
     stage_event(EV_K3A, true, st);
     if (rc) return rc;
@@ -539,11 +548,12 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
       XwDwT::Params ew{};
       rc = make_tmap(&ew.tm_wh, wc, D, cnt, D, 32, 32, CU_TENSOR_MAP_SWIZZLE_NONE); if (rc) return rc;
       ew.coef = coef; ew.dw = dw; ew.c0 = c0; ew.ld = D;
+      ew.dw_hint = (hints & 4) ? 1 : 0; ew.wh_hint = (hints & 8) ? 1 : 0;
 #ifdef B200F_PROBES
       ew.ablate = g_k3b_ablate.load(std::memory_order_relaxed);
 #endif
-      rc = (qw.pair == 2) ? launch_xw<2, XW_SWAP_MK, XwDwT>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW class-major (cta pair)", FMT_F16, k3b_rev, G, pl.ldg * 2)
-                          : launch_xw<1, XW_SWAP_MK, XwDwT>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW class-major", FMT_F16, k3b_rev, G, pl.ldg * 2);
+      rc = (qw.pair == 2) ? launch_xw<2, XW_SWAP_MK, XwDwT>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW class-major (cta pair)", FMT_F16, k3b_rev, G, pl.ldg * 2, false, (hints & 32) ? 2 : 0)
+                          : launch_xw<1, XW_SWAP_MK, XwDwT>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW class-major", FMT_F16, k3b_rev, G, pl.ldg * 2, false, (hints & 32) ? 2 : 0);
       if (rc) return rc;
     } else {
       // batch > 512: x_hat^T cannot stay resident, both operands stream through the generic core:
@@ -821,6 +831,7 @@ int b200f_set_tunable(const char* name, int value) {
   if (n == "pair") return b200f_umma_set_pair(value);
   if (n == "pdl") { const int old_v = pdl_enabled() ? 1 : 0; if (value == 0 || value == 1) pdl_set(value != 0); return old_v; }
   if (n == "stage_events") { if (value != 0 && value != 1) return g_stage_events.load(); return g_stage_events.exchange(value); }
+  if (n == "l2_hints") { if (value < 0) return g_l2_hints.load(); return g_l2_hints.exchange(value); }
   if (n == "early") { if (value != 0 && value != 1) return g_early.load(); return g_early.exchange(value); }
   if (n == "epi_groups") { if (value != 1 && value != 2) return g_epi_groups.load(); return g_epi_groups.exchange(value); }
 #ifdef B200F_PROBES

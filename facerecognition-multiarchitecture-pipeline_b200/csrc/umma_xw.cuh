@@ -115,6 +115,7 @@ struct XwParams {
                                         // sustains ~40 GB/s per SM where a tensor-bound K2 at cfg3 needs 60.
   const void* w_base;                   // streamed operand: first row of this launch, row pitch in bytes (prefetch only)
   int64_t w_row_bytes;
+  int w_hint;                           // L2 policy of the streamed operand's loads (l2_policy(): 0 none, 1 evict_first, 2 evict_last)
   int early_operands;                   // 1: BOTH operands were complete before the predecessor grid started (K3a: x_hat / w_hat
                                         // come from K1, the predecessor only supplies lse / grad4 to the epilogue), so the TMA and
                                         // MMA warps do not wait for the predecessor: loads and MMAs of the first tiles overlap its
@@ -242,6 +243,7 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
     // issues the TMA traffic.
     {
       const bool leader = elect_one();
+      const uint64_t w_pol = l2_policy(p.w_hint);
       int stage = 0; uint32_t phase = 0;
       int item_no = 0;
       bool ok = true;
@@ -289,7 +291,8 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
               else mbar_arrive_cluster(&full_bar[stage], 0);
               uint8_t* dst = ring + (size_t)stage * XW_TILE_BYTES;
               if (!W_MN) {
-                xw_tma_load<PAIR>(dst, &tm_w, &full_bar[stage], kb * XW_K, n0);
+                if (p.w_hint) xw_tma_load_hint<PAIR>(dst, &tm_w, &full_bar[stage], kb * XW_K, n0, w_pol);
+                else xw_tma_load<PAIR>(dst, &tm_w, &full_bar[stage], kb * XW_K, n0);
               } else {
                 xw_tma_load<PAIR>(dst, &tm_w, &full_bar[stage], n0, kb * XW_K);
                 xw_tma_load<PAIR>(dst + XW_TILE_BYTES / 2, &tm_w, &full_bar[stage], n0 + 64, kb * XW_K);

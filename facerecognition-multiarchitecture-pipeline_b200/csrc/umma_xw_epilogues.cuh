@@ -238,9 +238,10 @@ struct XwBwdGTT {
     float ls_eps, inv_Ctot, inv_scale;
     uint16_t* GT; int64_t ldgt; // G^T[class of this launch, batch row]
     float* r_part; int64_t ldr; // [2 * m_groups, ldr]: one partial per (row group, column half)
+    int gt_hint;                // L2 policy of the G^T stores (K3b and K3c read them next): 0 none, 2 evict_last
     B200F_PROBE_FIELD           // probe builds only: 2 = no G^T stores (WRONG results)
   };
-  struct State { float gs, r; int cls; bool row_ok; };
+  struct State { float gs, r; int cls; bool row_ok; uint64_t pol; };
 
   static __device__ __forceinline__ void item_begin(State& st, const Params& ep, const XwParams& p, const XwItem& it,
                                                     float* scratch, int TN) {
@@ -260,6 +261,7 @@ struct XwBwdGTT {
     epi_bar_sync(it.grp);
     st.gs = __ldg(ep.grad4) * __ldg(ep.grad4 + 3);
     st.r = 0.f; st.cls = 0; st.row_ok = false;
+    st.pol = l2_policy(ep.gt_hint);
   }
   static __device__ __forceinline__ void tile_begin(State& st, const Params&, const XwParams& p, const XwItem& it) {
     st.cls = (int)it.row; st.row_ok = it.row < p.C; st.r = 0.f;
@@ -338,8 +340,10 @@ struct XwBwdGTT {
 #pragma unroll
         for (int j = 0; j < SC / 2; ++j) w1[j] = pack_f16(g[2 * j], g[2 * j + 1]);
 #pragma unroll
-        for (int j = 0; j < SC / 2; j += 8)
-          st_global_256(gdst + 2 * j, w1[j], w1[j + 1], w1[j + 2], w1[j + 3], w1[j + 4], w1[j + 5], w1[j + 6], w1[j + 7]);
+        for (int j = 0; j < SC / 2; j += 8) {
+          if (ep.gt_hint) st_global_256_hint(gdst + 2 * j, w1[j], w1[j + 1], w1[j + 2], w1[j + 3], w1[j + 4], w1[j + 5], w1[j + 6], w1[j + 7], st.pol);
+          else st_global_256(gdst + 2 * j, w1[j], w1[j + 1], w1[j + 2], w1[j + 3], w1[j + 4], w1[j + 5], w1[j + 6], w1[j + 7]);
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < SC; ++j)
@@ -376,9 +380,11 @@ struct XwDwT {
   struct Params {
     alignas(64) CUtensorMap tm_wh;      // w_hat16 rows of this launch [classes, D], box 32 features x 32 classes, no swizzle
     CoefSrc coef; float* dw; int64_t c0; int ld;
+    int dw_hint, wh_hint;               // L2 policies: dW stores (nobody reads them in this step: 1 evict_first), w_hat boxes
     B200F_PROBE_FIELD                   // probe builds only: 1 = no w_hat loads, 2 = no dW stores (WRONG results)
   };
-  struct State { float2 cf; float rp_next[4]; float inw_next; int64_t next_row; float inv_sg; int seq, n_seq, row0, row_step; bool row_ok; };
+  struct State { float2 cf; float rp_next[4]; float inw_next; int64_t next_row; float inv_sg; int seq, n_seq, row0, row_step; bool row_ok;
+                 uint64_t dw_pol, wh_pol; };
 
   // slice n of this warp's item = column slice (n % spt) of its (n / spt)-th tile; buffer n & 1
   static __device__ __forceinline__ void issue(const State& st, const Params& ep, const XwParams& p, const XwItem& it, int n) {
@@ -389,7 +395,8 @@ struct XwDwT {
     if (it.lane == 0) {
       uint64_t* bar = it.aux_bar + (n & 1);
       mbar_arrive_expect_tx(bar, 2048);
-      tma_load_2d(it.aux + (n & 1) * 2048, &ep.tm_wh, bar, d0, st.row0 + (n / spt) * st.row_step);
+      if (ep.wh_hint) tma_load_2d_hint(it.aux + (n & 1) * 2048, &ep.tm_wh, bar, d0, st.row0 + (n / spt) * st.row_step, st.wh_pol);
+      else tma_load_2d(it.aux + (n & 1) * 2048, &ep.tm_wh, bar, d0, st.row0 + (n / spt) * st.row_step);
     }
   }
   static __device__ __forceinline__ void item_begin(State& st, const Params& ep, const XwParams& p, const XwItem& it,
@@ -401,6 +408,7 @@ struct XwDwT {
     st.row_step = p.reverse ? -p.tn : p.tn;
     st.seq = 0; st.next_row = -1; st.row_ok = false;
     st.inv_sg = ep.coef.inv_sg();
+    st.dw_pol = l2_policy(ep.dw_hint); st.wh_pol = l2_policy(ep.wh_hint);
     issue(st, ep, p, it, 0);
     issue(st, ep, p, it, 1);
   }
@@ -458,10 +466,16 @@ struct XwDwT {
       if (B200F_PROBE_ON(ep, 2) && o[0] != 12345.678f) {
       } else if (d0 + 32 <= p.B && (ep.ld & 7) == 0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          st_global_256(dst + i * 8, __float_as_uint(o[i * 8]), __float_as_uint(o[i * 8 + 1]), __float_as_uint(o[i * 8 + 2]),
-                        __float_as_uint(o[i * 8 + 3]), __float_as_uint(o[i * 8 + 4]), __float_as_uint(o[i * 8 + 5]),
-                        __float_as_uint(o[i * 8 + 6]), __float_as_uint(o[i * 8 + 7]));
+        for (int i = 0; i < 4; ++i) {
+          if (ep.dw_hint)
+            st_global_256_hint(dst + i * 8, __float_as_uint(o[i * 8]), __float_as_uint(o[i * 8 + 1]), __float_as_uint(o[i * 8 + 2]),
+                               __float_as_uint(o[i * 8 + 3]), __float_as_uint(o[i * 8 + 4]), __float_as_uint(o[i * 8 + 5]),
+                               __float_as_uint(o[i * 8 + 6]), __float_as_uint(o[i * 8 + 7]), st.dw_pol);
+          else
+            st_global_256(dst + i * 8, __float_as_uint(o[i * 8]), __float_as_uint(o[i * 8 + 1]), __float_as_uint(o[i * 8 + 2]),
+                          __float_as_uint(o[i * 8 + 3]), __float_as_uint(o[i * 8 + 4]), __float_as_uint(o[i * 8 + 5]),
+                          __float_as_uint(o[i * 8 + 6]), __float_as_uint(o[i * 8 + 7]));
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
