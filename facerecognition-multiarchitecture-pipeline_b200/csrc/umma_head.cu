@@ -201,7 +201,8 @@ __global__ void reduce_splits_kernel(const float* __restrict__ part, int n_split
 static std::atomic<int> g_pair{2};                 // 2 = tcgen05 cta_group::2 CTA pairs, 1 = single CTAs
 // L2 policy hints, a bit mask: 1 K3a streams w_hat evict_first; 2 K3a stores G^T evict_last; 4 K3b stores dW evict_first;
 // 8 K3b fetches its w_hat boxes evict_first; 16 K2 streams w_hat evict_last (K3a reads it again); 32 K3b streams G^T evict_last
-static std::atomic<int> g_l2_hints{0};
+static std::atomic<int> g_l2_hints{6};
+static std::atomic<int> g_k3b_groups{2};            // K3b: 2 = two epilogue groups on 16-feature slices, 1 = one group on 32
 static std::atomic<int> g_early{1};                 // K3a / K3c start their loads and MMAs without waiting for the predecessor grid
 static std::atomic<int> g_epi_groups{2};            // K2 / K3a: 2 = two epilogue groups of 8 warps (16-column slices), 1 = one group
 #ifdef B200F_PROBES                                 // tools/ builds only; the shipped library has neither the branch nor the switch
@@ -230,7 +231,7 @@ static void stage_event(int which, bool is_end, cudaStream_t st) {
   cudaEventRecord(is_end ? g_ev.end[which][j] : g_ev.beg[which][j], st);
   if (is_end) g_ev.n[which] = j + 1;
 }           // K3b walks each chunk last tile first
-static std::atomic<int> g_prefetch{2};             // L2 prefetch distance of the xw producer (tiles of the streamed operand)
+static std::atomic<int> g_prefetch{0};             // L2 prefetch distance of the xw producer (tiles of the streamed operand)
 static std::atomic<int> g_chunk_mb{112};           // budget of the fp16 logit-gradient buffer G per class chunk
 
 // MODE of the X-stationary kernel: 0 = both operands K-major (K2, gallery scan, probes); 1 = resident operand
@@ -545,15 +546,28 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
       rc = tmap_kmajor(&tg_k, G, cnt, B, pl.ldg, XW_WROWS); if (rc) return rc;
       const XwPlan qw = xw_plan(D, cnt, qg.pair);
       const bool k3b_rev = g_k3b_reverse.load(std::memory_order_relaxed) != 0;   // read K3a's freshest G^T rows first
-      XwDwT::Params ew{};
-      rc = make_tmap(&ew.tm_wh, wc, D, cnt, D, 32, 32, CU_TENSOR_MAP_SWIZZLE_NONE); if (rc) return rc;
-      ew.coef = coef; ew.dw = dw; ew.c0 = c0; ew.ld = D;
-      ew.dw_hint = (hints & 4) ? 1 : 0; ew.wh_hint = (hints & 8) ? 1 : 0;
+      const int gt_lhint = (hints & 32) ? 2 : 0;
+      if (g_k3b_groups.load(std::memory_order_relaxed) == 2) {
+        XwDwT2::Params ew{};
+        rc = make_tmap(&ew.tm_wh, wc, D, cnt, D, 16, 32, CU_TENSOR_MAP_SWIZZLE_NONE); if (rc) return rc;
+        ew.coef = coef; ew.dw = dw; ew.c0 = c0; ew.ld = D;
+        ew.dw_hint = (hints & 4) ? 1 : 0; ew.wh_hint = (hints & 8) ? 1 : 0;
 #ifdef B200F_PROBES
-      ew.ablate = g_k3b_ablate.load(std::memory_order_relaxed);
+        ew.ablate = g_k3b_ablate.load(std::memory_order_relaxed);
 #endif
-      rc = (qw.pair == 2) ? launch_xw<2, XW_SWAP_MK, XwDwT>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW class-major (cta pair)", FMT_F16, k3b_rev, G, pl.ldg * 2, false, (hints & 32) ? 2 : 0)
-                          : launch_xw<1, XW_SWAP_MK, XwDwT>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW class-major", FMT_F16, k3b_rev, G, pl.ldg * 2, false, (hints & 32) ? 2 : 0);
+        rc = (qw.pair == 2) ? launch_xw<2, XW_SWAP_MK, XwDwT2>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW class-major (cta pair, 2 epilogue groups)", FMT_F16, k3b_rev, G, pl.ldg * 2, false, gt_lhint)
+                            : launch_xw<1, XW_SWAP_MK, XwDwT2>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW class-major (2 epilogue groups)", FMT_F16, k3b_rev, G, pl.ldg * 2, false, gt_lhint);
+      } else {
+        XwDwT::Params ew{};
+        rc = make_tmap(&ew.tm_wh, wc, D, cnt, D, 32, 32, CU_TENSOR_MAP_SWIZZLE_NONE); if (rc) return rc;
+        ew.coef = coef; ew.dw = dw; ew.c0 = c0; ew.ld = D;
+        ew.dw_hint = (hints & 4) ? 1 : 0; ew.wh_hint = (hints & 8) ? 1 : 0;
+#ifdef B200F_PROBES
+        ew.ablate = g_k3b_ablate.load(std::memory_order_relaxed);
+#endif
+        rc = (qw.pair == 2) ? launch_xw<2, XW_SWAP_MK, XwDwT>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW class-major (cta pair)", FMT_F16, k3b_rev, G, pl.ldg * 2, false, gt_lhint)
+                            : launch_xw<1, XW_SWAP_MK, XwDwT>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW class-major", FMT_F16, k3b_rev, G, pl.ldg * 2, false, gt_lhint);
+      }
       if (rc) return rc;
     } else {
       // batch > 512: x_hat^T cannot stay resident, both operands stream through the generic core:
@@ -832,6 +846,7 @@ int b200f_set_tunable(const char* name, int value) {
   if (n == "pdl") { const int old_v = pdl_enabled() ? 1 : 0; if (value == 0 || value == 1) pdl_set(value != 0); return old_v; }
   if (n == "stage_events") { if (value != 0 && value != 1) return g_stage_events.load(); return g_stage_events.exchange(value); }
   if (n == "l2_hints") { if (value < 0) return g_l2_hints.load(); return g_l2_hints.exchange(value); }
+  if (n == "k3b_groups") { if (value != 1 && value != 2) return g_k3b_groups.load(); return g_k3b_groups.exchange(value); }
   if (n == "early") { if (value != 0 && value != 1) return g_early.load(); return g_early.exchange(value); }
   if (n == "epi_groups") { if (value != 1 && value != 2) return g_epi_groups.load(); return g_epi_groups.exchange(value); }
 #ifdef B200F_PROBES

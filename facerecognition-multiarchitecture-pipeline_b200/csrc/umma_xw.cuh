@@ -155,6 +155,7 @@ struct XwItem {                         // what an epilogue thread knows about i
   int item, chunk, group;
   int rank, ew, quad, half, lane;       // CTA rank in the pair, epilogue warp 0..7 of its group, TMEM quadrant, column half, lane
   int grp;                              // epilogue group 0..kEpiGroups-1
+  int first_tile;                       // position (in the item's walk order) of the first tile this group takes
   int64_t row;                          // global row of x owned by this thread
   uint8_t* aux;                         // this warp's staging bytes (nullptr unless the policy reserves them)
   uint64_t* aux_bar;                    // its two mbarriers
@@ -202,9 +203,10 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
   uint64_t* acc_empty = acc_full + XW_MAX_ACC;               // [ACC] epilogue (both CTAs) -> MMA (leader)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + XW_NUM_BARS);
   uint8_t* aux = ring + (size_t)STAGES * XW_TILE_BYTES;       // (XW_STAGES - STAGES) x 16 KB of warp-private staging
-  uint64_t* aux_bar = reinterpret_cast<uint64_t*>(scratch + XW_SCRATCH_FLOATS) - 2 * XW_EPI_WARPS;   // 2 per epilogue
-                                                              // warp, in the last 128 B of the scratch area
-  constexpr int AUX_WARP_BYTES = (XW_STAGES - STAGES) * XW_TILE_BYTES / XW_EPI_WARPS;
+  constexpr int EPI_WARPS_ALL = XW_EPI_WARPS * xw_epi_groups<Epi>::value;
+  uint64_t* aux_bar = reinterpret_cast<uint64_t*>(scratch + XW_SCRATCH_FLOATS) - 2 * EPI_WARPS_ALL;   // 2 per epilogue
+                                                              // warp, at the end of the scratch area
+  constexpr int AUX_WARP_BYTES = (XW_STAGES - STAGES) * XW_TILE_BYTES / EPI_WARPS_ALL;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -220,7 +222,7 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
     mbar_init(x_empty, 1);
     for (int s = 0; s < XW_STAGES; ++s) { mbar_init(&full_bar[s], PAIR); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < ACC; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], PAIR * XW_EPI_WARPS); }
-    if (STAGES < XW_STAGES) for (int s = 0; s < 2 * XW_EPI_WARPS; ++s) mbar_init(&aux_bar[s], 1);
+    if (STAGES < XW_STAGES) for (int s = 0; s < 2 * EPI_WARPS_ALL; ++s) mbar_init(&aux_bar[s], 1);
     fence_barrier_init();
   }
   if (warp == 1) xw_tmem_alloc<PAIR>(tmem_slot, 512);
@@ -371,8 +373,8 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
     XwItem it;
     it.rank = rank; it.grp = (warp - 2) / XW_EPI_WARPS; it.ew = (warp - 2) % XW_EPI_WARPS;
     it.quad = warp & 3; it.half = it.ew >> 2; it.lane = lane;
-    it.aux = (STAGES < XW_STAGES) ? aux + (size_t)it.ew * AUX_WARP_BYTES : nullptr;
-    it.aux_bar = aux_bar + 2 * it.ew; it.aux_phase = 0;
+    it.aux = (STAGES < XW_STAGES) ? aux + (size_t)(it.grp * XW_EPI_WARPS + it.ew) * AUX_WARP_BYTES : nullptr;
+    it.aux_bar = aux_bar + 2 * (it.grp * XW_EPI_WARPS + it.ew); it.aux_phase = 0; it.first_tile = 0;
     float* const gscratch = scratch + it.grp * (XW_SCRATCH_FLOATS / XW_MAX_EPI_GROUPS);   // this group's half of the scratch
     uint32_t tile_no = 0;                                      // running tile number of this CTA (all groups count alike)
     bool ok = true;
@@ -385,6 +387,7 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
         const int t_begin = (int)((int64_t)it.chunk * p.n_tiles / p.n_chunks);
         const int t_end = (int)((int64_t)(it.chunk + 1) * p.n_tiles / p.n_chunks);
         typename Epi::State stt;
+        it.first_tile = (EG > 1) ? (int)((it.grp + EG - (tile_no % EG)) % EG) : 0;
         Epi::item_begin(stt, ep, p, it, gscratch, TN);         // per-column tables of the group -> shared memory
         const int col_base = it.half * (TN / 2);
         for (int ti = t_begin; ti < t_end; ++ti) {

@@ -375,10 +375,14 @@ using XwBwdGT2 = XwBwdGTT<2, 16>;
 // features] boxes (2 KB, one cp.async.bulk.tensor per slice, issued two slices ahead by lane 0) into staging space
 // taken from the operand ring: G^T needs a third of the HBM rate, so 3 ring stages suffice and the other 32 KB are
 // 8 warps x 2 buffers x 2 KB.
-struct XwDwT {
+template <int EG, int SC>
+struct XwDwTT {
   static constexpr int kRingStages = 3;
+  static constexpr int kEpiGroups = EG;
+  static constexpr int kSliceCols = SC;
+  static constexpr int kBoxBytes = 32 * SC * 2;       // [32 classes x SC features] fp16: 2 KB (SC = 32) or 1 KB (SC = 16)
   struct Params {
-    alignas(64) CUtensorMap tm_wh;      // w_hat16 rows of this launch [classes, D], box 32 features x 32 classes, no swizzle
+    alignas(64) CUtensorMap tm_wh;      // w_hat16 rows of this launch [classes, D], box SC features x 32 classes, no swizzle
     CoefSrc coef; float* dw; int64_t c0; int ld;
     int dw_hint, wh_hint;               // L2 policies: dW stores (nobody reads them in this step: 1 evict_first), w_hat boxes
     B200F_PROBE_FIELD                   // probe builds only: 1 = no w_hat loads, 2 = no dW stores (WRONG results)
@@ -386,24 +390,27 @@ struct XwDwT {
   struct State { float2 cf; float rp_next[4]; float inw_next; int64_t next_row; float inv_sg; int seq, n_seq, row0, row_step; bool row_ok;
                  uint64_t dw_pol, wh_pol; };
 
-  // slice n of this warp's item = column slice (n % spt) of its (n / spt)-th tile; buffer n & 1
+  // slice n of this warp's item = column slice (n % spt) of its (n / spt)-th OWN tile (with EG groups a group owns every
+  // EG-th tile of the walk, starting at it.first_tile); buffer n & 1
   static __device__ __forceinline__ void issue(const State& st, const Params& ep, const XwParams& p, const XwItem& it, int n) {
-    const int spt = p.tn >> 6;
+    const int spt = (p.tn >> 1) / SC;
     if (n >= st.n_seq || B200F_PROBE_ON(ep, 1)) return;
-    const int d0 = it.group * p.tn + it.half * (p.tn >> 1) + (n % spt) * 32;
+    const int d0 = it.group * p.tn + it.half * (p.tn >> 1) + (n % spt) * SC;
     if (d0 >= p.B) return;                                    // ragged feature count: nothing there (the reader skips too)
     if (it.lane == 0) {
       uint64_t* bar = it.aux_bar + (n & 1);
-      mbar_arrive_expect_tx(bar, 2048);
-      if (ep.wh_hint) tma_load_2d_hint(it.aux + (n & 1) * 2048, &ep.tm_wh, bar, d0, st.row0 + (n / spt) * st.row_step, st.wh_pol);
-      else tma_load_2d(it.aux + (n & 1) * 2048, &ep.tm_wh, bar, d0, st.row0 + (n / spt) * st.row_step);
+      mbar_arrive_expect_tx(bar, kBoxBytes);
+      const int row = st.row0 + (it.first_tile + EG * (n / spt)) * st.row_step;
+      if (ep.wh_hint) tma_load_2d_hint(it.aux + (n & 1) * kBoxBytes, &ep.tm_wh, bar, d0, row, st.wh_pol);
+      else tma_load_2d(it.aux + (n & 1) * kBoxBytes, &ep.tm_wh, bar, d0, row);
     }
   }
   static __device__ __forceinline__ void item_begin(State& st, const Params& ep, const XwParams& p, const XwItem& it,
                                                     float*, int) {
     const int t_begin = (int)((int64_t)it.chunk * p.n_tiles / p.n_chunks);
     const int t_end = (int)((int64_t)(it.chunk + 1) * p.n_tiles / p.n_chunks);
-    st.n_seq = (t_end - t_begin) * (p.tn >> 6);
+    const int own = (t_end - t_begin - it.first_tile + EG - 1) / EG;         // tiles of this item this group takes
+    st.n_seq = (own > 0 ? own : 0) * ((p.tn >> 1) / SC);
     st.row0 = (p.reverse ? t_end - 1 : t_begin) * p.tn + it.rank * XW_WROWS + it.quad * 32;
     st.row_step = p.reverse ? -p.tn : p.tn;
     st.seq = 0; st.next_row = -1; st.row_ok = false;
@@ -415,13 +422,13 @@ struct XwDwT {
   static __device__ __forceinline__ void tile_begin(State& st, const Params& ep, const XwParams& p, const XwItem& it) {
     st.row_ok = it.row < p.C;
     if (!st.row_ok) return;
-    // this tile's coefficients were REQUESTED one tile ago (raw loads, consumed only here: the warp never waits for them
-    // in the middle of a tile; forming the sum where the loads are issued blocked it once per partial)
+    // this tile's coefficients were REQUESTED one (own) tile ago (raw loads, consumed only here: the warp never waits for
+    // them in the middle of a tile; forming the sum where the loads are issued blocked it once per partial)
     if (st.next_row == it.row)
       st.cf = make_float2(st.inw_next * st.inv_sg, ((st.rp_next[0] + st.rp_next[1]) + st.rp_next[2]) + st.rp_next[3]);
     else
       st.cf = ep.coef.load(it.row, ep.c0 + it.row, st.inv_sg);
-    const int64_t nr = it.row + st.row_step;
+    const int64_t nr = it.row + (int64_t)EG * st.row_step;
     st.next_row = -1;
     if (nr >= 0 && nr < p.C && ep.coef.n_rb <= 4) {
       st.next_row = nr;
@@ -432,29 +439,31 @@ struct XwDwT {
     }
   }
   static __device__ __forceinline__ void slice(State& st, const Params& ep, const XwParams& p, const XwItem& it,
-                                               float (&v)[32], int col0, float*) {
+                                               float (&v)[SC], int col0, float*) {
     const int n = st.seq++;
-    const int d0 = it.group * p.tn + col0;                   // first of this slice's 32 features
+    const int d0 = it.group * p.tn + col0;                   // first of this slice's SC features
     if (d0 >= p.B) return;
-    uint4 w[4];
+    constexpr int NV = SC / 8;                                // 16-byte vectors of fp16 per lane and slice
+    uint4 w[NV];
     if (B200F_PROBE_ON(ep, 1)) {
-      w[0] = w[1] = w[2] = w[3] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) w[i] = make_uint4(0, 0, 0, 0);
     } else {
       const uint32_t b = (uint32_t)n & 1u;
       mbar_wait(it.aux_bar + b, (it.aux_phase >> b) & 1u);
       it.aux_phase ^= 1u << b;
-      const uint32_t src = smem_u32(it.aux + b * 2048 + it.lane * 64);
+      const uint32_t src = smem_u32(it.aux + b * kBoxBytes + it.lane * (SC * 2));
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < NV; ++i)
         asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
                      : "=r"(w[i].x), "=r"(w[i].y), "=r"(w[i].z), "=r"(w[i].w) : "r"(src + i * 16) : "memory");
     }
     if (st.row_ok) {
       float* dst = ep.dw + (ep.c0 + it.row) * (int64_t)ep.ld + d0;
       const float cx = st.cf.x, cy = st.cf.y;
-      float o[32];
+      float o[SC];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < NV; ++i) {
         const uint32_t q[4] = {w[i].x, w[i].y, w[i].z, w[i].w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -464,9 +473,9 @@ struct XwDwT {
         }
       }
       if (B200F_PROBE_ON(ep, 2) && o[0] != 12345.678f) {
-      } else if (d0 + 32 <= p.B && (ep.ld & 7) == 0) {
+      } else if (d0 + SC <= p.B && (ep.ld & 7) == 0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < NV; ++i) {
           if (ep.dw_hint)
             st_global_256_hint(dst + i * 8, __float_as_uint(o[i * 8]), __float_as_uint(o[i * 8 + 1]), __float_as_uint(o[i * 8 + 2]),
                                __float_as_uint(o[i * 8 + 3]), __float_as_uint(o[i * 8 + 4]), __float_as_uint(o[i * 8 + 5]),
@@ -478,12 +487,15 @@ struct XwDwT {
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
+        for (int j = 0; j < SC; ++j)
           if (d0 + j < p.B) dst[j] = o[j];
       }
     } else {
       // a lane without a row still has to have RECEIVED its shared-memory reads before the buffer is handed back
-      asm volatile("" :: "r"(w[0].x ^ w[1].x ^ w[2].x ^ w[3].x) : "memory");
+      uint32_t acc = 0;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) acc ^= w[i].x;
+      asm volatile("" :: "r"(acc) : "memory");
     }
     // Refill only now: the stores above consumed w[], so every lane's reads of the buffer have completed.  (Issuing
     // the refill right after the ld.shared instructions let the TMA write overtake reads still queued in the
@@ -493,6 +505,8 @@ struct XwDwT {
   }
   static __device__ __forceinline__ void tile_end(State&, const Params&, const XwParams&, const XwItem&) {}
 };
+using XwDwT = XwDwTT<1, 32>;
+using XwDwT2 = XwDwTT<2, 16>;
 
 }  // namespace umma
 }  // namespace b200f
