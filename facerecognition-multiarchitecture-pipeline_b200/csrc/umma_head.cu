@@ -202,9 +202,14 @@ static std::atomic<int> g_pair{2};                 // 2 = tcgen05 cta_group::2 C
 // L2 policy hints, a bit mask: 1 K3a streams w_hat evict_first; 2 K3a stores G^T evict_last; 4 K3b stores dW evict_first;
 // 8 K3b fetches its w_hat boxes evict_first; 16 K2 streams w_hat evict_last (K3a reads it again); 32 K3b streams G^T evict_last
 static std::atomic<int> g_l2_hints{6};
-static std::atomic<int> g_k3b_groups{2};            // K3b: 2 = two epilogue groups on 16-feature slices, 1 = one group on 32
+// Epilogue geometry per kernel, as measured at cfg3 on one box (tools/run_r02_*.sh, gpurun_out/r02[a-f]_*): K2 59.8 us with
+// one group / 61-65 with two (it is bound by the TMA -> MMA pipeline, 3.0 of its 3.5 us per tile); K3a 75 / 70.5 (epilogue-
+// bound: two groups overlap Epi(t) with Epi(t+1)); K3b 91.6 / 99.4 (store-bound: 64-byte pieces per lane and 1 KB w_hat
+// boxes move the same bytes less efficiently than 128-byte pieces and 2 KB boxes).
+static std::atomic<int> g_k2_groups{1};             // K2: epilogue groups
+static std::atomic<int> g_k3b_groups{1};            // K3b: 2 = two epilogue groups on 16-feature slices, 1 = one group on 32
 static std::atomic<int> g_early{1};                 // K3a / K3c start their loads and MMAs without waiting for the predecessor grid
-static std::atomic<int> g_epi_groups{2};            // K2 / K3a: 2 = two epilogue groups of 8 warps (16-column slices), 1 = one group
+static std::atomic<int> g_epi_groups{2};            // K3a: 2 = two epilogue groups of 8 warps (16-column slices), 1 = one group
 #ifdef B200F_PROBES                                 // tools/ builds only; the shipped library has neither the branch nor the switch
 static std::atomic<int> g_k3a_ablate{0};            // probe: 2 = no G^T stores (WRONG results)
 static std::atomic<int> g_k3b_ablate{0};            // probe: 1 = no w_hat loads, 2 = no dW stores (WRONG results)
@@ -451,7 +456,7 @@ int head_fwd(const void* xh, const void* wh, const int64_t* label, int64_t B, in
   ep.cos_part = reinterpret_cast<float*>(ws + pl.off_cos);
   ep.nan_flag = nan_flag; ep.pair = q.pair;
   ep.zero_word = reinterpret_cast<unsigned int*>(ws + pl.off_counter);
-  const int eg = g_epi_groups.load(std::memory_order_relaxed);
+  const int eg = g_k2_groups.load(std::memory_order_relaxed);
   const int64_t wrb = (int64_t)D * 2;
   const int k2_hint = (g_l2_hints.load(std::memory_order_relaxed) & 16) ? 2 : 0;
   stage_reset(EV_K2);
@@ -846,6 +851,7 @@ int b200f_set_tunable(const char* name, int value) {
   if (n == "pdl") { const int old_v = pdl_enabled() ? 1 : 0; if (value == 0 || value == 1) pdl_set(value != 0); return old_v; }
   if (n == "stage_events") { if (value != 0 && value != 1) return g_stage_events.load(); return g_stage_events.exchange(value); }
   if (n == "l2_hints") { if (value < 0) return g_l2_hints.load(); return g_l2_hints.exchange(value); }
+  if (n == "k2_groups") { if (value != 1 && value != 2) return g_k2_groups.load(); return g_k2_groups.exchange(value); }
   if (n == "k3b_groups") { if (value != 1 && value != 2) return g_k3b_groups.load(); return g_k3b_groups.exchange(value); }
   if (n == "early") { if (value != 0 && value != 1) return g_early.load(); return g_early.exchange(value); }
   if (n == "epi_groups") { if (value != 1 && value != 2) return g_epi_groups.load(); return g_epi_groups.exchange(value); }

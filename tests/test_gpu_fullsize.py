@@ -104,16 +104,17 @@ def test_cfg3_full_size_vs_cpu_port(cuda_device):
 
 @pytest.mark.parametrize("epi_groups", [1, 2])
 def test_cfg3_full_size_epilogue_variants_agree(cuda_device, epi_groups):
-    """Both epilogue geometries of K2 / K3a (one group of 8 warps on 32-column slices, two groups on 16-column
+    """Both epilogue geometries of K2 / K3a / K3b (one group of 8 warps on 32-column slices, two groups on 16-column
     slices) against the CPU port at a size that still has full tiles, ragged tiles and several items per cluster."""
     from b200face import _lib
     lib = _lib.load_library()
     x, w, y = _inputs(384, 30_011, 512, 77)
-    old = lib.b200f_set_tunable(b"epi_groups", epi_groups)
+    old = [lib.b200f_set_tunable(n, epi_groups) for n in (b"k2_groups", b"epi_groups", b"k3b_groups")]
     try:
         gpu = _gpu_step(x, w, y, cuda_device)
     finally:
-        lib.b200f_set_tunable(b"epi_groups", old)
+        for n, v in zip((b"k2_groups", b"epi_groups", b"k3b_groups"), old):
+            lib.b200f_set_tunable(n, v)
     _check(gpu, _cpu_step(x, w, y), f"epi_groups={epi_groups}")
 
 
