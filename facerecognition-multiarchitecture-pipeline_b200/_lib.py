@@ -78,6 +78,12 @@ PROTOTYPES = {
                                      c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, POINTER(HeadCfg),
                                      c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
                                      c_void_p]),
+    "b200f_bn_stats": (c_int, [c_void_p, c_int, c_int64, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_void_p]),
+    "b200f_tail_fwd": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float,
+                               c_void_p, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200f_tail_bwd": (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_int, c_void_p, c_void_p, c_int, c_float, c_void_p,
+                               c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200f_gallery_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int, c_int, c_int]),
     "b200f_gallery_topk": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int64,
                                    c_int64, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p,

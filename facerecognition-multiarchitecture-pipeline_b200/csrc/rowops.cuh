@@ -607,5 +607,158 @@ reduce_splits_normbwd_kernel(const float* __restrict__ part, int n_splits, int64
   }
 }
 
+// =====================================================================================================================
+// The embedding tail in front of the head (src/face_models.py:515-525):
+//     z = embedding(features)            (Linear 512 -> 512, no bias: stays a library GEMM)
+//     b = BatchNorm1d(z)                 (train: batch statistics + running-stat update; eval: running statistics)
+//     y = dropout(b)                     (train only; the keep mask is an input: the caller owns the generator)
+//     emb = F.normalize(y)               (and the head normalises its input again, :351 -- the same values)
+// fused as  [bn_stats] -> tail_fwd: ONE pass over z that applies BN and the mask, forms the row norm and emits what the
+// head's K1 would: the fp16 operand rows y_hat * S, 1 / |y|, plus y itself (the rows the backward projects with).
+// Backward of dropout + BatchNorm: tail_bwd_cols (column sums d_beta, d_gamma) -> tail_bwd_apply.
+// =====================================================================================================================
+
+// Column statistics of z [rows, dim] (train mode).  One block per 32 columns, 32 x 8 threads, rows strided over ty;
+// double accumulators (B <= a few thousand rows: cheap, and the variance is a difference of large numbers in fp32).
+// mean_out / invstd_out [dim]; running_mean / running_var updated in place with torch's rule
+// (momentum; the running variance takes the UNBIASED batch variance).
+template <typename T>
+static __global__ void __launch_bounds__(256)
+bn_stats_kernel(const T* __restrict__ z, int64_t rows, int dim, float eps, float momentum, float* running_mean,
+                float* running_var, float* __restrict__ mean_out, float* __restrict__ invstd_out) {
+  pdl_trigger(); pdl_wait();
+  __shared__ double sh_s[8][33], sh_q[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + tx;
+  double s = 0.0, q = 0.0;
+  if (j < dim)
+    for (int64_t r = ty; r < rows; r += 8) { const double v = (double)to_f32<T>(z[r * dim + j]); s += v; q += v * v; }
+  sh_s[ty][tx] = s; sh_q[ty][tx] = q;
+  __syncthreads();
+  if (ty == 0 && j < dim) {
+    for (int k = 1; k < 8; ++k) { s += sh_s[k][tx]; q += sh_q[k][tx]; }
+    const double n = (double)rows;
+    const double mean = s / n;
+    double var = q / n - mean * mean; if (var < 0.0) var = 0.0;
+    mean_out[j] = (float)mean;
+    invstd_out[j] = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean != nullptr) running_mean[j] = (float)((1.0 - momentum) * (double)running_mean[j] + momentum * mean);
+    if (running_var != nullptr) {
+      const double unb = rows > 1 ? var * n / (n - 1.0) : var;
+      running_var[j] = (float)((1.0 - momentum) * (double)running_var[j] + momentum * unb);
+    }
+  }
+}
+
+// mean / invstd come from bn_stats_kernel (train) or are formed from the running statistics here (eval: stat_is_var).
+// mask: uint8 keep mask [rows, dim] or NULL; keep_scale = 1 / (1 - p).  Outputs (each optional but inv_norm):
+// y fp32 [rows, dim], y_hat16 = fp16(y / |y| * out_scale), emb = y / |y| fp32.  One warp per row, dim % 4 == 0, dim <= 1024.
+template <typename T, int NV>
+static __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+tail_fwd_kernel(const T* __restrict__ z, int64_t rows, int dim, const float* __restrict__ gamma, const float* __restrict__ beta,
+                const float* __restrict__ mean, const float* __restrict__ stat, int stat_is_var, float bn_eps,
+                const uint8_t* __restrict__ mask, float keep_scale, float norm_eps, float out_scale,
+                float* __restrict__ y_out, __half* __restrict__ yhat16, float* __restrict__ emb, float* __restrict__ inv_norm) {
+  pdl_trigger(); pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nvec = dim >> 2;
+  float4 y[NV];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    y[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < nvec) {
+      const int64_t off = row * dim + 4 * c;
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] = to_f32<T>(z[off + e]);
+      const float4 m4 = __ldg(reinterpret_cast<const float4*>(mean + 4 * c));
+      float4 s4 = __ldg(reinterpret_cast<const float4*>(stat + 4 * c));
+      if (stat_is_var) s4 = make_float4(rsqrtf(s4.x + bn_eps), rsqrtf(s4.y + bn_eps), rsqrtf(s4.z + bn_eps), rsqrtf(s4.w + bn_eps));
+      const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + 4 * c));
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + 4 * c));
+      float o[4] = {fmaf((v[0] - m4.x) * s4.x, g4.x, b4.x), fmaf((v[1] - m4.y) * s4.y, g4.y, b4.y),
+                    fmaf((v[2] - m4.z) * s4.z, g4.z, b4.z), fmaf((v[3] - m4.w) * s4.w, g4.w, b4.w)};
+      if (mask != nullptr) {
+        const uchar4 k4 = *reinterpret_cast<const uchar4*>(mask + off);
+        o[0] = k4.x ? o[0] * keep_scale : 0.f; o[1] = k4.y ? o[1] * keep_scale : 0.f;
+        o[2] = k4.z ? o[2] * keep_scale : 0.f; o[3] = k4.w ? o[3] * keep_scale : 0.f;
+      }
+      y[i] = make_float4(o[0], o[1], o[2], o[3]);
+      ss = fmaf(o[0], o[0], ss); ss = fmaf(o[1], o[1], ss); ss = fmaf(o[2], o[2], ss); ss = fmaf(o[3], o[3], ss);
+      if (y_out != nullptr) *reinterpret_cast<float4*>(y_out + off) = y[i];
+    }
+  }
+  ss = warp_sum(ss);
+  const float inv = 1.0f / fmaxf(sqrtf(ss), norm_eps);
+  if (lane == 0) inv_norm[row] = inv;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nvec) {
+      const int64_t off = row * dim + 4 * c;
+      if (emb != nullptr) *reinterpret_cast<float4*>(emb + off) = make_float4(y[i].x * inv, y[i].y * inv, y[i].z * inv, y[i].w * inv);
+      if (yhat16 != nullptr) {
+        const float sc = inv * out_scale;
+        *reinterpret_cast<uint2*>(yhat16 + off) = make_uint2(pack_f16x2(y[i].x * sc, y[i].y * sc), pack_f16x2(y[i].z * sc, y[i].w * sc));
+      }
+    }
+  }
+}
+
+// Column sums of the BatchNorm backward: d_beta_j = sum_b d_b, d_gamma_j = sum_b d_b * xbn_bj with d = dy * mask * keep_scale
+// (gradient at the BatchNorm output) and xbn = (z - mean) * invstd.  Same geometry as bn_stats_kernel.
+template <typename T>
+static __global__ void __launch_bounds__(256)
+tail_bwd_cols_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ mask, float keep_scale, const T* __restrict__ z,
+                     const float* __restrict__ mean, const float* __restrict__ invstd, int64_t rows, int dim,
+                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_trigger(); pdl_wait();
+  __shared__ double sh_b[8][33], sh_g[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + tx;
+  double sb = 0.0, sg = 0.0;
+  if (j < dim) {
+    const float mu = mean[j], is = invstd[j];
+    for (int64_t r = ty; r < rows; r += 8) {
+      float d = dy[r * dim + j];
+      if (mask != nullptr) d = mask[r * dim + j] ? d * keep_scale : 0.f;
+      sb += (double)d; sg += (double)d * (double)((to_f32<T>(z[r * dim + j]) - mu) * is);
+    }
+  }
+  sh_b[ty][tx] = sb; sh_g[ty][tx] = sg;
+  __syncthreads();
+  if (ty == 0 && j < dim) {
+    for (int k = 1; k < 8; ++k) { sb += sh_b[k][tx]; sg += sh_g[k][tx]; }
+    dbeta[j] = (float)sb; dgamma[j] = (float)sg;
+  }
+}
+
+// dz = invstd * gamma * (d - d_beta / B - xbn * d_gamma / B)  (train: batch statistics)  |  invstd * gamma * d  (eval)
+template <typename T>
+static __global__ void __launch_bounds__(256)
+tail_bwd_apply_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ mask, float keep_scale, const T* __restrict__ z,
+                      const float* __restrict__ mean, const float* __restrict__ stat, int stat_is_var, float bn_eps,
+                      const float* __restrict__ gamma, const float* __restrict__ dgamma, const float* __restrict__ dbeta,
+                      int batch_stats, int64_t rows, int dim, float* __restrict__ dz) {
+  pdl_trigger(); pdl_wait();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * (int64_t)dim) return;
+  const int j = (int)(i % dim);
+  float d = dy[i];
+  if (mask != nullptr) d = mask[i] ? d * keep_scale : 0.f;
+  const float is = stat_is_var ? rsqrtf(stat[j] + bn_eps) : stat[j];
+  float t = d;
+  if (batch_stats) {
+    const float xbn = (to_f32<T>(z[i]) - mean[j]) * is;
+    const float inv_b = 1.0f / (float)rows;
+    t = d - dbeta[j] * inv_b - xbn * dgamma[j] * inv_b;
+  }
+  dz[i] = is * gamma[j] * t;
+}
+
 }  // namespace rowops
 }  // namespace b200f

@@ -53,6 +53,21 @@ static inline size_t elem_size(int dt) { return dt == B200F_F32 ? 4 : 2; }
 
 using namespace b200f;
 
+template <typename T>
+static int tail_fwd_t(const T* z, int64_t rows, int dim, const float* gamma, const float* beta, const float* mean, const float* stat,
+                      int stat_is_var, float bn_eps, const uint8_t* mask, float keep_scale, float norm_eps, float out_scale, float* y,
+                      __half* yhat16, float* emb, float* inv_norm, cudaStream_t st) {
+  const int nvec = dim >> 2;
+  const unsigned grid = (unsigned)ceil_div(rows, rowops::WARPS_PER_BLOCK);
+  const dim3 blk(rowops::WARPS_PER_BLOCK * 32);
+#define TAILF(NV) launch_pdl(rowops::tail_fwd_kernel<T, NV>, dim3(grid), blk, 0, st, z, rows, dim, gamma, beta, mean, stat, stat_is_var, \
+                             bn_eps, mask, keep_scale, norm_eps, out_scale, y, yhat16, emb, inv_norm)
+  if (nvec <= 32) TAILF(1); else if (nvec <= 64) TAILF(2); else if (nvec <= 128) TAILF(4); else TAILF(8);
+#undef TAILF
+  B200F_LAUNCH_OK("tail_fwd_kernel");
+  return B200F_OK;
+}
+
 extern "C" {
 
 int b200f_version(void) { return 100; }
@@ -166,6 +181,67 @@ int b200f_arcface_hook_scale(const float* pq_norm2, const float* upstream, int64
   launch_pdl(rowops::hook_scale_kernel, dim3(1), dim3(1), 0, as_stream(stream), pq_norm2, upstream, (double)B, s_eff,
              rowops::HookCfg{hook_enabled, max_grad_norm, phase, epoch}, out4);
   B200F_LAUNCH_OK("hook_scale_kernel");
+  return B200F_OK;
+}
+
+int b200f_bn_stats(const void* z, int dtype, int64_t rows, int dim, float eps, float momentum, float* running_mean,
+                   float* running_var, float* mean_out, float* invstd_out, void* stream) {
+  if (!dtype_ok(dtype)) return fail(B200F_ERR_ARG, "bn_stats: bad dtype");
+  if (rows <= 0 || dim <= 0 || !z || !mean_out || !invstd_out) return fail(B200F_ERR_ARG, "bn_stats: bad argument");
+  const unsigned grid = (unsigned)ceil_div(dim, 32);
+  if (dtype == B200F_F32)
+    launch_pdl(rowops::bn_stats_kernel<float>, dim3(grid), dim3(256), 0, as_stream(stream), static_cast<const float*>(z), rows, dim, eps,
+               momentum, running_mean, running_var, mean_out, invstd_out);
+  else
+    launch_pdl(rowops::bn_stats_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, as_stream(stream), static_cast<const __nv_bfloat16*>(z),
+               rows, dim, eps, momentum, running_mean, running_var, mean_out, invstd_out);
+  B200F_LAUNCH_OK("bn_stats_kernel");
+  return B200F_OK;
+}
+
+int b200f_tail_fwd(const void* z, int dtype, int64_t rows, int dim, const float* gamma, const float* beta, const float* mean,
+                   const float* stat, int stat_is_var, float bn_eps, const uint8_t* mask_or_null, float keep_scale, float norm_eps,
+                   float out_scale, float* y_or_null, void* yhat16_or_null, float* emb_or_null, float* inv_norm, void* stream) {
+  if (!dtype_ok(dtype)) return fail(B200F_ERR_ARG, "tail_fwd: bad dtype");
+  if (rows <= 0 || dim <= 0 || dim % 4 != 0 || dim > 1024) return fail(B200F_ERR_ARG, "tail_fwd: rows > 0, dim %% 4 == 0, dim <= 1024");
+  if (!z || !gamma || !beta || !mean || !stat || !inv_norm) return fail(B200F_ERR_ARG, "tail_fwd: null pointer");
+  cudaStream_t st = as_stream(stream);
+  if (dtype == B200F_F32)
+    return tail_fwd_t<float>(static_cast<const float*>(z), rows, dim, gamma, beta, mean, stat, stat_is_var, bn_eps, mask_or_null, keep_scale,
+                             norm_eps, out_scale, y_or_null, static_cast<__half*>(yhat16_or_null), emb_or_null, inv_norm, st);
+  return tail_fwd_t<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(z), rows, dim, gamma, beta, mean, stat, stat_is_var, bn_eps,
+                                   mask_or_null, keep_scale, norm_eps, out_scale, y_or_null, static_cast<__half*>(yhat16_or_null),
+                                   emb_or_null, inv_norm, st);
+}
+
+int b200f_tail_bwd(const float* dy, const uint8_t* mask_or_null, float keep_scale, const void* z, int dtype, const float* mean,
+                   const float* stat, int stat_is_var, float bn_eps, const float* gamma, int batch_stats, int64_t rows, int dim,
+                   float* dgamma, float* dbeta, float* dz, void* stream) {
+  if (!dtype_ok(dtype)) return fail(B200F_ERR_ARG, "tail_bwd: bad dtype");
+  if (rows <= 0 || dim <= 0 || !dy || !z || !mean || !stat || !gamma || !dgamma || !dbeta || !dz)
+    return fail(B200F_ERR_ARG, "tail_bwd: bad argument");
+  if (batch_stats && stat_is_var) return fail(B200F_ERR_ARG, "tail_bwd: batch statistics come as (mean, invstd)");
+  cudaStream_t st = as_stream(stream);
+  const unsigned gcol = (unsigned)ceil_div(dim, 32);
+  const unsigned gel = (unsigned)ceil_div(rows * (int64_t)dim, 256);
+  // column sums: d_gamma / d_beta (both modes; eval uses invstd from the running variance)
+  if (dtype == B200F_F32) {
+    if (stat_is_var) return fail(B200F_ERR_UNSUPPORTED, "tail_bwd: pass invstd (b200f_bn_stats) for the column sums");
+    launch_pdl(rowops::tail_bwd_cols_kernel<float>, dim3(gcol), dim3(256), 0, st, dy, mask_or_null, keep_scale, static_cast<const float*>(z),
+               mean, stat, rows, dim, dgamma, dbeta);
+    B200F_LAUNCH_OK("tail_bwd_cols_kernel");
+    launch_pdl(rowops::tail_bwd_apply_kernel<float>, dim3(gel), dim3(256), 0, st, dy, mask_or_null, keep_scale, static_cast<const float*>(z),
+               mean, stat, stat_is_var, bn_eps, gamma, (const float*)dgamma, (const float*)dbeta, batch_stats, rows, dim, dz);
+  } else {
+    if (stat_is_var) return fail(B200F_ERR_UNSUPPORTED, "tail_bwd: pass invstd (b200f_bn_stats) for the column sums");
+    launch_pdl(rowops::tail_bwd_cols_kernel<__nv_bfloat16>, dim3(gcol), dim3(256), 0, st, dy, mask_or_null, keep_scale,
+               static_cast<const __nv_bfloat16*>(z), mean, stat, rows, dim, dgamma, dbeta);
+    B200F_LAUNCH_OK("tail_bwd_cols_kernel");
+    launch_pdl(rowops::tail_bwd_apply_kernel<__nv_bfloat16>, dim3(gel), dim3(256), 0, st, dy, mask_or_null, keep_scale,
+               static_cast<const __nv_bfloat16*>(z), mean, stat, stat_is_var, bn_eps, gamma, (const float*)dgamma, (const float*)dbeta,
+               batch_stats, rows, dim, dz);
+  }
+  B200F_LAUNCH_OK("tail_bwd_apply_kernel");
   return B200F_OK;
 }
 

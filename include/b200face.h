@@ -208,6 +208,26 @@ int b200f_arcface_bwd_dx(const void* x, const void* w, int dtype,
 int b200f_l2norm_bwd(const void* v, int dtype, float v_scale, const float* inv_norm, const float* dvhat,
                      int64_t rows, int dim, float* dv, void* dv_bf16_or_null, void* stream);
 
+/* ---- the embedding tail in front of the head (src/face_models.py:515-525,584-590) -------------------
+ *   z = embedding(features) [rows, dim]  ->  BatchNorm1d  ->  dropout (train)  ->  F.normalize  ->  head
+ * b200f_bn_stats (train mode): batch mean and 1 / sqrt(biased var + eps) per column, and torch's running-stat update
+ *   in place (momentum; the running variance takes the unbiased batch variance).  running_* may be NULL.
+ * b200f_tail_fwd: ONE pass over z: y = dropout(BN(z)) with (mean, stat) = (batch mean, invstd) from b200f_bn_stats, or
+ *   (running_mean, running_var) with stat_is_var = 1 (eval); mask_or_null = uint8 keep mask [rows, dim] (the caller owns
+ *   the random generator), keep_scale = 1 / (1 - p).  Outputs, each optional except inv_norm: y fp32 (the rows the
+ *   head's backward projects with), yhat16 = B200F_F16N operand rows y / |y| * out_scale (what b200f_l2norm_rows would
+ *   emit for y: the head takes them as is), emb = y / |y| fp32 (get_embedding), inv_norm = 1 / max(|y|, norm_eps).
+ * b200f_tail_bwd: gradient of dropout + BatchNorm: dy = dL/dy [rows, dim] fp32 (what b200f_arcface_bwd_dx returns as dx)
+ *   -> dgamma, dbeta [dim] and dz [rows, dim] fp32.  batch_stats = 1: train-mode BatchNorm (statistics depend on z). */
+int b200f_bn_stats(const void* z, int dtype, int64_t rows, int dim, float eps, float momentum, float* running_mean,
+                   float* running_var, float* mean_out, float* invstd_out, void* stream);
+int b200f_tail_fwd(const void* z, int dtype, int64_t rows, int dim, const float* gamma, const float* beta, const float* mean,
+                   const float* stat, int stat_is_var, float bn_eps, const uint8_t* mask_or_null, float keep_scale, float norm_eps,
+                   float out_scale, float* y_or_null, void* yhat16_or_null, float* emb_or_null, float* inv_norm, void* stream);
+int b200f_tail_bwd(const float* dy, const uint8_t* mask_or_null, float keep_scale, const void* z, int dtype, const float* mean,
+                   const float* stat, int stat_is_var, float bn_eps, const float* gamma, int batch_stats, int64_t rows, int dim,
+                   float* dgamma, float* dbeta, float* dz, void* stream);
+
 /* K5 -- optimizer step of the class-weight rows: torch.optim.AdamW (amsgrad when vmax != NULL) exactly as the
  * reference trains the head (src/training.py:343-348; default betas (0.9, 0.999), eps 1e-8), after the optional
  * clip_grad_norm_ of :528-533, whose coefficient the caller passes as the device scalar grad_scale (NULL = 1):
