@@ -190,7 +190,7 @@ def _check_head_inputs(x, w, label, dlogits=None):
 
 
 def _fwd_kernels(x, w, label, cfg: HeadCfg, class_offset, want_logits, w_cache=None, nan_flag=None,
-                 fused_hook: Optional[HookCfg] = None):
+                 fused_hook: Optional[HookCfg] = None, x_ops=None):
     """K1 (x and W) + K2.  fused_hook (an unsharded head that wants its loss): K2b and the hook scalars for an upstream
     gradient of 1 come out of the same launch chain (b200f_arcface_fwd_loss); the tuple then ends with
     (lse, loss, pq_norm2, out4)."""
@@ -199,10 +199,15 @@ def _fwd_kernels(x, w, label, cfg: HeadCfg, class_offset, want_logits, w_cache=N
     B, D = x.shape
     C = w.shape[0]
     dev = x.device
-    f16n = use_tcgen05(x, cfg.engine, want_logits)
+    f16n = use_tcgen05(x, cfg.engine, want_logits) if x_ops is None else True
     if not f16n and x.dtype != w.dtype:
         raise TypeError(f"CUDA-core engine: x ({x.dtype}) and weight ({w.dtype}) must share a dtype")
-    if f16n and x.dtype == w.dtype and _cached_weight(w, f16n, w_cache) is None:
+    if x_ops is not None:                         # the embedding tail already emitted K1's outputs for x (fused_tail)
+        xo, inv_nx = x_ops
+        if want_logits or xo.dtype != torch.float16 or tuple(xo.shape) != tuple(x.shape):
+            raise ValueError("x_operands: fp16 operand rows of x's shape for the fused (tcgen05) path only")
+        wo, inv_nw = _prepare_weight(w, True, w_cache)
+    elif f16n and x.dtype == w.dtype and _cached_weight(w, f16n, w_cache) is None:
         xo, inv_nx, wo, inv_nw = _k1_pair(x, w, w_cache)
     else:
         xo, inv_nx = _k1(x, f16n)
@@ -297,7 +302,7 @@ class _ArcFaceLossFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, w, label, cfg: HeadCfg, class_offset, group, hook: _Hook, stats: HeadStats,
-                w_cache, unit_upstream):
+                w_cache, unit_upstream, x_ops):
         # weight: the tensor autograd differentiates (fp32 master or already x.dtype);
         # w: what K1 reads (== weight, or a bf16 compute copy of it)
         ctx.w_dtype, ctx.x_dtype = weight.dtype, x.dtype
@@ -306,10 +311,11 @@ class _ArcFaceLossFn(torch.autograd.Function):
         lib = _lib.load_library()
         if group is None:
             (x, w, inv_nx, inv_nw, row_stats, row_best, row_argmax, cos_minmax, nan_flag, _, lse, loss, pq_norm2,
-             out4) = _fwd_kernels(x, w, label, cfg, class_offset, False, w_cache, stats.sticky_nan_flag, fused_hook=hk)
+             out4) = _fwd_kernels(x, w, label, cfg, class_offset, False, w_cache, stats.sticky_nan_flag, fused_hook=hk,
+                                  x_ops=x_ops)
         else:
             x, w, inv_nx, inv_nw, row_stats, row_best, row_argmax, cos_minmax, nan_flag, _ = _fwd_kernels(
-                x, w, label, cfg, class_offset, False, w_cache, stats.sticky_nan_flag)
+                x, w, label, cfg, class_offset, False, w_cache, stats.sticky_nan_flag, x_ops=x_ops)
             from . import parallel
             parallel.reduce_row_stats(row_stats, group)          # one SUM all-reduce of [B,4]
             B = x.shape[0]
@@ -354,7 +360,7 @@ class _ArcFaceLossFn(torch.autograd.Function):
                 dx, lowp = _normalize_bwd(x, inv_nx, dxhat, x_raw), None
         ctx.stats.dx_f32 = dx
         gx = lowp if lowp is not None else dx.to(ctx.x_dtype)
-        return gx, dw.to(ctx.w_dtype), None, None, None, None, None, None, None, None, None
+        return gx, dw.to(ctx.w_dtype), None, None, None, None, None, None, None, None, None, None
 
 
 class _ArcLogitsFn(torch.autograd.Function):
@@ -401,17 +407,19 @@ def arcface_loss(x, weight, label, *, m_eff, s_eff, label_smoothing=0.05, easy_m
                  class_offset=0, num_classes_total=None, group=None, hook: Optional[_Hook] = None,
                  stats: Optional[HeadStats] = None, engine=_lib.ENGINE_AUTO,
                  compute_weight: Optional[torch.Tensor] = None, weight_cache: Optional[dict] = None,
-                 unit_upstream: bool = False):
+                 unit_upstream: bool = False, x_operands=None):
     """Functional fused head: mean label-smoothed CE of the ArcFace logits of (x, weight).
     x [B,D] fp32 / bf16 CUDA, weight [C_local,D] (the tensor that receives the gradient: an fp32 master
     keeps an fp32 dW even when the kernels compute in bf16), label [B] int64 global ids.
     compute_weight: the copy of weight in x.dtype the kernels read (default: weight itself, or a cast).
     unit_upstream: the caller promises that backward's upstream gradient is exactly 1 (``loss.backward()`` of the bare
     loss; GraphedHeadStep's static root gradient): the hook scalars the forward formed are used as they are and the
-    backward launches no scalar kernel."""
+    backward launches no scalar kernel.
+    x_operands: (x_hat16, inv_norm) already made for x by the fused embedding tail (fused_tail): K1 over x is skipped and
+    the tcgen05 engine runs whatever x's dtype (x itself still supplies the rows the backward projects with)."""
     require_cuda(x, weight, label, compute_weight)
     if compute_weight is None:
-        if weight.dtype == x.dtype or use_tcgen05(x, engine):
+        if weight.dtype == x.dtype or use_tcgen05(x, engine) or x_operands is not None:
             compute_weight = weight.detach()          # K1 reads the master directly (fp32 or bf16)
         else:
             compute_weight = weight.detach().to(x.dtype)
@@ -419,7 +427,7 @@ def arcface_loss(x, weight, label, *, m_eff, s_eff, label_smoothing=0.05, easy_m
                     num_classes_total if num_classes_total is not None else weight.shape[0], engine)
     return _ArcFaceLossFn.apply(x.contiguous(), weight, compute_weight.contiguous(),
                                 label.contiguous().to(torch.int64), cfg, class_offset, group, hook or _Hook(),
-                                stats if stats is not None else HeadStats(), weight_cache, unit_upstream)
+                                stats if stats is not None else HeadStats(), weight_cache, unit_upstream, x_operands)
 
 
 class GraphedHeadStep:
@@ -609,12 +617,25 @@ class ArcMarginProduct(nn.Module):
         return _ArcLogitsFn.apply(x, weight, w.contiguous(), label.contiguous().to(torch.int64), cfg, self._hook,
                                   self.last_stats)
 
-    def forward_loss(self, input, label, label_smoothing=0.05, return_pred=False):
+    def wants_tensor_engine(self, input_dtype=torch.bfloat16) -> bool:
+        """Would forward_loss run on the tcgen05 engine for an input of this dtype (D permitting)?"""
+        if self.engine == _lib.ENGINE_SIMT or self.in_feats % 8 != 0 or self.in_feats > TCGEN05_MAX_D:
+            return False
+        if not _lib.load_library().b200f_has_tcgen05():
+            return False
+        dt = self.compute_dtype or input_dtype
+        return self.engine == _lib.ENGINE_TCGEN05 or dt == torch.bfloat16
+
+    def forward_loss(self, input, label, label_smoothing=0.05, return_pred=False, x_operands=None):
         """Fused criterion(forward(input,label), label) with nn.CrossEntropyLoss(label_smoothing):
         the logits never reach HBM.  return_pred: also return outputs.max(1) indices
-        (hyperparameter_tuning.py:1001)."""
+        (hyperparameter_tuning.py:1001).  x_operands: see arcface_loss (ArcFaceNet's fused tail passes them)."""
         m_eff, s_eff = self._step_schedule()
-        x, weight, w = self._operands(input)
+        if x_operands is not None:
+            require_cuda(input, self.weight)
+            x, weight, w = input.contiguous(), self.weight, self.weight.detach()
+        else:
+            x, weight, w = self._operands(input)
         if self.validate_labels:
             c_tot = self._num_classes_total or self.out_feats
             if label.numel() and (int(label.min()) < 0 or int(label.max()) >= c_tot):
@@ -625,7 +646,7 @@ class ArcMarginProduct(nn.Module):
                             easy_margin=self.easy_margin, hook=self._hook, stats=self.last_stats,
                             engine=self.engine, compute_weight=w, class_offset=self._class_offset,
                             num_classes_total=self._num_classes_total, group=self._group,
-                            weight_cache=self._w_prep if use_cache else None)
+                            weight_cache=self._w_prep if use_cache else None, x_operands=x_operands)
         if return_pred:
             if self._group is not None:
                 from . import parallel
@@ -719,6 +740,94 @@ class ArcMarginProduct(nn.Module):
         }
 
 
+class _FusedTailFn(torch.autograd.Function):
+    """y = dropout(BatchNorm1d(z)) -- and, in the same pass over z, what the head's K1 would make of y: 1 / |y| and the
+    fp16 operand rows (kernels bn_stats / tail_fwd / tail_bwd, include/b200face.h).  src/face_models.py:516-525."""
+
+    @staticmethod
+    def forward(ctx, z, gamma, beta, running_mean, running_var, training, momentum, eps, mask, keep_scale, want_ops,
+                want_emb, side):
+        lib = _lib.load_library()
+        z = z.contiguous()
+        if z.dtype not in (torch.float32, torch.bfloat16):
+            z = z.float()
+        B, D = z.shape
+        dev = z.device
+        g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        if training:
+            if B < 2:
+                raise ValueError(f"Expected more than 1 value per channel when training, got input size {tuple(z.shape)}")
+            mean = torch.empty(D, dtype=torch.float32, device=dev)
+            invstd = torch.empty(D, dtype=torch.float32, device=dev)
+            check(lib.b200f_bn_stats(ptr(z), dtype_code(z), B, D, float(eps), float(momentum), ptr(running_mean),
+                                     ptr(running_var), ptr(mean), ptr(invstd), stream_ptr(dev)), "b200f_bn_stats")
+            stat, stat_is_var = invstd, 0
+        else:
+            mean, stat, stat_is_var = running_mean.float().contiguous(), running_var.float().contiguous(), 1
+        y = torch.empty(B, D, dtype=torch.float32, device=dev)
+        xo = torch.empty(B, D, dtype=torch.float16, device=dev) if want_ops else None
+        emb = torch.empty(B, D, dtype=torch.float32, device=dev) if want_emb else None
+        inv = torch.empty(B, dtype=torch.float32, device=dev)
+        check(lib.b200f_tail_fwd(ptr(z), dtype_code(z), B, D, ptr(g32), ptr(b32), ptr(mean), ptr(stat), stat_is_var,
+                                 float(eps), ptr(mask), float(keep_scale), NORM_EPS, OPERAND_SCALE, ptr(y), ptr(xo), ptr(emb),
+                                 ptr(inv), stream_ptr(dev)), "b200f_tail_fwd")
+        side["x_operands"] = (xo, inv) if want_ops else None
+        side["emb"] = emb
+        side["inv_norm"] = inv
+        invstd_b = stat if not stat_is_var else torch.rsqrt(stat + eps)
+        ctx.save_for_backward(z, g32, mean, invstd_b, mask if mask is not None else torch.empty(0, device=dev))
+        ctx.has_mask, ctx.keep_scale, ctx.training, ctx.eps = mask is not None, float(keep_scale), bool(training), float(eps)
+        ctx.z_dtype, ctx.g_dtype = z.dtype, gamma.dtype
+        ctx.mark_non_differentiable(*(t for t in ()))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        z, g32, mean, invstd, mask = ctx.saved_tensors
+        lib = _lib.load_library()
+        B, D = z.shape
+        dev = z.device
+        dy = dy.float().contiguous()
+        dgamma = torch.empty(D, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(D, dtype=torch.float32, device=dev)
+        dz = torch.empty(B, D, dtype=torch.float32, device=dev)
+        check(lib.b200f_tail_bwd(ptr(dy), ptr(mask) if ctx.has_mask else None, ctx.keep_scale, ptr(z), dtype_code(z), ptr(mean),
+                                 ptr(invstd), 0, ctx.eps, ptr(g32), int(ctx.training), B, D, ptr(dgamma), ptr(dbeta), ptr(dz),
+                                 stream_ptr(dev)), "b200f_tail_bwd")
+        return (dz.to(ctx.z_dtype), dgamma.to(ctx.g_dtype), dbeta.to(ctx.g_dtype), None, None, None, None, None, None, None,
+                None, None, None)
+
+
+def fused_tail(z: torch.Tensor, bn: nn.BatchNorm1d, p_drop: float = 0.0, training: bool = True,
+               mask: Optional[torch.Tensor] = None, want_operands: bool = False, want_emb: bool = False):
+    """The embedding tail of ArcFaceNet behind the Linear layer (src/face_models.py:516-525) as ONE fused pass:
+    BatchNorm1d (train: batch statistics + running-stat update; eval: running statistics) -> dropout (train; `mask` =
+    uint8 keep mask [B, D], drawn here from torch's CUDA generator when None) -> row L2 norm.
+    Returns (y, side): y [B, D] fp32 = dropout(bn(z)), differentiable w.r.t. z and the BatchNorm affine parameters;
+    side = {"x_operands": (y_hat16, inv_norm) for ArcMarginProduct.forward_loss, "emb": normalised rows, "inv_norm"}."""
+    require_cuda(z, bn.weight, bn.bias, bn.running_mean, bn.running_var)
+    keep_scale = 1.0
+    if training and p_drop > 0.0:
+        if mask is None:
+            mask = (torch.rand(z.shape, device=z.device) >= p_drop).to(torch.uint8)
+        keep_scale = 1.0 / (1.0 - p_drop) if p_drop < 1.0 else 0.0
+    else:
+        mask = None
+    if mask is not None:
+        if mask.dtype != torch.uint8 or tuple(mask.shape) != tuple(z.shape) or not mask.is_cuda:
+            raise ValueError("mask: uint8 CUDA tensor of z's shape")
+        mask = mask.contiguous()
+    momentum = 0.1 if bn.momentum is None else bn.momentum
+    if training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    side = {}
+    rm = bn.running_mean if bn.track_running_stats else None
+    rv = bn.running_var if bn.track_running_stats else None
+    y = _FusedTailFn.apply(z, bn.weight, bn.bias, rm, rv, training or rm is None, momentum, bn.eps, mask, keep_scale,
+                           want_operands, want_emb, side)
+    return y, side
+
+
 class ArcFaceNet(nn.Module):
     """Drop-in for the reference ArcFaceNet (face_models.py:447-613).  The ResNet18 trunk is
     torchvision's (out of scope); the head tail -- embedding, bn, dropout, normalise, ArcFace, and
@@ -745,6 +854,7 @@ class ArcFaceNet(nn.Module):
         self.val_classifier = nn.Linear(512, num_classes)
         nn.init.xavier_normal_(self.val_classifier.weight, gain=math.sqrt(2))
         self._hook_armed = False          # the reference registers its hook after the 1st forward
+        self.fused_tail = True            # CUDA: BatchNorm + dropout + row norm (+ the head's K1) as one fused kernel
 
     def freeze_backbone(self):
         self.backbone_frozen = True
@@ -780,6 +890,12 @@ class ArcFaceNet(nn.Module):
             return l2_normalize(x)[0]                         # K1 (no autograd needed)
         return F.normalize(x, p=2, dim=1, eps=1e-12)
 
+    def _tail_fused(self, x, training, want_operands=False, want_emb=False):
+        """CUDA path of the tail: trunk and Linear stay torch modules, BatchNorm + dropout + row norm run as the fused
+        kernel."""
+        z = self.embedding(self.features(x).view(x.size(0), -1))
+        return fused_tail(z, self.bn, self.dropout.p, training, want_operands=want_operands, want_emb=want_emb)
+
     def _arm_hook(self):
         # hook state as the reference's closure would read it at backward time (:544-556)
         self.arcface._hook = _Hook(enabled=self._hook_armed, max_grad_norm=self.max_grad_norm,
@@ -790,7 +906,10 @@ class ArcFaceNet(nn.Module):
         if self.training:
             if labels is None:
                 raise ValueError("Labels must be provided during training")
-            pre = self._tail(x, True, normalize=not x.is_cuda)   # CUDA: the head's K1 does the (single) normalise
+            if x.is_cuda and self.fused_tail:
+                pre = self._tail_fused(x, True)[0]               # CUDA: fused tail; the head's K1 does the (single) normalise
+            else:
+                pre = self._tail(x, True, normalize=not x.is_cuda)
             self.arcface.update_epoch(self.current_epoch)
             self._arm_hook()
             return self.arcface(pre, labels)
@@ -804,12 +923,21 @@ class ArcFaceNet(nn.Module):
         """Fused training step head: == criterion(self(x, labels), labels) incl. the hook."""
         if labels is None:
             raise ValueError("Labels must be provided during training")
-        pre = self._tail(x, self.training, normalize=not x.is_cuda)
+        ops = None
+        if x.is_cuda and self.fused_tail:
+            # the head's K1 over x is fused into the tail when the head will run on the tcgen05 engine
+            want = self.arcface.wants_tensor_engine(torch.float32) and self.arcface._group is None
+            pre, side = self._tail_fused(x, self.training, want_operands=want)
+            ops = side["x_operands"]
+        else:
+            pre = self._tail(x, self.training, normalize=not x.is_cuda)
         self.arcface.update_epoch(self.current_epoch)
         self._arm_hook()
-        return self.arcface.forward_loss(pre, labels, label_smoothing, return_pred)
+        return self.arcface.forward_loss(pre, labels, label_smoothing, return_pred, x_operands=ops)
 
     def get_embedding(self, x):
+        if x.is_cuda and self.fused_tail and not torch.is_grad_enabled():
+            return self._tail_fused(x, False, want_emb=True)[1]["emb"]
         return self._tail(x, False)                           # no dropout (src/face_models.py:584-590)
 
     def update_epoch(self, epoch):
