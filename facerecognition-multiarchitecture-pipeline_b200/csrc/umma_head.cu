@@ -634,11 +634,13 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
 // tile of the first 16 k (32 k) rows.  Several row groups: 4 chunks of 8 tiles, so that a work item amortises its
 // x load over 8 tiles (one-tile items made the pre-pass cost a quarter of the scan at Q = 8192).
 constexpr int GALLERY_SAMPLE_MAX_LISTS = 32 * GALLERY_TAU_LISTS_PER_LANE;
+static std::atomic<int> g_gallery_compact{1};      // tunable "gallery_compact": 0 = the padded-list pre-pass / select of round 1
 struct GalleryScanPlan {
   XwPlan q, qs;                 // main scan / sample pre-pass
   int KT, n_lists;
   int64_t n_sample;             // gallery rows of the sample (0: no pre-pass)
-  size_t off_q16, off_ckey, off_cidx, off_skey, off_sidx, off_tau, off_qbad, total;
+  bool compact;                 // one row group with a sample bound: min-only pre-pass, compact candidates, warp select
+  size_t off_q16, off_ckey, off_cidx, off_skey, off_sidx, off_tau, off_qbad, off_cnt, total;
 };
 
 static GalleryScanPlan gallery_scan_plan(int64_t Q, int64_t N, int D, int k) {
@@ -647,9 +649,11 @@ static GalleryScanPlan gallery_scan_plan(int64_t Q, int64_t N, int D, int k) {
   g.KT = k <= 1 ? 8 : (k <= 6 ? 16 : 32);
   g.n_lists = g.q.n_chunks * 2;
   size_t off = 0;
+  size_t per_q = (size_t)g.n_lists * g.KT;                  // candidate slots per query: padded lists, or the compact array
+  if (per_q < (size_t)GALLERY_COMPACT_CAP) per_q = GALLERY_COMPACT_CAP;
   g.off_q16 = off;  off += align_up(2 * (size_t)Q * D, 1024);
-  g.off_ckey = off; off += align_up(sizeof(float) * (size_t)Q * g.n_lists * g.KT, 256);
-  g.off_cidx = off; off += align_up(sizeof(int32_t) * (size_t)Q * g.n_lists * g.KT, 256);
+  g.off_ckey = off; off += align_up(sizeof(float) * (size_t)Q * per_q, 256);
+  g.off_cidx = off; off += align_up(sizeof(int32_t) * (size_t)Q * per_q, 256);
   // sample pre-pass over the first rows of the gallery (skipped when that is a quarter of it or more)
   const int s_chunks = (g.q.m_groups == 1) ? GALLERY_SAMPLE_MAX_LISTS / 2 : 4;
   const int s_tiles = (g.q.m_groups == 1) ? 1 : 8;
@@ -661,6 +665,9 @@ static GalleryScanPlan gallery_scan_plan(int64_t Q, int64_t N, int D, int k) {
   g.off_sidx = off; off += align_up(sizeof(int32_t) * sl, 256);
   g.off_tau = off;  off += align_up(sizeof(float) * (size_t)Q, 256);
   g.off_qbad = off; off += align_up((size_t)Q, 256);
+  g.off_cnt = off;  off += align_up(sizeof(int32_t) * (size_t)Q, 256);
+  g.compact = g_gallery_compact.load(std::memory_order_relaxed) != 0 && g.n_sample > 0 && g.q.m_groups == 1 &&
+              g.qs.n_chunks * 2 >= 4 * g.KT && g.qs.n_chunks * 2 <= 256;
   g.total = off + 1024;
   return g;
 }
@@ -694,15 +701,25 @@ static int gallery_scan_kt(const GalleryScanPlan& gp, const void* g16, const CUt
                            const float* g, const float* bias, const float* q_inv, const float* g_inv, int64_t Q, int64_t N,
                            int64_t index_offset, int D, int k, int metric, int fmt, float thresh, int64_t* idx, float* score,
                            uint8_t* accept, uint8_t* redo, int32_t* redo_count, float* ckey, int32_t* cidx, float* skey,
-                           int32_t* sidx, float* tau0, const uint8_t* qbad, cudaStream_t st) {
+                           int32_t* sidx, float* tau0, const uint8_t* qbad, int32_t* cnt, cudaStream_t st) {
   const uint32_t mfmt = fmt == B200F_OPERAND_FP16 ? FMT_F16 : FMT_BF16;
   typename XwTopK<KT>::Params ep{};
   ep.bias = (metric == B200F_METRIC_COS) ? nullptr : bias;
   ep.mult = (metric == B200F_METRIC_COS) ? -1.0f : -2.0f;
-  if (gp.n_sample > 0) {
+  if (gp.compact) {
+    // sample pre-pass, min-only: every CTA scans one tile of the first n_sample rows and keeps the smallest key per
+    // (CTA, column half); tau0[q] = KT-th smallest of those minima; the same kernel zeroes the candidate counters
+    XwMinKey::Params es{ep.bias, ep.mult, skey, gp.qs.n_chunks * 2};
+    int rcs = (gp.qs.pair == 2) ? launch_xw<2, XW_KK, XwMinKey>(tx, tw, gp.qs, Q, gp.n_sample, D, es, st, "umma K4 gallery sample minima (cta pair)", mfmt)
+                                : launch_xw<1, XW_KK, XwMinKey>(tx, tw, gp.qs, Q, gp.n_sample, D, es, st, "umma K4 gallery sample minima", mfmt);
+    if (rcs) return rcs;
+    launch_pdl(gallery_tau_min_kernel<KT>, dim3((unsigned)ceil_div(Q, 4)), dim3(128), 0, st, (const float*)skey, es.n_lists, Q, tau0, cnt);
+    B200F_LAUNCH_OK("gallery_tau_min_kernel");
+    ep.tau0 = tau0; ep.cnt = cnt; ep.cap = GALLERY_COMPACT_CAP;
+  } else if (gp.n_sample > 0) {
     // sample pre-pass: the same scan over the first n_sample rows with few long chunks, then tau0[q] = KT-th best key
     typename XwTopK<KT>::Params es = ep;
-    es.cand_key = skey; es.cand_idx = sidx; es.n_lists = gp.qs.n_chunks * 2; es.tau0 = nullptr;
+    es.cand_key = skey; es.cand_idx = sidx; es.n_lists = gp.qs.n_chunks * 2; es.tau0 = nullptr; es.cnt = nullptr;
     int rcs = (gp.qs.pair == 2) ? launch_xw<2, XW_KK, XwTopK<KT>>(tx, tw, gp.qs, Q, gp.n_sample, D, es, st, "umma K4 gallery sample scan (cta pair)", mfmt)
                                 : launch_xw<1, XW_KK, XwTopK<KT>>(tx, tw, gp.qs, Q, gp.n_sample, D, es, st, "umma K4 gallery sample scan", mfmt);
     if (rcs) return rcs;
@@ -714,6 +731,13 @@ static int gallery_scan_kt(const GalleryScanPlan& gp, const void* g16, const CUt
   int rc = (gp.q.pair == 2) ? launch_xw<2, XW_KK, XwTopK<KT>>(tx, tw, gp.q, Q, N, D, ep, st, "umma K4 gallery scan (cta pair)", mfmt, false, g16, (int64_t)D * 2)
                             : launch_xw<1, XW_KK, XwTopK<KT>>(tx, tw, gp.q, Q, N, D, ep, st, "umma K4 gallery scan", mfmt, false, g16, (int64_t)D * 2);
   if (rc) return rc;
+  if (gp.compact) {
+    launch_pdl(gallery_select_warp_kernel<KT>, dim3((unsigned)ceil_div(Q, 4)), dim3(128), 0, st, (const float*)ckey, (const int32_t*)cidx,
+               (const int32_t*)cnt, q, g, q_inv, g_inv, (const float*)(bias ? bias + N : nullptr), qbad, Q, D, k, metric, fmt, thresh,
+               index_offset, idx, score, accept, redo, redo_count);
+    B200F_LAUNCH_OK("gallery_select_warp_kernel");
+    return B200F_OK;
+  }
   const int n_cand = gp.n_lists * KT;
   const size_t smem = (size_t)n_cand * 16;                 // candidates + survivors, (key, idx) each
   auto kern = gallery_select_kernel<float, KT>;
@@ -744,6 +768,7 @@ int gallery_scan_select(const float* q, const float* g, const void* g16, const f
   int32_t* sidx = reinterpret_cast<int32_t*>(ws + gp.off_sidx);
   float* tau0 = reinterpret_cast<float*>(ws + gp.off_tau);
   uint8_t* qbad = reinterpret_cast<uint8_t*>(ws + gp.off_qbad);
+  int32_t* cnt = reinterpret_cast<int32_t*>(ws + gp.off_cnt);
   launch_pdl(prepare_vec_ok(q, q16, D) ? gallery_prepare_vec8_kernel<float> : gallery_prepare_kernel<float>, dim3((unsigned)ceil_div(Q, 8)),
              dim3(256), 0, st, q, Q, D, B200F_METRIC_L2EPS, fmt, q16, (float*)nullptr, qbad);
   B200F_LAUNCH_OK("gallery_prepare_kernel (queries)");
@@ -751,7 +776,7 @@ int gallery_scan_select(const float* q, const float* g, const void* g16, const f
   int rc = tmap_kmajor(&tx, q16, Q, D, D, XW_M); if (rc) return rc;
   rc = tmap_kmajor(&tw, g16, N, D, D, XW_WROWS); if (rc) return rc;
 #define B200F_SCAN(KT) gallery_scan_kt<KT>(gp, g16, tx, tw, q, g, bias, q_inv, g_inv, Q, N, index_offset, D, k, metric, fmt, thresh, idx, \
-                                           score, accept, redo, redo_count, ckey, cidx, skey, sidx, tau0, qbad, st)
+                                           score, accept, redo, redo_count, ckey, cidx, skey, sidx, tau0, qbad, cnt, st)
   if (gp.KT == 8) return B200F_SCAN(8);
   if (gp.KT == 16) return B200F_SCAN(16);
   return B200F_SCAN(32);
@@ -853,6 +878,7 @@ int b200f_set_tunable(const char* name, int value) {
   if (n == "l2_hints") { if (value < 0) return g_l2_hints.load(); return g_l2_hints.exchange(value); }
   if (n == "k2_groups") { if (value != 1 && value != 2) return g_k2_groups.load(); return g_k2_groups.exchange(value); }
   if (n == "k3b_groups") { if (value != 1 && value != 2) return g_k3b_groups.load(); return g_k3b_groups.exchange(value); }
+  if (n == "gallery_compact") { if (value != 0 && value != 1) return g_gallery_compact.load(); return g_gallery_compact.exchange(value); }
   if (n == "early") { if (value != 0 && value != 1) return g_early.load(); return g_early.exchange(value); }
   if (n == "epi_groups") { if (value != 1 && value != 2) return g_epi_groups.load(); return g_epi_groups.exchange(value); }
 #ifdef B200F_PROBES

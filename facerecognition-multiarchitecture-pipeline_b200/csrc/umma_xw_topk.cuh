@@ -38,6 +38,11 @@ struct XwTopK {
     int n_lists;                // n_chunks * 2
     const float* tau0;          // [Q] upper bound of each query's KT-th best key from a scanned SAMPLE of the
                                 // gallery (gallery_tau_kernel), or NULL
+    // compact output (cnt != NULL; needs tau0): a list appends only its non-empty entries to its query's candidate
+    // array -- with the sample bound in place a query ends up with a few dozen candidates instead of n_lists * KT
+    // mostly empty slots, and gallery_select_warp_kernel ranks them with one WARP per query.  cnt[q] counts what was
+    // offered (the tau kernel zeroes it); entries beyond `cap` are dropped and the query goes to the exact engine.
+    int32_t* cnt; int cap;
   };
   struct State { float key[KT]; int32_t idx[KT]; float lim0; bool row_ok; };
 
@@ -115,6 +120,19 @@ struct XwTopK {
 
   static __device__ __forceinline__ void item_end(State& st, const Params& ep, const XwParams&, const XwItem& it, float*) {
     if (!st.row_ok) return;
+    if (ep.cnt != nullptr) {
+      int nv = 0;
+#pragma unroll
+      for (int s = 0; s < KT; ++s) nv += (st.idx[s] >= 0) ? 1 : 0;       // sorted: the valid entries come first
+      if (nv == 0) return;
+      const int pos = atomicAdd(ep.cnt + it.row, nv);
+      float* dk = ep.cand_key + (int64_t)it.row * ep.cap;
+      int32_t* di = ep.cand_idx + (int64_t)it.row * ep.cap;
+#pragma unroll
+      for (int s = 0; s < KT; ++s)
+        if (s < nv && pos + s < ep.cap) { dk[pos + s] = st.key[s]; di[pos + s] = st.idx[s]; }
+      return;
+    }
     const int64_t base = ((int64_t)it.row * ep.n_lists + it.chunk * 2 + it.half) * KT;
 #pragma unroll
     for (int s = 0; s < KT; s += 4) {
@@ -123,6 +141,235 @@ struct XwTopK {
     }
   }
 };
+
+// Sample pre-pass, single row group: only the SMALLEST key of each (CTA, column half) is kept -- the bound below needs
+// nothing else, and the full KT-deep sorted insertion of XwTopK was most of the pre-pass (24 us for one tile per CTA).
+struct XwMinKey {
+  struct Params { const float* bias; float mult; float* out; int n_lists; };
+  struct State { float m; bool row_ok; };
+  static __device__ __forceinline__ void item_begin(State& st, const Params&, const XwParams& p, const XwItem& it) {
+    st.m = 3.0e38f; st.row_ok = it.row < p.B;
+  }
+  static __device__ __forceinline__ void tile_begin(State&, const Params&, const XwParams&, const XwItem&, int, int, int) {}
+  static __device__ __forceinline__ void slice(State& st, const Params& ep, const XwParams& p, const XwItem&,
+                                               float (&v)[32], int cls0) {
+    const int cc = min(32, p.C - cls0);
+    float m4[4] = {3.0e38f, 3.0e38f, 3.0e38f, 3.0e38f};
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float a = (ep.bias != nullptr) ? fmaf(v[j + u], ep.mult, (j + u < cc) ? __ldg(ep.bias + cls0 + j + u) : 0.f)
+                                             : v[j + u] * ep.mult;
+        m4[u] = fminf(m4[u], (j + u < cc) ? a : 3.0e38f);      // NaN keys never win an fminf
+      }
+    }
+    st.m = fminf(st.m, fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3])));
+  }
+  static __device__ __forceinline__ void item_end(State& st, const Params& ep, const XwParams&, const XwItem& it, float*) {
+    if (st.row_ok) ep.out[(int64_t)it.row * ep.n_lists + it.chunk * 2 + it.half] = st.m;
+  }
+};
+
+// tau0[q] = KT-th smallest of the query's n_lists (<= 256) per-list minima: KT DISTINCT gallery rows have a key <= it
+// (the lists cover disjoint rows), so it bounds the KT-th best key of the whole gallery.  One warp per query, the
+// values in registers, KT rounds of a shuffle arg-min.  Also zeroes the query's candidate counter of the compact scan.
+template <int KT>
+__global__ void __launch_bounds__(128)
+gallery_tau_min_kernel(const float* __restrict__ key_min, int n_lists, int64_t Q, float* __restrict__ tau0,
+                       int32_t* __restrict__ cnt) {
+  pdl_trigger(); pdl_wait();
+  constexpr int L = 8;
+  const int lane = threadIdx.x & 31;
+  const int64_t qi = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (qi >= Q) return;
+  float v[L];
+#pragma unroll
+  for (int u = 0; u < L; ++u) { const int l = lane + 32 * u; v[u] = (l < n_lists) ? __ldg(key_min + qi * n_lists + l) : INFINITY; }
+  float last = INFINITY;
+  for (int r = 0; r < KT; ++r) {
+    float k = INFINITY; int who = 1 << 20;
+#pragma unroll
+    for (int u = 0; u < L; ++u) if (v[u] < k) { k = v[u]; who = lane + 32 * u; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ok = __shfl_xor_sync(0xffffffffu, k, o);
+      const int ow = __shfl_xor_sync(0xffffffffu, who, o);
+      if (ok < k || (ok == k && ow < who)) { k = ok; who = ow; }
+    }
+    if (who >= (1 << 20)) { last = INFINITY; break; }        // fewer than KT ranked lists: no bound
+#pragma unroll
+    for (int u = 0; u < L; ++u) if (who == lane + 32 * u) v[u] = INFINITY;
+    last = k;
+  }
+  if (lane == 0) { tau0[qi] = last; if (cnt != nullptr) cnt[qi] = 0; }
+}
+
+// ---- select, compact form: ONE WARP per query ranks the query's (few) candidates, re-scores the KT best exactly and
+// proves the top-k (same arithmetic and proof as gallery_select_kernel below; that kernel took 41-48 us for 128
+// queries: one block per query walking n_lists * KT mostly empty slots through shared memory with a dozen barriers).
+constexpr int GALLERY_COMPACT_CAP = 512;
+template <int KT>
+__global__ void __launch_bounds__(128)
+gallery_select_warp_kernel(const float* __restrict__ cand_key, const int32_t* __restrict__ cand_idx,
+                           const int32_t* __restrict__ cnt, const float* __restrict__ q, const float* __restrict__ g,
+                           const float* __restrict__ q_inv, const float* __restrict__ g_inv,
+                           const float* __restrict__ gmax_ptr, const uint8_t* __restrict__ q_bad, int64_t Q, int D, int k,
+                           int metric, int fmt, float thresh, int64_t index_offset, int64_t* __restrict__ idx_out,
+                           float* __restrict__ score_out, uint8_t* __restrict__ accept, uint8_t* __restrict__ redo,
+                           int32_t* __restrict__ redo_count) {
+  pdl_trigger(); pdl_wait();
+  static_assert(KT <= 32, "one winner per lane");
+  constexpr int CAP = GALLERY_COMPACT_CAP, PER = CAP / 32;
+  const int lane = threadIdx.x & 31;
+  const int64_t qi = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (qi >= Q) return;
+  const bool cosine = (metric == B200F_METRIC_COS);
+  const int n_all = __ldcg(cnt + qi);
+  const bool overflow = n_all > CAP;
+  const int n = overflow ? CAP : n_all;
+  float ck[PER]; int ci[PER];
+#pragma unroll
+  for (int u = 0; u < PER; ++u) {
+    const int i = lane + 32 * u;
+    const bool in = i < n;
+    ck[u] = in ? __ldcg(cand_key + qi * CAP + i) : INFINITY;
+    ci[u] = in ? __ldcg(cand_idx + qi * CAP + i) : INT32_MAX;
+  }
+  // the query row: D <= 512, lane owns elements 4 * (lane + 32 j) .. + 3
+  const int nvec = D >> 2;
+  float4 qv[4];
+  float nq = 0.f, sq = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = lane + 32 * j;
+    qv[j] = (c < nvec) ? __ldg(reinterpret_cast<const float4*>(q + qi * D) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    nq = fmaf(qv[j].x, qv[j].x, nq); nq = fmaf(qv[j].y, qv[j].y, nq); nq = fmaf(qv[j].z, qv[j].z, nq); nq = fmaf(qv[j].w, qv[j].w, nq);
+    sq += (qv[j].x + qv[j].y) + (qv[j].z + qv[j].w);
+  }
+  nq = warp_sum(nq); sq = warp_sum(sq);
+  // ---- the KT best approximate keys by (key, index); lane r keeps the r-th
+  float wk = INFINITY; int wi = -1;
+  {
+    float taken_k = -INFINITY; int taken_i = -1;
+    for (int r = 0; r < KT; ++r) {
+      float bk = INFINITY; int bi = INT32_MAX;
+#pragma unroll
+      for (int u = 0; u < PER; ++u) {
+        const bool after = (ck[u] > taken_k) || (ck[u] == taken_k && ci[u] > taken_i);
+        if (ci[u] != INT32_MAX && after && (ck[u] < bk || (ck[u] == bk && ci[u] < bi))) { bk = ck[u]; bi = ci[u]; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ok = __shfl_xor_sync(0xffffffffu, bk, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ok < bk || (ok == bk && oi < bi)) { bk = ok; bi = oi; }
+      }
+      if (bi == INT32_MAX) break;                             // uniform: candidates exhausted
+      if (lane == r) { wk = bk; wi = bi; }
+      taken_k = bk; taken_i = bi;
+    }
+  }
+  // ---- exact re-score (reference formula, fp32), four winners' rows in flight at a time
+  float ex = INFINITY;
+  for (int r0 = 0; r0 < KT; r0 += 4) {
+    int id[4]; float4 y[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      id[u] = __shfl_sync(0xffffffffu, wi, (r0 + u) & 31);
+      if (r0 + u >= KT) id[u] = -1;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = lane + 32 * j;
+        y[u][j] = (id[u] >= 0 && c < nvec) ? __ldg(reinterpret_cast<const float4*>(g + (int64_t)id[u] * D) + c)
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = lane + 32 * j;
+        if (c < nvec) {
+          if (cosine) {
+            acc = fmaf(qv[j].x, y[u][j].x, acc); acc = fmaf(qv[j].y, y[u][j].y, acc);
+            acc = fmaf(qv[j].z, y[u][j].z, acc); acc = fmaf(qv[j].w, y[u][j].w, acc);
+          } else {
+            float d0 = qv[j].x - y[u][j].x + GALLERY_EPS, d1 = qv[j].y - y[u][j].y + GALLERY_EPS;
+            float d2 = qv[j].z - y[u][j].z + GALLERY_EPS, d3 = qv[j].w - y[u][j].w + GALLERY_EPS;
+            acc = fmaf(d0, d0, acc); acc = fmaf(d1, d1, acc); acc = fmaf(d2, d2, acc); acc = fmaf(d3, d3, acc);
+          }
+        }
+      }
+      const float tot = warp_sum(acc);
+      float e;
+      if (id[u] < 0) e = INFINITY;
+      else if (cosine) e = -(tot * (q_inv ? q_inv[qi] : 1.0f) * (g_inv ? g_inv[id[u]] : 1.0f));
+      else e = sqrtf(tot);
+      if (lane == r0 + u) ex = e;
+    }
+  }
+  // ---- order the KT winners by (exact key, index): NaN keys behind the ranked ones, empty slots last
+  int rank = 0;
+  for (int s = 0; s < KT; ++s) {
+    const float ks = __shfl_sync(0xffffffffu, ex, s);
+    const int is = __shfl_sync(0xffffffffu, wi, s);
+    // does winner s come before mine?
+    bool first;
+    if (is < 0) first = (wi < 0) && (s < lane);
+    else if (wi < 0) first = true;
+    else if (ks != ks) first = (ex != ex) && (is < wi);
+    else first = (ex != ex) || ks < ex || (ks == ex && is < wi);
+    if (s != lane && first) ++rank;
+  }
+  float s_ex = INFINITY, s_wk = INFINITY; int s_wi = -1;      // lane p receives the winner ranked p
+  for (int s = 0; s < KT; ++s) {
+    const int rs = __shfl_sync(0xffffffffu, rank, s);
+    const float es = __shfl_sync(0xffffffffu, ex, s), ws = __shfl_sync(0xffffffffu, wk, s);
+    const int is = __shfl_sync(0xffffffffu, wi, s);
+    if (rs == lane) { s_ex = es; s_wk = ws; s_wi = is; }
+  }
+  // ---- proof: every row the scan dropped has an approximate key >= the worst kept one
+  const bool valid = (lane < KT) && s_wi >= 0;
+  float a_excl = warp_max(valid ? s_wk : -INFINITY);
+  const int n_valid = __popc(__ballot_sync(0xffffffffu, valid));
+  const int kk = min(k, n_valid);
+  const float ek = __shfl_sync(0xffffffffu, s_ex, (kk > 0 ? kk - 1 : 0) & 31);
+  const bool any_marked = (q_bad != nullptr && q_bad[qi] != 0) ||
+                          (gmax_ptr != nullptr && reinterpret_cast<const int*>(gmax_ptr)[1] != 0);
+  bool verified = !any_marked && !overflow;
+  if (verified && n_valid == KT) {                             // something may have been excluded
+    const float qn = sqrtf(nq);
+    const float gmax = gmax_ptr ? __int_as_float(*reinterpret_cast<const int*>(gmax_ptr)) : 1.0f;
+    float exact_in_approx_units, delta;
+    const float rel = (fmt == B200F_OPERAND_FP16) ? GALLERY_DOT_ERR_FP16 : GALLERY_DOT_ERR;
+    const float abs_e = (fmt == B200F_OPERAND_FP16) ? GALLERY_ABS_ERR_FP16 * sqrtf((float)D) : 0.f;
+    if (cosine) {
+      const float qvn = q_inv ? q_inv[qi] : 1.0f;
+      exact_in_approx_units = (qvn > 0.f) ? ek / qvn : -INFINITY;
+      delta = rel * qn * 1.01f + abs_e * (qn + 1.0f);
+    } else {
+      exact_in_approx_units = ek * ek - (nq + 2.0f * GALLERY_EPS * sq + (float)D * GALLERY_EPS * GALLERY_EPS);
+      delta = 2.0f * (rel * qn * gmax + abs_e * (qn + gmax)) + 1e-6f * (nq + gmax * gmax + 1.0f);
+    }
+    verified = (ek == ek) && (exact_in_approx_units < a_excl - delta);
+  }
+  if (lane < k) {
+    const bool ok = (lane < KT) && s_wi >= 0 && s_ex == s_ex;
+    idx_out[qi * k + lane] = ok ? (index_offset + s_wi) : -1;
+    score_out[qi * k + lane] = ok ? (cosine ? -s_ex : s_ex) : (cosine ? -INFINITY : INFINITY);
+  }
+  if (lane == 0) {
+    if (accept != nullptr) {
+      const bool ok = s_wi >= 0 && s_ex == s_ex;
+      const float best = cosine ? -s_ex : s_ex;
+      accept[qi] = ok && (cosine ? (best >= thresh) : (best <= thresh));
+    }
+    redo[qi] = verified ? 0 : 1;
+    if (!verified && redo_count != nullptr) atomicAdd(redo_count, 1);
+  }
+}
 
 // ---- prepare: rows -> 16-bit scan operand (+ bias, + max row norm) -------------------------------------
 // One warp per row (D <= 512).  This scalar form takes any D; rows of whole 8-element chunks at 16-byte aligned
