@@ -6,6 +6,8 @@
 #include <stdio.h>
 #include <string>
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX 3: ranges cost a null-pointer test unless a profiler injected itself
+
 #include "../../include/b200face.h"
 
 namespace b200f {
@@ -32,6 +34,17 @@ void count_launch();   // diagnostic counter behind b200f_launch_count()
                            cudaGetErrorString(_e));                                  \
     ::b200f::count_launch();                                                         \
   } while (0)
+
+// ---- NVTX ranges around every C-ABI stage (nsys / ncu timelines name the stages) ----------------------
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
+#define B200F_NVTX_CAT2(a, b) a##b
+#define B200F_NVTX_CAT(a, b) B200F_NVTX_CAT2(a, b)
+#define B200F_NVTX(name) ::b200f::NvtxRange B200F_NVTX_CAT(b200f_nvtx_range_, __LINE__)(name)
 
 // ---- programmatic dependent launch -----------------------------------------------------------------------
 // Every kernel of the head step is short (3-100 us) and the step is a chain of a dozen of them: with plain stream

@@ -99,6 +99,7 @@ int b200f_gallery_topk(const void* q, const void* g, int dtype, const float* q_i
                        int64_t Q, int64_t N_local, int64_t index_offset, int D, int k, int metric, float thresh,
                        int engine, int64_t* idx, float* score, uint8_t* accept, void* workspace,
                        size_t workspace_bytes, void* stream) {
+  B200F_NVTX("b200f_gallery_topk");
   if (!dtype_ok(dtype)) return fail(B200F_ERR_ARG, "gallery_topk: bad dtype");
   if (Q < 0 || N_local < 0 || D <= 0) return fail(B200F_ERR_ARG, "gallery_topk: bad shape");
   if (k < 1 || k > 16) return fail(B200F_ERR_ARG, "gallery_topk: k=%d outside [1,16]", k);
@@ -123,6 +124,7 @@ int b200f_gallery_has_tc(int D) { return umma::gallery_tc_supported(D) ? 1 : 0; 
 
 int b200f_gallery_prepare(const void* g, int dtype, int64_t N, int D, int metric, int operand_fmt, void* g16, float* bias,
                           void* stream) {
+  B200F_NVTX("b200f_gallery_prepare");
   if (!dtype_ok(dtype)) return fail(B200F_ERR_ARG, "gallery_prepare: bad dtype");
   if (N < 0 || D <= 0) return fail(B200F_ERR_ARG, "gallery_prepare: bad shape");
   if (metric != B200F_METRIC_L2EPS && metric != B200F_METRIC_COS) return fail(B200F_ERR_ARG, "gallery_prepare: bad metric");
@@ -142,6 +144,7 @@ int b200f_gallery_topk_tc(const void* q, const void* g, const void* g16, const f
                           const float* g_inv, int64_t Q, int64_t N_local, int64_t index_offset, int D, int k, int metric,
                           int operand_fmt, float thresh, int64_t* idx, float* score, uint8_t* accept, int32_t* redo_count,
                           void* workspace, size_t workspace_bytes, void* stream) {
+  B200F_NVTX("b200f_gallery_topk_tc");
   if (Q < 0 || N_local <= 0 || D <= 0) return fail(B200F_ERR_ARG, "gallery_topk_tc: bad shape");
   if (k < 1 || k > 16) return fail(B200F_ERR_ARG, "gallery_topk_tc: k=%d outside [1,16]", k);
   if (metric != B200F_METRIC_L2EPS && metric != B200F_METRIC_COS) return fail(B200F_ERR_ARG, "gallery_topk_tc: bad metric");
@@ -166,6 +169,7 @@ int b200f_gallery_topk_tc(const void* q, const void* g, const void* g16, const f
 
 int b200f_gallery_merge(const int64_t* idx_all, const float* score_all, int P, int64_t Q, int k, int metric,
                         float thresh, int64_t* idx, float* score, uint8_t* accept, void* stream) {
+  B200F_NVTX("b200f_gallery_merge");
   if (P < 0 || Q < 0 || k < 1 || k > 16) return fail(B200F_ERR_ARG, "gallery_merge: bad shape");
   if (Q == 0) return B200F_OK;
   if ((P > 0 && (!idx_all || !score_all)) || !idx || !score) return fail(B200F_ERR_ARG, "gallery_merge: null pointer");

@@ -238,6 +238,7 @@ int b200f_arcface_fwd(const void* x, const void* w, int dtype, const float* inv_
                       const b200f_head_cfg* cfg, float* row_stats, float* row_best, int64_t* row_argmax,
                       float* cos_minmax, int32_t* nan_flag, float* logits_or_null, int64_t ld_logits,
                       void* workspace, size_t workspace_bytes, void* stream) {
+  B200F_NVTX("b200f_arcface_fwd");
   return arcface_fwd_impl("arcface_fwd", x, w, dtype, inv_nx, inv_nw, label, B, C_local, class_offset, D, cfg, row_stats,
                           row_best, row_argmax, cos_minmax, nan_flag, logits_or_null, ld_logits, nullptr, workspace,
                           workspace_bytes, stream);
@@ -248,6 +249,7 @@ int b200f_arcface_fwd_loss(const void* x, const void* w, int dtype, const float*
                            const b200f_head_cfg* cfg, const b200f_hook_cfg* hook, float* row_stats, float* row_best,
                            int64_t* row_argmax, float* cos_minmax, int32_t* nan_flag, float* lse, float* loss,
                            float* pq_norm2, float* out4, void* workspace, size_t workspace_bytes, void* stream) {
+  B200F_NVTX("b200f_arcface_fwd_loss");
   if (!hook || !lse || !loss || !pq_norm2 || !out4) return fail(B200F_ERR_ARG, "arcface_fwd_loss: null pointer");
   if (cfg && C_local != cfg->num_classes_total)
     return fail(B200F_ERR_ARG, "arcface_fwd_loss: a class shard needs the cross-shard sum first (b200f_arcface_fwd, "
@@ -262,6 +264,7 @@ int b200f_arcface_bwd(const void* x, const void* w, int dtype, const float* inv_
                       const float* dlogits_or_null, int64_t ld_dlogits, int64_t B,
                       int64_t C_local, int64_t class_offset, int D, const b200f_head_cfg* cfg, float* dxhat,
                       float* dw, void* workspace, size_t workspace_bytes, void* stream) {
+  B200F_NVTX("b200f_arcface_bwd");
   return arcface_bwd_impl("arcface_bwd", x, w, dtype, inv_nx, inv_nw, label, lse, grad_scale, dlogits_or_null, ld_dlogits, B,
                           C_local, class_offset, D, cfg, dxhat, dw, nullptr, workspace, workspace_bytes, stream);
 }
@@ -272,6 +275,7 @@ int b200f_arcface_bwd_dx(const void* x, const void* w, int dtype, const float* i
                          int64_t C_local, int64_t class_offset, int D, const b200f_head_cfg* cfg, float* dxhat,
                          float* dw, const void* x_raw_or_null, int x_raw_dtype, float* dx, void* dx_bf16_or_null,
                          void* workspace, size_t workspace_bytes, void* stream) {
+  B200F_NVTX("b200f_arcface_bwd_dx");
   if (!dx || !inv_nx) return fail(B200F_ERR_ARG, "arcface_bwd_dx: dx and inv_nx are required");
   if (x_raw_or_null && !dtype_ok(x_raw_dtype)) return fail(B200F_ERR_ARG, "arcface_bwd_dx: bad x_raw dtype %d", x_raw_dtype);
   const umma::HeadDx hdx{x_raw_or_null, x_raw_dtype, inv_nx, dx, dx_bf16_or_null};

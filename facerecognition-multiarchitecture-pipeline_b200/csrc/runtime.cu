@@ -93,6 +93,7 @@ int b200f_has_tcgen05(void) {
 
 int b200f_l2norm_rows(const void* in, int in_dtype, int64_t rows, int dim, float eps, float* inv_norm,
                       void* out_or_null, int out_dtype, float out_scale, void* stream) {
+  B200F_NVTX("b200f_l2norm_rows");
   if (!dtype_ok(in_dtype)) return fail(B200F_ERR_ARG, "l2norm_rows: bad input dtype %d", in_dtype);
   if (out_or_null && !(dtype_ok(out_dtype) || out_dtype == B200F_F16N))
     return fail(B200F_ERR_ARG, "l2norm_rows: bad output dtype %d", out_dtype);
@@ -117,6 +118,7 @@ int b200f_l2norm_rows(const void* in, int in_dtype, int64_t rows, int dim, float
 int b200f_l2norm_rows_pair(const void* in0, int64_t rows0, float* inv0, void* out0, const void* in1, int64_t rows1,
                            float* inv1, void* out1, int in_dtype, int dim, float eps, int out_dtype, float out_scale,
                            void* stream) {
+  B200F_NVTX("b200f_l2norm_rows_pair");
   if (rows0 <= 0 || rows1 <= 0 || !in0 || !in1 || !inv0 || !inv1 || !out0 || !out1)
     return fail(B200F_ERR_ARG, "l2norm_rows_pair: both row sets need input, inverse norms and output");
   const bool al = ((reinterpret_cast<uintptr_t>(in0) | reinterpret_cast<uintptr_t>(in1) | reinterpret_cast<uintptr_t>(out0) |
@@ -137,6 +139,7 @@ int b200f_l2norm_rows_pair(const void* in0, int64_t rows0, float* inv0, void* ou
 
 int b200f_l2norm_bwd(const void* v, int dtype, float v_scale, const float* inv_norm, const float* dvhat, int64_t rows,
                      int dim, float* dv, void* dv_bf16_or_null, void* stream) {
+  B200F_NVTX("b200f_l2norm_bwd");
   if (!dtype_ok(dtype) && dtype != B200F_F16N) return fail(B200F_ERR_ARG, "l2norm_bwd: bad dtype");
   if (rows < 0 || dim <= 0) return fail(B200F_ERR_ARG, "l2norm_bwd: bad shape");
   if (rows == 0) return B200F_OK;
@@ -156,6 +159,7 @@ int b200f_l2norm_bwd(const void* v, int dtype, float v_scale, const float* inv_n
 
 int b200f_arcface_loss(const float* row_stats, int64_t B, const b200f_head_cfg* cfg, float* lse, float* loss,
                        float* pq_norm2, void* stream) {
+  B200F_NVTX("b200f_arcface_loss");
   if (!row_stats || !cfg || B <= 0) return fail(B200F_ERR_ARG, "arcface_loss: bad argument");
   launch_pdl(rowops::loss_kernel, dim3(1), dim3(1024), 0, as_stream(stream), row_stats, B, cfg->s_eff,
              cfg->label_smoothing, (double)cfg->num_classes_total, lse, loss, pq_norm2, rowops::HookCfg{0, 1.f, 1, 0},
@@ -166,6 +170,7 @@ int b200f_arcface_loss(const float* row_stats, int64_t B, const b200f_head_cfg* 
 
 int b200f_arcface_loss_hook(const float* row_stats, int64_t B, const b200f_head_cfg* cfg, const b200f_hook_cfg* hook,
                             float* lse, float* loss, float* pq_norm2, float* out4, void* stream) {
+  B200F_NVTX("b200f_arcface_loss_hook");
   if (!row_stats || !cfg || !hook || !out4 || B <= 0) return fail(B200F_ERR_ARG, "arcface_loss_hook: bad argument");
   launch_pdl(rowops::loss_kernel, dim3(1), dim3(1024), 0, as_stream(stream), row_stats, B, cfg->s_eff,
              cfg->label_smoothing, (double)cfg->num_classes_total, lse, loss, pq_norm2,
@@ -177,6 +182,7 @@ int b200f_arcface_loss_hook(const float* row_stats, int64_t B, const b200f_head_
 int b200f_arcface_hook_scale(const float* pq_norm2, const float* upstream, int64_t B, float s_eff,
                              int hook_enabled, float max_grad_norm, int phase, int epoch, float* out4,
                              void* stream) {
+  B200F_NVTX("b200f_arcface_hook_scale");
   if (!pq_norm2 || !out4 || B <= 0) return fail(B200F_ERR_ARG, "arcface_hook_scale: bad argument");
   launch_pdl(rowops::hook_scale_kernel, dim3(1), dim3(1), 0, as_stream(stream), pq_norm2, upstream, (double)B, s_eff,
              rowops::HookCfg{hook_enabled, max_grad_norm, phase, epoch}, out4);
@@ -186,6 +192,7 @@ int b200f_arcface_hook_scale(const float* pq_norm2, const float* upstream, int64
 
 int b200f_bn_stats(const void* z, int dtype, int64_t rows, int dim, float eps, float momentum, float* running_mean,
                    float* running_var, float* mean_out, float* invstd_out, void* stream) {
+  B200F_NVTX("b200f_bn_stats");
   if (!dtype_ok(dtype)) return fail(B200F_ERR_ARG, "bn_stats: bad dtype");
   if (rows <= 0 || dim <= 0 || !z || !mean_out || !invstd_out) return fail(B200F_ERR_ARG, "bn_stats: bad argument");
   const unsigned grid = (unsigned)ceil_div(dim, 32);
@@ -202,6 +209,7 @@ int b200f_bn_stats(const void* z, int dtype, int64_t rows, int dim, float eps, f
 int b200f_tail_fwd(const void* z, int dtype, int64_t rows, int dim, const float* gamma, const float* beta, const float* mean,
                    const float* stat, int stat_is_var, float bn_eps, const uint8_t* mask_or_null, float keep_scale, float norm_eps,
                    float out_scale, float* y_or_null, void* yhat16_or_null, float* emb_or_null, float* inv_norm, void* stream) {
+  B200F_NVTX("b200f_tail_fwd");
   if (!dtype_ok(dtype)) return fail(B200F_ERR_ARG, "tail_fwd: bad dtype");
   if (rows <= 0 || dim <= 0 || dim % 4 != 0 || dim > 1024) return fail(B200F_ERR_ARG, "tail_fwd: rows > 0, dim %% 4 == 0, dim <= 1024");
   if (!z || !gamma || !beta || !mean || !stat || !inv_norm) return fail(B200F_ERR_ARG, "tail_fwd: null pointer");
@@ -217,6 +225,7 @@ int b200f_tail_fwd(const void* z, int dtype, int64_t rows, int dim, const float*
 int b200f_tail_bwd(const float* dy, const uint8_t* mask_or_null, float keep_scale, const void* z, int dtype, const float* mean,
                    const float* stat, int stat_is_var, float bn_eps, const float* gamma, int batch_stats, int64_t rows, int dim,
                    float* dgamma, float* dbeta, float* dz, void* stream) {
+  B200F_NVTX("b200f_tail_bwd");
   if (!dtype_ok(dtype)) return fail(B200F_ERR_ARG, "tail_bwd: bad dtype");
   if (rows <= 0 || dim <= 0 || !dy || !z || !mean || !stat || !gamma || !dgamma || !dbeta || !dz)
     return fail(B200F_ERR_ARG, "tail_bwd: bad argument");
@@ -248,6 +257,7 @@ int b200f_tail_bwd(const float* dy, const uint8_t* mask_or_null, float keep_scal
 int b200f_head_adamw(float* w, const float* dw, float* m, float* v, float* vmax, int64_t rows, int dim, double lr,
                      double beta1, double beta2, double eps, double weight_decay, int64_t step, const float* grad_scale,
                      void* w_hat_out, float out_scale, float norm_eps, float* inv_norm, void* stream) {
+  B200F_NVTX("b200f_head_adamw");
   if (rows < 0 || dim <= 0 || step < 1) return fail(B200F_ERR_ARG, "head_adamw: bad shape / step (rows=%lld dim=%d step=%lld)",
                                                     (long long)rows, dim, (long long)step);
   if (rows == 0) return B200F_OK;

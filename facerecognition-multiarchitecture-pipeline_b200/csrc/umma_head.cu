@@ -459,6 +459,7 @@ int head_fwd(const void* xh, const void* wh, const int64_t* label, int64_t B, in
   const int eg = g_k2_groups.load(std::memory_order_relaxed);
   const int64_t wrb = (int64_t)D * 2;
   const int k2_hint = (g_l2_hints.load(std::memory_order_relaxed) & 16) ? 2 : 0;
+  B200F_NVTX("K2 cosine GEMM + margin + softmax statistics");
   stage_reset(EV_K2);
   stage_event(EV_K2, false, st);
   if (eg == 2) {
@@ -524,6 +525,7 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
 #ifdef B200F_PROBES
     eg.ablate = g_k3a_ablate.load(std::memory_order_relaxed);
 #endif
+    { B200F_NVTX("K3a logit gradient (recompute + G^T)");
     stage_event(EV_K3A, false, st);
     if (g_epi_groups.load(std::memory_order_relaxed) == 2) {
       XwBwdGT2::Params e2{};
@@ -539,12 +541,13 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
       rc = (qg.pair == 2) ? launch_xw<2, XW_SWAP, XwBwdGT>(tx_k, tw_k, qg, B, cnt, D, eg, st, "umma K3a logit-grad (cta pair)", FMT_F16, false, wc, wrb, true, k3a_whint)
                           : launch_xw<1, XW_SWAP, XwBwdGT>(tx_k, tw_k, qg, B, cnt, D, eg, st, "umma K3a logit-grad", FMT_F16, false, wc, wrb, true, k3a_whint);
     }
-    stage_event(EV_K3A, true, st);
+    stage_event(EV_K3A, true, st); }
     if (rc) return rc;
     // --- K3b: dW[c0 + c, d] = inv_nw_c (sum_b G^T[c, b] x_hat[b, d] - w_hat[c, d] r_c), class-major (the thread owns a
     //     class row), normalise-backward fused; its coefficients { inv_nw_c / (S g_scale), r_c } are formed in the epilogue
     //     from K3a's partials (CoefSrc)
     const CoefSrc coef{r_part, qg.m_groups * 2, pl.Cc, inv_nw, grad4, S};
+    { B200F_NVTX("K3b dW = G^T x_hat (+ normalise-backward of W)");
     stage_event(EV_K3B, false, st);
     if (pl.fused_dw) {                                      // x_hat^T resident, G^T rows streamed
       CUtensorMap tg_k;
@@ -587,7 +590,7 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
                         : launch_gemm<1, false, true, EpiDwNorm>(tg_km, tx_mn, pw, ew, st, "umma K3b dW (streamed)");
       if (rc) return rc;
     }
-    stage_event(EV_K3B, true, st);
+    stage_event(EV_K3B, true, st); }
     // --- K3c: dx_hat partials = G[:, k-range] w_hat[c0 + k-range, :]   (A = G read MN-major from G^T)
     CUtensorMap tg_mn, tw_mn;
     rc = tmap_mnmajor(&tg_mn, G, B, cnt, pl.ldg); if (rc) return rc;
@@ -649,8 +652,7 @@ static GalleryScanPlan gallery_scan_plan(int64_t Q, int64_t N, int D, int k) {
   g.KT = k <= 1 ? 8 : (k <= 6 ? 16 : 32);
   g.n_lists = g.q.n_chunks * 2;
   size_t off = 0;
-  size_t per_q = (size_t)g.n_lists * g.KT;                  // candidate slots per query: padded lists, or the compact array
-  if (per_q < (size_t)GALLERY_COMPACT_CAP) per_q = GALLERY_COMPACT_CAP;
+  const size_t per_q = (size_t)g.n_lists * g.KT;            // candidate slots per query: padded lists, or the compact array
   g.off_q16 = off;  off += align_up(2 * (size_t)Q * D, 1024);
   g.off_ckey = off; off += align_up(sizeof(float) * (size_t)Q * per_q, 256);
   g.off_cidx = off; off += align_up(sizeof(int32_t) * (size_t)Q * per_q, 256);
@@ -715,7 +717,7 @@ static int gallery_scan_kt(const GalleryScanPlan& gp, const void* g16, const CUt
     if (rcs) return rcs;
     launch_pdl(gallery_tau_min_kernel<KT>, dim3((unsigned)ceil_div(Q, 4)), dim3(128), 0, st, (const float*)skey, es.n_lists, Q, tau0, cnt);
     B200F_LAUNCH_OK("gallery_tau_min_kernel");
-    ep.tau0 = tau0; ep.cnt = cnt; ep.cap = GALLERY_COMPACT_CAP;
+    ep.tau0 = tau0; ep.cnt = cnt; ep.cap = gp.n_lists * KT;
   } else if (gp.n_sample > 0) {
     // sample pre-pass: the same scan over the first n_sample rows with few long chunks, then tau0[q] = KT-th best key
     typename XwTopK<KT>::Params es = ep;
@@ -733,7 +735,7 @@ static int gallery_scan_kt(const GalleryScanPlan& gp, const void* g16, const CUt
   if (rc) return rc;
   if (gp.compact) {
     launch_pdl(gallery_select_warp_kernel<KT>, dim3((unsigned)ceil_div(Q, 4)), dim3(128), 0, st, (const float*)ckey, (const int32_t*)cidx,
-               (const int32_t*)cnt, q, g, q_inv, g_inv, (const float*)(bias ? bias + N : nullptr), qbad, Q, D, k, metric, fmt, thresh,
+               (const int32_t*)cnt, gp.n_lists * KT, q, g, q_inv, g_inv, (const float*)(bias ? bias + N : nullptr), qbad, Q, D, k, metric, fmt, thresh,
                index_offset, idx, score, accept, redo, redo_count);
     B200F_LAUNCH_OK("gallery_select_warp_kernel");
     return B200F_OK;

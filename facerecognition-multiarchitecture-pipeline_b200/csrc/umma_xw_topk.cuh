@@ -208,11 +208,11 @@ gallery_tau_min_kernel(const float* __restrict__ key_min, int n_lists, int64_t Q
 // ---- select, compact form: ONE WARP per query ranks the query's (few) candidates, re-scores the KT best exactly and
 // proves the top-k (same arithmetic and proof as gallery_select_kernel below; that kernel took 41-48 us for 128
 // queries: one block per query walking n_lists * KT mostly empty slots through shared memory with a dozen barriers).
-constexpr int GALLERY_COMPACT_CAP = 512;
+constexpr int GALLERY_SURVIVORS_PER_LANE = 16;
 template <int KT>
 __global__ void __launch_bounds__(128)
 gallery_select_warp_kernel(const float* __restrict__ cand_key, const int32_t* __restrict__ cand_idx,
-                           const int32_t* __restrict__ cnt, const float* __restrict__ q, const float* __restrict__ g,
+                           const int32_t* __restrict__ cnt, int cap, const float* __restrict__ q, const float* __restrict__ g,
                            const float* __restrict__ q_inv, const float* __restrict__ g_inv,
                            const float* __restrict__ gmax_ptr, const uint8_t* __restrict__ q_bad, int64_t Q, int D, int k,
                            int metric, int fmt, float thresh, int64_t index_offset, int64_t* __restrict__ idx_out,
@@ -220,22 +220,48 @@ gallery_select_warp_kernel(const float* __restrict__ cand_key, const int32_t* __
                            int32_t* __restrict__ redo_count) {
   pdl_trigger(); pdl_wait();
   static_assert(KT <= 32, "one winner per lane");
-  constexpr int CAP = GALLERY_COMPACT_CAP, PER = CAP / 32;
+  constexpr int PER = GALLERY_SURVIVORS_PER_LANE;
   const int lane = threadIdx.x & 31;
   const int64_t qi = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
   if (qi >= Q) return;
   const bool cosine = (metric == B200F_METRIC_COS);
   const int n_all = __ldcg(cnt + qi);
-  const bool overflow = n_all > CAP;
-  const int n = overflow ? CAP : n_all;
+  const int n = n_all < cap ? n_all : cap;                    // (the scan cannot offer more than cap = n_lists * KT)
+  const float* qk = cand_key + qi * cap;
+  const int32_t* qidx = cand_idx + qi * cap;
+  // pass 1: the KT-th smallest of the 32 per-lane minima bounds the KT-th best candidate (32 >= KT distinct elements)
+  float lm = INFINITY;
+  for (int i = lane; i < n; i += 32) lm = fminf(lm, __ldcg(qk + i));
+  float bound = INFINITY;
+  {
+    float v = lm;
+    for (int r = 0; r < KT; ++r) {
+      float kmin = v; int who = lane;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ok = __shfl_xor_sync(0xffffffffu, kmin, o);
+        const int ow = __shfl_xor_sync(0xffffffffu, who, o);
+        if (ok < kmin || (ok == kmin && ow < who)) { kmin = ok; who = ow; }
+      }
+      bound = kmin;                                           // +inf once fewer than KT lanes hold anything: keep all
+      if (who == lane) v = INFINITY;
+    }
+  }
+  // pass 2: the survivors (key <= bound) into registers
   float ck[PER]; int ci[PER];
 #pragma unroll
-  for (int u = 0; u < PER; ++u) {
-    const int i = lane + 32 * u;
-    const bool in = i < n;
-    ck[u] = in ? __ldcg(cand_key + qi * CAP + i) : INFINITY;
-    ci[u] = in ? __ldcg(cand_idx + qi * CAP + i) : INT32_MAX;
+  for (int u = 0; u < PER; ++u) { ck[u] = INFINITY; ci[u] = INT32_MAX; }
+  int mine = 0;
+  for (int i = lane; i < n; i += 32) {
+    const float kk = __ldcg(qk + i);
+    if (kk <= bound) {
+      const int id = __ldcg(qidx + i);
+#pragma unroll
+      for (int u = 0; u < PER; ++u) if (u == mine) { ck[u] = kk; ci[u] = id; }
+      ++mine;
+    }
   }
+  const bool overflow = __any_sync(0xffffffffu, mine > PER);  // a lane ran out of slots: the exact engine takes the query
   // the query row: D <= 512, lane owns elements 4 * (lane + 32 j) .. + 3
   const int nvec = D >> 2;
   float4 qv[4];
