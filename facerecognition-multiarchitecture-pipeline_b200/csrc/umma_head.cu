@@ -637,7 +637,9 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
 // tile of the first 16 k (32 k) rows.  Several row groups: 4 chunks of 8 tiles, so that a work item amortises its
 // x load over 8 tiles (one-tile items made the pre-pass cost a quarter of the scan at Q = 8192).
 constexpr int GALLERY_SAMPLE_MAX_LISTS = 32 * GALLERY_TAU_LISTS_PER_LANE;
-static std::atomic<int> g_gallery_compact{1};      // tunable "gallery_compact": 0 = the padded-list pre-pass / select of round 1
+static std::atomic<int> g_gallery_compact{0};      // tunable "gallery_compact": 0 = the padded-list pre-pass / select of round 1 (default:
+                                                   // the compact variant measured 297 vs 295 us at Q = 128 x 1 M and its re-score sums in another order,
+                                                   // so sharded and unsharded scores differ in the last bit), 1 = compact candidate arrays + warp select
 struct GalleryScanPlan {
   XwPlan q, qs;                 // main scan / sample pre-pass
   int KT, n_lists;
