@@ -64,6 +64,9 @@ PROTOTYPES = {
     "b200f_arcface_bwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, POINTER(HeadCfg),
                                   c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "b200f_arcface_bwd_phase": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_int64, c_int64, c_int64, c_int, POINTER(HeadCfg), c_void_p, c_void_p, c_int,
+                                        c_void_p, c_size_t, c_void_p]),
     "b200f_l2norm_bwd": (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p, c_int64, c_int, c_void_p,
                                  c_void_p, c_void_p]),
     "b200f_l2norm_rows_pair": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
@@ -72,6 +75,10 @@ PROTOTYPES = {
                                        c_int64, c_int64, c_int64, c_int, POINTER(HeadCfg), POINTER(HookCfg),
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "b200f_arcface_fwd_raw": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_float,
+                                      c_void_p, c_int64, c_int64, c_int64, c_int, POINTER(HeadCfg), POINTER(HookCfg),
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "b200f_arcface_loss_hook": (c_int, [c_void_p, c_int64, POINTER(HeadCfg), POINTER(HookCfg), c_void_p, c_void_p,
                                         c_void_p, c_void_p, c_void_p]),
     "b200f_arcface_bwd_dx": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,

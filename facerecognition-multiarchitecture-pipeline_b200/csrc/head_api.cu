@@ -199,9 +199,11 @@ static int arcface_bwd_impl(const char* who, const void* x, const void* w, int d
                             const int64_t* label, const float* lse, const float* grad_scale,
                             const float* dlogits_or_null, int64_t ld_dlogits, int64_t B, int64_t C_local,
                             int64_t class_offset, int D, const b200f_head_cfg* cfg, float* dxhat, float* dw,
-                            const umma::HeadDx* hdx, void* workspace, size_t workspace_bytes, void* stream) {
+                            const umma::HeadDx* hdx, void* workspace, size_t workspace_bytes, void* stream, int phase = 0) {
   int rc = check_head_args(who, x, w, dtype, inv_nx, inv_nw, label, B, C_local, D, cfg);
   if (rc) return rc;
+  if (phase < 0 || phase > 2) return fail(B200F_ERR_ARG, "%s: phase must be 0, 1 or 2", who);
+  if (phase == 2 && dtype != B200F_F16N) return B200F_OK;      // CUDA-core engine: phase 1 already did everything
   if (!lse || !grad_scale || !dxhat || !dw) return fail(B200F_ERR_ARG, "%s: null pointer", who);
   const size_t need = b200f_head_workspace_bytes(B, C_local, D, dtype, cfg->engine);
   if (!workspace || workspace_bytes < need)
@@ -212,7 +214,7 @@ static int arcface_bwd_impl(const char* who, const void* x, const void* w, int d
     if (dlogits_or_null) return fail(B200F_ERR_UNSUPPORTED, "%s: the tcgen05 engine has no dlogits path", who);
     if (!inv_nw) return fail(B200F_ERR_ARG, "%s: inv_nw required", who);
     return umma::head_bwd(x, w, inv_nw, label, lse, grad_scale, B, C_local, class_offset, D, cfg, dxhat, dw, hdx,
-                          static_cast<char*>(workspace), workspace_bytes, st);
+                          static_cast<char*>(workspace), workspace_bytes, st, phase);
   }
   const HeadPlan pl = plan_head(B, C_local, D);
   if (dtype == B200F_F32)
@@ -259,6 +261,32 @@ int b200f_arcface_fwd_loss(const void* x, const void* w, int dtype, const float*
                           row_best, row_argmax, cos_minmax, nan_flag, nullptr, 0, &fin, workspace, workspace_bytes, stream);
 }
 
+int b200f_arcface_fwd_raw(const void* x_raw_or_null, int x_dtype, void* x_f16n, float* inv_nx,
+                          const void* w_raw, int w_dtype, void* w_f16n, float* inv_nw, float eps,
+                          const int64_t* label, int64_t B, int64_t C_local, int64_t class_offset, int D,
+                          const b200f_head_cfg* cfg, const b200f_hook_cfg* hook_or_null, float* row_stats, float* row_best,
+                          int64_t* row_argmax, float* cos_minmax, int32_t* nan_flag, float* lse, float* loss,
+                          float* pq_norm2, float* out4, void* workspace, size_t workspace_bytes, void* stream) {
+  B200F_NVTX("b200f_arcface_fwd_raw");
+  const char* who = "arcface_fwd_raw";
+  int rc = check_head_args(who, x_f16n, w_f16n, B200F_F16N, inv_nx, inv_nw, label, B, C_local, D, cfg);
+  if (rc) return rc;
+  if (!w_raw || !inv_nx || !inv_nw || !row_stats || !nan_flag) return fail(B200F_ERR_ARG, "%s: null pointer", who);
+  if (!dtype_ok(w_dtype) || (x_raw_or_null && !dtype_ok(x_dtype))) return fail(B200F_ERR_ARG, "%s: raw rows must be fp32 or bf16", who);
+  if (hook_or_null) {
+    if (!lse || !loss || !pq_norm2 || !out4) return fail(B200F_ERR_ARG, "%s: null loss output", who);
+    if (C_local != cfg->num_classes_total)
+      return fail(B200F_ERR_ARG, "%s: a class shard needs the cross-shard sum first (hook = NULL, all-reduce, b200f_arcface_loss_hook)", who);
+  }
+  const size_t need = b200f_head_workspace_bytes(B, C_local, D, B200F_F16N, cfg->engine);
+  if (!workspace || workspace_bytes < need) return fail(B200F_ERR_WORKSPACE, "%s: workspace %zu < %zu", who, workspace_bytes, need);
+  umma::HeadFinal fin{};
+  if (hook_or_null) fin = umma::HeadFinal{lse, loss, pq_norm2, hook_or_null->enabled, hook_or_null->max_grad_norm, hook_or_null->phase, hook_or_null->epoch, out4};
+  const umma::HeadPrep prep{x_raw_or_null, x_dtype, inv_nx, w_raw, w_dtype, inv_nw, eps};
+  return umma::head_fwd(x_f16n, w_f16n, label, B, C_local, class_offset, D, cfg, row_stats, row_best, row_argmax, cos_minmax,
+                        nan_flag, hook_or_null ? &fin : nullptr, static_cast<char*>(workspace), workspace_bytes, as_stream(stream), &prep);
+}
+
 int b200f_arcface_bwd(const void* x, const void* w, int dtype, const float* inv_nx, const float* inv_nw,
                       const int64_t* label, const float* lse, const float* grad_scale,
                       const float* dlogits_or_null, int64_t ld_dlogits, int64_t B,
@@ -267,6 +295,16 @@ int b200f_arcface_bwd(const void* x, const void* w, int dtype, const float* inv_
   B200F_NVTX("b200f_arcface_bwd");
   return arcface_bwd_impl("arcface_bwd", x, w, dtype, inv_nx, inv_nw, label, lse, grad_scale, dlogits_or_null, ld_dlogits, B,
                           C_local, class_offset, D, cfg, dxhat, dw, nullptr, workspace, workspace_bytes, stream);
+}
+
+int b200f_arcface_bwd_phase(const void* x, const void* w, int dtype, const float* inv_nx, const float* inv_nw,
+                            const int64_t* label, const float* lse, const float* grad_scale, int64_t B,
+                            int64_t C_local, int64_t class_offset, int D, const b200f_head_cfg* cfg, float* dxhat,
+                            float* dw, int phase, void* workspace, size_t workspace_bytes, void* stream) {
+  B200F_NVTX("b200f_arcface_bwd_phase");
+  if (phase != 1 && phase != 2) return fail(B200F_ERR_ARG, "arcface_bwd_phase: phase must be 1 or 2");
+  return arcface_bwd_impl("arcface_bwd_phase", x, w, dtype, inv_nx, inv_nw, label, lse, grad_scale, nullptr, 0, B,
+                          C_local, class_offset, D, cfg, dxhat, dw, nullptr, workspace, workspace_bytes, stream, phase);
 }
 
 int b200f_arcface_bwd_dx(const void* x, const void* w, int dtype, const float* inv_nx, const float* inv_nw,

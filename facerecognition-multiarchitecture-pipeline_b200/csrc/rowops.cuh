@@ -207,6 +207,15 @@ l2norm_rows_512x16_kernel(const TI* __restrict__ in, int64_t rows, float eps, fl
   pdl_trigger(); pdl_wait();
   l2norm_rows_512x16_body<TI, TO>(in, rows, eps, out_scale, inv_norm, out, (int64_t)blockIdx.x);
 }
+// K1 over the batch rows + clearing a word array for the kernel behind it (the row counters of K1(W)-inside-K2)
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+l2norm_rows_512x16_zero_kernel(const TI* __restrict__ in, int64_t rows, float eps, float out_scale,
+                               float* __restrict__ inv_norm, TO* __restrict__ out, unsigned int* __restrict__ zero, int n_zero) {
+  pdl_trigger(); pdl_wait();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_zero; i += gridDim.x * blockDim.x) zero[i] = 0u;
+  l2norm_rows_512x16_body<TI, TO>(in, rows, eps, out_scale, inv_norm, out, (int64_t)blockIdx.x);
+}
 // Two row sets in ONE launch (the head's K1 over the batch rows and over the class weights: the 16-block launch for
 // x otherwise costs a launch latency of its own in front of the 3125-block launch for W).  Blocks [0, blocks0) take
 // set 0, the rest set 1.

@@ -15,13 +15,19 @@ struct HeadFinal { float* lse; float* loss; float* pq_norm2; int hook_enabled; f
 // given (x_hat = x * inv_nx exactly; else against K1's fp16 rows), plus its bf16 copy.
 struct HeadDx { const void* x_raw; int x_raw_dtype; const float* inv_nx; float* dx; void* dx_bf16; };
 
+// Optional head of the forward: K1 from the RAW rows in the same call.  x_raw (may be null: xh is already prepared) -> xh,
+// inv_nx; w_raw -> wh, inv_nw -- inside K2 itself when the shape allows it (D = 512, 32-byte aligned rows; tunable
+// "k2_prep"), else as a pass of its own in front of K2.  xh / wh are then OUTPUTS of head_fwd.
+struct HeadPrep { const void* x_raw; int x_dtype; float* inv_nx; const void* w_raw; int w_dtype; float* inv_nw; float eps; };
+
 int head_fwd(const void* xh, const void* wh, const int64_t* label, int64_t B, int64_t C, int64_t class_offset, int D,
              const b200f_head_cfg* cfg, float* row_stats, float* row_best, int64_t* row_argmax, float* cos_minmax,
-             int32_t* nan_flag, const HeadFinal* fin, char* ws, size_t ws_bytes, cudaStream_t st);
+             int32_t* nan_flag, const HeadFinal* fin, char* ws, size_t ws_bytes, cudaStream_t st,
+             const HeadPrep* prep = nullptr);
 
 int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t* label, const float* lse,
              const float* grad4, int64_t B, int64_t C, int64_t class_offset, int D, const b200f_head_cfg* cfg,
-             float* dxhat, float* dw, const HeadDx* hdx, char* ws, size_t ws_bytes, cudaStream_t st);
+             float* dxhat, float* dw, const HeadDx* hdx, char* ws, size_t ws_bytes, cudaStream_t st, int phase = 0);
 
 // dx = normalise-backward(dxhat) with the rows HeadDx names (one launch of rowops::l2norm_bwd)
 int head_dx_finish(const void* xh, float S, const HeadDx* hdx, const float* dxhat, int64_t B, int D, cudaStream_t st);

@@ -107,7 +107,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
   const int n_clusters = gridDim.x / PAIR;
   const int total_work = p.m_tiles * p.n_tiles * p.k_splits;
 
-  pdl_trigger();
+  // An early kernel (K3c) lets its dependents be scheduled right away: they wait for its completion themselves.  Every other
+  // use triggers only AFTER its own wait (below): a dependent that starts early (K3c behind the streamed K3b) relies on
+  // everything older than its predecessor being complete, and that holds only if the predecessor could not release it
+  // before having waited itself.  (Triggering at the top let K3c read G^T while K3a was still writing it whenever the
+  // grids were small enough to be co-resident: NaN in dx at B = 640 x 24 k classes in three chunks.)
+  if (p.early) pdl_trigger();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
@@ -121,7 +126,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
   if (PAIR == 2) cluster_sync_all();                           // the peer's barriers exist before anyone signals them
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  if (!p.early) pdl_wait();
+  if (!p.early) { pdl_wait(); pdl_trigger(); }
 
   if (warp == 0) {
     // ================= TMA producer (both CTAs) =================

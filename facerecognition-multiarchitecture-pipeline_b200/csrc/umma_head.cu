@@ -125,7 +125,9 @@ __global__ void __launch_bounds__(256)
 reduce_row_partials_kernel(const float* __restrict__ part, int n_parts, int64_t B, const float* __restrict__ cos_part,
                            int n_cos, float* row_stats, float* __restrict__ row_best,
                            int64_t* __restrict__ row_argmax, float* __restrict__ cos_minmax, FwdFinal fin) {
-  pdl_trigger(); pdl_wait();
+  // wait, THEN let the dependent be scheduled: K3a follows and starts its operand loads without waiting for this grid
+  // (early_operands); what it loads must be complete, and with K1(W) fused into K2 the operand rows are K2's own output
+  pdl_wait(); pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row < B) {
@@ -308,11 +310,14 @@ static XwPlan xw_plan(int64_t B, int64_t C, int pair, int max_chunks = 0) {
   return q;
 }
 
+// K1 of the streamed rows inside the kernel (XwParams::prep_*; policies with kPrepWarps > 0)
+struct XwPrepArgs { const void* src; int f32; uint16_t* dst; float* inv; unsigned int* ready; float eps, scale; };
+
 template <int PAIR, int MODE, class Epi>
 static int launch_xw(const CUtensorMap& tx, const CUtensorMap& tw, const XwPlan& q, int64_t B, int64_t C, int D,
                      const typename Epi::Params& ep, cudaStream_t st, const char* what, uint32_t fmt = FMT_F16,
                      bool reverse = false, const void* w_base = nullptr, int64_t w_row_bytes = 0, bool early = false,
-                     int w_hint = 0) {
+                     int w_hint = 0, const XwPrepArgs* prep = nullptr) {
   int rc = xw_set_smem<PAIR, MODE, Epi>(); if (rc) return rc;
   XwParams p{};
   p.B = (int)B; p.C = (int)C; p.D = D;
@@ -324,6 +329,15 @@ static int launch_xw(const CUtensorMap& tx, const CUtensorMap& tw, const XwPlan&
   p.w_hint = w_hint;
   p.tn = XW_WROWS * PAIR;
   p.reverse = reverse ? 1 : 0;
+  if (prep != nullptr) {
+    p.prep_src = prep->src; p.prep_f32 = prep->f32; p.prep_dst = prep->dst; p.prep_inv = prep->inv; p.prep_ready = prep->ready;
+    p.prep_eps = prep->eps; p.prep_scale = prep->scale;
+    int cw = q.n_clusters / (q.m_groups > 0 ? q.m_groups : 1);       // chunks in flight at once: one per m_groups clusters
+    if (cw < 1) cw = 1;
+    if (cw > q.n_chunks) cw = q.n_chunks;
+    p.prep_cw = cw;
+    p.prefetch = 0;                                                   // nothing to pull into L2: the rows are being written
+  }
   p.idesc = make_idesc(fmt, fmt, MODE == XW_MK, MODE == XW_SWAP_MK, XW_M * PAIR, XW_WROWS * PAIR);   // A = resident, except SWAP modes
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)q.grid); cfg.blockDim = dim3((unsigned)xw_threads<Epi>()); cfg.dynamicSmemBytes = XW_SMEM_BYTES; cfg.stream = st;
@@ -340,7 +354,7 @@ static int launch_xw(const CUtensorMap& tx, const CUtensorMap& tw, const XwPlan&
 // ---- plan -------------------------------------------------------------------------------------------
 struct Plan {
   XwPlan fwd;
-  size_t off_part, off_cos, off_counter;
+  size_t off_part, off_cos, off_counter, off_ready;
   int64_t Cc, ldg; int n_chunks, dx_splits;
   size_t off_G, off_dxpart, off_rpart;
   int n_rb;                 // 32-row blocks of the batch that K3a emits r partials for
@@ -362,6 +376,7 @@ static Plan make_plan(int64_t B, int64_t C, int D) {
   pl.off_part = off; off += align_up(sizeof(float) * part_max * XW_MAX_EPI_GROUPS * B * PART_COLS, 256);   // one record per epilogue group
   pl.off_cos = off;  off += align_up(sizeof(float) * 2 * cos_max * XW_MAX_EPI_GROUPS, 256);
   pl.off_counter = off; off += 256;                       // the fused loss finalize counts its blocks here
+  pl.off_ready = off; off += align_up(sizeof(unsigned int) * (size_t)ceil_div(C, (int64_t)XW_WROWS), 256);   // K1(W)-in-K2 row counts
   const size_t fwd_total = off;
   // backward: classes are processed in chunks whose fp16 logit gradient G fits the budget.  G is written once
   // and read twice, all while the tensor pipe (not HBM) is the bound, so it need not stay L2-resident: cfg3's
@@ -437,13 +452,75 @@ int head_dx_finish(const void* xh, float S, const HeadDx* hdx, const float* dxha
   return B200F_OK;
 }
 
+// tunable "k2_prep": 1 = K1 of the class weights runs inside K2 (HeadPrep: prep warps + per-128-row hand-over counters),
+// 0 = as its own pass in front of K2 (default), 2 = probe: the 20-warp kernel with idle prep warps.  Measured at cfg3 on one
+// box (gpurun_out/r02k_*, r02m_*): K1(W) 40.5 us + K2 60 us apart; fused 227 us with 2 prep warps (168 registers), 140 us
+// with 6 (128), 115 us with 10 (96 registers, 16-column epilogue -- which alone still runs K2 in 60.6 us).  The rows are
+// bit-identical and the hand-over works, but normalising a row is ~160 warp instructions of latency-bound scalar work and
+// ten warps per SM turn over 5.9 rows/us where the stand-alone K1 (16 warps, the SM to itself) does 16.4: the fused kernel
+// waits for its own prep warps.  What K2 has to spare is HBM bandwidth, not issue slots and registers.
+static std::atomic<int> g_k2_prep{0};
+
+__global__ void zero_words_kernel(unsigned int* p, int n) {
+  pdl_trigger(); pdl_wait();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = 0u;
+}
+
+bool head_prep_fused(int64_t B, int64_t C, int D, const HeadPrep* prep, const void* wh) {
+  // a prep warp keeps one slot per lane: rows of a round per warp <= 32
+  const XwPlan q = xw_plan(B, C, g_pair.load(std::memory_order_relaxed));
+  int cw = q.n_clusters / (q.m_groups > 0 ? q.m_groups : 1);
+  if (cw < 1) cw = 1;
+  if (cw > q.n_chunks) cw = q.n_chunks;
+  const int64_t n_warps = (int64_t)q.grid * XwFwdP::kPrepWarps;
+  if (ceil_div((int64_t)cw * XW_WROWS * q.pair, n_warps) > 32) return false;
+  return prep != nullptr && prep->w_raw != nullptr && g_k2_prep.load(std::memory_order_relaxed) == 1 &&
+         g_k2_groups.load(std::memory_order_relaxed) == 1 && D == 512 &&
+         ((reinterpret_cast<uintptr_t>(prep->w_raw) | reinterpret_cast<uintptr_t>(wh)) & 31) == 0;
+}
+
 int head_fwd(const void* xh, const void* wh, const int64_t* label, int64_t B, int64_t C, int64_t class_offset, int D,
              const b200f_head_cfg* cfg, float* row_stats, float* row_best, int64_t* row_argmax, float* cos_minmax,
-             int32_t* nan_flag, const HeadFinal* fin, char* ws, size_t ws_bytes, cudaStream_t st) {
+             int32_t* nan_flag, const HeadFinal* fin, char* ws, size_t ws_bytes, cudaStream_t st, const HeadPrep* prep) {
   int rc = check_shape(B, C, D, cfg); if (rc) return rc;
   const Plan pl = make_plan(B, C, D);
   if (ws_bytes < pl.total) return fail(B200F_ERR_WORKSPACE, "umma head_fwd: workspace too small");
   ws = ws_align(ws);
+  // K1: the batch rows now (they are the resident operand), the class weights inside K2 (prep warps) or as a pass of their own
+  const bool fused_prep = head_prep_fused(B, C, D, prep, wh);
+  unsigned int* ready = reinterpret_cast<unsigned int*>(ws + pl.off_ready);
+  const int n_ready = (int)ceil_div(C, (int64_t)XW_WROWS);
+  if (prep != nullptr) {
+    const float S = cfg->operand_scale;
+    bool zeroed = false;
+    if (prep->x_raw != nullptr) {
+      __half* xo = static_cast<__half*>(const_cast<void*>(xh));
+      if (fused_prep && prep->x_dtype == B200F_BF16 && D == 512 &&
+          ((reinterpret_cast<uintptr_t>(prep->x_raw) | reinterpret_cast<uintptr_t>(xh)) & 31) == 0) {
+        launch_pdl(rowops::l2norm_rows_512x16_zero_kernel<__nv_bfloat16, __half>, dim3((unsigned)ceil_div(B, (int64_t)rowops::ROWS_PER_BLOCK)),
+                   dim3(rowops::WARPS_PER_BLOCK * 32), 0, st, static_cast<const __nv_bfloat16*>(prep->x_raw), B, prep->eps, S,
+                   prep->inv_nx, xo, ready, n_ready);
+        zeroed = true;
+      } else if (prep->x_dtype == B200F_BF16) {
+        rowops::launch_l2norm_rows<__nv_bfloat16, __half>(static_cast<const __nv_bfloat16*>(prep->x_raw), B, D, prep->eps, S, prep->inv_nx, xo, st);
+      } else {
+        rowops::launch_l2norm_rows<float, __half>(static_cast<const float*>(prep->x_raw), B, D, prep->eps, S, prep->inv_nx, xo, st);
+      }
+      B200F_LAUNCH_OK("K1 l2norm_rows (x)");
+    }
+    if (fused_prep && !zeroed) {
+      launch_pdl(zero_words_kernel, dim3((unsigned)ceil_div((int64_t)n_ready, (int64_t)256)), dim3(256), 0, st, ready, n_ready);
+      B200F_LAUNCH_OK("zero_words_kernel");
+    }
+    if (!fused_prep && prep->w_raw != nullptr) {
+      __half* wo = static_cast<__half*>(const_cast<void*>(wh));
+      if (prep->w_dtype == B200F_BF16)
+        rowops::launch_l2norm_rows<__nv_bfloat16, __half>(static_cast<const __nv_bfloat16*>(prep->w_raw), C, D, prep->eps, S, prep->inv_nw, wo, st);
+      else
+        rowops::launch_l2norm_rows<float, __half>(static_cast<const float*>(prep->w_raw), C, D, prep->eps, S, prep->inv_nw, wo, st);
+      B200F_LAUNCH_OK("K1 l2norm_rows (W)");
+    }
+  }
   CUtensorMap tx, tw;
   rc = tmap_kmajor(&tx, xh, B, D, D, XW_M); if (rc) return rc;
   rc = tmap_kmajor(&tw, wh, C, D, D, XW_WROWS); if (rc) return rc;
@@ -462,7 +539,16 @@ int head_fwd(const void* xh, const void* wh, const int64_t* label, int64_t B, in
   B200F_NVTX("K2 cosine GEMM + margin + softmax statistics");
   stage_reset(EV_K2);
   stage_event(EV_K2, false, st);
-  if (eg == 2) {
+  const bool p_kernel_only = !fused_prep && g_k2_prep.load(std::memory_order_relaxed) == 2;   // probe: the 20-warp kernel, prep warps idle
+  if (fused_prep || p_kernel_only) {
+    XwFwdP::Params epp{};
+    epp.label = ep.label; epp.class_offset = ep.class_offset; epp.hm = ep.hm; epp.inv_scale = ep.inv_scale; epp.part = ep.part;
+    epp.cos_part = ep.cos_part; epp.nan_flag = ep.nan_flag; epp.pair = ep.pair; epp.zero_word = ep.zero_word;
+    const XwPrepArgs pa{prep->w_raw, prep->w_dtype == B200F_F32 ? 1 : 0, static_cast<uint16_t*>(const_cast<void*>(wh)), prep->inv_nw,
+                        ready, prep->eps, cfg->operand_scale};
+    rc = (q.pair == 2) ? launch_xw<2, XW_KK, XwFwdP>(tx, tw, q, B, C, D, epp, st, "umma K2 arcface_fwd + K1(W) (cta pair)", FMT_F16, false, wh, wrb, false, k2_hint, fused_prep ? &pa : nullptr)
+                       : launch_xw<1, XW_KK, XwFwdP>(tx, tw, q, B, C, D, epp, st, "umma K2 arcface_fwd + K1(W)", FMT_F16, false, wh, wrb, false, k2_hint, fused_prep ? &pa : nullptr);
+  } else if (eg == 2) {
     XwFwd2::Params ep2{};
     ep2.label = ep.label; ep2.class_offset = ep.class_offset; ep2.hm = ep.hm; ep2.inv_scale = ep.inv_scale; ep2.part = ep.part;
     ep2.cos_part = ep.cos_part; ep2.nan_flag = ep.nan_flag; ep2.pair = ep.pair; ep2.zero_word = ep.zero_word;
@@ -489,10 +575,16 @@ int head_fwd(const void* xh, const void* wh, const int64_t* label, int64_t B, in
 
 int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t* label, const float* lse,
              const float* grad4, int64_t B, int64_t C, int64_t class_offset, int D, const b200f_head_cfg* cfg,
-             float* dxhat, float* dw, const HeadDx* hdx, char* ws, size_t ws_bytes, cudaStream_t st) {
+             float* dxhat, float* dw, const HeadDx* hdx, char* ws, size_t ws_bytes, cudaStream_t st, int phase) {
   int rc = check_shape(B, C, D, cfg); if (rc) return rc;
   const Plan pl = make_plan(B, C, D);
   if (ws_bytes < pl.total) return fail(B200F_ERR_WORKSPACE, "umma head_bwd: workspace too small");
+  if (phase < 0 || phase > 2) return fail(B200F_ERR_ARG, "umma head_bwd: phase must be 0, 1 or 2");
+  if (phase != 0 && hdx != nullptr) return fail(B200F_ERR_ARG, "umma head_bwd: the fused dL/dx tail belongs to the unsplit call");
+  // phase 0: per class chunk K3a -> K3b -> K3c -> split reduction (one call does everything).
+  // phases 1 / 2 (class shards): the dx_hat half first -- per chunk K3a -> K3c -> split reduction -> K3b, WITHOUT the last
+  // chunk's K3b (phase 1) -- so that the caller can start the cross-rank all-reduce of dx_hat on another stream, and then
+  // that last dW GEMM (phase 2: it needs the last chunk's G^T and r partials, which stay in the workspace) runs beside it.
   ws = ws_align(ws);
   uint16_t* G = reinterpret_cast<uint16_t*>(ws + pl.off_G);
   float* dxpart = reinterpret_cast<float*>(ws + pl.off_dxpart);
@@ -508,18 +600,20 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
     const int64_t cnt = (C - c0 < pl.Cc) ? (C - c0) : pl.Cc;
     const bool last_chunk = c0 + pl.Cc >= C;
     const uint16_t* wc = static_cast<const uint16_t*>(wh) + c0 * D;
-    // --- K3a: logit gradient of the chunk, class-major: G^T[c, b] (x_hat resident, w_hat rows [c0, c0 + cnt) streamed
-    //     on the A side, so a thread owns a class and r_c = sum_b G cos is a private sum)
-    CUtensorMap tw_k;
-    rc = tmap_kmajor(&tw_k, wc, cnt, D, D, XW_WROWS); if (rc) return rc;
+    if (phase == 2 && !last_chunk) continue;                // everything but the last chunk's dW ran in phase 1
     const XwPlan qg = xw_plan(B, cnt, pl.fwd.pair);
     float* r_part = reinterpret_cast<float*>(ws + pl.off_rpart);
+    const int hints = g_l2_hints.load(std::memory_order_relaxed);
+    // --- K3a: logit gradient of the chunk, class-major: G^T[c, b] (x_hat resident, w_hat rows [c0, c0 + cnt) streamed
+    //     on the A side, so a thread owns a class and r_c = sum_b G cos is a private sum)
+    auto run_k3a = [&]() -> int {
+    CUtensorMap tw_k;
+    int rc = tmap_kmajor(&tw_k, wc, cnt, D, D, XW_WROWS); if (rc) return rc;
     XwBwdGT::Params eg{};
     eg.label = label; eg.lse = lse; eg.grad4 = grad4; eg.class_offset = class_offset + c0;
     eg.hm = HeadMath{cfg->m_eff, cfg->s_eff, cfg->easy_margin};
     eg.ls_eps = cfg->label_smoothing; eg.inv_Ctot = 1.0f / (float)cfg->num_classes_total; eg.inv_scale = 1.0f / (S * S);
     eg.GT = G; eg.ldgt = pl.ldg; eg.r_part = r_part; eg.ldr = pl.Cc;
-    const int hints = g_l2_hints.load(std::memory_order_relaxed);
     eg.gt_hint = (hints & 2) ? 2 : 0;
     const int k3a_whint = (hints & 1) ? 1 : 0;
 #ifdef B200F_PROBES
@@ -542,11 +636,13 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
                           : launch_xw<1, XW_SWAP, XwBwdGT>(tx_k, tw_k, qg, B, cnt, D, eg, st, "umma K3a logit-grad", FMT_F16, false, wc, wrb, true, k3a_whint);
     }
     stage_event(EV_K3A, true, st); }
-    if (rc) return rc;
+    return rc; };
     // --- K3b: dW[c0 + c, d] = inv_nw_c (sum_b G^T[c, b] x_hat[b, d] - w_hat[c, d] r_c), class-major (the thread owns a
     //     class row), normalise-backward fused; its coefficients { inv_nw_c / (S g_scale), r_c } are formed in the epilogue
     //     from K3a's partials (CoefSrc)
     const CoefSrc coef{r_part, qg.m_groups * 2, pl.Cc, inv_nw, grad4, S};
+    auto run_k3b = [&]() -> int {
+    int rc = B200F_OK;
     { B200F_NVTX("K3b dW = G^T x_hat (+ normalise-backward of W)");
     stage_event(EV_K3B, false, st);
     if (pl.fused_dw) {                                      // x_hat^T resident, G^T rows streamed
@@ -591,12 +687,16 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
       if (rc) return rc;
     }
     stage_event(EV_K3B, true, st); }
+    return B200F_OK; };
     // --- K3c: dx_hat partials = G[:, k-range] w_hat[c0 + k-range, :]   (A = G read MN-major from G^T)
+    auto run_k3c = [&]() -> int {
     CUtensorMap tg_mn, tw_mn;
-    rc = tmap_mnmajor(&tg_mn, G, B, cnt, pl.ldg); if (rc) return rc;
+    int rc = tmap_mnmajor(&tg_mn, G, B, cnt, pl.ldg); if (rc) return rc;
     rc = tmap_mnmajor(&tw_mn, wc, D, cnt, D); if (rc) return rc;
     GemmParams px = gemm_params((int)B, D, (int)cnt, pl.dx_splits, true, true, FMT_F16, FMT_F16, gpair);
-    px.early = g_early.load(std::memory_order_relaxed);       // K3c reads G^T (K3a) and w_hat, writes dxpart: nothing of K3b's
+    // K3c reads G^T (K3a) and w_hat, writes dxpart: nothing of K3b's -- behind K3b it need not wait for it; directly behind
+    // K3a (phases 1 / 2) it does
+    px.early = (phase == 0) ? g_early.load(std::memory_order_relaxed) : 0;
     EpiStore::Params ex{dxpart, (int64_t)D, B * (int64_t)D, 0, 1.0f, nullptr};
     stage_event(EV_K3C, false, st);
     rc = (gpair == 2) ? launch_gemm<2, true, true, EpiStore>(tg_mn, tw_mn, px, ex, st, "umma K3c dX (cta pair)")
@@ -627,6 +727,18 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
       if (last_chunk && hdx != nullptr && hdx->dx != nullptr) {
         rc = head_dx_finish(xh, S, hdx, dxhat, B, D, st); if (rc) return rc;
       }
+    }
+    return B200F_OK; };
+    if (phase == 0) {
+      rc = run_k3a(); if (rc) return rc;
+      rc = run_k3b(); if (rc) return rc;
+      rc = run_k3c(); if (rc) return rc;
+    } else if (phase == 1) {
+      rc = run_k3a(); if (rc) return rc;
+      rc = run_k3c(); if (rc) return rc;
+      if (!last_chunk) { rc = run_k3b(); if (rc) return rc; }
+    } else {
+      rc = run_k3b(); if (rc) return rc;
     }
   }
   return B200F_OK;
@@ -879,6 +991,7 @@ int b200f_set_tunable(const char* name, int value) {
   if (n == "pair") return b200f_umma_set_pair(value);
   if (n == "pdl") { const int old_v = pdl_enabled() ? 1 : 0; if (value == 0 || value == 1) pdl_set(value != 0); return old_v; }
   if (n == "stage_events") { if (value != 0 && value != 1) return g_stage_events.load(); return g_stage_events.exchange(value); }
+  if (n == "k2_prep") { if (value < 0 || value > 2) return g_k2_prep.load(); return g_k2_prep.exchange(value); }
   if (n == "l2_hints") { if (value < 0) return g_l2_hints.load(); return g_l2_hints.exchange(value); }
   if (n == "k2_groups") { if (value != 1 && value != 2) return g_k2_groups.load(); return g_k2_groups.exchange(value); }
   if (n == "k3b_groups") { if (value != 1 && value != 2) return g_k3b_groups.load(); return g_k3b_groups.exchange(value); }

@@ -19,6 +19,7 @@
 // The Epilogue policy sees every 32-column slice of the accumulators plus item begin / end hooks, so per-row
 // statistics stay in registers across all class tiles of an item (one partial record per row and chunk).
 #pragma once
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "umma_core.cuh"
 
@@ -121,6 +122,19 @@ struct XwParams {
                                         // MMA warps do not wait for the predecessor: loads and MMAs of the first tiles overlap its
                                         // tail.  The epilogue warps wait (griddepcontrol.wait) before they touch anything.
   uint32_t idesc;
+  // ---- operand preparation fused into the kernel (policies with kPrepWarps > 0: K2 of the head) ------------------------
+  // The streamed operand does not exist yet when the kernel starts: prep warps of ALL CTAs produce it (K1 of the class
+  // weights: row L2-normalise -> fp16 rows * out_scale + 1/||w||) in the order the tiles are consumed, and count finished
+  // rows per 128-row block in prep_ready[]; a TMA producer loads a tile only after its block is complete.  The 41 us
+  // K1(W) pass of the cfg3 step (102 MB read + 102 MB written, HBM-bound, tensor pipe idle) then runs under K2's MMAs,
+  // and K2 reads the fresh rows from L2.  prep_ready must be zero when the kernel starts (the predecessor kernel clears it).
+  const void* prep_src;                 // raw rows of the streamed operand [C, D], bf16 (prep_f32 = 0) or fp32 (1); null = off
+  int prep_f32;
+  uint16_t* prep_dst;                   // fp16 rows [C, D] = what tm_w reads
+  float* prep_inv;                      // [C] 1 / max(||row||, eps)
+  unsigned int* prep_ready;             // [ceil(C / 128)] rows finished per 128-row block
+  float prep_eps, prep_scale;
+  int prep_cw;                          // chunks whose tiles are consumed at the same time (clusters / row groups)
 };
 
 struct XwItem;
@@ -146,10 +160,222 @@ template <class Epi> struct xw_epi_groups<Epi, decltype((void)Epi::kEpiGroups)> 
 // columns per slice() call: 32 (default) or 16 (kSliceCols = 16)
 template <class Epi, class = void> struct xw_slice_cols { static constexpr int value = 32; };
 template <class Epi> struct xw_slice_cols<Epi, decltype((void)Epi::kSliceCols)> { static constexpr int value = Epi::kSliceCols; };
-template <class Epi> __host__ __device__ constexpr int xw_threads() { return 64 + 32 * XW_EPI_WARPS * xw_epi_groups<Epi>::value; }
+// warps that prepare the streamed operand inside the kernel (XwParams::prep_*): 0 (default) or kPrepWarps
+template <class Epi, class = void> struct xw_prep_warps { static constexpr int value = 0; };
+template <class Epi> struct xw_prep_warps<Epi, decltype((void)Epi::kPrepWarps)> { static constexpr int value = Epi::kPrepWarps; };
+template <class Epi> __host__ __device__ constexpr int xw_threads() {
+  return 64 + 32 * XW_EPI_WARPS * xw_epi_groups<Epi>::value + 32 * xw_prep_warps<Epi>::value;
+}
 // registers per thread: 1 CTA per SM either way (shared memory).  The register file is handed out per FOUR warps:
 // 10 warps count as 12 (168 registers), 18 warps as 20 (96 registers; 112 is refused at launch: "too many resources").
-template <class Epi> __host__ __device__ constexpr int xw_maxnreg() { return xw_epi_groups<Epi>::value == 1 ? 168 : 96; }
+// 12 warps (10 + 2 spare): 168; up to 16 warps: 128; 20 (two groups, or one group of 16-column slices + 10 prep warps): 96.
+template <class Epi> __host__ __device__ constexpr int xw_maxnreg() {
+  return xw_threads<Epi>() <= 384 ? 168 : (xw_threads<Epi>() <= 512 ? 128 : 96);
+}
+
+
+// ---- operand preparation inside the kernel (XwParams::prep_*) ---------------------------------------------------------
+// Row L2-normalise of 512-wide rows: the arithmetic of rowops::l2norm_rows_512x16_body (same per-lane element order, same
+// reduction), so the rows are bit-identical to the stand-alone K1's for bf16 sources.  A warp keeps ROWS rows (ROWS x 1 KB
+// of bf16, ROWS x 2 KB of fp32) in flight; rows are visited in the order the TMA producers consume them: rounds of "the
+// k-th tile of every chunk that is being worked on", row blocks of a round spread over all prep warps of the grid.
+__device__ __forceinline__ bool xw_wait_ready(const unsigned int* flag, unsigned int need) {
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if (v >= need) return true;
+    __nanosleep(40);
+  }
+  atomicExch(&g_umma_timeout_flag, 1u);
+  __threadfence_system();
+  __trap();
+  return false;
+}
+
+// publish rows finished by this warp: one count per 128-row block, released at gpu scope (lane 0; the __syncwarp orders
+// the other lanes' stores before its fence)
+template <int ROWS>
+__device__ __forceinline__ void xw_prep_publish(const XwParams& p, const int (&row)[ROWS], int lane) {
+  __syncwarp();
+  if (lane == 0) {
+    // release at gpu scope ON the counter update (fence.acq_rel + red), not __threadfence(): that one is fence.sc, which
+    // cost ~4 us per trip under this kernel's memory traffic (K2 150 us instead of 60)
+    int blk = -1; unsigned int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j) {
+      if (row[j] < 0) continue;
+      const int b = row[j] >> 7;
+      if (b != blk) {
+        if (cnt) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p.prep_ready + blk), "r"(cnt) : "memory");
+        blk = b; cnt = 0;
+      }
+      ++cnt;
+    }
+    if (cnt) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p.prep_ready + blk), "r"(cnt) : "memory");
+  }
+}
+
+// Lane -> element mapping (it fixes the order of the sum of squares, hence the bits of 1/||w||):
+//   bf16 source: lane owns elements [16 lane, 16 lane + 16): one 32-byte load and one 32-byte store per row, as
+//                rowops::l2norm_rows_512x16_body;
+//   fp32 source: lane owns the float4 vectors lane, lane + 32, lane + 64, lane + 96, as rowops::l2norm_rows_vec_kernel
+//                <float, __half, 4> (and K5, which emits the same operands after an optimizer step).
+// A warp walks ITS rows (rpw per round, all rounds back to back) ROWS at a time through two register buffers: the loads
+// of trip t + 1 are in flight while trip t is reduced and stored, and the rows of trip t - 1 are published (fence +
+// counter) right after those loads were issued.  The arithmetic of a trip is written phase by phase over its rows
+// (squares, butterfly, inverse norms, stores) so that the rows' dependent chains interleave: six warps per SM have to
+// turn 680 rows around in ~50 us.
+template <int ROWS, bool F32>
+struct XwPrepBuf {
+  static constexpr int RW = F32 ? 16 : 8;                      // 32-bit words a lane holds per row (16 elements)
+  int row[ROWS];                                               // C < 2^30 (check_shape)
+  uint32_t raw[ROWS][RW];
+};
+
+// The warp's position in its row sequence: entry (k, slot) = slot-th of its rpw rows of round k.  Lane l holds what is
+// fixed per slot l for the current wave group -- r0 = first-round row, cnt = tiles of that slot's chunk -- so a row is
+// r0 + k * TN while k < cnt: no division in the loop.
+struct XwPrepPos { int k, slot; };
+
+template <int TN, int ROWS, bool F32>
+__device__ __forceinline__ void xw_prep_load(const XwParams& p, XwPrepBuf<ROWS, F32>& b, XwPrepPos& pos, int rpw, int maxT,
+                                             int r0_mine, int cnt_mine, int lane) {
+  constexpr int RW = XwPrepBuf<ROWS, F32>::RW;
+  int k = pos.k, s = pos.slot + lane;                           // lane j < ROWS resolves the j-th entry from pos
+  while (s >= rpw) { s -= rpw; ++k; }
+  const int r0 = __shfl_sync(0xffffffffu, r0_mine, s & 31);
+  const int cnt = __shfl_sync(0xffffffffu, cnt_mine, s & 31);
+  int mine = -1;
+  if (lane < ROWS && k < maxT && k < cnt) { const int64_t r = (int64_t)r0 + (int64_t)k * TN; if (r < p.C) mine = (int)r; }
+  pos.slot += ROWS;
+  while (pos.slot >= rpw) { pos.slot -= rpw; ++pos.k; }
+  const char* src = static_cast<const char*>(p.prep_src);
+#pragma unroll
+  for (int j = 0; j < ROWS; ++j) {
+    b.row[j] = __shfl_sync(0xffffffffu, mine, j);
+    if (b.row[j] >= 0) {
+      if (F32) {
+        const char* a = src + (int64_t)b.row[j] * 2048 + lane * 16;
+#pragma unroll
+        for (int it = 0; it < 4; ++it)
+          asm volatile("ld.global.nc.v4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(b.raw[j][4 * it]), "=r"(b.raw[j][4 * it + 1]), "=r"(b.raw[j][4 * it + 2]), "=r"(b.raw[j][4 * it + 3])
+                       : "l"(a + 512 * it));
+      } else {
+        const char* a = src + (int64_t)b.row[j] * 1024 + lane * 32;
+        asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(b.raw[j][0]), "=r"(b.raw[j][1]), "=r"(b.raw[j][2]), "=r"(b.raw[j][3]),
+                       "=r"(b.raw[j][4]), "=r"(b.raw[j][5]), "=r"(b.raw[j][6]), "=r"(b.raw[j][7])
+                     : "l"(a));
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < RW; ++i) b.raw[j][i] = 0u;
+    }
+  }
+}
+
+template <int ROWS, bool F32>
+__device__ __forceinline__ float xw_prep_elem(const XwPrepBuf<ROWS, F32>& b, int j, int i) {
+  if (F32) return __uint_as_float(b.raw[j][i]);
+  return (i & 1) ? __uint_as_float(b.raw[j][i >> 1] & 0xffff0000u) : __uint_as_float(b.raw[j][i >> 1] << 16);
+}
+
+template <int ROWS, bool F32>
+__device__ __forceinline__ void xw_prep_finish(const XwParams& p, const XwPrepBuf<ROWS, F32>& b, int lane) {
+  float ss[ROWS];
+#pragma unroll
+  for (int j = 0; j < ROWS; ++j) ss[j] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i)                                  // element-major: ROWS independent chains
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j) { const float v = xw_prep_elem<ROWS, F32>(b, j, i); ss[j] = fmaf(v, v, ss[j]); }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1)                        // warp_sum's butterfly, the rows side by side
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j) ss[j] += __shfl_xor_sync(0xffffffffu, ss[j], off);
+  // the square root and the division once per ROW (lane j takes row j), not once per row and lane: same arithmetic
+  float m = ss[0];
+#pragma unroll
+  for (int j = 1; j < ROWS; ++j) if (lane == j) m = ss[j];
+  const float inv_m = 1.0f / fmaxf(sqrtf(m), p.prep_eps);
+  if (lane < ROWS) {
+    int r = b.row[0];
+#pragma unroll
+    for (int j = 1; j < ROWS; ++j) if (lane == j) r = b.row[j];
+    if (r >= 0) p.prep_inv[r] = inv_m;
+  }
+#pragma unroll
+  for (int j = 0; j < ROWS; ++j) {
+    const float sc = __shfl_sync(0xffffffffu, inv_m, j) * p.prep_scale;
+    if (b.row[j] < 0) continue;                                 // warp-uniform
+    uint32_t o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const __half2 h = __halves2half2(__float2half_rn(xw_prep_elem<ROWS, F32>(b, j, 2 * i) * sc),
+                                       __float2half_rn(xw_prep_elem<ROWS, F32>(b, j, 2 * i + 1) * sc));
+      o[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    uint16_t* dst = p.prep_dst + (int64_t)b.row[j] * 512;
+    if (F32) {
+#pragma unroll
+      for (int it = 0; it < 4; ++it)
+        asm volatile("st.global.v2.b32 [%0], {%1, %2};" ::"l"(dst + (lane + 32 * it) * 4), "r"(o[2 * it]), "r"(o[2 * it + 1]) : "memory");
+    } else {
+      st_global_256(dst + lane * 16, o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7]);
+    }
+  }
+}
+
+// rpw (rows of a round per prep warp) <= 32 so that a lane can hold a slot: the host enables the fused path only then.
+template <int TN, int ROWS, bool F32>
+__device__ __forceinline__ void xw_prep_run(const XwParams& p, int gw, int nW) {
+  const int lane = threadIdx.x & 31;
+  const int cw = p.prep_cw;
+  const int n_groups = (p.n_chunks + cw - 1) / cw;
+  const int maxT = (p.n_tiles + p.n_chunks - 1) / p.n_chunks;  // a chunk has floor or ceil(n_tiles / n_chunks) tiles
+  const int round_rows = cw * TN;
+  const int rpw = (round_rows + nW - 1) / nW;
+  const int q_lo = gw * rpw;
+  const int q_hi = (q_lo + rpw < round_rows) ? q_lo + rpw : round_rows;
+  if (q_lo >= round_rows) return;
+  XwPrepBuf<ROWS, F32> a, b;
+  int prev[ROWS];
+  bool have_prev = false;
+#pragma unroll 1
+  for (int W = 0; W < n_groups; ++W) {
+    int r0_mine = 0, cnt_mine = 0;                              // slot `lane` of this warp in wave group W
+    if (lane < rpw && q_lo + lane < q_hi) {
+      const int q = q_lo + lane;
+      const int c = W * cw + q / TN;
+      if (c < p.n_chunks) {
+        const int tb = (int)((int64_t)c * p.n_tiles / p.n_chunks);
+        const int te = (int)((int64_t)(c + 1) * p.n_tiles / p.n_chunks);
+        r0_mine = tb * TN + (q % TN);
+        cnt_mine = te - tb;
+      }
+    }
+    XwPrepPos pos{0, 0};
+    const int n_total = maxT * rpw;
+    xw_prep_load<TN, ROWS, F32>(p, a, pos, rpw, maxT, r0_mine, cnt_mine, lane);
+#pragma unroll 1
+    for (int n0 = 0; n0 < n_total; n0 += 2 * ROWS) {
+      xw_prep_load<TN, ROWS, F32>(p, b, pos, rpw, maxT, r0_mine, cnt_mine, lane);
+      if (have_prev) xw_prep_publish<ROWS>(p, prev, lane);
+      xw_prep_finish<ROWS, F32>(p, a, lane);
+#pragma unroll
+      for (int j = 0; j < ROWS; ++j) prev[j] = a.row[j];
+      xw_prep_load<TN, ROWS, F32>(p, a, pos, rpw, maxT, r0_mine, cnt_mine, lane);
+      xw_prep_publish<ROWS>(p, prev, lane);
+      xw_prep_finish<ROWS, F32>(p, b, lane);
+#pragma unroll
+      for (int j = 0; j < ROWS; ++j) prev[j] = b.row[j];
+      have_prev = true;
+    }
+  }
+  if (have_prev) xw_prep_publish<ROWS>(p, prev, lane);
+}
 
 struct XwItem {                         // what an epilogue thread knows about its work item
   int item, chunk, group;
@@ -239,7 +465,16 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
   // predecessor could not release it before having waited itself (K1 -> K2 -> statistics -> K3a: K3a reads K1's output).
   pdl_trigger();
 
-  if (warp == 0) {
+  constexpr int PREP_WARPS = xw_prep_warps<Epi>::value;
+  if (PREP_WARPS > 0 && warp >= 2 + EPI_WARPS_ALL) {
+    // ================= operand preparation (K1 of the streamed rows, all CTAs) =================
+    if (p.prep_src != nullptr) {
+      const int gw = (int)blockIdx.x * PREP_WARPS + (warp - 2 - EPI_WARPS_ALL);
+      const int nW = (int)gridDim.x * PREP_WARPS;
+      if (p.prep_f32) xw_prep_run<TN, 2, true>(p, gw, nW);
+      else xw_prep_run<TN, 3, false>(p, gw, nW);
+    }
+  } else if (warp == 0) {
     // ================= TMA producer (both CTAs) =================
     // The whole warp walks the loops convergently (loop state stays in uniform registers); one elected lane
     // issues the TMA traffic.
@@ -284,6 +519,13 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
         for (int ti = t_begin; ti < t_end && ok; ++ti) {
           const int t = p.reverse ? (t_end - 1 - (ti - t_begin)) : ti;
           const int n0 = t * TN + rank * XW_WROWS;
+          if (PREP_WARPS > 0 && p.prep_src != nullptr && n0 < p.C) {
+            // this CTA's 128 rows of the tile are being written by prep warps somewhere on the chip: wait for the block's
+            // row count, then order the (generic-proxy) rows before this thread's async-proxy reads of them
+            const int left = p.C - n0;
+            xw_wait_ready(p.prep_ready + (n0 >> 7), (unsigned int)(left < XW_WROWS ? left : XW_WROWS));
+            asm volatile("fence.proxy.async;" ::: "memory");
+          }
           for (int kb = 0; kb < p.kb_count; ++kb) {
             ok = mbar_wait(&empty_bar[stage], phase ^ 1);
             if (!ok) break;
@@ -365,7 +607,7 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
         __syncwarp();
       }
     }
-  } else {
+  } else if (warp < 2 + EPI_WARPS_ALL) {
     // ================= epilogue (8 warps per group, both CTAs) =================
     constexpr int EG = xw_epi_groups<Epi>::value;
     constexpr int SC = xw_slice_cols<Epi>::value;

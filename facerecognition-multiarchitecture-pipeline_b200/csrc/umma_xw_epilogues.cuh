@@ -57,10 +57,11 @@ struct XwNull {
 // -------------------------------------------------------------------------------------------------
 // K2: cosine logits -> margin -> scale -> softmax / cross-entropy statistics (src/face_models.py:355-427,
 // training.py:515).  Nothing B x C is stored: ONE partial record per (row, class chunk).
-template <int EG, int SC>
+template <int EG, int SC, int PW = 0>
 struct XwFwdT {
   static constexpr int kEpiGroups = EG;
   static constexpr int kSliceCols = SC;
+  static constexpr int kPrepWarps = PW;        // warps that run K1 of the class weights inside the kernel (XwParams::prep_*)
   struct Params {
     const int64_t* label;
     int64_t class_offset;       // global id of this launch's class 0
@@ -199,6 +200,10 @@ struct XwFwdT {
 };
 using XwFwd = XwFwdT<1, 32>;        // one epilogue group, 32-column slices (round 1)
 using XwFwd2 = XwFwdT<2, 16>;       // two epilogue groups (16 warps), 16-column slices
+// K2 with K1(W) inside: one epilogue group on 16-column slices (<= 96 registers) + TEN prep warps = 20 warps.  The prep
+// code is latency-bound scalar work (a 4-row trip takes 3-5 us under this kernel's memory traffic), so it needs warps: two
+// beside the 32-column group gave K2 227 us, six at 128 registers 140 us.
+using XwFwdP = XwFwdT<1, 16, 10>;
 
 // -------------------------------------------------------------------------------------------------
 // K3a, class-major (xw_kernel SWAP mode): the thread owns ONE class of the tile, the 32 columns of a slice are batch

@@ -202,16 +202,28 @@ def _fwd_kernels(x, w, label, cfg: HeadCfg, class_offset, want_logits, w_cache=N
     f16n = use_tcgen05(x, cfg.engine, want_logits) if x_ops is None else True
     if not f16n and x.dtype != w.dtype:
         raise TypeError(f"CUDA-core engine: x ({x.dtype}) and weight ({w.dtype}) must share a dtype")
+    raw = None                                    # (x_raw or None, w_raw): K1 runs inside the forward call (b200f_arcface_fwd_raw)
     if x_ops is not None:                         # the embedding tail already emitted K1's outputs for x (fused_tail)
         xo, inv_nx = x_ops
         if want_logits or xo.dtype != torch.float16 or tuple(xo.shape) != tuple(x.shape):
             raise ValueError("x_operands: fp16 operand rows of x's shape for the fused (tcgen05) path only")
-        wo, inv_nw = _prepare_weight(w, True, w_cache)
-    elif f16n and x.dtype == w.dtype and _cached_weight(w, f16n, w_cache) is None:
-        xo, inv_nx, wo, inv_nw = _k1_pair(x, w, w_cache)
+        if _cached_weight(w, True, w_cache) is None and w.dtype in (torch.float32, torch.bfloat16):
+            raw = (None, w)
+        else:
+            wo, inv_nw = _prepare_weight(w, True, w_cache)
+    elif f16n and _cached_weight(w, f16n, w_cache) is None and w.dtype in (torch.float32, torch.bfloat16) \
+            and x.dtype in (torch.float32, torch.bfloat16):
+        raw = (x, w)                              # K1(x) + K2 with K1(W) inside it: one call, W's fp16 rows made under the MMAs
+        xo = torch.empty(x.shape, dtype=torch.float16, device=dev)
+        inv_nx = torch.empty(B, dtype=torch.float32, device=dev)
     else:
         xo, inv_nx = _k1(x, f16n)
         wo, inv_nw = _prepare_weight(w, f16n, w_cache)
+    if raw is not None:
+        wo = torch.empty(w.shape, dtype=torch.float16, device=dev)
+        inv_nw = torch.empty(C, dtype=torch.float32, device=dev)
+        if w_cache is not None:
+            w_cache["key"], w_cache["val"] = _weight_key(w, True), (wo, inv_nw)
     row_stats = torch.empty(B, _lib.STAT_COLS, dtype=torch.float32, device=dev)
     row_best = torch.empty(B, dtype=torch.float32, device=dev)
     row_argmax = torch.empty(B, dtype=torch.int64, device=dev)
@@ -228,6 +240,23 @@ def _fwd_kernels(x, w, label, cfg: HeadCfg, class_offset, want_logits, w_cache=N
         loss = torch.empty((), dtype=torch.float32, device=dev)
         pq_norm2 = torch.empty(1, dtype=torch.float32, device=dev)
         out4 = torch.empty(4, dtype=torch.float32, device=dev)
+    if raw is not None:
+        xr, wr = raw
+        hook_p = fused_hook if fused_hook is not None else None
+        with _lib.timed("arcface_fwd", dev):
+            check(lib.b200f_arcface_fwd_raw(ptr(xr), dtype_code(xr) if xr is not None else 0, ptr(xo), ptr(inv_nx),
+                                            ptr(wr), dtype_code(wr), ptr(wo), ptr(inv_nw), NORM_EPS, ptr(label), B, C,
+                                            int(class_offset), D, cfg, hook_p, ptr(row_stats), ptr(row_best),
+                                            ptr(row_argmax), ptr(cos_minmax), ptr(nan_flag),
+                                            ptr(lse) if fused_hook is not None else None,
+                                            ptr(loss) if fused_hook is not None else None,
+                                            ptr(pq_norm2) if fused_hook is not None else None,
+                                            ptr(out4) if fused_hook is not None else None,
+                                            ptr(ws), ws.numel(), stream_ptr(dev)), "b200f_arcface_fwd_raw")
+        if fused_hook is not None:
+            return xo, wo, inv_nx, inv_nw, row_stats, row_best, row_argmax, cos_minmax, nan_flag, logits, lse, loss, pq_norm2, out4
+        return xo, wo, inv_nx, inv_nw, row_stats, row_best, row_argmax, cos_minmax, nan_flag, logits
+    if fused_hook is not None:
         with _lib.timed("arcface_fwd", dev):
             check(lib.b200f_arcface_fwd_loss(ptr(xo), ptr(wo), dtype_code(xo), ptr(inv_nx), ptr(inv_nw), ptr(label), B, C,
                                              int(class_offset), D, cfg, fused_hook, ptr(row_stats), ptr(row_best),
@@ -252,18 +281,25 @@ def _raw_rows(x_raw, xo):
 
 
 def _bwd_kernels(xo, wo, label, inv_nx, inv_nw, lse, grad4, cfg: HeadCfg, class_offset, dlogits=None, finish_dx=False,
-                 x_raw=None, dx_bf16=False):
+                 x_raw=None, dx_bf16=False, phase=0, out=None):
     """K3.  finish_dx (unsharded head): dL/dx comes out of the same call (b200f_arcface_bwd_dx) -- returns
-    (dxhat, dw, dx, dx_lowp or None)."""
+    (dxhat, dw, dx, dx_lowp or None).  phase 1 / 2 (class shards, b200f_arcface_bwd_phase): 1 = everything up to a complete
+    dx_hat (the caller all-reduces it on another stream), 2 = the remaining dW GEMM into the (dxhat, dw) of phase 1 (`out`)."""
     lib = _lib.load_library()
     _check_head_inputs(xo, wo, label, dlogits)
     B, D = xo.shape
     C = wo.shape[0]
     dev = xo.device
-    dxhat = torch.empty(B, D, dtype=torch.float32, device=dev)
-    dw = torch.empty(C, D, dtype=torch.float32, device=dev)
+    dxhat, dw = out if out is not None else (torch.empty(B, D, dtype=torch.float32, device=dev),
+                                             torch.empty(C, D, dtype=torch.float32, device=dev))
     nbytes = lib.b200f_head_workspace_bytes(B, C, D, dtype_code(xo), cfg.engine)
     ws = _lib.workspace(nbytes, dev, "head")
+    if phase:
+        with _lib.timed("arcface_bwd", dev):
+            check(lib.b200f_arcface_bwd_phase(ptr(xo), ptr(wo), dtype_code(xo), ptr(inv_nx), ptr(inv_nw), ptr(label), ptr(lse),
+                                              ptr(grad4), B, C, int(class_offset), D, cfg, ptr(dxhat), ptr(dw), int(phase),
+                                              ptr(ws), ws.numel(), stream_ptr(dev)), "b200f_arcface_bwd_phase")
+        return dxhat, dw
     if finish_dx:
         dx = torch.empty(B, D, dtype=torch.float32, device=dev)
         lowp = torch.empty(B, D, dtype=torch.bfloat16, device=dev) if dx_bf16 else None
@@ -292,6 +328,18 @@ def _normalize_bwd(xo, inv_nx, dxhat, x_raw=None, dx_bf16=False):
     check(lib.b200f_l2norm_bwd(ptr(v), dtype_code(v), OPERAND_SCALE, ptr(inv_nx), ptr(dxhat), v.shape[0],
                                v.shape[1], ptr(dx), ptr(lowp), stream_ptr(v.device)), "b200f_l2norm_bwd")
     return (dx, lowp) if dx_bf16 else dx
+
+
+_OVERLAP_STREAMS: dict = {}
+
+
+def _overlap_stream(dev) -> torch.cuda.Stream:
+    """The side stream the class-sharded backward runs its dx_hat all-reduce on (one per device, made on first use)."""
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    s = _OVERLAP_STREAMS.get(key)
+    if s is None:
+        s = _OVERLAP_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return s
 
 
 class _ArcFaceLossFn(torch.autograd.Function):
@@ -351,9 +399,16 @@ class _ArcFaceLossFn(torch.autograd.Function):
             _, dw, dx, lowp = _bwd_kernels(x, w, label, inv_nx, inv_nw, lse, grad4, cfg, ctx.class_offset, finish_dx=True,
                                            x_raw=x_raw, dx_bf16=want_bf16)
         else:
-            dxhat, dw = _bwd_kernels(x, w, label, inv_nx, inv_nw, lse, grad4, cfg, ctx.class_offset)
+            # dx_hat first; its SUM all-reduce ([B,D] fp32) runs on a side stream under the last dW GEMM of this rank
             from . import parallel
-            parallel.reduce_dxhat(dxhat, ctx.group)              # one SUM all-reduce of [B,D]
+            dxhat, dw = _bwd_kernels(x, w, label, inv_nx, inv_nw, lse, grad4, cfg, ctx.class_offset, phase=1)
+            cur = torch.cuda.current_stream(x.device)
+            side = _overlap_stream(x.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                parallel.reduce_dxhat(dxhat, ctx.group)
+            _bwd_kernels(x, w, label, inv_nx, inv_nw, lse, grad4, cfg, ctx.class_offset, phase=2, out=(dxhat, dw))
+            cur.wait_stream(side)
             if want_bf16:
                 dx, lowp = _normalize_bwd(x, inv_nx, dxhat, x_raw, dx_bf16=True)
             else:

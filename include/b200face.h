@@ -143,6 +143,24 @@ int b200f_arcface_fwd_loss(const void* x, const void* w, int dtype,
                            float* lse, float* loss, float* pq_norm2, float* out4,
                            void* workspace, size_t workspace_bytes, void* stream);
 
+/* K1 + K2 (+ K2b) from the RAW rows in one call, tcgen05 engine only (F.normalize of input and weight, src/face_models.py:
+ * 351-352, then everything b200f_arcface_fwd computes).  x_raw [B,D] (bf16 / fp32; NULL when x_f16n was already made, e.g.
+ * by b200f_tail_fwd) -> x_f16n [B,D] fp16 rows * cfg->operand_scale + inv_nx [B]; w_raw [C_local,D] (bf16 / fp32) ->
+ * w_f16n [C_local,D] + inv_nw [C_local]: all four are OUTPUTS, to be handed to b200f_arcface_bwd.  With D = 512 and 32-byte
+ * aligned rows the class weights are normalised INSIDE K2 (two warps of every CTA produce the fp16 rows in the order the
+ * TMA producers consume them, handing over through per-128-row counters in the workspace), so the 2 x C x D x 2 bytes of
+ * the stand-alone K1 pass move under K2's MMAs; other shapes run K1 as its own pass first (tunable "k2_prep" = 0 forces
+ * that).  hook NULL: statistics only (class shards: all-reduce row_stats, then b200f_arcface_loss_hook); non-NULL
+ * (unsharded head): lse / loss / pq_norm2 / out4 as b200f_arcface_fwd_loss. */
+int b200f_arcface_fwd_raw(const void* x_raw_or_null, int x_dtype, void* x_f16n, float* inv_nx,
+                          const void* w_raw, int w_dtype, void* w_f16n, float* inv_nw, float eps,
+                          const int64_t* label, int64_t B, int64_t C_local, int64_t class_offset, int D,
+                          const b200f_head_cfg* cfg, const b200f_hook_cfg* hook_or_null,
+                          float* row_stats, float* row_best, int64_t* row_argmax,
+                          float* cos_minmax, int32_t* nan_flag,
+                          float* lse, float* loss, float* pq_norm2, float* out4,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
 /* K2b -- after the (optional) cross-shard SUM of row_stats: lse[i] = s_eff + log(sumexp_i),
  * loss = mean_i[ lse_i - (1-eps) z_target_i - (eps/C) sum_z_i ]  (CrossEntropyLoss with
  * label smoothing, mean reduction), pq_norm2 = sum_ij (p_ij - q_ij)^2  (the Frobenius norm the
@@ -183,6 +201,19 @@ int b200f_arcface_bwd(const void* x, const void* w, int dtype,
                       const b200f_head_cfg* cfg,
                       float* dxhat, float* dw,
                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* b200f_arcface_bwd in two calls, for class shards that overlap the cross-rank all-reduce of dx_hat with the dW GEMM.
+ * phase 1: per class chunk K3a -> K3c -> split reduction -> K3b, WITHOUT the last chunk's K3b: dxhat is complete when it
+ * returns (in stream order) and the caller starts its all-reduce on ANOTHER stream; phase 2 (same arguments, same
+ * workspace, nothing of this library in between on that workspace): the last chunk's K3b from the G^T and r partials phase
+ * 1 left in the workspace -- dw is complete after it.  Same results as the single call, bit for bit (the kernels and
+ * their inputs are the same; only the launch order differs).  CUDA-core engine: phase 1 does everything, phase 2 nothing. */
+int b200f_arcface_bwd_phase(const void* x, const void* w, int dtype,
+                            const float* inv_nx, const float* inv_nw, const int64_t* label,
+                            const float* lse, const float* grad_scale,
+                            int64_t B, int64_t C_local, int64_t class_offset, int D,
+                            const b200f_head_cfg* cfg, float* dxhat, float* dw, int phase,
+                            void* workspace, size_t workspace_bytes, void* stream);
 
 /* K3 for an unsharded head, finished: b200f_arcface_bwd, then dL/dx = normalise-backward of dxhat (below) written to
  * dx [B,D] fp32 and, optionally, as bf16 (the cast autograd applies for a bf16 input) -- on the tcgen05 engine inside

@@ -494,3 +494,79 @@ def test_backward_chunking_is_invisible(cuda_device, mb, B, C):
     assert float(loss) == pytest.approx(float(ref["loss"]), rel=TOL_BF16)
     assert rel_err(head.weight.grad.cpu().numpy(), ref["dw"]) < TOL_BF16
     assert rel_err(head.last_stats.dx_f32.cpu().numpy(), ref["dx"]) < TOL_BF16
+
+
+@pytest.mark.parametrize("B,C,wdt", [(512, 20000, torch.bfloat16), (1024, 30000, torch.bfloat16), (256, 10007, torch.bfloat16),
+                                     (64, 100, torch.bfloat16), (384, 9000, torch.float32), (2100, 6000, torch.bfloat16)])
+def test_k1w_inside_k2_equals_separate_pass(cuda_device, B, C, wdt):
+    """b200f_arcface_fwd_raw with the class weights normalised INSIDE K2 (prep warps + per-128-row hand-over counters, tunable
+    k2_prep = 1, the default) against K1 as a pass of its own in front of K2 (k2_prep = 0): the fp16 operand rows and the
+    inverse norms must be the same bits (bf16 weights: same per-lane element order and reduction), hence the same statistics,
+    loss and gradients; fp32 weights sum in another lane order, so there the bar is the operand rounding.  Shapes: one wave
+    (B = 512), several row groups and waves (B = 1024, 2100), a ragged last tile, fewer classes than one tile.  Repeated calls
+    re-arm the counters."""
+    from b200face import _lib
+    from b200face import head as H
+    lib = _lib.load_library()
+    D = 512
+    g = torch.Generator().manual_seed(B + C)
+    x = torch.randn(B, D, generator=g).bfloat16().to(cuda_device)
+    w = (torch.randn(C, D, generator=g) * 0.05).to(wdt).to(cuda_device)
+    y = torch.randint(0, C, (B,), generator=g).to(cuda_device)
+    cfg = H._head_cfg(0.45, 30.0, 0.05, False, C, _lib.ENGINE_AUTO)
+    hk = _lib.HookCfg(0, 1.0, 1, 0)
+    res = {}
+    for mode in (0, 1, 1):
+        old = lib.b200f_set_tunable(b"k2_prep", mode)
+        try:
+            out = H._fwd_kernels(x, w, y, cfg, 0, False, fused_hook=hk)
+            torch.cuda.synchronize()
+        finally:
+            lib.b200f_set_tunable(b"k2_prep", old)
+        res.setdefault(mode, []).append([t.clone() for t in (out[0], out[1], out[2], out[3], out[4], out[10], out[11])])
+    assert int(lib.b200f_umma_timeout_flag(1)) == 0
+    ref = res[0][0]
+    for got in res[1]:
+        assert torch.equal(got[0], ref[0]) and torch.equal(got[2], ref[2])                 # x operands, 1/||x||
+        if wdt == torch.bfloat16:
+            assert torch.equal(got[1], ref[1]) and torch.equal(got[3], ref[3])             # w operands, 1/||w||
+            # K2 itself runs on 16-column slices beside the prep warps (32 without): the statistics sum in another order
+            torch.testing.assert_close(got[4], ref[4], rtol=2e-5, atol=2e-3)    # column 3 is a sum of logits of both signs
+            torch.testing.assert_close(got[5], ref[5], rtol=2e-6, atol=0)
+            torch.testing.assert_close(got[6], ref[6], rtol=2e-6, atol=0)
+        else:
+            assert (got[1].float() - ref[1].float()).abs().max() <= 2 ** -3                # one fp16 ulp at 256
+            torch.testing.assert_close(got[3], ref[3], rtol=1e-6, atol=0)
+            torch.testing.assert_close(got[6], ref[6], rtol=1e-5, atol=0)
+    # the reference's own normalise as the anchor of the rows themselves
+    wn = torch.nn.functional.normalize(w.float(), dim=1) * 256.0
+    assert (res[1][0][1].float() - wn).abs().max() <= 2 ** -3 + 1e-3
+
+
+@pytest.mark.parametrize("B,C,mb", [(384, 9000, 112), (384, 9000, 4), (640, 24000, 1), (1024, 20000, 112)])
+def test_backward_in_two_phases_equals_one_call(cuda_device, B, C, mb):
+    """b200f_arcface_bwd_phase 1 + 2 (dx_hat first, the last dW GEMM afterwards: what the class-sharded backward does to hide
+    its all-reduce) == b200f_arcface_bwd, bit for bit, with one and with several class chunks, resident and streamed dW."""
+    from b200face import _lib
+    from b200face import head as H
+    lib = _lib.load_library()
+    D = 512
+    g = torch.Generator().manual_seed(B * 3 + C)
+    x = torch.randn(B, D, generator=g).bfloat16().to(cuda_device)
+    w = (torch.randn(C, D, generator=g) * 0.05).bfloat16().to(cuda_device)
+    y = torch.randint(0, C, (B,), generator=g).to(cuda_device)
+    cfg = H._head_cfg(0.45, 30.0, 0.05, False, C, _lib.ENGINE_AUTO)
+    old = lib.b200f_set_tunable(b"g_chunk_mb", mb)
+    try:
+        out = H._fwd_kernels(x, w, y, cfg, 0, False, fused_hook=_lib.HookCfg(0, 1.0, 1, 0))
+        xo, wo, inv_nx, inv_nw, lse, out4 = out[0], out[1], out[2], out[3], out[10], out[13]
+        dxhat0, dw0 = H._bwd_kernels(xo, wo, y, inv_nx, inv_nw, lse, out4, cfg, 0)
+        dxhat1, dw1 = H._bwd_kernels(xo, wo, y, inv_nx, inv_nw, lse, out4, cfg, 0, phase=1)
+        dx_after_phase1 = dxhat1.clone()
+        H._bwd_kernels(xo, wo, y, inv_nx, inv_nw, lse, out4, cfg, 0, phase=2, out=(dxhat1, dw1))
+        torch.cuda.synchronize()
+    finally:
+        lib.b200f_set_tunable(b"g_chunk_mb", old)
+    assert torch.equal(dx_after_phase1, dxhat0) and torch.equal(dxhat1, dxhat0)
+    assert torch.equal(dw1, dw0)
+    assert torch.isfinite(dw0).all() and torch.isfinite(dxhat0).all()
