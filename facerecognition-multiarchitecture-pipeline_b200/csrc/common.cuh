@@ -56,6 +56,8 @@ struct NvtxRange {
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 bool pdl_enabled();            // tunable "pdl" (default on)
+int k1_hints();                // tunable "k1_hints": L2 cache-policy bits of K1 over the class weights (rowops.cuh)
+int k1_hints_set(int v);
 void pdl_set(bool on);
 
 template <typename... KArgs, typename... Args>

@@ -148,18 +148,31 @@ l2norm_rows_vec_kernel(const TI* __restrict__ in, int64_t rows, int dim, float e
 
 // K1, 512-wide 16-bit rows (the head's shape): each lane owns 32 contiguous bytes of a row -- ONE 256-bit load and
 // ONE 256-bit store per lane and row (full 32 B sectors), 4 rows per warp in flight.
+// hints (tunable "k1_hints", a bit mask): 1 = the source rows are read once: L2 evict_first; 2 = the operand rows are read
+// again by the next kernel: L2 evict_last, so that they stay in the 126 MB L2 as dirty lines -- their write-back to HBM then
+// happens under the consumer (K2 has HBM bandwidth to spare) instead of competing with this kernel's reads.
 template <typename TI, typename TO>
 __device__ __forceinline__ void l2norm_rows_512x16_body(const TI* __restrict__ in, int64_t rows, float eps, float out_scale,
-                                                        float* __restrict__ inv_norm, TO* __restrict__ out, int64_t block) {
+                                                        float* __restrict__ inv_norm, TO* __restrict__ out, int64_t block,
+                                                        int hints = 0) {
   static_assert(sizeof(TI) == 2 && sizeof(TO) == 2, "16-bit rows only");
   const int lane = threadIdx.x & 31;
   const int64_t row0 = (block * WARPS_PER_BLOCK + (threadIdx.x >> 5)) * ROWS_PER_WARP;
   if (row0 >= rows) return;
+  uint64_t pol_ld = 0, pol_st = 0;
+  if (hints & 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_ld));
+  if (hints & 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_st));
   uint32_t raw[ROWS_PER_WARP][8];
 #pragma unroll
   for (int r = 0; r < ROWS_PER_WARP; ++r) {
     if (row0 + r < rows) {
       const TI* src = in + (row0 + r) * 512 + lane * 16;
+      if (hints & 1)
+        asm volatile("ld.global.nc.L2::cache_hint.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8], %9;"
+                     : "=r"(raw[r][0]), "=r"(raw[r][1]), "=r"(raw[r][2]), "=r"(raw[r][3]), "=r"(raw[r][4]), "=r"(raw[r][5]),
+                       "=r"(raw[r][6]), "=r"(raw[r][7])
+                     : "l"(src), "l"(pol_ld));
+      else
       asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                    : "=r"(raw[r][0]), "=r"(raw[r][1]), "=r"(raw[r][2]), "=r"(raw[r][3]), "=r"(raw[r][4]), "=r"(raw[r][5]),
                      "=r"(raw[r][6]), "=r"(raw[r][7])
@@ -193,6 +206,12 @@ __device__ __forceinline__ void l2norm_rows_512x16_body(const TI* __restrict__ i
         store_elem<TO>(&pr[0], v[2 * i] * s); store_elem<TO>(&pr[1], v[2 * i + 1] * s);
         o[i] = *reinterpret_cast<uint32_t*>(pr);
       }
+      if (hints & 2)
+        asm volatile("st.global.L2::cache_hint.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8}, %9;"
+                     ::"l"(out + (row0 + r) * 512 + lane * 16), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]),
+                       "r"(o[6]), "r"(o[7]), "l"(pol_st)
+                     : "memory");
+      else
       asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                    ::"l"(out + (row0 + r) * 512 + lane * 16), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]),
                      "r"(o[6]), "r"(o[7])
@@ -203,9 +222,9 @@ __device__ __forceinline__ void l2norm_rows_512x16_body(const TI* __restrict__ i
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 l2norm_rows_512x16_kernel(const TI* __restrict__ in, int64_t rows, float eps, float out_scale,
-                          float* __restrict__ inv_norm, TO* __restrict__ out) {
+                          float* __restrict__ inv_norm, TO* __restrict__ out, int hints) {
   pdl_trigger(); pdl_wait();
-  l2norm_rows_512x16_body<TI, TO>(in, rows, eps, out_scale, inv_norm, out, (int64_t)blockIdx.x);
+  l2norm_rows_512x16_body<TI, TO>(in, rows, eps, out_scale, inv_norm, out, (int64_t)blockIdx.x, hints);
 }
 // K1 over the batch rows + clearing a word array for the kernel behind it (the row counters of K1(W)-inside-K2)
 template <typename TI, typename TO>
@@ -223,10 +242,10 @@ template <typename TI, typename TO>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 l2norm_rows_512x16_pair_kernel(const TI* __restrict__ in0, int64_t rows0, float* __restrict__ inv0, TO* __restrict__ out0,
                                int blocks0, const TI* __restrict__ in1, int64_t rows1, float* __restrict__ inv1,
-                               TO* __restrict__ out1, float eps, float out_scale) {
+                               TO* __restrict__ out1, float eps, float out_scale, int hints1) {
   pdl_trigger(); pdl_wait();
   if ((int)blockIdx.x < blocks0) l2norm_rows_512x16_body<TI, TO>(in0, rows0, eps, out_scale, inv0, out0, (int64_t)blockIdx.x);
-  else l2norm_rows_512x16_body<TI, TO>(in1, rows1, eps, out_scale, inv1, out1, (int64_t)blockIdx.x - blocks0);
+  else l2norm_rows_512x16_body<TI, TO>(in1, rows1, eps, out_scale, inv1, out1, (int64_t)blockIdx.x - blocks0, hints1);
 }
 
 // K1, generic path (any dim / alignment): one warp per row, scalar accesses.
@@ -332,8 +351,9 @@ static inline void launch_l2norm_rows(const TI* in, int64_t rows, int dim, float
   constexpr int N = Vec16<TI>::N;
   if constexpr (sizeof(TI) == 2 && sizeof(TO) == 2) {
     if (dim == 512 && reinterpret_cast<uintptr_t>(in) % 32 == 0 && (!out || reinterpret_cast<uintptr_t>(out) % 32 == 0)) {
-      launch_pdl(l2norm_rows_512x16_kernel<TI, TO>, dim3((unsigned)ceil_div(rows, ROWS_PER_BLOCK)), dim3(WARPS_PER_BLOCK * 32), 0, st, 
-          in, rows, eps, out_scale, inv_norm, out);
+      // rows that fill a good part of the L2 are class weights on their way into K2: cache hints as the tunable says
+      launch_pdl(l2norm_rows_512x16_kernel<TI, TO>, dim3((unsigned)ceil_div(rows, ROWS_PER_BLOCK)), dim3(WARPS_PER_BLOCK * 32), 0, st,
+          in, rows, eps, out_scale, inv_norm, out, (out != nullptr && rows >= 16384) ? k1_hints() : 0);
       return;
     }
   }

@@ -27,6 +27,9 @@ int fail(int code, const char* fmt, ...) {
 static std::atomic<int> g_pdl{1};
 bool pdl_enabled() { return g_pdl.load(std::memory_order_relaxed) != 0; }
 void pdl_set(bool on) { g_pdl.store(on ? 1 : 0, std::memory_order_relaxed); }
+static std::atomic<int> g_k1_hints{0};
+int k1_hints() { return g_k1_hints.load(std::memory_order_relaxed); }
+int k1_hints_set(int v) { return g_k1_hints.exchange(v); }
 
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
@@ -128,7 +131,7 @@ int b200f_l2norm_rows_pair(const void* in0, int64_t rows0, float* inv0, void* ou
     launch_pdl(rowops::l2norm_rows_512x16_pair_kernel<__nv_bfloat16, __half>, dim3((unsigned)(b0 + b1)),
                dim3(rowops::WARPS_PER_BLOCK * 32), 0, as_stream(stream), static_cast<const __nv_bfloat16*>(in0), rows0, inv0,
                static_cast<__half*>(out0), (int)b0, static_cast<const __nv_bfloat16*>(in1), rows1, inv1,
-               static_cast<__half*>(out1), eps, out_scale);
+               static_cast<__half*>(out1), eps, out_scale, rows1 >= 16384 ? k1_hints() : 0);
     B200F_LAUNCH_OK("l2norm_rows pair kernel");
     return B200F_OK;
   }

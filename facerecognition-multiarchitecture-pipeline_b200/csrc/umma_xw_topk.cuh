@@ -85,14 +85,40 @@ struct XwTopK {
     constexpr float PAD = 3.0e38f;                            // beyond the gallery: finite, never selected
     float a[32];
     if (ep.bias != nullptr) {
+      if (cc == 32 && (reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0) {   // the slice's 32 biases as eight 16-byte loads (warp-uniform address)
+        const float4* b4 = reinterpret_cast<const float4*>(ep.bias + cls0);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) a[j] = (j < cc) ? fmaf(v[j], ep.mult, __ldg(ep.bias + cls0 + j)) : PAD;
+        for (int j = 0; j < 32; j += 4) {
+          const float4 bb = __ldg(b4 + (j >> 2));
+          a[j] = fmaf(v[j], ep.mult, bb.x); a[j + 1] = fmaf(v[j + 1], ep.mult, bb.y);
+          a[j + 2] = fmaf(v[j + 2], ep.mult, bb.z); a[j + 3] = fmaf(v[j + 3], ep.mult, bb.w);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) a[j] = (j < cc) ? fmaf(v[j], ep.mult, __ldg(ep.bias + cls0 + j)) : PAD;
+      }
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j) a[j] = (j < cc) ? v[j] * ep.mult : PAD;
     }
     // (NaN keys never win an fminf and never enter a list -- the exact engine drops NaN distances too.  Operands that
     //  turn non-finite only in 16 bits are caught when they are prepared, see gallery_prepare_kernel.)
+    // Reject test before any key is packed: a packed key differs from its element by < 2^-18 |element|, so an element
+    // whose packed key would beat the bound is itself below  bound + 2^-17 |bound|.  With the sample bound in place
+    // nearly every slice ends here -- one FFMA and one FMNMX per element (above 128 queries the scan is bound by this
+    // epilogue, not by HBM).
+    {
+      float u4[4] = {PAD, PAD, PAD, PAD};
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) u4[u] = fminf(u4[u], a[j + u]);
+      }
+      const float umin = fminf(fminf(u4[0], u4[1]), fminf(u4[2], u4[3]));
+      const float bound = fminf(st.key[KT - 1], st.lim0);
+      const float bound_hi = bound + fabsf(bound) * 7.7e-6f + 1e-37f;       // 2^-17 = 7.63e-6
+      if (!__any_sync(0xffffffffu, umin < bound_hi)) return;
+    }
     float m4[4] = {PAD, PAD, PAD, PAD};
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {

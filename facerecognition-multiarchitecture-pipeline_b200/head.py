@@ -18,6 +18,8 @@ import math
 from dataclasses import dataclass
 from typing import Optional
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -331,6 +333,8 @@ def _normalize_bwd(xo, inv_nx, dxhat, x_raw=None, dx_bf16=False):
 
 
 _OVERLAP_STREAMS: dict = {}
+# class-sharded backward: run the dx_hat all-reduce on a side stream under the last dW GEMM (B200F_OVERLAP=0: in stream order)
+OVERLAP_DXHAT_ALLREDUCE = os.environ.get("B200F_OVERLAP", "1") != "0"
 
 
 def _overlap_stream(dev) -> torch.cuda.Stream:
@@ -399,16 +403,20 @@ class _ArcFaceLossFn(torch.autograd.Function):
             _, dw, dx, lowp = _bwd_kernels(x, w, label, inv_nx, inv_nw, lse, grad4, cfg, ctx.class_offset, finish_dx=True,
                                            x_raw=x_raw, dx_bf16=want_bf16)
         else:
-            # dx_hat first; its SUM all-reduce ([B,D] fp32) runs on a side stream under the last dW GEMM of this rank
             from . import parallel
-            dxhat, dw = _bwd_kernels(x, w, label, inv_nx, inv_nw, lse, grad4, cfg, ctx.class_offset, phase=1)
-            cur = torch.cuda.current_stream(x.device)
-            side = _overlap_stream(x.device)
-            side.wait_stream(cur)
-            with torch.cuda.stream(side):
-                parallel.reduce_dxhat(dxhat, ctx.group)
-            _bwd_kernels(x, w, label, inv_nx, inv_nw, lse, grad4, cfg, ctx.class_offset, phase=2, out=(dxhat, dw))
-            cur.wait_stream(side)
+            if OVERLAP_DXHAT_ALLREDUCE and x.is_cuda:
+                # dx_hat first; its SUM all-reduce ([B,D] fp32) runs on a side stream under the last dW GEMM of this rank
+                dxhat, dw = _bwd_kernels(x, w, label, inv_nx, inv_nw, lse, grad4, cfg, ctx.class_offset, phase=1)
+                cur = torch.cuda.current_stream(x.device)
+                side = _overlap_stream(x.device)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    parallel.reduce_dxhat(dxhat, ctx.group)
+                _bwd_kernels(x, w, label, inv_nx, inv_nw, lse, grad4, cfg, ctx.class_offset, phase=2, out=(dxhat, dw))
+                cur.wait_stream(side)
+            else:
+                dxhat, dw = _bwd_kernels(x, w, label, inv_nx, inv_nw, lse, grad4, cfg, ctx.class_offset)
+                parallel.reduce_dxhat(dxhat, ctx.group)          # one SUM all-reduce of [B,D], in stream order
             if want_bf16:
                 dx, lowp = _normalize_bwd(x, inv_nx, dxhat, x_raw, dx_bf16=True)
             else:

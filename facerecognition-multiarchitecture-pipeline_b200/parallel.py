@@ -119,6 +119,7 @@ class ShardedArcMarginProduct(torch.nn.Module):
     def __init__(self, in_feats, out_feats, s=32.0, m=0.5, use_warm_up=True, easy_margin=False, group=None, seed=0):
         super().__init__()
         from .head import ArcMarginProduct
+        group = group if group is not None else dist.group.WORLD       # the head reads "no group" as "not sharded"
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
