@@ -217,6 +217,7 @@ static std::atomic<int> g_k3a_ablate{0};            // probe: 2 = no G^T stores 
 static std::atomic<int> g_k3b_ablate{0};            // probe: 1 = no w_hat loads, 2 = no dW stores (WRONG results)
 #endif
 static std::atomic<int> g_k3b_reverse{1};
+static std::atomic<int> g_x_whole{0};               // tunable "x_whole": 1 = first MMA of an item waits for the whole resident operand
 // "stage_events" tunable: record a CUDA event pair around each GEMM kernel of the head on the launching stream
 // (bench.py's per-kernel durations; eager launches only -- never inside a graph capture).
 static std::atomic<int> g_stage_events{0};
@@ -329,6 +330,7 @@ static int launch_xw(const CUtensorMap& tx, const CUtensorMap& tw, const XwPlan&
   p.w_hint = w_hint;
   p.tn = XW_WROWS * PAIR;
   p.reverse = reverse ? 1 : 0;
+  p.x_whole = g_x_whole.load(std::memory_order_relaxed);
   if (prep != nullptr) {
     p.prep_src = prep->src; p.prep_f32 = prep->f32; p.prep_dst = prep->dst; p.prep_inv = prep->inv; p.prep_ready = prep->ready;
     p.prep_eps = prep->eps; p.prep_scale = prep->scale;
@@ -992,6 +994,7 @@ int b200f_set_tunable(const char* name, int value) {
   if (n == "pdl") { const int old_v = pdl_enabled() ? 1 : 0; if (value == 0 || value == 1) pdl_set(value != 0); return old_v; }
   if (n == "stage_events") { if (value != 0 && value != 1) return g_stage_events.load(); return g_stage_events.exchange(value); }
   if (n == "k2_prep") { if (value < 0 || value > 2) return g_k2_prep.load(); return g_k2_prep.exchange(value); }
+  if (n == "x_whole") { if (value != 0 && value != 1) return g_x_whole.load(); return g_x_whole.exchange(value); }
   if (n == "k1_hints") { if (value < 0 || value > 3) return k1_hints(); return k1_hints_set(value); }
   if (n == "l2_hints") { if (value < 0) return g_l2_hints.load(); return g_l2_hints.exchange(value); }
   if (n == "k2_groups") { if (value != 1 && value != 2) return g_k2_groups.load(); return g_k2_groups.exchange(value); }

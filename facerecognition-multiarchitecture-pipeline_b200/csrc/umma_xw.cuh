@@ -38,7 +38,7 @@ constexpr int XW_THREADS = 64 + 32 * XW_EPI_WARPS;   // 320: producer + MMA issu
 constexpr int XW_MAX_EPI_GROUPS = 2;
 constexpr int XW_SCRATCH_FLOATS = 2048;
 constexpr int XW_MAX_ACC = 4;                     // accumulator stages: 2 x 256 columns (CTA pair) or 4 x 128 (single CTA)
-constexpr int XW_NUM_BARS = 2 + 2 * XW_STAGES + 2 * XW_MAX_ACC;
+constexpr int XW_NUM_BARS = 1 + XW_MAX_KB + 2 * XW_STAGES + 2 * XW_MAX_ACC;   // x_empty, x_full[kb], ring full / empty, accumulators
 constexpr size_t XW_SMEM_BYTES = 1024 + (size_t)(XW_MAX_KB + XW_STAGES) * XW_TILE_BYTES + XW_SCRATCH_FLOATS * 4 + 256;
 constexpr uint32_t XW_ACC_STRIDE = 256;         // TMEM columns between accumulator stages of a CTA pair (single CTA: 128)
 
@@ -122,6 +122,7 @@ struct XwParams {
                                         // MMA warps do not wait for the predecessor: loads and MMAs of the first tiles overlap its
                                         // tail.  The epilogue warps wait (griddepcontrol.wait) before they touch anything.
   uint32_t idesc;
+  int x_whole;                          // 1: the MMA issuer waits for the whole resident operand before the item's first MMA
   // ---- operand preparation fused into the kernel (policies with kPrepWarps > 0: K2 of the head) ------------------------
   // The streamed operand does not exist yet when the kernel starts: prep warps of ALL CTAs produce it (K1 of the class
   // weights: row L2-normalise -> fp16 rows * out_scale + 1/||w||) in the order the tiles are consumed, and count finished
@@ -417,15 +418,17 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
   uint8_t* ring = smem + (size_t)XW_MAX_KB * XW_TILE_BYTES;  // XW_STAGES x 16 KB
   float* scratch = reinterpret_cast<float*>(ring + (size_t)XW_STAGES * XW_TILE_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(scratch + XW_SCRATCH_FLOATS);
-  uint64_t* x_full = bars;                                   // TMA -> MMA (leader)
-  uint64_t* x_empty = bars + 1;                              // MMA -> TMA (both CTAs)
-  uint64_t* full_bar = bars + 2;                             // [STAGES] TMA -> MMA (leader)
-  uint64_t* empty_bar = bars + 2 + XW_STAGES;                // [STAGES] MMA -> TMA (both CTAs)
+  // one barrier per k-block of the resident operand: the first tile's MMAs of k-block kb start when ITS 16 KB have landed,
+  // not when all 128 KB have (148 CTAs pull 19 MB of x_hat out of L2 at the start of every kernel: ~3 us)
+  uint64_t* x_empty = bars;                                  // MMA -> TMA (both CTAs)
+  uint64_t* x_full = bars + 1;                               // [XW_MAX_KB] TMA -> MMA (leader)
+  uint64_t* full_bar = bars + 1 + XW_MAX_KB;                 // [STAGES] TMA -> MMA (leader)
+  uint64_t* empty_bar = full_bar + XW_STAGES;                // [STAGES] MMA -> TMA (both CTAs)
   // A single CTA's tile is 128 columns wide: its 512 TMEM columns hold FOUR accumulator stages, so the MMA issuer can run
   // two tiles ahead of the slowest epilogue warp (with two stages every hand-off latency sits on the critical path).
   constexpr int ACC = (PAIR == 1) ? 4 : 2;
   constexpr uint32_t ACC_STRIDE = 512 / ACC;
-  uint64_t* acc_full = bars + 2 + 2 * XW_STAGES;             // [ACC] MMA -> epilogue (both CTAs)
+  uint64_t* acc_full = empty_bar + XW_STAGES;                // [ACC] MMA -> epilogue (both CTAs)
   uint64_t* acc_empty = acc_full + XW_MAX_ACC;               // [ACC] epilogue (both CTAs) -> MMA (leader)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + XW_NUM_BARS);
   uint8_t* aux = ring + (size_t)STAGES * XW_TILE_BYTES;       // (XW_STAGES - STAGES) x 16 KB of warp-private staging
@@ -444,7 +447,7 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x);
     tma_prefetch_desc(&tm_w);
-    mbar_init(x_full, PAIR);
+    for (int kb = 0; kb < XW_MAX_KB; ++kb) mbar_init(&x_full[kb], PAIR);
     mbar_init(x_empty, 1);
     for (int s = 0; s < XW_STAGES; ++s) { mbar_init(&full_bar[s], PAIR); mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < ACC; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], PAIR * XW_EPI_WARPS); }
@@ -491,15 +494,15 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
         if (item_no > 0) { ok = mbar_wait(x_empty, (uint32_t)((item_no - 1) & 1)); if (!ok) break; }
         const int row0 = (g * PAIR + rank) * XW_M;
         if (leader) {
-          if (rank == 0) mbar_arrive_expect_tx(x_full, (uint32_t)(PAIR * p.kb_count * XW_TILE_BYTES));
-          else mbar_arrive_cluster(x_full, 0);
           for (int kb = 0; kb < p.kb_count; ++kb) {
+            if (rank == 0) mbar_arrive_expect_tx(&x_full[kb], (uint32_t)(PAIR * XW_TILE_BYTES));
+            else mbar_arrive_cluster(&x_full[kb], 0);
             uint8_t* dst = xres + (size_t)kb * XW_TILE_BYTES;
             if (!X_MN) {
-              xw_tma_load<PAIR>(dst, &tm_x, x_full, kb * XW_K, row0);
+              xw_tma_load<PAIR>(dst, &tm_x, &x_full[kb], kb * XW_K, row0);
             } else {                                              // two 64-wide row blocks of 64 k-rows each
-              xw_tma_load<PAIR>(dst, &tm_x, x_full, row0, kb * XW_K);
-              xw_tma_load<PAIR>(dst + XW_TILE_BYTES / 2, &tm_x, x_full, row0 + 64, kb * XW_K);
+              xw_tma_load<PAIR>(dst, &tm_x, &x_full[kb], row0, kb * XW_K);
+              xw_tma_load<PAIR>(dst + XW_TILE_BYTES / 2, &tm_x, &x_full[kb], row0 + 64, kb * XW_K);
             }
           }
         }
@@ -570,15 +573,20 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
         const int chunk = item / p.m_groups;
         const int t_begin = (int)((int64_t)chunk * p.n_tiles / p.n_chunks);
         const int t_end = (int)((int64_t)(chunk + 1) * p.n_tiles / p.n_chunks);
-        ok = mbar_wait(x_full, (uint32_t)(item_no & 1));
-        if (!ok) break;
-        tc_fence_after_sync();
         for (int t = t_begin; t < t_end && ok; ++t) {
           ok = mbar_wait(&acc_empty[acc], acc_phase ^ 1);
           if (!ok) break;
           tc_fence_after_sync();
           const uint32_t d_tmem = tmem_base + (uint32_t)acc * ACC_STRIDE;
           for (int kb = 0; kb < p.kb_count; ++kb) {
+            if (t == t_begin) {                                   // the item's resident operand, k-block by k-block
+              if (p.x_whole) {                                    // (tunable "x_whole" = 1: all of it before the first MMA, as round 1 did)
+                if (kb == 0) for (int k2 = 0; k2 < p.kb_count; ++k2) mbar_wait(&x_full[k2], (uint32_t)(item_no & 1));
+              } else {
+                ok = mbar_wait(&x_full[kb], (uint32_t)(item_no & 1));
+                if (!ok) break;
+              }
+            }
             ok = mbar_wait(&full_bar[stage], phase);
             if (!ok) break;
             tc_fence_after_sync();
