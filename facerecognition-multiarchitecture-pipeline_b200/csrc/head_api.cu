@@ -129,6 +129,20 @@ static int head_bwd_simt(const void* x, const void* w, const float* inv_nx, cons
   return B200F_OK;
 }
 
+// sum of squares of n floats, one block, fixed order (the fp32 engine's ||dW||^2: its problems are small)
+static __global__ void __launch_bounds__(1024) sumsq_kernel(const float* __restrict__ v, int64_t n, float* out) {
+  __shared__ float sh[1024];
+  float s = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += 1024) s = fmaf(v[i], v[i], s);
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = sh[0];
+}
+
 }  // namespace b200f
 
 using namespace b200f;
@@ -224,6 +238,13 @@ static int arcface_bwd_impl(const char* who, const void* x, const void* w, int d
     rc = head_bwd_simt<__nv_bfloat16>(x, w, inv_nx, inv_nw, label, lse, grad_scale, dlogits_or_null, ld_dlogits,
                                       B, C_local, class_offset, D, cfg, dxhat, dw,
                                       static_cast<char*>(workspace), pl, st);
+  if (float* sq = umma::head_dw_sqnorm_request()) {            // CUDA-core engine: one pass over its (small) dW
+    umma::head_request_dw_sqnorm(nullptr);
+    if (!rc) {
+      sumsq_kernel<<<1, 1024, 0, st>>>(dw, C_local * (int64_t)D, sq);
+      B200F_LAUNCH_OK("sumsq_kernel");
+    }
+  }
   if (rc || hdx == nullptr || hdx->dx == nullptr) return rc;
   // CUDA-core engine: its operands ARE the raw rows
   __nv_bfloat16* lowp = static_cast<__nv_bfloat16*>(hdx->dx_bf16);
@@ -295,6 +316,11 @@ int b200f_arcface_bwd(const void* x, const void* w, int dtype, const float* inv_
   B200F_NVTX("b200f_arcface_bwd");
   return arcface_bwd_impl("arcface_bwd", x, w, dtype, inv_nx, inv_nw, label, lse, grad_scale, dlogits_or_null, ld_dlogits, B,
                           C_local, class_offset, D, cfg, dxhat, dw, nullptr, workspace, workspace_bytes, stream);
+}
+
+int b200f_head_request_dw_sqnorm(float* out_or_null) {
+  umma::head_request_dw_sqnorm(out_or_null);
+  return B200F_OK;
 }
 
 int b200f_arcface_bwd_phase(const void* x, const void* w, int dtype, const float* inv_nx, const float* inv_nw,

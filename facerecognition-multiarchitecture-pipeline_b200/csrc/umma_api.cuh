@@ -29,6 +29,10 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
              const float* grad4, int64_t B, int64_t C, int64_t class_offset, int D, const b200f_head_cfg* cfg,
              float* dxhat, float* dw, const HeadDx* hdx, char* ws, size_t ws_bytes, cudaStream_t st, int phase = 0);
 
+// ||dW||^2 side output: the calling thread's next head_bwd (phase 0, or phases 1 + 2) leaves sum(dW^2) in out[0]
+void head_request_dw_sqnorm(float* out);
+float* head_dw_sqnorm_request();
+
 // dx = normalise-backward(dxhat) with the rows HeadDx names (one launch of rowops::l2norm_bwd)
 int head_dx_finish(const void* xh, float S, const HeadDx* hdx, const float* dxhat, int64_t B, int D, cudaStream_t st);
 

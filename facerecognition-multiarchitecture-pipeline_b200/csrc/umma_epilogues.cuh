@@ -90,9 +90,11 @@ struct CoefSrc {
 // row-per-lane loads of wh is a small fraction of the tile: fusing it removes the separate pass over dW (read + write of
 // 4 B per element plus the wh read) that used to follow.
 struct EpiDwNorm {
-  struct Params { float* out; int64_t ld; int64_t row_offset; CoefSrc coef; const __half* wh; };
+  struct Params { float* out; int64_t ld; int64_t row_offset; CoefSrc coef; const __half* wh;
+                  float* sq_part; };        // NULL, or [ceil(M / 128) * n_tiles * 4]: sum of dW^2 per (128-row block, n tile, warp)
   static __device__ __forceinline__ void run(const Params& ep, const GemmParams& p, const TileCoord& t,
                                              uint32_t tmem_acc, int quad, int lane, int epi_tid, float* scratch) {
+    float sq = 0.f;
     const int row = t.m0 + quad * 32 + lane;
     const int ncols = min(BLOCK_N, p.N - t.n0);
     const bool row_ok = row < p.M;
@@ -125,6 +127,15 @@ struct EpiDwNorm {
             o[i * 8 + 2 * j + 1] = cf.x * fmaf(-f.y, cf.y, v[i * 8 + 2 * j + 1]);
           }
         }
+        if (ep.sq_part != nullptr) {
+          float q4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) q4[u] = fmaf(o[j + u], o[j + u], q4[u]);
+          }
+          sq += (q4[0] + q4[1]) + (q4[2] + q4[3]);
+        }
 #pragma unroll
         for (int j = 0; j < 32; j += 8)
           st_global_256(dst + j, __float_as_uint(o[j]), __float_as_uint(o[j + 1]), __float_as_uint(o[j + 2]),
@@ -133,8 +144,15 @@ struct EpiDwNorm {
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (j < cc) dst[j] = cf.x * fmaf(-__half2float(__ldg(ep.wh + base + ch * 32 + j)), cf.y, v[j]);
+          if (j < cc) {
+            const float o1 = cf.x * fmaf(-__half2float(__ldg(ep.wh + base + ch * 32 + j)), cf.y, v[j]);
+            dst[j] = o1; sq = fmaf(o1, o1, sq);
+          }
       }
+    }
+    if (ep.sq_part != nullptr) {                              // every lane of the warp arrives here (rows beyond M hold 0)
+      const float s = warp_sum(sq);
+      if (lane == 0) ep.sq_part[((int64_t)(t.m0 / 128) * p.n_tiles + t.n0 / BLOCK_N) * 4 + quad] = s;
     }
     (void)epi_tid; (void)scratch;
   }

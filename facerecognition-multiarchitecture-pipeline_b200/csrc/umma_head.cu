@@ -358,7 +358,7 @@ struct Plan {
   XwPlan fwd;
   size_t off_part, off_cos, off_counter, off_ready;
   int64_t Cc, ldg; int n_chunks, dx_splits;
-  size_t off_G, off_dxpart, off_rpart;
+  size_t off_G, off_dxpart, off_rpart, off_sq, n_sq;
   int n_rb;                 // 32-row blocks of the batch that K3a emits r partials for
   bool fused_dw;            // B <= 512: dW GEMM on the MN-major X-stationary kernel (x_hat^T resident); above that
                             // on the generic core, transposed the same way; the normalise-backward is fused in both
@@ -410,6 +410,14 @@ static Plan make_plan(int64_t B, int64_t C, int D) {
   pl.fused_dw = (B <= (int64_t)XW_MAX_KB * XW_K);         // x_hat^T resident (else: both operands streamed)
   pl.n_rb = (int)ceil_div(B, 2 * XW_M) * 2 * 4;          // covers either pairing
   pl.off_rpart = off; off += align_up(sizeof(float) * (size_t)pl.n_rb * pl.Cc, 256);
+  // sum-of-squares partials of the dW epilogues (b200f_head_request_dw_sqnorm): per (item, CTA, epilogue warp) on the
+  // X-stationary kernel, per (128-row block, n tile, warp) on the streamed one
+  const XwPlan qw1 = xw_plan(D, pl.Cc, 1), qw2 = xw_plan(D, pl.Cc, 2);
+  size_t n_sq = (size_t)(qw1.items > 2 * qw2.items ? qw1.items : 2 * qw2.items) * XW_MAX_EPI_GROUPS * XW_EPI_WARPS;
+  const size_t n_sq_stream = (size_t)ceil_div(pl.Cc, (int64_t)128) * (size_t)ceil_div((int64_t)D, (int64_t)BLOCK_N) * 4;
+  if (n_sq_stream > n_sq) n_sq = n_sq_stream;
+  pl.n_sq = n_sq;
+  pl.off_sq = off; off += align_up(sizeof(float) * n_sq, 256);
   pl.total = (off > fwd_total ? off : fwd_total) + 1024;
   return pl;
 }
@@ -575,6 +583,28 @@ int head_fwd(const void* xh, const void* wh, const int64_t* label, int64_t B, in
   return B200F_OK;
 }
 
+// ---- ||dW||^2 as a side output of the dW epilogues ---------------------------------------------------------------
+// b200f_head_request_dw_sqnorm(out): the calling thread's NEXT backward (b200f_arcface_bwd / _bwd_dx, or the phase 1 +
+// phase 2 pair) also leaves sum(dW^2) of its class rows in out[0].  The epilogues add up what they store (fixed order:
+// bitwise reproducible), one small kernel folds the per-warp partials.
+static thread_local float* g_dw_sq_out = nullptr;
+void head_request_dw_sqnorm(float* out) { g_dw_sq_out = out; }
+float* head_dw_sqnorm_request() { return g_dw_sq_out; }
+
+__global__ void __launch_bounds__(256) fold_partials_kernel(const float* __restrict__ part, int n, float* out, int accumulate) {
+  pdl_trigger(); pdl_wait();
+  __shared__ float sh[256];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) s += part[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = accumulate ? out[0] + sh[0] : sh[0];
+}
+
 int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t* label, const float* lse,
              const float* grad4, int64_t B, int64_t C, int64_t class_offset, int D, const b200f_head_cfg* cfg,
              float* dxhat, float* dw, const HeadDx* hdx, char* ws, size_t ws_bytes, cudaStream_t st, int phase) {
@@ -590,6 +620,9 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
   ws = ws_align(ws);
   uint16_t* G = reinterpret_cast<uint16_t*>(ws + pl.off_G);
   float* dxpart = reinterpret_cast<float*>(ws + pl.off_dxpart);
+  float* const sq_out = g_dw_sq_out;                        // consumed by the call that runs the last dW GEMM
+  if (phase != 1) g_dw_sq_out = nullptr;
+  float* const sq_part = sq_out ? reinterpret_cast<float*>(ws + pl.off_sq) : nullptr;
   const float S = cfg->operand_scale;
   CUtensorMap tx_k, tx_mn;
   rc = tmap_kmajor(&tx_k, xh, B, D, D, XW_M); if (rc) return rc;
@@ -645,6 +678,7 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
     const CoefSrc coef{r_part, qg.m_groups * 2, pl.Cc, inv_nw, grad4, S};
     auto run_k3b = [&]() -> int {
     int rc = B200F_OK;
+    int n_sq_used = 0;
     { B200F_NVTX("K3b dW = G^T x_hat (+ normalise-backward of W)");
     stage_event(EV_K3B, false, st);
     if (pl.fused_dw) {                                      // x_hat^T resident, G^T rows streamed
@@ -656,8 +690,9 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
       if (g_k3b_groups.load(std::memory_order_relaxed) == 2) {
         XwDwT2::Params ew{};
         rc = make_tmap(&ew.tm_wh, wc, D, cnt, D, 16, 32, CU_TENSOR_MAP_SWIZZLE_NONE); if (rc) return rc;
-        ew.coef = coef; ew.dw = dw; ew.c0 = c0; ew.ld = D;
+        ew.coef = coef; ew.dw = dw; ew.c0 = c0; ew.ld = D; ew.sq_part = sq_part;
         ew.dw_hint = (hints & 4) ? 1 : 0; ew.wh_hint = (hints & 8) ? 1 : 0;
+        n_sq_used = qw.items * qw.pair * 2 * XW_EPI_WARPS;
 #ifdef B200F_PROBES
         ew.ablate = g_k3b_ablate.load(std::memory_order_relaxed);
 #endif
@@ -666,8 +701,9 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
       } else {
         XwDwT::Params ew{};
         rc = make_tmap(&ew.tm_wh, wc, D, cnt, D, 32, 32, CU_TENSOR_MAP_SWIZZLE_NONE); if (rc) return rc;
-        ew.coef = coef; ew.dw = dw; ew.c0 = c0; ew.ld = D;
+        ew.coef = coef; ew.dw = dw; ew.c0 = c0; ew.ld = D; ew.sq_part = sq_part;
         ew.dw_hint = (hints & 4) ? 1 : 0; ew.wh_hint = (hints & 8) ? 1 : 0;
+        n_sq_used = qw.items * qw.pair * 1 * XW_EPI_WARPS;
 #ifdef B200F_PROBES
         ew.ablate = g_k3b_ablate.load(std::memory_order_relaxed);
 #endif
@@ -683,12 +719,18 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
       CUtensorMap tg_km;
       rc = tmap_kmajor(&tg_km, G, cnt, B, pl.ldg, BLOCK_M); if (rc) return rc;
       GemmParams pw = gemm_params((int)cnt, D, (int)B, 1, false, true, FMT_F16, FMT_F16, gpair);
-      EpiDwNorm::Params ew{dw, (int64_t)D, c0, coef, static_cast<const __half*>(wh)};
+      EpiDwNorm::Params ew{dw, (int64_t)D, c0, coef, static_cast<const __half*>(wh), sq_part};
+      n_sq_used = (int)(ceil_div(cnt, (int64_t)128) * pw.n_tiles * 4);
       rc = (gpair == 2) ? launch_gemm<2, false, true, EpiDwNorm>(tg_km, tx_mn, pw, ew, st, "umma K3b dW (streamed, cta pair)")
                         : launch_gemm<1, false, true, EpiDwNorm>(tg_km, tx_mn, pw, ew, st, "umma K3b dW (streamed)");
       if (rc) return rc;
     }
     stage_event(EV_K3B, true, st); }
+    if (sq_part != nullptr) {                               // fold this chunk's partials into the caller's word
+      if ((size_t)n_sq_used > pl.n_sq) return fail(B200F_ERR_WORKSPACE, "umma head_bwd: dW^2 partials exceed the plan");
+      launch_pdl(fold_partials_kernel, dim3(1), dim3(256), 0, st, (const float*)sq_part, n_sq_used, sq_out, chunk_no > 0 ? 1 : 0);
+      B200F_LAUNCH_OK("fold_partials_kernel");
+    }
     return B200F_OK; };
     // --- K3c: dx_hat partials = G[:, k-range] w_hat[c0 + k-range, :]   (A = G read MN-major from G^T)
     auto run_k3c = [&]() -> int {

@@ -672,6 +672,7 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
           Epi::tile_end(stt, ep, p, it);
         }
         if (!ok) break;
+        Epi::item_end_swap(stt, ep, p, it, PAIR);
       }
     } else
     for (int item = cluster_id; item < items && ok; item += n_clusters) {

@@ -364,6 +364,7 @@ struct XwBwdGTT {
 
   // rows of the resident group = width of the column space = 128 * PAIR; carried in XwParams.tn
   static __device__ __forceinline__ int p_tn(const XwParams& p) { return p.tn; }
+  static __device__ __forceinline__ void item_end_swap(State&, const Params&, const XwParams&, const XwItem&, int) {}
 };
 using XwBwdGT = XwBwdGTT<1, 32>;
 using XwBwdGT2 = XwBwdGTT<2, 16>;
@@ -389,11 +390,13 @@ struct XwDwTT {
   struct Params {
     alignas(64) CUtensorMap tm_wh;      // w_hat16 rows of this launch [classes, D], box SC features x 32 classes, no swizzle
     CoefSrc coef; float* dw; int64_t c0; int ld;
+    float* sq_part;                     // NULL, or [items * PAIR * EG * 8]: sum of dW^2 per (item, CTA, epilogue warp) -- the
+                                        // ||dW||^2 clip_grad_norm_ needs (src/training.py:528-533) without a pass over dW
     int dw_hint, wh_hint;               // L2 policies: dW stores (nobody reads them in this step: 1 evict_first), w_hat boxes
     B200F_PROBE_FIELD                   // probe builds only: 1 = no w_hat loads, 2 = no dW stores (WRONG results)
   };
   struct State { float2 cf; float rp_next[4]; float inw_next; int64_t next_row; float inv_sg; int seq, n_seq, row0, row_step; bool row_ok;
-                 uint64_t dw_pol, wh_pol; };
+                 uint64_t dw_pol, wh_pol; float sq; };
 
   // slice n of this warp's item = column slice (n % spt) of its (n / spt)-th OWN tile (with EG groups a group owns every
   // EG-th tile of the walk, starting at it.first_tile); buffer n & 1
@@ -418,7 +421,7 @@ struct XwDwTT {
     st.n_seq = (own > 0 ? own : 0) * ((p.tn >> 1) / SC);
     st.row0 = (p.reverse ? t_end - 1 : t_begin) * p.tn + it.rank * XW_WROWS + it.quad * 32;
     st.row_step = p.reverse ? -p.tn : p.tn;
-    st.seq = 0; st.next_row = -1; st.row_ok = false;
+    st.seq = 0; st.next_row = -1; st.row_ok = false; st.sq = 0.f;
     st.inv_sg = ep.coef.inv_sg();
     st.dw_pol = l2_policy(ep.dw_hint); st.wh_pol = l2_policy(ep.wh_hint);
     issue(st, ep, p, it, 0);
@@ -477,6 +480,15 @@ struct XwDwTT {
           o[i * 8 + j * 2 + 1] = cx * fmaf(-f.y, cy, v[i * 8 + j * 2 + 1]);
         }
       }
+      if (ep.sq_part != nullptr) {                            // fixed order: slices in walk order, four chains per slice
+        float q4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < SC; j += 4) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) q4[u] = (d0 + j + u < p.B) ? fmaf(o[j + u], o[j + u], q4[u]) : q4[u];
+        }
+        st.sq += (q4[0] + q4[1]) + (q4[2] + q4[3]);
+      }
       if (B200F_PROBE_ON(ep, 2) && o[0] != 12345.678f) {
       } else if (d0 + SC <= p.B && (ep.ld & 7) == 0) {
 #pragma unroll
@@ -509,6 +521,11 @@ struct XwDwTT {
     issue(st, ep, p, it, n + 2);
   }
   static __device__ __forceinline__ void tile_end(State&, const Params&, const XwParams&, const XwItem&) {}
+  static __device__ __forceinline__ void item_end_swap(State& st, const Params& ep, const XwParams&, const XwItem& it, int pair) {
+    if (ep.sq_part == nullptr) return;
+    const float s = warp_sum(st.sq);
+    if (it.lane == 0) ep.sq_part[(((int64_t)it.item * pair + it.rank) * EG + it.grp) * XW_EPI_WARPS + it.ew] = s;
+  }
 };
 using XwDwT = XwDwTT<1, 32>;
 using XwDwT2 = XwDwTT<2, 16>;

@@ -68,6 +68,10 @@ class HeadStats:
     hook_out: Optional[torch.Tensor] = None      # [3] grad_scale, ||dL/dt||_F, kappa (after backward)
     lse: Optional[torch.Tensor] = None           # [B]
     dx_f32: Optional[torch.Tensor] = None        # [B,D] fp32 dL/dx before the cast to x.dtype (after backward)
+    # ||dW||^2 of this shard's rows as a side output of the dW epilogues (b200f_head_request_dw_sqnorm): set
+    # want_dw_sqnorm before the backward; dw_sqnorm is a [1] fp32 device tensor after it (class shards: SUM it over ranks)
+    want_dw_sqnorm: bool = False
+    dw_sqnorm: Optional[torch.Tensor] = None
 
 
 @dataclass
@@ -398,6 +402,9 @@ class _ArcFaceLossFn(torch.autograd.Function):
                                                float(hook.max_grad_norm), int(hook.phase), int(hook.epoch),
                                                ptr(grad4), stream_ptr(x.device)), "b200f_arcface_hook_scale")
         ctx.stats.hook_out = grad4
+        if ctx.stats.want_dw_sqnorm:                             # the calling thread's next backward leaves sum(dW^2) here
+            ctx.stats.dw_sqnorm = torch.empty(1, dtype=torch.float32, device=x.device)
+            check(lib.b200f_head_request_dw_sqnorm(ptr(ctx.stats.dw_sqnorm)), "b200f_head_request_dw_sqnorm")
         want_bf16 = ctx.x_dtype == torch.bfloat16
         if ctx.group is None:
             _, dw, dx, lowp = _bwd_kernels(x, w, label, inv_nx, inv_nw, lse, grad4, cfg, ctx.class_offset, finish_dx=True,
@@ -703,7 +710,7 @@ class ArcMarginProduct(nn.Module):
             c_tot = self._num_classes_total or self.out_feats
             if label.numel() and (int(label.min()) < 0 or int(label.max()) >= c_tot):
                 raise IndexError(f"label out of range [0, {c_tot})")      # the reference's scatter_ raises here (:381)
-        self.last_stats = HeadStats()
+        self.last_stats = HeadStats(want_dw_sqnorm=bool(getattr(self, "track_dw_norm", False)))
         use_cache = self.cache_weight_prep and (not self.training or self._w_prep.get("optimizer_current", False))
         loss = arcface_loss(x, weight, label, m_eff=m_eff, s_eff=s_eff, label_smoothing=label_smoothing,
                             easy_margin=self.easy_margin, hook=self._hook, stats=self.last_stats,

@@ -96,6 +96,22 @@ class HeadAdamW:
         torch.autograd.graph.increment_version(self.weight)     # the kernel wrote the parameter behind autograd's back
         self._publish()
 
+    @staticmethod
+    def clip_coef(max_norm: float, head_dw_sqnorm: torch.Tensor, other_sqnorm: Optional[torch.Tensor] = None,
+                  group=None) -> torch.Tensor:
+        """The coefficient ``torch.nn.utils.clip_grad_norm_(params, max_norm)`` multiplies every gradient with
+        (src/training.py:528-533: max_norm / (total_norm + 1e-6), clamped to 1), from the head's ||dW||^2 -- a side output
+        of the dW epilogues (``head.track_dw_norm = True`` -> ``head.last_stats.dw_sqnorm``; no pass over dW) -- plus the
+        squared norm of everything else the caller clips together with it.  group: class shards SUM their parts first.
+        Returns a [1] fp32 device tensor: pass it to ``step(grad_scale=...)`` and scale the other gradients with it."""
+        total = head_dw_sqnorm.detach().to(torch.float32).reshape(1).clone()
+        if group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+        if other_sqnorm is not None:
+            total = total + other_sqnorm.detach().to(torch.float32).reshape(1)
+        return torch.clamp(float(max_norm) / (torch.sqrt(total) + 1e-6), max=1.0)
+
     def zero_grad(self, set_to_none: bool = True):
         if self.weight.grad is not None:
             if set_to_none:

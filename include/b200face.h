@@ -202,6 +202,14 @@ int b200f_arcface_bwd(const void* x, const void* w, int dtype,
                       float* dxhat, float* dw,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* ||dW||^2 without a pass over dW (clip_grad_norm_, src/training.py:528-533, needs the gradient norm before the optimizer
+ * step; reading the 205 MB of dW again for it costs ~35 us at cfg3).  After this call the calling THREAD's next backward
+ * (b200f_arcface_bwd, b200f_arcface_bwd_dx, or the b200f_arcface_bwd_phase 1 + 2 pair) also writes sum(dW[c,d]^2) over its
+ * class rows to out[0] (device memory, fp32): the dW epilogues add up what they store, in a fixed order (bitwise
+ * reproducible), and one small kernel folds the per-warp partials.  One-shot: the request is consumed by that backward;
+ * NULL cancels it.  Class shards: all-reduce (SUM) the word with the other ranks' before taking the square root. */
+int b200f_head_request_dw_sqnorm(float* out_or_null);
+
 /* b200f_arcface_bwd in two calls, for class shards that overlap the cross-rank all-reduce of dx_hat with the dW GEMM.
  * phase 1: per class chunk K3a -> K3c -> split reduction -> K3b, WITHOUT the last chunk's K3b: dxhat is complete when it
  * returns (in stream order) and the caller starts its all-reduce on ANOTHER stream; phase 2 (same arguments, same

@@ -570,3 +570,39 @@ def test_backward_in_two_phases_equals_one_call(cuda_device, B, C, mb):
     assert torch.equal(dx_after_phase1, dxhat0) and torch.equal(dxhat1, dxhat0)
     assert torch.equal(dw1, dw0)
     assert torch.isfinite(dw0).all() and torch.isfinite(dxhat0).all()
+
+
+@pytest.mark.parametrize("B,C,mb,dt", [(384, 9000, 112, torch.bfloat16), (384, 9000, 4, torch.bfloat16), (640, 24000, 1, torch.bfloat16),
+                                       (1024, 20000, 112, torch.bfloat16), (96, 700, 112, torch.float32)])
+def test_dw_sqnorm_side_output(cuda_device, B, C, mb, dt):
+    """b200f_head_request_dw_sqnorm: sum(dW^2) out of the dW epilogues (X-stationary and streamed K3b, one and several class
+    chunks; the fp32 engine sums its small dW in one pass) == the norm torch takes of the stored gradient, and
+    HeadAdamW.clip_coef is clip_grad_norm_'s coefficient (src/training.py:528-533).  One-shot: the next backward is clean."""
+    import b200face
+    from b200face import _lib
+    lib = _lib.load_library()
+    D = 512
+    g = torch.Generator().manual_seed(B + C)
+    x = torch.randn(B, D, generator=g).to(dt).to(cuda_device)
+    y = torch.randint(0, C, (B,), generator=g).to(cuda_device)
+    head = b200face.ArcMarginProduct(D, C).to(cuda_device)
+    head.train(); head.update_epoch(12)
+    head.track_dw_norm = True
+    old = lib.b200f_set_tunable(b"g_chunk_mb", mb)
+    try:
+        loss = head.forward_loss(x.clone().requires_grad_(True), y, 0.05)
+        loss.backward()
+        sq = head.last_stats.dw_sqnorm
+        torch.cuda.synchronize()
+        want = head.weight.grad.double().pow(2).sum()
+        assert float(sq) == pytest.approx(float(want), rel=2e-5)
+        coef = b200face.HeadAdamW.clip_coef(0.05, sq)
+        ref_coef = min(1.0, 0.05 / (float(want) ** 0.5 + 1e-6))
+        assert float(coef) == pytest.approx(ref_coef, rel=2e-5)
+        head.track_dw_norm = False
+        head.zero_grad(set_to_none=True)
+        head.forward_loss(x.clone().requires_grad_(True), y, 0.05).backward()
+        assert head.last_stats.dw_sqnorm is None
+        torch.cuda.synchronize()
+    finally:
+        lib.b200f_set_tunable(b"g_chunk_mb", old)
