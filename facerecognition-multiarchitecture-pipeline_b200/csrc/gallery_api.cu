@@ -36,7 +36,10 @@ static int launch_gallery(const gallery::Params& p, const GalleryPlan& pl, cudaS
   const size_t dyn = gallery::dyn_smem_bytes();
   B200F_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
   dim3 grid(pl.n_chunks, pl.q_tiles);
-  kern<<<grid, simt::THREADS, dyn, st>>>(p);
+  // the gated fallback behind the tensor scan (only_rows) sits in a chain of programmatically serialised launches: its
+  // launch latency then overlaps the select kernel instead of following it
+  if (p.only_rows != nullptr) launch_pdl(kern, grid, dim3(simt::THREADS), dyn, st, p);
+  else kern<<<grid, simt::THREADS, dyn, st>>>(p);
   B200F_LAUNCH_OK("gallery::topk_kernel");
   return B200F_OK;
 }
@@ -55,10 +58,14 @@ static int launch_merge(const int64_t* idx_all, const float* score_all, int P, i
                         float thresh, int64_t* idx, float* score, uint8_t* accept, cudaStream_t st,
                         const uint8_t* only_rows = nullptr) {
   const unsigned grid = (unsigned)ceil_div(Q, 128);
-  if (k <= 1) gallery::merge_kernel<1><<<grid, 128, 0, st>>>(idx_all, score_all, P, Q, k, metric, thresh, idx, score, accept, only_rows);
-  else if (k <= 4) gallery::merge_kernel<4><<<grid, 128, 0, st>>>(idx_all, score_all, P, Q, k, metric, thresh, idx, score, accept, only_rows);
-  else if (k <= 8) gallery::merge_kernel<8><<<grid, 128, 0, st>>>(idx_all, score_all, P, Q, k, metric, thresh, idx, score, accept, only_rows);
-  else gallery::merge_kernel<16><<<grid, 128, 0, st>>>(idx_all, score_all, P, Q, k, metric, thresh, idx, score, accept, only_rows);
+  auto launch = [&](auto kern) {
+    if (only_rows != nullptr) launch_pdl(kern, dim3(grid), dim3(128), 0, st, idx_all, score_all, P, Q, k, metric, thresh, idx, score, accept, only_rows);
+    else kern<<<grid, 128, 0, st>>>(idx_all, score_all, P, Q, k, metric, thresh, idx, score, accept, only_rows);
+  };
+  if (k <= 1) launch(gallery::merge_kernel<1>);
+  else if (k <= 4) launch(gallery::merge_kernel<4>);
+  else if (k <= 8) launch(gallery::merge_kernel<8>);
+  else launch(gallery::merge_kernel<16>);
   B200F_LAUNCH_OK("gallery::merge_kernel");
   return B200F_OK;
 }

@@ -70,6 +70,7 @@ inline size_t dyn_smem_bytes() { return sizeof(float) * BN * SCORE_LD; }
 template <typename T, class Op, int K>
 __global__ void __launch_bounds__(THREADS)
 topk_kernel(const Params p) {
+  pdl_trigger(); pdl_wait();                                  // no-ops unless launched with programmatic serialization (the gated fallback)
   __shared__ simt::Smem sm;
   extern __shared__ float score_tile[];                       // [BN cols][SCORE_LD rows]
   const int chunk = blockIdx.x;
@@ -151,6 +152,7 @@ __global__ void merge_kernel(const int64_t* __restrict__ idx_all, const float* _
                              int P, int64_t Q, int k, int metric, float thresh,
                              int64_t* __restrict__ idx, float* __restrict__ score,
                              uint8_t* __restrict__ accept, const uint8_t* __restrict__ only_rows) {
+  pdl_trigger(); pdl_wait();
   const int64_t qid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (qid >= Q) return;
   if (only_rows != nullptr && only_rows[qid] == 0) return;

@@ -793,9 +793,11 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
 // tile of the first 16 k (32 k) rows.  Several row groups: 4 chunks of 8 tiles, so that a work item amortises its
 // x load over 8 tiles (one-tile items made the pre-pass cost a quarter of the scan at Q = 8192).
 constexpr int GALLERY_SAMPLE_MAX_LISTS = 32 * GALLERY_TAU_LISTS_PER_LANE;
-static std::atomic<int> g_gallery_compact{0};      // tunable "gallery_compact": 0 = the padded-list pre-pass / select of round 1 (default:
-                                                   // the compact variant measured 297 vs 295 us at Q = 128 x 1 M and its re-score sums in another order,
-                                                   // so sharded and unsharded scores differ in the last bit), 1 = compact candidate arrays + warp select
+// tunable "gallery_compact": 1 (default) = min-only sample pre-pass, compact candidate arrays, block select that re-scores all
+// winners in one round; 0 = the padded-list pre-pass / select of round 1.  Per 128-query call against 1 M x 512 (ncu launch
+// lists, gpurun_out/r02u / r02v): pre-pass 24.2 + 7.8 -> 13.4 + 6.0 us, main scan 162.6 -> 158.0 us, select 40.5 -> see
+// profiles/.  Both selects add the exact re-score in the same order: same score bits.
+static std::atomic<int> g_gallery_compact{1};
 struct GalleryScanPlan {
   XwPlan q, qs;                 // main scan / sample pre-pass
   int KT, n_lists;
@@ -892,10 +894,11 @@ static int gallery_scan_kt(const GalleryScanPlan& gp, const void* g16, const CUt
                             : launch_xw<1, XW_KK, XwTopK<KT>>(tx, tw, gp.q, Q, N, D, ep, st, "umma K4 gallery scan", mfmt, false, g16, (int64_t)D * 2);
   if (rc) return rc;
   if (gp.compact) {
-    launch_pdl(gallery_select_warp_kernel<KT>, dim3((unsigned)ceil_div(Q, 4)), dim3(128), 0, st, (const float*)ckey, (const int32_t*)cidx,
-               (const int32_t*)cnt, gp.n_lists * KT, q, g, q_inv, g_inv, (const float*)(bias ? bias + N : nullptr), qbad, Q, D, k, metric, fmt, thresh,
+    const int cap = gp.n_lists * KT;
+    launch_pdl(gallery_select_block_kernel<KT>, dim3((unsigned)Q), dim3(128), 0, st, (const float*)ckey, (const int32_t*)cidx,
+               (const int32_t*)cnt, cap, q, g, q_inv, g_inv, (const float*)(bias ? bias + N : nullptr), qbad, Q, D, k, metric, fmt, thresh,
                index_offset, idx, score, accept, redo, redo_count);
-    B200F_LAUNCH_OK("gallery_select_warp_kernel");
+    B200F_LAUNCH_OK("gallery_select_block_kernel");
     return B200F_OK;
   }
   const int n_cand = gp.n_lists * KT;

@@ -40,7 +40,7 @@ struct XwTopK {
                                 // gallery (gallery_tau_kernel), or NULL
     // compact output (cnt != NULL; needs tau0): a list appends only its non-empty entries to its query's candidate
     // array -- with the sample bound in place a query ends up with a few dozen candidates instead of n_lists * KT
-    // mostly empty slots, and gallery_select_warp_kernel ranks them with one WARP per query.  cnt[q] counts what was
+    // mostly empty slots, and gallery_select_block_kernel ranks them and re-scores the winners in one round.  cnt[q] counts what was
     // offered (the tau kernel zeroes it); entries beyond `cap` are dropped and the query goes to the exact engine.
     int32_t* cnt; int cap;
   };
@@ -231,195 +231,192 @@ gallery_tau_min_kernel(const float* __restrict__ key_min, int n_lists, int64_t Q
   if (lane == 0) { tau0[qi] = last; if (cnt != nullptr) cnt[qi] = 0; }
 }
 
-// ---- select, compact form: ONE WARP per query ranks the query's (few) candidates, re-scores the KT best exactly and
-// proves the top-k (same arithmetic and proof as gallery_select_kernel below; that kernel took 41-48 us for 128
-// queries: one block per query walking n_lists * KT mostly empty slots through shared memory with a dozen barriers).
-constexpr int GALLERY_SURVIVORS_PER_LANE = 16;
+// ---- select, compact form ------------------------------------------------------------------------------------------
+// Input: the query's compact candidate array (cnt[q] entries of (key, gallery row): with the sample bound at the 1e-3
+// quantile, ~1000 of a 1 M-row gallery).  One block of 128 threads per query, every step parallel over the block:
+//   candidates -> registers (16 per thread); the KT-th smallest of the 128 per-thread minima bounds the KT-th best key
+//   (rank by counting, no arg-min rounds) -> the few survivors under it -> shared memory -> rank by counting: the KT best
+//   approximate keys by (key, row) -> ALL KT winners re-scored exactly in ONE round (thread t owns elements t, t + 128, ..:
+//   4 x KT independent loads in flight per thread; the padded-list kernel below takes four rounds of four rows with a
+//   barrier pair each) -> ordered by (exact key, row) by counting -> thread 0 proves the top-k and writes the outputs.
+// The re-score adds in the SAME order as gallery_select_kernel (per-thread chain over d = t, t + 128, ..; warp butterfly;
+// (w0 + w1) + (w2 + w3)), so a gallery gives the same score bits whichever of the two kernels its size selects (sharded
+// and unsharded results are compared bit for bit).  History: one WARP per query 57 us for 128 queries (32 blocks, every
+// phase latency-bound); this block form with arg-min rounds over all ~1000 candidates 54 us; padded lists 41 us.
+constexpr int GALLERY_SEL_PER_THREAD = 16;                     // candidates a thread holds: 2048 per query, else the exact engine
+constexpr int GALLERY_SEL_MAX_SURV = 1024;
 template <int KT>
 __global__ void __launch_bounds__(128)
-gallery_select_warp_kernel(const float* __restrict__ cand_key, const int32_t* __restrict__ cand_idx,
-                           const int32_t* __restrict__ cnt, int cap, const float* __restrict__ q, const float* __restrict__ g,
-                           const float* __restrict__ q_inv, const float* __restrict__ g_inv,
-                           const float* __restrict__ gmax_ptr, const uint8_t* __restrict__ q_bad, int64_t Q, int D, int k,
-                           int metric, int fmt, float thresh, int64_t index_offset, int64_t* __restrict__ idx_out,
-                           float* __restrict__ score_out, uint8_t* __restrict__ accept, uint8_t* __restrict__ redo,
-                           int32_t* __restrict__ redo_count) {
+gallery_select_block_kernel(const float* __restrict__ cand_key, const int32_t* __restrict__ cand_idx,
+                            const int32_t* __restrict__ cnt, int cap, const float* __restrict__ q, const float* __restrict__ g,
+                            const float* __restrict__ q_inv, const float* __restrict__ g_inv,
+                            const float* __restrict__ gmax_ptr, const uint8_t* __restrict__ q_bad, int64_t Q, int D, int k,
+                            int metric, int fmt, float thresh, int64_t index_offset, int64_t* __restrict__ idx_out,
+                            float* __restrict__ score_out, uint8_t* __restrict__ accept, uint8_t* __restrict__ redo,
+                            int32_t* __restrict__ redo_count) {
   pdl_trigger(); pdl_wait();
-  static_assert(KT <= 32, "one winner per lane");
-  constexpr int PER = GALLERY_SURVIVORS_PER_LANE;
-  const int lane = threadIdx.x & 31;
-  const int64_t qi = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (qi >= Q) return;
+  constexpr int PER = GALLERY_SEL_PER_THREAD;
+  __shared__ float skey[GALLERY_SEL_MAX_SURV]; __shared__ int sidx[GALLERY_SEL_MAX_SURV];
+  __shared__ float mins[128];
+  __shared__ float red_k[4]; __shared__ float red_s[4];
+  __shared__ float win_key[KT]; __shared__ int win_idx[KT]; __shared__ float ex_key[KT];
+  __shared__ float srt_key[KT]; __shared__ int srt_idx[KT]; __shared__ float srt_win[KT];
+  __shared__ float qstat[2]; __shared__ float bound_s; __shared__ int n_surv;
+  __shared__ float red_acc[4][KT];
+  const int64_t qi = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const bool cosine = (metric == B200F_METRIC_COS);
   const int n_all = __ldcg(cnt + qi);
-  const int n = n_all < cap ? n_all : cap;                    // (the scan cannot offer more than cap = n_lists * KT)
-  const float* qk = cand_key + qi * cap;
-  const int32_t* qidx = cand_idx + qi * cap;
-  // pass 1: the KT-th smallest of the 32 per-lane minima bounds the KT-th best candidate (32 >= KT distinct elements)
-  float lm = INFINITY;
-  for (int i = lane; i < n; i += 32) lm = fminf(lm, __ldcg(qk + i));
-  float bound = INFINITY;
-  {
-    float v = lm;
-    for (int r = 0; r < KT; ++r) {
-      float kmin = v; int who = lane;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ok = __shfl_xor_sync(0xffffffffu, kmin, o);
-        const int ow = __shfl_xor_sync(0xffffffffu, who, o);
-        if (ok < kmin || (ok == kmin && ow < who)) { kmin = ok; who = ow; }
-      }
-      bound = kmin;                                           // +inf once fewer than KT lanes hold anything: keep all
-      if (who == lane) v = INFINITY;
-    }
-  }
-  // pass 2: the survivors (key <= bound) into registers
+  int ns = n_all < cap ? n_all : cap;
+  bool overflow = n_all > cap || ns > 128 * PER;             // more than fits: the exact engine takes the query
+  if (ns > 128 * PER) ns = 128 * PER;
+  // ---- candidates -> registers, per-thread minimum
   float ck[PER]; int ci[PER];
+  float lmin = INFINITY;
 #pragma unroll
-  for (int u = 0; u < PER; ++u) { ck[u] = INFINITY; ci[u] = INT32_MAX; }
-  int mine = 0;
-  for (int i = lane; i < n; i += 32) {
-    const float kk = __ldcg(qk + i);
-    if (kk <= bound) {
-      const int id = __ldcg(qidx + i);
-#pragma unroll
-      for (int u = 0; u < PER; ++u) if (u == mine) { ck[u] = kk; ci[u] = id; }
-      ++mine;
-    }
+  for (int u = 0; u < PER; ++u) {
+    const int i = tid + 128 * u;
+    ck[u] = (i < ns) ? __ldcg(cand_key + qi * cap + i) : INFINITY;
+    ci[u] = (i < ns) ? __ldcg(cand_idx + qi * cap + i) : -1;
+    if (ci[u] >= 0) lmin = fminf(lmin, ck[u]);
   }
-  const bool overflow = __any_sync(0xffffffffu, mine > PER);  // a lane ran out of slots: the exact engine takes the query
-  // the query row: D <= 512, lane owns elements 4 * (lane + 32 j) .. + 3
-  const int nvec = D >> 2;
-  float4 qv[4];
-  float nq = 0.f, sq = 0.f;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int c = lane + 32 * j;
-    qv[j] = (c < nvec) ? __ldg(reinterpret_cast<const float4*>(q + qi * D) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-    nq = fmaf(qv[j].x, qv[j].x, nq); nq = fmaf(qv[j].y, qv[j].y, nq); nq = fmaf(qv[j].z, qv[j].z, nq); nq = fmaf(qv[j].w, qv[j].w, nq);
-    sq += (qv[j].x + qv[j].y) + (qv[j].z + qv[j].w);
-  }
-  nq = warp_sum(nq); sq = warp_sum(sq);
-  // ---- the KT best approximate keys by (key, index); lane r keeps the r-th
-  float wk = INFINITY; int wi = -1;
-  {
-    float taken_k = -INFINITY; int taken_i = -1;
-    for (int r = 0; r < KT; ++r) {
-      float bk = INFINITY; int bi = INT32_MAX;
-#pragma unroll
-      for (int u = 0; u < PER; ++u) {
-        const bool after = (ck[u] > taken_k) || (ck[u] == taken_k && ci[u] > taken_i);
-        if (ci[u] != INT32_MAX && after && (ck[u] < bk || (ck[u] == bk && ci[u] < bi))) { bk = ck[u]; bi = ci[u]; }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ok = __shfl_xor_sync(0xffffffffu, bk, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ok < bk || (ok == bk && oi < bi)) { bk = ok; bi = oi; }
-      }
-      if (bi == INT32_MAX) break;                             // uniform: candidates exhausted
-      if (lane == r) { wk = bk; wi = bi; }
-      taken_k = bk; taken_i = bi;
-    }
-  }
-  // ---- exact re-score (reference formula, fp32), four winners' rows in flight at a time
-  float ex = INFINITY;
-  for (int r0 = 0; r0 < KT; r0 += 4) {
-    int id[4]; float4 y[4][4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      id[u] = __shfl_sync(0xffffffffu, wi, (r0 + u) & 31);
-      if (r0 + u >= KT) id[u] = -1;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c = lane + 32 * j;
-        y[u][j] = (id[u] >= 0 && c < nvec) ? __ldg(reinterpret_cast<const float4*>(g + (int64_t)id[u] * D) + c)
-                                            : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      float acc = 0.f;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c = lane + 32 * j;
-        if (c < nvec) {
-          if (cosine) {
-            acc = fmaf(qv[j].x, y[u][j].x, acc); acc = fmaf(qv[j].y, y[u][j].y, acc);
-            acc = fmaf(qv[j].z, y[u][j].z, acc); acc = fmaf(qv[j].w, y[u][j].w, acc);
-          } else {
-            float d0 = qv[j].x - y[u][j].x + GALLERY_EPS, d1 = qv[j].y - y[u][j].y + GALLERY_EPS;
-            float d2 = qv[j].z - y[u][j].z + GALLERY_EPS, d3 = qv[j].w - y[u][j].w + GALLERY_EPS;
-            acc = fmaf(d0, d0, acc); acc = fmaf(d1, d1, acc); acc = fmaf(d2, d2, acc); acc = fmaf(d3, d3, acc);
-          }
-        }
-      }
-      const float tot = warp_sum(acc);
-      float e;
-      if (id[u] < 0) e = INFINITY;
-      else if (cosine) e = -(tot * (q_inv ? q_inv[qi] : 1.0f) * (g_inv ? g_inv[id[u]] : 1.0f));
-      else e = sqrtf(tot);
-      if (lane == r0 + u) ex = e;
-    }
-  }
-  // ---- order the KT winners by (exact key, index): NaN keys behind the ranked ones, empty slots last
-  int rank = 0;
-  for (int s = 0; s < KT; ++s) {
-    const float ks = __shfl_sync(0xffffffffu, ex, s);
-    const int is = __shfl_sync(0xffffffffu, wi, s);
-    // does winner s come before mine?
-    bool first;
-    if (is < 0) first = (wi < 0) && (s < lane);
-    else if (wi < 0) first = true;
-    else if (ks != ks) first = (ex != ex) && (is < wi);
-    else first = (ex != ex) || ks < ex || (ks == ex && is < wi);
-    if (s != lane && first) ++rank;
-  }
-  float s_ex = INFINITY, s_wk = INFINITY; int s_wi = -1;      // lane p receives the winner ranked p
-  for (int s = 0; s < KT; ++s) {
-    const int rs = __shfl_sync(0xffffffffu, rank, s);
-    const float es = __shfl_sync(0xffffffffu, ex, s), ws = __shfl_sync(0xffffffffu, wk, s);
-    const int is = __shfl_sync(0xffffffffu, wi, s);
-    if (rs == lane) { s_ex = es; s_wk = ws; s_wi = is; }
-  }
-  // ---- proof: every row the scan dropped has an approximate key >= the worst kept one
-  const bool valid = (lane < KT) && s_wi >= 0;
-  float a_excl = warp_max(valid ? s_wk : -INFINITY);
-  const int n_valid = __popc(__ballot_sync(0xffffffffu, valid));
-  const int kk = min(k, n_valid);
-  const float ek = __shfl_sync(0xffffffffu, s_ex, (kk > 0 ? kk - 1 : 0) & 31);
+  mins[tid] = lmin;
+  if (tid == 0) { n_surv = 0; bound_s = INFINITY; }
+  if (tid < KT) { win_key[tid] = INFINITY; win_idx[tid] = -1; }
   const bool any_marked = (q_bad != nullptr && q_bad[qi] != 0) ||
                           (gmax_ptr != nullptr && reinterpret_cast<const int*>(gmax_ptr)[1] != 0);
-  bool verified = !any_marked && !overflow;
-  if (verified && n_valid == KT) {                             // something may have been excluded
-    const float qn = sqrtf(nq);
-    const float gmax = gmax_ptr ? __int_as_float(*reinterpret_cast<const int*>(gmax_ptr)) : 1.0f;
-    float exact_in_approx_units, delta;
-    const float rel = (fmt == B200F_OPERAND_FP16) ? GALLERY_DOT_ERR_FP16 : GALLERY_DOT_ERR;
-    const float abs_e = (fmt == B200F_OPERAND_FP16) ? GALLERY_ABS_ERR_FP16 * sqrtf((float)D) : 0.f;
-    if (cosine) {
-      const float qvn = q_inv ? q_inv[qi] : 1.0f;
-      exact_in_approx_units = (qvn > 0.f) ? ek / qvn : -INFINITY;
-      delta = rel * qn * 1.01f + abs_e * (qn + 1.0f);
-    } else {
-      exact_in_approx_units = ek * ek - (nq + 2.0f * GALLERY_EPS * sq + (float)D * GALLERY_EPS * GALLERY_EPS);
-      delta = 2.0f * (rel * qn * gmax + abs_e * (qn + gmax)) + 1e-6f * (nq + gmax * gmax + 1.0f);
+  // the query row: thread t owns elements t, t + 128, t + 256, t + 384 (D <= 512)
+  float xq[4];
+  float nq = 0.f, sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int d = tid + 128 * i;
+    xq[i] = (d < D) ? q[qi * D + d] : 0.f;
+    if (d < D) { nq = fmaf(xq[i], xq[i], nq); sq += xq[i]; }
+  }
+  nq = warp_sum(nq); sq = warp_sum(sq);
+  if (lane == 0) { red_k[wid] = nq; red_s[wid] = sq; }
+  __syncthreads();
+  if (tid == 0) { qstat[0] = red_k[0] + red_k[1] + red_k[2] + red_k[3]; qstat[1] = red_s[0] + red_s[1] + red_s[2] + red_s[3]; }
+  // ---- bound: the KT-th smallest of the 128 per-thread minima (128 distinct candidates are <= their minima's maximum;
+  // +inf when fewer than KT threads hold anything: keep all)
+  {
+    int before = 0;
+    for (int j = 0; j < 128; ++j) { const float mj = mins[j]; before += (mj < lmin || (mj == lmin && j < tid)) ? 1 : 0; }
+    if (before == KT - 1) bound_s = lmin;
+  }
+  __syncthreads();
+  const float bound = bound_s;
+#pragma unroll
+  for (int u = 0; u < PER; ++u) {
+    if (ci[u] >= 0 && ck[u] <= bound) {
+      const int pos = atomicAdd(&n_surv, 1);
+      if (pos < GALLERY_SEL_MAX_SURV) { skey[pos] = ck[u]; sidx[pos] = ci[u]; }
     }
-    verified = (ek == ek) && (exact_in_approx_units < a_excl - delta);
   }
-  if (lane < k) {
-    const bool ok = (lane < KT) && s_wi >= 0 && s_ex == s_ex;
-    idx_out[qi * k + lane] = ok ? (index_offset + s_wi) : -1;
-    score_out[qi * k + lane] = ok ? (cosine ? -s_ex : s_ex) : (cosine ? -INFINITY : INFINITY);
+  __syncthreads();
+  int nsv = n_surv;
+  if (nsv > GALLERY_SEL_MAX_SURV) { nsv = GALLERY_SEL_MAX_SURV; overflow = true; }   // a crowd of equal keys
+  // ---- the KT best approximate keys by (key, row): rank by counting (rows are distinct: a total order)
+  for (int t = tid; t < nsv; t += 128) {
+    const float kt = skey[t]; const int it = sidx[t];
+    int rank = 0;
+    for (int j = 0; j < nsv; ++j) { const float kj = skey[j]; rank += (kj < kt || (kj == kt && sidx[j] < it)) ? 1 : 0; }
+    if (rank < KT) { win_key[rank] = kt; win_idx[rank] = it; }
   }
-  if (lane == 0) {
+  __syncthreads();
+  // ---- exact re-score of all KT winners at once (reference formula, fp32)
+  {
+    int id[KT];
+    float y[4][KT];
+#pragma unroll
+    for (int u = 0; u < KT; ++u) id[u] = win_idx[u];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int d = tid + 128 * i;
+#pragma unroll
+      for (int u = 0; u < KT; ++u) y[i][u] = (d < D && id[u] >= 0) ? __ldg(g + (int64_t)id[u] * D + d) : 0.f;
+    }
+    float acc[KT];
+#pragma unroll
+    for (int u = 0; u < KT; ++u) acc[u] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (tid + 128 * i < D) {
+#pragma unroll
+        for (int u = 0; u < KT; ++u) {
+          if (cosine) acc[u] = fmaf(xq[i], y[i][u], acc[u]);
+          else { const float df = xq[i] - y[i][u] + GALLERY_EPS; acc[u] = fmaf(df, df, acc[u]); }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < KT; ++u) {
+      const float a = warp_sum(acc[u]);
+      if (lane == 0) red_acc[wid][u] = a;
+    }
+  }
+  __syncthreads();
+  if (tid < KT) {
+    const int idt = win_idx[tid];
+    const float tot = (red_acc[0][tid] + red_acc[1][tid]) + (red_acc[2][tid] + red_acc[3][tid]);
+    float e;                                                   // ordering key, smaller is better (as the exact engine)
+    if (idt < 0) e = INFINITY;
+    else if (cosine) e = -(tot * (q_inv ? q_inv[qi] : 1.0f) * (g_inv ? g_inv[idt] : 1.0f));
+    else e = sqrtf(tot);
+    ex_key[tid] = e;
+  }
+  __syncthreads();
+  // ---- order the KT winners by (exact key, row), NaN keys and empty slots last: the stable insertion sort of the
+  // padded-list kernel, as a rank by counting (a precedes b iff first(a, b), or neither precedes and a came earlier)
+  if (tid < KT) {
+    const float ka = ex_key[tid]; const int ia = win_idx[tid];
+    int pos = 0;
+    for (int j = 0; j < KT; ++j) {
+      if (j == tid) continue;
+      const float kb = ex_key[j]; const int ib = win_idx[j];
+      const bool j_first = (ib >= 0) && (ia < 0 || (kb == kb && (ka != ka || kb < ka || (kb == ka && ib < ia))));
+      const bool me_first = (ia >= 0) && (ib < 0 || (ka == ka && (kb != kb || ka < kb || (ka == kb && ia < ib))));
+      pos += (j_first || (!me_first && j < tid)) ? 1 : 0;
+    }
+    srt_key[pos] = ka; srt_idx[pos] = ia; srt_win[pos] = win_key[tid];
+  }
+  __syncthreads();
+  if (tid == 0) {
+    // worst kept approximate key = lower bound of every excluded row's approximate key
+    float a_excl = -INFINITY; int n_valid = 0;
+    for (int r = 0; r < KT; ++r) if (srt_idx[r] >= 0) { a_excl = fmaxf(a_excl, srt_win[r]); ++n_valid; }
+    bool verified = !any_marked && !overflow;
+    if (verified && n_valid == KT) {                           // something may have been excluded
+      const int kk = min(k, n_valid);
+      const float ek = srt_key[kk - 1];                        // exact k-th best ordering key
+      const float qn = sqrtf(qstat[0]);
+      const float gmax = gmax_ptr ? __int_as_float(*reinterpret_cast<const int*>(gmax_ptr)) : 1.0f;
+      float exact_in_approx_units, delta;
+      const float rel = (fmt == B200F_OPERAND_FP16) ? GALLERY_DOT_ERR_FP16 : GALLERY_DOT_ERR;
+      const float abs_e = (fmt == B200F_OPERAND_FP16) ? GALLERY_ABS_ERR_FP16 * sqrtf((float)D) : 0.f;
+      if (cosine) {
+        const float qv = q_inv ? q_inv[qi] : 1.0f;
+        exact_in_approx_units = (qv > 0.f) ? ek / qv : -INFINITY;
+        delta = rel * qn * 1.01f + abs_e * (qn + 1.0f);
+      } else {
+        exact_in_approx_units = ek * ek - (qstat[0] + 2.0f * GALLERY_EPS * qstat[1] + (float)D * GALLERY_EPS * GALLERY_EPS);
+        delta = 2.0f * (rel * qn * gmax + abs_e * (qn + gmax)) + 1e-6f * (qstat[0] + gmax * gmax + 1.0f);
+      }
+      verified = (ek == ek) && (exact_in_approx_units < a_excl - delta);
+    }
     if (accept != nullptr) {
-      const bool ok = s_wi >= 0 && s_ex == s_ex;
-      const float best = cosine ? -s_ex : s_ex;
+      const bool ok = srt_idx[0] >= 0 && srt_key[0] == srt_key[0];
+      const float best = cosine ? -srt_key[0] : srt_key[0];
       accept[qi] = ok && (cosine ? (best >= thresh) : (best <= thresh));
     }
     redo[qi] = verified ? 0 : 1;
     if (!verified && redo_count != nullptr) atomicAdd(redo_count, 1);
+  }
+  if (tid < k) {
+    const bool ok = (tid < KT) && srt_idx[tid] >= 0 && srt_key[tid] == srt_key[tid];
+    idx_out[qi * k + tid] = ok ? (index_offset + srt_idx[tid]) : -1;
+    score_out[qi * k + tid] = ok ? (cosine ? -srt_key[tid] : srt_key[tid]) : (cosine ? -INFINITY : INFINITY);
   }
 }
 
