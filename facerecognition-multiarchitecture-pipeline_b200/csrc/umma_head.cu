@@ -828,8 +828,11 @@ static GalleryScanPlan gallery_scan_plan(int64_t Q, int64_t N, int D, int k) {
   g.off_tau = off;  off += align_up(sizeof(float) * (size_t)Q, 256);
   g.off_qbad = off; off += align_up((size_t)Q, 256);
   g.off_cnt = off;  off += align_up(sizeof(int32_t) * (size_t)Q, 256);
-  g.compact = g_gallery_compact.load(std::memory_order_relaxed) != 0 && g.n_sample > 0 && g.q.m_groups == 1 &&
-              g.qs.n_chunks * 2 >= 4 * g.KT && g.qs.n_chunks * 2 <= 256;
+  // compact mode: the sample yields n_chunks * 2 * GALLERY_MIN_SUB minima per query (1024 for one row group: one tile per
+  // CTA; 32 for several: 4 chunks of 8 tiles) -- at least 2 KT of them for the KT-th smallest to be a bound worth having
+  const int n_min = g.qs.n_chunks * 2 * GALLERY_MIN_SUB;
+  g.compact = g_gallery_compact.load(std::memory_order_relaxed) != 0 && g.n_sample > 0 &&
+              n_min >= 2 * g.KT && n_min <= 32 * GALLERY_TAU_MIN_PER_LANE;
   g.total = off + 1024;
   return g;
 }
@@ -872,10 +875,14 @@ static int gallery_scan_kt(const GalleryScanPlan& gp, const void* g16, const CUt
     // sample pre-pass, min-only: every CTA scans one tile of the first n_sample rows and keeps the smallest key per
     // (CTA, column half); tau0[q] = KT-th smallest of those minima; the same kernel zeroes the candidate counters
     XwMinKey::Params es{ep.bias, ep.mult, skey, gp.qs.n_chunks * 2};
+    const int n_min = gp.qs.n_chunks * 2 * GALLERY_MIN_SUB;
     int rcs = (gp.qs.pair == 2) ? launch_xw<2, XW_KK, XwMinKey>(tx, tw, gp.qs, Q, gp.n_sample, D, es, st, "umma K4 gallery sample minima (cta pair)", mfmt)
                                 : launch_xw<1, XW_KK, XwMinKey>(tx, tw, gp.qs, Q, gp.n_sample, D, es, st, "umma K4 gallery sample minima", mfmt);
     if (rcs) return rcs;
-    launch_pdl(gallery_tau_min_kernel<KT>, dim3((unsigned)ceil_div(Q, 4)), dim3(128), 0, st, (const float*)skey, es.n_lists, Q, tau0, cnt);
+    const dim3 tgrid((unsigned)ceil_div(Q, 4));
+    if (n_min <= 32) launch_pdl(gallery_tau_min_kernel<KT, 1>, tgrid, dim3(128), 0, st, (const float*)skey, n_min, Q, tau0, cnt);
+    else if (n_min <= 256) launch_pdl(gallery_tau_min_kernel<KT, 8>, tgrid, dim3(128), 0, st, (const float*)skey, n_min, Q, tau0, cnt);
+    else launch_pdl(gallery_tau_min_kernel<KT, 32>, tgrid, dim3(128), 0, st, (const float*)skey, n_min, Q, tau0, cnt);
     B200F_LAUNCH_OK("gallery_tau_min_kernel");
     ep.tau0 = tau0; ep.cnt = cnt; ep.cap = gp.n_lists * KT;
   } else if (gp.n_sample > 0) {

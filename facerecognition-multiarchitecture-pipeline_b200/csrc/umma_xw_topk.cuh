@@ -168,44 +168,66 @@ struct XwTopK {
   }
 };
 
-// Sample pre-pass, single row group: only the SMALLEST key of each (CTA, column half) is kept -- the bound below needs
-// nothing else, and the full KT-deep sorted insertion of XwTopK was most of the pre-pass (24 us for one tile per CTA).
+// Sample pre-pass, min-only: a thread keeps GALLERY_MIN_SUB minima, one per residue class of its slice counter (disjoint
+// columns, so the minima belong to distinct gallery rows) -- the bound below needs nothing else, and the full KT-deep sorted
+// insertion of XwTopK was most of the pre-pass (24 us for one tile per CTA at Q = 128, 185 us at Q = 8192 x 125 k).
+constexpr int GALLERY_MIN_SUB = 4;
 struct XwMinKey {
-  struct Params { const float* bias; float mult; float* out; int n_lists; };
-  struct State { float m; bool row_ok; };
+  struct Params { const float* bias; float mult; float* out; int n_lists; };   // out [Q, n_lists, GALLERY_MIN_SUB]
+  struct State { float m[GALLERY_MIN_SUB]; int s; bool row_ok; };
   static __device__ __forceinline__ void item_begin(State& st, const Params&, const XwParams& p, const XwItem& it) {
-    st.m = 3.0e38f; st.row_ok = it.row < p.B;
+#pragma unroll
+    for (int b = 0; b < GALLERY_MIN_SUB; ++b) st.m[b] = 3.0e38f;
+    st.s = 0; st.row_ok = it.row < p.B;
   }
   static __device__ __forceinline__ void tile_begin(State&, const Params&, const XwParams&, const XwItem&, int, int, int) {}
   static __device__ __forceinline__ void slice(State& st, const Params& ep, const XwParams& p, const XwItem&,
                                                float (&v)[32], int cls0) {
     const int cc = min(32, p.C - cls0);
     float m4[4] = {3.0e38f, 3.0e38f, 3.0e38f, 3.0e38f};
+    if (ep.bias != nullptr && cc == 32 && (reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0) {
+      const float4* b4 = reinterpret_cast<const float4*>(ep.bias + cls0);   // eight 16-byte loads, not 32 scalar ones
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
+      for (int j = 0; j < 32; j += 4) {
+        const float4 bb = __ldg(b4 + (j >> 2));
+        m4[0] = fminf(m4[0], fmaf(v[j], ep.mult, bb.x)); m4[1] = fminf(m4[1], fmaf(v[j + 1], ep.mult, bb.y));
+        m4[2] = fminf(m4[2], fmaf(v[j + 2], ep.mult, bb.z)); m4[3] = fminf(m4[3], fmaf(v[j + 3], ep.mult, bb.w));
+      }
+    } else {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float a = (ep.bias != nullptr) ? fmaf(v[j + u], ep.mult, (j + u < cc) ? __ldg(ep.bias + cls0 + j + u) : 0.f)
-                                             : v[j + u] * ep.mult;
-        m4[u] = fminf(m4[u], (j + u < cc) ? a : 3.0e38f);      // NaN keys never win an fminf
+      for (int j = 0; j < 32; j += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float a = (ep.bias != nullptr) ? fmaf(v[j + u], ep.mult, (j + u < cc) ? __ldg(ep.bias + cls0 + j + u) : 0.f)
+                                               : v[j + u] * ep.mult;
+          m4[u] = fminf(m4[u], (j + u < cc) ? a : 3.0e38f);    // NaN keys never win an fminf
+        }
       }
     }
-    st.m = fminf(st.m, fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3])));
+    const float sm = fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3]));
+    const int b = st.s & (GALLERY_MIN_SUB - 1);
+    ++st.s;
+#pragma unroll
+    for (int u = 0; u < GALLERY_MIN_SUB; ++u) if (u == b) st.m[u] = fminf(st.m[u], sm);
   }
   static __device__ __forceinline__ void item_end(State& st, const Params& ep, const XwParams&, const XwItem& it, float*) {
-    if (st.row_ok) ep.out[(int64_t)it.row * ep.n_lists + it.chunk * 2 + it.half] = st.m;
+    static_assert(GALLERY_MIN_SUB == 4, "one float4 per thread");
+    if (st.row_ok)
+      *reinterpret_cast<float4*>(ep.out + ((int64_t)it.row * ep.n_lists + it.chunk * 2 + it.half) * GALLERY_MIN_SUB) =
+          make_float4(st.m[0], st.m[1], st.m[2], st.m[3]);
   }
 };
 
-// tau0[q] = KT-th smallest of the query's n_lists (<= 256) per-list minima: KT DISTINCT gallery rows have a key <= it
+// tau0[q] = KT-th smallest of the query's n_lists (<= 1024) minima: KT DISTINCT gallery rows have a key <= it
 // (the lists cover disjoint rows), so it bounds the KT-th best key of the whole gallery.  One warp per query, the
 // values in registers, KT rounds of a shuffle arg-min.  Also zeroes the query's candidate counter of the compact scan.
-template <int KT>
+constexpr int GALLERY_TAU_MIN_PER_LANE = 32;                    // minima a lane holds at most: 1024 per query
+template <int KT, int L>
 __global__ void __launch_bounds__(128)
 gallery_tau_min_kernel(const float* __restrict__ key_min, int n_lists, int64_t Q, float* __restrict__ tau0,
                        int32_t* __restrict__ cnt) {
   pdl_trigger(); pdl_wait();
-  constexpr int L = 8;
+  static_assert(L <= GALLERY_TAU_MIN_PER_LANE, "minima per lane");
   const int lane = threadIdx.x & 31;
   const int64_t qi = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
   if (qi >= Q) return;
