@@ -464,11 +464,13 @@ int head_dx_finish(const void* xh, float S, const HeadDx* hdx, const float* dxha
 
 // tunable "k2_prep": 1 = K1 of the class weights runs inside K2 (HeadPrep: prep warps + per-128-row hand-over counters),
 // 0 = as its own pass in front of K2 (default), 2 = probe: the 20-warp kernel with idle prep warps.  Measured at cfg3 on one
-// box (gpurun_out/r02k_*, r02m_*): K1(W) 40.5 us + K2 60 us apart; fused 227 us with 2 prep warps (168 registers), 140 us
-// with 6 (128), 115 us with 10 (96 registers, 16-column epilogue -- which alone still runs K2 in 60.6 us).  The rows are
-// bit-identical and the hand-over works, but normalising a row is ~160 warp instructions of latency-bound scalar work and
-// ten warps per SM turn over 5.9 rows/us where the stand-alone K1 (16 warps, the SM to itself) does 16.4: the fused kernel
-// waits for its own prep warps.  What K2 has to spare is HBM bandwidth, not issue slots and registers.
+// box each (gpurun_out/r02k_*, r02m_*): K1(W) 38.5-40.5 us + K2 60 us apart; fused 227 us with 2 prep warps (168
+// registers), 140 us with 6 (128), 115 us with 10 (96 registers, 16-column epilogue -- which alone still runs K2 in
+// 60.6 us), 123 us with packed fp32x2 math on shorter trips, 98.4 us once the gpu-scope release of the row counters was
+// paid per run of rows instead of per trip (it waits for the warp's stores: ~2 us), 104.7 us with L2 prefetches on top.
+// So the hand-over works and the rows agree to the last bit or one, but the fused kernel only breaks even: normalising a
+// row is latency-bound scalar work, ten warps per SM turn over ~7 rows/us where the stand-alone K1 (16 warps, the SM to
+// itself) does 16.4, and K2 finishes ~20 us after its last row arrives.  What K2 has to spare is HBM bandwidth, not warps.
 static std::atomic<int> g_k2_prep{0};
 
 __global__ void zero_words_kernel(unsigned int* p, int n) {

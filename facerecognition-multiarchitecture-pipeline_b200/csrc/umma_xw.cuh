@@ -194,26 +194,25 @@ __device__ __forceinline__ bool xw_wait_ready(const unsigned int* flag, unsigned
   return false;
 }
 
-// publish rows finished by this warp: one count per 128-row block, released at gpu scope (lane 0; the __syncwarp orders
-// the other lanes' stores before its fence)
-template <int ROWS>
-__device__ __forceinline__ void xw_prep_publish(const XwParams& p, const int (&row)[ROWS], int lane) {
+// Publishing finished rows: the count of a 128-row block is raised with a release at gpu scope (fence.acq_rel + red; not
+// __threadfence(), which is fence.sc).  The release waits for the warp's outstanding stores (1.5-2.5 us under this kernel's
+// memory traffic), so it is paid once per RUN of rows in the same block -- a warp's rows of one round -- not once per trip:
+// with one release per 2-3 rows the ten prep warps of an SM spent most of their time in it (K2 115-123 us).
+struct XwPrepPending { int blk; unsigned int cnt; };
+__device__ __forceinline__ void xw_prep_flush(const XwParams& p, XwPrepPending& pd, int lane) {
+  if (pd.cnt == 0) return;                                      // warp-uniform
   __syncwarp();
-  if (lane == 0) {
-    // release at gpu scope ON the counter update (fence.acq_rel + red), not __threadfence(): that one is fence.sc, which
-    // cost ~4 us per trip under this kernel's memory traffic (K2 150 us instead of 60)
-    int blk = -1; unsigned int cnt = 0;
+  if (lane == 0) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p.prep_ready + pd.blk), "r"(pd.cnt) : "memory");
+  pd.cnt = 0;
+}
+template <int ROWS>
+__device__ __forceinline__ void xw_prep_note(const XwParams& p, XwPrepPending& pd, const int (&row)[ROWS], int lane) {
 #pragma unroll
-    for (int j = 0; j < ROWS; ++j) {
-      if (row[j] < 0) continue;
-      const int b = row[j] >> 7;
-      if (b != blk) {
-        if (cnt) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p.prep_ready + blk), "r"(cnt) : "memory");
-        blk = b; cnt = 0;
-      }
-      ++cnt;
-    }
-    if (cnt) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p.prep_ready + blk), "r"(cnt) : "memory");
+  for (int j = 0; j < ROWS; ++j) {
+    if (row[j] < 0) continue;                                   // warp-uniform
+    const int b = row[j] >> 7;
+    if (b != pd.blk) { xw_prep_flush(p, pd, lane); pd.blk = b; }
+    ++pd.cnt;
   }
 }
 
@@ -243,6 +242,8 @@ template <int TN, int ROWS, bool F32>
 __device__ __forceinline__ void xw_prep_load(const XwParams& p, XwPrepBuf<ROWS, F32>& b, XwPrepPos& pos, int rpw, int maxT,
                                              int r0_mine, int cnt_mine, int lane) {
   constexpr int RW = XwPrepBuf<ROWS, F32>::RW;
+  // (Measured and dropped: bulk L2 prefetches of the rows of the next three rounds, one per slot -- K2 104.7 us against
+  //  98.4 without: the prep warps are not waiting for their loads.)
   int k = pos.k, s = pos.slot + lane;                           // lane j < ROWS resolves the j-th entry from pos
   while (s >= rpw) { s -= rpw; ++k; }
   const int r0 = __shfl_sync(0xffffffffu, r0_mine, s & 31);
@@ -277,26 +278,45 @@ __device__ __forceinline__ void xw_prep_load(const XwParams& p, XwPrepBuf<ROWS, 
   }
 }
 
+// packed fp32x2 arithmetic (sm_100): one instruction per element PAIR
+__device__ __forceinline__ uint64_t f32x2_pack(float lo, float hi) {
+  uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
+}
+__device__ __forceinline__ void f32x2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f32x2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r;
+}
+__device__ __forceinline__ uint64_t f32x2_mul(uint64_t a, uint64_t b) {
+  uint64_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
+}
+// element pair i (elements 2i, 2i + 1) of row j as a packed fp32x2
 template <int ROWS, bool F32>
-__device__ __forceinline__ float xw_prep_elem(const XwPrepBuf<ROWS, F32>& b, int j, int i) {
-  if (F32) return __uint_as_float(b.raw[j][i]);
-  return (i & 1) ? __uint_as_float(b.raw[j][i >> 1] & 0xffff0000u) : __uint_as_float(b.raw[j][i >> 1] << 16);
+__device__ __forceinline__ uint64_t xw_prep_pair(const XwPrepBuf<ROWS, F32>& b, int j, int i) {
+  if (F32) return f32x2_pack(__uint_as_float(b.raw[j][2 * i]), __uint_as_float(b.raw[j][2 * i + 1]));
+  return f32x2_pack(__uint_as_float(b.raw[j][i] << 16), __uint_as_float(b.raw[j][i] & 0xffff0000u));
 }
 
+// The sum of squares runs as two chains per lane (even and odd elements, packed FFMA2), added at the end: not the
+// stand-alone K1's single chain, so 1/||w|| can differ from its value in the last bit (and with it, rarely, an operand's).
 template <int ROWS, bool F32>
 __device__ __forceinline__ void xw_prep_finish(const XwParams& p, const XwPrepBuf<ROWS, F32>& b, int lane) {
+  uint64_t ss2[ROWS];
+#pragma unroll
+  for (int j = 0; j < ROWS; ++j) ss2[j] = 0ull;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)                                   // pair-major: ROWS independent chains
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j) { const uint64_t v = xw_prep_pair<ROWS, F32>(b, j, i); ss2[j] = f32x2_fma(v, v, ss2[j]); }
   float ss[ROWS];
 #pragma unroll
-  for (int j = 0; j < ROWS; ++j) ss[j] = 0.f;
-#pragma unroll
-  for (int i = 0; i < 16; ++i)                                  // element-major: ROWS independent chains
-#pragma unroll
-    for (int j = 0; j < ROWS; ++j) { const float v = xw_prep_elem<ROWS, F32>(b, j, i); ss[j] = fmaf(v, v, ss[j]); }
+  for (int j = 0; j < ROWS; ++j) { float lo, hi; f32x2_unpack(ss2[j], lo, hi); ss[j] = lo + hi; }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1)                        // warp_sum's butterfly, the rows side by side
 #pragma unroll
     for (int j = 0; j < ROWS; ++j) ss[j] += __shfl_xor_sync(0xffffffffu, ss[j], off);
-  // the square root and the division once per ROW (lane j takes row j), not once per row and lane: same arithmetic
+  // the square root and the division once per ROW (lane j takes row j), not once per row and lane
   float m = ss[0];
 #pragma unroll
   for (int j = 1; j < ROWS; ++j) if (lane == j) m = ss[j];
@@ -311,11 +331,13 @@ __device__ __forceinline__ void xw_prep_finish(const XwParams& p, const XwPrepBu
   for (int j = 0; j < ROWS; ++j) {
     const float sc = __shfl_sync(0xffffffffu, inv_m, j) * p.prep_scale;
     if (b.row[j] < 0) continue;                                 // warp-uniform
+    const uint64_t sc2 = f32x2_pack(sc, sc);
     uint32_t o[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const __half2 h = __halves2half2(__float2half_rn(xw_prep_elem<ROWS, F32>(b, j, 2 * i) * sc),
-                                       __float2half_rn(xw_prep_elem<ROWS, F32>(b, j, 2 * i + 1) * sc));
+      float lo, hi;
+      f32x2_unpack(f32x2_mul(xw_prep_pair<ROWS, F32>(b, j, i), sc2), lo, hi);
+      const __half2 h = __floats2half2_rn(lo, hi);
       o[i] = *reinterpret_cast<const uint32_t*>(&h);
     }
     uint16_t* dst = p.prep_dst + (int64_t)b.row[j] * 512;
@@ -342,8 +364,7 @@ __device__ __forceinline__ void xw_prep_run(const XwParams& p, int gw, int nW) {
   const int q_hi = (q_lo + rpw < round_rows) ? q_lo + rpw : round_rows;
   if (q_lo >= round_rows) return;
   XwPrepBuf<ROWS, F32> a, b;
-  int prev[ROWS];
-  bool have_prev = false;
+  XwPrepPending pd{-1, 0u};
 #pragma unroll 1
   for (int W = 0; W < n_groups; ++W) {
     int r0_mine = 0, cnt_mine = 0;                              // slot `lane` of this warp in wave group W
@@ -363,19 +384,14 @@ __device__ __forceinline__ void xw_prep_run(const XwParams& p, int gw, int nW) {
 #pragma unroll 1
     for (int n0 = 0; n0 < n_total; n0 += 2 * ROWS) {
       xw_prep_load<TN, ROWS, F32>(p, b, pos, rpw, maxT, r0_mine, cnt_mine, lane);
-      if (have_prev) xw_prep_publish<ROWS>(p, prev, lane);
       xw_prep_finish<ROWS, F32>(p, a, lane);
-#pragma unroll
-      for (int j = 0; j < ROWS; ++j) prev[j] = a.row[j];
+      xw_prep_note<ROWS>(p, pd, a.row, lane);
       xw_prep_load<TN, ROWS, F32>(p, a, pos, rpw, maxT, r0_mine, cnt_mine, lane);
-      xw_prep_publish<ROWS>(p, prev, lane);
       xw_prep_finish<ROWS, F32>(p, b, lane);
-#pragma unroll
-      for (int j = 0; j < ROWS; ++j) prev[j] = b.row[j];
-      have_prev = true;
+      xw_prep_note<ROWS>(p, pd, b.row, lane);
     }
   }
-  if (have_prev) xw_prep_publish<ROWS>(p, prev, lane);
+  xw_prep_flush(p, pd, lane);
 }
 
 struct XwItem {                         // what an epilogue thread knows about its work item
@@ -474,8 +490,8 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
     if (p.prep_src != nullptr) {
       const int gw = (int)blockIdx.x * PREP_WARPS + (warp - 2 - EPI_WARPS_ALL);
       const int nW = (int)gridDim.x * PREP_WARPS;
-      if (p.prep_f32) xw_prep_run<TN, 2, true>(p, gw, nW);
-      else xw_prep_run<TN, 3, false>(p, gw, nW);
+      if (p.prep_f32) xw_prep_run<TN, 1, true>(p, gw, nW);
+      else xw_prep_run<TN, 2, false>(p, gw, nW);
     }
   } else if (warp == 0) {
     // ================= TMA producer (both CTAs) =================

@@ -501,8 +501,8 @@ def test_backward_chunking_is_invisible(cuda_device, mb, B, C):
 def test_k1w_inside_k2_equals_separate_pass(cuda_device, B, C, wdt):
     """b200f_arcface_fwd_raw with the class weights normalised INSIDE K2 (prep warps + per-128-row hand-over counters, tunable
     k2_prep = 1, the default) against K1 as a pass of its own in front of K2 (k2_prep = 0): the fp16 operand rows and the
-    inverse norms must be the same bits (bf16 weights: same per-lane element order and reduction), hence the same statistics,
-    loss and gradients; fp32 weights sum in another lane order, so there the bar is the operand rounding.  Shapes: one wave
+    inverse norms agree to the last bit or one (the prep warps add the squares as two packed chains), the statistics and the loss
+    to fp32 summation order.  Shapes: one wave
     (B = 512), several row groups and waves (B = 1024, 2100), a ragged last tile, fewer classes than one tile.  Repeated calls
     re-arm the counters."""
     from b200face import _lib
@@ -528,16 +528,14 @@ def test_k1w_inside_k2_equals_separate_pass(cuda_device, B, C, wdt):
     ref = res[0][0]
     for got in res[1]:
         assert torch.equal(got[0], ref[0]) and torch.equal(got[2], ref[2])                 # x operands, 1/||x||
-        if wdt == torch.bfloat16:
-            assert torch.equal(got[1], ref[1]) and torch.equal(got[3], ref[3])             # w operands, 1/||w||
-            # K2 itself runs on 16-column slices beside the prep warps (32 without): the statistics sum in another order
-            torch.testing.assert_close(got[4], ref[4], rtol=2e-5, atol=2e-3)    # column 3 is a sum of logits of both signs
-            torch.testing.assert_close(got[5], ref[5], rtol=2e-6, atol=0)
-            torch.testing.assert_close(got[6], ref[6], rtol=2e-6, atol=0)
-        else:
-            assert (got[1].float() - ref[1].float()).abs().max() <= 2 ** -3                # one fp16 ulp at 256
-            torch.testing.assert_close(got[3], ref[3], rtol=1e-6, atol=0)
-            torch.testing.assert_close(got[6], ref[6], rtol=1e-5, atol=0)
+        # the prep warps sum the squares as two packed chains per lane (FFMA2), the stand-alone K1 as one: 1/||w|| may differ
+        # in the last bit, an operand then by one fp16 ulp; K2 itself runs on 16-column slices beside the prep warps (32
+        # without), so the statistics sum in another order
+        assert (got[1].float() - ref[1].float()).abs().max() <= 2 ** -3                    # one fp16 ulp at 256
+        torch.testing.assert_close(got[3], ref[3], rtol=1e-6, atol=0)
+        torch.testing.assert_close(got[4], ref[4], rtol=1e-4, atol=5e-3)                   # column 3 is a sum of logits of both signs
+        torch.testing.assert_close(got[5], ref[5], rtol=2e-5, atol=0)
+        torch.testing.assert_close(got[6], ref[6], rtol=2e-5, atol=0)
     # the reference's own normalise as the anchor of the rows themselves
     wn = torch.nn.functional.normalize(w.float(), dim=1) * 256.0
     assert (res[1][0][1].float() - wn).abs().max() <= 2 ** -3 + 1e-3

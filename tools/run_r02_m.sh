@@ -3,12 +3,12 @@ set -u
 mkdir -p gpurun_out
 O=gpurun_out
 B="--steps 300 --warmup 5 --no-cpu-baseline --no-gallery --no-train-step --no-cfg4"
-for v in 0 2 1; do
+for v in 0 1; do
   timeout 300 python bench.py $B --tune k2_prep=$v > $O/r02m_prep$v.json 2> $O/r02m_prep$v.err || { echo "prep$v failed"; tail -5 $O/r02m_prep$v.err; }
 done
 python - <<'PY'
 import json
-for v in (0,2,1):
+for v in (0,1):
     try:
         d=json.loads(open(f"gpurun_out/r02m_prep{v}.json").read().strip().splitlines()[-1])
         k=d["kernel_ms"]
@@ -16,6 +16,4 @@ for v in (0,2,1):
     except Exception as e:
         print(v, "no line", e)
 PY
-CMD2="python bench.py --steps 2 --warmup 3 --no-gallery --no-cpu-baseline --no-train-step --no-cfg4 --eager --tune k2_prep=1"
-timeout 900 ncu --set full --import-source on --clock-control none -k regex:"xw_kernel" --launch-skip 6 --launch-count 1 -f -o $O/r02m_k2prep $CMD2 > $O/r02m_ncu.log 2>&1
-echo "ncu full rc=$?"; tail -2 $O/r02m_ncu.log
+timeout 600 python -m pytest tests/test_gpu_head.py -m gpu -x -q -k "k1w_inside" > gpurun_out/r02m_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r02m_pytest.log | cut -c1-300
