@@ -899,8 +899,12 @@ static int gallery_scan_kt(const GalleryScanPlan& gp, const void* g16, const CUt
     ep.tau0 = tau0;
   }
   ep.cand_key = ckey; ep.cand_idx = cidx; ep.n_lists = gp.n_lists;
-  int rc = (gp.q.pair == 2) ? launch_xw<2, XW_KK, XwTopK<KT>>(tx, tw, gp.q, Q, N, D, ep, st, "umma K4 gallery scan (cta pair)", mfmt, false, g16, (int64_t)D * 2)
-                            : launch_xw<1, XW_KK, XwTopK<KT>>(tx, tw, gp.q, Q, N, D, ep, st, "umma K4 gallery scan", mfmt, false, g16, (int64_t)D * 2);
+  // Both operands of the main scan are older than its predecessor (q16: the query prepare, two or three kernels back; g16:
+  // the gallery): with a sample bound in front its TMA and MMA warps start without waiting for the tau kernel -- the 128 KB
+  // of queries per CTA and the first tiles load while that kernel runs -- and only the epilogue (tau0, the counters) waits.
+  const bool scan_early = gp.n_sample > 0;
+  int rc = (gp.q.pair == 2) ? launch_xw<2, XW_KK, XwTopK<KT>>(tx, tw, gp.q, Q, N, D, ep, st, "umma K4 gallery scan (cta pair)", mfmt, false, g16, (int64_t)D * 2, scan_early)
+                            : launch_xw<1, XW_KK, XwTopK<KT>>(tx, tw, gp.q, Q, N, D, ep, st, "umma K4 gallery scan", mfmt, false, g16, (int64_t)D * 2, scan_early);
   if (rc) return rc;
   if (gp.compact) {
     const int cap = gp.n_lists * KT;

@@ -21,5 +21,10 @@ timeout 500 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --
 python tools/condense_launches.py $O/r02j_launches_raw.csv $O/r02_launches_bench_cfg3.csv "ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv $CMD"; echo "condense rc=$?"
 CMD2="python bench.py --steps 2 --warmup 3 --no-gallery --no-cpu-baseline --no-train-step --no-cfg4 --eager"
 timeout 300 $CMD2 > $O/r02j_ncu_plain.json 2> $O/r02j_ncu_plain.err && \
-timeout 900 ncu --set full --import-source on --clock-control none -k regex:"xw_kernel|gemm_kernel|l2norm_rows" --launch-skip 20 --launch-count 6 -f -o $O/r02j_step $CMD2 > $O/r02j_ncu.log 2>&1
+timeout 900 ncu --set full --import-source on --clock-control none -k regex:"xw_kernel|gemm_kernel|l2norm_rows" --launch-skip 21 --launch-count 8 -f -o $O/r02j_step $CMD2 > $O/r02j_ncu.log 2>&1
 echo "ncu full rc=$?"; tail -3 $O/r02j_ncu.log; ls -la $O/r02j_step.ncu-rep
+# gallery: launch list + full capture of the streaming call
+GTIME=1 timeout 120 python tools/gallery_prof.py > $O/r02j_gal_plain.log 2>&1 && \
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $O/r02_launches_gallery_q128.csv python tools/gallery_prof.py > $O/r02j_gal_ncu.log 2>&1
+timeout 600 ncu --set full --import-source on --clock-control none -k regex:"xw_kernel|gallery_select|gallery_tau" --launch-skip 6 --launch-count 4 -f -o $O/r02j_gallery python tools/gallery_prof.py > $O/r02j_gal_ncu_full.log 2>&1
+echo "gallery ncu rc=$?"; tail -2 $O/r02j_gal_plain.log
