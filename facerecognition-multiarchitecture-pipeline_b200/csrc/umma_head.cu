@@ -217,6 +217,7 @@ static std::atomic<int> g_k3a_ablate{0};            // probe: 2 = no G^T stores 
 static std::atomic<int> g_k3b_ablate{0};            // probe: 1 = no w_hat loads, 2 = no dW stores (WRONG results)
 #endif
 static std::atomic<int> g_k3b_reverse{1};
+static std::atomic<int> g_target_patch{1};          // tunable "target_patch": 1 = K2 / K3a exchange a target element in place, 0 = whole slice element-wise
 static std::atomic<int> g_x_whole{0};               // tunable "x_whole": 1 = first MMA of an item waits for the whole resident operand
 // "stage_events" tunable: record a CUDA event pair around each GEMM kernel of the head on the launching stream
 // (bench.py's per-kernel durations; eager launches only -- never inside a graph capture).
@@ -545,6 +546,7 @@ int head_fwd(const void* xh, const void* wh, const int64_t* label, int64_t B, in
   ep.cos_part = reinterpret_cast<float*>(ws + pl.off_cos);
   ep.nan_flag = nan_flag; ep.pair = q.pair;
   ep.zero_word = reinterpret_cast<unsigned int*>(ws + pl.off_counter);
+  ep.whole_slice_targets = g_target_patch.load(std::memory_order_relaxed) ? 0 : 1;
   const int eg = g_k2_groups.load(std::memory_order_relaxed);
   const int64_t wrb = (int64_t)D * 2;
   const int k2_hint = (g_l2_hints.load(std::memory_order_relaxed) & 16) ? 2 : 0;
@@ -556,6 +558,7 @@ int head_fwd(const void* xh, const void* wh, const int64_t* label, int64_t B, in
     XwFwdP::Params epp{};
     epp.label = ep.label; epp.class_offset = ep.class_offset; epp.hm = ep.hm; epp.inv_scale = ep.inv_scale; epp.part = ep.part;
     epp.cos_part = ep.cos_part; epp.nan_flag = ep.nan_flag; epp.pair = ep.pair; epp.zero_word = ep.zero_word;
+    epp.whole_slice_targets = ep.whole_slice_targets;
     const XwPrepArgs pa{prep->w_raw, prep->w_dtype == B200F_F32 ? 1 : 0, static_cast<uint16_t*>(const_cast<void*>(wh)), prep->inv_nw,
                         ready, prep->eps, cfg->operand_scale};
     rc = (q.pair == 2) ? launch_xw<2, XW_KK, XwFwdP>(tx, tw, q, B, C, D, epp, st, "umma K2 arcface_fwd + K1(W) (cta pair)", FMT_F16, false, wh, wrb, false, k2_hint, fused_prep ? &pa : nullptr)
@@ -564,6 +567,7 @@ int head_fwd(const void* xh, const void* wh, const int64_t* label, int64_t B, in
     XwFwd2::Params ep2{};
     ep2.label = ep.label; ep2.class_offset = ep.class_offset; ep2.hm = ep.hm; ep2.inv_scale = ep.inv_scale; ep2.part = ep.part;
     ep2.cos_part = ep.cos_part; ep2.nan_flag = ep.nan_flag; ep2.pair = ep.pair; ep2.zero_word = ep.zero_word;
+    ep2.whole_slice_targets = ep.whole_slice_targets;
     rc = (q.pair == 2) ? launch_xw<2, XW_KK, XwFwd2>(tx, tw, q, B, C, D, ep2, st, "umma K2 arcface_fwd (cta pair, 2 epilogue groups)", FMT_F16, false, wh, wrb, false, k2_hint)
                        : launch_xw<1, XW_KK, XwFwd2>(tx, tw, q, B, C, D, ep2, st, "umma K2 arcface_fwd (2 epilogue groups)", FMT_F16, false, wh, wrb, false, k2_hint);
   } else {
@@ -652,6 +656,7 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
     eg.ls_eps = cfg->label_smoothing; eg.inv_Ctot = 1.0f / (float)cfg->num_classes_total; eg.inv_scale = 1.0f / (S * S);
     eg.GT = G; eg.ldgt = pl.ldg; eg.r_part = r_part; eg.ldr = pl.Cc;
     eg.gt_hint = (hints & 2) ? 2 : 0;
+    eg.whole_slice_targets = g_target_patch.load(std::memory_order_relaxed) ? 0 : 1;
     const int k3a_whint = (hints & 1) ? 1 : 0;
 #ifdef B200F_PROBES
     eg.ablate = g_k3a_ablate.load(std::memory_order_relaxed);
@@ -662,7 +667,7 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
       XwBwdGT2::Params e2{};
       e2.label = eg.label; e2.lse = eg.lse; e2.grad4 = eg.grad4; e2.class_offset = eg.class_offset; e2.hm = eg.hm;
       e2.ls_eps = eg.ls_eps; e2.inv_Ctot = eg.inv_Ctot; e2.inv_scale = eg.inv_scale; e2.GT = eg.GT; e2.ldgt = eg.ldgt;
-      e2.r_part = eg.r_part; e2.ldr = eg.ldr; e2.gt_hint = eg.gt_hint;
+      e2.r_part = eg.r_part; e2.ldr = eg.ldr; e2.gt_hint = eg.gt_hint; e2.whole_slice_targets = eg.whole_slice_targets;
 #ifdef B200F_PROBES
       e2.ablate = eg.ablate;
 #endif
@@ -1052,6 +1057,7 @@ int b200f_set_tunable(const char* name, int value) {
   if (n == "pdl") { const int old_v = pdl_enabled() ? 1 : 0; if (value == 0 || value == 1) pdl_set(value != 0); return old_v; }
   if (n == "stage_events") { if (value != 0 && value != 1) return g_stage_events.load(); return g_stage_events.exchange(value); }
   if (n == "k2_prep") { if (value < 0 || value > 2) return g_k2_prep.load(); return g_k2_prep.exchange(value); }
+  if (n == "target_patch") { if (value != 0 && value != 1) return g_target_patch.load(); return g_target_patch.exchange(value); }
   if (n == "x_whole") { if (value != 0 && value != 1) return g_x_whole.load(); return g_x_whole.exchange(value); }
   if (n == "k1_hints") { if (value < 0 || value > 3) return k1_hints(); return k1_hints_set(value); }
   if (n == "l2_hints") { if (value < 0) return g_l2_hints.load(); return g_l2_hints.exchange(value); }

@@ -88,6 +88,12 @@ __device__ __forceinline__ void tmem_ld_wait_dep(float (&v)[16]) {
       :
       : "memory");
 }
+// one column (32 lanes x 1 fp32), synchronous: a single accumulator element per thread, for rarely taken paths
+__device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n\ttcgen05.wait::ld.sync.aligned;" : "=r"(r) : "r"(taddr) : "memory");
+  return __uint_as_float(r);
+}
 // barrier over the 256 threads of ONE epilogue group (ids 1, 2: the groups run at their own pace)
 __device__ __forceinline__ void epi_bar_sync(int grp = 0) {
   asm volatile("bar.sync %0, 256;" ::"r"(1 + grp) : "memory");
@@ -400,6 +406,7 @@ struct XwItem {                         // what an epilogue thread knows about i
   int grp;                              // epilogue group 0..kEpiGroups-1
   int first_tile;                       // position (in the item's walk order) of the first tile this group takes
   int64_t row;                          // global row of x owned by this thread
+  uint32_t taddr0;                      // TMEM address of this thread's lane, column 0 of the current accumulator stage (SWAP mode)
   uint8_t* aux;                         // this warp's staging bytes (nullptr unless the policy reserves them)
   uint64_t* aux_bar;                    // its two mbarriers
   mutable uint32_t aux_phase;           // their parity bits; lives across the items of the kernel
@@ -667,6 +674,7 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
           tc_fence_after_sync();
           it.row = (int64_t)t * TN + rank * XW_WROWS + it.quad * 32 + lane;   // the class this thread owns in tile t
           const uint32_t taddr = tmem_base + (uint32_t)acc * ACC_STRIDE + ((uint32_t)(it.quad * 32) << 16) + (uint32_t)col_base;
+          it.taddr0 = taddr - (uint32_t)col_base;
           Epi::tile_begin(stt, ep, p, it);
           float va[SC], vb[SC];
           tmem_ld32_async(taddr, va);

@@ -16,6 +16,9 @@ namespace umma {
 
 constexpr int PART_COLS = 6;   // sumexp, sumexp2, ztarget, sumz, best, bestidx (int32 bits)
 
+// phi out of line: its acosf / cosf code is large, and it runs for one element of one slice in a hundred
+__device__ __noinline__ float head_phi_once(HeadMath hm, float c) { return hm.phi(c); }
+
 // -------------------------------------------------------------------------------------------------
 // Raw accumulators -> out[row, class] (self-test of the kernel itself).
 struct XwStore {
@@ -72,6 +75,7 @@ struct XwFwdT {
     int32_t* nan_flag;
     int pair;
     unsigned int* zero_word;    // a word of the workspace the kernel clears (block counter of the fused loss finalize)
+    int whole_slice_targets;    // tunable "target_patch" = 0: a slice with a target column goes the element-wise way (round 1)
   };
   struct State {
     float sumexp, sumexp2, sumz, ztgt, best, cmin, cmax;
@@ -125,19 +129,47 @@ struct XwFwdT {
     const float tmn = fminf(fminf(mn4[0], mn4[1]), fminf(mn4[2], mn4[3]));
     const float tmx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
     const bool has_t = (st.tgt >= cls0) && (st.tgt < cls0 + SC);
-    bool careful = !(s_eff > 0.f) || has_t || (cc < SC) || !(tmx * isc <= hi) || !(tmn * isc >= lo) ||
-                   !isfinite(ct) || !isfinite(ce);
+    // The whole slice goes the element-wise way only when something in it needs the clamp or the NaN scrub (or the slice is
+    // ragged).  A target column alone does not: the slice is summed as if it had no margin and the ONE element is then
+    // exchanged by the lane that owns it.  (Round 1 sent every slice with a target down the element-wise path -- 1 % of
+    // the slices at cfg3, but every second tile then waited for a warp in it: K2 61.9 us against 49.9 us with the labels
+    // moved out of range, tools/careful_probe.py.)
+    bool careful = !(s_eff > 0.f) || (cc < SC) || !(tmx * isc <= hi) || !(tmn * isc >= lo) ||
+                   !isfinite(ct) || !isfinite(ce) || (has_t && ep.whole_slice_targets);
     careful = __any_sync(0xffffffffu, careful);               // warp stays convergent for the next tcgen05.ld
     if (!careful) {
       st.sumexp += ce; st.sumexp2 += ce2; st.sumz = fmaf(ct, zs, st.sumz);
       st.cmin = fminf(st.cmin, tmn * isc); st.cmax = fmaxf(st.cmax, tmx * isc);
-      const float bz = tmx * zs;
-      if (bz > st.best) {                                     // rare after the first few slices
-        st.best = bz;
-        int tix = SC - 1;
+      if (!has_t) {
+        const float bz = tmx * zs;
+        if (bz > st.best) {                                   // rare after the first few slices
+          st.best = bz;
+          int tix = SC - 1;
 #pragma unroll
-        for (int j = SC - 2; j >= 0; --j) if (v[j] == tmx) tix = j;   // first index of the maximum
-        st.bestidx = cls0 + tix;
+          for (int j = SC - 2; j >= 0; --j) if (v[j] == tmx) tix = j;   // first index of the maximum
+          st.bestidx = cls0 + tix;
+        }
+      } else {
+        // my target column sits in this slice: take its margin-free contribution out, put phi(cos) in (:363-427)
+        const int jt = st.tgt - cls0;
+        float at = 0.f;
+#pragma unroll
+        for (int j = 0; j < SC; ++j) if (j == jt) at = v[j];
+        const float e_old = ex2_approx(fmaf(at, a, b));       // the bits the sums above hold for this element
+        const float z_old = at * zs;
+        float z_new = head_phi_once(ep.hm, at * isc) * s_eff;  // inside [lo, hi]: no clamp to apply
+        if (!isfinite(z_new)) { z_new = 0.f; st.saw_nan = true; }
+        const float e_new = exp2f((z_new - s_eff) * LOG2E);
+        st.sumexp += e_new - e_old;
+        st.sumexp2 += fmaf(e_new, e_new, -(e_old * e_old));
+        st.sumz += z_new - z_old;
+        st.ztgt = z_new;
+        // the row maximum with the exchanged element, first index wins (the element-wise order)
+#pragma unroll
+        for (int j = 0; j < SC; ++j) {
+          const float z = (j == jt) ? z_new : v[j] * zs;
+          if (z > st.best) { st.best = z; st.bestidx = cls0 + j; }
+        }
       }
     } else {
       // the margin touches ONE element of the slice: evaluate phi once (its acos / cos code is large; 32 inlined
@@ -244,6 +276,7 @@ struct XwBwdGTT {
     uint16_t* GT; int64_t ldgt; // G^T[class of this launch, batch row]
     float* r_part; int64_t ldr; // [2 * m_groups, ldr]: one partial per (row group, column half)
     int gt_hint;                // L2 policy of the G^T stores (K3b and K3c read them next): 0 none, 2 evict_last
+    int whole_slice_targets;    // tunable "target_patch" = 0: a slice with a target element goes the element-wise way (round 1)
     B200F_PROBE_FIELD           // probe builds only: 2 = no G^T stores (WRONG results)
   };
   struct State { float gs, r; int cls; bool row_ok; uint64_t pol; };
@@ -307,8 +340,17 @@ struct XwBwdGTT {
     int lab_l;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(lab_l) : "r"(smem_u32(tl + (it.lane & (SC - 1)))));
     const int c_w0 = st.cls - it.lane;
-    bool careful = !(s_eff > 0.f) || (lab_l >= c_w0 && lab_l < c_w0 + 32) || !(fabsf(amax) * isc <= hi);
+    // Element-wise path only for slices that need the clamp.  Target elements (a batch row of this slice labelled with one
+    // of the warp's 32 classes: 0.5 % of the slices at cfg3, but 64 % of the tiles then waited for a warp in that path --
+    // K3a 71.5 us against 62.7 us with the labels out of range, tools/careful_probe.py) go through the fast path like any
+    // other element and are PATCHED behind the slice's stores (below): the lane that checked the column hands (column,
+    // class) to the lane that owns the class, which overwrites its one fp16 element and corrects its r sum.  The patch
+    // sits after the hot code so that the phi / dphi call costs the slices without a target nothing.
+    const bool lab_hit = it.lane < SC && lab_l >= c_w0 && lab_l < c_w0 + 32;
+    bool careful = !(s_eff > 0.f) || !(fabsf(amax) * isc <= hi) || (lab_hit && ep.whole_slice_targets);
     careful = __any_sync(0xffffffffu, careful);
+    // columns of this slice whose label is one of the warp's classes (lane j < SC checked column j): patched after the stores
+    unsigned hits = careful ? 0u : __ballot_sync(0xffffffffu, lab_hit);
     float racc = 0.f;
     if (!careful) {
       float r4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -353,6 +395,29 @@ struct XwBwdGTT {
 #pragma unroll
         for (int j = 0; j < SC; ++j)
           if (b0 + j < p.B) gdst[j] = (uint16_t)(pack_f16(g[j], 0.f) & 0xffff);
+      }
+    }
+    while (hits) {                                            // warp-uniform, usually zero trips
+      const int src = __ffs(hits) - 1;
+      hits &= hits - 1;
+      const int lab_s = __shfl_sync(0xffffffffu, lab_l, src);          // column src of the slice is labelled lab_s
+      // the accumulator of (my class, that column) again from TMEM: the stage is still ours, and the cold code then does
+      // not index the slice's registers (a select chain over v[] here cost the hot path ~3 us per kernel)
+      const float vt = tmem_ld1(it.taddr0 + (uint32_t)(col0 + src));
+      if (st.row_ok && st.cls == lab_s) {
+        const float bb = scratch[col0 + src];
+        const float g_old = fmaf(gs, ex2_approx(fmaf(vt, a, bb)), -gq);    // the bits the fast path stored and summed
+        float tv, f;
+        head_phi_dphi(ep.hm, vt * isc, &tv, &f);              // inside [lo, hi]: no clamp to apply
+        float z = tv * s_eff;
+        if (!isfinite(z)) { z = 0.f; f = 0.f; }
+        const float pr = exp2f(fmaf(z, LOG2E, bb));
+        const float q = (1.0f - ep.ls_eps) + q_off;
+        const float gn = fminf(fmaxf(gs * (pr - q) * f, -65504.f), 65504.f);
+        st.r = fmaf(gn - g_old, vt, st.r);
+        const int64_t bt = (int64_t)it.group * p_tn(p) + col0 + src;
+        if (bt < p.B && !(B200F_PROBE_ON(ep, 2) && gn != 12345.678f))
+          ep.GT[(int64_t)st.cls * ep.ldgt + bt] = (uint16_t)(pack_f16(gn, 0.f) & 0xffff);
       }
     }
   }
