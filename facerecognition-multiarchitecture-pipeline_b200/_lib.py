@@ -39,7 +39,8 @@ class HeadCfg(Structure):
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, _LIB_NAME)
+    """The in-tree library, or the one B200FACE_LIB names (tools/ load instrumented builds of the same sources)."""
+    return os.environ.get("B200FACE_LIB") or os.path.join(_HERE, _LIB_NAME)
 
 
 _lib = None

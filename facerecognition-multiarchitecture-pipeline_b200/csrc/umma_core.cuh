@@ -155,6 +155,22 @@ __device__ __forceinline__ void tma_load_2d_pair_hint(void* smem_dst, const CUte
       : "memory");
 }
 
+// ---- TMA store (shared -> global), bulk async-group completion ---------------------------------------
+// The issuing THREAD owns the group: it commits after the store and waits (".read": the source may be overwritten;
+// without it: the global writes are complete) before reusing the staging or leaving the kernel.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* m, const void* smem_src, int c0, int c1, uint64_t pol) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "l"(pol) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ---- descriptors -------------------------------------------------------------------------------
 // Shared-memory matrix descriptor (64-bit), SWIZZLE_128B canonical layouts:
 //   bits [0,14)  start address >> 4        bits [16,30) leading-dim byte offset >> 4

@@ -57,6 +57,22 @@ static int make_tmap(CUtensorMap* m, const void* base, int64_t inner, int64_t ou
   if (r != CUDA_SUCCESS) return fail(B200F_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   return B200F_OK;
 }
+// fp32 matrix [outer, inner] (row stride ld floats) for TMA tensor STORES of [box_outer x box_inner] blocks
+static int make_tmap_f32(CUtensorMap* m, const void* base, int64_t inner, int64_t outer, int64_t ld, int box_inner, int box_outer,
+                         CUtensorMapSwizzle swz) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(B200F_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld % 4))
+    return fail(B200F_ERR_ARG, "TMA store target must be 16B aligned with a row stride that is a multiple of 4 floats");
+  cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(B200F_ERR_CUDA, "cuTensorMapEncodeTiled (fp32) failed (%d)", (int)r);
+  return B200F_OK;
+}
 // operand whose rows are the m/n index and whose contiguous axis is k
 static int tmap_kmajor(CUtensorMap* m, const void* base, int64_t rows, int64_t K, int64_t ld, int box_rows) {
   return make_tmap(m, base, K, rows, ld, BLOCK_K, box_rows);
@@ -211,12 +227,14 @@ static std::atomic<int> g_l2_hints{6};
 static std::atomic<int> g_k2_groups{1};             // K2: epilogue groups
 static std::atomic<int> g_k3b_groups{1};            // K3b: 2 = two epilogue groups on 16-feature slices, 1 = one group on 32
 static std::atomic<int> g_early{1};                 // K3a / K3c start their loads and MMAs without waiting for the predecessor grid
-static std::atomic<int> g_epi_groups{2};            // K3a: 2 = two epilogue groups of 8 warps (16-column slices), 1 = one group
+static std::atomic<int> g_epi_groups{1};            // K3a: 2 = two epilogue groups of 8 warps on alternating tiles (16-column slices), 1 = one group of 8,
+                                                    //      4 = one group of 16 warps on every tile (column quarters)
 #ifdef B200F_PROBES                                 // tools/ builds only; the shipped library has neither the branch nor the switch
 static std::atomic<int> g_k3a_ablate{0};            // probe: 2 = no G^T stores (WRONG results)
 static std::atomic<int> g_k3b_ablate{0};            // probe: 1 = no w_hat loads, 2 = no dW stores (WRONG results)
 #endif
 static std::atomic<int> g_k3b_reverse{1};
+static std::atomic<int> g_k3b_tma_store{0};         // tunable "k3b_tma_store": 1 = dW through shared-memory staging + TMA tensor stores (XwDwTS)
 static std::atomic<int> g_target_patch{1};          // tunable "target_patch": 1 = K2 / K3a exchange a target element in place, 0 = whole slice element-wise
 static std::atomic<int> g_x_whole{0};               // tunable "x_whole": 1 = first MMA of an item waits for the whole resident operand
 // "stage_events" tunable: record a CUDA event pair around each GEMM kernel of the head on the launching stream
@@ -258,7 +276,7 @@ static int xw_set_smem() {
   int dev = 0;
   B200F_CUDA_OK(cudaGetDevice(&dev));
   if (done_dev != dev) {
-    B200F_CUDA_OK(cudaFuncSetAttribute(XwKernel<PAIR, MODE, Epi>::fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XW_SMEM_BYTES));
+    B200F_CUDA_OK(cudaFuncSetAttribute(XwKernel<PAIR, MODE, Epi>::fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xw_smem_bytes<Epi>()));
     done_dev = dev;
   }
   return B200F_OK;
@@ -266,6 +284,9 @@ static int xw_set_smem() {
 
 // clusters of `pair` CTAs that can be co-resident (1 CTA per SM: 227 KB of shared memory each)
 static int xw_max_clusters(int pair) {
+#ifdef B200F_TIMELINE     // instrumented builds only: fewer clusters, to tell a per-SM limit from a chip-wide one
+  if (const char* e = getenv("B200F_TL_CLUSTERS")) { const int n = atoi(e); if (n > 0) return n; }
+#endif
   if (pair == 1) return num_sms();
   static thread_local int cached_dev = -1, cached = 0;
   int dev = 0;
@@ -315,20 +336,33 @@ static XwPlan xw_plan(int64_t B, int64_t C, int pair, int max_chunks = 0) {
 // K1 of the streamed rows inside the kernel (XwParams::prep_*; policies with kPrepWarps > 0)
 struct XwPrepArgs { const void* src; int f32; uint16_t* dst; float* inv; unsigned int* ready; float eps, scale; };
 
+#ifdef B200F_TIMELINE
+// tools/timeline_probe.py: the (which)-th X-stationary launch after this call stamps its timeline into buf (XW_TL)
+static unsigned long long* g_tl_buf = nullptr;
+static int g_tl_which = -1, g_tl_count = 0;
+extern "C" int b200f_xw_timeline(void* buf, int which) {
+  g_tl_buf = static_cast<unsigned long long*>(buf); g_tl_which = which; g_tl_count = 0;
+  return B200F_OK;
+}
+#endif
+
 template <int PAIR, int MODE, class Epi>
 static int launch_xw(const CUtensorMap& tx, const CUtensorMap& tw, const XwPlan& q, int64_t B, int64_t C, int D,
                      const typename Epi::Params& ep, cudaStream_t st, const char* what, uint32_t fmt = FMT_F16,
                      bool reverse = false, const void* w_base = nullptr, int64_t w_row_bytes = 0, bool early = false,
-                     int w_hint = 0, const XwPrepArgs* prep = nullptr) {
+                     int w_hint = 0, const XwPrepArgs* prep = nullptr, int prefetch_tiles = -1) {
   int rc = xw_set_smem<PAIR, MODE, Epi>(); if (rc) return rc;
   XwParams p{};
   p.B = (int)B; p.C = (int)C; p.D = D;
   p.kb_count = (int)ceil_div(D, XW_K);
   p.m_groups = q.m_groups; p.n_tiles = q.n_tiles; p.n_chunks = q.n_chunks;
-  p.prefetch = (w_base != nullptr) ? g_prefetch.load(std::memory_order_relaxed) : 0;
+  p.prefetch = (w_base != nullptr) ? (prefetch_tiles >= 0 ? prefetch_tiles : g_prefetch.load(std::memory_order_relaxed)) : 0;
   p.w_base = w_base; p.w_row_bytes = w_row_bytes;
   p.early_operands = (early && g_early.load(std::memory_order_relaxed)) ? 1 : 0;
   p.w_hint = w_hint;
+#ifdef B200F_TIMELINE
+  p.tl = (g_tl_buf != nullptr && g_tl_count++ == g_tl_which) ? g_tl_buf : nullptr;
+#endif
   p.tn = XW_WROWS * PAIR;
   p.reverse = reverse ? 1 : 0;
   p.x_whole = g_x_whole.load(std::memory_order_relaxed);
@@ -343,7 +377,7 @@ static int launch_xw(const CUtensorMap& tx, const CUtensorMap& tw, const XwPlan&
   }
   p.idesc = make_idesc(fmt, fmt, MODE == XW_MK, MODE == XW_SWAP_MK, XW_M * PAIR, XW_WROWS * PAIR);   // A = resident, except SWAP modes
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)q.grid); cfg.blockDim = dim3((unsigned)xw_threads<Epi>()); cfg.dynamicSmemBytes = XW_SMEM_BYTES; cfg.stream = st;
+  cfg.gridDim = dim3((unsigned)q.grid); cfg.blockDim = dim3((unsigned)xw_threads<Epi>()); cfg.dynamicSmemBytes = xw_smem_bytes<Epi>(); cfg.stream = st;
   cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = PAIR; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
@@ -650,30 +684,32 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
     auto run_k3a = [&]() -> int {
     CUtensorMap tw_k;
     int rc = tmap_kmajor(&tw_k, wc, cnt, D, D, XW_WROWS); if (rc) return rc;
-    XwBwdGT::Params eg{};
-    eg.label = label; eg.lse = lse; eg.grad4 = grad4; eg.class_offset = class_offset + c0;
-    eg.hm = HeadMath{cfg->m_eff, cfg->s_eff, cfg->easy_margin};
-    eg.ls_eps = cfg->label_smoothing; eg.inv_Ctot = 1.0f / (float)cfg->num_classes_total; eg.inv_scale = 1.0f / (S * S);
-    eg.GT = G; eg.ldgt = pl.ldg; eg.r_part = r_part; eg.ldr = pl.Cc;
-    eg.gt_hint = (hints & 2) ? 2 : 0;
-    eg.whole_slice_targets = g_target_patch.load(std::memory_order_relaxed) ? 0 : 1;
-    const int k3a_whint = (hints & 1) ? 1 : 0;
+    const int k3a_mode = g_epi_groups.load(std::memory_order_relaxed);
+    const int hints_k3a = hints;
+    auto fill = [&](auto& e) {
+      e.label = label; e.lse = lse; e.grad4 = grad4; e.class_offset = class_offset + c0;
+      e.hm = HeadMath{cfg->m_eff, cfg->s_eff, cfg->easy_margin};
+      e.ls_eps = cfg->label_smoothing; e.inv_Ctot = 1.0f / (float)cfg->num_classes_total; e.inv_scale = 1.0f / (S * S);
+      e.GT = G; e.ldgt = pl.ldg; e.r_part = r_part; e.ldr = pl.Cc;
+      e.gt_hint = (hints_k3a & 2) ? 2 : 0;
+      e.whole_slice_targets = g_target_patch.load(std::memory_order_relaxed) ? 0 : 1;
 #ifdef B200F_PROBES
-    eg.ablate = g_k3a_ablate.load(std::memory_order_relaxed);
+      e.ablate = g_k3a_ablate.load(std::memory_order_relaxed);
 #endif
+    };
+    const int k3a_whint = (hints & 1) ? 1 : 0;
     { B200F_NVTX("K3a logit gradient (recompute + G^T)");
     stage_event(EV_K3A, false, st);
-    if (g_epi_groups.load(std::memory_order_relaxed) == 2) {
-      XwBwdGT2::Params e2{};
-      e2.label = eg.label; e2.lse = eg.lse; e2.grad4 = eg.grad4; e2.class_offset = eg.class_offset; e2.hm = eg.hm;
-      e2.ls_eps = eg.ls_eps; e2.inv_Ctot = eg.inv_Ctot; e2.inv_scale = eg.inv_scale; e2.GT = eg.GT; e2.ldgt = eg.ldgt;
-      e2.r_part = eg.r_part; e2.ldr = eg.ldr; e2.gt_hint = eg.gt_hint; e2.whole_slice_targets = eg.whole_slice_targets;
-#ifdef B200F_PROBES
-      e2.ablate = eg.ablate;
-#endif
+    if (k3a_mode == 4) {
+      XwBwdGT4::Params e4{}; fill(e4);
+      rc = (qg.pair == 2) ? launch_xw<2, XW_SWAP, XwBwdGT4>(tx_k, tw_k, qg, B, cnt, D, e4, st, "umma K3a logit-grad (cta pair, 16 warps per tile)", FMT_F16, false, wc, wrb, true, k3a_whint)
+                          : launch_xw<1, XW_SWAP, XwBwdGT4>(tx_k, tw_k, qg, B, cnt, D, e4, st, "umma K3a logit-grad (16 warps per tile)", FMT_F16, false, wc, wrb, true, k3a_whint);
+    } else if (k3a_mode == 2) {
+      XwBwdGT2::Params e2{}; fill(e2);
       rc = (qg.pair == 2) ? launch_xw<2, XW_SWAP, XwBwdGT2>(tx_k, tw_k, qg, B, cnt, D, e2, st, "umma K3a logit-grad (cta pair, 2 epilogue groups)", FMT_F16, false, wc, wrb, true, k3a_whint)
                           : launch_xw<1, XW_SWAP, XwBwdGT2>(tx_k, tw_k, qg, B, cnt, D, e2, st, "umma K3a logit-grad (2 epilogue groups)", FMT_F16, false, wc, wrb, true, k3a_whint);
     } else {
+      XwBwdGT::Params eg{}; fill(eg);
       rc = (qg.pair == 2) ? launch_xw<2, XW_SWAP, XwBwdGT>(tx_k, tw_k, qg, B, cnt, D, eg, st, "umma K3a logit-grad (cta pair)", FMT_F16, false, wc, wrb, true, k3a_whint)
                           : launch_xw<1, XW_SWAP, XwBwdGT>(tx_k, tw_k, qg, B, cnt, D, eg, st, "umma K3a logit-grad", FMT_F16, false, wc, wrb, true, k3a_whint);
     }
@@ -682,7 +718,7 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
     // --- K3b: dW[c0 + c, d] = inv_nw_c (sum_b G^T[c, b] x_hat[b, d] - w_hat[c, d] r_c), class-major (the thread owns a
     //     class row), normalise-backward fused; its coefficients { inv_nw_c / (S g_scale), r_c } are formed in the epilogue
     //     from K3a's partials (CoefSrc)
-    const CoefSrc coef{r_part, qg.m_groups * 2, pl.Cc, inv_nw, grad4, S};
+    const CoefSrc coef{r_part, qg.m_groups * (g_epi_groups.load(std::memory_order_relaxed) == 4 ? 4 : 2), pl.Cc, inv_nw, grad4, S};
     auto run_k3b = [&]() -> int {
     int rc = B200F_OK;
     int n_sq_used = 0;
@@ -694,7 +730,21 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
       const XwPlan qw = xw_plan(D, cnt, qg.pair);
       const bool k3b_rev = g_k3b_reverse.load(std::memory_order_relaxed) != 0;   // read K3a's freshest G^T rows first
       const int gt_lhint = (hints & 32) ? 2 : 0;
-      if (g_k3b_groups.load(std::memory_order_relaxed) == 2) {
+      if (g_k3b_tma_store.load(std::memory_order_relaxed) != 0 && (D % 4) == 0) {
+        XwDwTS::Params ew{};
+        rc = make_tmap(&ew.tm_wh, wc, D, cnt, D, 32, 32, CU_TENSOR_MAP_SWIZZLE_NONE); if (rc) return rc;
+        // the map covers THIS launch's class rows only: a warp's rows beyond the chunk are clipped, not written as zeros
+        rc = make_tmap_f32(&ew.tm_dw, dw + c0 * (int64_t)D, D, cnt, D, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B); if (rc) return rc;
+        ew.coef = coef; ew.dw = dw; ew.c0 = c0; ew.ld = D; ew.sq_part = sq_part;
+        ew.dw_hint = (hints & 4) ? 1 : 0; ew.wh_hint = (hints & 8) ? 1 : 0;
+        n_sq_used = qw.items * qw.pair * 1 * XW_EPI_WARPS;
+#ifdef B200F_PROBES
+        ew.ablate = g_k3b_ablate.load(std::memory_order_relaxed);
+#endif
+        // two ring stages for G^T: its tiles are pulled into L2 two ahead so that the ring's loads are L2 hits
+        rc = (qw.pair == 2) ? launch_xw<2, XW_SWAP_MK, XwDwTS>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW class-major, TMA stores (cta pair)", FMT_F16, k3b_rev, G, pl.ldg * 2, false, gt_lhint, nullptr, 2)
+                            : launch_xw<1, XW_SWAP_MK, XwDwTS>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW class-major, TMA stores", FMT_F16, k3b_rev, G, pl.ldg * 2, false, gt_lhint, nullptr, 2);
+      } else if (g_k3b_groups.load(std::memory_order_relaxed) == 2) {
         XwDwT2::Params ew{};
         rc = make_tmap(&ew.tm_wh, wc, D, cnt, D, 16, 32, CU_TENSOR_MAP_SWIZZLE_NONE); if (rc) return rc;
         ew.coef = coef; ew.dw = dw; ew.c0 = c0; ew.ld = D; ew.sq_part = sq_part;
@@ -1065,12 +1115,13 @@ int b200f_set_tunable(const char* name, int value) {
   if (n == "k3b_groups") { if (value != 1 && value != 2) return g_k3b_groups.load(); return g_k3b_groups.exchange(value); }
   if (n == "gallery_compact") { if (value != 0 && value != 1) return g_gallery_compact.load(); return g_gallery_compact.exchange(value); }
   if (n == "early") { if (value != 0 && value != 1) return g_early.load(); return g_early.exchange(value); }
-  if (n == "epi_groups") { if (value != 1 && value != 2) return g_epi_groups.load(); return g_epi_groups.exchange(value); }
+  if (n == "epi_groups") { if (value != 1 && value != 2 && value != 4) return g_epi_groups.load(); return g_epi_groups.exchange(value); }
 #ifdef B200F_PROBES
   // probes that make the backward skip memory traffic (WRONG results): -DB200F_PROBES builds only (tools/)
   if (n == "k3a_ablate") { if (value < 0) return g_k3a_ablate.load(); return g_k3a_ablate.exchange(value); }
   if (n == "k3b_ablate") { if (value < 0) return g_k3b_ablate.load(); return g_k3b_ablate.exchange(value); }
 #endif
+  if (n == "k3b_tma_store") { if (value != 0 && value != 1) return g_k3b_tma_store.load(); return g_k3b_tma_store.exchange(value); }
   if (n == "k3b_reverse") { if (value != 0 && value != 1) return g_k3b_reverse.load(); return g_k3b_reverse.exchange(value); }
   if (n == "xw_prefetch") { if (value < 0) return g_prefetch.load(); return g_prefetch.exchange(value); }
   if (n == "g_chunk_mb") { if (value < 1) return g_chunk_mb.load(); return g_chunk_mb.exchange(value); }

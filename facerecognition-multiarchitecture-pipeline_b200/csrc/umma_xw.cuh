@@ -98,6 +98,10 @@ __device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
 __device__ __forceinline__ void epi_bar_sync(int grp = 0) {
   asm volatile("bar.sync %0, 256;" ::"r"(1 + grp) : "memory");
 }
+// ... over a group of NT threads (policies with kEpiSplit = 4: 512)
+template <int NT> __device__ __forceinline__ void epi_bar_sync_n(int grp) {
+  asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(NT) : "memory");
+}
 
 // X_MN / W_MN: layout of the resident ("x") and the streamed ("w") operand: false = K-major (rows x k, row-major),
 //   true = MN-major (stored [k, rows] row-major).  The dW stage runs as dW^T[d, c] = sum_b x_hat[b, d] * G^T[c, b]:
@@ -142,7 +146,24 @@ struct XwParams {
   unsigned int* prep_ready;             // [ceil(C / 128)] rows finished per 128-row block
   float prep_eps, prep_scale;
   int prep_cw;                          // chunks whose tiles are consumed at the same time (clusters / row groups)
+#ifdef B200F_TIMELINE
+  unsigned long long* tl;               // -DB200F_TIMELINE builds (tools/timeline_probe.py): SM clock stamps, see XW_TL
+#endif
 };
+
+// Timeline stamps (-DB200F_TIMELINE builds only; the shipped library has neither the field nor the stores): the first two
+// clusters record clock64() per (CTA, role, tile of the CTA, event) -- roles: 0 MMA issuer {wait for the accumulator stage,
+// stage granted, first ring stage of the tile full, last MMA issued}, 1 / 2 first / last epilogue warp {wait for the
+// accumulator, accumulator full, slices done}, 3 TMA producer {first slot wait of the tile, last load issued}.
+#ifdef B200F_TIMELINE
+#define XW_TL(cond, role, tile, k)                                                                                   \
+  do {                                                                                                               \
+    if ((cond) && p.tl != nullptr && blockIdx.x < 4 && (tile) < 32)                                                   \
+      p.tl[((((int)blockIdx.x * 4 + (role)) * 32 + (int)(tile)) << 2) + (k)] = (unsigned long long)clock64();         \
+  } while (0)
+#else
+#define XW_TL(cond, role, tile, k) do {} while (0)
+#endif
 
 struct XwItem;
 struct XwParams;
@@ -153,8 +174,18 @@ template <class Epi> struct xw_slice_wants_scratch<Epi, decltype((void)Epi::kSli
 // A policy may trade ring stages for warp-private staging ("aux") space: with kRingStages = S < XW_STAGES the
 // streamed operand gets S stages and every epilogue warp owns (XW_STAGES - S) * 16 KB / 8 bytes at XwItem::aux plus two
 // mbarriers (count 1) at XwItem::aux_bar -- e.g. for epilogue operands it fetches with its own TMA loads.
+#ifdef B200F_TL_RING     // instrumented builds only (tools/build_timeline.sh): a shorter ring, to tell latency from throughput
+template <class Epi, class = void> struct xw_ring_stages { static constexpr int value = B200F_TL_RING; };
+#else
 template <class Epi, class = void> struct xw_ring_stages { static constexpr int value = XW_STAGES; };
+#endif
 template <class Epi> struct xw_ring_stages<Epi, decltype((void)Epi::kRingStages)> { static constexpr int value = Epi::kRingStages; };
+
+// A policy may ask for shared memory beyond XW_SMEM_BYTES (kExtraSmem bytes behind the barriers) and lay out its own
+// warp-private areas (aux_layout): the dW kernel with TMA stores keeps boxes AND store staging per warp.
+template <class Epi, class = void> struct xw_extra_smem { static constexpr int value = 0; };
+template <class Epi> struct xw_extra_smem<Epi, decltype((void)Epi::kExtraSmem)> { static constexpr int value = Epi::kExtraSmem; };
+template <class Epi> constexpr size_t xw_smem_bytes() { return XW_SMEM_BYTES + (size_t)xw_extra_smem<Epi>::value; }
 
 // Epilogue groups.  A policy with kEpiGroups = 2 runs TWO groups of 8 epilogue warps (576 threads, <= 112 registers):
 // group g takes the tiles whose running number n has n % 2 == g, i.e. with two accumulator stages each group owns one
@@ -164,6 +195,14 @@ template <class Epi> struct xw_ring_stages<Epi, decltype((void)Epi::kRingStages)
 // record per (row, chunk, group).
 template <class Epi, class = void> struct xw_epi_groups { static constexpr int value = 1; };
 template <class Epi> struct xw_epi_groups<Epi, decltype((void)Epi::kEpiGroups)> { static constexpr int value = Epi::kEpiGroups; };
+// Column split of a tile inside ONE group.  Default 2: eight warps, two per TMEM lane quadrant, each half of the columns.
+// kEpiSplit = 4: SIXTEEN warps on the same tile, four per quadrant, each a quarter of the columns.  Against two groups on
+// alternating tiles (same warp count): a stage is held for M + hand-over + E, and there are only two stages, so the period
+// per tile is (M + h + E) / 2 either way -- but with all warps on one tile E halves (the epilogue is latency-bound, not
+// issue-bound: 43 % issue slots used), while with alternating groups it does not.
+template <class Epi, class = void> struct xw_epi_split { static constexpr int value = 2; };
+template <class Epi> struct xw_epi_split<Epi, decltype((void)Epi::kEpiSplit)> { static constexpr int value = Epi::kEpiSplit; };
+template <class Epi> __host__ __device__ constexpr int xw_group_warps() { return 4 * xw_epi_split<Epi>::value; }
 // columns per slice() call: 32 (default) or 16 (kSliceCols = 16)
 template <class Epi, class = void> struct xw_slice_cols { static constexpr int value = 32; };
 template <class Epi> struct xw_slice_cols<Epi, decltype((void)Epi::kSliceCols)> { static constexpr int value = Epi::kSliceCols; };
@@ -171,7 +210,7 @@ template <class Epi> struct xw_slice_cols<Epi, decltype((void)Epi::kSliceCols)> 
 template <class Epi, class = void> struct xw_prep_warps { static constexpr int value = 0; };
 template <class Epi> struct xw_prep_warps<Epi, decltype((void)Epi::kPrepWarps)> { static constexpr int value = Epi::kPrepWarps; };
 template <class Epi> __host__ __device__ constexpr int xw_threads() {
-  return 64 + 32 * XW_EPI_WARPS * xw_epi_groups<Epi>::value + 32 * xw_prep_warps<Epi>::value;
+  return 64 + 32 * xw_group_warps<Epi>() * xw_epi_groups<Epi>::value + 32 * xw_prep_warps<Epi>::value;
 }
 // registers per thread: 1 CTA per SM either way (shared memory).  The register file is handed out per FOUR warps:
 // 10 warps count as 12 (168 registers), 18 warps as 20 (96 registers; 112 is refused at launch: "too many resources").
@@ -408,6 +447,7 @@ struct XwItem {                         // what an epilogue thread knows about i
   int64_t row;                          // global row of x owned by this thread
   uint32_t taddr0;                      // TMEM address of this thread's lane, column 0 of the current accumulator stage (SWAP mode)
   uint8_t* aux;                         // this warp's staging bytes (nullptr unless the policy reserves them)
+  uint8_t* stage;                       // this warp's store staging (policies with kExtraSmem: set by their aux_layout)
   uint64_t* aux_bar;                    // its two mbarriers
   mutable uint32_t aux_phase;           // their parity bits; lives across the items of the kernel
 };
@@ -455,9 +495,15 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
   uint64_t* acc_empty = acc_full + XW_MAX_ACC;               // [ACC] epilogue (both CTAs) -> MMA (leader)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + XW_NUM_BARS);
   uint8_t* aux = ring + (size_t)STAGES * XW_TILE_BYTES;       // (XW_STAGES - STAGES) x 16 KB of warp-private staging
-  constexpr int EPI_WARPS_ALL = XW_EPI_WARPS * xw_epi_groups<Epi>::value;
-  uint64_t* aux_bar = reinterpret_cast<uint64_t*>(scratch + XW_SCRATCH_FLOATS) - 2 * EPI_WARPS_ALL;   // 2 per epilogue
-                                                              // warp, at the end of the scratch area
+  constexpr int SPLIT = xw_epi_split<Epi>::value;             // column split of a tile inside a group
+  constexpr int GW = xw_group_warps<Epi>();                  // epilogue warps of one group
+  static_assert(SPLIT == 2 || SPLIT == 4, "column split");
+  constexpr int EPI_WARPS_ALL = GW * xw_epi_groups<Epi>::value;
+  constexpr int EXTRA = xw_extra_smem<Epi>::value;
+  uint8_t* extra = reinterpret_cast<uint8_t*>(bars) + 256;    // EXTRA bytes behind the barrier block
+  // 2 mbarriers per epilogue warp: at the end of the scratch area, or (policies that use all of it) at the end of `extra`
+  uint64_t* aux_bar = (EXTRA > 0) ? reinterpret_cast<uint64_t*>(extra + EXTRA - 256)
+                                  : reinterpret_cast<uint64_t*>(scratch + XW_SCRATCH_FLOATS) - 2 * EPI_WARPS_ALL;
   constexpr int AUX_WARP_BYTES = (XW_STAGES - STAGES) * XW_TILE_BYTES / EPI_WARPS_ALL;
 
   const int warp = threadIdx.x >> 5;
@@ -473,7 +519,7 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
     for (int kb = 0; kb < XW_MAX_KB; ++kb) mbar_init(&x_full[kb], PAIR);
     mbar_init(x_empty, 1);
     for (int s = 0; s < XW_STAGES; ++s) { mbar_init(&full_bar[s], PAIR); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < ACC; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], PAIR * XW_EPI_WARPS); }
+    for (int s = 0; s < ACC; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], PAIR * GW); }
     if (STAGES < XW_STAGES) for (int s = 0; s < 2 * EPI_WARPS_ALL; ++s) mbar_init(&aux_bar[s], 1);
     fence_barrier_init();
   }
@@ -510,6 +556,7 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
       int stage = 0; uint32_t phase = 0;
       int item_no = 0;
       bool ok = true;
+      [[maybe_unused]] int tl_tile = 0;
       for (int item = cluster_id; item < items && ok; item += n_clusters, ++item_no) {
         const int g = item % p.m_groups, chunk = item / p.m_groups;
         const int t_begin = (int)((int64_t)chunk * p.n_tiles / p.n_chunks);
@@ -552,9 +599,12 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
             xw_wait_ready(p.prep_ready + (n0 >> 7), (unsigned int)(left < XW_WROWS ? left : XW_WROWS));
             asm volatile("fence.proxy.async;" ::: "memory");
           }
+          XW_TL(leader, 3, tl_tile, 0);
           for (int kb = 0; kb < p.kb_count; ++kb) {
+            XW_TL(leader && tl_tile == 3, 3, 16 + kb, 0);
             ok = mbar_wait(&empty_bar[stage], phase ^ 1);
             if (!ok) break;
+            XW_TL(leader && tl_tile == 3, 3, 16 + kb, 1);
             if (leader) {
               if (kb == 0) prefetch_tile(ti + p.prefetch);
               if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(PAIR * XW_TILE_BYTES));
@@ -570,6 +620,8 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
+          XW_TL(leader, 3, tl_tile, 1);
+          ++tl_tile;
         }
       }
       // do not leave while the leader's last commit may still signal this CTA's barriers
@@ -587,6 +639,7 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
       int acc = 0; uint32_t acc_phase = 0;
       int item_no = 0;
       bool ok = true;
+      [[maybe_unused]] int tl_tile = 0;
       // K-major: +32 B per 16 k; MN-major: +16 k-rows of 128 B, LBO = next 64-wide row block (8 KB)
       const uint32_t x_kstep = X_MN ? 2048u >> 4 : 32u >> 4;     // descriptor address units (16 B)
       const uint32_t w_kstep = W_MN ? 2048u >> 4 : 32u >> 4;
@@ -597,9 +650,11 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
         const int t_begin = (int)((int64_t)chunk * p.n_tiles / p.n_chunks);
         const int t_end = (int)((int64_t)(chunk + 1) * p.n_tiles / p.n_chunks);
         for (int t = t_begin; t < t_end && ok; ++t) {
+          XW_TL(leader, 0, tl_tile, 0);
           ok = mbar_wait(&acc_empty[acc], acc_phase ^ 1);
           if (!ok) break;
           tc_fence_after_sync();
+          XW_TL(leader, 0, tl_tile, 1);
           const uint32_t d_tmem = tmem_base + (uint32_t)acc * ACC_STRIDE;
           for (int kb = 0; kb < p.kb_count; ++kb) {
             if (t == t_begin) {                                   // the item's resident operand, k-block by k-block
@@ -613,6 +668,8 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
             ok = mbar_wait(&full_bar[stage], phase);
             if (!ok) break;
             tc_fence_after_sync();
+            XW_TL(leader && kb == 0, 0, tl_tile, 2);
+            XW_TL(leader && tl_tile == 3, 0, 16 + kb, 0);
             if (leader) {
               const uint64_t dx = desc_x0 + (uint64_t)((uint32_t)kb * (XW_TILE_BYTES >> 4));
               const uint64_t dw = desc_w0 + (uint64_t)((uint32_t)stage * (XW_TILE_BYTES >> 4));
@@ -626,10 +683,13 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
               }
               xw_commit<PAIR>(&empty_bar[stage]);
             }
+            XW_TL(leader && tl_tile == 3, 0, 16 + kb, 1);
             __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
           if (!ok) break;
+          XW_TL(leader, 0, tl_tile, 3);
+          ++tl_tile;
           if (leader) xw_commit<PAIR>(&acc_full[acc]);
           __syncwarp();
           if (++acc == ACC) { acc = 0; acc_phase ^= 1; }
@@ -644,14 +704,17 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
     constexpr int SC = xw_slice_cols<Epi>::value;
     static_assert(EG >= 1 && EG <= XW_MAX_EPI_GROUPS && (SC == 16 || SC == 32), "epilogue geometry");
     XwItem it;
-    it.rank = rank; it.grp = (warp - 2) / XW_EPI_WARPS; it.ew = (warp - 2) % XW_EPI_WARPS;
+    it.rank = rank; it.grp = (warp - 2) / GW; it.ew = (warp - 2) % GW;
     it.quad = warp & 3; it.half = it.ew >> 2; it.lane = lane;
-    it.aux = (STAGES < XW_STAGES) ? aux + (size_t)(it.grp * XW_EPI_WARPS + it.ew) * AUX_WARP_BYTES : nullptr;
-    it.aux_bar = aux_bar + 2 * (it.grp * XW_EPI_WARPS + it.ew); it.aux_phase = 0; it.first_tile = 0;
+    it.aux = (STAGES < XW_STAGES) ? aux + (size_t)(it.grp * GW + it.ew) * AUX_WARP_BYTES : nullptr;
+    it.stage = nullptr;
+    if constexpr (EXTRA > 0) Epi::aux_layout(it, ring, reinterpret_cast<uint8_t*>(scratch), extra);
+    it.aux_bar = aux_bar + 2 * (it.grp * GW + it.ew); it.aux_phase = 0; it.first_tile = 0;
     float* const gscratch = scratch + it.grp * (XW_SCRATCH_FLOATS / XW_MAX_EPI_GROUPS);   // this group's half of the scratch
     uint32_t tile_no = 0;                                      // running tile number of this CTA (all groups count alike)
     bool ok = true;
-    constexpr int SLICES = TN / 2 / SC;                        // slices per warp per tile
+    constexpr int SLICES = TN / SPLIT / SC;                    // slices per warp per tile
+    static_assert(SLICES >= 2 && SLICES % 2 == 0, "two slices per trip");
     if constexpr (SWAP) {
       // Accumulator lanes = streamed rows (classes), columns = the resident operand's rows (the batch rows of the
       // group): the thread owns ONE class per tile and sees half of the group's batch rows.
@@ -662,16 +725,18 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
         typename Epi::State stt;
         it.first_tile = (EG > 1) ? (int)((it.grp + EG - (tile_no % EG)) % EG) : 0;
         Epi::item_begin(stt, ep, p, it, gscratch, TN);         // per-column tables of the group -> shared memory
-        const int col_base = it.half * (TN / 2);
+        const int col_base = it.half * (TN / SPLIT);
         for (int ti = t_begin; ti < t_end; ++ti) {
           const uint32_t n = tile_no++;
           if (EG > 1 && (int)(n % EG) != it.grp) continue;     // the other group's tile
           const int acc = (int)(n % ACC); const uint32_t acc_phase = (n / ACC) & 1u;
           const int t = p.reverse ? (t_end - 1 - (ti - t_begin)) : ti;
+          XW_TL(lane == 0 && (it.ew == 0 || it.ew == GW - 1), it.ew == 0 ? 1 : 2, n, 0);
           ok = mbar_wait(&acc_full[acc], acc_phase);
           ok = __all_sync(0xffffffffu, ok);
           if (!ok) break;
           tc_fence_after_sync();
+          XW_TL(lane == 0 && (it.ew == 0 || it.ew == GW - 1), it.ew == 0 ? 1 : 2, n, 1);
           it.row = (int64_t)t * TN + rank * XW_WROWS + it.quad * 32 + lane;   // the class this thread owns in tile t
           const uint32_t taddr = tmem_base + (uint32_t)acc * ACC_STRIDE + ((uint32_t)(it.quad * 32) << 16) + (uint32_t)col_base;
           it.taddr0 = taddr - (uint32_t)col_base;
@@ -687,6 +752,7 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
             if (s + 2 < SLICES) tmem_ld32_async(taddr + (uint32_t)(s + 2) * SC, va);
             Epi::slice(stt, ep, p, it, vb, col_base + (s + 1) * SC, gscratch);
           }
+          XW_TL(lane == 0 && (it.ew == 0 || it.ew == GW - 1), it.ew == 0 ? 1 : 2, n, 2);
           tc_fence_before_sync();
           __syncwarp();
           if (lane == 0) {
@@ -711,14 +777,16 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
         if (EG > 1 && (int)(n % EG) != it.grp) continue;       // the other group's tile
         const int acc = (int)(n % ACC); const uint32_t acc_phase = (n / ACC) & 1u;
         const int t = p.reverse ? (t_end - 1 - (ti - t_begin)) : ti;
+        XW_TL(lane == 0 && (it.ew == 0 || it.ew == GW - 1), it.ew == 0 ? 1 : 2, n, 0);
         ok = mbar_wait(&acc_full[acc], acc_phase);
         ok = __all_sync(0xffffffffu, ok);
         if (!ok) break;
         tc_fence_after_sync();
-        const int col_base = it.half * (TN / 2);
+        XW_TL(lane == 0 && (it.ew == 0 || it.ew == GW - 1), it.ew == 0 ? 1 : 2, n, 1);
+        const int col_base = it.half * (TN / SPLIT);
         const uint32_t taddr = tmem_base + (uint32_t)acc * ACC_STRIDE + ((uint32_t)(it.quad * 32) << 16) + (uint32_t)col_base;
         const int cls_base = t * TN + col_base;
-        Epi::tile_begin(stt, ep, p, it, cls_base, (ti + 1 < t_end) ? cls_base + (p.reverse ? -TN : TN) : -1, TN / 2);
+        Epi::tile_begin(stt, ep, p, it, cls_base, (ti + 1 < t_end) ? cls_base + (p.reverse ? -TN : TN) : -1, TN / SPLIT);
         float va[SC], vb[SC];
         tmem_ld32_async(taddr, va);
         // two slices per trip, NOT fully unrolled: the policy code exists twice, not 2 * SLICES times (i-cache)
@@ -731,6 +799,7 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
           if (s + 2 < SLICES) tmem_ld32_async(taddr + (uint32_t)(s + 2) * SC, va);
           if (cls_base + (s + 1) * SC < p.C) xw_call_slice<Epi>(stt, ep, p, it, vb, cls_base + (s + 1) * SC, gscratch);
         }
+        XW_TL(lane == 0 && (it.ew == 0 || it.ew == GW - 1), it.ew == 0 ? 1 : 2, n, 2);
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) {

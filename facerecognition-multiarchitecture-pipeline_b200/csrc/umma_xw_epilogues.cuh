@@ -264,17 +264,19 @@ __device__ __noinline__ void head_phi_dphi(HeadMath hm, float c, float* phi, flo
 #define B200F_PROBE_ON(ep, bit) false
 #endif
 
-template <int EG, int SC>
+template <int EG, int SC, int SPLIT = 2>
 struct XwBwdGTT {
   static constexpr int kEpiGroups = EG;
   static constexpr int kSliceCols = SC;
+  static constexpr int kEpiSplit = SPLIT;     // 4: sixteen warps of ONE group on every tile, a quarter of its columns each
+  static constexpr int kGroupThreads = 32 * 4 * SPLIT;
   struct Params {
     const int64_t* label; const float* lse; const float* grad4;
     int64_t class_offset;       // global id of this launch's class 0
     HeadMath hm;
     float ls_eps, inv_Ctot, inv_scale;
     uint16_t* GT; int64_t ldgt; // G^T[class of this launch, batch row]
-    float* r_part; int64_t ldr; // [2 * m_groups, ldr]: one partial per (row group, column half)
+    float* r_part; int64_t ldr; // [SPLIT * m_groups, ldr]: one partial per (row group, column half / quarter)
     int gt_hint;                // L2 policy of the G^T stores (K3b and K3c read them next): 0 none, 2 evict_last
     int whole_slice_targets;    // tunable "target_patch" = 0: a slice with a target element goes the element-wise way (round 1)
     B200F_PROBE_FIELD           // probe builds only: 2 = no G^T stores (WRONG results)
@@ -283,7 +285,7 @@ struct XwBwdGTT {
 
   static __device__ __forceinline__ void item_begin(State& st, const Params& ep, const XwParams& p, const XwItem& it,
                                                     float* scratch, int TN) {
-    epi_bar_sync(it.grp);                                     // the previous item's readers (of this group) are done
+    epi_bar_sync_n<kGroupThreads>(it.grp);                    // the previous item's readers (of this group) are done
     const int e = it.ew * 32 + it.lane;
     if (e < TN) {
       const int64_t b = (int64_t)it.group * TN + e;
@@ -296,7 +298,7 @@ struct XwBwdGTT {
       scratch[e] = bneg;
       reinterpret_cast<int*>(scratch)[TN + e] = lab;
     }
-    epi_bar_sync(it.grp);
+    epi_bar_sync_n<kGroupThreads>(it.grp);
     st.gs = __ldg(ep.grad4) * __ldg(ep.grad4 + 3);
     st.r = 0.f; st.cls = 0; st.row_ok = false;
     st.pol = l2_policy(ep.gt_hint);
@@ -424,7 +426,7 @@ struct XwBwdGTT {
 
   static __device__ __forceinline__ void tile_end(State& st, const Params& ep, const XwParams&, const XwItem& it) {
     if (st.row_ok && ep.r_part != nullptr)
-      ep.r_part[(int64_t)(it.group * 2 + it.half) * ep.ldr + st.cls] = st.r * ep.inv_scale;
+      ep.r_part[(int64_t)(it.group * SPLIT + it.half) * ep.ldr + st.cls] = st.r * ep.inv_scale;
   }
 
   // rows of the resident group = width of the column space = 128 * PAIR; carried in XwParams.tn
@@ -433,6 +435,7 @@ struct XwBwdGTT {
 };
 using XwBwdGT = XwBwdGTT<1, 32>;
 using XwBwdGT2 = XwBwdGTT<2, 16>;
+using XwBwdGT4 = XwBwdGTT<1, 16, 4>;   // one group of sixteen warps, column quarters
 
 // -------------------------------------------------------------------------------------------------
 // ---- K3b, class-major: dW[c, d] = coef.x * (acc[c, d] - w_hat16[c, d] * coef.y) --------------------------------
@@ -446,21 +449,37 @@ using XwBwdGT2 = XwBwdGTT<2, 16>;
 // features] boxes (2 KB, one cp.async.bulk.tensor per slice, issued two slices ahead by lane 0) into staging space
 // taken from the operand ring: G^T needs a third of the HBM rate, so 3 ring stages suffice and the other 32 KB are
 // 8 warps x 2 buffers x 2 KB.
-template <int EG, int SC>
+// TMAST (round 2): dW leaves through shared-memory staging and TMA tensor stores instead of row-per-lane 32-byte stores
+// (tools/microbench/store_bw.cu: 4.35 TB/s for that pattern, 5.55 TB/s coalesced).  Per warp and slice: the [32 classes x 32
+// features] fp32 block goes to a 4 KB staging buffer in the 128-byte swizzle (lane = class row, its 16-byte chunk c at
+// chunk c ^ (row & 7): conflict-free st.shared.v4), fence.proxy.async, one cp.async.bulk.tensor store by lane 0; the
+// buffer is reused once that store has READ it.  The 32 KB of staging come out of the ring (G^T gets 2 stages instead of
+// 3, its tiles are prefetched into L2 two ahead) and the w_hat boxes move into the third stage, the scratch area (unused by
+// this policy) and 8 KB of extra shared memory.
+template <int EG, int SC, bool TMAST = false>
 struct XwDwTT {
-  static constexpr int kRingStages = 3;
+  static_assert(!TMAST || (EG == 1 && SC == 32), "the TMA-store form: one epilogue group, 32-feature slices");
+  static constexpr int kRingStages = TMAST ? 2 : 3;
+  static constexpr int kExtraSmem = TMAST ? 8192 + 256 : 0;
   static constexpr int kEpiGroups = EG;
   static constexpr int kSliceCols = SC;
   static constexpr int kBoxBytes = 32 * SC * 2;       // [32 classes x SC features] fp16: 2 KB (SC = 32) or 1 KB (SC = 16)
+  // boxes: warps 0-3 in ring stage 2, warps 4-5 in the scratch area, warps 6-7 in the extra bytes; staging: ring stages 3-4
+  static __device__ __forceinline__ void aux_layout(XwItem& it, uint8_t* ring, uint8_t* scratch, uint8_t* extra) {
+    const int w = it.ew;
+    it.aux = (w < 4) ? ring + 2 * XW_TILE_BYTES + w * 4096 : (w < 6) ? scratch + (w - 4) * 4096 : extra + (w - 6) * 4096;
+    it.stage = ring + 3 * XW_TILE_BYTES + w * 4096;
+  }
   struct Params {
     alignas(64) CUtensorMap tm_wh;      // w_hat16 rows of this launch [classes, D], box SC features x 32 classes, no swizzle
+    alignas(64) CUtensorMap tm_dw;      // TMAST: dW [classes of this launch, D] fp32, box 32 features x 32 classes, 128-byte swizzle
     CoefSrc coef; float* dw; int64_t c0; int ld;
     float* sq_part;                     // NULL, or [items * PAIR * EG * 8]: sum of dW^2 per (item, CTA, epilogue warp) -- the
                                         // ||dW||^2 clip_grad_norm_ needs (src/training.py:528-533) without a pass over dW
     int dw_hint, wh_hint;               // L2 policies: dW stores (nobody reads them in this step: 1 evict_first), w_hat boxes
     B200F_PROBE_FIELD                   // probe builds only: 1 = no w_hat loads, 2 = no dW stores (WRONG results)
   };
-  struct State { float2 cf; float rp_next[4]; float inw_next; int64_t next_row; float inv_sg; int seq, n_seq, row0, row_step; bool row_ok;
+  struct State { float2 cf; float rp_next[8]; float inw_next; int64_t next_row; float inv_sg; int seq, n_seq, row0, row_step; bool row_ok;
                  uint64_t dw_pol, wh_pol; float sq; };
 
   // slice n of this warp's item = column slice (n % spt) of its (n / spt)-th OWN tile (with EG groups a group owns every
@@ -498,15 +517,18 @@ struct XwDwTT {
     // this tile's coefficients were REQUESTED one (own) tile ago (raw loads, consumed only here: the warp never waits for
     // them in the middle of a tile; forming the sum where the loads are issued blocked it once per partial)
     if (st.next_row == it.row)
-      st.cf = make_float2(st.inw_next * st.inv_sg, ((st.rp_next[0] + st.rp_next[1]) + st.rp_next[2]) + st.rp_next[3]);
+      st.cf = make_float2(st.inw_next * st.inv_sg,
+                          (ep.coef.n_rb <= 4) ? ((st.rp_next[0] + st.rp_next[1]) + st.rp_next[2]) + st.rp_next[3]
+                                              : ((((((st.rp_next[0] + st.rp_next[1]) + st.rp_next[2]) + st.rp_next[3]) + st.rp_next[4]) +
+                                                  st.rp_next[5]) + st.rp_next[6]) + st.rp_next[7]);   // CoefSrc::load's order
     else
       st.cf = ep.coef.load(it.row, ep.c0 + it.row, st.inv_sg);
     const int64_t nr = it.row + (int64_t)EG * st.row_step;
     st.next_row = -1;
-    if (nr >= 0 && nr < p.C && ep.coef.n_rb <= 4) {
+    if (nr >= 0 && nr < p.C && ep.coef.n_rb <= 8) {
       st.next_row = nr;
 #pragma unroll
-      for (int rb = 0; rb < 4; ++rb)
+      for (int rb = 0; rb < 8; ++rb)
         st.rp_next[rb] = (rb < ep.coef.n_rb) ? __ldg(ep.coef.r_part + (int64_t)rb * ep.coef.ldr + nr) : 0.f;
       st.inw_next = __ldg(ep.coef.inv_nw + ep.c0 + nr);
     }
@@ -531,10 +553,14 @@ struct XwDwTT {
         asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
                      : "=r"(w[i].x), "=r"(w[i].y), "=r"(w[i].z), "=r"(w[i].w) : "r"(src + i * 16) : "memory");
     }
+    float o[SC];
+    if constexpr (TMAST) {
+#pragma unroll
+      for (int j = 0; j < SC; ++j) o[j] = 0.f;                 // rows beyond C: staged as zeros, clipped by the tensor map
+    }
     if (st.row_ok) {
       float* dst = ep.dw + (ep.c0 + it.row) * (int64_t)ep.ld + d0;
       const float cx = st.cf.x, cy = st.cf.y;
-      float o[SC];
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const uint32_t q[4] = {w[i].x, w[i].y, w[i].z, w[i].w};
@@ -554,6 +580,9 @@ struct XwDwTT {
         }
         st.sq += (q4[0] + q4[1]) + (q4[2] + q4[3]);
       }
+      if constexpr (TMAST) {
+        // (handled below, by the whole warp)
+      } else
       if (B200F_PROBE_ON(ep, 2) && o[0] != 12345.678f) {
       } else if (d0 + SC <= p.B && (ep.ld & 7) == 0) {
 #pragma unroll
@@ -579,6 +608,25 @@ struct XwDwTT {
       for (int i = 0; i < NV; ++i) acc ^= w[i].x;
       asm volatile("" :: "r"(acc) : "memory");
     }
+    if constexpr (TMAST) {
+      if (!(B200F_PROBE_ON(ep, 2) && o[0] != 12345.678f)) {
+        if (it.lane == 0) tma_store_wait_read();              // the previous slice's store has read the staging buffer
+        __syncwarp();
+        const uint32_t sb = smem_u32(it.stage) + (uint32_t)it.lane * 128u;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};"
+                       ::"r"(sb + (uint32_t)((c ^ (it.lane & 7)) << 4)), "f"(o[4 * c]), "f"(o[4 * c + 1]), "f"(o[4 * c + 2]), "f"(o[4 * c + 3])
+                       : "memory");
+        fence_proxy_async();
+        __syncwarp();
+        const int64_t row_w = it.row - it.lane;               // first class row of this warp in the tile (row of the launch)
+        if (it.lane == 0 && row_w < p.C) {
+          if (ep.dw_hint) tma_store_2d_hint(&ep.tm_dw, it.stage, d0, (int)row_w, st.dw_pol);
+          else tma_store_2d(&ep.tm_dw, it.stage, d0, (int)row_w);
+        }
+      }
+    }
     // Refill only now: the stores above consumed w[], so every lane's reads of the buffer have completed.  (Issuing
     // the refill right after the ld.shared instructions let the TMA write overtake reads still queued in the
     // load/store unit behind this kernel's global stores: single 16-byte pieces of the NEXT box showed up.)
@@ -587,6 +635,7 @@ struct XwDwTT {
   }
   static __device__ __forceinline__ void tile_end(State&, const Params&, const XwParams&, const XwItem&) {}
   static __device__ __forceinline__ void item_end_swap(State& st, const Params& ep, const XwParams&, const XwItem& it, int pair) {
+    if constexpr (TMAST) { if (it.lane == 0) tma_store_wait_all(); }      // this thread's tensor stores are in global memory
     if (ep.sq_part == nullptr) return;
     const float s = warp_sum(st.sq);
     if (it.lane == 0) ep.sq_part[(((int64_t)it.item * pair + it.rank) * EG + it.grp) * XW_EPI_WARPS + it.ew] = s;
@@ -594,6 +643,7 @@ struct XwDwTT {
 };
 using XwDwT = XwDwTT<1, 32>;
 using XwDwT2 = XwDwTT<2, 16>;
+using XwDwTS = XwDwTT<1, 32, true>;   // dW through staging + TMA stores
 
 }  // namespace umma
 }  // namespace b200f

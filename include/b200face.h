@@ -346,8 +346,11 @@ int b200f_umma_set_pair(int pair);
 int b200f_umma_xw_probe(const void* x, const void* w, float* rowsum, int B, int C, int D, int pair, void* stream);
 /* Tunables for tests and bench sweeps: "pair" (1 | 2), "g_chunk_mb" (budget in MB of the fp16 logit-gradient buffer
  * per class chunk of the backward; default 112), "pdl" (0 | 1), "k3b_reverse" (0 | 1),
- * "xw_prefetch" (tiles of the streamed operand pulled into L2 ahead of the TMA ring; default 2), "stage_events" (0 | 1), "k2_groups" / "epi_groups" / "k3b_groups" (1 | 2: epilogue warp groups of
- * K2 / K3a / K3b; defaults 1 / 2 / 1), "early" (0 | 1: K3a / K3c start before their predecessor grid has drained), "l2_hints" (bit mask of
+ * "xw_prefetch" (tiles of the streamed operand pulled into L2 ahead of the TMA ring; default 0: measured +-0), "stage_events" (0 | 1),
+ * "k2_groups" / "epi_groups" / "k3b_groups" (epilogue geometry of K2 / K3a / K3b: 1 = one group of 8 warps on 32-column slices,
+ * 2 = two groups on alternating tiles, 16-column slices; "epi_groups" also takes 4 = one group of 16 warps on column quarters of
+ * every tile; defaults 1 / 1 / 1), "k3b_tma_store" (0 | 1: dW through shared-memory staging and TMA tensor stores; default 0, it
+ * measured slower), "early" (0 | 1: K3a / K3c start before their predecessor grid has drained), "l2_hints" (bit mask of
  * L2 cache-policy hints, default 6: G^T stores evict_last, dW stores evict_first).
  * Returns the previous value, -1 for an unknown name.  Every setting computes the same results ("g_chunk_mb" changes the
  * workspace size: query b200f_head_workspace_bytes again after changing it).  The measurement probes that skip memory

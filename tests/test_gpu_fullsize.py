@@ -102,10 +102,11 @@ def test_cfg3_full_size_vs_cpu_port(cuda_device):
     _check(_gpu_step(x, w, y, cuda_device), _cpu_step(x, w, y), "cfg3")
 
 
-@pytest.mark.parametrize("epi_groups", [1, 2])
+@pytest.mark.parametrize("epi_groups", [1, 2, 4])
 def test_cfg3_full_size_epilogue_variants_agree(cuda_device, epi_groups):
     """Both epilogue geometries of K2 / K3a / K3b (one group of 8 warps on 32-column slices, two groups on 16-column
-    slices) against the CPU port at a size that still has full tiles, ragged tiles and several items per cluster."""
+    slices; 4 = K3a with one group of 16 warps on column quarters) against the CPU port at a size that still has full
+    tiles, ragged tiles and several items per cluster."""
     from b200face import _lib
     lib = _lib.load_library()
     x, w, y = _inputs(384, 30_011, 512, 77)
