@@ -226,7 +226,8 @@ static std::atomic<int> g_l2_hints{6};
 // boxes move the same bytes less efficiently than 128-byte pieces and 2 KB boxes).
 static std::atomic<int> g_k2_groups{1};             // K2: epilogue groups
 static std::atomic<int> g_k3b_groups{1};            // K3b: 2 = two epilogue groups on 16-feature slices, 1 = one group on 32
-static std::atomic<int> g_early{1};                 // K3a / K3c start their loads and MMAs without waiting for the predecessor grid
+static std::atomic<int> g_early{2};                 // >= 1: K3a / K3c start their loads and MMAs without waiting for the predecessor grid,
+                                                    // 2: K3b also loads its resident x_hat^T before it waits
 static std::atomic<int> g_epi_groups{1};            // K3a: 2 = two epilogue groups of 8 warps on alternating tiles (16-column slices), 1 = one group of 8,
                                                     //      4 = one group of 16 warps on every tile (column quarters)
 #ifdef B200F_PROBES                                 // tools/ builds only; the shipped library has neither the branch nor the switch
@@ -235,7 +236,8 @@ static std::atomic<int> g_k3b_ablate{0};            // probe: 1 = no w_hat loads
 #endif
 static std::atomic<int> g_k3b_reverse{1};
 static std::atomic<int> g_k3b_tma_store{0};         // tunable "k3b_tma_store": 1 = dW through shared-memory staging + TMA tensor stores (XwDwTS)
-static std::atomic<int> g_target_patch{1};          // tunable "target_patch": 1 = K2 / K3a exchange a target element in place, 0 = whole slice element-wise
+static std::atomic<int> g_target_patch{2};          // tunable "target_patch": 0 = a slice with a target goes element-wise (round 1), 1 = K2 / K3a exchange the element
+                                                    // in place, 2 = ... and K3a queues its patches to the end of the item
 static std::atomic<int> g_x_whole{0};               // tunable "x_whole": 1 = first MMA of an item waits for the whole resident operand
 // "stage_events" tunable: record a CUDA event pair around each GEMM kernel of the head on the launching stream
 // (bench.py's per-kernel durations; eager launches only -- never inside a graph capture).
@@ -349,7 +351,7 @@ extern "C" int b200f_xw_timeline(void* buf, int which) {
 template <int PAIR, int MODE, class Epi>
 static int launch_xw(const CUtensorMap& tx, const CUtensorMap& tw, const XwPlan& q, int64_t B, int64_t C, int D,
                      const typename Epi::Params& ep, cudaStream_t st, const char* what, uint32_t fmt = FMT_F16,
-                     bool reverse = false, const void* w_base = nullptr, int64_t w_row_bytes = 0, bool early = false,
+                     bool reverse = false, const void* w_base = nullptr, int64_t w_row_bytes = 0, int early = 0,
                      int w_hint = 0, const XwPrepArgs* prep = nullptr, int prefetch_tiles = -1) {
   int rc = xw_set_smem<PAIR, MODE, Epi>(); if (rc) return rc;
   XwParams p{};
@@ -358,7 +360,7 @@ static int launch_xw(const CUtensorMap& tx, const CUtensorMap& tw, const XwPlan&
   p.m_groups = q.m_groups; p.n_tiles = q.n_tiles; p.n_chunks = q.n_chunks;
   p.prefetch = (w_base != nullptr) ? (prefetch_tiles >= 0 ? prefetch_tiles : g_prefetch.load(std::memory_order_relaxed)) : 0;
   p.w_base = w_base; p.w_row_bytes = w_row_bytes;
-  p.early_operands = (early && g_early.load(std::memory_order_relaxed)) ? 1 : 0;
+  p.early_operands = (early && g_early.load(std::memory_order_relaxed)) ? early : 0;   // 1: both operands older than the predecessor, 2: the resident one
   p.w_hint = w_hint;
 #ifdef B200F_TIMELINE
   p.tl = (g_tl_buf != nullptr && g_tl_count++ == g_tl_which) ? g_tl_buf : nullptr;
@@ -693,6 +695,7 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
       e.GT = G; e.ldgt = pl.ldg; e.r_part = r_part; e.ldr = pl.Cc;
       e.gt_hint = (hints_k3a & 2) ? 2 : 0;
       e.whole_slice_targets = g_target_patch.load(std::memory_order_relaxed) ? 0 : 1;
+      e.defer_targets = g_target_patch.load(std::memory_order_relaxed) == 2 ? 1 : 0;
 #ifdef B200F_PROBES
       e.ablate = g_k3a_ablate.load(std::memory_order_relaxed);
 #endif
@@ -730,6 +733,8 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
       const XwPlan qw = xw_plan(D, cnt, qg.pair);
       const bool k3b_rev = g_k3b_reverse.load(std::memory_order_relaxed) != 0;   // read K3a's freshest G^T rows first
       const int gt_lhint = (hints & 32) ? 2 : 0;
+      // x_hat^T (K1's output) is older than K3a: the producers load it while K3a drains ("early" = 2: then wait, then G^T)
+      const int k3b_early = (g_early.load(std::memory_order_relaxed) >= 2) ? 2 : 0;
       if (g_k3b_tma_store.load(std::memory_order_relaxed) != 0 && (D % 4) == 0) {
         XwDwTS::Params ew{};
         rc = make_tmap(&ew.tm_wh, wc, D, cnt, D, 32, 32, CU_TENSOR_MAP_SWIZZLE_NONE); if (rc) return rc;
@@ -764,8 +769,8 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
 #ifdef B200F_PROBES
         ew.ablate = g_k3b_ablate.load(std::memory_order_relaxed);
 #endif
-        rc = (qw.pair == 2) ? launch_xw<2, XW_SWAP_MK, XwDwT>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW class-major (cta pair)", FMT_F16, k3b_rev, G, pl.ldg * 2, false, gt_lhint)
-                            : launch_xw<1, XW_SWAP_MK, XwDwT>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW class-major", FMT_F16, k3b_rev, G, pl.ldg * 2, false, gt_lhint);
+        rc = (qw.pair == 2) ? launch_xw<2, XW_SWAP_MK, XwDwT>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW class-major (cta pair)", FMT_F16, k3b_rev, G, pl.ldg * 2, k3b_early, gt_lhint)
+                            : launch_xw<1, XW_SWAP_MK, XwDwT>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW class-major", FMT_F16, k3b_rev, G, pl.ldg * 2, k3b_early, gt_lhint);
       }
       if (rc) return rc;
     } else {
@@ -1107,14 +1112,14 @@ int b200f_set_tunable(const char* name, int value) {
   if (n == "pdl") { const int old_v = pdl_enabled() ? 1 : 0; if (value == 0 || value == 1) pdl_set(value != 0); return old_v; }
   if (n == "stage_events") { if (value != 0 && value != 1) return g_stage_events.load(); return g_stage_events.exchange(value); }
   if (n == "k2_prep") { if (value < 0 || value > 2) return g_k2_prep.load(); return g_k2_prep.exchange(value); }
-  if (n == "target_patch") { if (value != 0 && value != 1) return g_target_patch.load(); return g_target_patch.exchange(value); }
+  if (n == "target_patch") { if (value < 0 || value > 2) return g_target_patch.load(); return g_target_patch.exchange(value); }
   if (n == "x_whole") { if (value != 0 && value != 1) return g_x_whole.load(); return g_x_whole.exchange(value); }
   if (n == "k1_hints") { if (value < 0 || value > 3) return k1_hints(); return k1_hints_set(value); }
   if (n == "l2_hints") { if (value < 0) return g_l2_hints.load(); return g_l2_hints.exchange(value); }
   if (n == "k2_groups") { if (value != 1 && value != 2) return g_k2_groups.load(); return g_k2_groups.exchange(value); }
   if (n == "k3b_groups") { if (value != 1 && value != 2) return g_k3b_groups.load(); return g_k3b_groups.exchange(value); }
   if (n == "gallery_compact") { if (value != 0 && value != 1) return g_gallery_compact.load(); return g_gallery_compact.exchange(value); }
-  if (n == "early") { if (value != 0 && value != 1) return g_early.load(); return g_early.exchange(value); }
+  if (n == "early") { if (value < 0 || value > 2) return g_early.load(); return g_early.exchange(value); }
   if (n == "epi_groups") { if (value != 1 && value != 2 && value != 4) return g_epi_groups.load(); return g_epi_groups.exchange(value); }
 #ifdef B200F_PROBES
   // probes that make the backward skip memory traffic (WRONG results): -DB200F_PROBES builds only (tools/)

@@ -131,6 +131,10 @@ struct XwParams {
                                         // come from K1, the predecessor only supplies lse / grad4 to the epilogue), so the TMA and
                                         // MMA warps do not wait for the predecessor: loads and MMAs of the first tiles overlap its
                                         // tail.  The epilogue warps wait (griddepcontrol.wait) before they touch anything.
+                                        // 2: only the RESIDENT operand is that old (K3b: x_hat from K1; its streamed G^T is the
+                                        // predecessor's output): the producer loads the first item's resident rows, THEN waits, then
+                                        // streams.  It does not release dependents itself (a kernel in front of an early starter
+                                        // must have waited before it triggers: the epilogue warps do both, in that order).
   uint32_t idesc;
   int x_whole;                          // 1: the MMA issuer waits for the whole resident operand before the item's first MMA
   // ---- operand preparation fused into the kernel (policies with kPrepWarps > 0: K2 of the head) ------------------------
@@ -531,11 +535,12 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
   const uint32_t tmem_base = *tmem_slot;
   // prologue done; predecessor grids complete from here on -- for everyone, or (early_operands) for the epilogue warps only:
   // every CTA has epilogue warps, so no CTA (hence not the grid) completes before its predecessor has.
-  if (!p.early_operands || warp >= 2) pdl_wait();
+  const bool waits_now = !p.early_operands || warp >= 2;
+  if (waits_now) pdl_wait();
   // Dependents may be scheduled from here on -- AFTER the wait, not at the top of the kernel: a dependent that starts
   // "early" (above) relies on everything older than its predecessor being complete, and that holds only if the
   // predecessor could not release it before having waited itself (K1 -> K2 -> statistics -> K3a: K3a reads K1's output).
-  pdl_trigger();
+  if (waits_now || p.early_operands == 1) pdl_trigger();
 
   constexpr int PREP_WARPS = xw_prep_warps<Epi>::value;
   if (PREP_WARPS > 0 && warp >= 2 + EPI_WARPS_ALL) {
@@ -576,6 +581,7 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
             }
           }
         }
+        if (p.early_operands == 2 && item_no == 0) pdl_wait();      // the streamed operand is the predecessor's output
         // L2 prefetch of whole tiles ahead of the ring (K-major streamed operand only)
         auto prefetch_tile = [&](int tj) {                      // tj: position in the walk order of this item
           if (W_MN || p.prefetch <= 0 || tj >= t_end) return;

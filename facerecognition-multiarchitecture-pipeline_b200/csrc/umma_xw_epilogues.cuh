@@ -279,9 +279,15 @@ struct XwBwdGTT {
     float* r_part; int64_t ldr; // [SPLIT * m_groups, ldr]: one partial per (row group, column half / quarter)
     int gt_hint;                // L2 policy of the G^T stores (K3b and K3c read them next): 0 none, 2 evict_last
     int whole_slice_targets;    // tunable "target_patch" = 0: a slice with a target element goes the element-wise way (round 1)
+    int defer_targets;          // tunable "target_patch" = 2: target elements are queued and patched at the end of the item
     B200F_PROBE_FIELD           // probe builds only: 2 = no G^T stores (WRONG results)
   };
-  struct State { float gs, r; int cls; bool row_ok; uint64_t pol; };
+  // Deferred target patches: up to kQueue entries {accumulator, -lse log2 e, batch row, class row} per warp and item in the
+  // group's scratch behind the two column tables.  Why: a patch costs the warp ~1.5 us (one TMEM column, the out-of-line
+  // phi / dphi, exp2, a scalar store) while its tile's accumulator stage is held; 3.5 of them per CTA and item sat on the
+  // critical path (K3a 65 us against 60 us with the labels out of range).  At the end of the item they run lane-parallel.
+  static constexpr int kQueue = 8;
+  struct State { float gs, r; int cls; bool row_ok; uint64_t pol; int nq; uint32_t q_s; };
 
   static __device__ __forceinline__ void item_begin(State& st, const Params& ep, const XwParams& p, const XwItem& it,
                                                     float* scratch, int TN) {
@@ -302,6 +308,8 @@ struct XwBwdGTT {
     st.gs = __ldg(ep.grad4) * __ldg(ep.grad4 + 3);
     st.r = 0.f; st.cls = 0; st.row_ok = false;
     st.pol = l2_policy(ep.gt_hint);
+    st.nq = 0;
+    st.q_s = smem_u32(scratch + 2 * TN) + (uint32_t)it.ew * (kQueue * 16);   // 2 * TN + 16 warps * 32 floats <= 1024 floats
   }
   static __device__ __forceinline__ void tile_begin(State& st, const Params&, const XwParams& p, const XwItem& it) {
     st.cls = (int)it.row; st.row_ok = it.row < p.C; st.r = 0.f;
@@ -406,6 +414,16 @@ struct XwBwdGTT {
       // the accumulator of (my class, that column) again from TMEM: the stage is still ours, and the cold code then does
       // not index the slice's registers (a select chain over v[] here cost the hot path ~3 us per kernel)
       const float vt = tmem_ld1(it.taddr0 + (uint32_t)(col0 + src));
+      if (ep.defer_targets && st.nq < kQueue) {               // warp-uniform: queue it, patch at the end of the item
+        if (st.row_ok && st.cls == lab_s) {                   // exactly one lane owns the class
+          const int bt = it.group * p_tn(p) + col0 + src;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                       ::"r"(st.q_s + (uint32_t)st.nq * 16u), "r"(__float_as_uint(vt)), "r"(__float_as_uint(scratch[col0 + src])), "r"(bt), "r"(st.cls)
+                       : "memory");
+        }
+        ++st.nq;
+        continue;
+      }
       if (st.row_ok && st.cls == lab_s) {
         const float bb = scratch[col0 + src];
         const float g_old = fmaf(gs, ex2_approx(fmaf(vt, a, bb)), -gq);    // the bits the fast path stored and summed
@@ -431,7 +449,48 @@ struct XwBwdGTT {
 
   // rows of the resident group = width of the column space = 128 * PAIR; carried in XwParams.tn
   static __device__ __forceinline__ int p_tn(const XwParams& p) { return p.tn; }
-  static __device__ __forceinline__ void item_end_swap(State&, const Params&, const XwParams&, const XwItem&, int) {}
+  // The queued target patches of this warp: lane e re-evaluates entry e (phi / dphi once for all of them), overwrites the
+  // fp16 element the fast path stored, and lane 0 then corrects the r partials one after the other (two entries may share a
+  // class: a fixed order keeps the sum reproducible).  All tile_end stores of the item precede this in program order and
+  // __syncwarp orders them for the other lanes.
+  static __device__ __forceinline__ void item_end_swap(State& st, const Params& ep, const XwParams& p, const XwItem& it, int) {
+    const int n = st.nq;
+    if (n == 0) return;
+    __syncwarp();
+    float delta = 0.f; int cls = 0;
+    if (it.lane < n) {
+      uint32_t u0, u1, u2, u3;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u0), "=r"(u1), "=r"(u2), "=r"(u3) : "r"(st.q_s + (uint32_t)it.lane * 16u) : "memory");
+      const float vt = __uint_as_float(u0), bb = __uint_as_float(u1);
+      const int bt = (int)u2; cls = (int)u3;
+      const float s_eff = ep.hm.s_eff, isc = ep.inv_scale, gs = st.gs;
+      const float q_off = ep.ls_eps * ep.inv_Ctot;
+      const float g_old = fmaf(gs, ex2_approx(fmaf(vt, isc * s_eff * LOG2E, bb)), -(gs * q_off));   // the bits the fast path stored and summed
+      float tv, f;
+      head_phi_dphi(ep.hm, vt * isc, &tv, &f);                // inside [lo, hi]: the slice took the fast path
+      float z = tv * s_eff;
+      if (!isfinite(z)) { z = 0.f; f = 0.f; }
+      const float pr = exp2f(fmaf(z, LOG2E, bb));
+      const float q = (1.0f - ep.ls_eps) + q_off;
+      const float gn = fminf(fmaxf(gs * (pr - q) * f, -65504.f), 65504.f);
+      delta = (gn - g_old) * vt * ep.inv_scale;
+      if (bt < p.B && !(B200F_PROBE_ON(ep, 2) && gn != 12345.678f))
+        ep.GT[(int64_t)cls * ep.ldgt + bt] = (uint16_t)(pack_f16(gn, 0.f) & 0xffff);
+    }
+    if (ep.r_part != nullptr) {
+      float* const rrow = ep.r_part + (int64_t)(it.group * SPLIT + it.half) * ep.ldr;
+      for (int e = 0; e < n; ++e) {                           // warp-uniform
+        const float d = __shfl_sync(0xffffffffu, delta, e);
+        const int c = __shfl_sync(0xffffffffu, cls, e);
+        if (it.lane == 0) {
+          float v;
+          asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(rrow + c) : "memory");
+          rrow[c] = v + d;
+        }
+      }
+    }
+    st.nq = 0;
+  }
 };
 using XwBwdGT = XwBwdGTT<1, 32>;
 using XwBwdGT2 = XwBwdGTT<2, 16>;

@@ -229,6 +229,42 @@ def test_bf16_vs_oracle(cuda_device, B, C, D, engine):
     assert rel_err(xg.grad.float().cpu().numpy(), ref["dx"]) < TOL_BF16 + 2 ** -8
 
 
+@pytest.mark.parametrize("patch", [0, 1, 2])
+@pytest.mark.parametrize("n_cls", [1, 3, 40])
+def test_few_classes_many_samples(cuda_device, patch, n_cls):
+    """Every batch row is labelled with one of n_cls classes: one epilogue warp of K3a owns up to 256 target elements of
+    a tile (its queue of deferred patches holds 8 -- the rest take the in-place path), and several patches correct the r
+    sum of the same class.  All three target_patch modes (whole slice element-wise / in place / queued) against the oracle."""
+    import b200face
+    from b200face import _lib
+    lib = _lib.load_library()
+    B, C, D = 512, 6000, 512
+    x, w, y = _random_case(B, C, D, 4242 + n_cls, planted=0.25)
+    g = torch.Generator().manual_seed(n_cls)
+    classes = torch.randint(0, C, (n_cls,), generator=g)
+    y = classes[torch.randint(0, n_cls, (B,), generator=g)]
+    xb, wb = x.bfloat16(), w.bfloat16()
+    cfg = oracle.HeadConfig(current_epoch=12, training=True, label_smoothing=0.05)
+    head = _head_from_cfg(cfg, C, D, cuda_device, wb.float())
+    xg = xb.to(cuda_device).requires_grad_(True)
+    old = lib.b200f_set_tunable(b"target_patch", patch)
+    try:
+        loss = head.forward_loss(xg, y.to(cuda_device), 0.05)
+        loss.backward()
+        torch.cuda.synchronize()
+    finally:
+        lib.b200f_set_tunable(b"target_patch", old)
+    assert lib.b200f_umma_timeout_flag(1) == 0
+    ref = oracle.head_forward_backward(xb.float().numpy(), wb.float().numpy(), y.numpy(), cfg)
+    assert float(loss) == pytest.approx(float(ref["loss"]), rel=TOL_BF16)
+    assert rel_err(head.weight.grad.cpu().numpy(), ref["dw"]) < TOL_BF16
+    assert rel_err(head.last_stats.dx_f32.cpu().numpy(), ref["dx"]) < TOL_BF16
+    # the labelled classes' rows of dW carry almost all of the gradient: held row by row
+    dw = head.weight.grad.cpu().numpy()
+    for c in classes.tolist():
+        assert rel_err(dw[c], ref["dw"][c]) < TOL_BF16
+
+
 def test_nan_inf_scrub(cuda_device):
     """face_models.py:423-427: non-finite logits become 0 (and their gradient is cut)."""
     import b200face
