@@ -596,18 +596,48 @@ reduce_splits_normbwd_kernel(const float* __restrict__ part, int n_splits, int64
   float dot = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const int c = lane + 32 * i;
 #pragma unroll
     for (int e = 0; e < N; ++e) { g[i][e] = 0.f; xh[i][e] = 0.f; }
-    if (c < nvec) {
-      const int64_t off = row * dim + (int64_t)c * N;
-      for (int k = 0; k < n_splits; ++k) {
+  }
+  // The split partials: FOUR splits per trip, all of their 16-byte loads (4 x NV x N / 4 = 16 per lane) issued before the
+  // first add.  (One split per trip left two loads in flight per lane: 512 warps x 1 KB against ~0.6 us of L2 latency is
+  // 0.9 TB/s -- 17 us for the 19 MB of cfg3's 18 splits, at the very end of the step where nothing overlaps it.)  Every
+  // element is still summed over k in ascending order: the same bits.
+  constexpr int KU = 4;
+  for (int k0 = 0; k0 < n_splits; k0 += KU) {
+    float4 pv[KU][NV][N / 4];
+#pragma unroll
+    for (int kk = 0; kk < KU; ++kk) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
 #pragma unroll
         for (int e = 0; e < N; e += 4) {
-          const float4 pv = __ldcg(reinterpret_cast<const float4*>(part + (int64_t)k * n + off + e));
-          g[i][e] += pv.x; g[i][e + 1] += pv.y; g[i][e + 2] += pv.z; g[i][e + 3] += pv.w;
+          pv[kk][i][e / 4] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (c < nvec && k0 + kk < n_splits)
+            pv[kk][i][e / 4] = __ldcg(reinterpret_cast<const float4*>(part + (int64_t)(k0 + kk) * n + row * dim + (int64_t)c * N + e));
         }
       }
+    }
+#pragma unroll
+    for (int kk = 0; kk < KU; ++kk) {
+      if (k0 + kk < n_splits) {                                // (a skipped split must not even add +0: -0 + 0 = +0)
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+#pragma unroll
+          for (int e = 0; e < N; e += 4) {
+            const float4 q = pv[kk][i][e / 4];
+            g[i][e] += q.x; g[i][e + 1] += q.y; g[i][e + 2] += q.z; g[i][e + 3] += q.w;
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nvec) {
+      const int64_t off = row * dim + (int64_t)c * N;
       Vec16<T>::load(v + off, xh[i]);
 #pragma unroll
       for (int e = 0; e < N; ++e) { g[i][e] *= sc; xh[i][e] *= vmul; dot = fmaf(xh[i][e], g[i][e], dot); }

@@ -207,9 +207,14 @@ __global__ void reduce_splits_kernel(const float* __restrict__ part, int n_split
   const float sc = (dev_scale != nullptr) ? scale / __ldg(dev_scale) : scale;
   float4 s = accumulate ? *reinterpret_cast<const float4*>(dst + i) : make_float4(0.f, 0.f, 0.f, 0.f);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int k = 0; k < n_splits; ++k) {
-    const float4 v = *reinterpret_cast<const float4*>(part + (int64_t)k * n + i);
-    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  for (int k0 = 0; k0 < n_splits; k0 += 4) {                  // four loads in flight per thread, summed in ascending order
+    float4 v[4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+      if (k0 + kk < n_splits) v[kk] = __ldcg(reinterpret_cast<const float4*>(part + (int64_t)(k0 + kk) * n + i));
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+      if (k0 + kk < n_splits) { acc.x += v[kk].x; acc.y += v[kk].y; acc.z += v[kk].z; acc.w += v[kk].w; }
   }
   s.x = fmaf(acc.x, sc, s.x); s.y = fmaf(acc.y, sc, s.y); s.z = fmaf(acc.z, sc, s.z); s.w = fmaf(acc.w, sc, s.w);
   *reinterpret_cast<float4*>(dst + i) = s;
