@@ -742,7 +742,7 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
       const int k3b_early = (g_early.load(std::memory_order_relaxed) >= 2) ? 2 : 0;
       if (g_k3b_tma_store.load(std::memory_order_relaxed) != 0 && (D % 4) == 0) {
         XwDwTS::Params ew{};
-        rc = make_tmap(&ew.tm_wh, wc, D, cnt, D, 32, 32, CU_TENSOR_MAP_SWIZZLE_NONE); if (rc) return rc;
+        rc = make_tmap(&ew.tm_wh, wc, D, cnt, D, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B); if (rc) return rc;
         // the map covers THIS launch's class rows only: a warp's rows beyond the chunk are clipped, not written as zeros
         rc = make_tmap_f32(&ew.tm_dw, dw + c0 * (int64_t)D, D, cnt, D, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B); if (rc) return rc;
         ew.coef = coef; ew.dw = dw; ew.c0 = c0; ew.ld = D; ew.sq_part = sq_part;
@@ -767,7 +767,7 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
                             : launch_xw<1, XW_SWAP_MK, XwDwT2>(tx_mn, tg_k, qw, D, cnt, (int)B, ew, st, "umma K3b dW class-major (2 epilogue groups)", FMT_F16, k3b_rev, G, pl.ldg * 2, false, gt_lhint);
       } else {
         XwDwT::Params ew{};
-        rc = make_tmap(&ew.tm_wh, wc, D, cnt, D, 32, 32, CU_TENSOR_MAP_SWIZZLE_NONE); if (rc) return rc;
+        rc = make_tmap(&ew.tm_wh, wc, D, cnt, D, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B); if (rc) return rc;
         ew.coef = coef; ew.dw = dw; ew.c0 = c0; ew.ld = D; ew.sq_part = sq_part;
         ew.dw_hint = (hints & 4) ? 1 : 0; ew.wh_hint = (hints & 8) ? 1 : 0;
         n_sq_used = qw.items * qw.pair * 1 * XW_EPI_WARPS;

@@ -519,18 +519,18 @@ template <int EG, int SC, bool TMAST = false>
 struct XwDwTT {
   static_assert(!TMAST || (EG == 1 && SC == 32), "the TMA-store form: one epilogue group, 32-feature slices");
   static constexpr int kRingStages = TMAST ? 2 : 3;
-  static constexpr int kExtraSmem = TMAST ? 8192 + 256 : 0;
+  static constexpr int kExtraSmem = TMAST ? 256 + 8192 + 256 : 0;   // pad to a 512-byte boundary (the boxes' 64-byte swizzle), boxes, barriers
   static constexpr int kEpiGroups = EG;
   static constexpr int kSliceCols = SC;
   static constexpr int kBoxBytes = 32 * SC * 2;       // [32 classes x SC features] fp16: 2 KB (SC = 32) or 1 KB (SC = 16)
   // boxes: warps 0-3 in ring stage 2, warps 4-5 in the scratch area, warps 6-7 in the extra bytes; staging: ring stages 3-4
   static __device__ __forceinline__ void aux_layout(XwItem& it, uint8_t* ring, uint8_t* scratch, uint8_t* extra) {
     const int w = it.ew;
-    it.aux = (w < 4) ? ring + 2 * XW_TILE_BYTES + w * 4096 : (w < 6) ? scratch + (w - 4) * 4096 : extra + (w - 6) * 4096;
+    it.aux = (w < 4) ? ring + 2 * XW_TILE_BYTES + w * 4096 : (w < 6) ? scratch + (w - 4) * 4096 : extra + 256 + (w - 6) * 4096;
     it.stage = ring + 3 * XW_TILE_BYTES + w * 4096;
   }
   struct Params {
-    alignas(64) CUtensorMap tm_wh;      // w_hat16 rows of this launch [classes, D], box SC features x 32 classes, no swizzle
+    alignas(64) CUtensorMap tm_wh;      // w_hat16 rows of this launch [classes, D], box SC features x 32 classes; 64-byte swizzle (SC = 32) or none (16)
     alignas(64) CUtensorMap tm_dw;      // TMAST: dW [classes of this launch, D] fp32, box 32 features x 32 classes, 128-byte swizzle
     CoefSrc coef; float* dw; int64_t c0; int ld;
     float* sq_part;                     // NULL, or [items * PAIR * EG * 8]: sum of dW^2 per (item, CTA, epilogue warp) -- the
@@ -607,10 +607,13 @@ struct XwDwTT {
       mbar_wait(it.aux_bar + b, (it.aux_phase >> b) & 1u);
       it.aux_phase ^= 1u << b;
       const uint32_t src = smem_u32(it.aux + b * kBoxBytes + it.lane * (SC * 2));
+      // SC = 32: the box arrives in the 64-byte swizzle (16-byte chunk c of row r sits at chunk c ^ ((r >> 1) & 3)): a lane
+      // owns a 64-byte row, so eight lanes reading the same chunk of their rows would hit the same four banks four times over
+      const uint32_t sw = (SC == 32) ? ((uint32_t)(it.lane >> 1) & 3u) : 0u;
 #pragma unroll
       for (int i = 0; i < NV; ++i)
         asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                     : "=r"(w[i].x), "=r"(w[i].y), "=r"(w[i].z), "=r"(w[i].w) : "r"(src + i * 16) : "memory");
+                     : "=r"(w[i].x), "=r"(w[i].y), "=r"(w[i].z), "=r"(w[i].w) : "r"(src + (((uint32_t)i ^ sw) << 4)) : "memory");
     }
     float o[SC];
     if constexpr (TMAST) {

@@ -119,6 +119,23 @@ def test_cfg3_full_size_epilogue_variants_agree(cuda_device, epi_groups):
     _check(gpu, _cpu_step(x, w, y), f"epi_groups={epi_groups}")
 
 
+@pytest.mark.parametrize("B,C", [(384, 30_011), (300, 4_097), (512, 33)])
+def test_dw_through_tma_stores_is_bit_identical(cuda_device, B, C):
+    """K3b's alternative way out (tunable k3b_tma_store: dW staged in shared memory in the 128-byte swizzle, one
+    cp.async.bulk.tensor store per warp and slice, rows beyond the launch clipped by the tensor map) does the same
+    arithmetic: dW must come out bit for bit as through the global stores, ragged class counts included."""
+    from b200face import _lib
+    lib = _lib.load_library()
+    x, w, y = _inputs(B, C, 512, 99)
+    ref = _gpu_step(x, w, y, cuda_device)
+    old = lib.b200f_set_tunable(b"k3b_tma_store", 1)
+    try:
+        alt = _gpu_step(x, w, y, cuda_device)
+    finally:
+        lib.b200f_set_tunable(b"k3b_tma_store", old)
+    assert np.array_equal(ref[2], alt[2]) and np.array_equal(ref[1], alt[1]) and ref[0] == alt[0]
+
+
 def test_cfg4_rank_shape_vs_cpu_port(cuda_device):
     """One rank's share of cfg4 on 8 GPUs (batch 4096 x 125 000 classes x 512): 16 row groups, one 1 GB class chunk of
     G^T, dW through the streamed pair GEMM with the fused normalise-backward -- against the CPU port of the reference on
