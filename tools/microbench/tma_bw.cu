@@ -7,7 +7,7 @@
 //   v0: box [64 k x 128 rows] (16 KB, 128-byte swizzle) -- what the kernel does: 8 boxes walk one 128-row block
 //   v1: box [64 k x 256 rows] (32 KB)
 //   v2: two boxes [64 k x 64 rows] per stage
-//   v3: box [512 k x 16 rows], no swizzle: 1 KB contiguous per row (not an MMA layout: the per-row-segment cost)
+//   v3: box [256 k x 32 rows], no swizzle: 512 B contiguous per row (not an MMA layout: the per-row-segment cost)
 //   v4: 3-D map [64 k][8 k-blocks][rows], box (64, 2, 128): two k-blocks per instruction (32 KB)
 // build: nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o tools/microbench/tma_bw tools/microbench/tma_bw.cu -lcuda
 #include <cstdio>
@@ -46,8 +46,8 @@ __global__ void __launch_bounds__(64, 1) tma_kernel(const __grid_constant__ CUte
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) { for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); } asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   __syncthreads();
-  constexpr int ROWS = (V == 1) ? 256 : (V == 3 ? 16 : 128);       // rows per stage-load group
-  constexpr int LOADS_PER_BLOCK = (V == 3) ? 1 : (V == 4 ? 4 : 8);   // stage loads that cover the block's 512 k
+  constexpr int ROWS = (V == 1) ? 256 : (V == 3 ? 32 : 128);       // rows per stage-load group
+  constexpr int LOADS_PER_BLOCK = (V == 3) ? 2 : (V == 4 ? 4 : 8);   // stage loads that cover the block's 512 k
   if (warp == 0) {
     int s = 0; uint32_t ph = 0;
     for (int r = 0; r < repeats; ++r)
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(64, 1) tma_kernel(const __grid_constant__ CUte
             uint8_t* dst = smem + (size_t)s * stage_bytes;
             if (V == 0 || V == 1) tma2d(dst, &tm, &full[s], i * 64, b * ROWS);
             else if (V == 2) { tma2d(dst, &tm, &full[s], i * 64, b * ROWS); tma2d(dst + stage_bytes / 2, &tm, &full[s], i * 64, b * ROWS + 64); }
-            else if (V == 3) tma2d(dst, &tm, &full[s], 0, b * ROWS);
+            else if (V == 3) tma2d(dst, &tm, &full[s], i * 256, b * ROWS);
             else tma3d(dst, &tm, &full[s], 0, i * 2, b * ROWS);
           }
           __syncwarp();
@@ -97,13 +97,13 @@ static int run(EncodeFn enc, uint16_t* w, int64_t rows, int grid, int stages, in
     cuuint32_t box[2] = {64, 128};
     if (V == 1) box[1] = 256;
     if (V == 2) box[1] = 64;
-    if (V == 3) { box[0] = 512; box[1] = 16; }
+    if (V == 3) { box[0] = 256; box[1] = 32; }
     r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, w, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             V == 3 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     stage_bytes = (V == 1) ? 32768 : 16384;
   }
   if (r != CUDA_SUCCESS) { printf("encode failed %d\n", (int)r); return 1; }
-  const int rows_per_block = (V == 1) ? 256 : (V == 3 ? 16 : 128);
+  const int rows_per_block = (V == 1) ? 256 : (V == 3 ? 32 : 128);
   const int n_blocks = (int)(rows / rows_per_block);
   const size_t smem = (size_t)stages * stage_bytes + 1024 + 512;
   CK(cudaFuncSetAttribute(tma_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -134,7 +134,7 @@ int main() {
       for (int st : {2, 3, 5, 8, 12}) if (run<0>(enc, w, rows, grid, st, rep, "v0 box 64k x 128 rows (16 KB)")) return 1;
       for (int st : {2, 3, 6}) if (run<1>(enc, w, rows, grid, st, rep, "v1 box 64k x 256 rows (32 KB)")) return 1;
       for (int st : {5, 12}) if (run<2>(enc, w, rows, grid, st, rep, "v2 2 boxes 64k x 64 rows per stage")) return 1;
-      for (int st : {5, 12}) if (run<3>(enc, w, rows, grid, st, rep, "v3 box 512k x 16 rows, 1 KB rows, no swizzle")) return 1;
+      for (int st : {5, 12}) if (run<3>(enc, w, rows, grid, st, rep, "v3 box 256k x 32 rows, 512 B rows, no swizzle")) return 1;
       for (int st : {3, 6}) if (run<4>(enc, w, rows, grid, st, rep, "v4 3-D box (64, 2 k-blocks, 128 rows) 32 KB")) return 1;
     }
   }

@@ -55,7 +55,7 @@ for cta in (0, 1):
     us = lambda v: (v - t0) / GHZ if v > 0 else float("nan")
     print(f"--- {which} CTA {cta} (leader = CTA 0 of the pair issues the MMAs) ---")
     print("tile | MMA: wait_acc granted first_full last_mma (dur grant->last) | epi0: wait full done (E) | epiL: wait full done (E) | TMA: first last")
-    for i in range(32):
+    for i in range(16):                                        # slots 16.. hold tile 3's k-blocks (below)
         m, e0, e1, pr = t[cta, 0, i], t[cta, 1, i], t[cta, 2, i], t[cta, 3, i]
         if not (m.any() or e0.any() or pr.any()): continue
         f = lambda a: " ".join(f"{us(v):7.2f}" for v in a)
