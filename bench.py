@@ -389,14 +389,7 @@ def run_b200(args):
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True,
         "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": ("cfg3: ArcFace head 512-d, 100k classes, batch 512 bf16 fwd+bwd, 1 B200" if world == 1 else
-                                f"cfg4: ArcFace partial-FC 512-d, 1M classes class-sharded over {world} B200 "
-                                f"({C_local} per rank), batch 4096, one all-reduce each way"),
-                   "B": B, "C_total": C_total, "C_per_rank": C_local, "D": D, "label_smoothing": LS,
-                   "m_eff": round(m_eff, 4), "s_eff": round(s_eff, 4), "engine": args.engine,
-                   "launch": "cuda-graph replay of the captured step" if use_graph else "eager (one C-ABI call per stage)",
-                   "grads": "dx fp32, dW fp32", "l2": "inputs_exceed_l2 (W bf16 + dW fp32 = 3 x C x D x 2 B per rank)",
-                   "parallelism": "single GPU" if world == 1 else f"class-parallel x{world} (NCCL all-reduce [B,4] fwd, [B,D] bwd)"},
+        "config": workload_config(world, args, m_eff, s_eff),
         "algorithmic_tflops": round(flops_step * args.steps / (ms_total * 1e-3) / 1e12, 2),
         "frac_of_bf16_peak": round(flops_step * args.steps / (ms_total * 1e-3) / 1e12 / (pk["tf_sustained"] * world), 4),
         "e2e": {"value": round(e2e_val, 1), "unit": "samples/s", "h2d_bytes_per_step": int(xh.numel() * 2 + yh.numel() * 8),
@@ -868,6 +861,21 @@ def cpu_cfg1_baseline(steps=4):
             "head_share_of_step": round(dth / dt, 5)}
 
 
+def workload_config(world, args, m_eff, s_eff):
+    """The `config` object of the JSON line: the workload BASELINE.json names, identical in both arms (the reference arm
+    times the reference's CPU path on THIS configuration; what it samples of it is stated in its cpu_baseline.sample)."""
+    cfgw = CFG3 if world == 1 else CFG4
+    c_local = cfgw["C"] // world + (1 if cfgw["C"] % world else 0)
+    return {"workload": ("cfg3: ArcFace head 512-d, 100k classes, batch 512 bf16 fwd+bwd, 1 B200" if world == 1 else
+                         f"cfg4: ArcFace partial-FC 512-d, 1M classes class-sharded over {world} B200 "
+                         f"({c_local} per rank), batch 4096, one all-reduce each way"),
+            "B": cfgw["B"], "C_total": cfgw["C"], "C_per_rank": c_local, "D": cfgw["D"], "label_smoothing": LS,
+            "m_eff": round(m_eff, 4), "s_eff": round(s_eff, 4), "engine": args.engine,
+            "launch": "cuda-graph replay of the captured step" if not args.eager else "eager (one C-ABI call per stage)",
+            "grads": "dx fp32, dW fp32", "l2": "inputs_exceed_l2 (W bf16 + dW fp32 = 3 x C x D x 2 B per rank)",
+            "parallelism": "single GPU" if world == 1 else f"class-parallel x{world} (NCCL all-reduce [B,4] fwd, [B,D] bwd)"}
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (torch port of
     src/face_models.py:334-429 + CrossEntropyLoss + autograd), all host threads.
@@ -878,6 +886,9 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import torch_port
+    from b200face.head import effective_margin_scale, head_schedule      # pure Python (the schedule); loads no library
+    mf, sf = head_schedule(EPOCH, 10, True, True, 0.0, 0.3)
+    m_eff, s_eff = effective_margin_scale(32.0, 0.5, mf, sf, True)
     multi = args.gpus > 1
     c = dict(CFG3) if not multi else dict(CFG4, C=CFG4["C"] // 8)
     shards = 8 if multi else 1
@@ -908,10 +919,8 @@ def run_reference(args):
         "impl": "reference", "metric": "arcface_head_samples_per_sec", "value": round(val, 1), "unit": "samples/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warm + 1, "ms_per_step": round(dt * shards * 1e3, 2),
         "higher_is_better": True, "scaling": "strong" if multi else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": ("cfg3: ArcFace head 512-d, 100k classes, batch 512 bf16 fwd+bwd, 1 B200" if not multi else
-                                "cfg4: ArcFace partial-FC 512-d, 1M classes, batch 4096 (reference CPU path: one 125k-class shard "
-                                "timed at the full batch, x8)"),
-                   "B": c["B"], "C_total": c["C"] * shards, "C_timed": c["C"], "D": c["D"], "label_smoothing": LS},
+        "config": workload_config(args.gpus, args, m_eff, s_eff),
+        "timed": {"B": c["B"], "C_timed": c["C"], "shards_extrapolated": shards},
         "cpu_baseline": {"value": round(val, 1), "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": round(val, 1), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "loss": round(float(loss), 5)}), flush=True)
