@@ -68,6 +68,10 @@ PROTOTYPES = {
     "b200f_arcface_bwd_phase": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_int64, c_int64, c_int64, c_int, POINTER(HeadCfg), c_void_p, c_void_p, c_int,
                                         c_void_p, c_size_t, c_void_p]),
+    "b200f_arcface_bwd_parts_ok": (c_int, [c_int64, c_int64, c_int, c_int]),
+    "b200f_arcface_bwd_part": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_int64, c_int64, c_int64, c_int, POINTER(HeadCfg), c_void_p, c_void_p,
+                                       c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "b200f_head_request_dw_sqnorm": (c_int, [c_void_p]),
     "b200f_l2norm_bwd": (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p, c_int64, c_int, c_void_p,
                                  c_void_p, c_void_p]),

@@ -213,10 +213,13 @@ static int arcface_bwd_impl(const char* who, const void* x, const void* w, int d
                             const int64_t* label, const float* lse, const float* grad_scale,
                             const float* dlogits_or_null, int64_t ld_dlogits, int64_t B, int64_t C_local,
                             int64_t class_offset, int D, const b200f_head_cfg* cfg, float* dxhat, float* dw,
-                            const umma::HeadDx* hdx, void* workspace, size_t workspace_bytes, void* stream, int phase = 0) {
+                            const umma::HeadDx* hdx, void* workspace, size_t workspace_bytes, void* stream, int phase = 0,
+                            int cluster_limit = 0) {
   int rc = check_head_args(who, x, w, dtype, inv_nx, inv_nw, label, B, C_local, D, cfg);
   if (rc) return rc;
-  if (phase < 0 || phase > 2) return fail(B200F_ERR_ARG, "%s: phase must be 0, 1 or 2", who);
+  const bool part = phase >= umma::HEAD_BWD_PART_K3A && phase <= umma::HEAD_BWD_PART_K3C;
+  if ((phase < 0 || phase > 2) && !part) return fail(B200F_ERR_ARG, "%s: phase must be 0, 1 or 2", who);
+  if (part && dtype != B200F_F16N) return fail(B200F_ERR_UNSUPPORTED, "%s: parts exist on the tcgen05 engine only", who);
   if (phase == 2 && dtype != B200F_F16N) return B200F_OK;      // CUDA-core engine: phase 1 already did everything
   if (!lse || !grad_scale || !dxhat || !dw) return fail(B200F_ERR_ARG, "%s: null pointer", who);
   const size_t need = b200f_head_workspace_bytes(B, C_local, D, dtype, cfg->engine);
@@ -228,7 +231,7 @@ static int arcface_bwd_impl(const char* who, const void* x, const void* w, int d
     if (dlogits_or_null) return fail(B200F_ERR_UNSUPPORTED, "%s: the tcgen05 engine has no dlogits path", who);
     if (!inv_nw) return fail(B200F_ERR_ARG, "%s: inv_nw required", who);
     return umma::head_bwd(x, w, inv_nw, label, lse, grad_scale, B, C_local, class_offset, D, cfg, dxhat, dw, hdx,
-                          static_cast<char*>(workspace), workspace_bytes, st, phase);
+                          static_cast<char*>(workspace), workspace_bytes, st, phase, cluster_limit);
   }
   const HeadPlan pl = plan_head(B, C_local, D);
   if (dtype == B200F_F32)
@@ -331,6 +334,27 @@ int b200f_arcface_bwd_phase(const void* x, const void* w, int dtype, const float
   if (phase != 1 && phase != 2) return fail(B200F_ERR_ARG, "arcface_bwd_phase: phase must be 1 or 2");
   return arcface_bwd_impl("arcface_bwd_phase", x, w, dtype, inv_nx, inv_nw, label, lse, grad_scale, nullptr, 0, B,
                           C_local, class_offset, D, cfg, dxhat, dw, nullptr, workspace, workspace_bytes, stream, phase);
+}
+
+int b200f_arcface_bwd_parts_ok(int64_t B, int64_t C_local, int D, int dtype) {
+  return (dtype == B200F_F16N && umma::available()) ? umma::head_bwd_parts_ok(B, C_local, D) : 0;
+}
+
+int b200f_arcface_bwd_part(const void* x, const void* w, int dtype, const float* inv_nx, const float* inv_nw,
+                           const int64_t* label, const float* lse, const float* grad_scale, int64_t B,
+                           int64_t C_local, int64_t class_offset, int D, const b200f_head_cfg* cfg, float* dxhat,
+                           float* dw, const void* x_raw_or_null, int x_raw_dtype, float* dx_or_null, void* dx_bf16_or_null,
+                           int part, int max_clusters, void* workspace, size_t workspace_bytes, void* stream) {
+  B200F_NVTX("b200f_arcface_bwd_part");
+  if (part < 1 || part > 3) return fail(B200F_ERR_ARG, "arcface_bwd_part: part must be 1 (G^T), 2 (dW) or 3 (dx)");
+  if (max_clusters < 0) return fail(B200F_ERR_ARG, "arcface_bwd_part: max_clusters < 0");
+  if (x_raw_or_null && !dtype_ok(x_raw_dtype)) return fail(B200F_ERR_ARG, "arcface_bwd_part: bad x_raw dtype %d", x_raw_dtype);
+  const umma::HeadDx hdx{x_raw_or_null, x_raw_dtype, inv_nx, dx_or_null, dx_bf16_or_null};
+  const bool want_dx = part == 3 && dx_or_null != nullptr;
+  if (want_dx && !inv_nx) return fail(B200F_ERR_ARG, "arcface_bwd_part: dx needs inv_nx");
+  return arcface_bwd_impl("arcface_bwd_part", x, w, dtype, inv_nx, inv_nw, label, lse, grad_scale, nullptr, 0, B, C_local,
+                          class_offset, D, cfg, dxhat, dw, want_dx ? &hdx : nullptr, workspace, workspace_bytes, stream,
+                          umma::HEAD_BWD_PART_K3A + part - 1, max_clusters);
 }
 
 int b200f_arcface_bwd_dx(const void* x, const void* w, int dtype, const float* inv_nx, const float* inv_nw,

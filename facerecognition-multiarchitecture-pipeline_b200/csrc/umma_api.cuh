@@ -27,7 +27,14 @@ int head_fwd(const void* xh, const void* wh, const int64_t* label, int64_t B, in
 
 int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t* label, const float* lse,
              const float* grad4, int64_t B, int64_t C, int64_t class_offset, int D, const b200f_head_cfg* cfg,
-             float* dxhat, float* dw, const HeadDx* hdx, char* ws, size_t ws_bytes, cudaStream_t st, int phase = 0);
+             float* dxhat, float* dw, const HeadDx* hdx, char* ws, size_t ws_bytes, cudaStream_t st, int phase = 0,
+             int cluster_limit = 0);
+// phase values beyond 0 / 1 / 2: ONE of the three GEMM stages (b200f_arcface_bwd_part), single class chunk, batch <= 512
+constexpr int HEAD_BWD_PART_K3A = 10;   // logit gradient G^T + r partials
+constexpr int HEAD_BWD_PART_K3B = 11;   // dW from them (cluster_limit: clusters it may occupy, 0 = all)
+constexpr int HEAD_BWD_PART_K3C = 12;   // dx_hat (+ the fused dL/dx tail) from them (cluster_limit likewise)
+// 1 if head_bwd can run in parts for this shape
+int head_bwd_parts_ok(int64_t B, int64_t C, int D);
 
 // ||dW||^2 side output: the calling thread's next head_bwd (phase 0, or phases 1 + 2) leaves sum(dW^2) in out[0]
 void head_request_dw_sqnorm(float* out);

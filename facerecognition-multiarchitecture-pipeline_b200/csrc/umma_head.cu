@@ -107,11 +107,12 @@ static int xw_max_clusters(int pair);
 // 128-row boxes: gemm_b_rows(2))
 template <int PAIR, bool A_MN, bool B_MN, class Epi>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
-                       const typename Epi::Params& ep, cudaStream_t st, const char* what) {
+                       const typename Epi::Params& ep, cudaStream_t st, const char* what, int cluster_limit = 0) {
   auto kern = gemm_kernel<PAIR, A_MN, B_MN, Epi>;
   B200F_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   const int work = p.m_tiles * p.n_tiles * p.k_splits;
   int clusters = (PAIR == 2) ? xw_max_clusters(2) : num_sms();
+  if (cluster_limit > 0 && cluster_limit < clusters) clusters = cluster_limit;
   if (clusters > work) clusters = work;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(clusters * PAIR)); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
@@ -318,12 +319,13 @@ static int gcd_int(int a, int b) { while (b) { int t = a % b; a = b; b = t; } re
 
 struct XwPlan { int pair, m_groups, n_tiles, n_clusters, n_chunks, items, grid; };
 
-static XwPlan xw_plan(int64_t B, int64_t C, int pair, int max_chunks = 0) {
+static XwPlan xw_plan(int64_t B, int64_t C, int pair, int max_chunks = 0, int cluster_limit = 0) {
   XwPlan q{};
   q.pair = pair;
   q.m_groups = (int)ceil_div(B, (int64_t)XW_M * pair);
   q.n_tiles = (int)ceil_div(C, (int64_t)XW_WROWS * pair);
   q.n_clusters = xw_max_clusters(pair);
+  if (cluster_limit > 0 && cluster_limit < q.n_clusters) q.n_clusters = cluster_limit;   // part of the chip (head_bwd parts)
   if (max_chunks > 0) {                                   // few, long chunks (the gallery's sample pre-pass)
     q.n_chunks = max_chunks < q.n_tiles ? max_chunks : q.n_tiles;
     q.items = q.m_groups * q.n_chunks;
@@ -652,14 +654,27 @@ __global__ void __launch_bounds__(256) fold_partials_kernel(const float* __restr
   if (threadIdx.x == 0) out[0] = accumulate ? out[0] + sh[0] : sh[0];
 }
 
+int head_bwd_parts_ok(int64_t B, int64_t C, int D) {
+  if (B <= 0 || C <= 0 || D <= 0 || D % 8 != 0 || D > XW_MAX_KB * XW_K) return 0;
+  const Plan pl = make_plan(B, C, D);
+  return (pl.n_chunks == 1 && pl.fused_dw) ? 1 : 0;
+}
+
 int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t* label, const float* lse,
              const float* grad4, int64_t B, int64_t C, int64_t class_offset, int D, const b200f_head_cfg* cfg,
-             float* dxhat, float* dw, const HeadDx* hdx, char* ws, size_t ws_bytes, cudaStream_t st, int phase) {
+             float* dxhat, float* dw, const HeadDx* hdx, char* ws, size_t ws_bytes, cudaStream_t st, int phase,
+             int cluster_limit) {
   int rc = check_shape(B, C, D, cfg); if (rc) return rc;
   const Plan pl = make_plan(B, C, D);
   if (ws_bytes < pl.total) return fail(B200F_ERR_WORKSPACE, "umma head_bwd: workspace too small");
-  if (phase < 0 || phase > 2) return fail(B200F_ERR_ARG, "umma head_bwd: phase must be 0, 1 or 2");
-  if (phase != 0 && hdx != nullptr) return fail(B200F_ERR_ARG, "umma head_bwd: the fused dL/dx tail belongs to the unsplit call");
+  const bool part = phase >= HEAD_BWD_PART_K3A && phase <= HEAD_BWD_PART_K3C;
+  if ((phase < 0 || phase > 2) && !part) return fail(B200F_ERR_ARG, "umma head_bwd: phase must be 0, 1 or 2 (or a part)");
+  if (phase != 0 && phase != HEAD_BWD_PART_K3C && hdx != nullptr)
+    return fail(B200F_ERR_ARG, "umma head_bwd: the fused dL/dx tail belongs to the unsplit call or to the dx part");
+  // Parts (b200f_arcface_bwd_part): the three GEMM stages as separate calls, the dW and the dx stage each on a bounded
+  // number of clusters, so that the caller can run them SIDE BY SIDE on two streams behind K3a.  One class chunk only.
+  if (part && (pl.n_chunks != 1 || !pl.fused_dw))
+    return fail(B200F_ERR_UNSUPPORTED, "umma head_bwd: parts need a single class chunk and batch <= 512");
   // phase 0: per class chunk K3a -> K3b -> K3c -> split reduction (one call does everything).
   // phases 1 / 2 (class shards): the dx_hat half first -- per chunk K3a -> K3c -> split reduction -> K3b, WITHOUT the last
   // chunk's K3b (phase 1) -- so that the caller can start the cross-rank all-reduce of dx_hat on another stream, and then
@@ -668,13 +683,18 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
   uint16_t* G = reinterpret_cast<uint16_t*>(ws + pl.off_G);
   float* dxpart = reinterpret_cast<float*>(ws + pl.off_dxpart);
   float* const sq_out = g_dw_sq_out;                        // consumed by the call that runs the last dW GEMM
-  if (phase != 1) g_dw_sq_out = nullptr;
+  if (phase == 0 || phase == 2 || phase == HEAD_BWD_PART_K3B) g_dw_sq_out = nullptr;
   float* const sq_part = sq_out ? reinterpret_cast<float*>(ws + pl.off_sq) : nullptr;
   const float S = cfg->operand_scale;
   CUtensorMap tx_k, tx_mn;
   rc = tmap_kmajor(&tx_k, xh, B, D, D, XW_M); if (rc) return rc;
   rc = tmap_mnmajor(&tx_mn, xh, D, B, D); if (rc) return rc;
   stage_reset(EV_K3A); stage_reset(EV_K3B); stage_reset(EV_K3C);
+  // K3a's epilogue geometry decides how many r partial rows K3b sums: read the tunable ONCE per backward -- and in phase 2
+  // take what this thread's phase 1 used (another thread may have moved the tunable between the two calls)
+  static thread_local int t_k3a_mode = 1;
+  if (phase == 0 || phase == 1 || phase == HEAD_BWD_PART_K3A) t_k3a_mode = g_epi_groups.load(std::memory_order_relaxed);
+  const int k3a_mode = t_k3a_mode;
   const int gpair = pl.fwd.pair;                            // generic core: single CTAs or cta_group::2 pairs, like K2 / K3a
   const int64_t wrb = (int64_t)D * 2;
   int chunk_no = 0;
@@ -691,7 +711,6 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
     auto run_k3a = [&]() -> int {
     CUtensorMap tw_k;
     int rc = tmap_kmajor(&tw_k, wc, cnt, D, D, XW_WROWS); if (rc) return rc;
-    const int k3a_mode = g_epi_groups.load(std::memory_order_relaxed);
     const int hints_k3a = hints;
     auto fill = [&](auto& e) {
       e.label = label; e.lse = lse; e.grad4 = grad4; e.class_offset = class_offset + c0;
@@ -726,7 +745,7 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
     // --- K3b: dW[c0 + c, d] = inv_nw_c (sum_b G^T[c, b] x_hat[b, d] - w_hat[c, d] r_c), class-major (the thread owns a
     //     class row), normalise-backward fused; its coefficients { inv_nw_c / (S g_scale), r_c } are formed in the epilogue
     //     from K3a's partials (CoefSrc)
-    const CoefSrc coef{r_part, qg.m_groups * (g_epi_groups.load(std::memory_order_relaxed) == 4 ? 4 : 2), pl.Cc, inv_nw, grad4, S};
+    const CoefSrc coef{r_part, qg.m_groups * (k3a_mode == 4 ? 4 : 2), pl.Cc, inv_nw, grad4, S};
     auto run_k3b = [&]() -> int {
     int rc = B200F_OK;
     int n_sq_used = 0;
@@ -735,7 +754,7 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
     if (pl.fused_dw) {                                      // x_hat^T resident, G^T rows streamed
       CUtensorMap tg_k;
       rc = tmap_kmajor(&tg_k, G, cnt, B, pl.ldg, XW_WROWS); if (rc) return rc;
-      const XwPlan qw = xw_plan(D, cnt, qg.pair);
+      const XwPlan qw = xw_plan(D, cnt, qg.pair, 0, phase == HEAD_BWD_PART_K3B ? cluster_limit : 0);
       const bool k3b_rev = g_k3b_reverse.load(std::memory_order_relaxed) != 0;   // read K3a's freshest G^T rows first
       const int gt_lhint = (hints & 32) ? 2 : 0;
       // x_hat^T (K1's output) is older than K3a: the producers load it while K3a drains ("early" = 2: then wait, then G^T)
@@ -804,14 +823,23 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
     CUtensorMap tg_mn, tw_mn;
     int rc = tmap_mnmajor(&tg_mn, G, B, cnt, pl.ldg); if (rc) return rc;
     rc = tmap_mnmajor(&tw_mn, wc, D, cnt, D); if (rc) return rc;
-    GemmParams px = gemm_params((int)B, D, (int)cnt, pl.dx_splits, true, true, FMT_F16, FMT_F16, gpair);
+    // the dx part on a bounded number of clusters: as many K splits as those clusters carry output tiles
+    const int k3c_limit = (phase == HEAD_BWD_PART_K3C) ? cluster_limit : 0;
+    int dx_splits = pl.dx_splits;
+    if (k3c_limit > 0) {
+      const int out_tiles = (int)ceil_div(B, (int64_t)BLOCK_M * gpair) * (int)ceil_div((int64_t)D, (int64_t)BLOCK_N);
+      dx_splits = k3c_limit / out_tiles;
+      if (dx_splits < 1) dx_splits = 1;
+      if (dx_splits > pl.dx_splits) dx_splits = pl.dx_splits;
+    }
+    GemmParams px = gemm_params((int)B, D, (int)cnt, dx_splits, true, true, FMT_F16, FMT_F16, gpair);
     // K3c reads G^T (K3a) and w_hat, writes dxpart: nothing of K3b's -- behind K3b it need not wait for it; directly behind
     // K3a (phases 1 / 2) it does
     px.early = (phase == 0) ? g_early.load(std::memory_order_relaxed) : 0;
     EpiStore::Params ex{dxpart, (int64_t)D, B * (int64_t)D, 0, 1.0f, nullptr};
     stage_event(EV_K3C, false, st);
-    rc = (gpair == 2) ? launch_gemm<2, true, true, EpiStore>(tg_mn, tw_mn, px, ex, st, "umma K3c dX (cta pair)")
-                      : launch_gemm<1, true, true, EpiStore>(tg_mn, tw_mn, px, ex, st, "umma K3c dX");
+    rc = (gpair == 2) ? launch_gemm<2, true, true, EpiStore>(tg_mn, tw_mn, px, ex, st, "umma K3c dX (cta pair)", k3c_limit)
+                      : launch_gemm<1, true, true, EpiStore>(tg_mn, tw_mn, px, ex, st, "umma K3c dX", k3c_limit * 2);
     stage_event(EV_K3C, true, st);
     if (rc) return rc;
     const int64_t n = B * (int64_t)D;
@@ -848,7 +876,11 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
       rc = run_k3a(); if (rc) return rc;
       rc = run_k3c(); if (rc) return rc;
       if (!last_chunk) { rc = run_k3b(); if (rc) return rc; }
-    } else {
+    } else if (phase == HEAD_BWD_PART_K3A) {
+      rc = run_k3a(); if (rc) return rc;
+    } else if (phase == HEAD_BWD_PART_K3C) {
+      rc = run_k3c(); if (rc) return rc;
+    } else {                                                  // phase 2, or the dW part
       rc = run_k3b(); if (rc) return rc;
     }
   }

@@ -10,6 +10,8 @@ GPU so the Streamlit loop (src/app.py:631-639) does not re-upload it every frame
 No CPU path: the kernels run on CUDA or the call raises."""
 from __future__ import annotations
 
+import collections
+import weakref
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -67,6 +69,31 @@ class PreparedGallery:
         return self.key == (g.data_ptr(), g._version, tuple(g.shape), metric)
 
 
+# Callers that pass the same gallery TENSOR again and again without keeping a PreparedGallery (compare_faces in a loop,
+# gallery_topk(q, g)) would pay a full pass over g plus a host read of its maximum per call.  The last few prepared
+# operands are therefore remembered per tensor OBJECT (a weak reference: the entry dies with the tensor, and a new tensor
+# that happens to land on the same address never matches) and per version counter.  As with every version-keyed cache,
+# writes through `.data` are invisible to it -- GalleryIndex, which owns its rows, is the interface for galleries that change.
+_PREPARED_KEEP = 2
+_prepared_cache: "collections.OrderedDict[int, tuple]" = collections.OrderedDict()
+
+
+def _prepared_for(g: torch.Tensor, metric: str) -> PreparedGallery:
+    ent = _prepared_cache.get(id(g))
+    if ent is not None:
+        ref, prep = ent
+        if ref() is g and prep.matches(g, metric):
+            _prepared_cache.move_to_end(id(g))
+            return prep
+        del _prepared_cache[id(g)]
+    prep = PreparedGallery(g, metric)
+    key = id(g)
+    _prepared_cache[key] = (weakref.ref(g, lambda _r, k=key: _prepared_cache.pop(k, None)), prep)
+    while len(_prepared_cache) > _PREPARED_KEEP:
+        _prepared_cache.popitem(last=False)
+    return prep
+
+
 def tensor_engine_ok(q: torch.Tensor, g: torch.Tensor, engine: int) -> bool:
     """The bf16 tcgen05 scan + exact re-rank takes fp32 inputs with D % 8 == 0, D <= 512 on sm_100; AUTO uses it
     once the scan is big enough to matter."""
@@ -116,7 +143,7 @@ def gallery_topk(q: torch.Tensor, g: torch.Tensor, k: int = 1, thresh: float = 1
         # tensor engine: bf16 tcgen05 scan of the prepared gallery, exact fp32 re-rank, proof of exactness per query
         # (unproven queries are recomputed by the exact engine on the device; redo_count counts them)
         if prepared is None or not prepared.matches(g, metric):
-            prepared = PreparedGallery(g, metric)
+            prepared = _prepared_for(g, metric)
         nbytes = lib.b200f_gallery_tc_workspace_bytes(Q, N, D, k)
         ws = _lib.workspace(nbytes, dev, "gallery_tc")
         check(lib.b200f_gallery_topk_tc(ptr(q), ptr(g), ptr(prepared.g16), ptr(prepared.bias), ptr(q_inv), ptr(gi), Q, N,
@@ -158,7 +185,7 @@ def gallery_topk_batches(batches: Sequence[torch.Tensor], g: torch.Tensor, k: in
                              redo_count=redo_count) for q in batches]
     # what every call shares is built once, on the caller's stream, before the side streams fork from it
     if prepared is None and any(tensor_engine_ok(q, g, engine) for q in batches if q.dtype == g.dtype):
-        prepared = PreparedGallery(g, metric)
+        prepared = _prepared_for(g, metric)
     g_inv = _inv_norm(g) if metric == "cos" else None
     cur = torch.cuda.current_stream(dev)
     depth = min(depth, len(batches))

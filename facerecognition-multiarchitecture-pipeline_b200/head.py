@@ -310,6 +310,27 @@ def _bwd_kernels(xo, wo, label, inv_nx, inv_nw, lse, grad4, cfg: HeadCfg, class_
         dx = torch.empty(B, D, dtype=torch.float32, device=dev)
         lowp = torch.empty(B, D, dtype=torch.bfloat16, device=dev) if dx_bf16 else None
         rp, rd = _raw_rows(x_raw, xo)
+        pairs_c = BWD_SIDE_BY_SIDE_PAIRS
+        if (pairs_c > 0 and dlogits is None and xo.dtype == torch.float16
+                and lib.b200f_arcface_bwd_parts_ok(B, C, D, dtype_code(xo))):
+            total = max(2, torch.cuda.get_device_properties(dev).multi_processor_count // 2)
+            pairs_c = min(pairs_c, total - 1)
+
+            def part(n, limit):
+                check(lib.b200f_arcface_bwd_part(ptr(xo), ptr(wo), dtype_code(xo), ptr(inv_nx), ptr(inv_nw), ptr(label),
+                                                 ptr(lse), ptr(grad4), B, C, int(class_offset), D, cfg, ptr(dxhat), ptr(dw),
+                                                 rp, rd, ptr(dx), ptr(lowp), n, limit, ptr(ws), ws.numel(), stream_ptr(dev)),
+                      "b200f_arcface_bwd_part")
+            with _lib.timed("arcface_bwd", dev):
+                cur = torch.cuda.current_stream(dev)
+                side = _overlap_stream(dev)
+                part(1, 0)                                        # K3a: G^T and the r partials
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    part(3, pairs_c)                              # K3c + split reduction + dL/dx
+                part(2, total - pairs_c)                          # K3b beside it
+                cur.wait_stream(side)
+            return dxhat, dw, dx, lowp
         with _lib.timed("arcface_bwd", dev):
             check(lib.b200f_arcface_bwd_dx(ptr(xo), ptr(wo), dtype_code(xo), ptr(inv_nx), ptr(inv_nw), ptr(label), ptr(lse),
                                            ptr(grad4), ptr(dlogits), (dlogits.shape[1] if dlogits is not None else 0),
@@ -339,6 +360,11 @@ def _normalize_bwd(xo, inv_nx, dxhat, x_raw=None, dx_bf16=False):
 _OVERLAP_STREAMS: dict = {}
 # class-sharded backward: run the dx_hat all-reduce on a side stream under the last dW GEMM (B200F_OVERLAP=0: in stream order)
 OVERLAP_DXHAT_ALLREDUCE = os.environ.get("B200F_OVERLAP", "1") != "0"
+# Unsharded backward at batch <= 512 (one class chunk): the dW GEMM (K3b: bound by its epilogue's latency on every SM, the
+# tensor pipe 30 % busy) and the dx GEMM (K3c: bound by the tensor pipe) run SIDE BY SIDE behind K3a, K3c + the split
+# reduction + dL/dx on a side stream with this many CTA pairs, K3b on the rest of the chip (b200f_arcface_bwd_part).
+# 0 = one after the other (b200f_arcface_bwd_dx).  B200F_BWD_SPLIT overrides.
+BWD_SIDE_BY_SIDE_PAIRS = int(os.environ.get("B200F_BWD_SPLIT", "24"))
 
 
 def _overlap_stream(dev) -> torch.cuda.Stream:

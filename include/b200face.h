@@ -13,10 +13,12 @@
  *     (PyTorch) owns every buffer including the workspace;
  *   - the last argument is the cudaStream_t to launch on (void* so no CUDA header is needed);
  *   - no allocation, no implicit synchronisation; results depend only on the arguments.  The only process-wide
- *     state is the set of performance tunables (b200f_set_tunable, tests / bench sweeps): they select between
- *     kernel variants with identical results, a workspace queried under one setting is valid under every other
- *     (sizes are the maximum over the variants), so a thread that changes one cannot invalidate another thread's
- *     call (the Streamlit UI thread + webcam thread of src/app.py:331-335,639 may both be inside the library);
+ *     state is the set of performance tunables (b200f_set_tunable): they select between kernel variants with the
+ *     same results and exist for tests and bench sweeps.  Set them before the first call or between calls, not while
+ *     another thread is inside the library: every call reads each tunable once, so a call is consistent in itself,
+ *     but "pair" and "g_chunk_mb" change the workspace layout between a b200f_arcface_bwd_phase 1 / 2 pair.  With
+ *     the defaults untouched any number of threads may call in concurrently (the Streamlit UI thread + webcam
+ *     thread of src/app.py:331-335,639), each on its own stream with its own workspace;
  *   - return 0 on success, <0 on error; b200f_last_error() gives the thread-local message;
  *   - a pipeline wait inside a tcgen05 kernel that expires (seconds; a bug, a stalled peer CTA) ABORTS the kernel
  *     with a trap: the next CUDA call on the stream returns an error, nothing computed from partial accumulators
@@ -222,6 +224,29 @@ int b200f_arcface_bwd_phase(const void* x, const void* w, int dtype,
                             int64_t B, int64_t C_local, int64_t class_offset, int D,
                             const b200f_head_cfg* cfg, float* dxhat, float* dw, int phase,
                             void* workspace, size_t workspace_bytes, void* stream);
+
+/* The backward as its three GEMM stages, for a caller that runs two of them SIDE BY SIDE (single class chunk, batch <= 512,
+ * tcgen05 engine: b200f_arcface_bwd_parts_ok says whether the shape qualifies).
+ *   part 1: K3a -- the logit gradient G^T and the r partials, into the workspace;
+ *   part 2: K3b -- dW from them, on at most max_clusters CTA pairs (0 = the whole chip);
+ *   part 3: K3c + split reduction -- dxhat (and, when dx_or_null is given, dL/dx and its bf16 copy as in
+ *           b200f_arcface_bwd_dx), on at most max_clusters CTA pairs.
+ * Parts 2 and 3 only READ what part 1 left in the workspace and write disjoint outputs, so behind part 1 they may run on
+ * two streams at once.  Why: at 512 x 100 k x 512 the dW stage is bound by the latency of its epilogue on every SM (87 us
+ * on 74 pairs, 133 us on 44) and the dx stage by the tensor pipe (51 us on 74 pairs, 81 us on 30): one after the other they
+ * take 145 us, side by side on 44 + 30 pairs less.  Results: dW as from the single call, bit for bit; dxhat
+ * sums fewer, longer K splits (same inputs, last-bit differences).  A b200f_head_request_dw_sqnorm request is consumed
+ * by part 2. */
+int b200f_arcface_bwd_parts_ok(int64_t B, int64_t C_local, int D, int dtype);
+int b200f_arcface_bwd_part(const void* x, const void* w, int dtype,
+                           const float* inv_nx, const float* inv_nw, const int64_t* label,
+                           const float* lse, const float* grad_scale,
+                           int64_t B, int64_t C_local, int64_t class_offset, int D,
+                           const b200f_head_cfg* cfg,
+                           float* dxhat, float* dw,
+                           const void* x_raw_or_null, int x_raw_dtype, float* dx_or_null, void* dx_bf16_or_null,
+                           int part, int max_clusters,
+                           void* workspace, size_t workspace_bytes, void* stream);
 
 /* K3 for an unsharded head, finished: b200f_arcface_bwd, then dL/dx = normalise-backward of dxhat (below) written to
  * dx [B,D] fp32 and, optionally, as bf16 (the cast autograd applies for a bf16 input) -- on the tcgen05 engine inside

@@ -213,3 +213,33 @@ def test_batches_in_flight_equal_serial_calls(cuda_device, metric, depth):
     torch.cuda.synchronize()
     for a, b in zip(got, want):
         assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+
+
+def test_repeated_calls_reuse_the_prepared_operand_of_the_same_tensor(cuda_device):
+    """gallery_topk(q, g) without a PreparedGallery: the operand of the SAME tensor object is built once (weak reference +
+    version counter), rebuilt after an in-place change, never shared with another tensor, and dropped with the tensor."""
+    import gc
+    from b200face import gallery as G
+    from b200face import _lib
+    g0 = torch.Generator().manual_seed(3)
+    gal = torch.randn(20000, 256, generator=g0).to(cuda_device)
+    q = (gal[:300] + 0.01 * torch.randn(300, 256, generator=g0).to(cuda_device)).contiguous()
+    G._prepared_cache.clear()
+    i1, s1, a1 = G.gallery_topk(q, gal, 3, 1.0, engine=_lib.ENGINE_TCGEN05)
+    prep = G._prepared_cache[id(gal)][1]
+    i2, s2, a2 = G.gallery_topk(q, gal, 3, 1.0, engine=_lib.ENGINE_TCGEN05)
+    assert G._prepared_cache[id(gal)][1] is prep                   # reused
+    assert torch.equal(i1, i2) and torch.equal(s1, s2)
+    assert torch.equal(i1[:, 0].cpu(), torch.arange(300))
+    gal.mul_(-1.0)                                                  # in place: the version counter moves
+    i3, _, _ = G.gallery_topk(q, gal, 3, 1.0, engine=_lib.ENGINE_TCGEN05)
+    assert G._prepared_cache[id(gal)][1] is not prep
+    ref3, _, _ = G.gallery_topk(q, gal, 3, 1.0, engine=_lib.ENGINE_SIMT)
+    assert torch.equal(i3, ref3)
+    other = gal.clone()
+    G.gallery_topk(q, other, 3, 1.0, engine=_lib.ENGINE_TCGEN05)
+    assert G._prepared_cache[id(other)][1] is not G._prepared_cache[id(gal)][1]
+    n = len(G._prepared_cache)
+    del other
+    gc.collect()
+    assert len(G._prepared_cache) == n - 1                          # the entry died with its tensor

@@ -265,6 +265,49 @@ def test_few_classes_many_samples(cuda_device, patch, n_cls):
         assert rel_err(dw[c], ref["dw"][c]) < TOL_BF16
 
 
+@pytest.mark.parametrize("B,C,pairs", [(512, 20000, 24), (300, 4097, 10), (512, 33, 40), (64, 1000, 1)])
+def test_backward_side_by_side_equals_one_after_the_other(cuda_device, B, C, pairs):
+    """b200f_arcface_bwd_part: K3a, then the dW GEMM on the main stream BESIDE the dx GEMM + split reduction + dL/dx on a
+    side stream, each on its share of the CTA pairs -- against the single call (b200f_arcface_bwd_dx).  dW bit for bit
+    (same kernel, same inputs, fewer clusters); dx sums fewer, longer K splits: last-bit differences only.  The ||dW||^2
+    side output goes through the dW part."""
+    import b200face
+    from b200face import head as H
+    x, w, y = _random_case(B, C, 512, 31 * B + C)
+    xb, wb = x.bfloat16(), w.bfloat16()
+
+    def step(pairs_c):
+        old = H.BWD_SIDE_BY_SIDE_PAIRS
+        H.BWD_SIDE_BY_SIDE_PAIRS = pairs_c
+        try:
+            head = b200face.ArcMarginProduct(512, C).to(cuda_device)
+            head.update_epoch(12); head.train()
+            head.track_dw_norm = True
+            with torch.no_grad():
+                head.weight.copy_(wb.float())
+            xg = xb.to(cuda_device).requires_grad_(True)
+            loss = head.forward_loss(xg, y.to(cuda_device), 0.05)
+            loss.backward()
+            torch.cuda.synchronize()
+            return (float(loss), head.weight.grad.clone(), head.last_stats.dx_f32.clone(), xg.grad.clone(),
+                    float(head.last_stats.dw_sqnorm))
+        finally:
+            H.BWD_SIDE_BY_SIDE_PAIRS = old
+    l0, dw0, dx0, gx0, sq0 = step(0)
+    l1, dw1, dx1, gx1, sq1 = step(pairs)
+    assert l0 == l1
+    assert torch.equal(dw0, dw1)
+    assert rel_err(dx1.cpu().numpy(), dx0.cpu().numpy()) < 2e-5   # fp32 sums of 20 k terms in another grouping (measured 4e-6)
+    assert rel_err(gx1.float().cpu().numpy(), gx0.float().cpu().numpy()) < 2e-3      # bf16 roundings of nearly equal values
+    assert sq1 == pytest.approx(sq0, rel=1e-6)
+    assert _lib_timeout_clear()
+
+
+def _lib_timeout_clear():
+    from b200face import _lib
+    return _lib.load_library().b200f_umma_timeout_flag(1) == 0
+
+
 def test_nan_inf_scrub(cuda_device):
     """face_models.py:423-427: non-finite logits become 0 (and their gradient is cut)."""
     import b200face
