@@ -751,11 +751,16 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
           tmem_ld32_async(taddr, va);
 #pragma unroll 1
           for (int s = 0; s < SLICES; s += 2) {
+            // __syncwarp() behind each prefetch: ptxas otherwise sinks the tcgen05.ld to the END of the slice's first basic
+            // block (behind all of its math: it gives the next slice's accumulators the registers of this slice's
+            // temporaries), and the load's latency then sits at the top of the next slice
             tmem_ld_wait_dep(va);
             tmem_ld32_async(taddr + (uint32_t)(s + 1) * SC, vb);
+            __syncwarp();
             Epi::slice(stt, ep, p, it, va, col_base + s * SC, gscratch);
             tmem_ld_wait_dep(vb);
             if (s + 2 < SLICES) tmem_ld32_async(taddr + (uint32_t)(s + 2) * SC, va);
+            __syncwarp();
             Epi::slice(stt, ep, p, it, vb, col_base + (s + 1) * SC, gscratch);
           }
           XW_TL(lane == 0 && (it.ew == 0 || it.ew == GW - 1), it.ew == 0 ? 1 : 2, n, 2);
@@ -800,9 +805,11 @@ xw_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
         for (int s = 0; s < SLICES; s += 2) {
           tmem_ld_wait_dep(va);
           tmem_ld32_async(taddr + (uint32_t)(s + 1) * SC, vb);
+          __syncwarp();                                          // keeps the prefetch where it is written (see the SWAP loop)
           if (cls_base + s * SC < p.C) xw_call_slice<Epi>(stt, ep, p, it, va, cls_base + s * SC, gscratch);
           tmem_ld_wait_dep(vb);
           if (s + 2 < SLICES) tmem_ld32_async(taddr + (uint32_t)(s + 2) * SC, va);
+          __syncwarp();
           if (cls_base + (s + 1) * SC < p.C) xw_call_slice<Epi>(stt, ep, p, it, vb, cls_base + (s + 1) * SC, gscratch);
         }
         XW_TL(lane == 0 && (it.ew == 0 || it.ew == GW - 1), it.ew == 0 ? 1 : 2, n, 2);

@@ -287,7 +287,10 @@ struct XwBwdGTT {
   // phi / dphi, exp2, a scalar store) while its tile's accumulator stage is held; 3.5 of them per CTA and item sat on the
   // critical path (K3a 65 us against 60 us with the labels out of range).  At the end of the item they run lane-parallel.
   static constexpr int kQueue = 8;
-  struct State { float gs, r; int cls; bool row_ok; uint64_t pol; int nq; uint32_t q_s; };
+  // a / gq / lim / tab_s: per-item constants of the fast path, formed ONCE (item_begin).  Re-forming them in every slice
+  // put an LDC -> FMUL -> FMUL chain in front of the slice's first FFMA: with two epilogue warps per scheduler nothing hid it
+  // (ncu, B = 4096 x 125 k: 5 % of the kernel's stall samples on that one FMUL).
+  struct State { float gs, r; int cls; bool row_ok; uint64_t pol; int nq; uint32_t q_s; float a, gq, lim; uint32_t tab_s; };
 
   static __device__ __forceinline__ void item_begin(State& st, const Params& ep, const XwParams& p, const XwItem& it,
                                                     float* scratch, int TN) {
@@ -309,6 +312,10 @@ struct XwBwdGTT {
     st.r = 0.f; st.cls = 0; st.row_ok = false;
     st.pol = l2_policy(ep.gt_hint);
     st.nq = 0;
+    st.a = ep.inv_scale * ep.hm.s_eff * LOG2E;                // p = 2^(acc * a - lse log2 e)
+    st.gq = st.gs * (ep.ls_eps * ep.inv_Ctot);
+    st.lim = (ep.hm.s_eff > 0.f) ? cos_hi() / ep.inv_scale : -1.0f;   // |acc| above it (or NaN, or s_eff <= 0): element-wise path
+    st.tab_s = smem_u32(scratch);
     st.q_s = smem_u32(scratch + 2 * TN) + (uint32_t)it.ew * (kQueue * 16);   // 2 * TN + 16 warps * 32 floats <= 1024 floats
   }
   static __device__ __forceinline__ void tile_begin(State& st, const Params&, const XwParams& p, const XwItem& it) {
@@ -317,28 +324,43 @@ struct XwBwdGTT {
 
   static __device__ __forceinline__ void slice(State& st, const Params& ep, const XwParams& p, const XwItem& it,
                                                float (&v)[SC], int col0, float* scratch) {
-    const float s_eff = ep.hm.s_eff;
-    const float isc = ep.inv_scale;
-    const float a = isc * s_eff * LOG2E;                      // p = 2^(acc * a - lse log2 e)
-    const float lo = cos_lo(), hi = cos_hi();
-    const float gs = st.gs;
-    const float q_off = ep.ls_eps * ep.inv_Ctot;
-    const float gq = gs * q_off;
-    // explicit ld.shared: through the generic pointer these compile to LD.E, which queues in the global load/store
-    // path behind this kernel's own G^T stores
-    const uint32_t tb_s = smem_u32(scratch + col0);
-    float g[SC];
+    // Fast path first, for every slice, in blocks of 16 columns: table loads -> exponentials -> fp16 pack -> ONE 32-byte store
+    // per block, the r sum and the |max| test riding along.  Whether the slice needed the element-wise path is judged AFTER
+    // its stores; if so (rare) that path runs over the same registers and overwrites them.  Why this order: with the test
+    // in front of the stores all SC gradients were live next to the SC accumulators, ptxas gave the NEXT slice's
+    // tcgen05.ld the same registers and could issue it only at the end of this slice -- its latency sat at the top of every
+    // slice (ncu: 13 % of the slice's stall samples on the first instruction behind tcgen05.wait::ld).
+    const float a = st.a, gs = st.gs, gq = st.gq;
+    const uint32_t tb_s = st.tab_s + (uint32_t)col0 * 4u;
+    const int64_t b0 = (int64_t)it.group * p_tn(p) + col0;
+    uint16_t* const gdst = ep.GT + (int64_t)st.cls * ep.ldgt + b0;
+    const bool cols_full = b0 + SC <= p.B;                     // warp-uniform
     float am4[4] = {0.f, 0.f, 0.f, 0.f};
+    float r4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int j = 0; j < SC; j += 4) {
-      float bb[4];                                             // -lse_b log2 e of the four batch rows (columns)
-      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                   : "=f"(bb[0]), "=f"(bb[1]), "=f"(bb[2]), "=f"(bb[3]) : "r"(tb_s + j * 4));
+    for (int h = 0; h < SC; h += 16) {
+      uint32_t w1[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float tt = v[j + u];
-        g[j + u] = fmaf(gs, ex2_approx(fmaf(tt, a, bb[u])), -gq);
-        asm("max.NaN.xorsign.abs.f32 %0, %0, %1;" : "+f"(am4[u]) : "f"(tt));
+      for (int j = 0; j < 16; j += 4) {
+        float bb[4];                                           // -lse_b log2 e of the four batch rows (columns)
+        // explicit ld.shared: through the generic pointer these compile to LD.E, which queues in the global load/store
+        // path behind this kernel's own G^T stores
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(bb[0]), "=f"(bb[1]), "=f"(bb[2]), "=f"(bb[3]) : "r"(tb_s + (uint32_t)(h + j) * 4u));
+        float g4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float tt = v[h + j + u];
+          g4[u] = fmaf(gs, ex2_approx(fmaf(tt, a, bb[u])), -gq);
+          asm("max.NaN.xorsign.abs.f32 %0, %0, %1;" : "+f"(am4[u]) : "f"(tt));
+          r4[u] = fmaf(g4[u], tt, r4[u]);
+        }
+        w1[j / 2] = pack_f16(g4[0], g4[1]);
+        w1[j / 2 + 1] = pack_f16(g4[2], g4[3]);
+      }
+      if (cols_full && st.row_ok && !(B200F_PROBE_ON(ep, 2) && w1[0] != 0x12345678u)) {
+        if (ep.gt_hint) st_global_256_hint(gdst + h, w1[0], w1[1], w1[2], w1[3], w1[4], w1[5], w1[6], w1[7], st.pol);
+        else st_global_256(gdst + h, w1[0], w1[1], w1[2], w1[3], w1[4], w1[5], w1[6], w1[7]);
       }
     }
     float amax = 0.f;
@@ -348,65 +370,60 @@ struct XwBwdGTT {
     // a target element sits in this slice iff one of its SC batch rows is labelled with one of the warp's 32 classes
     const int* tl = reinterpret_cast<const int*>(scratch) + p_tn(p) + col0;
     int lab_l;
-    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(lab_l) : "r"(smem_u32(tl + (it.lane & (SC - 1)))));
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(lab_l) : "r"(st.tab_s + (uint32_t)(p_tn(p) + col0 + (it.lane & (SC - 1))) * 4u));
     const int c_w0 = st.cls - it.lane;
-    // Element-wise path only for slices that need the clamp.  Target elements (a batch row of this slice labelled with one
-    // of the warp's 32 classes: 0.5 % of the slices at cfg3, but 64 % of the tiles then waited for a warp in that path --
-    // K3a 71.5 us against 62.7 us with the labels out of range, tools/careful_probe.py) go through the fast path like any
-    // other element and are PATCHED behind the slice's stores (below): the lane that checked the column hands (column,
-    // class) to the lane that owns the class, which overwrites its one fp16 element and corrects its r sum.  The patch
-    // sits after the hot code so that the phi / dphi call costs the slices without a target nothing.
+    // Element-wise path only for slices that need the clamp (or whose columns run past the batch).  Target elements (a batch
+    // row of this slice labelled with one of the warp's 32 classes: 0.5 % of the slices at cfg3, but 64 % of the tiles then
+    // waited for a warp in that path -- K3a 71.5 us against 62.7 us with the labels out of range, tools/careful_probe.py) go
+    // through the fast path like any other element and are PATCHED behind the slice's stores (below): the lane that checked
+    // the column hands (column, class) to the lane that owns the class, which overwrites its one fp16 element and corrects
+    // its r sum.  The patch sits after the hot code so that the phi / dphi call costs the slices without a target nothing.
     const bool lab_hit = it.lane < SC && lab_l >= c_w0 && lab_l < c_w0 + 32;
-    bool careful = !(s_eff > 0.f) || !(fabsf(amax) * isc <= hi) || (lab_hit && ep.whole_slice_targets);
+    bool careful = !(fabsf(amax) <= st.lim) || (lab_hit && ep.whole_slice_targets) || !cols_full;
     careful = __any_sync(0xffffffffu, careful);
     // columns of this slice whose label is one of the warp's classes (lane j < SC checked column j): patched after the stores
     unsigned hits = careful ? 0u : __ballot_sync(0xffffffffu, lab_hit);
-    float racc = 0.f;
-    if (!careful) {
-      float r4[4] = {0.f, 0.f, 0.f, 0.f};
+    float racc = (r4[0] + r4[1]) + (r4[2] + r4[3]);
+    if (careful) {                                            // the reference's element-wise sequence; overwrites the block stores
+      const float s_eff = ep.hm.s_eff, isc = ep.inv_scale;
+      const float lo = cos_lo(), hi = cos_hi();
+      const float q_off = ep.ls_eps * ep.inv_Ctot;
+      racc = 0.f;
 #pragma unroll
-      for (int j = 0; j < SC; j += 4) {
+      for (int h = 0; h < SC; h += 16) {
+        float g[16];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) r4[u] = fmaf(g[j + u], v[j + u], r4[u]);
-      }
-      racc = (r4[0] + r4[1]) + (r4[2] + r4[3]);
-    } else {
+        for (int j = 0; j < 16; ++j) {
+          const float vj = v[h + j];
+          const float cosv = vj * isc;
+          const float c = (cosv != cosv) ? cosv : fminf(fmaxf(cosv, lo), hi);
+          const bool is_t = st.row_ok && (tl[h + j] == st.cls);
+          float tv = c, f = 1.0f;
+          if (is_t) head_phi_dphi(ep.hm, c, &tv, &f);
+          float z = tv * s_eff;
+          if (!isfinite(z)) { z = 0.f; f = 0.f; }
+          if (!(cosv >= lo && cosv <= hi)) f = 0.f;
+          const float pr = exp2f(fmaf(z, LOG2E, scratch[col0 + h + j]));
+          const float q = is_t ? (1.0f - ep.ls_eps) + q_off : q_off;
+          g[j] = fminf(fmaxf(gs * (pr - q) * f, -65504.f), 65504.f);
+          const float t = g[j] * vj;
+          racc += (g[j] != 0.f && t == t) ? t : 0.f;
+        }
+        if (st.row_ok && !(B200F_PROBE_ON(ep, 2) && g[0] != 12345.678f)) {
+          if (cols_full) {
+            uint32_t w1[8];
 #pragma unroll
-      for (int j = 0; j < SC; ++j) {
-        const float cosv = v[j] * isc;
-        const float c = (cosv != cosv) ? cosv : fminf(fmaxf(cosv, lo), hi);
-        const bool is_t = st.row_ok && (tl[j] == st.cls);
-        float tv = c, f = 1.0f;
-        if (is_t) head_phi_dphi(ep.hm, c, &tv, &f);
-        float z = tv * s_eff;
-        if (!isfinite(z)) { z = 0.f; f = 0.f; }
-        if (!(cosv >= lo && cosv <= hi)) f = 0.f;
-        const float pr = exp2f(fmaf(z, LOG2E, scratch[col0 + j]));
-        const float q = is_t ? (1.0f - ep.ls_eps) + q_off : q_off;
-        g[j] = fminf(fmaxf(gs * (pr - q) * f, -65504.f), 65504.f);
-        const float t = g[j] * v[j];
-        racc += (g[j] != 0.f && t == t) ? t : 0.f;
+            for (int j = 0; j < 8; ++j) w1[j] = pack_f16(g[2 * j], g[2 * j + 1]);
+            st_global_256(gdst + h, w1[0], w1[1], w1[2], w1[3], w1[4], w1[5], w1[6], w1[7]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (b0 + h + j < p.B) gdst[h + j] = (uint16_t)(pack_f16(g[j], 0.f) & 0xffff);
+          }
+        }
       }
     }
     st.r += racc;
-    if (st.row_ok && !(B200F_PROBE_ON(ep, 2) && g[0] != 12345.678f)) {
-      const int64_t b0 = (int64_t)it.group * p_tn(p) + col0;
-      uint16_t* gdst = ep.GT + (int64_t)st.cls * ep.ldgt + b0;
-      if (b0 + SC <= p.B) {
-        uint32_t w1[SC / 2];
-#pragma unroll
-        for (int j = 0; j < SC / 2; ++j) w1[j] = pack_f16(g[2 * j], g[2 * j + 1]);
-#pragma unroll
-        for (int j = 0; j < SC / 2; j += 8) {
-          if (ep.gt_hint) st_global_256_hint(gdst + 2 * j, w1[j], w1[j + 1], w1[j + 2], w1[j + 3], w1[j + 4], w1[j + 5], w1[j + 6], w1[j + 7], st.pol);
-          else st_global_256(gdst + 2 * j, w1[j], w1[j + 1], w1[j + 2], w1[j + 3], w1[j + 4], w1[j + 5], w1[j + 6], w1[j + 7]);
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < SC; ++j)
-          if (b0 + j < p.B) gdst[j] = (uint16_t)(pack_f16(g[j], 0.f) & 0xffff);
-      }
-    }
     while (hits) {                                            // warp-uniform, usually zero trips
       const int src = __ffs(hits) - 1;
       hits &= hits - 1;
@@ -425,6 +442,8 @@ struct XwBwdGTT {
         continue;
       }
       if (st.row_ok && st.cls == lab_s) {
+        const float s_eff = ep.hm.s_eff, isc = ep.inv_scale;
+        const float q_off = ep.ls_eps * ep.inv_Ctot;
         const float bb = scratch[col0 + src];
         const float g_old = fmaf(gs, ex2_approx(fmaf(vt, a, bb)), -gq);    // the bits the fast path stored and summed
         float tv, f;
