@@ -44,6 +44,7 @@ constexpr int MN_BLOCK_BYTES = 64 * BLOCK_K * 2;          // one 64-wide MN bloc
 constexpr int EPI_SMEM_FLOATS = 1024;                     // scratch for the epilogue policy
 constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + EPI_SMEM_FLOATS * 4 + 256;
 constexpr int MAX_STAGES = 6;
+constexpr int FOLLOW_TILE_K = 256;                         // follow mode: k extent of one tile of the neighbour kernel (its 256-class tiles)
 __host__ __device__ constexpr int gemm_b_rows(int pair) { return BLOCK_N / pair; }                  // B rows a CTA loads
 __host__ __device__ constexpr int gemm_stage_bytes(int pair) { return A_TILE_BYTES + gemm_b_rows(pair) * BLOCK_K * 2; }
 __host__ __device__ constexpr int gemm_stages(int pair) { return STAGES * STAGE_BYTES / gemm_stage_bytes(pair); }   // 4 | 6
@@ -55,6 +56,15 @@ struct GemmParams {
   // descriptor knobs (bytes); defaults in default_params(); the self-test can override them
   uint32_t a_lbo, a_sbo, b_lbo, b_sbo, a_kstep, b_kstep;
   uint32_t idesc;
+  int n_fastest;            // 1: work items run (n_tile, m_tile, k_split) with n fastest: the clusters that run side by side
+                            // share their A rows through L2 (dW at batch > 512: A = G^T, 2 MB per 256 class rows, would
+                            // otherwise come from HBM once per n tile -- 2.24 GB read per launch at 4096 x 125 k, ncu)
+  // "follow" mode (K3c beside K3b, b200f_arcface_bwd_part): the k range is walked in the order in which the dW kernel that
+  // runs next to this one reads the same class rows -- its follow_chunks class chunks of the follow_tiles 256-class tiles,
+  // each last tile first (follow_rev) or first tile first, all chunks in step -- dealt round-robin to the k_splits splits.
+  // Both kernels read G^T and w_hat (204 MB at cfg3) and nothing else of size; walked at their own orders one kernel's
+  // lines are gone from the L2 before the other asks for them.  0 = off (a split is a contiguous k range).
+  int follow_chunks, follow_tiles, follow_rev;
   int early;                // 1: neither operand nor the output is touched by the predecessor grid (K3c behind K3b: both only READ
                             // G^T): nobody waits for it up front -- CTAs start on SMs the predecessor has left -- and the epilogue
                             // warps wait at their END, so that this grid still completes after its predecessor (stream order holds
@@ -67,14 +77,38 @@ struct TileCoord { int m0, n0, split, k_begin, k_end, nb0; };   // m0: first row
 template <int PAIR>
 __device__ __forceinline__ TileCoord decode_work(const GemmParams& p, int w, int rank) {
   TileCoord t;
-  const int m = w % p.m_tiles;
-  const int n = (w / p.m_tiles) % p.n_tiles;
+  const int m = p.n_fastest ? (w / p.n_tiles) % p.m_tiles : w % p.m_tiles;
+  const int n = p.n_fastest ? w % p.n_tiles : (w / p.m_tiles) % p.n_tiles;
   t.split = w / (p.m_tiles * p.n_tiles);
   t.m0 = (m * PAIR + rank) * BLOCK_M; t.n0 = n * BLOCK_N;
   t.nb0 = t.n0 + rank * gemm_b_rows(PAIR);
-  t.k_begin = t.split * p.k_per_split;
-  t.k_end = min(p.K, t.k_begin + p.k_per_split);
+  if (p.follow_chunks > 0) {                                    // LOGICAL k range: this split's share of the tile sequence
+    t.k_begin = 0;
+    t.k_end = ((p.follow_tiles - t.split + p.k_splits - 1) / p.k_splits) * FOLLOW_TILE_K;
+  } else {
+    t.k_begin = t.split * p.k_per_split;
+    t.k_end = min(p.K, t.k_begin + p.k_per_split);
+  }
   return t;
+}
+
+// follow mode: first k of the tile that stands at position n of the neighbour's reading order.  Its chunk c covers tiles
+// [c T / nc, (c + 1) T / nc) -- base or base + 1 of them; step i of all chunks comes before step i + 1 of any.
+__device__ __forceinline__ int follow_tile_k(const GemmParams& p, int n) {
+  const int T = p.follow_tiles, nc = p.follow_chunks;
+  const int base = T / nc;
+  int i, c;
+  if (n < base * nc) { i = n / nc; c = n - i * nc; }
+  else {                                                       // the (n - base nc)-th of the chunks that have base + 1 tiles
+    i = base; c = 0;
+    int left = n - base * nc;
+    for (; c < nc; ++c) {
+      const int len = (int)(((int64_t)(c + 1) * T) / nc) - (int)(((int64_t)c * T) / nc);
+      if (len > base && left-- == 0) break;
+    }
+  }
+  const int tb = (int)(((int64_t)c * T) / nc), te = (int)(((int64_t)(c + 1) * T) / nc);
+  return (p.follow_rev ? te - 1 - i : tb + i) * FOLLOW_TILE_K;
 }
 
 // Epilogue policy interface:
@@ -136,7 +170,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
       bool ok = true;
       for (int w = cluster_id; w < total_work && ok; w += n_clusters) {
         const TileCoord t = decode_work<PAIR>(p, w, rank);
-        for (int k0 = t.k_begin; k0 < t.k_end && ok; k0 += BLOCK_K) {
+        int k_tile = 0;                                         // follow mode: physical k of the current logical tile
+        for (int kl = t.k_begin; kl < t.k_end && ok; kl += BLOCK_K) {
+          int k0 = kl;
+          if (p.follow_chunks > 0) {
+            if ((kl & (FOLLOW_TILE_K - 1)) == 0) k_tile = follow_tile_k(p, (kl / FOLLOW_TILE_K) * p.k_splits + t.split);
+            k0 = k_tile + (kl & (FOLLOW_TILE_K - 1));
+          }
           ok = mbar_wait(&empty_bar[stage], phase ^ 1);
           if (!ok) break;
           if (leader) {

@@ -241,6 +241,8 @@ static std::atomic<int> g_k3a_ablate{0};            // probe: 2 = no G^T stores 
 static std::atomic<int> g_k3b_ablate{0};            // probe: 1 = no w_hat loads, 2 = no dW stores (WRONG results)
 #endif
 static std::atomic<int> g_k3b_reverse{1};
+static std::atomic<int> g_k3c_follow{0};            // tunable "k3c_follow": 1 = the dx part beside the dW part reads the class rows in the dW kernel's order (measured at cfg3: step 263.6 -> 262.3 us, e2e 1.763 -> 1.743 M samples/s: within noise, off)
+static std::atomic<int> g_dw_n_fastest{1};          // tunable "dw_n_fastest": streamed dW GEMM (batch > 512) runs the n tiles of a class block side by side
 static std::atomic<int> g_k3b_tma_store{0};         // tunable "k3b_tma_store": 1 = dW through shared-memory staging + TMA tensor stores (XwDwTS)
 static std::atomic<int> g_target_patch{2};          // tunable "target_patch": 0 = a slice with a target goes element-wise (round 1), 1 = K2 / K3a exchange the element
                                                     // in place, 2 = ... and K3a queues its patches to the end of the item
@@ -805,6 +807,7 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
       CUtensorMap tg_km;
       rc = tmap_kmajor(&tg_km, G, cnt, B, pl.ldg, BLOCK_M); if (rc) return rc;
       GemmParams pw = gemm_params((int)cnt, D, (int)B, 1, false, true, FMT_F16, FMT_F16, gpair);
+      pw.n_fastest = g_dw_n_fastest.load(std::memory_order_relaxed) ? 1 : 0;
       EpiDwNorm::Params ew{dw, (int64_t)D, c0, coef, static_cast<const __half*>(wh), sq_part};
       n_sq_used = (int)(ceil_div(cnt, (int64_t)128) * pw.n_tiles * 4);
       rc = (gpair == 2) ? launch_gemm<2, false, true, EpiDwNorm>(tg_km, tx_mn, pw, ew, st, "umma K3b dW (streamed, cta pair)")
@@ -836,6 +839,15 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
     // K3c reads G^T (K3a) and w_hat, writes dxpart: nothing of K3b's -- behind K3b it need not wait for it; directly behind
     // K3a (phases 1 / 2) it does
     px.early = (phase == 0) ? g_early.load(std::memory_order_relaxed) : 0;
+    if (k3c_limit > 0 && gpair == 2 && pl.fused_dw && g_k3c_follow.load(std::memory_order_relaxed) != 0) {
+      // beside the dW part, which runs on the rest of the chip: walk the class rows in ITS order (GemmParams::follow_*)
+      const int rest = xw_max_clusters(2) - k3c_limit;
+      if (rest > 0) {
+        const XwPlan qw = xw_plan(D, cnt, 2, 0, rest);
+        if (qw.n_tiles >= px.k_splits && qw.n_chunks >= 1) { px.follow_chunks = qw.n_chunks; px.follow_tiles = qw.n_tiles; }
+        px.follow_rev = g_k3b_reverse.load(std::memory_order_relaxed) != 0 ? 1 : 0;
+      }
+    }
     EpiStore::Params ex{dxpart, (int64_t)D, B * (int64_t)D, 0, 1.0f, nullptr};
     stage_event(EV_K3C, false, st);
     rc = (gpair == 2) ? launch_gemm<2, true, true, EpiStore>(tg_mn, tw_mn, px, ex, st, "umma K3c dX (cta pair)", k3c_limit)
@@ -1164,6 +1176,8 @@ int b200f_set_tunable(const char* name, int value) {
   if (n == "k3b_ablate") { if (value < 0) return g_k3b_ablate.load(); return g_k3b_ablate.exchange(value); }
 #endif
   if (n == "k3b_tma_store") { if (value != 0 && value != 1) return g_k3b_tma_store.load(); return g_k3b_tma_store.exchange(value); }
+  if (n == "k3c_follow") { if (value != 0 && value != 1) return g_k3c_follow.load(); return g_k3c_follow.exchange(value); }
+  if (n == "dw_n_fastest") { if (value != 0 && value != 1) return g_dw_n_fastest.load(); return g_dw_n_fastest.exchange(value); }
   if (n == "k3b_reverse") { if (value != 0 && value != 1) return g_k3b_reverse.load(); return g_k3b_reverse.exchange(value); }
   if (n == "xw_prefetch") { if (value < 0) return g_prefetch.load(); return g_prefetch.exchange(value); }
   if (n == "g_chunk_mb") { if (value < 1) return g_chunk_mb.load(); return g_chunk_mb.exchange(value); }

@@ -303,6 +303,43 @@ def test_backward_side_by_side_equals_one_after_the_other(cuda_device, B, C, pai
     assert _lib_timeout_clear()
 
 
+@pytest.mark.parametrize("name,B,C", [("k3c_follow", 512, 20000), ("k3c_follow", 384, 6000), ("dw_n_fastest", 640, 9000)])
+def test_work_order_tunables_change_no_result(cuda_device, name, B, C):
+    """Two orderings that exist for the L2's sake: the dx GEMM beside the dW GEMM walks the class rows in the dW kernel's
+    order (k3c_follow: another grouping of the fp32 sum over classes -- last-bit differences in dx, dW untouched), and the
+    streamed dW GEMM at batch > 512 runs the two feature tiles of a class block side by side (dw_n_fastest: same tiles,
+    another order -- bit-identical)."""
+    import b200face
+    from b200face import _lib
+    lib = _lib.load_library()
+    x, w, y = _random_case(B, C, 512, 17 * B + C)
+    xb, wb = x.bfloat16(), w.bfloat16()
+
+    def step(value):
+        old = lib.b200f_set_tunable(name.encode(), value)
+        try:
+            head = b200face.ArcMarginProduct(512, C).to(cuda_device)
+            head.update_epoch(12); head.train()
+            with torch.no_grad():
+                head.weight.copy_(wb.float())
+            xg = xb.to(cuda_device).requires_grad_(True)
+            loss = head.forward_loss(xg, y.to(cuda_device), 0.05)
+            loss.backward()
+            torch.cuda.synchronize()
+            return float(loss), head.weight.grad.clone(), head.last_stats.dx_f32.clone()
+        finally:
+            lib.b200f_set_tunable(name.encode(), old)
+    l0, dw0, dx0 = step(0)
+    l1, dw1, dx1 = step(1)
+    assert l0 == l1
+    assert torch.equal(dw0, dw1)
+    if name == "dw_n_fastest":
+        assert torch.equal(dx0, dx1)
+    else:
+        assert rel_err(dx1.cpu().numpy(), dx0.cpu().numpy()) < 2e-5
+    assert _lib_timeout_clear()
+
+
 def _lib_timeout_clear():
     from b200face import _lib
     return _lib.load_library().b200f_umma_timeout_flag(1) == 0
