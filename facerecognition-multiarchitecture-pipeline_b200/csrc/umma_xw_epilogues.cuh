@@ -352,9 +352,11 @@ struct XwBwdGTT {
         for (int u = 0; u < 4; ++u) {
           const float tt = v[h + j + u];
           g4[u] = fmaf(gs, ex2_approx(fmaf(tt, a, bb[u])), -gq);
-          asm("max.NaN.xorsign.abs.f32 %0, %0, %1;" : "+f"(am4[u]) : "f"(tt));
           r4[u] = fmaf(g4[u], tt, r4[u]);
         }
+        // |max| of the four accumulators, NaN-propagating, two per instruction (FMNMX3)
+        asm("max.NaN.abs.f32 %0, %0, %1, %2;" : "+f"(am4[(j >> 2) & 1]) : "f"(v[h + j]), "f"(v[h + j + 1]));
+        asm("max.NaN.abs.f32 %0, %0, %1, %2;" : "+f"(am4[2 + ((j >> 2) & 1)]) : "f"(v[h + j + 2]), "f"(v[h + j + 3]));
         w1[j / 2] = pack_f16(g4[0], g4[1]);
         w1[j / 2 + 1] = pack_f16(g4[2], g4[3]);
       }
@@ -364,9 +366,8 @@ struct XwBwdGTT {
       }
     }
     float amax = 0.f;
-    asm("max.NaN.xorsign.abs.f32 %0, %1, %2;" : "=f"(amax) : "f"(am4[0]), "f"(am4[1]));
-    asm("max.NaN.xorsign.abs.f32 %0, %0, %1;" : "+f"(amax) : "f"(am4[2]));
-    asm("max.NaN.xorsign.abs.f32 %0, %0, %1;" : "+f"(amax) : "f"(am4[3]));
+    asm("max.NaN.abs.f32 %0, %1, %2, %3;" : "=f"(amax) : "f"(am4[0]), "f"(am4[1]), "f"(am4[2]));
+    asm("max.NaN.abs.f32 %0, %0, %1, %1;" : "+f"(amax) : "f"(am4[3]));
     // a target element sits in this slice iff one of its SC batch rows is labelled with one of the warp's 32 classes
     const int* tl = reinterpret_cast<const int*>(scratch) + p_tn(p) + col0;
     int lab_l;
@@ -379,7 +380,7 @@ struct XwBwdGTT {
     // the column hands (column, class) to the lane that owns the class, which overwrites its one fp16 element and corrects
     // its r sum.  The patch sits after the hot code so that the phi / dphi call costs the slices without a target nothing.
     const bool lab_hit = it.lane < SC && lab_l >= c_w0 && lab_l < c_w0 + 32;
-    bool careful = !(fabsf(amax) <= st.lim) || (lab_hit && ep.whole_slice_targets) || !cols_full;
+    bool careful = !(amax <= st.lim) || (lab_hit && ep.whole_slice_targets) || !cols_full;
     careful = __any_sync(0xffffffffu, careful);
     // columns of this slice whose label is one of the warp's classes (lane j < SC checked column j): patched after the stores
     unsigned hits = careful ? 0u : __ballot_sync(0xffffffffu, lab_hit);

@@ -526,6 +526,113 @@ def arcface_loss(x, weight, label, *, m_eff, s_eff, label_smoothing=0.05, easy_m
                                 stats if stats is not None else HeadStats(), weight_cache, unit_upstream, x_operands)
 
 
+class LazyArcLogits(torch.Tensor):
+    """What ``ArcMarginProduct.forward`` hands an UNMODIFIED reference trainer (``output = model(data, target); loss =
+    criterion(output, target); loss.backward()``, src/training.py:508-521; ``_, predicted = outputs.max(1)``,
+    src/hyperparameter_tuning.py:1001): a tensor that has the logits' shape, dtype and device but has not been computed.
+
+    * ``F.cross_entropy`` / ``nn.CrossEntropyLoss`` on it with the labels of the forward (mean reduction, no class weights)
+      runs the FUSED loss -- the head's own kernels, the B x C logits never stored, the same autograd node as
+      ``forward_loss`` (so the ArcFaceNet hook scalars, ``last_stats`` and the tcgen05 engine for bf16 inputs all apply);
+    * ``.max(1)`` / ``torch.max(.., 1)`` / ``.argmax(1)`` after that come from the forward's row statistics;
+    * ``.detach()`` / ``.data`` stay lazy; any OTHER use materialises the logits once through the compatibility path
+      (``_ArcLogitsFn``: the logits are stored, its backward takes dL/dlogits) and goes on with the real tensor.
+    ``ArcMarginProduct.lazy_logits = False`` restores the eager compatibility path."""
+
+    @staticmethod
+    def __new__(cls, head, x, weight, w, label, m_eff, s_eff):
+        r = torch.Tensor._make_wrapper_subclass(cls, (x.shape[0], weight.shape[0]), dtype=torch.float32, device=x.device,
+                                                requires_grad=False)
+        r._arc = {"head": head, "x": x, "weight": weight, "w": w, "label": label, "m_eff": m_eff, "s_eff": s_eff,
+                  "hook": head._hook, "real": None, "loss": None, "stats": None}
+        return r
+
+    def __repr__(self):
+        return f"LazyArcLogits(shape={tuple(self.shape)}, materialised={self._arc['real'] is not None})"
+
+    # ---- the two ways out -------------------------------------------------------------------------------------------
+    def materialise(self):
+        """The stored logits (compatibility path), made once."""
+        a = self._arc
+        if a["real"] is None:
+            head = a["head"]
+            cfg = _head_cfg(a["m_eff"], a["s_eff"], 0.0, head.easy_margin, head.out_feats, head.engine)
+            # the logits-storing kernels are the CUDA-core engine's: a tensor-engine head gets a shadow of x.dtype
+            x = a["x"]
+            w = a["w"] if a["w"].dtype == x.dtype else a["w"].to(x.dtype)
+            head.last_stats = HeadStats()
+            a["real"] = _ArcLogitsFn.apply(x, a["weight"], w.contiguous(), a["label"], cfg, a["hook"], head.last_stats)
+        return a["real"]
+
+    def fused_loss(self, label_smoothing):
+        a = self._arc
+        head = a["head"]
+        if head.validate_labels:
+            c_tot = head._num_classes_total or head.out_feats
+            lab = a["label"]
+            if lab.numel() and (int(lab.min()) < 0 or int(lab.max()) >= c_tot):
+                raise IndexError(f"label out of range [0, {c_tot})")      # the reference's scatter_ raises here (:381)
+        head.last_stats = HeadStats(want_dw_sqnorm=bool(getattr(head, "track_dw_norm", False)))
+        a["stats"] = head.last_stats
+        use_cache = head.cache_weight_prep and (not head.training or head._w_prep.get("optimizer_current", False))
+        w = a["weight"].detach() if use_tcgen05(a["x"], head.engine) else a["w"]
+        a["loss"] = arcface_loss(a["x"], a["weight"], a["label"], m_eff=a["m_eff"], s_eff=a["s_eff"],
+                                 label_smoothing=label_smoothing, easy_margin=head.easy_margin, hook=a["hook"],
+                                 stats=head.last_stats, engine=head.engine, compute_weight=w,
+                                 class_offset=head._class_offset, num_classes_total=head._num_classes_total,
+                                 group=head._group, weight_cache=head._w_prep if use_cache else None)
+        return a["loss"]
+
+    def _same_labels(self, target):
+        lab = self._arc["label"]
+        if not isinstance(target, torch.Tensor) or target.dim() != 1 or target.shape != lab.shape or target.is_floating_point():
+            return False
+        if target.data_ptr() == lab.data_ptr() and target.dtype == lab.dtype:
+            return True
+        return target.device == lab.device and bool(torch.equal(target.to(torch.int64), lab))
+
+    @classmethod
+    def __torch_dispatch__(cls, func, types, args=(), kwargs=None):
+        # below __torch_function__ (which sees every Python-level call first): only reached by C++ callers -- the real logits
+        from torch.utils._pytree import tree_map
+        swap = lambda v: v.materialise() if isinstance(v, LazyArcLogits) else v
+        return func(*tree_map(swap, args), **tree_map(swap, kwargs or {}))
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        kwargs = kwargs or {}
+        lazy = next((a for a in args if isinstance(a, LazyArcLogits)), None)
+        if lazy is None:
+            lazy = next((v for v in kwargs.values() if isinstance(v, LazyArcLogits)), None)
+        name = getattr(func, "__name__", "")
+        with torch._C.DisableTorchFunctionSubclass():
+            if lazy is not None and lazy._arc["real"] is None:
+                if func is F.cross_entropy and args and args[0] is lazy:
+                    names = ("input", "target", "weight", "size_average", "ignore_index", "reduce", "reduction", "label_smoothing")
+                    kw = dict(zip(names, args)); kw.update(kwargs)
+                    if (kw.get("weight") is None and kw.get("reduction", "mean") == "mean" and kw.get("size_average") is None
+                            and kw.get("reduce") is None and lazy._same_labels(kw.get("target"))):
+                        return lazy.fused_loss(float(kw.get("label_smoothing", 0.0)))
+                elif name in ("max", "argmax") and args and args[0] is lazy and lazy._arc["stats"] is not None \
+                        and lazy._arc["head"]._group is None:
+                    dim = kwargs.get("dim", args[1] if len(args) > 1 else None)
+                    keep = kwargs.get("keepdim", args[2] if len(args) > 2 else False)
+                    st = lazy._arc["stats"]
+                    if isinstance(dim, int) and dim in (1, -1) and not keep and st.row_argmax is not None:
+                        if name == "argmax":
+                            return st.row_argmax
+                        return torch.return_types.max((st.row_best, st.row_argmax))
+                elif name in ("detach", "__get__") and (name == "detach" or func == torch.Tensor.data.__get__):
+                    return lazy
+                elif name in ("size", "dim", "numel", "__len__") or func in (torch.Tensor.shape.__get__, torch.Tensor.dtype.__get__,
+                                                                   torch.Tensor.device.__get__, torch.Tensor.requires_grad.__get__,
+                                                                   torch.Tensor.is_cuda.__get__, torch.Tensor.ndim.__get__):
+                    return func(*args, **kwargs)
+            # everything else: on the real logits
+            swap = lambda v: v.materialise() if isinstance(v, LazyArcLogits) else v
+            return func(*[swap(v) for v in args], **{k: swap(v) for k, v in kwargs.items()})
+
+
 class GraphedHeadStep:
     """One fused head step (K1-K3: loss = arcface_loss(x, weight, y); loss.backward()) captured once into a CUDA
     graph and replayed per batch.  Why: the step is ~20 short kernels; launched from Python they cost ~0.75 ms of
@@ -656,6 +763,7 @@ class ArcMarginProduct(nn.Module):
         # would silently train on old weights.  load_state_dict clears the cache (hook below).
         self.cache_weight_prep = True
         self.validate_labels = False       # debug: check 0 <= label < C on the host (one sync), like scatter_ would
+        self.lazy_logits = True            # forward() returns a LazyArcLogits: criterion(output, target) runs the fused loss
         # class-parallel placement (parallel.ShardedArcMarginProduct sets these): this module owns the class rows
         # [_class_offset, _class_offset + out_feats) of a [_num_classes_total, D] matrix sharded over _group
         self._class_offset = 0
@@ -705,8 +813,13 @@ class ArcMarginProduct(nn.Module):
         return x, self.weight, self._w_shadow[1]
 
     def forward(self, input, label):
-        """Scaled logits [B,C] fp32 (compatibility path; stores the logits)."""
+        """Scaled logits [B,C] fp32 -- as a LazyArcLogits (``lazy_logits``, default on): the reference trainer's
+        ``criterion(output, target)`` then runs the fused loss and nothing B x C is stored; any other use of the result
+        computes and stores the logits (compatibility path)."""
         m_eff, s_eff = self._step_schedule()
+        if getattr(self, "lazy_logits", True) and input.is_cuda and input.dim() == 2:
+            x, weight, w = self._operands(input)
+            return LazyArcLogits(self, x, weight, w.contiguous(), label.contiguous().to(torch.int64), m_eff, s_eff)
         x, weight, w = self._operands(input, wants_logits=True)
         cfg = _head_cfg(m_eff, s_eff, 0.0, self.easy_margin, self.out_feats, self.engine)
         self.last_stats = HeadStats()

@@ -220,3 +220,19 @@ def test_bench_claims_stdout_for_the_json_line(tmp_path):
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, check=True)
     assert r.stdout == '{"ok": 1}\n'
     assert "banner-from-a-library" in r.stderr and "stray python print" in r.stderr
+
+
+def test_lazy_logits_metadata_needs_no_kernel():
+    """LazyArcLogits (what ArcMarginProduct.forward returns on CUDA): shape / dtype / device / detach / .data are answered
+    without computing anything -- checked here on CPU tensors with a stand-in head, no library call involved."""
+    import b200face
+
+    class _Head:
+        _hook = None
+    x, w, y = torch.zeros(4, 8), torch.zeros(10, 8), torch.zeros(4, dtype=torch.int64)
+    out = b200face.LazyArcLogits(_Head(), x, w, w, y, 0.5, 32.0)
+    assert isinstance(out, torch.Tensor)
+    assert tuple(out.shape) == (4, 10) and out.size(0) == 4 and out.dim() == 2 and len(out) == 4 and out.numel() == 40
+    assert out.dtype == torch.float32 and out.device == x.device and not out.requires_grad
+    assert out.detach() is out and out.data is out
+    assert out._arc["real"] is None and "materialised=False" in repr(out)

@@ -56,7 +56,9 @@ def test_golden_logits_compat_path(cuda_device, name):
     head = _head_from_cfg(cfg, d["w"].shape[0], d["w"].shape[1], cuda_device, d["w"])
     x = torch.tensor(d["x"], device=cuda_device, requires_grad=True)
     y = torch.tensor(d["y"], device=cuda_device)
+    head.lazy_logits = False                                  # the stored-logits path itself (default: LazyArcLogits)
     out = head(x, y)
+    assert type(out) is torch.Tensor
     tol = 2e-4 if name.startswith("extreme") else TOL_F32
     assert rel_err(out.detach().cpu().numpy(), d["logits"]) < tol
     assert head.max_cos_theta == pytest.approx(float(d["cos_max"]), abs=2e-6)
@@ -89,6 +91,75 @@ def test_golden_fused_loss_and_grads(cuda_device, name):
     assert not head.nan_seen
 
 
+@pytest.mark.parametrize("name", head_golden_names())
+def test_lazy_logits_reference_trainer_loop(cuda_device, name):
+    """The UNMODIFIED reference training step (src/training.py:508-521: ``output = model(data, target); loss =
+    criterion(output, target); loss.backward()``; src/hyperparameter_tuning.py:1001: ``_, predicted = outputs.max(1)``)
+    on the drop-in head: the output is a LazyArcLogits, the criterion runs the fused loss -- nothing B x C is stored --
+    and the numbers are the reference's own (golden fixtures)."""
+    import b200face
+    d = golden(f"head_{name}.npz")
+    cfg = cfg_from_golden(d)
+    head = _head_from_cfg(cfg, d["w"].shape[0], d["w"].shape[1], cuda_device, d["w"])
+    x = torch.tensor(d["x"], device=cuda_device, requires_grad=True)
+    y = torch.tensor(d["y"], device=cuda_device)
+    criterion = torch.nn.CrossEntropyLoss(label_smoothing=cfg.label_smoothing)
+    output = head(x, y)
+    assert isinstance(output, b200face.LazyArcLogits) and isinstance(output, torch.Tensor)
+    assert tuple(output.shape) == d["logits"].shape and output.dtype == torch.float32 and output.is_cuda
+    loss = criterion(output, y)
+    loss.backward()
+    assert output._arc["real"] is None, "the criterion must not have materialised the logits"
+    assert float(loss) == pytest.approx(float(d["loss"]), rel=1e-5)
+    gt = 5e-3 if name.startswith("extreme") else 2e-5
+    assert rel_err(x.grad.cpu().numpy(), d["dx"]) < gt
+    assert rel_err(head.weight.grad.cpu().numpy(), d["dw"]) < gt
+    _, predicted = output.max(1)
+    assert output.data is output and output._arc["real"] is None
+    if not name.startswith("extreme"):
+        assert np.array_equal(predicted.cpu().numpy(), d["logits"].argmax(1))
+        assert np.array_equal(torch.max(output.data, 1)[1].cpu().numpy(), d["logits"].argmax(1))
+    # any other use: the real logits (compatibility path), made once
+    tol = 2e-4 if name.startswith("extreme") else TOL_F32
+    assert rel_err((output + 0).detach().cpu().numpy(), d["logits"]) < tol
+    assert output._arc["real"] is not None
+
+
+def test_lazy_logits_equal_forward_loss_on_the_tensor_engine(cuda_device):
+    """bf16 rows: criterion(head(x, y), y) is forward_loss(x, y) -- same autograd node, same engine (tcgen05), same bits --
+    including a criterion with another target tensor of equal values; a DIFFERENT target falls back to the stored logits."""
+    import b200face
+    B, C = 256, 9000
+    x, w, y = _random_case(B, C, 512, 5)
+    xb = x.bfloat16().to(cuda_device)
+    yd = y.to(cuda_device)
+
+    def run(lazy):
+        head = b200face.ArcMarginProduct(512, C).to(cuda_device)
+        head.update_epoch(12); head.train()
+        with torch.no_grad():
+            head.weight.copy_(w.bfloat16().float())
+        xg = xb.clone().requires_grad_(True)
+        if lazy:
+            out = head(xg, yd)
+            loss = torch.nn.functional.cross_entropy(out, yd.clone(), label_smoothing=0.05)
+            assert out._arc["real"] is None
+        else:
+            loss = head.forward_loss(xg, yd, 0.05)
+        loss.backward()
+        return float(loss), xg.grad.clone(), head.weight.grad.clone(), head
+
+    l0, dx0, dw0, _ = run(False)
+    l1, dx1, dw1, head = run(True)
+    assert l0 == l1 and torch.equal(dx0, dx1) and torch.equal(dw0, dw1)
+    out = head(xb, yd)
+    other = (yd + 1) % C
+    ref = torch.nn.functional.cross_entropy(out.materialise().float(), other)
+    got = torch.nn.functional.cross_entropy(head(xb, yd), other)
+    assert float(got) == pytest.approx(float(ref), rel=1e-6)
+    assert _lib_timeout_clear()
+
+
 def test_golden_hook_arcfacenet(cuda_device):
     """The ArcFaceNet backward hook (face_models.py:538-570) on the reference's own recorded step 2."""
     import b200face
@@ -112,12 +183,15 @@ def test_golden_hook_arcfacenet(cuda_device):
             out3 = head.last_stats.hook_out.cpu().numpy()
             assert out3[1] == pytest.approx(float(d["last_grad_norm1"]), rel=1e-5)
             assert out3[2] < 1.0
-        # same through the logits path + external criterion
-        head.zero_grad(); x.grad = None
-        out = head(x, y)
-        torch.nn.CrossEntropyLoss(label_smoothing=0.05)(out, y).backward()
-        assert rel_err(x.grad.cpu().numpy(), d[f"demb{step}"]) < 2e-5
-        assert rel_err(head.weight.grad.cpu().numpy(), d[f"dw{step}"]) < 2e-5
+        # same through forward() + external criterion: lazy logits (fused loss) and stored logits (compatibility path)
+        for lazy in (True, False):
+            head.zero_grad(); x.grad = None
+            head.lazy_logits = lazy
+            out = head(x, y)
+            assert isinstance(out, b200face.LazyArcLogits) == lazy
+            torch.nn.CrossEntropyLoss(label_smoothing=0.05)(out, y).backward()
+            assert rel_err(x.grad.cpu().numpy(), d[f"demb{step}"]) < 2e-5
+            assert rel_err(head.weight.grad.cpu().numpy(), d[f"dw{step}"]) < 2e-5
 
 
 def test_arcfacenet_hook_arms_after_first_forward(cuda_device):
