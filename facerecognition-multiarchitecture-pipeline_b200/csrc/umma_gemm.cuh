@@ -65,6 +65,12 @@ struct GemmParams {
   // Both kernels read G^T and w_hat (204 MB at cfg3) and nothing else of size; walked at their own orders one kernel's
   // lines are gone from the L2 before the other asks for them.  0 = off (a split is a contiguous k range).
   int follow_chunks, follow_tiles, follow_rev;
+  // stream-K: the (tile, k-block) space -- tiles in decode order, k_units k-blocks each -- is cut into one contiguous,
+  // equally long range per cluster; a range that crosses a tile boundary gives its cluster two (rarely three) pieces.
+  // A piece's output slot (TileCoord::split) is its cluster's rank among the clusters that touch the tile; the reduction
+  // sums stream_k_pieces(tile) slots.  Why: with 32 output tiles and 74 clusters (dx at batch 4096) split-K by 2 leaves
+  // 10 clusters idle and split-K by 3 runs two waves; 0 = off.
+  int stream_k, k_units;
   int early;                // 1: neither operand nor the output is touched by the predecessor grid (K3c behind K3b: both only READ
                             // G^T): nobody waits for it up front -- CTAs start on SMs the predecessor has left -- and the epilogue
                             // warps wait at their END, so that this grid still completes after its predecessor (stream order holds
@@ -90,6 +96,41 @@ __device__ __forceinline__ TileCoord decode_work(const GemmParams& p, int w, int
     t.k_end = min(p.K, t.k_begin + p.k_per_split);
   }
   return t;
+}
+
+// ---- work items of a cluster: split-K (item w = cluster, cluster + n_clusters, ...) or stream-K ------------------------
+struct WorkIter { long long pos, hi; };
+__device__ __forceinline__ void work_begin(const GemmParams& p, int cluster_id, int n_clusters, WorkIter& it) {
+  if (p.stream_k) {
+    const long long total = (long long)p.m_tiles * p.n_tiles * p.k_units;
+    it.pos = total * cluster_id / n_clusters; it.hi = total * (cluster_id + 1) / n_clusters;
+  } else {
+    it.pos = cluster_id; it.hi = (long long)p.m_tiles * p.n_tiles * p.k_splits;
+  }
+}
+// the cluster whose range holds position pos of the (tile, k-block) space (ranges: [total c / n, total (c + 1) / n))
+__host__ __device__ __forceinline__ int stream_k_owner(long long pos, long long total, int n_clusters) {
+  return (int)(((pos + 1) * n_clusters - 1) / total);
+}
+// slots the reduction has to sum for a tile
+__host__ __device__ __forceinline__ int stream_k_pieces(int tile, int k_units, long long total, int n_clusters) {
+  return stream_k_owner((long long)(tile + 1) * k_units - 1, total, n_clusters) - stream_k_owner((long long)tile * k_units, total, n_clusters) + 1;
+}
+template <int PAIR>
+__device__ __forceinline__ bool work_next(const GemmParams& p, int cluster_id, int n_clusters, int rank, WorkIter& it, TileCoord& t) {
+  if (it.pos >= it.hi) return false;
+  if (!p.stream_k) { t = decode_work<PAIR>(p, (int)it.pos, rank); it.pos += n_clusters; return true; }
+  const int U = p.k_units;
+  const int tile = (int)(it.pos / U);
+  const int kb = (int)(it.pos - (long long)tile * U);
+  long long len = it.hi - it.pos;
+  if (len > U - kb) len = U - kb;
+  t = decode_work<PAIR>(p, tile, rank);                         // m0 / n0 / nb0 of the tile
+  t.k_begin = kb * BLOCK_K;
+  t.k_end = min(p.K, (kb + (int)len) * BLOCK_K);
+  t.split = cluster_id - stream_k_owner((long long)tile * U, (long long)p.m_tiles * p.n_tiles * U, n_clusters);
+  it.pos += len;
+  return true;
 }
 
 // follow mode: first k of the tile that stands at position n of the neighbour's reading order.  Its chunk c covers tiles
@@ -139,7 +180,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
   const int rank = (PAIR == 2) ? (int)cluster_ctarank() : 0;
   const int cluster_id = blockIdx.x / PAIR;
   const int n_clusters = gridDim.x / PAIR;
-  const int total_work = p.m_tiles * p.n_tiles * p.k_splits;
 
   // An early kernel (K3c) lets its dependents be scheduled right away: they wait for its completion themselves.  Every other
   // use triggers only AFTER its own wait (below): a dependent that starts early (K3c behind the streamed K3b) relies on
@@ -168,8 +208,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
       const bool leader = elect_one();
       int stage = 0; uint32_t phase = 0;
       bool ok = true;
-      for (int w = cluster_id; w < total_work && ok; w += n_clusters) {
-        const TileCoord t = decode_work<PAIR>(p, w, rank);
+      WorkIter wi; work_begin(p, cluster_id, n_clusters, wi);
+      TileCoord t;
+      while (ok && work_next<PAIR>(p, cluster_id, n_clusters, rank, wi, t)) {
         int k_tile = 0;                                         // follow mode: physical k of the current logical tile
         for (int kl = t.k_begin; kl < t.k_end && ok; kl += BLOCK_K) {
           int k0 = kl;
@@ -215,8 +256,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
       const uint64_t desc_a0 = make_smem_desc(smem_u32(tiles), p.a_lbo, p.a_sbo);
       const uint64_t desc_b0 = make_smem_desc(smem_u32(tiles) + A_TILE_BYTES, p.b_lbo, p.b_sbo);
       const uint32_t a_kstep = p.a_kstep >> 4, b_kstep = p.b_kstep >> 4;
-      for (int w = cluster_id; w < total_work && ok; w += n_clusters) {
-        const TileCoord t = decode_work<PAIR>(p, w, rank);
+      WorkIter wi; work_begin(p, cluster_id, n_clusters, wi);
+      TileCoord t;
+      while (ok && work_next<PAIR>(p, cluster_id, n_clusters, rank, wi, t)) {
         ok = mbar_wait(&acc_empty[acc], acc_phase ^ 1);        // epilogue has drained this accumulator
         if (!ok) break;
         tc_fence_after_sync();
@@ -251,8 +293,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
     const int epi_tid = (warp - EPI_WARP0) * 32 + lane;
     int acc = 0; uint32_t acc_phase = 0;
     bool ok = true;
-    for (int w = cluster_id; w < total_work && ok; w += n_clusters) {
-      const TileCoord t = decode_work<PAIR>(p, w, rank);
+    WorkIter wi; work_begin(p, cluster_id, n_clusters, wi);
+    TileCoord t;
+    while (ok && work_next<PAIR>(p, cluster_id, n_clusters, rank, wi, t)) {
       ok = mbar_wait(&acc_full[acc], acc_phase);
       ok = __all_sync(0xffffffffu, ok);
       if (!ok) break;

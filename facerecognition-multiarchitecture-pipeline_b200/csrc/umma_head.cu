@@ -103,6 +103,35 @@ static GemmParams gemm_params(int M, int N, int K, int k_splits, bool a_mn, bool
 
 static int xw_max_clusters(int pair);
 
+static int gemm_clusters(int pair, int cluster_limit) {
+  int clusters = (pair == 2) ? xw_max_clusters(2) : num_sms();
+  if (cluster_limit > 0 && cluster_limit < clusters) clusters = cluster_limit;
+  return clusters;
+}
+// tunable "stream_k": 1 = the dx GEMM may cut its (tile, k) space into equal ranges per cluster.  Measured at 4096 x 125 k (32 tiles,
+// 74 clusters): 405 -> 497 us -- with split-K the clusters of a wave walk the SAME k range, so the 16 that share a G row block and
+// the 2 x 16 that share a w_hat column block find each other's operand tiles in L2; staggered ranges read every tile's operands
+// from HBM (4.1 GB instead of 1.15 GB).  Correct, tested, off.
+static std::atomic<int> g_stream_k{0};
+// Turn p into a stream-K launch when plain split-K would leave more than 7 % of the clusters' time idle and the partial
+// buffers (slots of them) suffice.  Returns the slots the reduction sums at most (p.k_splits otherwise).
+static int gemm_stream_k(GemmParams& p, int pair, int cluster_limit, int slots) {
+  if (!g_stream_k.load(std::memory_order_relaxed) || p.follow_chunks > 0) return p.k_splits;
+  const int clusters = gemm_clusters(pair, cluster_limit);
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int work = tiles * p.k_splits;
+  const int rounds = (work + clusters - 1) / clusters;
+  if ((double)work >= 0.93 * (double)rounds * clusters) return p.k_splits;
+  const int U = (int)ceil_div(p.K, BLOCK_K);
+  const long long total = (long long)tiles * U;
+  if (total < 4LL * clusters) return p.k_splits;              // too little work to cut
+  int most = 0;
+  for (int t = 0; t < tiles; ++t) { const int n = stream_k_pieces(t, U, total, clusters); if (n > most) most = n; }
+  if (most > slots) return p.k_splits;
+  p.stream_k = 1; p.k_units = U;
+  return most;
+}
+
 // PAIR = 2: clusters of two CTAs on 256 x 256 tiles (p from gemm_params(..., pair = 2); a K-major B map needs
 // 128-row boxes: gemm_b_rows(2))
 template <int PAIR, bool A_MN, bool B_MN, class Epi>
@@ -111,9 +140,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   auto kern = gemm_kernel<PAIR, A_MN, B_MN, Epi>;
   B200F_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   const int work = p.m_tiles * p.n_tiles * p.k_splits;
-  int clusters = (PAIR == 2) ? xw_max_clusters(2) : num_sms();
-  if (cluster_limit > 0 && cluster_limit < clusters) clusters = cluster_limit;
-  if (clusters > work) clusters = work;
+  int clusters = gemm_clusters(PAIR, cluster_limit);
+  if (!p.stream_k && clusters > work) clusters = work;      // stream-K: every cluster has a range (gemm_stream_k checked that)
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(clusters * PAIR)); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
   cudaLaunchAttribute at[2];
@@ -200,11 +228,19 @@ reduce_row_partials_kernel(const float* __restrict__ part, int n_parts, int64_t 
 }
 
 // dst (=|+=) scale / *dev_scale * sum_s part[s], fixed order
+// stream-K partials (GemmParams::stream_k): how many slots a tile of the [rows, D] output has is a function of the tile
+struct StreamGeom { int on, D, tile_m, tile_n, m_tiles, k_units, n_clusters; long long total; };
 __global__ void reduce_splits_kernel(const float* __restrict__ part, int n_splits, int64_t n, float* __restrict__ dst,
-                                     int accumulate, float scale, const float* __restrict__ dev_scale) {
+                                     int accumulate, float scale, const float* __restrict__ dev_scale, const StreamGeom sg) {
   pdl_trigger(); pdl_wait();
   const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
+  if (sg.on) {                                                // a float4 lies inside one tile (tile_n % 4 == 0)
+    const int64_t row = i / sg.D;
+    const int col = (int)(i - row * sg.D);
+    const int tile = (int)(row / sg.tile_m) + sg.m_tiles * (col / sg.tile_n);
+    n_splits = stream_k_pieces(tile, sg.k_units, sg.total, sg.n_clusters);
+  }
   const float sc = (dev_scale != nullptr) ? scale / __ldg(dev_scale) : scale;
   float4 s = accumulate ? *reinterpret_cast<const float4*>(dst + i) : make_float4(0.f, 0.f, 0.f, 0.f);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -241,6 +277,7 @@ static std::atomic<int> g_k3a_ablate{0};            // probe: 2 = no G^T stores 
 static std::atomic<int> g_k3b_ablate{0};            // probe: 1 = no w_hat loads, 2 = no dW stores (WRONG results)
 #endif
 static std::atomic<int> g_k3b_reverse{1};
+static std::atomic<int> g_k3a_reverse{0};           // tunable "k3a_reverse": K3a walks each chunk last tile first (K2 read those w_hat rows last)
 static std::atomic<int> g_k3c_follow{0};            // tunable "k3c_follow": 1 = the dx part beside the dW part reads the class rows in the dW kernel's order (measured at cfg3: step 263.6 -> 262.3 us, e2e 1.763 -> 1.743 M samples/s: within noise, off)
 static std::atomic<int> g_dw_n_fastest{1};          // tunable "dw_n_fastest": streamed dW GEMM (batch > 512) runs the n tiles of a class block side by side
 static std::atomic<int> g_k3b_tma_store{0};         // tunable "k3b_tma_store": 1 = dW through shared-memory staging + TMA tensor stores (XwDwTS)
@@ -403,7 +440,7 @@ static int launch_xw(const CUtensorMap& tx, const CUtensorMap& tw, const XwPlan&
 struct Plan {
   XwPlan fwd;
   size_t off_part, off_cos, off_counter, off_ready;
-  int64_t Cc, ldg; int n_chunks, dx_splits;
+  int64_t Cc, ldg; int n_chunks, dx_splits, dx_slots;   // dx_slots: partial buffers of the dx GEMM the workspace holds
   size_t off_G, off_dxpart, off_rpart, off_sq, n_sq;
   int n_rb;                 // 32-row blocks of the batch that K3a emits r partials for
   bool fused_dw;            // B <= 512: dW GEMM on the MN-major X-stationary kernel (x_hat^T resident); above that
@@ -452,6 +489,12 @@ static Plan make_plan(int64_t B, int64_t C, int D) {
   int splits_max = num_sms() / ((int)ceil_div(B, BLOCK_M) * (int)ceil_div(D, BLOCK_N));   // either pairing fits
   if (splits_max < splits) splits_max = splits;
   if (splits_max < 1) splits_max = 1;
+  {  // stream-K of the dx GEMM: a tile is touched by at most ceil(clusters / tiles) + 1 clusters (GemmParams::stream_k)
+    const int cl = (pair == 2) ? xw_max_clusters(2) : num_sms();
+    const int sk = (cl + out_tiles - 1) / out_tiles + 1;
+    if (splits_max < sk) splits_max = sk;
+  }
+  pl.dx_slots = splits_max;
   pl.off_dxpart = off; off += align_up(sizeof(float) * (size_t)splits_max * B * D, 256);
   pl.fused_dw = (B <= (int64_t)XW_MAX_KB * XW_K);         // x_hat^T resident (else: both operands streamed)
   pl.n_rb = (int)ceil_div(B, 2 * XW_M) * 2 * 4;          // covers either pairing
@@ -727,20 +770,21 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
 #endif
     };
     const int k3a_whint = (hints & 1) ? 1 : 0;
+    const bool k3a_rev = g_k3a_reverse.load(std::memory_order_relaxed) != 0;
     { B200F_NVTX("K3a logit gradient (recompute + G^T)");
     stage_event(EV_K3A, false, st);
     if (k3a_mode == 4) {
       XwBwdGT4::Params e4{}; fill(e4);
-      rc = (qg.pair == 2) ? launch_xw<2, XW_SWAP, XwBwdGT4>(tx_k, tw_k, qg, B, cnt, D, e4, st, "umma K3a logit-grad (cta pair, 16 warps per tile)", FMT_F16, false, wc, wrb, true, k3a_whint)
-                          : launch_xw<1, XW_SWAP, XwBwdGT4>(tx_k, tw_k, qg, B, cnt, D, e4, st, "umma K3a logit-grad (16 warps per tile)", FMT_F16, false, wc, wrb, true, k3a_whint);
+      rc = (qg.pair == 2) ? launch_xw<2, XW_SWAP, XwBwdGT4>(tx_k, tw_k, qg, B, cnt, D, e4, st, "umma K3a logit-grad (cta pair, 16 warps per tile)", FMT_F16, k3a_rev, wc, wrb, true, k3a_whint)
+                          : launch_xw<1, XW_SWAP, XwBwdGT4>(tx_k, tw_k, qg, B, cnt, D, e4, st, "umma K3a logit-grad (16 warps per tile)", FMT_F16, k3a_rev, wc, wrb, true, k3a_whint);
     } else if (k3a_mode == 2) {
       XwBwdGT2::Params e2{}; fill(e2);
-      rc = (qg.pair == 2) ? launch_xw<2, XW_SWAP, XwBwdGT2>(tx_k, tw_k, qg, B, cnt, D, e2, st, "umma K3a logit-grad (cta pair, 2 epilogue groups)", FMT_F16, false, wc, wrb, true, k3a_whint)
-                          : launch_xw<1, XW_SWAP, XwBwdGT2>(tx_k, tw_k, qg, B, cnt, D, e2, st, "umma K3a logit-grad (2 epilogue groups)", FMT_F16, false, wc, wrb, true, k3a_whint);
+      rc = (qg.pair == 2) ? launch_xw<2, XW_SWAP, XwBwdGT2>(tx_k, tw_k, qg, B, cnt, D, e2, st, "umma K3a logit-grad (cta pair, 2 epilogue groups)", FMT_F16, k3a_rev, wc, wrb, true, k3a_whint)
+                          : launch_xw<1, XW_SWAP, XwBwdGT2>(tx_k, tw_k, qg, B, cnt, D, e2, st, "umma K3a logit-grad (2 epilogue groups)", FMT_F16, k3a_rev, wc, wrb, true, k3a_whint);
     } else {
       XwBwdGT::Params eg{}; fill(eg);
-      rc = (qg.pair == 2) ? launch_xw<2, XW_SWAP, XwBwdGT>(tx_k, tw_k, qg, B, cnt, D, eg, st, "umma K3a logit-grad (cta pair)", FMT_F16, false, wc, wrb, true, k3a_whint)
-                          : launch_xw<1, XW_SWAP, XwBwdGT>(tx_k, tw_k, qg, B, cnt, D, eg, st, "umma K3a logit-grad", FMT_F16, false, wc, wrb, true, k3a_whint);
+      rc = (qg.pair == 2) ? launch_xw<2, XW_SWAP, XwBwdGT>(tx_k, tw_k, qg, B, cnt, D, eg, st, "umma K3a logit-grad (cta pair)", FMT_F16, k3a_rev, wc, wrb, true, k3a_whint)
+                          : launch_xw<1, XW_SWAP, XwBwdGT>(tx_k, tw_k, qg, B, cnt, D, eg, st, "umma K3a logit-grad", FMT_F16, k3a_rev, wc, wrb, true, k3a_whint);
     }
     stage_event(EV_K3A, true, st); }
     return rc; };
@@ -848,6 +892,16 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
         px.follow_rev = g_k3b_reverse.load(std::memory_order_relaxed) != 0 ? 1 : 0;
       }
     }
+    // flat split reduction behind it (not the fused dL/dx tail of the single-chunk, single-shard step): stream-K allowed
+    const bool fused_tail = hdx != nullptr && hdx->dx != nullptr && pl.n_chunks == 1;
+    const int k3c_climit = (gpair == 2) ? k3c_limit : k3c_limit * 2;
+    const int n_slots = fused_tail ? px.k_splits : gemm_stream_k(px, gpair, k3c_climit, pl.dx_slots);
+    StreamGeom sg{};
+    if (px.stream_k) {
+      sg.on = 1; sg.D = D; sg.tile_m = BLOCK_M * gpair; sg.tile_n = BLOCK_N; sg.m_tiles = px.m_tiles; sg.k_units = px.k_units;
+      sg.n_clusters = gemm_clusters(gpair, k3c_climit);
+      sg.total = (long long)px.m_tiles * px.n_tiles * px.k_units;
+    }
     EpiStore::Params ex{dxpart, (int64_t)D, B * (int64_t)D, 0, 1.0f, nullptr};
     stage_event(EV_K3C, false, st);
     rc = (gpair == 2) ? launch_gemm<2, true, true, EpiStore>(tg_mn, tw_mn, px, ex, st, "umma K3c dX (cta pair)", k3c_limit)
@@ -872,8 +926,8 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
                    grad4 + 3, static_cast<const __half*>(xh), S, hdx->inv_nx, dxhat, hdx->dx, lowp);
       B200F_LAUNCH_OK("umma reduce_splits_normbwd_kernel");
     } else {
-      launch_pdl(reduce_splits_kernel, dim3((unsigned)ceil_div(n / 4, 256)), dim3(256), 0, st, dxpart, px.k_splits, n, dxhat, chunk_no > 0,
-                                                                          1.0f / S, grad4 + 3);
+      launch_pdl(reduce_splits_kernel, dim3((unsigned)ceil_div(n / 4, 256)), dim3(256), 0, st, dxpart, n_slots, n, dxhat, chunk_no > 0,
+                                                                          1.0f / S, grad4 + 3, sg);
       B200F_LAUNCH_OK("umma reduce_splits_kernel");
       if (last_chunk && hdx != nullptr && hdx->dx != nullptr) {
         rc = head_dx_finish(xh, S, hdx, dxhat, B, D, st); if (rc) return rc;
@@ -1176,6 +1230,8 @@ int b200f_set_tunable(const char* name, int value) {
   if (n == "k3b_ablate") { if (value < 0) return g_k3b_ablate.load(); return g_k3b_ablate.exchange(value); }
 #endif
   if (n == "k3b_tma_store") { if (value != 0 && value != 1) return g_k3b_tma_store.load(); return g_k3b_tma_store.exchange(value); }
+  if (n == "stream_k") { if (value != 0 && value != 1) return g_stream_k.load(); return g_stream_k.exchange(value); }
+  if (n == "k3a_reverse") { if (value != 0 && value != 1) return g_k3a_reverse.load(); return g_k3a_reverse.exchange(value); }
   if (n == "k3c_follow") { if (value != 0 && value != 1) return g_k3c_follow.load(); return g_k3c_follow.exchange(value); }
   if (n == "dw_n_fastest") { if (value != 0 && value != 1) return g_dw_n_fastest.load(); return g_dw_n_fastest.exchange(value); }
   if (n == "k3b_reverse") { if (value != 0 && value != 1) return g_k3b_reverse.load(); return g_k3b_reverse.exchange(value); }

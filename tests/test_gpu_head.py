@@ -377,12 +377,14 @@ def test_backward_side_by_side_equals_one_after_the_other(cuda_device, B, C, pai
     assert _lib_timeout_clear()
 
 
-@pytest.mark.parametrize("name,B,C", [("k3c_follow", 512, 20000), ("k3c_follow", 384, 6000), ("dw_n_fastest", 640, 9000)])
+@pytest.mark.parametrize("name,B,C", [("k3c_follow", 512, 20000), ("k3c_follow", 384, 6000), ("dw_n_fastest", 640, 9000),
+                                      ("stream_k", 2560, 6000), ("stream_k", 4096, 8192), ("stream_k", 1100, 3000)])
 def test_work_order_tunables_change_no_result(cuda_device, name, B, C):
     """Two orderings that exist for the L2's sake: the dx GEMM beside the dW GEMM walks the class rows in the dW kernel's
     order (k3c_follow: another grouping of the fp32 sum over classes -- last-bit differences in dx, dW untouched), and the
     streamed dW GEMM at batch > 512 runs the two feature tiles of a class block side by side (dw_n_fastest: same tiles,
-    another order -- bit-identical)."""
+    another order -- bit-identical).  stream_k: the dx GEMM cuts its (tile, k) space into one equal range per cluster where
+    split-K would leave clusters idle (20 or 32 output tiles on 74 clusters) -- another grouping of the sum again."""
     import b200face
     from b200face import _lib
     lib = _lib.load_library()
