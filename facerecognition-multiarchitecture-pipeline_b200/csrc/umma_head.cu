@@ -277,6 +277,7 @@ static std::atomic<int> g_k3a_ablate{0};            // probe: 2 = no G^T stores 
 static std::atomic<int> g_k3b_ablate{0};            // probe: 1 = no w_hat loads, 2 = no dW stores (WRONG results)
 #endif
 static std::atomic<int> g_k3b_reverse{1};
+static std::atomic<int> g_k3a_tma_store{0};         // tunable "k3a_tma_store": 1 = G^T through shared-memory staging + TMA tensor stores (XwBwdGTS)
 static std::atomic<int> g_k3a_reverse{0};           // tunable "k3a_reverse": K3a walks each chunk last tile first (K2 read those w_hat rows last)
 static std::atomic<int> g_k3c_follow{0};            // tunable "k3c_follow": 1 = the dx part beside the dW part reads the class rows in the dW kernel's order (measured at cfg3: step 263.6 -> 262.3 us, e2e 1.763 -> 1.743 M samples/s: within noise, off)
 static std::atomic<int> g_dw_n_fastest{1};          // tunable "dw_n_fastest": streamed dW GEMM (batch > 512) runs the n tiles of a class block side by side
@@ -773,7 +774,12 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
     const bool k3a_rev = g_k3a_reverse.load(std::memory_order_relaxed) != 0;
     { B200F_NVTX("K3a logit gradient (recompute + G^T)");
     stage_event(EV_K3A, false, st);
-    if (k3a_mode == 4) {
+    if (g_k3a_tma_store.load(std::memory_order_relaxed) != 0 && k3a_mode == 1 && (pl.ldg % 8) == 0) {
+      XwBwdGTS::Params es{}; fill(es);
+      rc = make_tmap(&es.tm_gt, G, B, cnt, pl.ldg, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B); if (rc) return rc;
+      rc = (qg.pair == 2) ? launch_xw<2, XW_SWAP, XwBwdGTS>(tx_k, tw_k, qg, B, cnt, D, es, st, "umma K3a logit-grad (cta pair, TMA stores)", FMT_F16, k3a_rev, wc, wrb, true, k3a_whint)
+                          : launch_xw<1, XW_SWAP, XwBwdGTS>(tx_k, tw_k, qg, B, cnt, D, es, st, "umma K3a logit-grad (TMA stores)", FMT_F16, k3a_rev, wc, wrb, true, k3a_whint);
+    } else if (k3a_mode == 4) {
       XwBwdGT4::Params e4{}; fill(e4);
       rc = (qg.pair == 2) ? launch_xw<2, XW_SWAP, XwBwdGT4>(tx_k, tw_k, qg, B, cnt, D, e4, st, "umma K3a logit-grad (cta pair, 16 warps per tile)", FMT_F16, k3a_rev, wc, wrb, true, k3a_whint)
                           : launch_xw<1, XW_SWAP, XwBwdGT4>(tx_k, tw_k, qg, B, cnt, D, e4, st, "umma K3a logit-grad (16 warps per tile)", FMT_F16, k3a_rev, wc, wrb, true, k3a_whint);
@@ -1231,6 +1237,7 @@ int b200f_set_tunable(const char* name, int value) {
 #endif
   if (n == "k3b_tma_store") { if (value != 0 && value != 1) return g_k3b_tma_store.load(); return g_k3b_tma_store.exchange(value); }
   if (n == "stream_k") { if (value != 0 && value != 1) return g_stream_k.load(); return g_stream_k.exchange(value); }
+  if (n == "k3a_tma_store") { if (value != 0 && value != 1) return g_k3a_tma_store.load(); return g_k3a_tma_store.exchange(value); }
   if (n == "k3a_reverse") { if (value != 0 && value != 1) return g_k3a_reverse.load(); return g_k3a_reverse.exchange(value); }
   if (n == "k3c_follow") { if (value != 0 && value != 1) return g_k3c_follow.load(); return g_k3c_follow.exchange(value); }
   if (n == "dw_n_fastest") { if (value != 0 && value != 1) return g_dw_n_fastest.load(); return g_dw_n_fastest.exchange(value); }

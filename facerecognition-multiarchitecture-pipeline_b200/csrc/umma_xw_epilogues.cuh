@@ -264,8 +264,14 @@ __device__ __noinline__ void head_phi_dphi(HeadMath hm, float c, float* phi, flo
 #define B200F_PROBE_ON(ep, bit) false
 #endif
 
-template <int EG, int SC, int SPLIT = 2>
+// TMAST: the slice's packed words leave through a 2 KB staging buffer per warp (one ring stage given up: 4 instead of 5) and
+// ONE cp.async.bulk.tensor store per slice instead of two 32-byte stores per lane.  Why: a 32-byte-per-lane store touches 32
+// lines; ncu had 14 % of the kernel's stall samples on the instructions that reuse such a store's registers -- it sits in the
+// load/store queue for ~500 cycles before it has read them.  st.shared.v4 into the 64-byte swizzle is 4 wavefronts.
+template <int EG, int SC, int SPLIT = 2, bool TMAST = false>
 struct XwBwdGTT {
+  static_assert(!TMAST || (EG == 1 && SC == 32 && SPLIT == 2), "the TMA-store form: one group of 8 warps, 32-column slices");
+  static constexpr int kRingStages = TMAST ? XW_STAGES - 1 : XW_STAGES;
   static constexpr int kEpiGroups = EG;
   static constexpr int kSliceCols = SC;
   static constexpr int kEpiSplit = SPLIT;     // 4: sixteen warps of ONE group on every tile, a quarter of its columns each
@@ -275,6 +281,7 @@ struct XwBwdGTT {
     int64_t class_offset;       // global id of this launch's class 0
     HeadMath hm;
     float ls_eps, inv_Ctot, inv_scale;
+    alignas(64) CUtensorMap tm_gt;   // TMAST: G^T [classes of this launch, B] fp16, box 32 batch rows x 32 classes, 64-byte swizzle
     uint16_t* GT; int64_t ldgt; // G^T[class of this launch, batch row]
     float* r_part; int64_t ldr; // [SPLIT * m_groups, ldr]: one partial per (row group, column half / quarter)
     int gt_hint;                // L2 policy of the G^T stores (K3b and K3c read them next): 0 none, 2 evict_last
@@ -321,6 +328,17 @@ struct XwBwdGTT {
   static __device__ __forceinline__ void tile_begin(State& st, const Params&, const XwParams& p, const XwItem& it) {
     st.cls = (int)it.row; st.row_ok = it.row < p.C; st.r = 0.f;
   }
+  // TMAST: 16 columns (two 16-byte chunks) of this lane's 64-byte row of the warp's staging box, in the 64-byte swizzle
+  // (chunk c of row r sits at chunk c ^ ((r >> 1) & 3); the box starts on a 512-byte boundary)
+  static __device__ __forceinline__ void stage_block(const XwItem& it, int h, const uint32_t (&w)[8]) {
+    const uint32_t row_s = smem_u32(it.aux) + (uint32_t)it.lane * 64u;
+    const uint32_t sw = ((uint32_t)it.lane >> 1) & 3u;
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                   ::"r"(row_s + ((((uint32_t)(h >> 3) + c) ^ sw) << 4)), "r"(w[4 * c]), "r"(w[4 * c + 1]), "r"(w[4 * c + 2]), "r"(w[4 * c + 3])
+                   : "memory");
+  }
 
   static __device__ __forceinline__ void slice(State& st, const Params& ep, const XwParams& p, const XwItem& it,
                                                float (&v)[SC], int col0, float* scratch) {
@@ -330,6 +348,10 @@ struct XwBwdGTT {
     // in front of the stores all SC gradients were live next to the SC accumulators, ptxas gave the NEXT slice's
     // tcgen05.ld the same registers and could issue it only at the end of this slice -- its latency sat at the top of every
     // slice (ncu: 13 % of the slice's stall samples on the first instruction behind tcgen05.wait::ld).
+    if constexpr (TMAST) {                                    // the previous slice's tensor store has READ the staging buffer
+      if (it.lane == 0) tma_store_wait_read();
+      __syncwarp();
+    }
     const float a = st.a, gs = st.gs, gq = st.gq;
     const uint32_t tb_s = st.tab_s + (uint32_t)col0 * 4u;
     const int64_t b0 = (int64_t)it.group * p_tn(p) + col0;
@@ -360,6 +382,9 @@ struct XwBwdGTT {
         w1[j / 2] = pack_f16(g4[0], g4[1]);
         w1[j / 2 + 1] = pack_f16(g4[2], g4[3]);
       }
+      if constexpr (TMAST) {
+        stage_block(it, h, w1);
+      } else
       if (cols_full && st.row_ok && !(B200F_PROBE_ON(ep, 2) && w1[0] != 0x12345678u)) {
         if (ep.gt_hint) st_global_256_hint(gdst + h, w1[0], w1[1], w1[2], w1[3], w1[4], w1[5], w1[6], w1[7], st.pol);
         else st_global_256(gdst + h, w1[0], w1[1], w1[2], w1[3], w1[4], w1[5], w1[6], w1[7]);
@@ -410,6 +435,12 @@ struct XwBwdGTT {
           const float t = g[j] * vj;
           racc += (g[j] != 0.f && t == t) ? t : 0.f;
         }
+        if constexpr (TMAST) {                                // over the fast path's words in the staging buffer
+          uint32_t w1[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) w1[j] = pack_f16(g[2 * j], g[2 * j + 1]);
+          stage_block(it, h, w1);
+        } else
         if (st.row_ok && !(B200F_PROBE_ON(ep, 2) && g[0] != 12345.678f)) {
           if (cols_full) {
             uint32_t w1[8];
@@ -425,6 +456,19 @@ struct XwBwdGTT {
       }
     }
     st.r += racc;
+    if constexpr (TMAST) {
+      // one tensor store per slice: [32 batch rows x 32 classes] from the staging buffer; the map clips columns beyond the
+      // batch and class rows beyond this launch
+      fence_proxy_async();
+      __syncwarp();
+      const int row_w = st.cls - it.lane;                     // first class row of this warp in the tile
+      if (it.lane == 0 && row_w < p.C && b0 < p.B && !B200F_PROBE_ON(ep, 2)) {
+        if (ep.gt_hint) tma_store_2d_hint(&ep.tm_gt, it.aux, (int)b0, row_w, st.pol);
+        else tma_store_2d(&ep.tm_gt, it.aux, (int)b0, row_w);
+      }
+      // a patch that is applied right away (not queued) writes behind this store: it has to be in memory first
+      if (hits != 0u && !(ep.defer_targets && st.nq < kQueue)) { if (it.lane == 0) tma_store_wait_all(); __syncwarp(); }
+    }
     while (hits) {                                            // warp-uniform, usually zero trips
       const int src = __ffs(hits) - 1;
       hits &= hits - 1;
@@ -474,6 +518,10 @@ struct XwBwdGTT {
   // class: a fixed order keeps the sum reproducible).  All tile_end stores of the item precede this in program order and
   // __syncwarp orders them for the other lanes.
   static __device__ __forceinline__ void item_end_swap(State& st, const Params& ep, const XwParams& p, const XwItem& it, int) {
+    if constexpr (TMAST) {                                    // this warp's tensor stores are in memory: the patches write behind them
+      if (it.lane == 0) tma_store_wait_all();
+      __syncwarp();
+    }
     const int n = st.nq;
     if (n == 0) return;
     __syncwarp();
@@ -515,6 +563,7 @@ struct XwBwdGTT {
 using XwBwdGT = XwBwdGTT<1, 32>;
 using XwBwdGT2 = XwBwdGTT<2, 16>;
 using XwBwdGT4 = XwBwdGTT<1, 16, 4>;   // one group of sixteen warps, column quarters
+using XwBwdGTS = XwBwdGTT<1, 32, 2, true>;   // G^T through staging + TMA tensor stores
 
 // -------------------------------------------------------------------------------------------------
 // ---- K3b, class-major: dW[c, d] = coef.x * (acc[c, d] - w_hat16[c, d] * coef.y) --------------------------------
