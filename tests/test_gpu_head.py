@@ -209,6 +209,42 @@ def test_arcfacenet_hook_arms_after_first_forward(cuda_device):
     with pytest.raises(ValueError, match="Labels must be provided during training"):
         net(img)
 
+def test_arcfacenet_reference_loop_runs_the_fused_path(cuda_device):
+    """The reference's training step on the whole drop-in model (src/training.py:508-521): ``output = model(data,
+    target)`` is a LazyArcLogits, ``criterion(output, target)`` the fused loss with the hook armed as in forward_loss --
+    same loss, same gradients for every trainable parameter as ``model.forward_loss`` (dropout off: deterministic)."""
+    import b200face
+    torch.manual_seed(3)
+    img = torch.randn(8, 3, 64, 64, device=cuda_device)
+    y = torch.tensor([0, 3, 5, 11, 2, 2, 7, 9], device=cuda_device)
+    criterion = torch.nn.CrossEntropyLoss(label_smoothing=0.05)
+
+    def run(reference_loop):
+        torch.manual_seed(4)
+        net = b200face.ArcFaceNet(num_classes=12).to(cuda_device).train()
+        net.dropout.p = 0.0
+        out = []
+        for _ in range(2):                                    # the hook is armed from the second forward on
+            net.zero_grad()
+            if reference_loop:
+                output = net(img, y)
+                assert isinstance(output, b200face.LazyArcLogits)
+                loss = criterion(output, y)
+                assert output._arc["real"] is None
+            else:
+                loss = net.forward_loss(img, y, 0.05)
+            loss.backward()
+            out.append((float(loss), net.arcface.weight.grad.clone(), net.embedding.weight.grad.clone(), net.last_grad_norm))
+        return out
+    a, b = run(True), run(False)
+    for (la, dwa, dea, na), (lb, dwb, deb, nb) in zip(a, b):
+        assert la == pytest.approx(lb, rel=1e-6)
+        assert rel_err(dwa.cpu().numpy(), dwb.cpu().numpy()) < 1e-5
+        assert rel_err(dea.cpu().numpy(), deb.cpu().numpy()) < 1e-5
+        assert na == pytest.approx(nb, rel=1e-5)
+    assert a[1][3] > 0.5                                      # the hook acted on step 2
+
+
 def test_arcfacenet_single_normalise_equals_double(cuda_device):
     """ArcFaceNet hands the head the row BEFORE F.normalize (the head's K1 normalises it): same loss and the same
     gradients as the reference's normalise-then-normalise-again chain (src/face_models.py:525 + :351)."""
