@@ -71,6 +71,9 @@ struct GemmParams {
   // sums stream_k_pieces(tile) slots.  Why: with 32 output tiles and 74 clusters (dx at batch 4096) split-K by 2 leaves
   // 10 clusters idle and split-K by 3 runs two waves; 0 = off.
   int stream_k, k_units;
+  // A operand in [32 classes x 64 batch rows] blocks of 4 KB (a_blocked = 1; G^T at batch > 512, umma_head.cu "gt_blocked"):
+  // tm_a is a rank-4 map {batch row within block, class within block, batch block, class block}
+  int a_blocked;
   int early;                // 1: neither operand nor the output is touched by the predecessor grid (K3c behind K3b: both only READ
                             // G^T): nobody waits for it up front -- CTAs start on SMs the predecessor has left -- and the epilogue
                             // warps wait at their END, so that this grid still completes after its predecessor (stream order holds
@@ -225,6 +228,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
             uint8_t* sb = sa + A_TILE_BYTES;
             if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], PAIR * STG_BYTES);
             else mbar_arrive_cluster(&full_bar[stage], 0);
+            if (p.a_blocked) {                                  // class rows and batch rows are multiples of 64 here
+              if (!A_MN) {                                      // rows = classes (t.m0), k = batch
+                xw_tma_load4<PAIR>(sa, &tm_a, &full_bar[stage], 0, 0, k0 >> 6, t.m0 >> 5);
+              } else {                                          // rows = batch (t.m0), k = classes
+#pragma unroll
+                for (int j = 0; j < BLOCK_M / 64; ++j)
+                  xw_tma_load4<PAIR>(sa + j * MN_BLOCK_BYTES, &tm_a, &full_bar[stage], 0, 0, (t.m0 + 64 * j) >> 6, k0 >> 5);
+              }
+            } else
             if (!A_MN) {
               xw_tma_load<PAIR>(sa, &tm_a, &full_bar[stage], k0, t.m0);
             } else {

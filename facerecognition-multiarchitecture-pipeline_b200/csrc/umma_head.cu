@@ -57,6 +57,26 @@ static int make_tmap(CUtensorMap* m, const void* base, int64_t inner, int64_t ou
   if (r != CUDA_SUCCESS) return fail(B200F_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   return B200F_OK;
 }
+// rank-4 map of G^T stored in [32 classes x 64 batch rows] blocks of 4 KB: element (c, b) at
+// base[(((c >> 5) * nb + (b >> 6)) << 11) + ((c & 31) << 6) + (b & 63)], nb = batch blocks per class block.  Dimensions
+// {b & 63, c & 31, b >> 6, c >> 5}; a box {64, 32, 1, cb} lands in shared memory as [32 cb classes][64 batch rows = 128 bytes]:
+// K-major rows for the dW GEMM, and the same bytes are the MN-major [class][64 batch rows] blocks the dx GEMM wants.
+// 128-byte swizzle over full 128-byte inner rows (with 64-byte inner rows -- 2 KB blocks -- the boxes did not arrive in the
+// layout the MMA descriptors describe).
+static int make_tmap_gt_blocked(CUtensorMap* m, const void* base, int64_t classes, int64_t nb, int box_class_blocks) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(B200F_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  if (reinterpret_cast<uintptr_t>(base) & 15) return fail(B200F_ERR_ARG, "TMA operand must be 16B aligned");
+  cuuint64_t gdim[4] = {64, 32, (cuuint64_t)nb, (cuuint64_t)ceil_div(classes, (int64_t)32)};
+  cuuint64_t gstr[3] = {128, 4096, (cuuint64_t)nb * 4096};  // bytes: next class of the block, next batch block, next class block
+  cuuint32_t box[4] = {64, 32, 1, (cuuint32_t)box_class_blocks};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<void*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(B200F_ERR_CUDA, "cuTensorMapEncodeTiled (rank 4) failed (%d)", (int)r);
+  return B200F_OK;
+}
 // fp32 matrix [outer, inner] (row stride ld floats) for TMA tensor STORES of [box_outer x box_inner] blocks
 static int make_tmap_f32(CUtensorMap* m, const void* base, int64_t inner, int64_t outer, int64_t ld, int box_inner, int box_outer,
                          CUtensorMapSwizzle swz) {
@@ -277,6 +297,12 @@ static std::atomic<int> g_k3a_ablate{0};            // probe: 2 = no G^T stores 
 static std::atomic<int> g_k3b_ablate{0};            // probe: 1 = no w_hat loads, 2 = no dW stores (WRONG results)
 #endif
 static std::atomic<int> g_k3b_reverse{1};
+// tunable "gt_blocked": G^T of a batch > 512 (a multiple of 256 rows, CTA pairs) is stored in [32 classes x 64 batch rows]
+// blocks of 4 KB, so that what a K3a warp writes in two consecutive slices is 4 KB contiguous (128 bytes per lane) instead of
+// 32 row pieces 8 KB apart.  Probe builds that only moved K3a's stores (tools/build_probe.sh -DB200F_GT_BLOCKED_PROBE): 412
+// instead of 465 us at 4096 x 125 k with 2 KB blocks; per 256-row groups ([group][class][256]: pieces 512 bytes apart) it
+// stayed at 458; at batch <= 512 (row pitch 1 KB) the probe gains 1.4 us of 60.6, so that path keeps the plain layout.
+static std::atomic<int> g_gt_blocked{1};
 static std::atomic<int> g_k3a_tma_store{0};         // tunable "k3a_tma_store": 1 = G^T through shared-memory staging + TMA tensor stores (XwBwdGTS)
 static std::atomic<int> g_k3a_reverse{0};           // tunable "k3a_reverse": K3a walks each chunk last tile first (K2 read those w_hat rows last)
 static std::atomic<int> g_k3c_follow{0};            // tunable "k3c_follow": 1 = the dx part beside the dW part reads the class rows in the dW kernel's order (measured at cfg3: step 263.6 -> 262.3 us, e2e 1.763 -> 1.743 M samples/s: within noise, off)
@@ -750,6 +776,13 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
     const uint16_t* wc = static_cast<const uint16_t*>(wh) + c0 * D;
     if (phase == 2 && !last_chunk) continue;                // everything but the last chunk's dW ran in phase 1
     const XwPlan qg = xw_plan(B, cnt, pl.fwd.pair);
+    // G^T in 2 KB blocks (see g_gt_blocked): the streamed path only, whole 256-row groups only; read once per backward call --
+    // phase 2 (the held-back dW GEMM) must read the layout phase 1 wrote
+    static thread_local int t_blocked = 0;
+    if (phase == 0 || phase == 1 || phase == HEAD_BWD_PART_K3A)
+      t_blocked = g_gt_blocked.load(std::memory_order_relaxed) != 0 ? 1 : 0;
+    const bool blocked = t_blocked != 0 && !pl.fused_dw && pl.fwd.pair == 2 && B % (2 * XW_M) == 0;
+    const int64_t NB = B / 64;                                  // batch blocks per class block
     float* r_part = reinterpret_cast<float*>(ws + pl.off_rpart);
     const int hints = g_l2_hints.load(std::memory_order_relaxed);
     // --- K3a: logit gradient of the chunk, class-major: G^T[c, b] (x_hat resident, w_hat rows [c0, c0 + cnt) streamed
@@ -762,7 +795,8 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
       e.label = label; e.lse = lse; e.grad4 = grad4; e.class_offset = class_offset + c0;
       e.hm = HeadMath{cfg->m_eff, cfg->s_eff, cfg->easy_margin};
       e.ls_eps = cfg->label_smoothing; e.inv_Ctot = 1.0f / (float)cfg->num_classes_total; e.inv_scale = 1.0f / (S * S);
-      e.GT = G; e.ldgt = pl.ldg; e.r_part = r_part; e.ldr = pl.Cc;
+      e.GT = G; e.ldgt = pl.ldg; e.gstride = (int64_t)XW_M * qg.pair; e.blocked_nb = blocked ? (int)NB : 0;
+      e.r_part = r_part; e.ldr = pl.Cc;
       e.gt_hint = (hints_k3a & 2) ? 2 : 0;
       e.whole_slice_targets = g_target_patch.load(std::memory_order_relaxed) ? 0 : 1;
       e.defer_targets = g_target_patch.load(std::memory_order_relaxed) == 2 ? 1 : 0;
@@ -774,7 +808,7 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
     const bool k3a_rev = g_k3a_reverse.load(std::memory_order_relaxed) != 0;
     { B200F_NVTX("K3a logit gradient (recompute + G^T)");
     stage_event(EV_K3A, false, st);
-    if (g_k3a_tma_store.load(std::memory_order_relaxed) != 0 && k3a_mode == 1 && (pl.ldg % 8) == 0) {
+    if (g_k3a_tma_store.load(std::memory_order_relaxed) != 0 && k3a_mode == 1 && (pl.ldg % 8) == 0 && !blocked) {
       XwBwdGTS::Params es{}; fill(es);
       rc = make_tmap(&es.tm_gt, G, B, cnt, pl.ldg, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B); if (rc) return rc;
       rc = (qg.pair == 2) ? launch_xw<2, XW_SWAP, XwBwdGTS>(tx_k, tw_k, qg, B, cnt, D, es, st, "umma K3a logit-grad (cta pair, TMA stores)", FMT_F16, k3a_rev, wc, wrb, true, k3a_whint)
@@ -855,8 +889,11 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
       // row and finishes the normalise-backward in place (EpiDwNorm) -- no separate pass over dW.
       // (An earlier TRANSPOSED fused epilogue on this core measured 2.3x slower at B = 4096: per-element global loads.)
       CUtensorMap tg_km;
-      rc = tmap_kmajor(&tg_km, G, cnt, B, pl.ldg, BLOCK_M); if (rc) return rc;
+      if (blocked) rc = make_tmap_gt_blocked(&tg_km, G, cnt, NB, BLOCK_M / 32);
+      else rc = tmap_kmajor(&tg_km, G, cnt, B, pl.ldg, BLOCK_M);
+      if (rc) return rc;
       GemmParams pw = gemm_params((int)cnt, D, (int)B, 1, false, true, FMT_F16, FMT_F16, gpair);
+      pw.a_blocked = blocked ? 1 : 0;
       pw.n_fastest = g_dw_n_fastest.load(std::memory_order_relaxed) ? 1 : 0;
       EpiDwNorm::Params ew{dw, (int64_t)D, c0, coef, static_cast<const __half*>(wh), sq_part};
       n_sq_used = (int)(ceil_div(cnt, (int64_t)128) * pw.n_tiles * 4);
@@ -874,7 +911,8 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
     // --- K3c: dx_hat partials = G[:, k-range] w_hat[c0 + k-range, :]   (A = G read MN-major from G^T)
     auto run_k3c = [&]() -> int {
     CUtensorMap tg_mn, tw_mn;
-    int rc = tmap_mnmajor(&tg_mn, G, B, cnt, pl.ldg); if (rc) return rc;
+    int rc = blocked ? make_tmap_gt_blocked(&tg_mn, G, cnt, NB, BLOCK_K / 32) : tmap_mnmajor(&tg_mn, G, B, cnt, pl.ldg);
+    if (rc) return rc;
     rc = tmap_mnmajor(&tw_mn, wc, D, cnt, D); if (rc) return rc;
     // the dx part on a bounded number of clusters: as many K splits as those clusters carry output tiles
     const int k3c_limit = (phase == HEAD_BWD_PART_K3C) ? cluster_limit : 0;
@@ -889,6 +927,7 @@ int head_bwd(const void* xh, const void* wh, const float* inv_nw, const int64_t*
     // K3c reads G^T (K3a) and w_hat, writes dxpart: nothing of K3b's -- behind K3b it need not wait for it; directly behind
     // K3a (phases 1 / 2) it does
     px.early = (phase == 0) ? g_early.load(std::memory_order_relaxed) : 0;
+    px.a_blocked = blocked ? 1 : 0;
     if (k3c_limit > 0 && gpair == 2 && pl.fused_dw && g_k3c_follow.load(std::memory_order_relaxed) != 0) {
       // beside the dW part, which runs on the rest of the chip: walk the class rows in ITS order (GemmParams::follow_*)
       const int rest = xw_max_clusters(2) - k3c_limit;
@@ -1237,6 +1276,7 @@ int b200f_set_tunable(const char* name, int value) {
 #endif
   if (n == "k3b_tma_store") { if (value != 0 && value != 1) return g_k3b_tma_store.load(); return g_k3b_tma_store.exchange(value); }
   if (n == "stream_k") { if (value != 0 && value != 1) return g_stream_k.load(); return g_stream_k.exchange(value); }
+  if (n == "gt_blocked") { if (value != 0 && value != 1) return g_gt_blocked.load(); return g_gt_blocked.exchange(value); }
   if (n == "k3a_tma_store") { if (value != 0 && value != 1) return g_k3a_tma_store.load(); return g_k3a_tma_store.exchange(value); }
   if (n == "k3a_reverse") { if (value != 0 && value != 1) return g_k3a_reverse.load(); return g_k3a_reverse.exchange(value); }
   if (n == "k3c_follow") { if (value != 0 && value != 1) return g_k3c_follow.load(); return g_k3c_follow.exchange(value); }

@@ -282,7 +282,14 @@ struct XwBwdGTT {
     HeadMath hm;
     float ls_eps, inv_Ctot, inv_scale;
     alignas(64) CUtensorMap tm_gt;   // TMAST: G^T [classes of this launch, B] fp16, box 32 batch rows x 32 classes, 64-byte swizzle
-    uint16_t* GT; int64_t ldgt; // G^T[class of this launch, batch row]
+    uint16_t* GT; int64_t ldgt; // G^T[class of this launch, batch row]: element (c, b) at GT[(b / tn) * gstride + c * ldgt + b % tn] with tn
+    int blocked_nb;             // > 0: G^T in [32 classes x 64 batch rows] blocks of 4 KB, blocked_nb = batch blocks per class block:
+                                // element (c, b) at GT[(((c >> 5) * blocked_nb + (b >> 6)) << 11) + ((c & 31) << 6) + (b & 63)] -- what a
+                                // warp writes in two consecutive slices is 4 KB contiguous, 128 bytes per lane.  Class rows beyond this
+                                // launch inside its last block are written as ZEROS (the dx GEMM reads whole blocks).  0: the
+                                // (gstride, ldgt) form below
+    int64_t gstride;            // the rows of a resident group.  Plain row-major [c, b]: gstride = tn, ldgt = row pitch.  Per-group
+                                // storage [group][c][tn] (batch > 512): gstride = classes * tn, ldgt = tn
     float* r_part; int64_t ldr; // [SPLIT * m_groups, ldr]: one partial per (row group, column half / quarter)
     int gt_hint;                // L2 policy of the G^T stores (K3b and K3c read them next): 0 none, 2 evict_last
     int whole_slice_targets;    // tunable "target_patch" = 0: a slice with a target element goes the element-wise way (round 1)
@@ -355,8 +362,16 @@ struct XwBwdGTT {
     const float a = st.a, gs = st.gs, gq = st.gq;
     const uint32_t tb_s = st.tab_s + (uint32_t)col0 * 4u;
     const int64_t b0 = (int64_t)it.group * p_tn(p) + col0;
-    uint16_t* const gdst = ep.GT + (int64_t)st.cls * ep.ldgt + b0;
+#ifdef B200F_GT_BLOCKED_PROBE   // tools/ probe builds only (WRONG results for the consumers): a warp's slice = 2 KB contiguous
+    uint16_t* const gdst = ep.GT + ((((int64_t)(st.cls >> 5) * (ep.ldgt >> 5)) + (b0 >> 5)) << 10) + (st.cls & 31) * 32;
+#else
+    uint16_t* const gdst = ep.blocked_nb > 0
+        ? ep.GT + ((((int64_t)(st.cls >> 5) * ep.blocked_nb) + (b0 >> 6)) << 11) + ((st.cls & 31) << 6) + (b0 & 63)
+        : ep.GT + (int64_t)it.group * ep.gstride + (int64_t)st.cls * ep.ldgt + col0;
+#endif
     const bool cols_full = b0 + SC <= p.B;                     // warp-uniform
+    // blocked layout: a lane whose class lies beyond the launch but inside its last 32-class block stores zeros
+    const bool zero_row = ep.blocked_nb > 0 && !st.row_ok && (st.cls - it.lane) < p.C;
     float am4[4] = {0.f, 0.f, 0.f, 0.f};
     float r4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -382,10 +397,14 @@ struct XwBwdGTT {
         w1[j / 2] = pack_f16(g4[0], g4[1]);
         w1[j / 2 + 1] = pack_f16(g4[2], g4[3]);
       }
+      if (zero_row) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w1[j] = 0u;
+      }
       if constexpr (TMAST) {
         stage_block(it, h, w1);
       } else
-      if (cols_full && st.row_ok && !(B200F_PROBE_ON(ep, 2) && w1[0] != 0x12345678u)) {
+      if (cols_full && (st.row_ok || zero_row) && !(B200F_PROBE_ON(ep, 2) && w1[0] != 0x12345678u)) {
         if (ep.gt_hint) st_global_256_hint(gdst + h, w1[0], w1[1], w1[2], w1[3], w1[4], w1[5], w1[6], w1[7], st.pol);
         else st_global_256(gdst + h, w1[0], w1[1], w1[2], w1[3], w1[4], w1[5], w1[6], w1[7]);
       }
@@ -501,7 +520,7 @@ struct XwBwdGTT {
         st.r = fmaf(gn - g_old, vt, st.r);
         const int64_t bt = (int64_t)it.group * p_tn(p) + col0 + src;
         if (bt < p.B && !(B200F_PROBE_ON(ep, 2) && gn != 12345.678f))
-          ep.GT[(int64_t)st.cls * ep.ldgt + bt] = (uint16_t)(pack_f16(gn, 0.f) & 0xffff);
+          gdst[src] = (uint16_t)(pack_f16(gn, 0.f) & 0xffff);
       }
     }
   }
@@ -543,7 +562,9 @@ struct XwBwdGTT {
       const float gn = fminf(fmaxf(gs * (pr - q) * f, -65504.f), 65504.f);
       delta = (gn - g_old) * vt * ep.inv_scale;
       if (bt < p.B && !(B200F_PROBE_ON(ep, 2) && gn != 12345.678f))
-        ep.GT[(int64_t)cls * ep.ldgt + bt] = (uint16_t)(pack_f16(gn, 0.f) & 0xffff);
+        ep.GT[ep.blocked_nb > 0 ? ((((int64_t)(cls >> 5) * ep.blocked_nb) + (bt >> 6)) << 11) + ((cls & 31) << 6) + (bt & 63)
+                                : (int64_t)(bt / p_tn(p)) * ep.gstride + (int64_t)cls * ep.ldgt + bt % p_tn(p)] =
+            (uint16_t)(pack_f16(gn, 0.f) & 0xffff);
     }
     if (ep.r_part != nullptr) {
       float* const rrow = ep.r_part + (int64_t)(it.group * SPLIT + it.half) * ep.ldr;
