@@ -380,6 +380,8 @@ int b200f_umma_xw_probe(const void* x, const void* w, float* rowsum, int B, int 
  * "dw_n_fastest" (0 | 1, default 1: the streamed dW GEMM at batch > 512 runs the feature tiles of a class block side by side, so
  * G^T comes from HBM once), "k3c_follow" (0 | 1, default 0: the dx part beside the dW part walks the class rows in the dW kernel's
  * order; measured within noise), "k3a_reverse" (0 | 1, default 0: K3a walks its chunks last tile first; within noise),
+ * "gt_blocked" (0 | 1, default 1: at batch > 512 the logit gradient is kept in [32 classes x 64 batch rows] blocks and read back
+ * through rank-4 tensor maps; bit-identical),
  * "k3a_tma_store" (0 | 1, default 0: G^T through shared-memory staging and TMA tensor stores; bit-identical, measured slower),
  * "stream_k" (0 | 1, default 0: stream-K of the dx GEMM where split-K leaves clusters idle; measured slower, see umma_head.cu).
  * Returns the previous value, -1 for an unknown name.  Every setting computes the same results ("g_chunk_mb" changes the
